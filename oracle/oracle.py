@@ -1,0 +1,324 @@
+"""CPU oracle for the FinaleToolkit hot path (TEST INFRASTRUCTURE).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this module.  The product package
+``finaletoolkit_b200`` never does; its compute path is CUDA only.
+
+Thin numpy/ctypes front-end over ``oracle/ftk_oracle.c`` (the literal C
+restatement of the reference's loops) plus small pure-Python restatements of
+the reference's host-side arithmetic (statistics in dict order, binning, MDS,
+site/window construction).  Every function cites the reference file:line it
+follows (relative to /root/reference/src/finaletoolkit).
+
+Parity pin: ``tests/test_oracle_golden.py`` checks every function here against
+``tests/golden/*`` - outputs of the UNMODIFIED reference produced in the build
+container by ``oracle/make_golden.py``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libftk_oracle.so")
+_SRC = os.path.join(_HERE, "ftk_oracle.c")
+NONE = -(2 ** 63)  # ORC_NONE: Python None (unbounded)
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement with gcc (seconds)."""
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        subprocess.check_call(
+            ["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", _SO, _SRC, "-lm"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        i32p, u8p, i64p, dp = POINTER(c_int32), POINTER(c_uint8), POINTER(c_int64), POINTER(c_double)
+        L = _lib
+        L.orc_wps_interval.restype = c_int64
+        L.orc_wps_interval.argtypes = [i32p, i32p, u8p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                       c_int64, c_int64, c_int64, c_int64, i64p]
+        L.orc_wps_intervals.restype = None
+        L.orc_wps_intervals.argtypes = [i32p, i32p, u8p, c_int64, c_int64, i64p, i64p, i64p, c_int64, c_int64,
+                                        c_int64, c_int64, c_int64, c_int64, i64p, c_int]
+        L.orc_single_coverage.restype = c_int64
+        L.orc_single_coverage.argtypes = [i32p, i32p, u8p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int64]
+        L.orc_interval_coverage.restype = None
+        L.orc_interval_coverage.argtypes = [i32p, i32p, u8p, c_int64, c_int64, i64p, i64p, c_int64, c_int64, c_int64, c_int, c_int64, i64p, c_int]
+        L.orc_length_dist.restype = c_int64
+        L.orc_length_dist.argtypes = [i32p, i32p, u8p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int64, i64p, i64p, c_int64]
+        L.orc_frag_lengths.restype = c_int64
+        L.orc_frag_lengths.argtypes = [i32p, i32p, u8p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int64, i32p, c_int64]
+        L.orc_region_end_motifs.restype = c_int
+        L.orc_region_end_motifs.argtypes = [i32p, i32p, u8p, u8p, c_int64, c_int64, c_int64, c_int64, c_char_p, c_int64, c_int, c_int, c_int64, i64p]
+        L.orc_local_filter.restype = c_int64
+        L.orc_local_filter.argtypes = [dp, c_int64, c_int64, c_int, dp]
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(POINTER(t))
+
+
+def _n(v):
+    return NONE if v is None else int(v)
+
+
+class Frags:
+    """Start-sorted fragments of one contig as C-contiguous columns."""
+
+    def __init__(self, start, stop, mapq, strand=None):
+        self.start = np.ascontiguousarray(start, dtype=np.int32)
+        self.stop = np.ascontiguousarray(stop, dtype=np.int32)
+        self.mapq = np.ascontiguousarray(mapq, dtype=np.uint8)
+        self.strand = (np.ones_like(self.mapq) if strand is None
+                       else np.ascontiguousarray(strand, dtype=np.uint8))
+        self.n = int(self.start.shape[0])
+        self.max_len = int((self.stop.astype(np.int64) - self.start).max()) if self.n else 0
+        self.max_len = max(self.max_len, 0)
+
+    def _args(self):
+        return (_p(self.start, c_int32), _p(self.stop, c_int32), _p(self.mapq, c_uint8), self.n, self.max_len)
+
+
+# ------------------------------------------------------------------- WPS
+def wps_interval(fr: Frags, start, stop, chrom_size, window_size=120, min_length=120,
+                 max_length=180, quality_threshold=30) -> np.ndarray:
+    """frag/_wps.py:56-205 -> int64[stop-start]."""
+    n = max(int(stop) - int(start), 0)
+    out = np.zeros(n, dtype=np.int64)
+    lib().orc_wps_interval(*fr._args(), int(start), int(stop), int(chrom_size), int(window_size),
+                           int(min_length), int(max_length), int(quality_threshold), _p(out, c_int64))
+    return out
+
+
+def wps_intervals(fr: Frags, ivl_start, ivl_stop, chrom_size, window_size=120, min_length=120,
+                  max_length=180, quality_threshold=30, threads=1) -> tuple[np.ndarray, np.ndarray]:
+    """frag/_multi_wps.py:196-198 : the Pool over intervals. Returns (out int64, offsets)."""
+    s = np.ascontiguousarray(ivl_start, dtype=np.int64)
+    e = np.ascontiguousarray(ivl_stop, dtype=np.int64)
+    ln = np.maximum(e - s, 0)
+    off = np.zeros(len(s) + 1, dtype=np.int64)
+    np.cumsum(ln, out=off[1:])
+    out = np.zeros(int(off[-1]), dtype=np.int64)
+    lib().orc_wps_intervals(*fr._args(), _p(s, c_int64), _p(e, c_int64), _p(off, c_int64), len(s),
+                            int(chrom_size), int(window_size), int(min_length), int(max_length),
+                            int(quality_threshold), _p(out, c_int64), int(threads))
+    return out, off
+
+
+def read_sites(lines, interval_size, chrom_sizes: dict):
+    """frag/_multi_wps.py:240-297 (_read_sites) + :152-160 (header-order sort).
+
+    ``lines`` is an iterable of BED lines; ``chrom_sizes`` an ordered dict.
+    Returns a list of (contig, start, stop).  Raises ValueError like the reference.
+    """
+    left = round(-interval_size / 2)
+    right = round(interval_size / 2)
+    assert right - left == interval_size
+    out = []
+    prev_contig, prev_start, prev_stop = None, 0, 0
+    for line in lines:
+        c = line.split()
+        contig = c[0].strip()
+        if int(c[1]) > int(c[2]):
+            raise ValueError("start after stop")
+        if contig not in chrom_sizes:
+            continue
+        mid = (int(c[1]) + int(c[2])) // 2
+        start = max(0, mid + int(left))
+        stop = min(mid + int(right), chrom_sizes[contig])
+        if contig == prev_contig and start < prev_stop:
+            prev_stop = start
+        if prev_contig is not None and prev_stop > prev_start:
+            out.append((prev_contig, prev_start, prev_stop))
+        prev_contig, prev_start, prev_stop = contig, start, stop
+    if prev_stop > prev_start:
+        out.append((prev_contig, prev_start, prev_stop))
+    order = {c: i for i, c in enumerate(chrom_sizes)}
+    out.sort(key=lambda t: (order.get(t[0], len(order)), t[1]))  # stable, like sorted()
+    return out
+
+
+# ------------------------------------------------------ coverage / lengths
+_POLICY = {"midpoint": 0, "any": 1}
+
+
+def single_coverage(fr: Frags, start=0, stop=None, min_length=None, max_length=None,
+                    intersect_policy="midpoint", quality_threshold=30) -> int:
+    """frag/_coverage.py:117-130."""
+    return int(lib().orc_single_coverage(*fr._args(), _n(start), _n(stop), _n(min_length), _n(max_length),
+                                         _POLICY[intersect_policy], int(quality_threshold)))
+
+
+def interval_coverage(fr: Frags, ivl_start, ivl_stop, min_length=None, max_length=None,
+                      intersect_policy="midpoint", quality_threshold=30, threads=1) -> np.ndarray:
+    """frag/_coverage.py:244-248."""
+    s = np.ascontiguousarray(ivl_start, dtype=np.int64)
+    e = np.ascontiguousarray(ivl_stop, dtype=np.int64)
+    out = np.zeros(len(s), dtype=np.int64)
+    lib().orc_interval_coverage(*fr._args(), _p(s, c_int64), _p(e, c_int64), len(s), _n(min_length), _n(max_length),
+                                _POLICY[intersect_policy], int(quality_threshold), _p(out, c_int64), int(threads))
+    return out
+
+
+def length_dist(fr: Frags, start=None, stop=None, min_length=None, max_length=None,
+                intersect_policy="midpoint", quality_threshold=30) -> dict:
+    """frag/_frag_length.py:147-153 : dict length->count in first-seen order."""
+    cap = 1 << 16
+    while True:
+        k = np.zeros(cap, np.int64)
+        v = np.zeros(cap, np.int64)
+        r = lib().orc_length_dist(*fr._args(), _n(start), _n(stop), _n(min_length), _n(max_length),
+                                  _POLICY[intersect_policy], int(quality_threshold), _p(k, c_int64), _p(v, c_int64), cap)
+        if r >= 0:
+            return dict(zip(k[:r].tolist(), v[:r].tolist()))
+        cap *= 16
+
+
+def frag_lengths(fr: Frags, start=None, stop=None, intersect_policy="midpoint", quality_threshold=30) -> np.ndarray:
+    """frag/_frag_length.py:290-308 (length filter hard-wired 0..1e9)."""
+    out = np.zeros(max(fr.n, 1), np.int32)
+    r = lib().orc_frag_lengths(*fr._args(), _n(start), _n(stop), 0, 1000000000, _POLICY[intersect_policy],
+                               int(quality_threshold), _p(out, c_int32), fr.n)
+    assert r >= 0
+    return out[:r].copy()
+
+
+def merge_dists(dists) -> dict:
+    """Genome-wide stream = contigs in file order; merge keeps first-seen order."""
+    out: dict = {}
+    for d in dists:
+        for k, v in d.items():
+            out[k] = out.get(k, 0) + v
+    return out
+
+
+def find_median(d: dict) -> float:
+    """frag/_frag_length.py:156-172 (_find_median), quirks included."""
+    val = np.array(list(d.keys()))
+    freq = np.array(list(d.values()))
+    order = np.argsort(val)
+    val, freq = val[order], freq[order]
+    cdf = np.cumsum(freq)
+    total = cdf[-1]
+    if total % 2 == 1:
+        return float(val[np.searchsorted(cdf, total // 2)])
+    idx = np.searchsorted(cdf, [total // 2, total // 2 + 1])
+    return float(np.mean(val[idx]))
+
+
+def length_stats(d: dict, short_reads: int):
+    """frag/_frag_length.py:204-238 : (mean, median, stdev, min, max, count, frac_short) or -1s."""
+    total = sum(d.values())
+    if total == 0:
+        return (-1, -1, -1, -1, -1, -1, -1)
+    mean = sum(v * c for v, c in d.items()) / total
+    median = find_median(d)
+    var = sum(c * ((v - mean) ** 2) for v, c in d.items()) / total
+    n_short = sum(c for v, c in d.items() if v <= short_reads)
+    return (mean, median, var ** 0.5, min(d), max(d), total, n_short / total)
+
+
+def length_bins(d: dict, bin_size: int):
+    """frag/_frag_length.py:458-469 : (bins ndarray, counts list)."""
+    lo, hi = min(d), max(d)
+    n_bins = (hi - lo) // bin_size
+    bins = np.arange(lo, hi + bin_size, bin_size)
+    counts = np.zeros(n_bins + 1, dtype=np.int64)
+    for v, c in d.items():
+        counts[(v - lo) // bin_size] += c
+    return bins, counts.tolist()
+
+
+# --------------------------------------------------------------- end motifs
+def region_end_motifs(fr: Frags, seq_ascii: bytes, start, stop, k=4, both_strands=True,
+                      negative_strand=False, quality_threshold=20) -> np.ndarray:
+    """frag/_end_motifs.py:51-187 -> int64[4**k] in gen_kmers order. RuntimeError like the reference."""
+    if both_strands and negative_strand:
+        raise ValueError("Cannot have both both_strands and negative_strand.")
+    mode = 0 if both_strands else (2 if negative_strand else 1)
+    counts = np.zeros(4 ** k, np.int64)
+    err = lib().orc_region_end_motifs(*fr._args()[:3], _p(fr.strand, c_uint8), fr.n, fr.max_len, int(start), int(stop),
+                                      seq_ascii, len(seq_ascii), int(k), mode, int(quality_threshold), _p(counts, c_int64))
+    if err:
+        raise RuntimeError("Error querying sequence (reverse k-mer out of bounds)")
+    return counts
+
+
+def genome_windows(chrom_len: int, window: int = 1_000_000):
+    """frag/_motif_common.py:527-577 (_genome_window_args) for one contig."""
+    w = [(s, s + window) for s in range(0, chrom_len - window, window)]
+    w.append((chrom_len - chrom_len % window, chrom_len))
+    return w
+
+
+def mds(freq, k: int, miller_madow=False, n=None) -> float:
+    """frag/_motif_common.py:38-94 (_normalized_shannon_mds)."""
+    freq = np.asarray(freq, dtype=np.float64)
+    ent = -np.sum(freq * np.log(freq, out=np.zeros_like(freq), where=(freq != 0)))
+    if miller_madow:
+        if not n > 0:
+            return float("nan")
+        ent = ent + (int(np.count_nonzero(np.nan_to_num(freq))) - 1) / (2 * n)
+    return float(ent / np.log(4 ** k))
+
+
+# --------------------------------------------------------------- adjust_wps
+def local_filter(data, w: int, use_mean=False) -> np.ndarray:
+    """frag/_adjust_wps.py:25-45 via the C restatement (sort-based median)."""
+    x = np.ascontiguousarray(data, dtype=np.float64)
+    out = np.zeros(max(len(x) - w, 0), np.float64)
+    lib().orc_local_filter(_p(x, c_double), len(x), int(w), int(bool(use_mean)), _p(out, c_double))
+    return out
+
+
+def adjust_core(data, w=1000, use_mean=False, savgol=True, sg_window=21, sg_deg=2) -> np.ndarray:
+    """frag/_adjust_wps.py:131-140 : the same numpy + scipy calls the reference makes.
+
+    Third-party arithmetic: numpy.median/mean over sliding_window_view and
+    scipy.signal.savgol_filter (reference pins scipy 1.15.3/1.17.0; this image
+    has 1.18.1 - same algorithm).
+    """
+    from numpy.lib.stride_tricks import sliding_window_view
+    from scipy.signal import savgol_filter
+    x = np.asarray(data, dtype=np.float64)
+    nw = len(x) - w
+    if nw <= 0:
+        run = np.array([], dtype=np.float64)
+    else:
+        win = sliding_window_view(x, w)[:nw]
+        run = np.mean(win, axis=1) if use_mean else np.median(win, axis=1)
+    adj = x[w // 2: -(w // 2)] - run
+    return savgol_filter(adj, sg_window, sg_deg) if savgol else adj
+
+
+def adjust_sites(lines, interval_size, median_window_size):
+    """frag/_adjust_wps.py:219-263 : BED -> merged (contig, start, stop) intervals."""
+    left = round(-interval_size / 2)
+    right = round(interval_size / 2)
+    assert right - left == interval_size
+    dec = median_window_size // 2
+    out = []
+    for line in lines:
+        c = line.split("\t")
+        contig = c[0].strip()
+        mid = (int(c[1]) + int(c[2])) // 2
+        start = max(0, mid + int(left))
+        stop = mid + int(right)
+        if out and out[-1][0] == contig and out[-1][2] - dec > start + dec:
+            start = out[-1][1]
+            out.pop()
+        out.append((contig, int(start), int(stop)))
+    return out
