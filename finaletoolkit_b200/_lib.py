@@ -33,6 +33,14 @@ SYMBOLS = {
                                      _i32p, _i32p, _i32p, _i32p, _i64p]),
     "ftk_wps_tiles_i32": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int64,
                                   c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
+    "ftk_interval_hist_u64": (c_int, [_P, _P, _P, c_int64, c_int32, _P, _P, c_int64,
+                                      c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                      _P, _P, _P, _P, _P]),
+    "ftk_frag_lengths_i32": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                     c_int32, c_int32, c_int32, _P, c_int64, _P, _P, _P]),
+    "ftk_end_motif_hist_u64": (c_int, [_P, _P, _P, _P, c_int64, c_int32, _P, _P, c_int64,
+                                       _P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                       _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -1,0 +1,338 @@
+// Per-interval fragment counts, fragment-length histograms and raw lengths.
+//
+// Replaces the reference's generator loops over the fragment stream:
+//   coverage      frag/_coverage.py:117-130   `for _ in frags: coverage += 1`
+//   length dict   frag/_frag_length.py:147-153 `value_counts[len] += 1`
+//   raw lengths   frag/_frag_length.py:303     list of stop-start in stream order
+// with the stream's predicate folded into the kernels:
+//   io/alignment.py:270-302       tabix overlap rows, mapq >= q
+//   utils/_frag_generator.py:21-55, 117-123  inclusive length filter + policy
+//
+// Each (interval, split) pair is one CTA streaming a contiguous slice of the
+// start-sorted fragment columns (coalesced loads, several batches in flight),
+// counting in registers and binning lengths into a shared-memory-privatised
+// histogram that is flushed once with 64-bit global atomics.
+// Roofline: HBM, 9 B per candidate fragment (start, stop, mapq).
+#include "ftk_common.cuh"
+
+namespace ftk {
+
+constexpr int kHistThreads = 256;
+constexpr int kHistSmemBins = 2048;  // lengths below this are privatised in smem
+constexpr int kHistUnroll = 4;
+
+struct Pred {
+    int policy, min_len, max_len, min_mapq;
+};
+
+// Stream membership of one fragment for region [S, E) (FTK_NONE = unbounded).
+__device__ __forceinline__ bool frag_in_stream(int fs, int fe, int q, int S, int E, const Pred &p) {
+    const int L = fe - fs;
+    if (q < p.min_mapq || L < 0 || !frag_len_ok(L, p.min_len, p.max_len)) return false;
+    // tabix fetch(contig, S, E): rec.stop > start (None -> 0) and rec.start < stop
+    const bool overlap = (fe > (S == FTK_NONE ? 0 : S)) && (E == FTK_NONE || fs < E);
+    if (!overlap) return false;
+    if (p.policy == FTK_POLICY_MIDPOINT) {
+        const int mid = fs + (L >> 1);
+        return (S == FTK_NONE || mid >= S) && (E == FTK_NONE || mid < E);
+    }
+    return true;  // "any": the overlap test is the policy
+}
+
+// Candidate index range of each interval: a superset of its stream.
+__global__ void interval_ranges_kernel(const int32_t *__restrict__ frag_start, int64_t n_frag,
+                                       const int32_t *__restrict__ ivl_start,
+                                       const int32_t *__restrict__ ivl_stop, int64_t n_ivl,
+                                       int halo, int64_t *__restrict__ ranges) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n_ivl) return;
+    const int64_t k = t >> 1;
+    if ((t & 1) == 0) {
+        const int S = ivl_start[k];
+        ranges[t] = (S == FTK_NONE) ? 0 : lower_bound(frag_start, n_frag, (int64_t)S - halo);
+    } else {
+        const int E = ivl_stop[k];
+        ranges[t] = (E == FTK_NONE) ? n_frag : lower_bound(frag_start, n_frag, (int64_t)E);
+    }
+}
+
+template <bool HIST>
+__global__ void __launch_bounds__(kHistThreads)
+interval_hist_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
+                     const uint8_t *__restrict__ frag_mapq,
+                     const int32_t *__restrict__ ivl_start, const int32_t *__restrict__ ivl_stop,
+                     const int64_t *__restrict__ ranges, Pred pred, int n_bins, int pooled, int splits,
+                     unsigned long long *__restrict__ counts, unsigned long long *__restrict__ hist,
+                     int32_t *__restrict__ first_seen) {
+    __shared__ int s_cnt[HIST ? kHistSmemBins : 1];
+    __shared__ int s_first[HIST ? kHistSmemBins : 1];
+    __shared__ unsigned long long s_red[kHistThreads / 32];
+
+    const int tid = threadIdx.x;
+    const int64_t ivl = blockIdx.x / splits;
+    const int split = blockIdx.x % splits;
+    const int64_t row = pooled ? 0 : ivl;
+    const int S = ivl_start[ivl], E = ivl_stop[ivl];
+    const int64_t lo_all = ranges[2 * ivl], hi_all = ranges[2 * ivl + 1];
+    // contiguous slice of the candidate range for this split (multiple of 4 fragments)
+    int64_t chunk = (hi_all - lo_all + splits - 1) / splits;
+    chunk = (chunk + 3) & ~(int64_t)3;
+    const int64_t lo = lo_all + (int64_t)split * chunk;
+    const int64_t hi = min(hi_all, lo + chunk);
+    const bool want_first = HIST && (first_seen != nullptr);
+
+    if (HIST) {
+        for (int b = tid; b < kHistSmemBins; b += kHistThreads) { s_cnt[b] = 0; s_first[b] = INT32_MAX; }
+        __syncthreads();
+    }
+
+    unsigned long long my_count = 0;
+    int fs_r[kHistUnroll], fe_r[kHistUnroll], q_r[kHistUnroll];
+    for (int64_t i0 = lo + tid; i0 < hi; i0 += (int64_t)kHistUnroll * kHistThreads) {
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; ++u) {
+            const int64_t i = i0 + (int64_t)u * kHistThreads;
+            const bool in = i < hi;
+            fs_r[u] = in ? __ldcs(frag_start + i) : 0;
+            fe_r[u] = in ? __ldcs(frag_stop + i) : 0;
+            q_r[u] = in ? (frag_mapq ? (int)__ldcs(frag_mapq + i) : 255) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; ++u) {
+            if (!frag_in_stream(fs_r[u], fe_r[u], q_r[u], S, E, pred)) continue;
+            ++my_count;
+            if (HIST) {
+                const int L = fe_r[u] - fs_r[u];
+                const int idx = (int)(i0 + (int64_t)u * kHistThreads);
+                if (L < kHistSmemBins) {
+                    atomicAdd(&s_cnt[L], 1);
+                    if (want_first) atomicMin(&s_first[L], idx);
+                } else if (L < n_bins) {
+                    atomicAdd(&hist[row * n_bins + L], 1ull);
+                    if (want_first) atomicMin(&first_seen[row * n_bins + L], idx);
+                }
+            }
+        }
+    }
+
+    // block reduction of the count -> one 64-bit atomic per CTA
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) my_count += __shfl_down_sync(0xffffffffu, my_count, off);
+    if ((tid & 31) == 0) s_red[tid >> 5] = my_count;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < kHistThreads / 32; ++w) tot += s_red[w];
+        if (tot) atomicAdd(&counts[row], tot);
+    }
+    if (HIST) {
+        const int nb = min(n_bins, kHistSmemBins);
+        for (int b = tid; b < nb; b += kHistThreads) {
+            const int c = s_cnt[b];
+            if (c) {
+                atomicAdd(&hist[row * n_bins + b], (unsigned long long)c);
+                if (want_first) atomicMin(&first_seen[row * n_bins + b], s_first[b]);
+            }
+        }
+    }
+}
+
+// ---- raw lengths in stream order (frag_length): count / scan / scatter
+constexpr int kLenBlock = 1024;  // fragments per CTA
+
+__global__ void one_range_kernel(const int32_t *__restrict__ fs, int64_t n, int S, int E, int halo,
+                                 int64_t *__restrict__ r) {
+    if (threadIdx.x == 0) r[0] = (S == FTK_NONE) ? 0 : lower_bound(fs, n, (int64_t)S - halo);
+    if (threadIdx.x == 1) r[1] = (E == FTK_NONE) ? n : lower_bound(fs, n, (int64_t)E);
+}
+
+__global__ void __launch_bounds__(256)
+lengths_count_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
+                     const uint8_t *__restrict__ frag_mapq, const int64_t *__restrict__ range,
+                     int S, int E, Pred pred, int32_t *__restrict__ block_counts) {
+    __shared__ int s_red[8];
+    const int64_t lo = range[0], hi = range[1];
+    const int64_t base = lo + (int64_t)blockIdx.x * kLenBlock;
+    int c = 0;
+#pragma unroll
+    for (int u = 0; u < kLenBlock / 256; ++u) {
+        const int64_t i = base + u * 256 + threadIdx.x;
+        if (i < hi) {
+            const int q = frag_mapq ? (int)__ldcs(frag_mapq + i) : 255;
+            c += frag_in_stream(__ldcs(frag_start + i), __ldcs(frag_stop + i), q, S, E, pred);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+// single-CTA exclusive scan of block counts (n_blocks <= a few million); writes total to *n_out
+__global__ void __launch_bounds__(1024)
+lengths_scan_kernel(const int32_t *__restrict__ block_counts, const int64_t *__restrict__ range,
+                    int64_t *__restrict__ block_offsets, int64_t *__restrict__ n_out) {
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    const int64_t n_blocks = (range[1] - range[0] + kLenBlock - 1) / kLenBlock;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < n_blocks; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        long long v = (i < n_blocks) ? block_counts[i] : 0;
+        long long t = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            long long n = __shfl_up_sync(0xffffffffu, t, off);
+            if (lane >= off) t += n;
+        }
+        if (lane == 31) s_warp[warp] = t;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = s_warp[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                long long n = __shfl_up_sync(0xffffffffu, w, off);
+                if (lane >= off) w += n;
+            }
+            s_warp[lane] = w;  // inclusive
+        }
+        __syncthreads();
+        const long long warp_excl = warp ? s_warp[warp - 1] : 0;
+        const long long carry = s_carry;
+        if (i < n_blocks) block_offsets[i] = carry + warp_excl + t - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out = s_carry;
+}
+
+__global__ void __launch_bounds__(256)
+lengths_scatter_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
+                       const uint8_t *__restrict__ frag_mapq, const int64_t *__restrict__ range,
+                       int S, int E, Pred pred, const int64_t *__restrict__ block_offsets,
+                       int32_t *__restrict__ out) {
+    __shared__ int s_warp[8];
+    const int64_t lo = range[0], hi = range[1];
+    const int64_t base = lo + (int64_t)blockIdx.x * kLenBlock;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t off = block_offsets[blockIdx.x];
+    // stream order = index order: thread t of pass u owns fragment base + u*256 + t
+    for (int u = 0; u < kLenBlock / 256; ++u) {
+        const int64_t i = base + u * 256 + threadIdx.x;
+        int L = 0;
+        bool pass = false;
+        if (i < hi) {
+            const int fs = __ldcs(frag_start + i), fe = __ldcs(frag_stop + i);
+            const int q = frag_mapq ? (int)__ldcs(frag_mapq + i) : 255;
+            pass = frag_in_stream(fs, fe, q, S, E, pred);
+            L = fe - fs;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const int c = s_warp[w]; before += (w < warp) ? c : 0; total += c; }
+        if (pass) out[off + before + __popc(m & ((1u << lane) - 1))] = L;
+        off += total;
+        __syncthreads();
+    }
+}
+
+}  // namespace ftk
+
+using namespace ftk;
+
+static int effective_halo(int policy, int max_frag_len, int max_len) {
+    int m = max_frag_len;
+    if (max_len != FTK_NONE && max_len < m) m = max_len;
+    if (m < 0) m = 0;
+    // midpoint: fs + (L>>1) >= S  =>  fs >= S - (maxL>>1);  any: fe > S  =>  fs > S - maxL
+    return policy == FTK_POLICY_MIDPOINT ? (m >> 1) : m;
+}
+
+extern "C" int ftk_interval_hist_u64(const int32_t *frag_start, const int32_t *frag_stop,
+                                     const uint8_t *frag_mapq, int64_t n_frag, int32_t max_frag_len,
+                                     const int32_t *ivl_start, const int32_t *ivl_stop, int64_t n_ivl,
+                                     int32_t policy, int32_t min_len, int32_t max_len, int32_t min_mapq,
+                                     int32_t n_bins, int32_t pooled, int32_t splits,
+                                     int64_t *scratch, uint64_t *counts, uint64_t *hist,
+                                     int32_t *first_seen, ftk_stream_t stream_) {
+    if (n_ivl == 0) return FTK_OK;
+    if (n_frag < 0 || n_ivl < 0 || splits < 1 || n_bins < 0) return FTK_E_INVALID;
+    if (policy != FTK_POLICY_MIDPOINT && policy != FTK_POLICY_ANY) return FTK_E_INVALID;
+    if (!ivl_start || !ivl_stop || !scratch || !counts) return FTK_E_INVALID;
+    if (n_frag > 0 && (!frag_start || !frag_stop)) return FTK_E_INVALID;
+    if (n_bins > 0 && !hist) return FTK_E_INVALID;
+    if (n_frag > INT32_MAX) return FTK_E_RANGE;  // first-seen indices are int32
+    if (n_ivl * (int64_t)splits > INT32_MAX) return FTK_E_RANGE;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int halo = effective_halo(policy, max_frag_len, max_len);
+    {
+        const int64_t n = 2 * n_ivl;
+        interval_ranges_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(
+            frag_start, n_frag, ivl_start, ivl_stop, n_ivl, halo, scratch);
+        FTK_CHECK_LAUNCH("interval_ranges_kernel");
+    }
+    Pred pred{policy, min_len, max_len, min_mapq};
+    const unsigned grid = (unsigned)(n_ivl * splits);
+    auto *c = reinterpret_cast<unsigned long long *>(counts);
+    auto *h = reinterpret_cast<unsigned long long *>(hist);
+    if (n_bins > 0)
+        interval_hist_kernel<true><<<grid, kHistThreads, 0, stream>>>(
+            frag_start, frag_stop, frag_mapq, ivl_start, ivl_stop, scratch, pred, n_bins, pooled, splits, c, h, first_seen);
+    else
+        interval_hist_kernel<false><<<grid, kHistThreads, 0, stream>>>(
+            frag_start, frag_stop, frag_mapq, ivl_start, ivl_stop, scratch, pred, 0, pooled, splits, c, nullptr, nullptr);
+    FTK_CHECK_LAUNCH("interval_hist_kernel");
+    return FTK_OK;
+}
+
+extern "C" int ftk_frag_lengths_i32(const int32_t *frag_start, const int32_t *frag_stop,
+                                    const uint8_t *frag_mapq, int64_t n_frag, int32_t max_frag_len,
+                                    int32_t region_start, int32_t region_stop, int32_t policy,
+                                    int32_t min_len, int32_t max_len, int32_t min_mapq,
+                                    int64_t *scratch, int64_t scratch_len, int32_t *out,
+                                    int64_t *n_out, ftk_stream_t stream_) {
+    // scratch (int64 slots): [0..1] candidate range, [2 .. 2+nb) block offsets,
+    // then nb int32 block counts packed two per slot.
+    if (n_frag < 0 || !scratch || !out || !n_out) return FTK_E_INVALID;
+    if (policy != FTK_POLICY_MIDPOINT && policy != FTK_POLICY_ANY) return FTK_E_INVALID;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int64_t nb = (n_frag + kLenBlock - 1) / kLenBlock + 1;
+    if (scratch_len < 2 + nb + (nb + 1) / 2) return FTK_E_INVALID;
+    if (nb > INT32_MAX) return FTK_E_RANGE;
+    if (n_frag == 0) {
+        FTK_CUDA_TRY(cudaMemsetAsync(n_out, 0, sizeof(int64_t), stream));
+        return FTK_OK;
+    }
+    if (!frag_start || !frag_stop) return FTK_E_INVALID;
+    const int halo = effective_halo(policy, max_frag_len, max_len);
+    int64_t *range = scratch;
+    int64_t *block_offsets = scratch + 2;
+    int32_t *block_counts = reinterpret_cast<int32_t *>(scratch + 2 + nb);
+    Pred pred{policy, min_len, max_len, min_mapq};
+    one_range_kernel<<<1, 32, 0, stream>>>(frag_start, n_frag, region_start, region_stop, halo, range);
+    FTK_CHECK_LAUNCH("one_range_kernel");
+    // The candidate range stays on the device (no host sync): the grids cover the
+    // whole contig and CTAs beyond the range find nothing to do.
+    const unsigned grid = (unsigned)(nb - 1);
+    lengths_count_kernel<<<grid, 256, 0, stream>>>(frag_start, frag_stop, frag_mapq, range,
+                                                   region_start, region_stop, pred, block_counts);
+    FTK_CHECK_LAUNCH("lengths_count_kernel");
+    lengths_scan_kernel<<<1, 1024, 0, stream>>>(block_counts, range, block_offsets, n_out);
+    FTK_CHECK_LAUNCH("lengths_scan_kernel");
+    lengths_scatter_kernel<<<grid, 256, 0, stream>>>(frag_start, frag_stop, frag_mapq, range,
+                                                     region_start, region_stop, pred, block_offsets, out);
+    FTK_CHECK_LAUNCH("lengths_scatter_kernel");
+    return FTK_OK;
+}

@@ -1,0 +1,171 @@
+// 5' end-motif k-mer histograms on sm_100a.
+//
+// Replaces the per-fragment loop of region_end_motifs (frag/_end_motifs.py:115-179):
+// two py2bit sequence() calls + a dict increment per fragment become two 64-bit
+// window reads of a 2-bit packed contig (L2-resident: chr1 = 62 MB + 31 MB N-mask)
+// and shared-memory-privatised histogram atomics.
+//   forward k-mer : ref[fs, fs+k)              index = sum code_j * 4^(k-1-j)
+//   reverse k-mer : revcomp(ref[fe-k, fe))     (utils/utils.py:413-437)
+//   k-mers containing N are skipped (frag/_end_motifs.py:133,142)
+//   forward window out of bounds -> fragment skipped entirely (:135-136)
+//   reverse window out of bounds -> RuntimeError in the reference (:144-151):
+//       reported through *error_flag, the host raises.
+// Membership is tabix overlap only - no length filter, no midpoint policy
+// (frag/_end_motifs.py:115-120).
+// Index order = itertools.product("ACGT") (utils/utils.py:388-410): A0 C1 G2 T3.
+// Roofline: HBM, 10 B per candidate fragment (start, stop, mapq, strand) + 2 x 2 B
+// of packed reference per end served from L2.
+#include "ftk_common.cuh"
+
+namespace ftk {
+
+constexpr int kMotifThreads = 256;
+constexpr int kMotifSmemBins = 4096;  // k <= 6 privatised in shared memory
+constexpr int kMotifUnroll = 4;
+
+// 2k-bit window starting at base `pos` (base i at bits 2*(i%16) of word i/16).
+__device__ __forceinline__ uint32_t window2(const uint32_t *__restrict__ seq, int64_t pos, int k) {
+    const int64_t w = pos >> 4;
+    const int sh = (int)(pos & 15) * 2;
+    const unsigned long long v = ((unsigned long long)__ldg(seq + w + 1) << 32) | __ldg(seq + w);
+    const unsigned long long mask = (k >= 16) ? 0xffffffffull : ((1ull << (2 * k)) - 1ull);
+    return (uint32_t)((v >> sh) & mask);
+}
+__device__ __forceinline__ bool has_n(const uint32_t *__restrict__ nmask, int64_t pos, int k) {
+    const int64_t w = pos >> 5;
+    const int sh = (int)(pos & 31);
+    const unsigned long long v = ((unsigned long long)__ldg(nmask + w + 1) << 32) | __ldg(nmask + w);
+    return ((v >> sh) & ((1ull << k) - 1ull)) != 0ull;
+}
+// reverse the order of the k 2-bit digits of x (first base becomes the most significant digit)
+__device__ __forceinline__ uint32_t digit_reverse(uint32_t x, int k) {
+    x = __brev(x);
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    return x >> (32 - 2 * k);
+}
+
+__global__ void motif_ranges_kernel(const int32_t *__restrict__ frag_start, int64_t n_frag,
+                                    const int32_t *__restrict__ ivl_start,
+                                    const int32_t *__restrict__ ivl_stop, int64_t n_ivl,
+                                    int halo, int64_t *__restrict__ ranges) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n_ivl) return;
+    const int64_t k = t >> 1;
+    // overlap: fe > S (=> fs > S - maxL) and fs < E
+    const int64_t key = (t & 1) ? (int64_t)ivl_stop[k] : (int64_t)ivl_start[k] - halo;
+    ranges[t] = lower_bound(frag_start, n_frag, key);
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kMotifThreads)
+end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
+                 const uint8_t *__restrict__ frag_mapq, const uint8_t *__restrict__ frag_strand,
+                 const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask, int64_t contig_len,
+                 const int32_t *__restrict__ ivl_start, const int32_t *__restrict__ ivl_stop,
+                 const int64_t *__restrict__ ranges, int k, int strand_mode, int min_mapq,
+                 int pooled, int splits, unsigned long long *__restrict__ counts,
+                 int32_t *__restrict__ error_flag) {
+    __shared__ int s_cnt[SMEM ? kMotifSmemBins : 1];
+    const int tid = threadIdx.x;
+    const int n_bins = 1 << (2 * k);
+    const int64_t ivl = blockIdx.x / splits;
+    const int split = blockIdx.x % splits;
+    unsigned long long *__restrict__ row = counts + (pooled ? 0 : ivl * (int64_t)n_bins);
+    const int S = ivl_start[ivl], E = ivl_stop[ivl];
+    const int64_t lo_all = ranges[2 * ivl], hi_all = ranges[2 * ivl + 1];
+    int64_t chunk = (hi_all - lo_all + splits - 1) / splits;
+    chunk = (chunk + 3) & ~(int64_t)3;
+    const int64_t lo = lo_all + (int64_t)split * chunk;
+    const int64_t hi = min(hi_all, lo + chunk);
+
+    if (SMEM) {
+        for (int b = tid; b < n_bins; b += kMotifThreads) s_cnt[b] = 0;
+        __syncthreads();
+    }
+    auto bump = [&](uint32_t idx) {
+        if (SMEM) atomicAdd(&s_cnt[idx], 1); else atomicAdd(&row[idx], 1ull);
+    };
+
+    int fs_r[kMotifUnroll], fe_r[kMotifUnroll], q_r[kMotifUnroll], sd_r[kMotifUnroll];
+    for (int64_t i0 = lo + tid; i0 < hi; i0 += (int64_t)kMotifUnroll * kMotifThreads) {
+#pragma unroll
+        for (int u = 0; u < kMotifUnroll; ++u) {
+            const int64_t i = i0 + (int64_t)u * kMotifThreads;
+            const bool in = i < hi;
+            fs_r[u] = in ? __ldcs(frag_start + i) : 0;
+            fe_r[u] = in ? __ldcs(frag_stop + i) : 0;
+            q_r[u] = in ? (frag_mapq ? (int)__ldcs(frag_mapq + i) : 255) : -1;
+            sd_r[u] = (in && frag_strand) ? (int)__ldcs(frag_strand + i) : 1;
+        }
+#pragma unroll
+        for (int u = 0; u < kMotifUnroll; ++u) {
+            const int fs = fs_r[u], fe = fe_r[u];
+            if (q_r[u] < min_mapq || !(fe > S && fs < E)) continue;
+            if (strand_mode == 1 && !sd_r[u]) continue;  // forward-only: '+' fragments only
+            if (strand_mode != 2) {
+                if (fs < 0 || (int64_t)fs + k > contig_len) continue;  // ValueError -> `continue`
+                if (!has_n(nmask, fs, k)) bump(digit_reverse(window2(seq, fs, k), k));
+            }
+            if (strand_mode != 1) {
+                const int64_t rs = (int64_t)fe - k;
+                if (rs < 0 || (int64_t)fe > contig_len) {
+                    if (strand_mode == 0) atomicOr(error_flag, 1);  // RuntimeError in the reference
+                    continue;
+                }
+                if (!has_n(nmask, rs, k)) {
+                    const uint32_t mask = (k >= 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
+                    bump((~window2(seq, rs, k)) & mask);
+                }
+            }
+        }
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int b = tid; b < n_bins; b += kMotifThreads) {
+            const int c = s_cnt[b];
+            if (c) atomicAdd(&row[b], (unsigned long long)c);
+        }
+    }
+}
+
+}  // namespace ftk
+
+using namespace ftk;
+
+extern "C" int ftk_end_motif_hist_u64(const int32_t *frag_start, const int32_t *frag_stop,
+                                      const uint8_t *frag_mapq, const uint8_t *frag_strand,
+                                      int64_t n_frag, int32_t max_frag_len,
+                                      const uint32_t *seq_words, const uint32_t *nmask_words,
+                                      int64_t contig_len,
+                                      const int32_t *ivl_start, const int32_t *ivl_stop, int64_t n_ivl,
+                                      int32_t k, int32_t strand_mode, int32_t min_mapq,
+                                      int32_t pooled, int32_t splits,
+                                      int64_t *scratch, uint64_t *counts, int32_t *error_flag,
+                                      ftk_stream_t stream_) {
+    if (n_ivl == 0) return FTK_OK;
+    if (n_frag < 0 || n_ivl < 0 || splits < 1 || k < 1 || k > 12) return FTK_E_INVALID;
+    if (strand_mode < 0 || strand_mode > 2) return FTK_E_INVALID;
+    if (!seq_words || !nmask_words || !ivl_start || !ivl_stop || !scratch || !counts || !error_flag)
+        return FTK_E_INVALID;
+    if (n_frag > 0 && (!frag_start || !frag_stop)) return FTK_E_INVALID;
+    if (n_ivl * (int64_t)splits > INT32_MAX) return FTK_E_RANGE;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    {
+        const int64_t n = 2 * n_ivl;
+        motif_ranges_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(
+            frag_start, n_frag, ivl_start, ivl_stop, n_ivl, max_frag_len < 0 ? 0 : max_frag_len, scratch);
+        FTK_CHECK_LAUNCH("motif_ranges_kernel");
+    }
+    const unsigned grid = (unsigned)(n_ivl * splits);
+    auto *c = reinterpret_cast<unsigned long long *>(counts);
+    if ((1 << (2 * k)) <= kMotifSmemBins)
+        end_motif_kernel<true><<<grid, kMotifThreads, 0, stream>>>(
+            frag_start, frag_stop, frag_mapq, frag_strand, seq_words, nmask_words, contig_len,
+            ivl_start, ivl_stop, scratch, k, strand_mode, min_mapq, pooled, splits, c, error_flag);
+    else
+        end_motif_kernel<false><<<grid, kMotifThreads, 0, stream>>>(
+            frag_start, frag_stop, frag_mapq, frag_strand, seq_words, nmask_words, contig_len,
+            ivl_start, ivl_stop, scratch, k, strand_mode, min_mapq, pooled, splits, c, error_flag);
+    FTK_CHECK_LAUNCH("end_motif_kernel");
+    return FTK_OK;
+}

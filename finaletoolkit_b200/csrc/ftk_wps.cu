@@ -24,6 +24,7 @@ constexpr int kWpsWarps = kWpsThreads / 32;
 constexpr int kWpsCap = 5120;                    // smem slots per tile
 constexpr int kWpsIters = kWpsCap / (kWpsThreads * 4);  // int4 groups per lane
 constexpr int kWpsSpan = kWpsIters * 128;        // positions per warp
+constexpr int kWpsUnroll = 4;                    // fragment loads in flight per thread (x3 columns)
 static_assert(kWpsIters * kWpsThreads * 4 == kWpsCap, "tile must split evenly");
 static_assert(FTK_WPS_TILE < kWpsCap, "one guard slot for odd windows");
 
@@ -76,24 +77,16 @@ wps_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restric
     const int g0 = ODD ? p0 - 1 : p0;
     const int glen = ODD ? len + 1 : len;
 
-#pragma unroll
-    for (int j = 0; j < kWpsIters; ++j)
-        reinterpret_cast<int4 *>(D)[j * kWpsThreads + tid] = make_int4(0, 0, 0, 0);
-    __syncthreads();
-
-    // ---- scatter: coalesced streaming loads, 2 or 4 shared atomics per passing fragment
-    for (int64_t i = lo + tid; i < hi; i += kWpsThreads) {
-        const int fs = ld_stream(frag_start + i);
-        const int fe = ld_stream(frag_stop + i);
-        const int q = frag_mapq ? (int)ld_stream_u8(frag_mapq + i) : 255;
+    // One fragment's events -> shared atomics (2, or 4 when L > W).
+    auto scatter = [&](int fs, int fe, int q) {
         const int L = fe - fs;
         const int mid = fs + (L >> 1);  // (fs+fe)//2 for L >= 0
         const bool pass = (q >= min_mapq) && (L >= 0) && frag_len_ok(L, min_len, max_len) &&
                           (mid >= mid_lo) && (mid < mid_hi);
-        if (!pass) continue;
+        if (!pass) return;
         const int e_last = fe + a + 1 - g0;  // +1
         const int e_first = fs - b - g0;     // -1
-        if (e_last <= 0 || e_first >= glen) continue;  // cancels on slot 0 / entirely right of the tile
+        if (e_last <= 0 || e_first >= glen) return;  // cancels on slot 0 / entirely right of the tile
         atomicAdd(&D[max(e_first, 0)], -1);
         if (e_last < glen) atomicAdd(&D[e_last], 1);
         if (L > window) {
@@ -102,6 +95,38 @@ wps_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restric
             if (e1 < glen) atomicAdd(&D[max(e1, 0)], 2);
             if (e2 < glen) atomicAdd(&D[max(e2, 0)], -2);
         }
+    };
+
+    // ---- software-pipelined scatter: kWpsUnroll x 3 coalesced streaming loads stay in
+    // flight per thread while the previous batch is turned into shared atomics; the
+    // first batch is issued before the tile is zeroed so its latency hides behind that.
+    int fs_r[kWpsUnroll], fe_r[kWpsUnroll], q_r[kWpsUnroll];
+    auto load_batch = [&](int64_t i0) {
+#pragma unroll
+        for (int u = 0; u < kWpsUnroll; ++u) {
+            const int64_t i = i0 + (int64_t)u * kWpsThreads;
+            const bool in = i < hi;
+            fs_r[u] = in ? __ldcs(frag_start + i) : 0;
+            fe_r[u] = in ? __ldcs(frag_stop + i) : 0;
+            q_r[u] = in ? (frag_mapq ? (int)__ldcs(frag_mapq + i) : 255) : -1;  // -1 never passes
+        }
+    };
+    int64_t i0 = lo + tid;
+    load_batch(i0);
+
+#pragma unroll
+    for (int j = 0; j < kWpsIters; ++j)
+        reinterpret_cast<int4 *>(D)[j * kWpsThreads + tid] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+
+    while (i0 < hi) {  // block-uniform trip count not required: no barrier inside
+        int fs_c[kWpsUnroll], fe_c[kWpsUnroll], q_c[kWpsUnroll];
+#pragma unroll
+        for (int u = 0; u < kWpsUnroll; ++u) { fs_c[u] = fs_r[u]; fe_c[u] = fe_r[u]; q_c[u] = q_r[u]; }
+        i0 += (int64_t)kWpsUnroll * kWpsThreads;
+        if (i0 < hi) load_batch(i0);
+#pragma unroll
+        for (int u = 0; u < kWpsUnroll; ++u) scatter(fs_c[u], fe_c[u], q_c[u]);
     }
     __syncthreads();
 

@@ -83,6 +83,65 @@ int ftk_wps_tiles_i32(const int32_t *frag_start_dev, const int32_t *frag_stop_de
                       int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
                       int64_t *scratch_dev, int32_t *out_dev, ftk_stream_t stream);
 
+/* ------------------------------------------- coverage / fragment lengths
+ * Fragment stream of a region (S, E) - FTK_NONE = None - exactly as the
+ * reference builds it: tabix overlap rows (io/alignment.py:270-302:
+ * stop > S and start < E, mapq >= min_mapq), inclusive length filter and
+ * intersect policy (utils/_frag_generator.py:21-55,117-123).
+ *
+ * ftk_interval_hist_u64 replaces, per interval,
+ *   - single_coverage's counting loop, frag/_coverage.py:117-130  -> counts
+ *   - _distribution_from_gen, frag/_frag_length.py:147-153        -> hist (+ first_seen)
+ * counts[row] += number of stream fragments; hist[row*n_bins + L] += 1 for
+ * L < n_bins; first_seen[row*n_bins + L] = min fragment index with that
+ * length (the dict's first-insertion order, which the reference's fp sums
+ * follow, frag/_frag_length.py:213-217).  row = interval index, or 0 when
+ * `pooled`.  Outputs are ACCUMULATED: the caller zeroes counts/hist and fills
+ * first_seen with INT32_MAX.  n_bins == 0: counts only (hist/first_seen NULL).
+ * Each interval is processed by `splits` CTAs.  scratch_dev: int64[2*n_ivl].
+ * max_frag_len = max(stop-start) over the contig (bounds the left halo).
+ */
+int ftk_interval_hist_u64(const int32_t *frag_start_dev, const int32_t *frag_stop_dev,
+                          const uint8_t *frag_mapq_dev, int64_t n_frag, int32_t max_frag_len,
+                          const int32_t *ivl_start_dev, const int32_t *ivl_stop_dev, int64_t n_ivl,
+                          int32_t policy, int32_t min_len, int32_t max_len, int32_t min_mapq,
+                          int32_t n_bins, int32_t pooled, int32_t splits,
+                          int64_t *scratch_dev, uint64_t *counts_dev, uint64_t *hist_dev,
+                          int32_t *first_seen_dev, ftk_stream_t stream);
+
+/* frag_length(): lengths (stop-start) of the stream of one region in stream
+ * order, frag/_frag_length.py:290-308.  out_dev must hold n_frag int32;
+ * *n_out_dev receives the count.  scratch_dev: int64[scratch_len],
+ * scratch_len >= 2 + nb + (nb+1)/2 with nb = ceil(n_frag/1024) + 1. */
+int ftk_frag_lengths_i32(const int32_t *frag_start_dev, const int32_t *frag_stop_dev,
+                         const uint8_t *frag_mapq_dev, int64_t n_frag, int32_t max_frag_len,
+                         int32_t region_start, int32_t region_stop, int32_t policy,
+                         int32_t min_len, int32_t max_len, int32_t min_mapq,
+                         int64_t *scratch_dev, int64_t scratch_len, int32_t *out_dev,
+                         int64_t *n_out_dev, ftk_stream_t stream);
+
+/* ------------------------------------------------------------ end motifs
+ * Replaces the per-fragment loop of region_end_motifs, frag/_end_motifs.py:115-179
+ * (and its Pool drivers frag/_motif_common.py:580-610, 633-687).
+ * seq_words_dev: 2 bits per base, base i in bits 2*(i%16).. of word i/16, codes
+ * A0 C1 G2 T3; nmask_words_dev: 1 bit per base (bit i%32 of word i/32), set for
+ * N.  Both padded with >= 2 spare words.  counts[row*4^k + index] += 1 with
+ * index in itertools.product("ACGT") order (utils/utils.py:388-410); row =
+ * interval, or 0 when `pooled`.  strand_mode 0 = both strands, 1 = forward only,
+ * 2 = negative only.  *error_flag_dev is OR-ed with 1 when the reference would
+ * raise RuntimeError (reverse k-mer out of bounds, frag/_end_motifs.py:144-151).
+ * 1 <= k <= 12.  scratch_dev: int64[2*n_ivl]. */
+int ftk_end_motif_hist_u64(const int32_t *frag_start_dev, const int32_t *frag_stop_dev,
+                           const uint8_t *frag_mapq_dev, const uint8_t *frag_strand_dev,
+                           int64_t n_frag, int32_t max_frag_len,
+                           const uint32_t *seq_words_dev, const uint32_t *nmask_words_dev,
+                           int64_t contig_len,
+                           const int32_t *ivl_start_dev, const int32_t *ivl_stop_dev, int64_t n_ivl,
+                           int32_t k, int32_t strand_mode, int32_t min_mapq,
+                           int32_t pooled, int32_t splits,
+                           int64_t *scratch_dev, uint64_t *counts_dev, int32_t *error_flag_dev,
+                           ftk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
