@@ -162,3 +162,126 @@ class WpsPlan:
             int(window_size), none_to_ftk(min_length), int(max_length), int(quality_threshold),
             self.scratch.data_ptr(), out.data_ptr(), _stream_ptr(self.device)), "ftk_wps_tiles_i32")
         return out
+
+
+_POLICY = {"midpoint": 0, "any": 1}
+_TARGET_CTAS = 148 * 8  # SM count x resident CTAs: enough slices to fill the chip
+
+
+def policy_code(intersect_policy: str) -> int:
+    """utils/_frag_generator.py:52-53: unknown policy -> InvalidInputError."""
+    try:
+        return _POLICY[intersect_policy]
+    except KeyError:
+        from .exceptions import InvalidInputError
+        raise InvalidInputError(f"{intersect_policy} is not a valid policy") from None
+
+
+def _splits_for(n_ivl: int, n_frag: int) -> int:
+    """CTAs per interval: fill the chip without slicing below ~4k candidates."""
+    if n_ivl <= 0:
+        return 1
+    by_grid = -(-_TARGET_CTAS // n_ivl)
+    by_size = max(1, (n_frag // max(n_ivl, 1)) // 4096 + 1)
+    return int(max(1, min(by_grid, by_size, 65536)))
+
+
+def _ivl_to_device(ivl_start, ivl_stop, device):
+    s = np.array([FTK_NONE if v is None else int(v) for v in ivl_start], dtype=np.int64)
+    e = np.array([FTK_NONE if v is None else int(v) for v in ivl_stop], dtype=np.int64)
+    lim = 2 ** 31 - 1
+    s = np.where(s == FTK_NONE, FTK_NONE, np.clip(s, -lim, lim)).astype(np.int32)
+    e = np.where(e == FTK_NONE, FTK_NONE, np.clip(e, -lim, lim)).astype(np.int32)
+    return _to_device(s, device, np.int32), _to_device(e, device, np.int32)
+
+
+def interval_hist(frags: ContigFragments, ivl_start, ivl_stop, intersect_policy="midpoint",
+                  min_length=None, max_length=None, quality_threshold=30, n_bins=0,
+                  pooled=False, first_seen=False):
+    """Counts (and optional length histograms) of the fragment stream of each interval.
+
+    Returns device tensors ``(counts int64[rows], hist int64[rows, n_bins] | None,
+    first int32[rows, n_bins] | None)``; rows = 1 when ``pooled``.
+    """
+    t = torch()
+    dev = frags.device
+    n_ivl = len(ivl_start)
+    rows = 1 if pooled else n_ivl
+    counts = t.zeros(max(rows, 1), dtype=t.int64, device=dev)
+    hist = t.zeros((max(rows, 1), n_bins), dtype=t.int64, device=dev) if n_bins else None
+    first = (t.full((max(rows, 1), n_bins), 2 ** 31 - 1, dtype=t.int32, device=dev)
+             if (n_bins and first_seen) else None)
+    if n_ivl == 0:
+        return counts[:rows], hist, first
+    s_dev, e_dev = _ivl_to_device(ivl_start, ivl_stop, dev)
+    scratch = t.empty(2 * n_ivl, dtype=t.int64, device=dev)
+    fs, fe, mq = frags.ptrs()
+    check(lib().ftk_interval_hist_u64(
+        fs, fe, mq, frags.n, frags.max_len, s_dev.data_ptr(), e_dev.data_ptr(), n_ivl,
+        policy_code(intersect_policy), none_to_ftk(min_length), none_to_ftk(max_length),
+        int(quality_threshold), int(n_bins), int(bool(pooled)), _splits_for(n_ivl, frags.n),
+        scratch.data_ptr(), counts.data_ptr(), 0 if hist is None else hist.data_ptr(),
+        0 if first is None else first.data_ptr(), _stream_ptr(dev)), "ftk_interval_hist_u64")
+    return counts[:rows], hist, first
+
+
+def frag_lengths(frags: ContigFragments, start=None, stop=None, intersect_policy="midpoint",
+                 min_length=0, max_length=1000000000, quality_threshold=30):
+    """int32 lengths of the stream of one region, in stream order (device tensor)."""
+    t = torch()
+    dev = frags.device
+    nb = (frags.n + 1023) // 1024 + 1
+    scratch = t.empty(2 + nb + (nb + 1) // 2, dtype=t.int64, device=dev)
+    out = t.empty(max(frags.n, 1), dtype=t.int32, device=dev)
+    n_out = t.zeros(1, dtype=t.int64, device=dev)
+    fs, fe, mq = frags.ptrs()
+    check(lib().ftk_frag_lengths_i32(
+        fs, fe, mq, frags.n, frags.max_len, none_to_ftk(start), none_to_ftk(stop),
+        policy_code(intersect_policy), none_to_ftk(min_length), none_to_ftk(max_length),
+        int(quality_threshold), scratch.data_ptr(), scratch.numel(), out.data_ptr(),
+        n_out.data_ptr(), _stream_ptr(dev)), "ftk_frag_lengths_i32")
+    return out[: int(n_out.item())]
+
+
+class PackedContig:
+    """2-bit packed reference contig + N mask in HBM (layout: synth.pack_twobit)."""
+
+    def __init__(self, seq_words: np.ndarray, nmask_words: np.ndarray, length: int, device=None):
+        self.device = require_cuda(device)
+        self.length = int(length)
+        self.seq = _to_device(seq_words, self.device, np.uint32)
+        self.nmask = _to_device(nmask_words, self.device, np.uint32)
+
+    @classmethod
+    def from_codes(cls, codes: np.ndarray, n_mask: np.ndarray, device=None):
+        from .synth import pack_twobit
+        sw, nw = pack_twobit(codes, n_mask)
+        return cls(sw, nw, codes.shape[0], device)
+
+
+def end_motif_hist(frags: ContigFragments, ref: PackedContig, ivl_start, ivl_stop, k=4,
+                   strand_mode=0, quality_threshold=20, pooled=False, counts=None):
+    """k-mer counts int64[rows, 4**k] (device); raises RuntimeError like the reference."""
+    t = torch()
+    dev = frags.device
+    n_ivl = len(ivl_start)
+    rows = 1 if pooled else n_ivl
+    if counts is None:
+        counts = t.zeros((max(rows, 1), 4 ** k), dtype=t.int64, device=dev)
+    if n_ivl == 0:
+        return counts[:rows]
+    s_dev, e_dev = _ivl_to_device(ivl_start, ivl_stop, dev)
+    scratch = t.empty(2 * n_ivl, dtype=t.int64, device=dev)
+    err = t.zeros(1, dtype=t.int32, device=dev)
+    fs, fe, mq = frags.ptrs()
+    sd = 0 if frags.strand is None else frags.strand.data_ptr()
+    check(lib().ftk_end_motif_hist_u64(
+        fs, fe, mq, sd, frags.n, frags.max_len, ref.seq.data_ptr(), ref.nmask.data_ptr(), ref.length,
+        s_dev.data_ptr(), e_dev.data_ptr(), n_ivl, int(k), int(strand_mode), int(quality_threshold),
+        int(bool(pooled)), _splits_for(n_ivl, frags.n), scratch.data_ptr(), counts.data_ptr(),
+        err.data_ptr(), _stream_ptr(dev)), "ftk_end_motif_hist_u64")
+    if int(err.item()):
+        raise RuntimeError(
+            "Error querying sequence: reverse k-mer window out of contig bounds. Please verify "
+            "that the reference file matches the fragment file.")
+    return counts[:rows]
