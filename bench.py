@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native FinaleToolkit hot path (contract: see DESIGN.md §6).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
+
+Workload (BASELINE.json configs[1]): synthetic chr1-scale 30x fragment set - one
+249,250,621-bp contig, 80 M start-sorted fragments per GPU (SURVEY.md §8d seeds) -
+and one "step" = L-WPS (window 120, fragments 120-180, mapq >= 30) over the contig
+tiled by 49,851 5-kb intervals + per-interval coverage counts + the pooled
+fragment-length histogram.  N > 1: every rank owns its own chr1-scale shard
+(contig-sharded, no data-path collective) -> weak scaling.
+
+One JSON line on stdout (rank 0).  `value` = fragments/s with inputs resident in
+HBM; `e2e` = the same step from pinned HOST columns (H2D + kernels + D2H of every
+result); `roofline` = the WPS tile kernel's algorithmic bytes / its own CUDA-event
+time vs the measured HBM peak; `cpu_baseline` = the oracle's OpenMP port of the
+reference loops on a bounded sample of the same intervals.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+CONTIG_LEN = 249_250_621
+N_FRAG = int(os.environ.get("FTK_BENCH_NFRAG", 80_000_000))
+IVL = 5000
+WINDOW, MIN_LEN, MAX_LEN, MAPQ = 120, 120, 180, 30
+METRIC = "wps_fragments_per_sec"
+UNIT = "fragments/s"
+WORKLOAD = ("synthetic chr1-scale 30x: 249,250,621 bp, %d fragments/GPU; L-WPS (W=120, 120-180, mapq>=30) "
+            "over 49,851 5-kb intervals + per-interval coverage + length histogram" % N_FRAG)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_intervals():
+    edges = np.arange(0, CONTIG_LEN + IVL, IVL, dtype=np.int64).clip(max=CONTIG_LEN)
+    return edges[:-1].copy(), edges[1:].copy()
+
+
+# --------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Polls NVML (SM clock, throttle reasons) while the timed region runs."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.mask, self.max_mhz = [], 0, None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join()
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        reasons = [n for b, n in self.REASONS.items() if self.mask & b and n != "gpu_idle"]
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------- CPU baseline leg
+def cpu_sample_rate(st, sp, mq, target_s: float, seed=0):
+    """Time the oracle's OpenMP port of the reference loops on a bounded interval sample."""
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    fr = O.Frags(st, sp, mq)
+    fr.max_len = min(fr.max_len, 600)
+    s_all, e_all = make_intervals()
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(len(s_all))
+
+    def run(idx):
+        t0 = time.perf_counter()
+        out, off = O.wps_intervals(fr, s_all[idx], e_all[idx], CONTIG_LEN, WINDOW, MIN_LEN, MAX_LEN, MAPQ, threads=cores)
+        cov = O.interval_coverage(fr, s_all[idx], e_all[idx], None, None, "midpoint", MAPQ, threads=cores)
+        return time.perf_counter() - t0, int(off[-1]), int(cov.sum())
+
+    probe = perm[: max(4 * cores, 64)]
+    t_probe, pos_probe, _ = run(probe)
+    n = int(min(len(perm), max(len(probe), len(probe) * target_s / max(t_probe, 1e-6))))
+    idx = perm[:n]
+    t, pos, _ = run(idx)
+    pos_per_s = pos / t
+    frag_per_s = pos_per_s * (len(st) / CONTIG_LEN)
+    return {"value": frag_per_s, "unit": UNIT, "cores": cores, "kind": "port",
+            "positions_per_sec": pos_per_s, "seconds": t,
+            "sample": f"{n} random 5-kb intervals ({pos} positions) of the same workload: brute-force WPS "
+                      f"(reference frag/_wps.py:176-188 loops) + per-interval coverage, OpenMP over intervals "
+                      f"like the reference's Pool; fragments/s = positions/s x fragments/position of the workload"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from finaletoolkit_b200.synth import synth_fragments
+    t0 = time.time()
+    st, sp, mq, _ = synth_fragments(CONTIG_LEN, N_FRAG, 0)
+    log(f"[reference] synthesised {N_FRAG} fragments in {time.time() - t0:.1f}s")
+    per_step = float(os.environ.get("FTK_BENCH_REF_STEP_S", 2.0))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_sample_rate(st, sp, mq, per_step, seed=i)
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    ms = float(np.mean([r["seconds"] for r in vals]) * 1e3)
+    base = dict(vals[-1]); base["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "each step = a bounded random sample of the workload's intervals"},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from finaletoolkit_b200 import device as D
+    from finaletoolkit_b200.synth import synth_fragments
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    D.require_cuda(dev)
+
+    t0 = time.time()
+    st, sp, mq, sd = synth_fragments(CONTIG_LEN, N_FRAG, rank)
+    log(f"[rank {rank}] synthesised {N_FRAG} fragments in {time.time() - t0:.1f}s")
+    # pinned host columns: the form the host decoder hands over
+    h_st = torch.from_numpy(st).pin_memory()
+    h_sp = torch.from_numpy(sp).pin_memory()
+    h_mq = torch.from_numpy(mq).pin_memory()
+    frags = D.ContigFragments(h_st.to(dev), h_sp.to(dev), h_mq.to(dev), None, device=dev, max_len=600)
+
+    ivl_s, ivl_e = make_intervals()
+    plan = D.WpsPlan(ivl_s, ivl_e, CONTIG_LEN, MAX_LEN, dev)
+    cov_set = D.IntervalSet(ivl_s.tolist(), ivl_e.tolist(), dev)
+    all_set = D.IntervalSet([0], [None], dev)
+    n_bins = frags.max_len + 1
+    wps_out = torch.empty(plan.n_positions, dtype=torch.int32, device=dev)
+    cov_out = torch.zeros(cov_set.n, dtype=torch.int64, device=dev)
+    tot_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    hist_out = torch.zeros((1, n_bins), dtype=torch.int64, device=dev)
+    launches_per_step = 6
+
+    def step(ev=None):
+        if ev is not None:
+            ev[0].record()
+        plan.ranges(frags, WINDOW)
+        if ev is not None:
+            ev[1].record()
+        plan.run(frags, WINDOW, MIN_LEN, MAX_LEN, MAPQ, out=wps_out, ranges_ready=True)
+        if ev is not None:
+            ev[2].record()
+        cov_out.zero_(); tot_out.zero_(); hist_out.zero_()
+        D.interval_hist(frags, intersect_policy="midpoint", quality_threshold=MAPQ, ivl_set=cov_set,
+                        out=(cov_out, None, None))
+        D.interval_hist(frags, intersect_policy="midpoint", quality_threshold=MAPQ, n_bins=n_bins, pooled=True,
+                        ivl_set=all_set, out=(tot_out, hist_out, None))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- device-resident timed region
+    K = args.steps
+    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0.record()
+    for k in range(K):
+        step(kev[k])
+    e1.record()
+    barrier()
+    clocks = sampler.finish()
+    ms_total = e0.elapsed_time(e1)
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_total = float(t_ms.item())
+    ms_step = ms_total / K
+    wps_ms = float(np.mean([kev[k][1].elapsed_time(kev[k][2]) for k in range(K)]))
+    rng_ms = float(np.mean([kev[k][0].elapsed_time(kev[k][1]) for k in range(K)]))
+    value = world * N_FRAG / (ms_step * 1e-3)
+    pos_per_s = world * plan.n_positions / (ms_step * 1e-3)
+
+    # ---- end-to-end: pinned host columns -> H2D -> kernels -> D2H of every result
+    d_st, d_sp, d_mq = frags.start, frags.stop, frags.mapq
+    h_wps = torch.empty(plan.n_positions, dtype=torch.int32).pin_memory()
+    h_cov = torch.empty(cov_set.n, dtype=torch.int64).pin_memory()
+    h_hist = torch.empty((1, n_bins), dtype=torch.int64).pin_memory()
+    h_tot = torch.empty(1, dtype=torch.int64).pin_memory()
+    h2d = h_st.numel() * 4 + h_sp.numel() * 4 + h_mq.numel()
+    d2h = h_wps.numel() * 4 + h_cov.numel() * 8 + h_hist.numel() * 8 + 8
+
+    def e2e_step():
+        d_st.copy_(h_st, non_blocking=True)
+        d_sp.copy_(h_sp, non_blocking=True)
+        d_mq.copy_(h_mq, non_blocking=True)
+        step()
+        h_wps.copy_(wps_out, non_blocking=True)
+        h_cov.copy_(cov_out, non_blocking=True)
+        h_hist.copy_(hist_out, non_blocking=True)
+        h_tot.copy_(tot_out, non_blocking=True)
+        torch.cuda.synchronize()  # the caller reads the results
+
+    E = max(3, min(K, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t_e0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(E):
+        e2e_step()
+    g1.record()
+    barrier()
+    e2e_ms = g0.elapsed_time(g1) / E
+    wall_ms = (time.perf_counter() - t_e0) * 1e3 / E
+    e2e_ms = max(e2e_ms, 0.0)
+    t_e = torch.tensor([max(e2e_ms, wall_ms * 0.0)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t_e.item())
+    e2e_value = world * N_FRAG / (e2e_ms * 1e-3)
+    checksum = int(h_wps.sum(dtype=torch.int64)) if rank == 0 else 0
+
+    if rank == 0:
+        peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        algo_bytes = 9 * N_FRAG + 4 * plan.n_positions
+        achieved = algo_bytes / (wps_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(REPO, "profiles", "wps_tile_kernel_ncu.json")
+        if os.path.exists(prof) and N_FRAG == 80_000_000:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "fragments_per_gpu": N_FRAG, "positions_per_gpu": plan.n_positions,
+                       "intervals_per_gpu": int(len(ivl_s)), "sharding": f"contig-per-rank x{world}",
+                       "l2": "no flush: per-step working set 1.7 GB >> 126 MB L2"},
+            "positions_per_sec": pos_per_s,
+            "roofline": {"bound": "hbm", "kernel": "wps_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": wps_ms, "ranges_prepass_ms": rng_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "steps": E},
+            "gpu_launches": launches_per_step * K, "clocks": clocks, "wps_checksum": checksum,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_sample_rate(st, sp, mq, float(os.environ.get("FTK_BENCH_CPU_S", 10.0)))
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

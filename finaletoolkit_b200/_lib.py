@@ -31,8 +31,9 @@ SYMBOLS = {
     "ftk_last_cuda_error": (c_char_p, []),
     "ftk_wps_plan_tiles": (c_int64, [_i64p, _i64p, _i64p, c_int64, c_int64, c_int32,
                                      _i32p, _i32p, _i32p, _i32p, _i64p]),
+    "ftk_wps_tile_ranges": (c_int, [_P, c_int64, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
     "ftk_wps_tiles_i32": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int64,
-                                  c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
+                                  c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
     "ftk_interval_hist_u64": (c_int, [_P, _P, _P, c_int64, c_int32, _P, _P, c_int64,
                                       c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                       _P, _P, _P, _P, _P]),

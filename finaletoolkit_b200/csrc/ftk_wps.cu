@@ -224,33 +224,59 @@ extern "C" int64_t ftk_wps_plan_tiles(const int64_t *ivl_start, const int64_t *i
     return n_tiles;
 }
 
+static int wps_check_args(const int32_t *frag_start, const int32_t *frag_stop, int64_t n_frag,
+                          const int32_t *tile_p0, const int32_t *tile_len, int64_t n_tiles,
+                          int32_t window_size, int32_t max_len, const int64_t *scratch) {
+    if (n_frag < 0 || n_tiles < 0 || window_size < 1) return FTK_E_INVALID;
+    if (!tile_p0 || !tile_len || !scratch) return FTK_E_INVALID;
+    if (n_frag > 0 && (!frag_start || !frag_stop)) return FTK_E_INVALID;
+    // the reference requires an integer max_length (frag/_wps.py:156 round(start - max_length))
+    if (max_len == FTK_NONE || max_len < 0) return FTK_E_INVALID;
+    if (n_tiles > INT32_MAX / 2) return FTK_E_RANGE;
+    return FTK_OK;
+}
+
+extern "C" int ftk_wps_tile_ranges(const int32_t *frag_start, int64_t n_frag,
+                                   const int32_t *tile_p0, const int32_t *tile_len, int64_t n_tiles,
+                                   int32_t window_size, int32_t max_len, int64_t *scratch,
+                                   ftk_stream_t stream_) {
+    using namespace ftk;
+    if (n_tiles == 0) return FTK_OK;
+    int rc = wps_check_args(frag_start, frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size, max_len, scratch);
+    if (rc != FTK_OK) return rc;
+    const bool odd = (window_size & 1) != 0;
+    const int a = odd ? (window_size - 1) / 2 : window_size / 2;
+    const int b = odd ? a : a - 1;
+    const int64_t n = 2 * n_tiles;
+    const int threads = 128;
+    wps_tile_ranges_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0,
+                             static_cast<cudaStream_t>(stream_)>>>(
+        frag_start, n_frag, tile_p0, tile_len, n_tiles, a, b, max_len, scratch);
+    FTK_CHECK_LAUNCH("wps_tile_ranges_kernel");
+    return FTK_OK;
+}
+
 extern "C" int ftk_wps_tiles_i32(const int32_t *frag_start, const int32_t *frag_stop,
                                  const uint8_t *frag_mapq, int64_t n_frag,
                                  const int32_t *tile_p0, const int32_t *tile_len,
                                  const int32_t *tile_mid_lo, const int32_t *tile_mid_hi,
                                  const int64_t *tile_out_off, int64_t n_tiles,
                                  int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
-                                 int64_t *scratch, int32_t *out, ftk_stream_t stream_) {
+                                 int32_t ranges_ready, int64_t *scratch, int32_t *out,
+                                 ftk_stream_t stream_) {
     using namespace ftk;
     if (n_tiles == 0) return FTK_OK;
-    if (n_frag < 0 || n_tiles < 0 || window_size < 1) return FTK_E_INVALID;
-    if (!tile_p0 || !tile_len || !tile_mid_lo || !tile_mid_hi || !tile_out_off || !scratch || !out)
-        return FTK_E_INVALID;
-    if (n_frag > 0 && (!frag_start || !frag_stop)) return FTK_E_INVALID;
-    // the reference requires an integer max_length (frag/_wps.py:156 round(start - max_length))
-    if (max_len == FTK_NONE || max_len < 0) return FTK_E_INVALID;
-    if (n_tiles > INT32_MAX) return FTK_E_RANGE;
+    int rc = wps_check_args(frag_start, frag_stop, n_frag, tile_p0, tile_len, n_tiles, window_size, max_len, scratch);
+    if (rc != FTK_OK) return rc;
+    if (!tile_mid_lo || !tile_mid_hi || !tile_out_off || !out) return FTK_E_INVALID;
+    if (!ranges_ready) {
+        rc = ftk_wps_tile_ranges(frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size, max_len, scratch, stream_);
+        if (rc != FTK_OK) return rc;
+    }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const bool odd = (window_size & 1) != 0;
     const int a = odd ? (window_size - 1) / 2 : window_size / 2;
     const int b = odd ? a : a - 1;
-    {
-        const int64_t n = 2 * n_tiles;
-        const int threads = 128;
-        wps_tile_ranges_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(
-            frag_start, n_frag, tile_p0, tile_len, n_tiles, a, b, max_len, scratch);
-        FTK_CHECK_LAUNCH("wps_tile_ranges_kernel");
-    }
     if (odd)
         wps_tile_kernel<true><<<(unsigned)n_tiles, kWpsThreads, 0, stream>>>(
             frag_start, frag_stop, frag_mapq, tile_p0, tile_len, tile_mid_lo, tile_mid_hi, tile_out_off,

@@ -11,7 +11,8 @@ import numpy as np
 
 from ._lib import FTK_NONE, FtkLibraryError, check, lib
 
-__all__ = ["ContigFragments", "WpsPlan", "require_cuda", "none_to_ftk"]
+__all__ = ["ContigFragments", "WpsPlan", "IntervalSet", "PackedContig", "interval_hist", "frag_lengths",
+           "end_motif_hist", "require_cuda", "none_to_ftk", "policy_code"]
 
 _torch = None
 
@@ -142,8 +143,16 @@ class WpsPlan:
         self.tile_out_off = _to_device(off, self.device, np.int64)
         self.scratch = t.empty(2 * max(self.n_tiles, 1), dtype=t.int64, device=self.device)
 
+    def ranges(self, frags: ContigFragments, window_size=120):
+        """Only the per-tile fragment-range prepass (lets a caller time the main kernel alone)."""
+        if self.n_tiles:
+            check(lib().ftk_wps_tile_ranges(frags.start.data_ptr(), frags.n, self.tile_p0.data_ptr(),
+                                            self.tile_len.data_ptr(), self.n_tiles, int(window_size),
+                                            self.max_length, self.scratch.data_ptr(), _stream_ptr(self.device)),
+                  "ftk_wps_tile_ranges")
+
     def run(self, frags: ContigFragments, window_size=120, min_length=120, max_length=180,
-            quality_threshold=30, out=None):
+            quality_threshold=30, out=None, ranges_ready=False):
         """Launch the WPS kernels on the current stream; returns int32[n_positions] (device)."""
         t = torch()
         if int(max_length) != self.max_length:
@@ -160,7 +169,8 @@ class WpsPlan:
             self.tile_p0.data_ptr(), self.tile_len.data_ptr(), self.tile_mid_lo.data_ptr(),
             self.tile_mid_hi.data_ptr(), self.tile_out_off.data_ptr(), self.n_tiles,
             int(window_size), none_to_ftk(min_length), int(max_length), int(quality_threshold),
-            self.scratch.data_ptr(), out.data_ptr(), _stream_ptr(self.device)), "ftk_wps_tiles_i32")
+            int(bool(ranges_ready)), self.scratch.data_ptr(), out.data_ptr(), _stream_ptr(self.device)),
+            "ftk_wps_tiles_i32")
         return out
 
 
@@ -195,32 +205,49 @@ def _ivl_to_device(ivl_start, ivl_stop, device):
     return _to_device(s, device, np.int32), _to_device(e, device, np.int32)
 
 
-def interval_hist(frags: ContigFragments, ivl_start, ivl_stop, intersect_policy="midpoint",
+class IntervalSet:
+    """Interval table of one contig resident in HBM (+ the per-interval range scratch)."""
+
+    def __init__(self, ivl_start, ivl_stop, device=None):
+        self.device = require_cuda(device)
+        self.n = len(ivl_start)
+        if self.n:
+            self.start, self.stop = _ivl_to_device(ivl_start, ivl_stop, self.device)
+        else:
+            self.start = self.stop = None
+        self.scratch = torch().empty(2 * max(self.n, 1), dtype=torch().int64, device=self.device)
+
+
+def interval_hist(frags: ContigFragments, ivl_start=None, ivl_stop=None, intersect_policy="midpoint",
                   min_length=None, max_length=None, quality_threshold=30, n_bins=0,
-                  pooled=False, first_seen=False):
+                  pooled=False, first_seen=False, ivl_set: IntervalSet | None = None, out=None):
     """Counts (and optional length histograms) of the fragment stream of each interval.
 
     Returns device tensors ``(counts int64[rows], hist int64[rows, n_bins] | None,
-    first int32[rows, n_bins] | None)``; rows = 1 when ``pooled``.
+    first int32[rows, n_bins] | None)``; rows = 1 when ``pooled``.  ``ivl_set`` /
+    ``out=(counts, hist, first)`` let a caller reuse device buffers (outputs accumulate).
     """
     t = torch()
     dev = frags.device
-    n_ivl = len(ivl_start)
+    if ivl_set is None:
+        ivl_set = IntervalSet(ivl_start, ivl_stop, dev)
+    n_ivl = ivl_set.n
     rows = 1 if pooled else n_ivl
-    counts = t.zeros(max(rows, 1), dtype=t.int64, device=dev)
-    hist = t.zeros((max(rows, 1), n_bins), dtype=t.int64, device=dev) if n_bins else None
-    first = (t.full((max(rows, 1), n_bins), 2 ** 31 - 1, dtype=t.int32, device=dev)
-             if (n_bins and first_seen) else None)
+    if out is not None:
+        counts, hist, first = out
+    else:
+        counts = t.zeros(max(rows, 1), dtype=t.int64, device=dev)
+        hist = t.zeros((max(rows, 1), n_bins), dtype=t.int64, device=dev) if n_bins else None
+        first = (t.full((max(rows, 1), n_bins), 2 ** 31 - 1, dtype=t.int32, device=dev)
+                 if (n_bins and first_seen) else None)
     if n_ivl == 0:
         return counts[:rows], hist, first
-    s_dev, e_dev = _ivl_to_device(ivl_start, ivl_stop, dev)
-    scratch = t.empty(2 * n_ivl, dtype=t.int64, device=dev)
     fs, fe, mq = frags.ptrs()
     check(lib().ftk_interval_hist_u64(
-        fs, fe, mq, frags.n, frags.max_len, s_dev.data_ptr(), e_dev.data_ptr(), n_ivl,
+        fs, fe, mq, frags.n, frags.max_len, ivl_set.start.data_ptr(), ivl_set.stop.data_ptr(), n_ivl,
         policy_code(intersect_policy), none_to_ftk(min_length), none_to_ftk(max_length),
         int(quality_threshold), int(n_bins), int(bool(pooled)), _splits_for(n_ivl, frags.n),
-        scratch.data_ptr(), counts.data_ptr(), 0 if hist is None else hist.data_ptr(),
+        ivl_set.scratch.data_ptr(), counts.data_ptr(), 0 if hist is None else hist.data_ptr(),
         0 if first is None else first.data_ptr(), _stream_ptr(dev)), "ftk_interval_hist_u64")
     return counts[:rows], hist, first
 

@@ -74,14 +74,22 @@ int64_t ftk_wps_plan_tiles(const int64_t *ivl_start, const int64_t *ivl_stop,
                            int32_t *tile_mid_lo, int32_t *tile_mid_hi,
                            int64_t *tile_out_off);
 
-/* scratch_dev: int64[2 * n_tiles] (per-tile fragment index range). */
+/* Per-tile fragment index ranges (binary search over the sorted starts) into
+ * scratch_dev: int64[2 * n_tiles].  Called implicitly by ftk_wps_tiles_i32
+ * unless ranges_ready != 0. */
+int ftk_wps_tile_ranges(const int32_t *frag_start_dev, int64_t n_frag,
+                        const int32_t *tile_p0_dev, const int32_t *tile_len_dev, int64_t n_tiles,
+                        int32_t window_size, int32_t max_len, int64_t *scratch_dev,
+                        ftk_stream_t stream);
+
 int ftk_wps_tiles_i32(const int32_t *frag_start_dev, const int32_t *frag_stop_dev,
                       const uint8_t *frag_mapq_dev /* NULL = no mapq filter */, int64_t n_frag,
                       const int32_t *tile_p0_dev, const int32_t *tile_len_dev,
                       const int32_t *tile_mid_lo_dev, const int32_t *tile_mid_hi_dev,
                       const int64_t *tile_out_off_dev, int64_t n_tiles,
                       int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
-                      int64_t *scratch_dev, int32_t *out_dev, ftk_stream_t stream);
+                      int32_t ranges_ready, int64_t *scratch_dev, int32_t *out_dev,
+                      ftk_stream_t stream);
 
 /* ------------------------------------------- coverage / fragment lengths
  * Fragment stream of a region (S, E) - FTK_NONE = None - exactly as the
