@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8
 
 __all__ = ["lib", "check", "FtkLibraryError", "FTK_NONE", "SO_PATH", "SYMBOLS"]
 
-SO_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libftk_b200.so")
+SO_PATH = os.environ.get("FTK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libftk_b200.so")
 FTK_NONE = -(2 ** 31)
 
 
@@ -42,6 +42,11 @@ SYMBOLS = {
     "ftk_end_motif_hist_u64": (c_int, [_P, _P, _P, _P, c_int64, c_int32, _P, _P, c_int64,
                                        _P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32,
                                        _P, _P, _P, _P]),
+    "ftk_adjust_edge_shift_f64": (c_int, [_P, _P, c_int32, c_int32, _P, _P]),
+    "ftk_adjust_wps_f64": (c_int, [_P, _P, _P, _P, _P, c_int32, c_int64, c_int32, c_int32, c_int32,
+                                   c_int32, c_int32, _P, _P, _P, _P, _P, _P]),
+    "ftk_adjust_wps_generic_f64": (c_int, [_P, _P, _P, _P, _P, c_int32, _P, c_int64, c_int32, c_int32,
+                                           c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -25,18 +25,37 @@ struct Pred {
     int policy, min_len, max_len, min_mapq;
 };
 
-// Stream membership of one fragment for region [S, E) (FTK_NONE = unbounded).
-__device__ __forceinline__ bool frag_in_stream(int fs, int fe, int q, int S, int E, const Pred &p) {
-    const int L = fe - fs;
-    if (q < p.min_mapq || L < 0 || !frag_len_ok(L, p.min_len, p.max_len)) return false;
-    // tabix fetch(contig, S, E): rec.stop > start (None -> 0) and rec.start < stop
-    const bool overlap = (fe > (S == FTK_NONE ? 0 : S)) && (E == FTK_NONE || fs < E);
-    if (!overlap) return false;
-    if (p.policy == FTK_POLICY_MIDPOINT) {
-        const int mid = fs + (L >> 1);
-        return (S == FTK_NONE || mid >= S) && (E == FTK_NONE || mid < E);
+// Stream membership of one fragment for region [S, E) (FTK_NONE = unbounded), with the
+// None handling and the length window folded into per-CTA constants:
+//   tabix fetch(contig, S, E): rec.stop > start (None -> 0) and rec.start < stop
+//   length filter inclusive; midpoint policy mid in [S, E); "any" = the overlap test itself
+struct Stream {
+    int len_lo; unsigned len_span; bool len_any;
+    int min_mapq; int s_over; int e_eff; int s_mid; bool midpoint;
+    __device__ __forceinline__ Stream(int S, int E, const Pred &p) {
+        len_lo = (p.min_len == FTK_NONE || p.min_len < 0) ? 0 : p.min_len;
+        const int hi = (p.max_len == FTK_NONE) ? INT32_MAX : p.max_len;
+        len_any = hi >= len_lo;
+        len_span = len_any ? (unsigned)(hi - len_lo) : 0u;
+        min_mapq = p.min_mapq;
+        s_over = (S == FTK_NONE) ? 0 : S;
+        s_mid = (S == FTK_NONE) ? INT32_MIN : S;
+        e_eff = (E == FTK_NONE) ? INT32_MAX : E;
+        midpoint = p.policy == FTK_POLICY_MIDPOINT;
     }
-    return true;  // "any": the overlap test is the policy
+    __device__ __forceinline__ bool operator()(int fs, int fe, int q) const {
+        const int L = fe - fs;
+        bool ok = (q >= min_mapq) && ((unsigned)(L - len_lo) <= len_span) && (fe > s_over) && (fs < e_eff);
+        if (midpoint) {
+            const int mid = fs + (L >> 1);
+            ok = ok && (mid >= s_mid) && (mid < e_eff);
+        }
+        return ok && len_any;
+    }
+};
+
+__device__ __forceinline__ bool frag_in_stream(int fs, int fe, int q, int S, int E, const Pred &p) {
+    return Stream(S, E, p)(fs, fe, q);
 }
 
 // Candidate index range of each interval: a superset of its stream.
@@ -86,34 +105,72 @@ interval_hist_kernel(const int32_t *__restrict__ frag_start, const int32_t *__re
         __syncthreads();
     }
 
-    unsigned long long my_count = 0;
-    int fs_r[kHistUnroll], fe_r[kHistUnroll], q_r[kHistUnroll];
-    for (int64_t i0 = lo + tid; i0 < hi; i0 += (int64_t)kHistUnroll * kHistThreads) {
+    const Stream in_stream(S, E, pred);
+    unsigned my_count32 = 0;  // a CTA slice never holds 2^32 fragments (n_frag <= INT32_MAX)
+    auto visit = [&](int fs, int fe, int q, int idx) {
+        if (!in_stream(fs, fe, q)) return;
+        ++my_count32;
+        if (HIST) {
+            const int L = fe - fs;
+            if (L < kHistSmemBins) {
+                atomicAdd(&s_cnt[L], 1);
+                if (want_first) atomicMin(&s_first[L], idx);
+            } else if (L < n_bins) {
+                atomicAdd(&hist[row * n_bins + L], 1ull);
+                if (want_first) atomicMin(&first_seen[row * n_bins + L], idx);
+            }
+        }
+    };
+    // 128-bit streaming loads: the slice is widened to 16-byte boundaries on the left (fragments
+    // outside [lo, hi) are masked by index), 4 fragments per lane per load, kHistUnroll loads in flight.
+    const int64_t lo_al = lo & ~(int64_t)3;
+    const int skip = (int)(lo - lo_al);
+    const int cnt = (hi > lo) ? (int)(hi - lo_al) : 0;
+    const int nvec = cnt >> 2;
+    const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(frag_start + lo_al);
+    const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(frag_stop + lo_al);
+    const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(frag_mapq ? frag_mapq + lo_al : nullptr);
+    const int base_idx = (int)lo_al;
+    for (int v0 = tid; v0 < nvec; v0 += kHistUnroll * kHistThreads) {
+        int4 s4[kHistUnroll], e4[kHistUnroll];
+        uchar4 q4[kHistUnroll];
 #pragma unroll
         for (int u = 0; u < kHistUnroll; ++u) {
-            const int64_t i = i0 + (int64_t)u * kHistThreads;
-            const bool in = i < hi;
-            fs_r[u] = in ? __ldcs(frag_start + i) : 0;
-            fe_r[u] = in ? __ldcs(frag_stop + i) : 0;
-            q_r[u] = in ? (frag_mapq ? (int)__ldcs(frag_mapq + i) : 255) : -1;
+            const int v = v0 + u * kHistThreads;
+            if (v < nvec) {
+                s4[u] = __ldcs(vs + v);
+                e4[u] = __ldcs(ve + v);
+                q4[u] = vq ? __ldcs(vq + v) : make_uchar4(255, 255, 255, 255);
+            } else {
+                s4[u] = make_int4(0, 0, 0, 0);
+                e4[u] = make_int4(-1, -1, -1, -1);  // L < 0: never in a stream
+                q4[u] = make_uchar4(0, 0, 0, 0);
+            }
         }
 #pragma unroll
         for (int u = 0; u < kHistUnroll; ++u) {
-            if (!frag_in_stream(fs_r[u], fe_r[u], q_r[u], S, E, pred)) continue;
-            ++my_count;
-            if (HIST) {
-                const int L = fe_r[u] - fs_r[u];
-                const int idx = (int)(i0 + (int64_t)u * kHistThreads);
-                if (L < kHistSmemBins) {
-                    atomicAdd(&s_cnt[L], 1);
-                    if (want_first) atomicMin(&s_first[L], idx);
-                } else if (L < n_bins) {
-                    atomicAdd(&hist[row * n_bins + L], 1ull);
-                    if (want_first) atomicMin(&first_seen[row * n_bins + L], idx);
-                }
+            const int v = v0 + u * kHistThreads;
+            const int i = v * 4;
+            if (v == 0 && skip) {  // the widened head: mask fragments left of lo
+                if (skip <= 0) visit(s4[u].x, e4[u].x, q4[u].x, base_idx + i);
+                if (skip <= 1) visit(s4[u].y, e4[u].y, q4[u].y, base_idx + i + 1);
+                if (skip <= 2) visit(s4[u].z, e4[u].z, q4[u].z, base_idx + i + 2);
+                visit(s4[u].w, e4[u].w, q4[u].w, base_idx + i + 3);
+            } else {
+                visit(s4[u].x, e4[u].x, q4[u].x, base_idx + i);
+                visit(s4[u].y, e4[u].y, q4[u].y, base_idx + i + 1);
+                visit(s4[u].z, e4[u].z, q4[u].z, base_idx + i + 2);
+                visit(s4[u].w, e4[u].w, q4[u].w, base_idx + i + 3);
             }
         }
     }
+    {   // tail: at most 3 fragments (and the head mask when the whole slice is shorter than a vector)
+        const int i = nvec * 4 + tid;
+        if (i < cnt && i >= skip)
+            visit(__ldcs(frag_start + lo_al + i), __ldcs(frag_stop + lo_al + i),
+                  frag_mapq ? (int)__ldcs(frag_mapq + lo_al + i) : 255, base_idx + i);
+    }
+    unsigned long long my_count = my_count32;
 
     // block reduction of the count -> one 64-bit atomic per CTA
 #pragma unroll
@@ -136,6 +193,72 @@ interval_hist_kernel(const int32_t *__restrict__ frag_start, const int32_t *__re
             }
         }
     }
+}
+
+// Counts only (coverage): one WARP per (interval, split).  A 5-kb interval at 30x holds
+// ~1600 candidates - far too few to amortise a CTA's launch, barrier and reduction latency -
+// so eight independent warps share a CTA, each streaming its own slice with 128-bit loads
+// (kHistUnroll x 3 in flight per lane) and finishing with a shuffle reduction + one atomic.
+__global__ void __launch_bounds__(kHistThreads, 4)
+interval_count_warp_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
+                           const uint8_t *__restrict__ frag_mapq,
+                           const int32_t *__restrict__ ivl_start, const int32_t *__restrict__ ivl_stop,
+                           const int64_t *__restrict__ ranges, Pred pred, int pooled, int splits,
+                           int64_t n_units, unsigned long long *__restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int64_t unit = (int64_t)blockIdx.x * (kHistThreads / 32) + (threadIdx.x >> 5);
+    if (unit >= n_units) return;
+    const int64_t ivl = unit / splits;
+    const int split = (int)(unit % splits);
+    const int S = __ldg(ivl_start + ivl), E = __ldg(ivl_stop + ivl);
+    const int64_t lo_all = __ldg(ranges + 2 * ivl), hi_all = __ldg(ranges + 2 * ivl + 1);
+    int64_t chunk = (hi_all - lo_all + splits - 1) / splits;
+    chunk = (chunk + 3) & ~(int64_t)3;
+    const int64_t lo = lo_all + (int64_t)split * chunk;
+    const int64_t hi = min(hi_all, lo + chunk);
+    const Stream in_stream(S, E, pred);
+
+    const int64_t lo_al = lo & ~(int64_t)3;
+    const int skip = (int)(lo - lo_al);
+    const int cnt = (hi > lo) ? (int)(hi - lo_al) : 0;
+    const int nvec = cnt >> 2;
+    const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(frag_start + lo_al);
+    const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(frag_stop + lo_al);
+    const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(frag_mapq ? frag_mapq + lo_al : nullptr);
+    unsigned c = 0;
+    for (int v0 = lane; v0 < nvec; v0 += kHistUnroll * 32) {
+        int4 s4[kHistUnroll], e4[kHistUnroll];
+        uchar4 q4[kHistUnroll];
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; ++u) {
+            const int v = v0 + u * 32;
+            if (v < nvec) {
+                s4[u] = __ldcs(vs + v);
+                e4[u] = __ldcs(ve + v);
+                q4[u] = vq ? __ldcs(vq + v) : make_uchar4(255, 255, 255, 255);
+            } else {
+                s4[u] = make_int4(0, 0, 0, 0);
+                e4[u] = make_int4(-1, -1, -1, -1);  // L < 0: never in a stream
+                q4[u] = make_uchar4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; ++u) {
+            const bool head = (v0 + u * 32 == 0);  // the widened head: mask fragments left of lo
+            c += (!(head && skip > 0)) && in_stream(s4[u].x, e4[u].x, q4[u].x);
+            c += (!(head && skip > 1)) && in_stream(s4[u].y, e4[u].y, q4[u].y);
+            c += (!(head && skip > 2)) && in_stream(s4[u].z, e4[u].z, q4[u].z);
+            c += in_stream(s4[u].w, e4[u].w, q4[u].w);
+        }
+    }
+    {   // tail: at most 3 fragments
+        const int i = nvec * 4 + lane;
+        if (i < cnt && i >= skip)
+            c += in_stream(__ldcs(frag_start + lo_al + i), __ldcs(frag_stop + lo_al + i),
+                           frag_mapq ? (int)__ldcs(frag_mapq + lo_al + i) : 255);
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0 && c) atomicAdd(&counts[pooled ? 0 : ivl], (unsigned long long)c);
 }
 
 // ---- raw lengths in stream order (frag_length): count / scan / scatter
@@ -290,9 +413,12 @@ extern "C" int ftk_interval_hist_u64(const int32_t *frag_start, const int32_t *f
     if (n_bins > 0)
         interval_hist_kernel<true><<<grid, kHistThreads, 0, stream>>>(
             frag_start, frag_stop, frag_mapq, ivl_start, ivl_stop, scratch, pred, n_bins, pooled, splits, c, h, first_seen);
-    else
-        interval_hist_kernel<false><<<grid, kHistThreads, 0, stream>>>(
-            frag_start, frag_stop, frag_mapq, ivl_start, ivl_stop, scratch, pred, 0, pooled, splits, c, nullptr, nullptr);
+    else {
+        const int64_t n_units = n_ivl * (int64_t)splits;
+        const int per_cta = kHistThreads / 32;
+        interval_count_warp_kernel<<<(unsigned)((n_units + per_cta - 1) / per_cta), kHistThreads, 0, stream>>>(
+            frag_start, frag_stop, frag_mapq, ivl_start, ivl_stop, scratch, pred, pooled, splits, n_units, c);
+    }
     FTK_CHECK_LAUNCH("interval_hist_kernel");
     return FTK_OK;
 }

@@ -24,7 +24,6 @@ constexpr int kWpsWarps = kWpsThreads / 32;
 constexpr int kWpsCap = 5120;                    // smem slots per tile
 constexpr int kWpsIters = kWpsCap / (kWpsThreads * 4);  // int4 groups per lane
 constexpr int kWpsSpan = kWpsIters * 128;        // positions per warp
-constexpr int kWpsUnroll = 4;                    // fragment loads in flight per thread (x3 columns)
 static_assert(kWpsIters * kWpsThreads * 4 == kWpsCap, "tile must split evenly");
 static_assert(FTK_WPS_TILE < kWpsCap, "one guard slot for odd windows");
 
@@ -50,87 +49,81 @@ __global__ void wps_tile_ranges_kernel(const int32_t *__restrict__ frag_start, i
     ranges[t] = lower_bound(frag_start, n_frag, key);
 }
 
+// ---------------------------------------------------------------------------
+// Pieces shared by the two tile kernels
+// ---------------------------------------------------------------------------
+struct WpsParams {
+    int window, a, b;       // window [c-a, c+b]
+    int len_lo;             // fragment-length window as an unsigned range test
+    unsigned len_span;
+    int min_mapq;
+    int max_len;
+};
+
+struct TileCtx {
+    int p0, len, mid_lo, g0, glen;
+    int eb;                 // b + g0: first event slot of a fragment = fs - eb
+    unsigned mid_span;
+    bool need_mid;          // tile-uniform: the midpoint test can exclude a contributing fragment
+};
+
 template <bool ODD>
-__global__ void __launch_bounds__(kWpsThreads)
-wps_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
-                const uint8_t *__restrict__ frag_mapq,
-                const int32_t *__restrict__ tile_p0, const int32_t *__restrict__ tile_len,
-                const int32_t *__restrict__ tile_mid_lo, const int32_t *__restrict__ tile_mid_hi,
-                const int64_t *__restrict__ tile_out_off, const int64_t *__restrict__ ranges,
-                int window, int a, int b, int min_len, int max_len, int min_mapq,
-                int32_t *__restrict__ out) {
-    __shared__ __align__(16) int D[kWpsCap];
-    __shared__ int warp_tot[kWpsWarps];
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int64_t tile = blockIdx.x;
-
-    const int p0 = tile_p0[tile];
-    const int len = tile_len[tile];
-    const int mid_lo = tile_mid_lo[tile];
-    const int mid_hi = tile_mid_hi[tile];
-    const int64_t lo = ranges[2 * tile];
-    const int64_t hi = ranges[2 * tile + 1];
+__device__ __forceinline__ TileCtx make_tile_ctx(const WpsParams &P, int p0, int len, int mid_lo, int mid_hi) {
+    TileCtx t;
+    t.p0 = p0; t.len = len; t.mid_lo = mid_lo;
+    t.mid_span = (mid_hi > mid_lo) ? (unsigned)(mid_hi - mid_lo) : 0u;
     // grid of the symmetric-window score G: one extra slot on the left for odd W
-    const int g0 = ODD ? p0 - 1 : p0;
-    const int glen = ODD ? len + 1 : len;
+    t.g0 = ODD ? p0 - 1 : p0;
+    t.glen = ODD ? len + 1 : len;
+    t.eb = P.b + t.g0;
+    // The interval's padded fetch window [S-max_len, E+max_len) (frag/_wps.py:156-157) contains
+    // the midpoint of every fragment that can touch the interval whenever W + 2 <= max_len, so
+    // the test is only needed for wide windows or where the window was clamped to the contig.
+    t.need_mid = (P.window + 2 > P.max_len) || ((long long)mid_hi < (long long)p0 + len + P.max_len) ||
+                 ((long long)mid_lo > (long long)p0 - P.max_len);
+    return t;
+}
 
-    // One fragment's events -> shared atomics (2, or 4 when L > W).
-    auto scatter = [&](int fs, int fe, int q) {
-        const int L = fe - fs;
-        const int mid = fs + (L >> 1);  // (fs+fe)//2 for L >= 0
-        const bool pass = (q >= min_mapq) && (L >= 0) && frag_len_ok(L, min_len, max_len) &&
-                          (mid >= mid_lo) && (mid < mid_hi);
-        if (!pass) return;
-        const int e_last = fe + a + 1 - g0;  // +1
-        const int e_first = fs - b - g0;     // -1
-        if (e_last <= 0 || e_first >= glen) return;  // cancels on slot 0 / entirely right of the tile
-        atomicAdd(&D[max(e_first, 0)], -1);
-        if (e_last < glen) atomicAdd(&D[e_last], 1);
-        if (L > window) {
-            const int e1 = fs + a + 1 - g0;  // +2
-            const int e2 = fe - b - g0;      // -2
-            if (e1 < glen) atomicAdd(&D[max(e1, 0)], 2);
-            if (e2 < glen) atomicAdd(&D[max(e2, 0)], -2);
+// One fragment's events -> shared atomics (2, or 4 when L > W).  The predicate is the
+// reference's (utils/_frag_generator.py:117-123; mapq io/alignment.py:291) as unsigned range
+// tests: min_len <= L <= max_len and mid_lo <= (fs+fe)//2 < mid_hi (L < 0 never passes).
+// Event slots relative to the tile: e0 = fs-b-g0 (-1), e0+W (+2), e0+L (-2), e0+L+W (+1).
+__device__ __forceinline__ void wps_scatter(int *__restrict__ D, const WpsParams &P, const TileCtx &T,
+                                            int fs, int fe, int q) {
+    const int L = fe - fs;
+    bool pass = (q >= P.min_mapq) && ((unsigned)(L - P.len_lo) <= P.len_span);
+    if (T.need_mid) pass = pass && ((unsigned)(fs + (L >> 1) - T.mid_lo) < T.mid_span);
+    if (!pass) return;
+    const int e0 = fs - T.eb;
+    const int e3 = e0 + L + P.window;
+    if (e0 >= 0 && e3 < T.glen) {  // interior fragment (97 % at 30x): no clamping
+        int *__restrict__ p = D + e0;
+        atomicAdd(p, -1);
+        atomicAdd(p + (L + P.window), 1);
+        if (L > P.window) {
+            atomicAdd(p + P.window, 2);
+            atomicAdd(p + L, -2);
         }
-    };
-
-    // ---- software-pipelined scatter: kWpsUnroll x 3 coalesced streaming loads stay in
-    // flight per thread while the previous batch is turned into shared atomics; the
-    // first batch is issued before the tile is zeroed so its latency hides behind that.
-    int fs_r[kWpsUnroll], fe_r[kWpsUnroll], q_r[kWpsUnroll];
-    auto load_batch = [&](int64_t i0) {
-#pragma unroll
-        for (int u = 0; u < kWpsUnroll; ++u) {
-            const int64_t i = i0 + (int64_t)u * kWpsThreads;
-            const bool in = i < hi;
-            fs_r[u] = in ? __ldcs(frag_start + i) : 0;
-            fe_r[u] = in ? __ldcs(frag_stop + i) : 0;
-            q_r[u] = in ? (frag_mapq ? (int)__ldcs(frag_mapq + i) : 255) : -1;  // -1 never passes
-        }
-    };
-    int64_t i0 = lo + tid;
-    load_batch(i0);
-
-#pragma unroll
-    for (int j = 0; j < kWpsIters; ++j)
-        reinterpret_cast<int4 *>(D)[j * kWpsThreads + tid] = make_int4(0, 0, 0, 0);
-    __syncthreads();
-
-    while (i0 < hi) {  // block-uniform trip count not required: no barrier inside
-        int fs_c[kWpsUnroll], fe_c[kWpsUnroll], q_c[kWpsUnroll];
-#pragma unroll
-        for (int u = 0; u < kWpsUnroll; ++u) { fs_c[u] = fs_r[u]; fe_c[u] = fe_r[u]; q_c[u] = q_r[u]; }
-        i0 += (int64_t)kWpsUnroll * kWpsThreads;
-        if (i0 < hi) load_batch(i0);
-#pragma unroll
-        for (int u = 0; u < kWpsUnroll; ++u) scatter(fs_c[u], fe_c[u], q_c[u]);
+        return;
     }
-    __syncthreads();
+    if (e3 <= 0 || e0 >= T.glen) return;  // cancels on slot 0 / entirely right of the tile
+    atomicAdd(&D[max(e0, 0)], -1);
+    if (e3 < T.glen) atomicAdd(&D[e3], 1);
+    if (L > P.window) {
+        const int e1 = e0 + P.window, e2 = e0 + L;
+        if (e1 < T.glen) atomicAdd(&D[max(e1, 0)], 2);
+        if (e2 < T.glen) atomicAdd(&D[max(e2, 0)], -2);
+    }
+}
 
-    // ---- block prefix scan: lane owns int4 groups, warp owns a contiguous span
+// Block prefix scan of D and the store of the tile.  Lane owns int4 groups, warp owns a
+// contiguous span, one barrier for the warp totals.  `sync` = the CTA-wide (or
+// consumer-wide) barrier of the calling kernel.
+template <bool ODD, typename Sync>
+__device__ __forceinline__ void wps_scan_store(int *__restrict__ D, int *__restrict__ warp_tot,
+                                               const WpsParams &P, const TileCtx &T,
+                                               int32_t *__restrict__ dst, int tid, Sync sync) {
+    const int lane = tid & 31, warp = tid >> 5;
     int4 v[kWpsIters];
     int carry = 0;
     const int span0 = warp * kWpsSpan;
@@ -150,25 +143,24 @@ wps_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restric
         carry += __shfl_sync(0xffffffffu, t, 31);
     }
     if (lane == 0) warp_tot[warp] = carry;
-    __syncthreads();
+    sync();
     int offset = 0;
 #pragma unroll
     for (int w = 0; w < kWpsWarps; ++w) offset += (w < warp) ? warp_tot[w] : 0;
 
-    int32_t *__restrict__ dst = out + tile_out_off[tile];
     if (!ODD) {
         const bool aligned = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
 #pragma unroll
         for (int j = 0; j < kWpsIters; ++j) {
             const int base = span0 + j * 128 + lane * 4;
             const int4 r = make_int4(v[j].x + offset, v[j].y + offset, v[j].z + offset, v[j].w + offset);
-            if (aligned && base + 3 < len) {
+            if (aligned && base + 3 < T.len) {
                 st_stream4(reinterpret_cast<int4 *>(dst + base), r);
             } else {
-                if (base + 0 < len) dst[base + 0] = r.x;
-                if (base + 1 < len) dst[base + 1] = r.y;
-                if (base + 2 < len) dst[base + 2] = r.z;
-                if (base + 3 < len) dst[base + 3] = r.w;
+                if (base + 0 < T.len) dst[base + 0] = r.x;
+                if (base + 1 < T.len) dst[base + 1] = r.y;
+                if (base + 2 < T.len) dst[base + 2] = r.z;
+                if (base + 3 < T.len) dst[base + 3] = r.w;
             }
         }
     } else {
@@ -179,11 +171,269 @@ wps_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restric
             *reinterpret_cast<int4 *>(&D[base]) =
                 make_int4(v[j].x + offset, v[j].y + offset, v[j].z + offset, v[j].w + offset);
         }
-        __syncthreads();
-        for (int k = tid; k < len; k += kWpsThreads) {
-            const int c = p0 + k;
-            dst[k] = D[c - ((c - a) & 1) - g0];
+        sync();
+        for (int k = tid; k < T.len; k += kWpsThreads) {
+            const int c = T.p0 + k;
+            dst[k] = D[c - ((c - P.a) & 1) - T.g0];
         }
+        sync();  // D is recycled by the caller
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Kernel A ("direct"): one CTA per tile, fragments streamed with 128-bit loads.
+// Kept as the simple variant; the pipelined kernel below is the default.
+// ---------------------------------------------------------------------------
+template <bool ODD>
+__global__ void __launch_bounds__(kWpsThreads)
+wps_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
+                const uint8_t *__restrict__ frag_mapq,
+                const int32_t *__restrict__ tile_p0, const int32_t *__restrict__ tile_len,
+                const int32_t *__restrict__ tile_mid_lo, const int32_t *__restrict__ tile_mid_hi,
+                const int64_t *__restrict__ tile_out_off, const int64_t *__restrict__ ranges,
+                WpsParams P, int32_t *__restrict__ out) {
+    __shared__ __align__(16) int D[kWpsCap];
+    __shared__ int warp_tot[kWpsWarps];
+
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const TileCtx T = make_tile_ctx<ODD>(P, tile_p0[tile], tile_len[tile], tile_mid_lo[tile], tile_mid_hi[tile]);
+    const int64_t lo = ranges[2 * tile];
+    const int64_t hi = ranges[2 * tile + 1];
+
+    // The fragment slice [lo, hi) is widened to a 16-byte boundary on the left (extra
+    // fragments are harmless: the range is only a superset) so every lane streams 4
+    // fragments per 128-bit load: 3 loads per 4 fragments, 32-bit indexing.
+    const int64_t lo_al = lo & ~(int64_t)3;
+    const int cnt = (int)(hi - lo_al);
+    const int nvec = cnt >> 2;
+    const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(frag_start + lo_al);
+    const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(frag_stop + lo_al);
+    const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(frag_mapq ? frag_mapq + lo_al : nullptr);
+
+    // first batch of loads is issued before the tile is zeroed so its latency hides behind that
+    int4 s0 = make_int4(0, 0, 0, 0), e0 = make_int4(-1, -1, -1, -1);
+    uchar4 q0 = make_uchar4(255, 255, 255, 255);
+    if (tid < nvec) {
+        s0 = __ldcs(vs + tid);
+        e0 = __ldcs(ve + tid);
+        if (vq) q0 = __ldcs(vq + tid);
+    }
+#pragma unroll
+    for (int j = 0; j < kWpsIters; ++j)
+        reinterpret_cast<int4 *>(D)[j * kWpsThreads + tid] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+
+    for (int v = tid; v < nvec; v += kWpsThreads) {
+        const int4 s = s0, e = e0;
+        const uchar4 q = q0;
+        const int vn = v + kWpsThreads;
+        if (vn < nvec) {  // prefetch the next vector triple while this one turns into atomics
+            s0 = __ldcs(vs + vn);
+            e0 = __ldcs(ve + vn);
+            if (vq) q0 = __ldcs(vq + vn);
+        }
+        wps_scatter(D, P, T, s.x, e.x, q.x);
+        wps_scatter(D, P, T, s.y, e.y, q.y);
+        wps_scatter(D, P, T, s.z, e.z, q.z);
+        wps_scatter(D, P, T, s.w, e.w, q.w);
+    }
+    {   // tail: at most 3 fragments
+        const int i = nvec * 4 + tid;
+        if (i < cnt)
+            wps_scatter(D, P, T, __ldcs(frag_start + lo_al + i), __ldcs(frag_stop + lo_al + i),
+                        frag_mapq ? (int)__ldcs(frag_mapq + lo_al + i) : 255);
+    }
+    __syncthreads();
+    wps_scan_store<ODD>(D, warp_tot, P, T, out + tile_out_off[tile], tid, [] { __syncthreads(); });
+}
+
+// ---------------------------------------------------------------------------
+// Kernel B ("stream", default): persistent, warp-specialised, TMA-fed.
+//
+// grid = resident CTAs (SMs x kStreamCtasPerSm); each CTA walks tiles
+// blockIdx.x, +gridDim.x, ...  One producer warp runs ahead of eight consumer
+// warps: it reads the next tile's descriptor and fragment range and issues 1-D
+// bulk async copies (cp.async.bulk ... mbarrier::complete_tx::bytes, SASS UBLKCP)
+// of the start / stop / mapq slices into a 2-stage shared-memory ring.  The
+// consumers wait on the stage's "full" mbarrier, turn the staged fragments into
+// shared atomics, release the stage through its "empty" mbarrier, then scan and
+// store the tile - while the next tile's bytes are already in flight.  HBM
+// latency is therefore never exposed to the compute warps.
+// ---------------------------------------------------------------------------
+constexpr int kStreamFrags = 1920;        // fragments per stage (multiple of 16)
+constexpr int kStreamStages = 2;
+constexpr int kStreamCtasPerSm = 4;
+constexpr int kStreamThreads = kWpsThreads + 32;  // 8 consumer warps + 1 producer warp
+
+struct __align__(16) StreamDesc {
+    int tile;        // -1: no more work
+    int p0, len, mid_lo, mid_hi;
+    int n;           // staged fragments (multiple of 16, may be 0)
+    int first, last; // first / last chunk of its tile
+    long long out_off;
+    long long tail_lo, tail_hi;  // ragged end of the contig, read straight from global (rare)
+};
+
+struct __align__(128) StreamSmem {
+    int D[kWpsCap];
+    int start[kStreamStages][kStreamFrags];
+    int stop[kStreamStages][kStreamFrags];
+    unsigned char mapq[kStreamStages][kStreamFrags];
+    StreamDesc desc[kStreamStages];
+    unsigned long long full_bar[kStreamStages];
+    unsigned long long empty_bar[kStreamStages];
+    int warp_tot[kWpsWarps];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
+    const uint32_t addr = smem_u32(bar);
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(void *bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void *bar, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D TMA: global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() {
+    asm volatile("bar.sync 1, %0;" :: "n"(kWpsThreads) : "memory");
+}
+
+template <bool ODD>
+__global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
+wps_stream_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
+                  const uint8_t *__restrict__ frag_mapq, int64_t n_frag,
+                  const int32_t *__restrict__ tile_p0, const int32_t *__restrict__ tile_len,
+                  const int32_t *__restrict__ tile_mid_lo, const int32_t *__restrict__ tile_mid_hi,
+                  const int64_t *__restrict__ tile_out_off, const int64_t *__restrict__ ranges,
+                  int n_tiles, WpsParams P, int32_t *__restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StreamSmem &S = *reinterpret_cast<StreamSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStreamStages; ++s) {
+            mbar_init(&S.full_bar[s], 1);   // the producer's arrive(.expect_tx)
+            mbar_init(&S.empty_bar[s], 1);  // one elected consumer
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= kWpsThreads) {
+        // ===================== producer warp (one elected lane) =====================
+        if (tid == kWpsThreads) {
+            int stage = 0;
+            unsigned phase = 0;
+            const int64_t n16 = n_frag & ~(int64_t)15;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int64_t lo = ranges[2 * (int64_t)tile], hi = ranges[2 * (int64_t)tile + 1];
+                const int p0 = tile_p0[tile], len = tile_len[tile];
+                const int mlo = tile_mid_lo[tile], mhi = tile_mid_hi[tile];
+                const long long ooff = tile_out_off[tile];
+                // bulk copies need 16-byte aligned sources and sizes for all three columns
+                // (mapq is 1 byte wide): widen to multiples of 16 fragments - a superset is
+                // harmless - but never read past the last full 16-block of the arrays.
+                const int64_t lo16 = lo & ~(int64_t)15;
+                int64_t hi16 = (hi + 15) & ~(int64_t)15;
+                if (hi16 > n16) hi16 = n16;
+                if (hi16 < lo16) hi16 = lo16;
+                const int64_t t_lo = (hi16 > lo16) ? hi16 : lo16;
+                const bool has_tail = hi > t_lo;
+                const int64_t span = hi16 - lo16;
+                const int n_chunks = span > 0 ? (int)((span + kStreamFrags - 1) / kStreamFrags) : 1;
+                for (int c = 0; c < n_chunks; ++c) {
+                    mbar_wait(&S.empty_bar[stage], phase ^ 1u);
+                    const int64_t c0 = lo16 + (int64_t)c * kStreamFrags;
+                    const int n = (int)min((int64_t)kStreamFrags, hi16 - c0);
+                    StreamDesc &d = S.desc[stage];
+                    d.tile = tile; d.p0 = p0; d.len = len; d.mid_lo = mlo; d.mid_hi = mhi;
+                    d.n = n > 0 ? n : 0;
+                    d.first = (c == 0); d.last = (c == n_chunks - 1);
+                    d.out_off = ooff;
+                    d.tail_lo = (d.last && has_tail) ? t_lo : 0;
+                    d.tail_hi = (d.last && has_tail) ? hi : 0;
+                    if (n > 0) {
+                        const unsigned bytes = (unsigned)n * (frag_mapq ? 9u : 8u);
+                        mbar_arrive_expect_tx(&S.full_bar[stage], bytes);
+                        bulk_g2s(S.start[stage], frag_start + c0, (unsigned)n * 4u, &S.full_bar[stage]);
+                        bulk_g2s(S.stop[stage], frag_stop + c0, (unsigned)n * 4u, &S.full_bar[stage]);
+                        if (frag_mapq) bulk_g2s(S.mapq[stage], frag_mapq + c0, (unsigned)n, &S.full_bar[stage]);
+                    } else {
+                        mbar_arrive(&S.full_bar[stage]);
+                    }
+                    stage ^= 1;
+                    if (stage == 0) phase ^= 1u;
+                }
+            }
+            mbar_wait(&S.empty_bar[stage], phase ^ 1u);
+            S.desc[stage].tile = -1;
+            mbar_arrive(&S.full_bar[stage]);
+        }
+        return;
+    }
+
+    // ========================= consumer warps =========================
+    int stage = 0;
+    unsigned phase = 0;
+    TileCtx T = make_tile_ctx<ODD>(P, 0, 0, 0, 0);
+    for (;;) {
+        mbar_wait(&S.full_bar[stage], phase);
+        const StreamDesc d = S.desc[stage];
+        if (d.tile < 0) break;
+        if (d.first) {
+            T = make_tile_ctx<ODD>(P, d.p0, d.len, d.mid_lo, d.mid_hi);
+#pragma unroll
+            for (int j = 0; j < kWpsIters; ++j)
+                reinterpret_cast<int4 *>(S.D)[j * kWpsThreads + tid] = make_int4(0, 0, 0, 0);
+            consumer_sync();
+        }
+        const int nvec = d.n >> 2;
+        const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(S.start[stage]);
+        const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(S.stop[stage]);
+        const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(S.mapq[stage]);
+        for (int v = tid; v < nvec; v += kWpsThreads) {
+            const int4 s = vs[v], e = ve[v];
+            const uchar4 q = frag_mapq ? vq[v] : make_uchar4(255, 255, 255, 255);
+            wps_scatter(S.D, P, T, s.x, e.x, q.x);
+            wps_scatter(S.D, P, T, s.y, e.y, q.y);
+            wps_scatter(S.D, P, T, s.z, e.z, q.z);
+            wps_scatter(S.D, P, T, s.w, e.w, q.w);
+        }
+        if (d.tail_hi > d.tail_lo) {  // < 16 fragments at the very end of the contig
+            const int64_t i = d.tail_lo + tid;
+            if (i < d.tail_hi)
+                wps_scatter(S.D, P, T, __ldcs(frag_start + i), __ldcs(frag_stop + i),
+                            frag_mapq ? (int)__ldcs(frag_mapq + i) : 255);
+        }
+        consumer_sync();                                // scatter done; stage buffers are free
+        if (tid == 0) mbar_arrive(&S.empty_bar[stage]);  // hand the stage back to the producer
+        if (d.last)
+            wps_scan_store<ODD>(S.D, S.warp_tot, P, T, out + d.out_off, tid, [] { consumer_sync(); });
+        stage ^= 1;
+        if (stage == 0) phase ^= 1u;
     }
 }
 
@@ -256,6 +506,45 @@ extern "C" int ftk_wps_tile_ranges(const int32_t *frag_start, int64_t n_frag,
     return FTK_OK;
 }
 
+static int g_wps_impl = 0;  // 0 = stream (TMA pipeline, default), 1 = direct (one CTA per tile)
+extern "C" void ftk_debug_set_wps_impl(int impl) { g_wps_impl = impl; }
+
+template <bool ODD>
+static int launch_wps(const int32_t *frag_start, const int32_t *frag_stop, const uint8_t *frag_mapq,
+                      int64_t n_frag, const int32_t *tile_p0, const int32_t *tile_len,
+                      const int32_t *tile_mid_lo, const int32_t *tile_mid_hi,
+                      const int64_t *tile_out_off, int64_t n_tiles, const ftk::WpsParams &P,
+                      const int64_t *ranges, int32_t *out, cudaStream_t stream) {
+    using namespace ftk;
+    if (g_wps_impl == 1) {
+        wps_tile_kernel<ODD><<<(unsigned)n_tiles, kWpsThreads, 0, stream>>>(
+            frag_start, frag_stop, frag_mapq, tile_p0, tile_len, tile_mid_lo, tile_mid_hi, tile_out_off,
+            ranges, P, out);
+        FTK_CHECK_LAUNCH("wps_tile_kernel");
+        return FTK_OK;
+    }
+    static thread_local int sm_count[64] = {0};
+    static thread_local bool attr_set[64] = {false};
+    int dev = 0;
+    FTK_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return FTK_E_RANGE;
+    if (!sm_count[dev])
+        FTK_CUDA_TRY(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+    const int smem = (int)sizeof(StreamSmem);
+    if (!attr_set[dev]) {
+        FTK_CUDA_TRY(cudaFuncSetAttribute(wps_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        FTK_CUDA_TRY(cudaFuncSetAttribute(wps_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[dev] = true;
+    }
+    int64_t grid = (int64_t)sm_count[dev] * kStreamCtasPerSm;  // one persistent CTA per resident slot
+    if (grid > n_tiles) grid = n_tiles;
+    wps_stream_kernel<ODD><<<(unsigned)grid, kStreamThreads, smem, stream>>>(
+        frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo, tile_mid_hi, tile_out_off,
+        ranges, (int)n_tiles, P, out);
+    FTK_CHECK_LAUNCH("wps_stream_kernel");
+    return FTK_OK;
+}
+
 extern "C" int ftk_wps_tiles_i32(const int32_t *frag_start, const int32_t *frag_stop,
                                  const uint8_t *frag_mapq, int64_t n_frag,
                                  const int32_t *tile_p0, const int32_t *tile_len,
@@ -275,16 +564,21 @@ extern "C" int ftk_wps_tiles_i32(const int32_t *frag_start, const int32_t *frag_
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const bool odd = (window_size & 1) != 0;
-    const int a = odd ? (window_size - 1) / 2 : window_size / 2;
-    const int b = odd ? a : a - 1;
-    if (odd)
-        wps_tile_kernel<true><<<(unsigned)n_tiles, kWpsThreads, 0, stream>>>(
-            frag_start, frag_stop, frag_mapq, tile_p0, tile_len, tile_mid_lo, tile_mid_hi, tile_out_off,
-            scratch, window_size, a, b, min_len, max_len, min_mapq, out);
-    else
-        wps_tile_kernel<false><<<(unsigned)n_tiles, kWpsThreads, 0, stream>>>(
-            frag_start, frag_stop, frag_mapq, tile_p0, tile_len, tile_mid_lo, tile_mid_hi, tile_out_off,
-            scratch, window_size, a, b, min_len, max_len, min_mapq, out);
-    FTK_CHECK_LAUNCH("wps_tile_kernel");
-    return FTK_OK;
+    WpsParams P;
+    P.window = window_size;
+    P.a = odd ? (window_size - 1) / 2 : window_size / 2;
+    P.b = odd ? P.a : P.a - 1;
+    P.len_lo = (min_len == FTK_NONE || min_len < 0) ? 0 : min_len;
+    P.max_len = max_len;
+    if (max_len < P.len_lo) {  // empty length window: every position scores 0
+        // (still run the kernel so `out` is fully written; nothing passes the range test)
+        P.len_lo = 1; P.len_span = 0; P.min_mapq = 256;
+    } else {
+        P.len_span = (unsigned)(max_len - P.len_lo);
+        P.min_mapq = min_mapq;
+    }
+    return odd ? launch_wps<true>(frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo,
+                                  tile_mid_hi, tile_out_off, n_tiles, P, scratch, out, stream)
+               : launch_wps<false>(frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo,
+                                   tile_mid_hi, tile_out_off, n_tiles, P, scratch, out, stream);
 }

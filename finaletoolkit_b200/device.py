@@ -187,12 +187,13 @@ def policy_code(intersect_policy: str) -> int:
         raise InvalidInputError(f"{intersect_policy} is not a valid policy") from None
 
 
-def _splits_for(n_ivl: int, n_frag: int) -> int:
-    """CTAs per interval: fill the chip without slicing below ~4k candidates."""
+def _splits_for(n_ivl: int, n_frag: int, per_unit: int = 16384) -> int:
+    """Slices per interval: enough units to fill the chip several times over, none below
+    ~``per_unit`` candidate fragments (estimated from the contig-wide mean)."""
     if n_ivl <= 0:
         return 1
-    by_grid = -(-_TARGET_CTAS // n_ivl)
-    by_size = max(1, (n_frag // max(n_ivl, 1)) // 4096 + 1)
+    by_grid = -(-4 * _TARGET_CTAS // n_ivl)
+    by_size = max(1, (n_frag // max(n_ivl, 1)) // per_unit + 1)
     return int(max(1, min(by_grid, by_size, 65536)))
 
 
@@ -312,3 +313,93 @@ def end_motif_hist(frags: ContigFragments, ref: PackedContig, ivl_start, ivl_sto
             "Error querying sequence: reverse k-mer window out of contig bounds. Please verify "
             "that the reference file matches the fragment file.")
     return counts[:rows]
+
+
+def savgol_tables(window: int, degree: int):
+    """Savitzky-Golay interior coefficients and mode='interp' edge-fit matrices (host, fp64).
+
+    Same least-squares construction as scipy.signal.savgol_filter (reference call site
+    frag/_adjust_wps.py:135-138; scipy/signal/_savitzky_golay.py): interior = the centre
+    row of the hat matrix of a degree-``degree`` polynomial fit over ``window`` points;
+    the first/last ``window//2`` outputs evaluate the fit of the first/last ``window``
+    samples at their own positions.
+    """
+    if window % 2 != 1 or window < 1:
+        raise ValueError("window_length must be odd.")
+    if degree >= window:
+        raise ValueError("polyorder must be less than window_length.")
+    half = window // 2
+    pos = np.arange(-half, half + 1, dtype=np.float64)
+    A = np.vander(pos, degree + 1, increasing=True)
+    hat = A @ np.linalg.pinv(A)              # hat[i, j]: weight of sample j in the fit at i
+    coef = np.ascontiguousarray(hat[half])   # symmetric: correlation == convolution
+    edge_first = np.ascontiguousarray(hat[:half])
+    edge_last = np.ascontiguousarray(hat[half + 1:])
+    return coef, edge_first, edge_last
+
+
+def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, savgol=True,
+                    savgol_window_size=21, savgol_poly_deg=2, subtract_edges=False, edge_size=500,
+                    run_len=2048):
+    """Median/mean-adjust + Savitzky-Golay smooth contiguous raw-WPS segments on the GPU.
+
+    ``x``: float32 samples of all segments back to back (numpy or CUDA tensor);
+    ``seg_lengths``: samples per segment.  Returns ``(out float64 CUDA tensor, out_off)``
+    with segment s's ``n_s - w`` outputs at ``out[out_off[s]:out_off[s+1]]``.
+    Raises ValueError exactly where the reference does (frag/_adjust_wps.py:125-129 and
+    numpy/scipy shape errors for odd windows / too-short segments).
+    """
+    t = torch()
+    dev = require_cuda(x.device if t.is_tensor(x) and x.is_cuda else None)
+    w = int(median_window_size)
+    seg_lengths = np.asarray(seg_lengths, dtype=np.int64)
+    if (seg_lengths < w).any():
+        bad = int(seg_lengths[seg_lengths < w][0])
+        raise ValueError(f"median_window_size ({w}) cannot be greater than the length of interval ({bad}).")
+    if w % 2 or w < 2:
+        raise ValueError("operands could not be broadcast together: median_window_size must be even "
+                         "(frag/_adjust_wps.py:43 slices w//2 from both ends)")
+    n_out = seg_lengths - w
+    if savgol and (n_out < savgol_window_size).any():
+        raise ValueError("If mode is 'interp', window_length must be less than or equal to the size of x.")
+    n_seg = len(seg_lengths)
+    seg_off = np.zeros(n_seg + 1, np.int64); np.cumsum(seg_lengths, out=seg_off[1:])
+    out_off = np.zeros(n_seg + 1, np.int64); np.cumsum(n_out, out=out_off[1:])
+    runs = -(-n_out // run_len)
+    run_off = np.zeros(n_seg + 1, np.int64); np.cumsum(runs, out=run_off[1:])
+    n_runs = int(run_off[-1])
+    xd = x if t.is_tensor(x) else _to_device(np.asarray(x), dev, np.float32)
+    xd = xd.to(dev, t.float32).contiguous()
+    out = t.empty(max(int(out_off[-1]), 1), dtype=t.float64, device=dev)
+    if n_runs == 0:
+        return out[:0], out_off
+    d_seg = _to_device(seg_off, dev, np.int64)
+    d_out = _to_device(out_off, dev, np.int64)
+    d_run = _to_device(run_off, dev, np.int64)
+    if savgol:
+        coef, ef, el = savgol_tables(int(savgol_window_size), int(savgol_poly_deg))
+    else:
+        coef, ef, el = np.ones(1), np.zeros((1, 1)), np.zeros((1, 1))
+    d_coef = _to_device(coef, dev, np.float64)
+    d_ef = _to_device(ef.reshape(-1) if ef.size else np.zeros(1), dev, np.float64)
+    d_el = _to_device(el.reshape(-1) if el.size else np.zeros(1), dev, np.float64)
+    L = lib()
+    sp = _stream_ptr(dev)
+    shift_ptr = 0
+    if subtract_edges:
+        shift = t.empty(n_seg, dtype=t.float64, device=dev)
+        check(L.ftk_adjust_edge_shift_f64(xd.data_ptr(), d_seg.data_ptr(), n_seg, int(edge_size),
+                                          shift.data_ptr(), sp), "ftk_adjust_edge_shift_f64")
+        shift_ptr = shift.data_ptr()
+    fb = t.empty(n_runs, dtype=t.uint8, device=dev)
+    args = (int(w), int(bool(use_mean)), int(bool(savgol)), int(savgol_window_size) if savgol else 1, int(run_len),
+            d_coef.data_ptr(), d_ef.data_ptr(), d_el.data_ptr(), out.data_ptr())
+    check(L.ftk_adjust_wps_f64(xd.data_ptr(), d_seg.data_ptr(), d_out.data_ptr(), d_run.data_ptr(), shift_ptr,
+                               n_seg, n_runs, *args, fb.data_ptr(), sp), "ftk_adjust_wps_f64")
+    flagged = t.nonzero(fb).flatten().to(t.int64)   # plumbing: compact the flagged run ids
+    if flagged.numel():
+        scratch = t.empty(flagged.numel() * w, dtype=t.float32, device=dev)
+        check(L.ftk_adjust_wps_generic_f64(xd.data_ptr(), d_seg.data_ptr(), d_out.data_ptr(), d_run.data_ptr(),
+                                           shift_ptr, n_seg, flagged.data_ptr(), flagged.numel(), *args,
+                                           scratch.data_ptr(), sp), "ftk_adjust_wps_generic_f64")
+    return out[: int(out_off[-1])], out_off

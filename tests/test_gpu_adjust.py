@@ -1,0 +1,103 @@
+"""CUDA adjust_wps (median/mean + Savitzky-Golay) vs the reference goldens and the oracle.
+
+Tolerance per BASELINE.json north_star: adjust_wps floats within 1e-5 relative
+(absolute floor 1e-9 for values that are exactly 0 in the reference).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-9
+
+
+def _run(x, lens, **kw):
+    import torch
+    from finaletoolkit_b200.device import adjust_segments
+    out, off = adjust_segments(np.asarray(x, np.float32), lens, **kw)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), off
+
+
+def test_core_golden(manifest, golden):
+    g = golden("adjust"); m = manifest["adjust"]
+    worst = 0.0
+    for c in m["core_cases"]:
+        x = g[c["input"]]
+        sg = c["sg"]
+        kw = dict(median_window_size=c["w"], use_mean=c["mean"], savgol=sg is not None)
+        if sg:
+            kw.update(savgol_window_size=sg[0], savgol_poly_deg=sg[1])
+        got, _ = _run(x, [len(x)], **kw)
+        exp = g[c["key"] + "_out"]
+        np.testing.assert_allclose(got, exp, rtol=RTOL, atol=ATOL, err_msg=str(c))
+        worst = max(worst, float(np.abs(got - exp).max()))
+        if sg is None and not c["mean"]:
+            assert np.array_equal(got, exp), c          # the pre-SG median path is exact
+    assert worst < 1e-10
+
+
+def test_driver_golden_and_run_splitting(manifest, golden):
+    """Segments from the reference's adjust_wps driver (merged intervals), several run lengths."""
+    g = golden("adjust"); m = manifest["adjust"]
+    raw_pos, raw_val = g["raw_pos"], g["raw_val_f32"]
+    lut = {int(p): i for i, p in enumerate(raw_pos.tolist())}
+    for j, c in enumerate(m["adjust_cases"]):
+        kw = {"interval_size": 5000, "median_window_size": 1000, "savgol_window_size": 21, "savgol_poly_deg": 2,
+              "savgol": True, "mean": False, "subtract_edges": False, "edge_size": 500, **c["kwargs"]}
+        sites = O.adjust_sites(c["bed"].splitlines(keepends=True), kw["interval_size"], kw["median_window_size"])
+        segs, lens = [], []
+        for contig, s, e in sites:
+            idx = [lut[p] for p in range(s, e) if p in lut]
+            if idx:
+                segs.append(raw_val[idx]); lens.append(len(idx))
+        for run_len in (2048, 257, 64):
+            got, off = _run(np.concatenate(segs), lens, median_window_size=kw["median_window_size"], use_mean=kw["mean"],
+                            savgol=kw["savgol"], savgol_window_size=kw["savgol_window_size"],
+                            savgol_poly_deg=kw["savgol_poly_deg"], subtract_edges=kw["subtract_edges"],
+                            edge_size=kw["edge_size"], run_len=run_len)
+            exp = g[f"adj_{j}_val_f32"]
+            assert got.shape == exp.shape
+            np.testing.assert_allclose(got, exp.astype(np.float64), rtol=2e-5, atol=1e-6, err_msg=f"{c} run={run_len}")
+            # the reference stores float32 in the bigWig: after the same rounding almost all values are identical
+            assert (got.astype(np.float32) == exp).mean() > 0.999
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_vs_oracle(seed):
+    rng = np.random.default_rng(seed)
+    lens = [int(v) for v in rng.integers(300, 9000, 6)]
+    w = int(rng.choice([2, 100, 250, 300]))
+    lens = [max(l, w + 40) for l in lens]
+    kinds = []
+    xs = []
+    for i, l in enumerate(lens):
+        if i % 3 == 0:      # integer WPS-like (fast path)
+            v = np.cumsum(rng.integers(-2, 3, l)).astype(np.float32)
+        elif i % 3 == 1:    # wide range: leaves the 256-bin window -> generic path
+            v = (rng.integers(-5, 6, l) * rng.choice([1, 1, 1, 400], l)).astype(np.float32)
+        else:               # non-integer floats -> generic path
+            v = rng.normal(0, 3, l).astype(np.float32)
+        xs.append(v)
+    for use_mean in (False, True):
+        for sub in (False, True):
+            got, off = _run(np.concatenate(xs), lens, median_window_size=w, use_mean=use_mean, savgol=True,
+                            savgol_window_size=21, savgol_poly_deg=2, subtract_edges=sub, edge_size=77, run_len=500)
+            for i, v in enumerate(xs):
+                x = v.astype(np.float64)
+                if sub:
+                    x = x - np.mean([np.mean(x[:77]), np.mean(x[-77:])])
+                exp = O.adjust_core(x, w, use_mean, True, 21, 2)
+                np.testing.assert_allclose(got[off[i]:off[i + 1]], exp, rtol=RTOL, atol=1e-8, err_msg=f"seg {i} mean={use_mean} sub={sub}")
+
+
+def test_errors():
+    from finaletoolkit_b200.device import adjust_segments
+    x = np.zeros(500, np.float32)
+    with pytest.raises(ValueError):
+        adjust_segments(x, [500], median_window_size=1000)
+    with pytest.raises(ValueError):
+        adjust_segments(x, [500], median_window_size=101)
+    with pytest.raises(ValueError):
+        adjust_segments(x, [500], median_window_size=490)  # 10 outputs < savgol window
