@@ -1,0 +1,42 @@
+"""finaletoolkit_b200 - B200-native (sm_100a CUDA) implementation of FinaleToolkit's
+per-fragment interval-feature hot path, behind the reference's own Python API.
+
+Flat namespace resolved lazily like the reference's (finaletoolkit/__init__.py:49-128):
+``finaletoolkit_b200.wps``, ``.multi_wps``, ``.adjust_wps``, ``.coverage``, ...
+Importing the package needs neither CUDA nor torch; calling a feature without a CUDA
+device / libftk_b200.so raises ``FtkLibraryError`` (there is no CPU fallback).
+"""
+from __future__ import annotations
+
+__version__ = "0.1.0"
+
+_SUBMODULES = ("cli", "frag", "io", "utils", "device", "synth", "exceptions", "sharding")
+
+_EXPORTS = {
+    "frag_length": ("frag", "frag_length"), "frag_length_bins": ("frag", "frag_length_bins"),
+    "frag_length_intervals": ("frag", "frag_length_intervals"),
+    "coverage": ("frag", "coverage"), "single_coverage": ("frag", "single_coverage"),
+    "wps": ("frag", "wps"), "multi_wps": ("frag", "multi_wps"), "adjust_wps": ("frag", "adjust_wps"),
+    "end_motifs": ("frag", "end_motifs"), "region_end_motifs": ("frag", "region_end_motifs"),
+    "interval_end_motifs": ("frag", "interval_end_motifs"),
+    "EndMotifFreqs": ("frag", "EndMotifFreqs"), "EndMotifsIntervals": ("frag", "EndMotifsIntervals"),
+    "frag_generator": ("utils", "frag_generator"), "frag_array": ("utils", "frag_array"),
+    "frags_in_region": ("utils", "frags_in_region"), "get_intervals": ("utils", "get_intervals"),
+    "gen_kmers": ("utils", "gen_kmers"), "reverse_complement": ("utils", "reverse_complement"),
+    "chrom_sizes_to_dict": ("utils", "chrom_sizes_to_dict"), "chrom_sizes_to_list": ("utils", "chrom_sizes_to_list"),
+    "ReferenceWrapper": ("io", "ReferenceWrapper"),
+}
+_ALIASES = {"end_motif": "end_motifs"}
+
+
+def __getattr__(name: str):
+    import importlib
+    if name in _SUBMODULES:
+        return importlib.import_module(f".{name}", __name__)
+    target = _ALIASES.get(name, name)
+    if target in _EXPORTS:
+        sub, attr = _EXPORTS[target]
+        value = getattr(importlib.import_module(f".{sub}", __name__), attr)
+        globals()[name] = value
+        return value
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

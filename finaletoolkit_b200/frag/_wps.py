@@ -1,0 +1,80 @@
+"""Windowed Protection Score over one interval - API mirror of reference frag/_wps.py:56-229.
+
+Same signature, return dtype, warnings and errors; the per-position numba loop
+(frag/_wps.py:176-188) is replaced by the CUDA tile kernel behind
+``ftk_wps_tiles_i32`` (finaletoolkit_b200/csrc/ftk_wps.cu).
+"""
+from __future__ import annotations
+
+import gzip
+import time
+import warnings
+from sys import stderr, stdout
+
+import numpy as np
+
+from ..io.fragments import as_table
+from ._common import resolve_length_aliases
+
+__all__ = ["wps"]
+
+_WPS_DTYPE = [("contig", "U16"), ("start", "i8"), ("wps", "i8")]
+
+
+def _wps_device(table, chrom, starts, stops, chrom_size, window_size, min_length, max_length,
+                quality_threshold, device=None):
+    """int32 CUDA tensor with the WPS of every interval back to back + host offsets."""
+    from ..device import WpsPlan
+    frags = table.device(chrom, device)
+    plan = WpsPlan(starts, stops, chrom_size, max_length, frags.device)
+    return plan.run(frags, window_size, min_length, max_length, quality_threshold), plan.offsets
+
+
+def wps(input_file, chrom, start, stop, chrom_size, output_file=None, window_size=120, min_length=120,
+        max_length=180, quality_threshold=30, verbose=0, fraction_low=None, fraction_high=None,
+        reference_file=None) -> np.ndarray:
+    """Raw WPS over ``chrom:[start, stop)``: structured array ('contig','start','wps')."""
+    if verbose:
+        start_time = time.time()
+        stderr.write("[finaletoolkit-wps] Reading fragments\n")
+        stderr.write(f"Region: {chrom}:{start}-{stop}\n")
+    min_length, max_length = resolve_length_aliases(min_length, max_length, fraction_low, fraction_high)
+    start, stop = int(start), int(stop)
+    if stop <= start:
+        warnings.warn(f"[wps] {chrom}:{start}-{stop} is a degenerate interval (stop <= start); skipping.",
+                      UserWarning, stacklevel=2)
+        return np.zeros(0, dtype=_WPS_DTYPE)
+    table = as_table(input_file, reference_file)
+    out, _ = _wps_device(table, chrom, [start], [stop], int(chrom_size), int(window_size), min_length,
+                         int(round(max_length)), quality_threshold)
+    scores = np.zeros(stop - start, dtype=_WPS_DTYPE)
+    scores["contig"] = chrom
+    scores["start"] = np.arange(start, stop, dtype=np.int64)
+    scores["wps"] = out.cpu().numpy()
+    if isinstance(output_file, str):
+        if verbose:
+            stderr.write("Writing to output file.\n")
+        _write_wig(output_file, chrom, start, stop, scores)
+    elif output_file is not None:
+        raise TypeError(f'output_file is unsupported type "{type(input_file)}". output_file should be a '
+                        "string specifying the path of the file to output scores to.")
+    if verbose:
+        stderr.write(f"wps took {time.time() - start_time} s to complete\n")
+    return scores
+
+
+def _write_wig(output_file, chrom, start, stop, scores) -> None:
+    """fixedStep WIG exactly as frag/_wps.py:208-229."""
+    header = f"fixedStep\tchrom={chrom}\tstart={start}\tstep={1}\tspan={stop - start}\n"
+    body = "".join(f"{s}\n" for s in scores["wps"])
+    if output_file.endswith(".wig.gz"):
+        with gzip.open(output_file, "wt") as out:
+            out.write(header + body)
+    elif output_file.endswith(".wig"):
+        with open(output_file, "wt") as out:
+            out.write(header + body)
+    elif output_file == "-":
+        stdout.write(header + body)
+        stdout.flush()
+    else:
+        raise ValueError("output_file can only have suffixes .wig or .wig.gz.")

@@ -1,0 +1,5 @@
+"""Host-side I/O: fragment decode to columns, reference genomes, bigWig."""
+from .fragments import FragmentTable, as_table, load_fragments
+from .reference import ReferenceWrapper
+
+__all__ = ["FragmentTable", "as_table", "load_fragments", "ReferenceWrapper"]

@@ -1,0 +1,358 @@
+"""bigWig reader / writer (numpy + zlib) with the slice of the pyBigWig API the hot path uses.
+
+pyBigWig (libBigWig) is not available in this image, and ``.bw`` is the primary
+WPS format of the reference CLI: ``multi_wps`` writes raw WPS with
+``addEntries(chrom, start, values=..., span=1, step=1)`` (frag/_multi_wps.py:300-325)
+and ``adjust_wps`` reads it back with ``intervals(contig, start, stop)``
+(frag/_adjust_wps.py:80-105) and writes ``addEntries(chroms, starts, ends=, values=)``
+(frag/_adjust_wps.py:275-291).  This module implements the UCSC bigWig container
+(header, chromosome B+ tree, zlib-compressed fixedStep / bedGraph sections, R-tree
+index, total summary; zoom levels are optional in the format and omitted) so files
+interoperate with pyBigWig / UCSC tools.  Values are stored as float32 like libBigWig.
+
+    bw = open(path, "w"); bw.addHeader([(chrom, size), ...]); bw.addEntries(...); bw.close()
+    bw = open(path);      bw.chroms(); bw.intervals(chrom, start, end); bw.values(chrom, s, e)
+"""
+from __future__ import annotations
+
+import builtins
+import struct
+import zlib
+
+import numpy as np
+
+__all__ = ["open", "BigWigReader", "BigWigWriter"]
+
+_BW_MAGIC = 0x888FFC26
+_CHROM_TREE_MAGIC = 0x78CA8C91
+_RTREE_MAGIC = 0x2468ACE0
+_ITEMS_PER_SECTION = 16384   # <= 65535 (itemCount is u16)
+_RTREE_BLOCK = 256
+
+
+class BigWigWriter:
+    def __init__(self, path: str):
+        self.path = str(path)
+        self._fh = builtins.open(self.path, "wb")
+        self._chroms: list[tuple[str, int]] | None = None
+        self._ids: dict[str, int] = {}
+        self._sections: list[tuple[int, int, int, int, int]] = []  # chromId, start, end, offset, size
+        self._last = (-1, -1)   # (chromId, end) of the previous entry: entries must be sorted
+        self._max_uncomp = 0
+        self._n_cov, self._min, self._max, self._sum, self._sumsq = 0, np.inf, -np.inf, 0.0, 0.0
+        self._closed = False
+
+    # -- pyBigWig-compatible surface ------------------------------------
+    def addHeader(self, header, maxZooms: int = 10) -> None:
+        self._chroms = [(str(c), int(n)) for c, n in header]
+        self._ids = {c: i for i, (c, _) in enumerate(self._chroms)}
+        n = len(self._chroms)
+        key_size = max((len(c.encode()) for c, _ in self._chroms), default=1)
+        # header (64) + total summary (40) + chrom tree; data follows
+        self._fh.write(b"\0" * 64)
+        self._summary_off = self._fh.tell()
+        self._fh.write(b"\0" * 40)
+        self._chrom_tree_off = self._fh.tell()
+        self._fh.write(struct.pack("<IIIIQQ", _CHROM_TREE_MAGIC, max(n, 1), key_size, 8, n, 0))
+        self._fh.write(struct.pack("<BBH", 1, 0, n))
+        for c, i in sorted(self._ids.items(), key=lambda kv: kv[0].encode()):   # keys sorted bytewise
+            self._fh.write(c.encode().ljust(key_size, b"\0") + struct.pack("<II", i, self._chroms[i][1]))
+        self._data_off = self._fh.tell()
+        self._fh.write(struct.pack("<Q", 0))  # section count, patched on close
+
+    def addEntries(self, chroms, starts, ends=None, values=None, span=None, step=None, validate=True) -> None:
+        if self._chroms is None:
+            raise RuntimeError("The bigWig file handle is not opened for writing or has no header.")
+        vals = np.ascontiguousarray(np.asarray(values, dtype=np.float64).astype(np.float32))
+        if vals.size == 0:
+            return
+        if isinstance(chroms, str):
+            cid = self._chrom_id(chroms)
+            if span is not None and step is not None and np.ndim(starts) == 0:
+                self._add_fixed(cid, int(starts), int(span), int(step), vals)
+                return
+            st = np.asarray(starts, dtype=np.int64)
+            en = st + int(span) if ends is None else np.asarray(ends, dtype=np.int64)
+            self._add_bedgraph(cid, st, en, vals)
+            return
+        chroms = list(chroms)
+        st = np.asarray(starts, dtype=np.int64)
+        en = np.asarray(ends, dtype=np.int64)
+        if not (len(chroms) == st.size == en.size == vals.size):
+            raise RuntimeError("chroms, starts, ends and values must have the same length")
+        # runs of identical contigs
+        i = 0
+        while i < len(chroms):
+            j = i
+            while j < len(chroms) and chroms[j] == chroms[i]:
+                j += 1
+            self._add_bedgraph(self._chrom_id(chroms[i]), st[i:j], en[i:j], vals[i:j])
+            i = j
+
+    def close(self) -> None:
+        if self._closed:
+            return
+        self._closed = True
+        fh = self._fh
+        if self._chroms is None:
+            fh.close()
+            return
+        index_off = fh.tell()
+        self._write_rtree(index_off)
+        end = fh.tell()
+        fh.seek(self._data_off)
+        fh.write(struct.pack("<Q", len(self._sections)))
+        fh.seek(self._summary_off)
+        if self._n_cov:
+            fh.write(struct.pack("<Qdddd", self._n_cov, self._min, self._max, self._sum, self._sumsq))
+        fh.seek(0)
+        fh.write(struct.pack("<IHHQQQHHQQIQ", _BW_MAGIC, 4, 0, self._chrom_tree_off, self._data_off, index_off,
+                             0, 0, 0, self._summary_off, self._max_uncomp, 0))
+        fh.seek(end)
+        fh.write(struct.pack("<I", _BW_MAGIC))
+        fh.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
+
+    # -- internals ------------------------------------------------------
+    def _chrom_id(self, chrom: str) -> int:
+        try:
+            return self._ids[chrom]
+        except KeyError:
+            raise RuntimeError(f"Invalid chromosome {chrom!r}: not in the bigWig header") from None
+
+    def _check_order(self, cid: int, start: int, end: int) -> None:
+        size = self._chroms[cid][1]
+        if start < 0 or end > size or end <= start:
+            raise RuntimeError("The entries you tried to add are out of bounds or empty")
+        if (cid, start) < self._last:
+            raise RuntimeError("The entries you tried to add are out of order")
+
+    def _stats(self, vals: np.ndarray, bases: np.ndarray | int) -> None:
+        v = vals.astype(np.float64)
+        b = np.broadcast_to(np.asarray(bases, dtype=np.float64), v.shape)
+        self._n_cov += int(b.sum())
+        self._min = min(self._min, float(v.min())); self._max = max(self._max, float(v.max()))
+        self._sum += float((v * b).sum()); self._sumsq += float((v * v * b).sum())
+
+    def _emit(self, cid, start, end, step, span, typ, payload: bytes, n_items: int) -> None:
+        raw = struct.pack("<IIIIIBBH", cid, start, end, step, span, typ, 0, n_items) + payload
+        self._max_uncomp = max(self._max_uncomp, len(raw))
+        comp = zlib.compress(raw, 6)
+        off = self._fh.tell()
+        self._fh.write(comp)
+        self._sections.append((cid, start, end, off, len(comp)))
+
+    def _add_fixed(self, cid, start, span, step, vals) -> None:
+        n = vals.size
+        end = start + (n - 1) * step + span
+        self._check_order(cid, start, end)
+        for i in range(0, n, _ITEMS_PER_SECTION):
+            v = vals[i: i + _ITEMS_PER_SECTION]
+            s = start + i * step
+            self._emit(cid, s, s + (v.size - 1) * step + span, step, span, 3, v.astype("<f4").tobytes(), v.size)
+        self._stats(vals, span)
+        self._last = (cid, end)
+
+    def _add_bedgraph(self, cid, st, en, vals) -> None:
+        if st.size == 0:
+            return
+        if np.any(st[1:] < en[:-1]) or np.any(en <= st):
+            raise RuntimeError("The entries you tried to add are out of order or overlap")
+        self._check_order(cid, int(st[0]), int(en[-1]))
+        for i in range(0, st.size, _ITEMS_PER_SECTION):
+            s, e, v = st[i: i + _ITEMS_PER_SECTION], en[i: i + _ITEMS_PER_SECTION], vals[i: i + _ITEMS_PER_SECTION]
+            rec = np.empty(s.size, dtype=[("s", "<u4"), ("e", "<u4"), ("v", "<f4")])
+            rec["s"], rec["e"], rec["v"] = s, e, v
+            self._emit(cid, int(s[0]), int(e[-1]), 0, 0, 1, rec.tobytes(), s.size)
+        self._stats(vals, en - st)
+        self._last = (cid, int(en[-1]))
+
+    def _write_rtree(self, index_off: int) -> None:
+        fh = self._fh
+        secs = self._sections
+        n = len(secs)
+        if n == 0:
+            fh.write(struct.pack("<IIQIIIIQII", _RTREE_MAGIC, _RTREE_BLOCK, 0, 0, 0, 0, 0, index_off, 1, 0))
+            fh.write(struct.pack("<BBH", 1, 0, 0))
+            return
+        # level 0 = leaves over sections; upper levels group _RTREE_BLOCK children
+        levels = [[(s[0], s[1], s[0], s[2], i) for i, s in enumerate(secs)]]
+        while len(levels[-1]) > _RTREE_BLOCK:
+            prev, cur = levels[-1], []
+            for i in range(0, len(prev), _RTREE_BLOCK):
+                grp = prev[i: i + _RTREE_BLOCK]
+                cur.append((grp[0][0], grp[0][1], grp[-1][2], max(g[3] for g in grp if g[2] == grp[-1][2]), i))
+            levels.append(cur)
+        fh.write(struct.pack("<IIQIIIIQII", _RTREE_MAGIC, _RTREE_BLOCK, n, secs[0][0], secs[0][1],
+                             secs[-1][0], secs[-1][2], index_off, 1, 0))
+        # node sizes per level, top-down layout
+        top = len(levels) - 1
+        node_counts = [(-(-len(levels[k]) // _RTREE_BLOCK)) for k in range(len(levels))]
+        offsets = {}
+        pos = fh.tell()
+        for k in range(top, -1, -1):
+            item = 32 if k == 0 else 24
+            for j in range(node_counts[k]):
+                cnt = min(_RTREE_BLOCK, len(levels[k]) - j * _RTREE_BLOCK)
+                offsets[(k, j)] = pos
+                pos += 4 + cnt * item
+        for k in range(top, -1, -1):
+            for j in range(node_counts[k]):
+                items = levels[k][j * _RTREE_BLOCK: (j + 1) * _RTREE_BLOCK]
+                fh.write(struct.pack("<BBH", 1 if k == 0 else 0, 0, len(items)))
+                for it in items:
+                    if k == 0:
+                        s = secs[it[4]]
+                        fh.write(struct.pack("<IIIIQQ", s[0], s[1], s[0], s[2], s[3], s[4]))
+                    else:
+                        child = offsets[(k - 1, it[4] // _RTREE_BLOCK)]
+                        fh.write(struct.pack("<IIIIQ", it[0], it[1], it[2], it[3], child))
+
+
+class BigWigReader:
+    def __init__(self, path: str):
+        self.path = str(path)
+        with builtins.open(self.path, "rb") as fh:
+            self._buf = fh.read()
+        b = self._buf
+        magic = struct.unpack_from("<I", b, 0)[0]
+        self._e = "<"
+        if magic != _BW_MAGIC:
+            if struct.unpack_from(">I", b, 0)[0] != _BW_MAGIC:
+                raise RuntimeError(f"{path} is not a bigWig file")
+            self._e = ">"
+        e = self._e
+        (_, self.version, self.n_zoom, ct_off, self._data_off, self._index_off, _, _, _, self._summary_off,
+         self._uncomp, _) = struct.unpack_from(e + "IHHQQQHHQQIQ", b, 0)
+        self._chroms: dict[str, tuple[int, int]] = {}
+        _, _, key_size, _, _, _ = struct.unpack_from(e + "IIIIQQ", b, ct_off)
+        self._walk_chrom_tree(ct_off + 32, key_size)
+        self._by_id = {cid: (name, size) for name, (cid, size) in self._chroms.items()}
+
+    def _walk_chrom_tree(self, off: int, key_size: int) -> None:
+        b, e = self._buf, self._e
+        is_leaf, _, count = struct.unpack_from(e + "BBH", b, off)
+        off += 4
+        for _ in range(count):
+            key = b[off: off + key_size].rstrip(b"\0").decode()
+            if is_leaf:
+                cid, size = struct.unpack_from(e + "II", b, off + key_size)
+                self._chroms[key] = (cid, size)
+            else:
+                (child,) = struct.unpack_from(e + "Q", b, off + key_size)
+                self._walk_chrom_tree(child, key_size)
+            off += key_size + 8
+
+    def chroms(self, chrom=None):
+        if chrom is not None:
+            return self._chroms[chrom][1] if chrom in self._chroms else None
+        return {c: s for c, (_, s) in self._chroms.items()}
+
+    def header(self):
+        b, e = self._buf, self._e
+        n, mn, mx, sm, sq = struct.unpack_from(e + "Qdddd", b, self._summary_off)
+        return {"version": self.version, "nLevels": self.n_zoom, "nBasesCovered": n, "minVal": mn,
+                "maxVal": mx, "sumData": sm, "sumSquared": sq}
+
+    def _blocks(self, cid: int, start: int, end: int):
+        b, e = self._buf, self._e
+        out = []
+
+        def overlaps(sc, sb, ec, eb):
+            return (sc, sb) < (cid, end) and (ec, eb) > (cid, start)
+
+        def walk(off):
+            is_leaf, _, count = struct.unpack_from(e + "BBH", b, off)
+            off += 4
+            for _ in range(count):
+                if is_leaf:
+                    sc, sb, ec, eb, doff, dsize = struct.unpack_from(e + "IIIIQQ", b, off)
+                    if overlaps(sc, sb, ec, eb):
+                        out.append((doff, dsize))
+                    off += 32
+                else:
+                    sc, sb, ec, eb, child = struct.unpack_from(e + "IIIIQ", b, off)
+                    if overlaps(sc, sb, ec, eb):
+                        walk(child)
+                    off += 24
+
+        walk(self._index_off + 48)
+        return out
+
+    def _intervals_arrays(self, chrom, start, end):
+        if chrom not in self._chroms:
+            raise RuntimeError("Invalid interval bounds!")
+        cid, size = self._chroms[chrom]
+        start = 0 if start is None else int(start)
+        end = size if end is None or end == 0 else int(end)
+        if start < 0 or end > size or start >= end:
+            raise RuntimeError("Invalid interval bounds!")
+        b, e = self._buf, self._e
+        S, E, V = [], [], []
+        for doff, dsize in self._blocks(cid, start, end):
+            raw = b[doff: doff + dsize]
+            if self._uncomp:
+                raw = zlib.decompress(raw)
+            bcid, bstart, bend, step, span, typ, _, n = struct.unpack_from(e + "IIIIIBBH", raw, 0)
+            if bcid != cid:
+                continue
+            if typ == 3:
+                v = np.frombuffer(raw, e + "f4", n, 24)
+                s = bstart + np.arange(n, dtype=np.int64) * step
+                en = s + span
+            elif typ == 2:
+                rec = np.frombuffer(raw, np.dtype([("s", e + "u4"), ("v", e + "f4")]), n, 24)
+                s = rec["s"].astype(np.int64); en = s + span; v = rec["v"]
+            else:
+                rec = np.frombuffer(raw, np.dtype([("s", e + "u4"), ("e", e + "u4"), ("v", e + "f4")]), n, 24)
+                s = rec["s"].astype(np.int64); en = rec["e"].astype(np.int64); v = rec["v"]
+            m = (en > start) & (s < end)
+            if m.any():
+                S.append(s[m]); E.append(en[m]); V.append(v[m])
+        if not S:
+            return None
+        s, en, v = np.concatenate(S), np.concatenate(E), np.concatenate(V)
+        order = np.argsort(s, kind="stable")
+        return s[order], en[order], v[order]
+
+    def intervals(self, chrom, start=0, end=0):
+        """pyBigWig.intervals: tuple of (start, end, value) overlapping the range, or None."""
+        r = self._intervals_arrays(chrom, start, end)
+        if r is None:
+            return None
+        return tuple((int(a), int(b), float(c)) for a, b, c in zip(*r))
+
+    def intervals_arrays(self, chrom, start=0, end=0):
+        """Same query as ``intervals`` but as (starts int64, ends int64, values float32) arrays."""
+        return self._intervals_arrays(chrom, start, end)
+
+    def values(self, chrom, start=0, end=0, numpy=True):
+        cid, size = self._chroms[chrom]
+        end = size if end == 0 else end
+        out = np.full(end - start, np.nan, dtype=np.float32)
+        r = self._intervals_arrays(chrom, start, end)
+        if r is not None:
+            for s, e_, v in zip(*r):
+                out[max(s, start) - start: min(e_, end) - start] = v
+        return out if numpy else out.tolist()
+
+    def close(self) -> None:
+        self._buf = b""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
+
+
+def open(path, mode: str = "r"):
+    """pyBigWig.open look-alike."""
+    if "w" in mode:
+        return BigWigWriter(path)
+    return BigWigReader(path)

@@ -1,0 +1,240 @@
+"""Host-side fragment decode: file -> per-contig columnar int32 arrays -> HBM.
+
+Replaces the per-interval ``AlignmentWrapper(...).fetch(...)`` text stream of the
+reference (io/alignment.py:74-302, re-opened for EVERY interval by
+utils/_frag_generator.py:112) with "decode once, keep columns resident": a
+``FragmentTable`` holds, per contig and in file order (start-sorted for a
+tabix-indexable file), ``start, stop:int32`` and ``mapq, strand:uint8``; its
+``device()`` method uploads a contig once and caches the ``ContigFragments``.
+
+Formats (io/alignment.py:143-156, 158-203, 270-302):
+  * FinaleDB ``.frag.gz`` 5 columns ``chrom start stop mapq strand``;
+  * BED6+ ``.bed.gz`` (more than 5 columns on the first line: mapq = col 5,
+    strand = col 6, ``UserWarning`` like the reference);
+  * malformed rows are skipped (``ValueError``/``IndexError`` -> continue);
+  * a ``.gz``/``.bgz`` path needs its ``.tbi`` sibling (``MissingIndexError``),
+    other extensions raise ``UnsupportedFormatError``; a missing file
+    ``FileNotFoundError``.
+BGZF is multi-member gzip, so Python's ``gzip`` reads it; the tabix index itself
+is not needed because whole contigs are decoded.  BAM/CRAM need htslib: they are
+read through ``pysam`` when it is importable (same read filter as
+io/alignment.py:60-71, 242-268) and rejected with ``UnsupportedFormatError``
+otherwise.  The mapq filter is NOT applied at load time - it is a kernel predicate.
+"""
+from __future__ import annotations
+
+import gzip
+import os
+import warnings
+from os import PathLike
+from typing import Dict, Iterable, Tuple
+
+import numpy as np
+
+from ..exceptions import MissingIndexError, UnsupportedFormatError
+
+__all__ = ["FragmentTable", "load_fragments", "as_table"]
+
+Columns = Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]
+
+
+class FragmentTable:
+    """Per-contig fragment columns (host) with a device cache."""
+
+    def __init__(self, columns: Dict[str, Columns], source: str | None = None, is_sam: bool = False,
+                 contig_lengths: Dict[str, int] | None = None):
+        self.source = source
+        self.is_sam = is_sam
+        self.contig_lengths = contig_lengths  # BAM/CRAM header only
+        self.columns: Dict[str, Columns] = {}
+        for contig, (st, sp, mq, sd) in columns.items():
+            st = np.ascontiguousarray(st, dtype=np.int32)
+            sp = np.ascontiguousarray(sp, dtype=np.int32)
+            mq = np.ascontiguousarray(mq, dtype=np.uint8)
+            sd = np.ascontiguousarray(sd, dtype=np.uint8)
+            if st.size and not np.all(st[1:] >= st[:-1]):
+                order = np.argsort(st, kind="stable")  # keeps file order among equal starts
+                st, sp, mq, sd = st[order], sp[order], mq[order], sd[order]
+            self.columns[contig] = (st, sp, mq, sd)
+        self._device: dict = {}
+
+    @property
+    def contigs(self):
+        return list(self.columns.keys())
+
+    def n_fragments(self, contig=None) -> int:
+        if contig is None:
+            return sum(c[0].size for c in self.columns.values())
+        return self.columns[contig][0].size if contig in self.columns else 0
+
+    def host(self, contig: str) -> Columns:
+        if contig not in self.columns:
+            z = np.zeros(0, np.int32)
+            return z, z.copy(), np.zeros(0, np.uint8), np.zeros(0, np.uint8)
+        return self.columns[contig]
+
+    def device(self, contig: str, device=None):
+        """``ContigFragments`` of one contig in HBM (uploaded once, then cached)."""
+        from ..device import ContigFragments, require_cuda
+        dev = require_cuda(device)
+        key = (contig, str(dev))
+        if key not in self._device:
+            st, sp, mq, sd = self.host(contig)
+            self._device[key] = ContigFragments(st, sp, mq, sd, device=dev, contig=contig)
+        return self._device[key]
+
+
+_CACHE: dict = {}
+
+
+def _check_path(path: str) -> None:
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"Alignment file not found: {path}")
+    lower = path.lower()
+    if lower.endswith((".bam", ".cram", ".sam")):
+        if lower.endswith(".bam") and not (os.path.exists(path + ".bai") or os.path.exists(path[:-4] + ".bai")):
+            raise MissingIndexError(f"BAM file {path} missing index (.bai)")
+        if lower.endswith(".cram") and not (os.path.exists(path + ".crai") or os.path.exists(path[:-5] + ".crai")):
+            raise MissingIndexError(f"CRAM file {path} missing index (.crai)")
+    elif lower.endswith((".gz", ".bgz")):
+        if not os.path.exists(path + ".tbi"):
+            raise MissingIndexError(f"Compressed file {path} missing tabix index (.tbi)")
+    else:
+        raise UnsupportedFormatError(f"Unsupported file format: {path}")
+
+
+def _parse_text_rows(lines: Iterable[str]) -> Dict[str, Columns]:
+    """Tab-separated fragment rows -> columns per contig (file order)."""
+    bed_format = None
+    acc: Dict[str, list] = {}
+    for line in lines:
+        if not line or line[0] == "#" or not line.strip():
+            continue
+        f = line.rstrip("\n").split("\t")
+        if bed_format is None:
+            bed_format = len(f) > 5
+            if bed_format:
+                warnings.warn(
+                    "input_file does not follow Fragmentation file format accepted by FinaleToolkit. "
+                    "Attempting to read as a BED6 file.", UserWarning)
+        try:
+            st, sp = int(f[1]), int(f[2])
+            if bed_format:
+                mq, fw = int(f[4]), "+" in f[5]
+            else:
+                mq, fw = int(f[3]), "+" in f[4]
+        except (ValueError, IndexError):
+            continue  # io/alignment.py:301-302
+        a = acc.get(f[0])
+        if a is None:
+            a = acc[f[0]] = ([], [], [], [])
+        a[0].append(st); a[1].append(sp); a[2].append(min(max(mq, 0), 255)); a[3].append(1 if fw else 0)
+    return {c: (np.array(a[0], np.int64), np.array(a[1], np.int64), np.array(a[2], np.uint8), np.array(a[3], np.uint8))
+            for c, a in acc.items()}
+
+
+def _parse_text_fast(path: str) -> Dict[str, Columns] | None:
+    """pandas C parser for well-formed files; None -> caller falls back to the row parser."""
+    try:
+        import pandas as pd
+        with gzip.open(path, "rt") as fh:
+            first = fh.readline()
+        n_cols = len(first.rstrip("\n").split("\t"))
+        if n_cols < 5 or first.startswith("#"):
+            return None
+        bed = n_cols > 5
+        use = [0, 1, 2, 4, 5] if bed else [0, 1, 2, 3, 4]
+        df = pd.read_csv(path, sep="\t", header=None, usecols=use, compression="gzip", comment="#",
+                         dtype={0: str, use[1]: np.int64, use[2]: np.int64, use[3]: np.int64, use[4]: str},
+                         engine="c", na_filter=False)
+        if bed:
+            warnings.warn(
+                "input_file does not follow Fragmentation file format accepted by FinaleToolkit. "
+                "Attempting to read as a BED6 file.", UserWarning)
+        cols = {}
+        contig = df[0].to_numpy()
+        st = df[use[1]].to_numpy(); sp = df[use[2]].to_numpy()
+        mq = np.clip(df[use[3]].to_numpy(), 0, 255).astype(np.uint8)
+        fw = df[use[4]].str.contains("+", regex=False).to_numpy().astype(np.uint8)
+        # contigs in order of first appearance, rows in file order
+        uniq, first_idx = np.unique(contig, return_index=True)
+        for c in uniq[np.argsort(first_idx)]:
+            m = contig == c
+            cols[str(c)] = (st[m], sp[m], mq[m], fw[m])
+        return cols
+    except Exception:  # noqa: BLE001 - any irregularity: use the tolerant row parser
+        return None
+
+
+def _load_sam(path: str, reference_file=None) -> FragmentTable:
+    try:
+        import pysam
+    except ImportError as e:
+        raise UnsupportedFormatError(
+            f"{path}: BAM/CRAM/SAM decoding needs htslib (pysam), which is not installed; "
+            "convert to a tabix-indexed .frag.gz") from e
+    acc: Dict[str, list] = {}
+    with pysam.AlignmentFile(path, "r", reference_filename=str(reference_file) if reference_file else None) as bam:
+        lengths = dict(zip(bam.references, bam.lengths))
+        for read in bam.fetch():
+            # io/alignment.py:60-71 with quality_threshold deferred to the kernels, :248 read1 only
+            if (read.is_unmapped or read.is_secondary or not read.is_paired or read.mate_is_unmapped
+                    or read.is_duplicate or read.is_qcfail or read.is_supplementary
+                    or not read.is_proper_pair or read.is_read2):
+                continue
+            tlen = read.template_length
+            if tlen > 0:
+                st, sp = read.reference_start, read.reference_start + tlen
+            elif tlen < 0:
+                st, sp = read.reference_end + tlen, read.reference_end
+            else:
+                continue
+            a = acc.setdefault(read.reference_name, ([], [], [], []))
+            a[0].append(st); a[1].append(sp); a[2].append(read.mapping_quality); a[3].append(1 if read.is_forward else 0)
+    cols = {c: (np.array(a[0], np.int64), np.array(a[1], np.int64), np.array(a[2], np.uint8), np.array(a[3], np.uint8))
+            for c, a in acc.items()}
+    return FragmentTable(cols, source=path, is_sam=True, contig_lengths=lengths)
+
+
+def load_fragments(input_file, reference_file=None) -> FragmentTable:
+    """Decode ``input_file`` once into a cached ``FragmentTable``."""
+    path = str(input_file)
+    _check_path(path)
+    st = os.stat(path)
+    key = (os.path.abspath(path), st.st_mtime_ns, st.st_size)
+    tab = _CACHE.get(key)
+    if tab is not None:
+        return tab
+    if path.lower().endswith((".bam", ".cram", ".sam")):
+        tab = _load_sam(path, reference_file)
+    else:
+        cols = _parse_text_fast(path)
+        if cols is None:
+            with gzip.open(path, "rt") as fh:
+                cols = _parse_text_rows(fh)
+        tab = FragmentTable(cols, source=path)
+    if len(_CACHE) > 8:
+        _CACHE.pop(next(iter(_CACHE)))
+    _CACHE[key] = tab
+    return tab
+
+
+def as_table(input_file, reference_file=None) -> FragmentTable:
+    """Accept what the reference's ``FragFile`` accepts (utils/typing.py:13) plus a ``FragmentTable``.
+
+    A path (str / PathLike) is decoded (and cached); an open ``pysam.TabixFile`` /
+    ``pysam.AlignmentFile`` is re-opened by its filename; a ``FragmentTable`` or a dict
+    ``{contig: (start, stop, mapq, strand)}`` is used as is.
+    """
+    if isinstance(input_file, FragmentTable):
+        return input_file
+    if isinstance(input_file, dict):
+        return FragmentTable(input_file)
+    if isinstance(input_file, (str, PathLike)):
+        return load_fragments(input_file, reference_file)
+    name = getattr(input_file, "filename", None)
+    if name is not None:  # open pysam handle
+        if isinstance(name, bytes):
+            name = name.decode()
+        return load_fragments(name, reference_file)
+    raise TypeError(f"unsupported input_file type {type(input_file)!r}")

@@ -61,6 +61,15 @@ class _BW:
         return dict(self._f["header"] or [])
 
     def intervals(self, chrom, start=0, end=None):
+        # pyBigWig.c pyBwGetIntervals: unknown contig, end <= start or end > chromLen
+        # -> RuntimeError("Invalid interval bounds!")
+        sizes = dict(self._f["header"] or [])
+        if chrom not in sizes:
+            raise RuntimeError("Invalid interval bounds!")
+        if end is None:
+            end = sizes[chrom]
+        if end <= start or end > sizes[chrom] or start < 0:
+            raise RuntimeError("Invalid interval bounds!")
         ent = self._f["data"].get(chrom)
         if not ent:
             return None

@@ -1,0 +1,61 @@
+"""Test helpers: materialise golden inputs as the files the public API reads."""
+import gzip
+import os
+import struct
+
+import numpy as np
+
+
+def write_frag_gz(path, columns, bed6=False):
+    """columns: {contig: (start, stop, mapq, strand)} -> (b)gzip text + a placeholder .tbi."""
+    with gzip.open(path, "wt") as fh:
+        for contig, (st, sp, mq, sd) in columns.items():
+            for a, b, q, s in zip(st.tolist(), sp.tolist(), mq.tolist(), sd.tolist()):
+                if bed6:
+                    fh.write(f"{contig}\t{a}\t{b}\t.\t{q}\t{'+' if s else '-'}\n")
+                else:
+                    fh.write(f"{contig}\t{a}\t{b}\t{q}\t{'+' if s else '-'}\n")
+    open(str(path) + ".tbi", "wb").close()
+    return str(path)
+
+
+def write_text_gz(path, text):
+    with gzip.open(path, "wt") as fh:
+        fh.write(text)
+    open(str(path) + ".tbi", "wb").close()
+    return str(path)
+
+
+def write_2bit(path, seqs):
+    """seqs: [(name, codes A0C1G2T3 uint8, n_mask bool)] -> UCSC .2bit (T0 C1 A2 G3, MSB first)."""
+    remap = np.array([2, 1, 3, 0], np.uint8)
+    recs = []
+    for name, codes, nm in seqs:
+        n = codes.shape[0]
+        u = remap[codes].copy()
+        u[nm] = 0
+        q = np.concatenate([u, np.zeros((-n) % 4, np.uint8)]).reshape(-1, 4)
+        packed = ((q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]).astype(np.uint8)
+        d = np.diff(np.concatenate([[0], nm.astype(np.int8), [0]]))
+        starts, ends = np.flatnonzero(d == 1), np.flatnonzero(d == -1)
+        body = struct.pack("<II", n, len(starts)) + starts.astype("<u4").tobytes() + (ends - starts).astype("<u4").tobytes()
+        body += struct.pack("<II", 0, 0) + packed.tobytes()
+        recs.append((name, body))
+    off = 16 + sum(1 + len(n.encode()) + 4 for n, _ in recs)
+    idx = b""
+    for name, body in recs:
+        idx += bytes([len(name.encode())]) + name.encode() + struct.pack("<I", off)
+        off += len(body)
+    with open(path, "wb") as fh:
+        fh.write(struct.pack("<IIII", 0x1A412743, 0, len(recs), 0) + idx + b"".join(b for _, b in recs))
+    return str(path)
+
+
+def golden_codes(g, name, n):
+    codes = np.unpackbits(g[f"{name}_codes_packed"]).reshape(-1, 2)[:n]
+    return (codes[:, 0] * 2 + codes[:, 1]).astype(np.uint8), np.unpackbits(g[f"{name}_nmask_packed"])[:n].astype(bool)
+
+
+def read_gz(path):
+    with gzip.open(path, "rt") as fh:
+        return fh.read()

@@ -48,7 +48,10 @@ def test_driver_golden_and_run_splitting(manifest, golden):
               "savgol": True, "mean": False, "subtract_edges": False, "edge_size": 500, **c["kwargs"]}
         sites = O.adjust_sites(c["bed"].splitlines(keepends=True), kw["interval_size"], kw["median_window_size"])
         segs, lens = [], []
+        sizes = dict(manifest["synth_small"]["contigs"])
         for contig, s, e in sites:
+            if e > sizes[contig]:
+                continue  # the reference skips it (pyBigWig "Invalid interval bounds!")
             idx = [lut[p] for p in range(s, e) if p in lut]
             if idx:
                 segs.append(raw_val[idx]); lens.append(len(idx))

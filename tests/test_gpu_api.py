@@ -1,0 +1,231 @@
+"""The public API (finaletoolkit_b200.frag / flat namespace) replayed against outputs of the
+unmodified reference (tests/golden/manifest.json): same calls, same kwargs, same files out."""
+import hashlib
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from helpers import golden_codes, read_gz, write_2bit, write_frag_gz, write_text_gz
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fx(tmp_path_factory, manifest):
+    """The reference's 17-fragment fixture as files."""
+    d = tmp_path_factory.mktemp("fx17")
+    m = manifest["fixture17"]
+    p = {"frag": write_text_gz(d / "12.3444.b37.frag.gz", m["frag_gz_text"]),
+         "bed6": write_text_gz(d / "12.3444.b37.frag.bed.gz", m["frag_bed_gz_text"]),
+         "ivl": str(d / "intervals.bed"), "ivl_ov": str(d / "intervals_overlapped.bed"), "cs": str(d / "b37.chrom.sizes"),
+         "dir": d}
+    open(p["ivl"], "w").write(m["intervals_bed"])
+    open(p["ivl_ov"], "w").write(m["intervals_overlapped_bed"])
+    open(p["cs"], "w").write(m["chrom_sizes"])
+    return p
+
+
+@pytest.fixture(scope="module")
+def syn(tmp_path_factory, manifest, golden):
+    d = tmp_path_factory.mktemp("syn")
+    g = golden("synth_small"); m = manifest["synth_small"]
+    cols = {c: tuple(g[f"{c}_{k}"] for k in ("start", "stop", "mapq", "strand")) for c, _ in m["contigs"]}
+    p = {"frag": write_frag_gz(d / "syn.frag.gz", cols), "cs": str(d / "syn.chrom.sizes"), "sites": str(d / "sites.bed"),
+         "ivbed": str(d / "cov_iv.bed"), "dir": d}
+    open(p["cs"], "w").write("".join(f"{c}\t{n}\n" for c, n in m["contigs"]))
+    open(p["sites"], "w").write(m["sites_bed"])
+    open(p["ivbed"], "w").write(m["cov_intervals_bed"])
+    return p
+
+
+def test_wps_fixture(fx, manifest, golden):
+    import finaletoolkit_b200 as F
+    g = golden("fixture17"); m = manifest["fixture17"]
+    for i, c in enumerate(m["wps_cases"]):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r = F.wps(fx["frag"], "12", c["start"], c["stop"], m["chrom_size"], **c["kwargs"])
+        assert r.dtype.names == ("contig", "start", "wps") and r["wps"].dtype == np.int64
+        assert np.array_equal(r["wps"], g[f"wps_{i}"])
+        assert np.all(r["contig"] == "12") and np.array_equal(r["start"], np.arange(c["start"], max(c["stop"], c["start"])))
+    with pytest.warns(UserWarning):
+        assert F.wps(fx["frag"], "12", 5, 5, 100).shape == (0,)
+    with pytest.raises(ValueError):
+        F.wps(fx["frag"], "12", 1, 2, 100, fraction_low=100)
+    with pytest.raises(TypeError):
+        F.wps(fx["frag"], "12", 34444145, 34444155, m["chrom_size"], output_file=3)
+    out = str(fx["dir"] / "w.wig")
+    F.wps(fx["frag"], "12", 34444145, 34444155, m["chrom_size"], output_file=out, quality_threshold=0)
+    assert open(out).read() == "fixedStep\tchrom=12\tstart=34444145\tstep=1\tspan=10\n" + "-1\n" * 5 + "1\n" * 5
+
+
+def test_multi_wps(fx, syn, manifest, golden):
+    import finaletoolkit_b200 as F
+    from finaletoolkit_b200.io import bigwig
+    m = manifest["fixture17"]
+    c = m["multi_wps"][0]
+    out = str(fx["dir"] / "cfg1.bed.gz")
+    assert F.multi_wps(fx["frag"], fx["ivl"], chrom_sizes=fx["cs"], output_file=out, workers=1) == out
+    txt = read_gz(out)
+    assert hashlib.sha256(txt.encode()).hexdigest() == c["sha256_text"] and len(txt.splitlines()) == 7213
+    with pytest.raises(ValueError):   # BED row with start > stop (frag/_multi_wps.py:258-263)
+        F.multi_wps(fx["frag"], fx["ivl_ov"], chrom_sizes=fx["cs"], output_file=str(fx["dir"] / "x.bed.gz"), **m["multi_wps"][1]["kwargs"])
+    with pytest.raises(ValueError):   # suffix rule
+        F.multi_wps(fx["frag"], fx["ivl"], chrom_sizes=fx["cs"], output_file="-")
+    with pytest.raises(ValueError):   # chrom_sizes mandatory for fragment files
+        F.multi_wps(fx["frag"], fx["ivl"], output_file=out)
+    # bigWig output holds the same values (float32) at the same positions
+    bw = str(fx["dir"] / "cfg1.bw")
+    F.multi_wps(fx["frag"], fx["ivl"], chrom_sizes=fx["cs"], output_file=bw)
+    g = golden("fixture17")
+    s, e, v = bigwig.open(bw).intervals_arrays("12", 34440000, 34450000)
+    assert np.array_equal(s, g["bw_cfg1_pos"]) and np.array_equal(v, g["bw_cfg1_val"])
+    # synthetic sites: overlaps, unknown contig (warning), header-order sort
+    ms = manifest["synth_small"]
+    for j, c in enumerate(ms["multi_wps"]):
+        out = str(syn["dir"] / f"mw{j}.bed.gz")
+        with pytest.warns(UserWarning):
+            F.multi_wps(syn["frag"], syn["sites"], chrom_sizes=syn["cs"], output_file=out, **c["kwargs"])
+        assert hashlib.sha256(read_gz(out).encode()).hexdigest() == c["sha256_text"], c
+
+
+def test_coverage(fx, syn, manifest):
+    import finaletoolkit_b200 as F
+    m = manifest["fixture17"]
+    for c in m["single_coverage"]:
+        assert list(F.single_coverage(fx["frag"], **c["kwargs"])) == c["result"]
+    for c in m["coverage"]:
+        out = str(fx["dir"] / ("cov" + c["suffix"]))
+        r = F.coverage(fx["frag"], fx["ivl"], out, **c["kwargs"])
+        assert [list(x) for x in r] == c["results"]
+        assert (read_gz(out) if out.endswith(".gz") else open(out).read()) == c["text"]
+    assert [list(x) for x in F.coverage(fx["frag"], fx["ivl"], None)] == m["coverage"][0]["results"]
+    with pytest.raises(ValueError):
+        F.coverage(fx["frag"], fx["ivl"], "out.txt")
+    from finaletoolkit_b200.exceptions import InvalidInputError
+    with pytest.raises(InvalidInputError):
+        F.single_coverage(fx["frag"], "12", 1, 2, intersect_policy="nope")
+    with pytest.raises(InvalidInputError):
+        F.single_coverage(fx["frag"], None, 5, 10)
+    ms = manifest["synth_small"]
+    for c in ms["coverage"]:
+        out = str(syn["dir"] / "scov.bed")
+        r = F.coverage(syn["frag"], syn["ivbed"], out, **c["kwargs"])
+        assert [list(x) for x in r] == c["results"] and open(out).read() == c["text"]
+    assert [list(F.single_coverage(syn["frag"])), list(F.single_coverage(syn["frag"], quality_threshold=0, min_length=200))] == ms["single_coverage_genome"]
+
+
+def test_frag_length(fx, syn, manifest, golden):
+    import finaletoolkit_b200 as F
+    m = manifest["fixture17"]
+    for c in m["frag_length"]:
+        assert F.frag_length(fx["frag"], **c["kwargs"]).tolist() == c["lengths"]
+    for src, mm in ((fx, m), (syn, manifest["synth_small"])):
+        for c in mm["frag_length_bins"]:
+            out = str(src["dir"] / "flb.tsv")
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                bins, counts = F.frag_length_bins(src["frag"], output_file=out, **c["kwargs"])
+            assert np.asarray(bins).tolist() == c["bins"] and np.asarray(counts).tolist() == c["counts"]
+            if c["text"] is not None and len(c["bins"]):
+                assert open(out).read() == c["text"]
+    with pytest.warns(RuntimeWarning):
+        b, c_ = F.frag_length_bins(fx["frag"], contig="12", start=1, stop=2)
+        assert len(b) == 0 and len(c_) == 0
+    for src, mm, bed in ((fx, m, fx["ivl"]), (syn, manifest["synth_small"], syn["ivbed"])):
+        for c in mm["frag_length_intervals"]:
+            out = str(src["dir"] / "fli.bed")
+            r = F.frag_length_intervals(src["frag"], bed, output_file=out, **c["kwargs"])
+            assert [list(x) for x in r] == c["results"] and open(out).read() == c["text"]
+    g = golden("synth_small")
+    for c in manifest["synth_small"]["frag_length"]:
+        assert np.array_equal(F.frag_length(syn["frag"], **c["kwargs"]), g[c["key"]])
+
+
+def test_host_stream_helpers(fx, manifest):
+    import finaletoolkit_b200 as F
+    m = manifest["fixture17"]
+    fa = F.frag_array(fx["frag"], "12", min_length=120, max_length=180)
+    assert [[int(a), int(b), bool(c)] for a, b, c in fa.tolist()] == m["frag_array_120_180"]
+    assert [list(x) for x in F.frag_generator(fx["frag"], "12", start=34443119, stop=34443538)] == m["frag_generator_detail"]
+    with pytest.warns(UserWarning):
+        from finaletoolkit_b200.io import fragments
+        fragments._CACHE.clear()
+        assert [list(x) for x in F.frag_generator(fx["bed6"], "12", start=34443119, stop=34443538)] == m["frag_generator_bed6"]
+    assert sum(1 for _ in F.frag_generator(fx["frag"], None, quality_threshold=0)) == m["frag_generator_count_all"]
+
+
+def test_end_motifs(tmp_path, manifest, golden):
+    import finaletoolkit_b200 as F
+    g = golden("motif"); m = manifest["motif"]
+    sizes = dict(m["contigs"])
+    cols = {c: tuple(g[f"{c}_{k}"] for k in ("start", "stop", "mapq", "strand")) for c in sizes}
+    frag = write_frag_gz(tmp_path / "m.frag.gz", cols)
+    tb = write_2bit(tmp_path / "m.2bit", [(c, *golden_codes(g, c, n)) for c, n in sizes.items()])
+    for c in m["region_end_motifs"]:
+        d = F.region_end_motifs(frag, c["contig"], c["start"], c["stop"], tb, **c["kwargs"])
+        assert np.array_equal(np.array(list(d.values())), g[c["key"]]) and list(d)[:2] == F.gen_kmers(c["kwargs"].get("k", 4))[:2]
+    for j, c in enumerate(m["end_motifs"]):
+        out = str(tmp_path / f"em{j}.tsv")
+        r = F.end_motifs(frag, tb, output_file=out, **c["kwargs"])
+        assert np.array_equal(np.array(r.frequencies()), g[c["key"]])
+        assert r.motif_diversity_score() == c["mds"] and open(out).read() == c["tsv"]
+    for j, c in enumerate(m["interval_end_motifs"]):
+        out = str(tmp_path / f"iem{j}.tsv")
+        r = F.interval_end_motifs(frag, tb, [tuple(x) for x in m["intervals"]], output_file=out, **c["kwargs"])
+        assert open(out).read() == c["tsv"]
+        r.to_tsv(out, calc_freq=False); assert open(out).read() == c["tsv_counts"]
+        r.mds_bed(out); assert open(out).read() == c["mds_bed"]
+        got = [v for _, v in r.motif_diversity_score(miller_madow=True)]
+        assert all((a == b) or (np.isnan(a) and np.isnan(b)) for a, b in zip(got, c["mds_mm"]))
+    with pytest.raises(ValueError):
+        F.region_end_motifs(frag, "chrM2", 0, 10, tb, negative_strand=True)
+    bad = write_frag_gz(tmp_path / "bad.frag.gz", {"chrM2": (np.array([0, 50]), np.array([3, 220]), np.array([60, 60]), np.array([1, 0]))})
+    with pytest.raises(RuntimeError):
+        F.region_end_motifs(bad, "chrM2", 0, 1000, tb)
+    # the reference's own golden TSVs: regional MDS and round trip (tests/test_end_motifs.py:170-247)
+    f = manifest["fixture17"]
+    p = str(tmp_path / "ivl_dif.tsv"); open(p, "w").write(f["end_motifs_intervals_dif_tsv"])
+    emi = F.EndMotifsIntervals.from_file(p, 30, sep="\t")
+    assert [[list(iv), v] for iv, v in emi.motif_diversity_score()] == f["regional_mds"]
+    assert [[list(iv), v] for iv, v in emi.motif_diversity_score(miller_madow=True)] == f["regional_mds_mm"]
+    p2 = str(tmp_path / "dif.tsv"); open(p2, "w").write(f["end_motifs_dif_tsv"])
+    emf = F.EndMotifFreqs.from_file(p2, 30)
+    assert emf.motif_diversity_score() == f["mds_from_dif_tsv"]
+    emf.to_tsv(str(tmp_path / "rt.tsv")); assert open(tmp_path / "rt.tsv").read() == f["end_motifs_dif_tsv"]
+
+
+def test_adjust_wps(fx, syn, manifest, golden, tmp_path):
+    import finaletoolkit_b200 as F
+    from finaletoolkit_b200.io import bigwig
+    # fixture: multi_wps -> .bw -> adjust_wps, vs the reference's float32 bigWig values
+    g = golden("fixture17"); m = manifest["fixture17"]
+    bw = str(tmp_path / "cfg1.bw")
+    F.multi_wps(fx["frag"], fx["ivl"], chrom_sizes=fx["cs"], output_file=bw)
+    for j, c in enumerate(m["adjust_wps_cases"]):
+        bed = str(tmp_path / f"a{j}.bed"); open(bed, "w").write(c["bed"])
+        out = str(tmp_path / f"a{j}.bw")
+        F.adjust_wps(bw, bed, out, fx["cs"], **c["kwargs"])
+        s, e, v = bigwig.open(out).intervals_arrays("12", 34440000, 34450000)
+        assert np.array_equal(s, g[f"adj_{j}_pos"]) and np.array_equal(e, s + 1)
+        np.testing.assert_allclose(v, g[f"adj_{j}_val_f32"], rtol=1e-5, atol=1e-6)
+    # synthetic: tiled intervals (merge rule), mean, subtract_edges, no savgol, custom windows
+    g = golden("adjust"); ma = manifest["adjust"]
+    bed = str(tmp_path / "tile.bed"); open(bed, "w").write(ma["tile_bed"])
+    bw = str(tmp_path / "tile.bw")
+    F.multi_wps(syn["frag"], bed, chrom_sizes=syn["cs"], output_file=bw)
+    s, e, v = bigwig.open(bw).intervals_arrays("chrB", 0, 80_000)
+    assert np.array_equal(s, g["raw_pos"]) and np.array_equal(v, g["raw_val_f32"])
+    for j, c in enumerate(ma["adjust_cases"]):
+        b = str(tmp_path / f"s{j}.bed"); open(b, "w").write(c["bed"])
+        out = str(tmp_path / f"s{j}.bw")
+        F.adjust_wps(bw, b, out, syn["cs"], **c["kwargs"])
+        r = bigwig.open(out).intervals_arrays("chrB", 0, 80_000)
+        assert np.array_equal(r[0], g[f"adj_{j}_pos"])
+        np.testing.assert_allclose(r[2], g[f"adj_{j}_val_f32"], rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        F.adjust_wps(bw, str(tmp_path / "s0.bed"), str(tmp_path / "e.bw"), syn["cs"], median_window_size=100000)
+    with pytest.raises(ValueError):
+        F.adjust_wps(bw, "intervals.txt", str(tmp_path / "e.bw"), syn["cs"])

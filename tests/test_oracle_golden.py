@@ -227,7 +227,10 @@ def test_adjust_driver(manifest, golden):
               "savgol": True, "mean": False, "subtract_edges": False, "edge_size": 500, **c["kwargs"]}
         sites = O.adjust_sites(c["bed"].splitlines(keepends=True), kw["interval_size"], kw["median_window_size"])
         pos_all, val_all = [], []
+        sizes = dict(manifest["synth_small"]["contigs"])
         for contig, s, e in sites:
+            if e > sizes[contig]:
+                continue  # pyBigWig: "Invalid interval bounds!" -> RuntimeError -> interval skipped (:145-153)
             idx = [lut[p] for p in range(s, e) if p in lut]
             if not idx:
                 continue
