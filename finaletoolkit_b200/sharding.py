@@ -1,0 +1,126 @@
+"""Multi-GPU sharding: contigs -> ranks (no data-path collective) + the one small allreduce.
+
+The reference parallelises with ``multiprocessing.Pool`` over intervals on one host
+(frag/_multi_wps.py:196-198, frag/_coverage.py:212-248, frag/_motif_common.py:592-598); every
+feature is a sum of per-fragment contributions confined to one contig, so the B200 analogue is
+one process per GPU owning whole contigs (greedy LPT by fragment count / length).  WPS,
+per-interval coverage, per-interval length statistics, interval end motifs and adjust_wps need
+NO communication.  Only genome-wide scalars / histograms - ``coverage(normalize=True)``'s total
+(frag/_coverage.py:215-254), ``frag_length_bins``' genome-wide dict (frag/_frag_length.py:421),
+``end_motifs``' 4^k counts (frag/_motif_common.py:599-609) - are combined, with a single
+``all_reduce(SUM)`` over one packed int64 buffer (NCCL over NVLink on GPUs, gloo in CPU tests)
+plus a ``MIN`` reduce of first-seen keys when the reference's dict order matters.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Iterable, List, Sequence
+
+import numpy as np
+
+__all__ = ["lpt_pack", "my_contigs", "DistContext", "pack_partials", "unpack_partials",
+           "merge_first_seen"]
+
+FIRST_SEEN_NONE = np.iinfo(np.int64).max
+
+
+def lpt_pack(weights: Dict[str, int], n_ranks: int) -> List[List[str]]:
+    """Greedy longest-processing-time packing of contigs onto ranks (deterministic).
+
+    Returns one contig list per rank, each in the original (file / header) order so that
+    per-rank outputs concatenate in header order within a rank.
+    """
+    order = {c: i for i, c in enumerate(weights)}
+    loads = [0] * n_ranks
+    bins: List[List[str]] = [[] for _ in range(n_ranks)]
+    for c in sorted(weights, key=lambda c: (-weights[c], order[c])):
+        r = min(range(n_ranks), key=lambda r: (loads[r], r))
+        bins[r].append(c)
+        loads[r] += weights[c]
+    return [sorted(b, key=order.get) for b in bins]
+
+
+def my_contigs(weights: Dict[str, int], rank: int, world: int) -> List[str]:
+    return lpt_pack(weights, world)[rank]
+
+
+class DistContext:
+    """Thin wrapper over torch.distributed (if initialised); world 1 otherwise."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank() if self.on else 0
+        self.world = dist.get_world_size() if self.on else 1
+
+    def all_reduce_sum(self, t):
+        if self.on and self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t
+
+    def all_reduce_min(self, t):
+        if self.on and self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return t
+
+    def barrier(self):
+        if self.on and self.world > 1:
+            self.dist.barrier()
+
+
+def pack_partials(total: int, hist, motif=None):
+    """One int64 buffer [total, hist..., motif...] -> a single all_reduce(SUM)."""
+    import torch
+    parts = [torch.as_tensor([int(total)], dtype=torch.int64, device=hist.device), hist.reshape(-1).to(torch.int64)]
+    if motif is not None:
+        parts.append(motif.reshape(-1).to(torch.int64))
+    return torch.cat(parts)
+
+
+def unpack_partials(buf, n_hist: int, n_motif: int = 0):
+    total = int(buf[0].item())
+    hist = buf[1: 1 + n_hist]
+    motif = buf[1 + n_hist: 1 + n_hist + n_motif] if n_motif else None
+    return total, hist, motif
+
+
+def first_seen_keys(first_idx, contig_order: int):
+    """Genome-wide stream position of each length's first occurrence: (contig order, row index).
+
+    ``first_idx`` is the kernel's per-contig int32 first-seen index (INT32_MAX = absent)."""
+    import torch
+    key = first_idx.to(torch.int64) + (int(contig_order) << 32)
+    return torch.where(first_idx == 2 ** 31 - 1, torch.full_like(key, FIRST_SEEN_NONE), key)
+
+
+def merge_first_seen(keys: Iterable):
+    """Element-wise min over per-contig key vectors (local part of the MIN reduce)."""
+    import torch
+    out = None
+    for k in keys:
+        out = k.clone() if out is None else torch.minimum(out, k)
+    return out
+
+
+def genome_length_dict(ctx: DistContext, per_contig: Sequence[tuple], n_bins: int) -> dict:
+    """Rebuild the reference's genome-wide ``length -> count`` dict in first-seen order from
+    per-contig (contig_order, hist, first_idx) partials that live on different ranks.
+
+    Every rank contributes the contigs it owns (possibly none); two tiny collectives
+    (SUM of histograms, MIN of first-seen keys) give every rank the same dict.
+    """
+    import torch
+    dev = per_contig[0][1].device if per_contig else torch.device("cpu")
+    hist = torch.zeros(n_bins, dtype=torch.int64, device=dev)
+    keys = torch.full((n_bins,), FIRST_SEEN_NONE, dtype=torch.int64, device=dev)
+    for order, h, f in per_contig:
+        hist[: h.numel()] += h.reshape(-1).to(torch.int64)
+        k = first_seen_keys(f.reshape(-1), order)
+        keys[: k.numel()] = torch.minimum(keys[: k.numel()], k)
+    ctx.all_reduce_sum(hist)
+    ctx.all_reduce_min(keys)
+    h, k = hist.cpu().numpy(), keys.cpu().numpy()
+    nz = np.flatnonzero(h)
+    nz = nz[np.argsort(k[nz], kind="stable")]
+    return {int(L): int(h[L]) for L in nz}

@@ -1,7 +1,7 @@
 """Synthetic fragment sets and 2-bit genomes.
 
 Host-side numpy only.  The distributions are the ones the measurement
-contract fixes so that the CUDA path, the oracle and the CPU baseline all see
+contract fixes so that the CUDA path, its CPU checker and the CPU baseline all see
 identical inputs:
 
 * ``start ~ U{0 .. len-L}``, then sorted ascending (coordinate-sorted like a

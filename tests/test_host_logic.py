@@ -1,0 +1,256 @@
+"""CPU-only tests: host logic of the product, the C ABI surface, and the N>1 sharding path (gloo)."""
+import os
+import re
+import subprocess
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+from helpers import write_2bit, write_frag_gz, write_text_gz
+from oracle import oracle as O
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_library_exports_every_declared_symbol():
+    """include/ftk_b200.h <-> libftk_b200.so <-> the ctypes table (no compute calls)."""
+    from finaletoolkit_b200 import _lib
+    from finaletoolkit_b200.csrc.build import build
+    build()
+    hdr = open(os.path.join(REPO, "include", "ftk_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ftk_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    h = _lib.lib()
+    for name in declared:
+        assert hasattr(h, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    assert h.ftk_abi_version() == 1
+    assert h.ftk_error_string(-1) == b"invalid argument"
+    # the host-only planner is callable without a GPU
+    import ctypes
+    s = np.array([0, 10_000, 7], np.int64); e = np.array([5000, 22_000, 7], np.int64); off = np.array([0, 5000, 17000], np.int64)
+    p = lambda a, t: a.ctypes.data_as(ctypes.POINTER(t))
+    n = h.ftk_wps_plan_tiles(p(s, ctypes.c_int64), p(e, ctypes.c_int64), p(off, ctypes.c_int64), 3, 100_000, 180,
+                             None, None, None, None, None)
+    assert n == 1 + 3  # 5000 -> 1 tile, 12000 -> 3 tiles, degenerate -> 0
+
+
+def test_no_cpu_fallback():
+    """Without CUDA every feature fails loudly instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import finaletoolkit_b200 as F
+    from finaletoolkit_b200._lib import FtkLibraryError
+    cols = {"c": (np.array([1, 5]), np.array([150, 170]), np.array([60, 60]), np.array([1, 0]))}
+    with pytest.raises(FtkLibraryError):
+        F.wps(cols, "c", 0, 100, 1000)
+    with pytest.raises(FtkLibraryError):
+        F.single_coverage(cols, "c", 0, 100)
+    with pytest.raises(FtkLibraryError):
+        F.frag_length_bins(cols)
+
+
+def test_product_never_imports_oracle():
+    for root, _, files in os.walk(os.path.join(REPO, "finaletoolkit_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                txt = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|ftk_oracle|libftk_oracle", txt, flags=re.M), \
+                    f"{f} references the oracle"
+
+
+def test_read_sites_matches_oracle(tmp_path, manifest):
+    from finaletoolkit_b200.frag._multi_wps import _read_sites
+    from finaletoolkit_b200.frag._adjust_wps import _read_adjust_sites
+    m = manifest["synth_small"]
+    sizes = dict(m["contigs"])
+    bed = tmp_path / "s.bed"; bed.write_text(m["sites_bed"])
+    for isz in (5000, 2000, 600, 2):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            c, s, e = _read_sites(str(bed), isz, list(sizes), sizes)
+        order = {k: i for i, k in enumerate(sizes)}
+        got = sorted(zip(c, s, e), key=lambda t: (order[t[0]], t[1]))
+        assert got == O.read_sites(m["sites_bed"].splitlines(), isz, sizes)
+    ab = tmp_path / "a.bed"; ab.write_text(manifest["adjust"]["tile_bed"])
+    assert _read_adjust_sites(str(ab), 5000, 1000) == O.adjust_sites(manifest["adjust"]["tile_bed"].splitlines(keepends=True), 5000, 1000)
+    with pytest.raises(ValueError):
+        _read_adjust_sites("x.txt", 5000, 1000)
+
+
+def test_fragment_loader(tmp_path, manifest):
+    from finaletoolkit_b200.exceptions import MissingIndexError, UnsupportedFormatError
+    from finaletoolkit_b200.io import load_fragments
+    m = manifest["fixture17"]
+    p = write_text_gz(tmp_path / "a.frag.gz", m["frag_gz_text"])
+    t = load_fragments(p)
+    assert t.contigs == ["12"] and t.n_fragments() == 17
+    st, sp, mq, sd = t.host("12")
+    assert st[0] == 34443118 and sp[0] == 34443284 and mq[4] == 54 and sd[3] == 0 and st.dtype == np.int32
+    assert load_fragments(p) is t  # cached
+    # malformed rows are skipped, BED6 is detected with a warning
+    bad = m["frag_gz_text"].splitlines()
+    bad.insert(2, "12\tx\t5\t60\t+"); bad.insert(5, "12\t7")
+    t2 = load_fragments(write_text_gz(tmp_path / "b.frag.gz", "\n".join(bad) + "\n"))
+    assert t2.n_fragments() == 17
+    with pytest.warns(UserWarning):
+        assert load_fragments(write_text_gz(tmp_path / "c.bed.gz", m["frag_bed_gz_text"])).n_fragments() == 17
+    with pytest.raises(FileNotFoundError):
+        load_fragments(str(tmp_path / "missing.frag.gz"))
+    (tmp_path / "noidx.frag.gz").write_bytes(open(p, "rb").read())
+    with pytest.raises(MissingIndexError):
+        load_fragments(str(tmp_path / "noidx.frag.gz"))
+    (tmp_path / "x.txt").write_text("hi")
+    with pytest.raises(UnsupportedFormatError):
+        load_fragments(str(tmp_path / "x.txt"))
+
+
+def test_reference_wrapper(tmp_path):
+    from finaletoolkit_b200.exceptions import ContigNotFoundError, OutOfBoundsError
+    from finaletoolkit_b200.io import ReferenceWrapper
+    from finaletoolkit_b200.synth import pack_twobit, synth_twobit
+    codes, nm = synth_twobit(5003, 0, telomere=100, n_blocks=2, block_len=50)
+    tb = write_2bit(tmp_path / "r.2bit", [("chrZ", codes, nm), ("s", codes[:7], nm[:7] & False)])
+    r = ReferenceWrapper(tb)
+    assert r.chroms == {"chrZ": 5003, "s": 7}
+    seq = np.frombuffer(b"ACGT", np.uint8)[codes].copy(); seq[nm] = ord("N")
+    assert r.sequence("chrZ") == seq.tobytes().decode() and r.sequence("chrZ", 120, 131) == seq[120:131].tobytes().decode()
+    assert r["chrZ"][200:204] == seq[200:204].tobytes().decode() and len(r["chrZ"]) == 5003
+    with pytest.raises(OutOfBoundsError):
+        r.sequence("chrZ", 5000, 5004)
+    assert r.sequence("chrZ", 5000, 5004, fail_on_excess_range=False) == seq[5000:5003].tobytes().decode()
+    with pytest.raises(ContigNotFoundError):
+        r.sequence("nope", 0, 1)
+    with pytest.raises(FileNotFoundError):
+        ReferenceWrapper(str(tmp_path / "none.2bit"))
+    fa = tmp_path / "r.fa"
+    fa.write_text(">chrZ desc\n" + "\n".join(seq.tobytes().decode()[i:i + 60] for i in range(0, 5003, 60)) + "\n")
+    f = ReferenceWrapper(str(fa))
+    assert f.chroms == {"chrZ": 5003} and f.sequence("chrZ", 90, 140) == r.sequence("chrZ", 90, 140)
+    # device packing layout: base i at bits 2*(i%16) of word i//16, N bit i%32 of word i//32
+    sw, nw = pack_twobit(codes, nm)
+    i = np.arange(5003)
+    assert np.array_equal((sw[i // 16] >> (2 * (i % 16))) & 3, codes) and np.array_equal((nw[i // 32] >> (i % 32)) & 1, nm.astype(np.uint32))
+
+
+def test_bigwig_roundtrip_and_real_file_layout(tmp_path):
+    from finaletoolkit_b200.io import bigwig
+    p = str(tmp_path / "a.bw")
+    rng = np.random.default_rng(1)
+    v = rng.integers(-40, 40, 100_000).astype(np.float64)
+    with bigwig.open(p, "w") as w:
+        w.addHeader([("2", 5_000_000), ("10", 4_000_000)])
+        w.addEntries("2", 123, values=v, span=1, step=1)
+        w.addEntries("2", 2_000_000, values=v[:10], span=1, step=1)
+        st = np.arange(50, 20_050)
+        w.addEntries(["10"] * st.size, st, ends=st + 1, values=np.sin(st))
+        with pytest.raises(RuntimeError):
+            w.addEntries("2", 5, values=[1.0], span=1, step=1)       # out of order
+        with pytest.raises(RuntimeError):
+            w.addEntries("zz", 5, values=[1.0], span=1, step=1)      # unknown contig
+    r = bigwig.open(p)
+    assert r.chroms() == {"2": 5_000_000, "10": 4_000_000}
+    s, e, x = r.intervals_arrays("2", 0, 5_000_000)
+    assert np.array_equal(x[:100_000], v.astype(np.float32)) and s[0] == 123 and s[100_000] == 2_000_000
+    assert r.intervals("2", 123 + 99_999, 2_000_001) == ((123 + 99_999, 123 + 100_000, float(np.float32(v[-1]))), (2_000_000, 2_000_001, float(np.float32(v[0]))))
+    assert r.intervals("10", 0, 50) is None
+    assert np.allclose(r.intervals_arrays("10", 0, 4_000_000)[2], np.sin(st).astype(np.float32))
+    with pytest.raises(RuntimeError):
+        r.intervals("2", 10, 5_000_001)   # pyBigWig: "Invalid interval bounds!"
+    hd = r.header()
+    assert hd["nBasesCovered"] == 100_000 + 10 + 20_000 and hd["minVal"] <= -39
+
+
+def test_savgol_tables_match_scipy():
+    from scipy.signal import savgol_coeffs, savgol_filter
+    from finaletoolkit_b200.device import savgol_tables
+    x = np.random.default_rng(0).normal(size=300)
+    for w, d in [(21, 2), (11, 3), (31, 4), (5, 2), (3, 1)]:
+        c, ef, el = savgol_tables(w, d)
+        y = savgol_filter(x, w, d)
+        h = w // 2
+        assert np.abs(c - savgol_coeffs(w, d)).max() < 1e-11
+        assert np.abs(ef @ x[:w] - y[:h]).max() < 1e-10 and np.abs(el @ x[-w:] - y[-h:]).max() < 1e-10
+    with pytest.raises(ValueError):
+        savgol_tables(20, 2)
+
+
+def test_lpt_packing():
+    from finaletoolkit_b200.sharding import lpt_pack
+    from finaletoolkit_b200.synth import B37_CONTIGS
+    w = dict(B37_CONTIGS)
+    tot = sum(w.values())
+    for n, bound in [(1, 0.0), (2, 0.01), (4, 0.02), (8, 0.05)]:
+        bins = lpt_pack(w, n)
+        assert sorted(c for b in bins for c in b) == sorted(w)
+        loads = [sum(w[c] for c in b) for b in bins]
+        assert max(loads) / (tot / n) - 1 <= bound, (n, loads)
+        order = {c: i for i, c in enumerate(w)}
+        assert all(b == sorted(b, key=order.get) for b in bins)
+
+
+_GLOO_WORKER = r'''
+import os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["FTK_REPO"])
+from finaletoolkit_b200.sharding import DistContext, genome_length_dict, lpt_pack, pack_partials, unpack_partials
+from finaletoolkit_b200.synth import synth_fragments
+from oracle import oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["FTK_PORT"],
+                        rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+ctx = DistContext()
+contigs = {"a": 50_000, "b": 30_000, "c": 80_000, "d": 10_000, "e": 45_000}
+mine = lpt_pack(contigs, ctx.world)[ctx.rank]
+order = {c: i for i, c in enumerate(contigs)}
+n_bins = 601
+parts, total, motif = [], 0, torch.zeros(256, dtype=torch.int64)
+for c in mine:   # per-contig partials as the CUDA kernels would deliver them (here: from the oracle)
+    st, sp, mq, sd = synth_fragments(contigs[c], contigs[c] // 5, order[c], seed_base=4000)
+    fr = O.Frags(st, sp, mq, sd)
+    d = O.length_dist(fr, None, None, 0, None, "midpoint", 30)
+    hist = torch.zeros(n_bins, dtype=torch.int64); first = torch.full((n_bins,), 2**31 - 1, dtype=torch.int32)
+    L = (sp - st); ok = (mq >= 30)
+    for i in np.flatnonzero(ok):
+        hist[L[i]] += 1
+        first[L[i]] = min(int(first[L[i]]), int(i))
+    assert {int(k): int(hist[k]) for k in torch.nonzero(hist).flatten()} == {k: v for k, v in sorted(d.items())}
+    parts.append((order[c], hist, first)); total += int(hist.sum()); motif[order[c]] += 7
+buf = pack_partials(total, torch.zeros(n_bins, dtype=torch.int64) if not parts else sum(p[1] for p in parts), motif)
+ctx.all_reduce_sum(buf)
+tot, hist, mot = unpack_partials(buf, n_bins, 256)
+d = genome_length_dict(ctx, parts, n_bins)
+if ctx.rank == 0:
+    print(json.dumps({"total": tot, "hist_sum": int(hist.sum()), "motif": mot[:5].tolist(), "keys": list(d)[:40], "vals": list(d.values())[:40], "n": len(d)}))
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_gloo_world2_genome_histogram(tmp_path):
+    """World-size-2 run of the N>1 host path on CPU (gloo): LPT sharding by contig, one packed
+    SUM all-reduce + the first-seen MIN reduce; result must equal the single-process stream."""
+    from finaletoolkit_b200.synth import synth_fragments
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", FTK_REPO=REPO, FTK_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=240) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    import json
+    got = json.loads(outs[0][0].strip().splitlines()[-1])
+    # single-process expectation: contigs streamed in file order a..e
+    contigs = {"a": 50_000, "b": 30_000, "c": 80_000, "d": 10_000, "e": 45_000}
+    dicts = []
+    for i, (c, n) in enumerate(contigs.items()):
+        st, sp, mq, sd = synth_fragments(n, n // 5, i, seed_base=4000)
+        dicts.append(O.length_dist(O.Frags(st, sp, mq, sd), None, None, 0, None, "midpoint", 30))
+    exp = O.merge_dists(dicts)
+    assert got["total"] == sum(exp.values()) == got["hist_sum"] and got["n"] == len(exp)
+    assert got["keys"] == list(exp)[:40] and got["vals"] == list(exp.values())[:40]
+    assert got["motif"] == [7, 7, 7, 7, 7]
