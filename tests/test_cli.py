@@ -30,8 +30,10 @@ def test_mds_commands(tmp_path, manifest):
     from finaletoolkit_b200.cli.main_cli import main_cli
     f = manifest["fixture17"]
     p = tmp_path / "dif.tsv"; p.write_text(f["end_motifs_dif_tsv"])
-    r = CliRunner().invoke(main_cli, ["mds", str(p)])
-    assert r.exit_code == 0 and float(r.output) == f["mds_from_dif_tsv"]
+    import subprocess, sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "finaletoolkit_b200.cli", "mds", str(p)], capture_output=True, text=True, cwd=repo)
+    assert r.returncode == 0 and float(r.stdout) == f["mds_from_dif_tsv"]
     p2 = tmp_path / "ivl.tsv"; p2.write_text(f["end_motifs_intervals_dif_tsv"])
     out = tmp_path / "rmds.bed"
     assert CliRunner().invoke(main_cli, ["regional-mds", str(p2), str(out)]).exit_code == 0
@@ -44,9 +46,12 @@ def test_coverage_stdout(tmp_path, manifest):
     m = manifest["fixture17"]
     frag = write_text_gz(tmp_path / "a.frag.gz", m["frag_gz_text"])
     ivl = tmp_path / "intervals.bed"; ivl.write_text(m["intervals_bed"])
-    r = CliRunner().invoke(main_cli, ["coverage", frag, str(ivl), "-n"])
-    assert r.exit_code == 0, r.output
-    assert "12\t34443118\t34443538\t.\t0.25" in r.output and "12\t34444968\t34446115\t.\t0.4375" in r.output
+    import subprocess, sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "finaletoolkit_b200.cli", "coverage", frag, str(ivl), "-n"],
+                       capture_output=True, text=True, cwd=repo)
+    assert r.returncode == 0, r.stderr
+    assert "12\t34443118\t34443538\t.\t0.25" in r.stdout and "12\t34444968\t34446115\t.\t0.4375" in r.stdout
     # wps with the default '-o -' is a ValueError in the reference too
     cs = tmp_path / "cs"; cs.write_text(m["chrom_sizes"])
     r = CliRunner().invoke(main_cli, ["wps", frag, str(ivl), "--chrom-sizes", str(cs)])
