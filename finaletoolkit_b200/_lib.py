@@ -34,6 +34,8 @@ SYMBOLS = {
     "ftk_wps_tile_ranges": (c_int, [_P, c_int64, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
     "ftk_wps_tiles_i32": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int64,
                                   c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
+    "ftk_wps_tiles_i16": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int64,
+                                  c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "ftk_interval_hist_u64": (c_int, [_P, _P, _P, c_int64, c_int32, _P, _P, c_int64,
                                       c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                       _P, _P, _P, _P, _P]),

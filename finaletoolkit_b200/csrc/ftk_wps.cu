@@ -119,10 +119,32 @@ __device__ __forceinline__ void wps_scatter(int *__restrict__ D, const WpsParams
 // Block prefix scan of D and the store of the tile.  Lane owns int4 groups, warp owns a
 // contiguous span, one barrier for the warp totals.  `sync` = the CTA-wide (or
 // consumer-wide) barrier of the calling kernel.
-template <bool ODD, typename Sync>
+// Store four consecutive scores.  int32: one 128-bit streaming store.  int16 (halves the
+// device->host bytes of the end-to-end path): one 64-bit store + a range check that raises
+// *overflow so the caller can redo the launch in int32 (|WPS| <= local depth, so this needs a
+// > 32767-fold pile-up).
+__device__ __forceinline__ void store4(int32_t *p, const int4 &r, int *) {
+    st_stream4(reinterpret_cast<int4 *>(p), r);
+}
+__device__ __forceinline__ void store4(int16_t *p, const int4 &r, int *overflow) {
+    const unsigned bad = ((unsigned)(r.x + 32768) | (unsigned)(r.y + 32768) | (unsigned)(r.z + 32768) |
+                          (unsigned)(r.w + 32768)) >> 16;
+    if (bad) atomicOr(overflow, 1);
+    int2 v;
+    v.x = (r.x & 0xffff) | (r.y << 16);
+    v.y = (r.z & 0xffff) | (r.w << 16);
+    asm volatile("st.global.L1::no_allocate.v2.s32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void store1(int32_t *p, int v, int *) { *p = v; }
+__device__ __forceinline__ void store1(int16_t *p, int v, int *overflow) {
+    if ((unsigned)(v + 32768) >> 16) atomicOr(overflow, 1);
+    *p = (int16_t)v;
+}
+
+template <bool ODD, typename OutT, typename Sync>
 __device__ __forceinline__ void wps_scan_store(int *__restrict__ D, int *__restrict__ warp_tot,
                                                const WpsParams &P, const TileCtx &T,
-                                               int32_t *__restrict__ dst, int tid, Sync sync) {
+                                               OutT *__restrict__ dst, int *overflow, int tid, Sync sync) {
     const int lane = tid & 31, warp = tid >> 5;
     int4 v[kWpsIters];
     int carry = 0;
@@ -149,18 +171,18 @@ __device__ __forceinline__ void wps_scan_store(int *__restrict__ D, int *__restr
     for (int w = 0; w < kWpsWarps; ++w) offset += (w < warp) ? warp_tot[w] : 0;
 
     if (!ODD) {
-        const bool aligned = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+        const bool aligned = ((reinterpret_cast<uintptr_t>(dst) & (4 * sizeof(OutT) - 1)) == 0);
 #pragma unroll
         for (int j = 0; j < kWpsIters; ++j) {
             const int base = span0 + j * 128 + lane * 4;
             const int4 r = make_int4(v[j].x + offset, v[j].y + offset, v[j].z + offset, v[j].w + offset);
             if (aligned && base + 3 < T.len) {
-                st_stream4(reinterpret_cast<int4 *>(dst + base), r);
+                store4(dst + base, r, overflow);
             } else {
-                if (base + 0 < T.len) dst[base + 0] = r.x;
-                if (base + 1 < T.len) dst[base + 1] = r.y;
-                if (base + 2 < T.len) dst[base + 2] = r.z;
-                if (base + 3 < T.len) dst[base + 3] = r.w;
+                if (base + 0 < T.len) store1(dst + base + 0, r.x, overflow);
+                if (base + 1 < T.len) store1(dst + base + 1, r.y, overflow);
+                if (base + 2 < T.len) store1(dst + base + 2, r.z, overflow);
+                if (base + 3 < T.len) store1(dst + base + 3, r.w, overflow);
             }
         }
     } else {
@@ -174,7 +196,7 @@ __device__ __forceinline__ void wps_scan_store(int *__restrict__ D, int *__restr
         sync();
         for (int k = tid; k < T.len; k += kWpsThreads) {
             const int c = T.p0 + k;
-            dst[k] = D[c - ((c - P.a) & 1) - T.g0];
+            store1(dst + k, D[c - ((c - P.a) & 1) - T.g0], overflow);
         }
         sync();  // D is recycled by the caller
     }
@@ -184,14 +206,14 @@ __device__ __forceinline__ void wps_scan_store(int *__restrict__ D, int *__restr
 // Kernel A ("direct"): one CTA per tile, fragments streamed with 128-bit loads.
 // Kept as the simple variant; the pipelined kernel below is the default.
 // ---------------------------------------------------------------------------
-template <bool ODD>
+template <bool ODD, typename OutT>
 __global__ void __launch_bounds__(kWpsThreads)
 wps_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
                 const uint8_t *__restrict__ frag_mapq,
                 const int32_t *__restrict__ tile_p0, const int32_t *__restrict__ tile_len,
                 const int32_t *__restrict__ tile_mid_lo, const int32_t *__restrict__ tile_mid_hi,
                 const int64_t *__restrict__ tile_out_off, const int64_t *__restrict__ ranges,
-                WpsParams P, int32_t *__restrict__ out) {
+                WpsParams P, OutT *__restrict__ out, int *__restrict__ overflow) {
     __shared__ __align__(16) int D[kWpsCap];
     __shared__ int warp_tot[kWpsWarps];
 
@@ -245,7 +267,7 @@ wps_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restric
                         frag_mapq ? (int)__ldcs(frag_mapq + lo_al + i) : 255);
     }
     __syncthreads();
-    wps_scan_store<ODD>(D, warp_tot, P, T, out + tile_out_off[tile], tid, [] { __syncthreads(); });
+    wps_scan_store<ODD>(D, warp_tot, P, T, out + tile_out_off[tile], overflow, tid, [] { __syncthreads(); });
 }
 
 // ---------------------------------------------------------------------------
@@ -320,14 +342,14 @@ __device__ __forceinline__ void consumer_sync() {
     asm volatile("bar.sync 1, %0;" :: "n"(kWpsThreads) : "memory");
 }
 
-template <bool ODD>
+template <bool ODD, typename OutT>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
 wps_stream_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
                   const uint8_t *__restrict__ frag_mapq, int64_t n_frag,
                   const int32_t *__restrict__ tile_p0, const int32_t *__restrict__ tile_len,
                   const int32_t *__restrict__ tile_mid_lo, const int32_t *__restrict__ tile_mid_hi,
                   const int64_t *__restrict__ tile_out_off, const int64_t *__restrict__ ranges,
-                  int n_tiles, WpsParams P, int32_t *__restrict__ out) {
+                  int n_tiles, WpsParams P, OutT *__restrict__ out, int *__restrict__ overflow) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StreamSmem &S = *reinterpret_cast<StreamSmem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -431,7 +453,7 @@ wps_stream_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restr
         consumer_sync();                                // scatter done; stage buffers are free
         if (tid == 0) mbar_arrive(&S.empty_bar[stage]);  // hand the stage back to the producer
         if (d.last)
-            wps_scan_store<ODD>(S.D, S.warp_tot, P, T, out + d.out_off, tid, [] { consumer_sync(); });
+            wps_scan_store<ODD>(S.D, S.warp_tot, P, T, out + d.out_off, overflow, tid, [] { consumer_sync(); });
         stage ^= 1;
         if (stage == 0) phase ^= 1u;
     }
@@ -509,17 +531,17 @@ extern "C" int ftk_wps_tile_ranges(const int32_t *frag_start, int64_t n_frag,
 static int g_wps_impl = 0;  // 0 = stream (TMA pipeline, default), 1 = direct (one CTA per tile)
 extern "C" void ftk_debug_set_wps_impl(int impl) { g_wps_impl = impl; }
 
-template <bool ODD>
+template <bool ODD, typename OutT>
 static int launch_wps(const int32_t *frag_start, const int32_t *frag_stop, const uint8_t *frag_mapq,
                       int64_t n_frag, const int32_t *tile_p0, const int32_t *tile_len,
                       const int32_t *tile_mid_lo, const int32_t *tile_mid_hi,
                       const int64_t *tile_out_off, int64_t n_tiles, const ftk::WpsParams &P,
-                      const int64_t *ranges, int32_t *out, cudaStream_t stream) {
+                      const int64_t *ranges, OutT *out, int *overflow, cudaStream_t stream) {
     using namespace ftk;
     if (g_wps_impl == 1) {
-        wps_tile_kernel<ODD><<<(unsigned)n_tiles, kWpsThreads, 0, stream>>>(
+        wps_tile_kernel<ODD, OutT><<<(unsigned)n_tiles, kWpsThreads, 0, stream>>>(
             frag_start, frag_stop, frag_mapq, tile_p0, tile_len, tile_mid_lo, tile_mid_hi, tile_out_off,
-            ranges, P, out);
+            ranges, P, out, overflow);
         FTK_CHECK_LAUNCH("wps_tile_kernel");
         return FTK_OK;
     }
@@ -532,27 +554,27 @@ static int launch_wps(const int32_t *frag_start, const int32_t *frag_stop, const
         FTK_CUDA_TRY(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
     const int smem = (int)sizeof(StreamSmem);
     if (!attr_set[dev]) {
-        FTK_CUDA_TRY(cudaFuncSetAttribute(wps_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        FTK_CUDA_TRY(cudaFuncSetAttribute(wps_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        FTK_CUDA_TRY(cudaFuncSetAttribute(wps_stream_kernel<ODD, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set[dev] = true;
     }
     int64_t grid = (int64_t)sm_count[dev] * kStreamCtasPerSm;  // one persistent CTA per resident slot
     if (grid > n_tiles) grid = n_tiles;
-    wps_stream_kernel<ODD><<<(unsigned)grid, kStreamThreads, smem, stream>>>(
+    wps_stream_kernel<ODD, OutT><<<(unsigned)grid, kStreamThreads, smem, stream>>>(
         frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo, tile_mid_hi, tile_out_off,
-        ranges, (int)n_tiles, P, out);
+        ranges, (int)n_tiles, P, out, overflow);
     FTK_CHECK_LAUNCH("wps_stream_kernel");
     return FTK_OK;
 }
 
-extern "C" int ftk_wps_tiles_i32(const int32_t *frag_start, const int32_t *frag_stop,
-                                 const uint8_t *frag_mapq, int64_t n_frag,
-                                 const int32_t *tile_p0, const int32_t *tile_len,
-                                 const int32_t *tile_mid_lo, const int32_t *tile_mid_hi,
-                                 const int64_t *tile_out_off, int64_t n_tiles,
-                                 int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
-                                 int32_t ranges_ready, int64_t *scratch, int32_t *out,
-                                 ftk_stream_t stream_) {
+template <typename OutT>
+static int wps_tiles_impl(const int32_t *frag_start, const int32_t *frag_stop,
+                          const uint8_t *frag_mapq, int64_t n_frag,
+                          const int32_t *tile_p0, const int32_t *tile_len,
+                          const int32_t *tile_mid_lo, const int32_t *tile_mid_hi,
+                          const int64_t *tile_out_off, int64_t n_tiles,
+                          int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
+                          int32_t ranges_ready, int64_t *scratch, OutT *out, int *overflow,
+                          ftk_stream_t stream_) {
     using namespace ftk;
     if (n_tiles == 0) return FTK_OK;
     int rc = wps_check_args(frag_start, frag_stop, n_frag, tile_p0, tile_len, n_tiles, window_size, max_len, scratch);
@@ -577,8 +599,35 @@ extern "C" int ftk_wps_tiles_i32(const int32_t *frag_start, const int32_t *frag_
         P.len_span = (unsigned)(max_len - P.len_lo);
         P.min_mapq = min_mapq;
     }
-    return odd ? launch_wps<true>(frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo,
-                                  tile_mid_hi, tile_out_off, n_tiles, P, scratch, out, stream)
-               : launch_wps<false>(frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo,
-                                   tile_mid_hi, tile_out_off, n_tiles, P, scratch, out, stream);
+    return odd ? launch_wps<true, OutT>(frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo,
+                                        tile_mid_hi, tile_out_off, n_tiles, P, scratch, out, overflow, stream)
+               : launch_wps<false, OutT>(frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo,
+                                         tile_mid_hi, tile_out_off, n_tiles, P, scratch, out, overflow, stream);
+}
+
+extern "C" int ftk_wps_tiles_i32(const int32_t *frag_start, const int32_t *frag_stop,
+                                 const uint8_t *frag_mapq, int64_t n_frag,
+                                 const int32_t *tile_p0, const int32_t *tile_len,
+                                 const int32_t *tile_mid_lo, const int32_t *tile_mid_hi,
+                                 const int64_t *tile_out_off, int64_t n_tiles,
+                                 int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
+                                 int32_t ranges_ready, int64_t *scratch, int32_t *out,
+                                 ftk_stream_t stream_) {
+    return wps_tiles_impl<int32_t>(frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo,
+                                   tile_mid_hi, tile_out_off, n_tiles, window_size, min_len, max_len, min_mapq,
+                                   ranges_ready, scratch, out, nullptr, stream_);
+}
+
+extern "C" int ftk_wps_tiles_i16(const int32_t *frag_start, const int32_t *frag_stop,
+                                 const uint8_t *frag_mapq, int64_t n_frag,
+                                 const int32_t *tile_p0, const int32_t *tile_len,
+                                 const int32_t *tile_mid_lo, const int32_t *tile_mid_hi,
+                                 const int64_t *tile_out_off, int64_t n_tiles,
+                                 int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
+                                 int32_t ranges_ready, int64_t *scratch, int16_t *out,
+                                 int32_t *overflow_flag, ftk_stream_t stream_) {
+    if (n_tiles > 0 && !overflow_flag) return FTK_E_INVALID;
+    return wps_tiles_impl<int16_t>(frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo,
+                                   tile_mid_hi, tile_out_off, n_tiles, window_size, min_len, max_len, min_mapq,
+                                   ranges_ready, scratch, out, overflow_flag, stream_);
 }

@@ -142,3 +142,32 @@ def test_full_size_properties(dev):
     rng = np.random.default_rng(0)
     for s in rng.integers(0, clen - 5000, 40).tolist():
         assert np.array_equal(ah[s:s + 5000], O.wps_interval(ofr, s, s + 5000, clen, W, lo, hi, q))
+
+
+def test_streamed_pipeline_matches_resident(dev):
+    """Chunked host->device->host pipeline (int16 WPS on the wire) == the resident int32 path."""
+    import torch
+    from finaletoolkit_b200 import device as D
+    from finaletoolkit_b200.pipeline import StreamedContig
+    from finaletoolkit_b200.synth import synth_fragments
+    clen, n = 3_000_000, 900_000
+    st, sp, mq, sd = synth_fragments(clen, n, 5)
+    edges = np.arange(0, clen + 5000, 5000).clip(max=clen)
+    fr = D.ContigFragments(st, sp, mq, sd, device=dev)
+    ref = D.WpsPlan(edges[:-1], edges[1:], clen, 180, dev).run(fr).cpu().numpy()
+    cov, _, _ = D.interval_hist(fr, edges[:-1].tolist(), edges[1:].tolist())
+    tot, hist, _ = D.interval_hist(fr, [0], [None], n_bins=fr.max_len + 1, pooled=True)
+    for chunks in (1, 3, 7):
+        pipe = StreamedContig(torch.from_numpy(st).pin_memory(), torch.from_numpy(sp).pin_memory(),
+                              torch.from_numpy(mq).pin_memory(), edges[:-1], edges[1:], clen, n_chunks=chunks, device=dev)
+        for _ in range(2):   # twice: buffers and events are reused across runs
+            w, c, h, t = pipe.run()
+        assert np.array_equal(w.numpy()[: pipe.n_positions].astype(np.int32), ref)
+        assert np.array_equal(c.numpy(), cov.cpu().numpy()) and int(t[0]) == int(tot[0])
+        assert np.array_equal(h.numpy(), hist.cpu().numpy())
+    # int16 overflow is detected, not silently wrapped: 40000 identical fragments
+    big_s = np.full(40_000, 1000, np.int32); big_e = big_s + 150
+    pipe = StreamedContig(torch.from_numpy(big_s).pin_memory(), torch.from_numpy(big_e).pin_memory(),
+                          torch.full((40_000,), 60, dtype=torch.uint8).pin_memory(), [0], [5000], 10_000, device=dev)
+    with pytest.raises(OverflowError):
+        pipe.run()
