@@ -195,70 +195,112 @@ interval_hist_kernel(const int32_t *__restrict__ frag_start, const int32_t *__re
     }
 }
 
-// Counts only (coverage): one WARP per (interval, split).  A 5-kb interval at 30x holds
-// ~1600 candidates - far too few to amortise a CTA's launch, barrier and reduction latency -
-// so eight independent warps share a CTA, each streaming its own slice with 128-bit loads
-// (kHistUnroll x 3 in flight per lane) and finishing with a shuffle reduction + one atomic.
+// Counts (coverage): one WARP per (interval, split).  A 5-kb interval at 30x holds ~1600
+// candidates - far too few to amortise a CTA's launch, barrier and reduction latency - so eight
+// independent warps share a CTA, each streaming its own slice with 128-bit loads (kHistUnroll x 3
+// in flight per lane) and finishing with a shuffle reduction + one atomic.  PHIST additionally
+// bins the lengths of every counted fragment into ONE pooled histogram (row 0), privatised per
+// CTA in shared memory: per-interval coverage and the length distribution of the union of the
+// intervals in a single pass over the fragments.
+template <bool PHIST>
 __global__ void __launch_bounds__(kHistThreads, 4)
 interval_count_warp_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
                            const uint8_t *__restrict__ frag_mapq,
                            const int32_t *__restrict__ ivl_start, const int32_t *__restrict__ ivl_stop,
-                           const int64_t *__restrict__ ranges, Pred pred, int pooled, int splits,
-                           int64_t n_units, unsigned long long *__restrict__ counts) {
-    const int lane = threadIdx.x & 31;
-    const int64_t unit = (int64_t)blockIdx.x * (kHistThreads / 32) + (threadIdx.x >> 5);
-    if (unit >= n_units) return;
-    const int64_t ivl = unit / splits;
-    const int split = (int)(unit % splits);
-    const int S = __ldg(ivl_start + ivl), E = __ldg(ivl_stop + ivl);
-    const int64_t lo_all = __ldg(ranges + 2 * ivl), hi_all = __ldg(ranges + 2 * ivl + 1);
-    int64_t chunk = (hi_all - lo_all + splits - 1) / splits;
-    chunk = (chunk + 3) & ~(int64_t)3;
-    const int64_t lo = lo_all + (int64_t)split * chunk;
-    const int64_t hi = min(hi_all, lo + chunk);
-    const Stream in_stream(S, E, pred);
+                           const int64_t *__restrict__ ranges, Pred pred, int pooled_counts, int splits,
+                           int64_t n_units, int n_bins, unsigned long long *__restrict__ counts,
+                           unsigned long long *__restrict__ hist, int32_t *__restrict__ first_seen) {
+    __shared__ int s_cnt[PHIST ? kHistSmemBins : 1];
+    __shared__ int s_first[PHIST ? kHistSmemBins : 1];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const bool want_first = PHIST && (first_seen != nullptr);
+    if (PHIST) {
+        for (int b = tid; b < kHistSmemBins; b += kHistThreads) { s_cnt[b] = 0; s_first[b] = INT32_MAX; }
+        __syncthreads();
+    }
+    const int64_t unit = (int64_t)blockIdx.x * (kHistThreads / 32) + (tid >> 5);
+    if (unit < n_units) {
+        const int64_t ivl = unit / splits;
+        const int split = (int)(unit % splits);
+        const int S = __ldg(ivl_start + ivl), E = __ldg(ivl_stop + ivl);
+        const int64_t lo_all = __ldg(ranges + 2 * ivl), hi_all = __ldg(ranges + 2 * ivl + 1);
+        int64_t chunk = (hi_all - lo_all + splits - 1) / splits;
+        chunk = (chunk + 3) & ~(int64_t)3;
+        const int64_t lo = lo_all + (int64_t)split * chunk;
+        const int64_t hi = min(hi_all, lo + chunk);
+        const Stream in_stream(S, E, pred);
 
-    const int64_t lo_al = lo & ~(int64_t)3;
-    const int skip = (int)(lo - lo_al);
-    const int cnt = (hi > lo) ? (int)(hi - lo_al) : 0;
-    const int nvec = cnt >> 2;
-    const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(frag_start + lo_al);
-    const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(frag_stop + lo_al);
-    const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(frag_mapq ? frag_mapq + lo_al : nullptr);
-    unsigned c = 0;
-    for (int v0 = lane; v0 < nvec; v0 += kHistUnroll * 32) {
-        int4 s4[kHistUnroll], e4[kHistUnroll];
-        uchar4 q4[kHistUnroll];
+        const int64_t lo_al = lo & ~(int64_t)3;
+        const int skip = (int)(lo - lo_al);
+        const int cnt = (hi > lo) ? (int)(hi - lo_al) : 0;
+        const int nvec = cnt >> 2;
+        const int base_idx = (int)lo_al;
+        const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(frag_start + lo_al);
+        const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(frag_stop + lo_al);
+        const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(frag_mapq ? frag_mapq + lo_al : nullptr);
+        unsigned c = 0;
+        auto visit = [&](int fs, int fe, int q, int idx, bool masked) {
+            if (masked || !in_stream(fs, fe, q)) return;
+            ++c;
+            if (PHIST) {
+                const int L = fe - fs;
+                if (L < kHistSmemBins) {
+                    atomicAdd(&s_cnt[L], 1);
+                    if (want_first) atomicMin(&s_first[L], idx);
+                } else if (L < n_bins) {
+                    atomicAdd(&hist[L], 1ull);
+                    if (want_first) atomicMin(&first_seen[L], idx);
+                }
+            }
+        };
+        for (int v0 = lane; v0 < nvec; v0 += kHistUnroll * 32) {
+            int4 s4[kHistUnroll], e4[kHistUnroll];
+            uchar4 q4[kHistUnroll];
 #pragma unroll
-        for (int u = 0; u < kHistUnroll; ++u) {
-            const int v = v0 + u * 32;
-            if (v < nvec) {
-                s4[u] = __ldcs(vs + v);
-                e4[u] = __ldcs(ve + v);
-                q4[u] = vq ? __ldcs(vq + v) : make_uchar4(255, 255, 255, 255);
-            } else {
-                s4[u] = make_int4(0, 0, 0, 0);
-                e4[u] = make_int4(-1, -1, -1, -1);  // L < 0: never in a stream
-                q4[u] = make_uchar4(0, 0, 0, 0);
+            for (int u = 0; u < kHistUnroll; ++u) {
+                const int v = v0 + u * 32;
+                if (v < nvec) {
+                    s4[u] = __ldcs(vs + v);
+                    e4[u] = __ldcs(ve + v);
+                    q4[u] = vq ? __ldcs(vq + v) : make_uchar4(255, 255, 255, 255);
+                } else {
+                    s4[u] = make_int4(0, 0, 0, 0);
+                    e4[u] = make_int4(-1, -1, -1, -1);  // L < 0: never in a stream
+                    q4[u] = make_uchar4(0, 0, 0, 0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kHistUnroll; ++u) {
+                const int v = v0 + u * 32;
+                const bool head = (v == 0);  // the widened head: mask fragments left of lo
+                const int i = base_idx + v * 4;
+                visit(s4[u].x, e4[u].x, q4[u].x, i, head && skip > 0);
+                visit(s4[u].y, e4[u].y, q4[u].y, i + 1, head && skip > 1);
+                visit(s4[u].z, e4[u].z, q4[u].z, i + 2, head && skip > 2);
+                visit(s4[u].w, e4[u].w, q4[u].w, i + 3, false);
             }
         }
-#pragma unroll
-        for (int u = 0; u < kHistUnroll; ++u) {
-            const bool head = (v0 + u * 32 == 0);  // the widened head: mask fragments left of lo
-            c += (!(head && skip > 0)) && in_stream(s4[u].x, e4[u].x, q4[u].x);
-            c += (!(head && skip > 1)) && in_stream(s4[u].y, e4[u].y, q4[u].y);
-            c += (!(head && skip > 2)) && in_stream(s4[u].z, e4[u].z, q4[u].z);
-            c += in_stream(s4[u].w, e4[u].w, q4[u].w);
+        {   // tail: at most 3 fragments
+            const int i = nvec * 4 + lane;
+            if (i < cnt && i >= skip)
+                visit(__ldcs(frag_start + lo_al + i), __ldcs(frag_stop + lo_al + i),
+                      frag_mapq ? (int)__ldcs(frag_mapq + lo_al + i) : 255, base_idx + i, false);
+        }
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0 && c) atomicAdd(&counts[pooled_counts ? 0 : ivl], (unsigned long long)c);
+    }
+    if (PHIST) {
+        __syncthreads();
+        const int nb = min(n_bins, kHistSmemBins);
+        for (int b = tid; b < nb; b += kHistThreads) {
+            const int v = s_cnt[b];
+            if (v) {
+                atomicAdd(&hist[b], (unsigned long long)v);
+                if (want_first) atomicMin(&first_seen[b], s_first[b]);
+            }
         }
     }
-    {   // tail: at most 3 fragments
-        const int i = nvec * 4 + lane;
-        if (i < cnt && i >= skip)
-            c += in_stream(__ldcs(frag_start + lo_al + i), __ldcs(frag_stop + lo_al + i),
-                           frag_mapq ? (int)__ldcs(frag_mapq + lo_al + i) : 255);
-    }
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (lane == 0 && c) atomicAdd(&counts[pooled ? 0 : ivl], (unsigned long long)c);
 }
 
 // ---- raw lengths in stream order (frag_length): count / scan / scatter
@@ -391,7 +433,7 @@ extern "C" int ftk_interval_hist_u64(const int32_t *frag_start, const int32_t *f
                                      int64_t *scratch, uint64_t *counts, uint64_t *hist,
                                      int32_t *first_seen, ftk_stream_t stream_) {
     if (n_ivl == 0) return FTK_OK;
-    if (n_frag < 0 || n_ivl < 0 || splits < 1 || n_bins < 0) return FTK_E_INVALID;
+    if (n_frag < 0 || n_ivl < 0 || splits < 1 || n_bins < 0 || pooled < 0 || pooled > 2) return FTK_E_INVALID;
     if (policy != FTK_POLICY_MIDPOINT && policy != FTK_POLICY_ANY) return FTK_E_INVALID;
     if (!ivl_start || !ivl_stop || !scratch || !counts) return FTK_E_INVALID;
     if (n_frag > 0 && (!frag_start || !frag_stop)) return FTK_E_INVALID;
@@ -410,15 +452,19 @@ extern "C" int ftk_interval_hist_u64(const int32_t *frag_start, const int32_t *f
     const unsigned grid = (unsigned)(n_ivl * splits);
     auto *c = reinterpret_cast<unsigned long long *>(counts);
     auto *h = reinterpret_cast<unsigned long long *>(hist);
-    if (n_bins > 0)
+    const int64_t n_units = n_ivl * (int64_t)splits;
+    const int per_cta = kHistThreads / 32;
+    const unsigned wgrid = (unsigned)((n_units + per_cta - 1) / per_cta);
+    if (n_bins > 0 && pooled == FTK_POOL_HIST_ONLY)
+        // per-interval counts + ONE pooled histogram in a single pass
+        interval_count_warp_kernel<true><<<wgrid, kHistThreads, 0, stream>>>(
+            frag_start, frag_stop, frag_mapq, ivl_start, ivl_stop, scratch, pred, 0, splits, n_units, n_bins, c, h, first_seen);
+    else if (n_bins > 0)
         interval_hist_kernel<true><<<grid, kHistThreads, 0, stream>>>(
             frag_start, frag_stop, frag_mapq, ivl_start, ivl_stop, scratch, pred, n_bins, pooled, splits, c, h, first_seen);
-    else {
-        const int64_t n_units = n_ivl * (int64_t)splits;
-        const int per_cta = kHistThreads / 32;
-        interval_count_warp_kernel<<<(unsigned)((n_units + per_cta - 1) / per_cta), kHistThreads, 0, stream>>>(
-            frag_start, frag_stop, frag_mapq, ivl_start, ivl_stop, scratch, pred, pooled, splits, n_units, c);
-    }
+    else
+        interval_count_warp_kernel<false><<<wgrid, kHistThreads, 0, stream>>>(
+            frag_start, frag_stop, frag_mapq, ivl_start, ivl_stop, scratch, pred, pooled, splits, n_units, 0, c, nullptr, nullptr);
     FTK_CHECK_LAUNCH("interval_hist_kernel");
     return FTK_OK;
 }

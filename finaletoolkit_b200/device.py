@@ -233,13 +233,15 @@ def interval_hist(frags: ContigFragments, ivl_start=None, ivl_stop=None, interse
     if ivl_set is None:
         ivl_set = IntervalSet(ivl_start, ivl_stop, dev)
     n_ivl = ivl_set.n
-    rows = 1 if pooled else n_ivl
+    pool_mode = {False: 0, True: 1, "hist": 2}[pooled]   # "hist": per-interval counts + one pooled histogram
+    rows = 1 if pool_mode == 1 else n_ivl
     if out is not None:
         counts, hist, first = out
     else:
+        hrows = 1 if pool_mode else rows
         counts = t.zeros(max(rows, 1), dtype=t.int64, device=dev)
-        hist = t.zeros((max(rows, 1), n_bins), dtype=t.int64, device=dev) if n_bins else None
-        first = (t.full((max(rows, 1), n_bins), 2 ** 31 - 1, dtype=t.int32, device=dev)
+        hist = t.zeros((max(hrows, 1), n_bins), dtype=t.int64, device=dev) if n_bins else None
+        first = (t.full((max(hrows, 1), n_bins), 2 ** 31 - 1, dtype=t.int32, device=dev)
                  if (n_bins and first_seen) else None)
     if n_ivl == 0:
         return counts[:rows], hist, first
@@ -247,7 +249,7 @@ def interval_hist(frags: ContigFragments, ivl_start=None, ivl_stop=None, interse
     check(lib().ftk_interval_hist_u64(
         fs, fe, mq, frags.n, frags.max_len, ivl_set.start.data_ptr(), ivl_set.stop.data_ptr(), n_ivl,
         policy_code(intersect_policy), none_to_ftk(min_length), none_to_ftk(max_length),
-        int(quality_threshold), int(n_bins), int(bool(pooled)), _splits_for(n_ivl, frags.n),
+        int(quality_threshold), int(n_bins), pool_mode, _splits_for(n_ivl, frags.n),
         ivl_set.scratch.data_ptr(), counts.data_ptr(), 0 if hist is None else hist.data_ptr(),
         0 if first is None else first.data_ptr(), _stream_ptr(dev)), "ftk_interval_hist_u64")
     return counts[:rows], hist, first

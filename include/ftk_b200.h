@@ -36,6 +36,11 @@ extern "C" {
 #define FTK_E_CUDA -2      /* a CUDA runtime call or launch failed            */
 #define FTK_E_RANGE -3     /* a size exceeds what the kernel supports         */
 
+/* `pooled` modes of ftk_interval_hist_u64 */
+#define FTK_POOL_NONE 0       /* counts and histogram rows per interval            */
+#define FTK_POOL_ALL 1        /* counts and histogram pooled into row 0            */
+#define FTK_POOL_HIST_ONLY 2  /* counts per interval, ONE pooled histogram (row 0) */
+
 #define FTK_POLICY_MIDPOINT 0
 #define FTK_POLICY_ANY 1
 
@@ -116,7 +121,8 @@ int ftk_wps_tiles_i16(const int32_t *frag_start_dev, const int32_t *frag_stop_de
  * L < n_bins; first_seen[row*n_bins + L] = min fragment index with that
  * length (the dict's first-insertion order, which the reference's fp sums
  * follow, frag/_frag_length.py:213-217).  row = interval index, or 0 when
- * `pooled`.  Outputs are ACCUMULATED: the caller zeroes counts/hist and fills
+ * pooled (FTK_POOL_*: FTK_POOL_HIST_ONLY keeps per-interval counts and pools only
+ * the histogram - coverage + length distribution in one pass).  Outputs are ACCUMULATED: the caller zeroes counts/hist and fills
  * first_seen with INT32_MAX.  n_bins == 0: counts only (hist/first_seen NULL).
  * Each interval is processed by `splits` CTAs.  scratch_dev: int64[2*n_ivl].
  * max_frag_len = max(stop-start) over the contig (bounds the left halo).

@@ -197,3 +197,26 @@ def test_random_counts_vs_oracle(seed, dev):
             exp = O.region_end_motifs(ofr2, seq.tobytes(), a, b, k, mode == 0, mode == 2, q)
             assert np.array_equal(got[j], exp), (k, mode, a, b)
             j += 1
+
+
+def test_fused_coverage_and_pooled_histogram(dev):
+    """pooled="hist": per-interval counts + one pooled histogram in a single pass."""
+    from finaletoolkit_b200 import device as D
+    from finaletoolkit_b200.device import ContigFragments
+    from finaletoolkit_b200.synth import synth_fragments
+    clen, n = 1_500_000, 450_000
+    st, sp, mq, sd = synth_fragments(clen, n, 11)
+    fr = ContigFragments(st, sp, mq, sd, device=dev)
+    nb = fr.max_len + 1
+    edges = np.arange(0, clen + 5000, 5000).clip(max=clen)
+    for ivs, kw in [((edges[:-1].tolist(), edges[1:].tolist()), dict()),
+                    (([0, 1000, 1000, 700_000], [900_000, 5000, 5000, None]), dict(intersect_policy="any", min_length=100, max_length=400, quality_threshold=0))]:
+        cnt, hist, first = D.interval_hist(fr, *ivs, n_bins=nb, pooled="hist", first_seen=True, **kw)
+        c0, h0, f0 = D.interval_hist(fr, *ivs, n_bins=nb, first_seen=True, **kw)
+        assert np.array_equal(cnt.cpu().numpy(), c0.cpu().numpy())
+        assert np.array_equal(hist[0].cpu().numpy(), h0.sum(0).cpu().numpy())
+        assert np.array_equal(first[0].cpu().numpy(), f0.min(0).values.cpu().numpy())
+    # tiling intervals: the pooled histogram is the whole-contig one
+    cnt, hist, _ = D.interval_hist(fr, edges[:-1].tolist(), edges[1:].tolist(), n_bins=nb, pooled="hist")
+    _, hall, _ = D.interval_hist(fr, [0], [None], n_bins=nb, pooled=True)
+    assert np.array_equal(hist.cpu().numpy(), hall.cpu().numpy()) and int(cnt.sum()) == int(hall.sum())
