@@ -11,13 +11,12 @@
 //
 // Raw WPS is integer-valued with a small local range, so the running median is a
 // sliding HISTOGRAM median (add one sample, drop one, walk the median bin): O(1) per
-// output instead of a sort per window.  Work unit = "run": kAdjRun consecutive outputs
+// output instead of a sort per window.  Work unit = "run": run_len consecutive outputs
 // of one segment, owned by ONE thread that slides its private shared-memory histogram
-// (int16 bins, bank-conflict-free layout) along the run; the run also carries its own
-// Savitzky-Golay ring buffer, so median, subtraction and smoothing are fused and the
-// adjusted series never round-trips through HBM.  Runs whose samples are not integers
-// or leave the kAdjBins-wide local window are flagged and redone by the generic
-// kernel (sorted-window insertion, any float input).
+// (int16 bins, bank-conflict-free layout) along the run, fed from warp-cooperative
+// coalesced tile refills.  Runs whose samples are not integers or leave the kAdjBins-wide
+// local window are flagged and redone by the generic kernel (sorted-window insertion, any
+// float input).  Savitzky-Golay is a separate one-thread-per-output stencil kernel.
 // fp64 arithmetic follows numpy's: median of an even window = (lo + hi) / 2 on the
 // shifted values; mean = exact integer sum / w.
 // Roofline: HBM, 4 B in (float32 sample) + 8 B out (float64) per position.
@@ -26,163 +25,193 @@
 namespace ftk {
 
 constexpr int kAdjThreads = 128;
+constexpr int kAdjWarps = kAdjThreads / 32;
 constexpr int kAdjBins = 256;       // local value window of the fast path
-constexpr int kAdjMaxSg = 127;      // Savitzky-Golay window limit (ring buffer)
-constexpr int kAdjRing = 128;
+constexpr int kAdjMaxSg = 127;      // Savitzky-Golay window limit
+constexpr int kAdjTile = 16;        // samples staged per lane per refill
+constexpr int kAdjTilePitch = 20;   // bytes per tile row: 5-word stride, row reads are bank-conflict-free
 
 struct AdjParams {
     int w;            // median / mean window (even)
     int use_mean;
-    int savgol;       // 0: out = adj
-    int sg_w;         // odd, <= kAdjMaxSg
     int run;          // outputs per run
 };
 
-// Emits SG outputs for the run [ja, jb) while adj values arrive in order.
-struct SgEmitter {
-    const double *coef;        // [sg_w] interior stencil (correlation order)
-    const double *edge_first;  // [half][sg_w]
-    const double *edge_last;   // [half][sg_w]
-    double *out;               // segment output base
-    double ring[kAdjRing];
-    int sg_w, half;
-    long long ja, jb, n_out;
-
-    __device__ __forceinline__ void push(long long c, double adj) {
-        ring[c & (kAdjRing - 1)] = adj;
-        // interior output j = c - half
-        const long long j = c - half;
-        if (j >= ja && j < jb && j >= half && j < n_out - half) {
-            double acc = 0.0;
-            for (int i = 0; i < sg_w; ++i) acc += coef[i] * ring[(j - half + i) & (kAdjRing - 1)];
-            out[j] = acc;
-        }
-        if (c == sg_w - 1) {  // first sg_w samples complete: left edge outputs
-            const long long hi = jb < half ? jb : half;
-            for (long long e = ja; e < hi; ++e) {
-                double acc = 0.0;
-                for (int i = 0; i < sg_w; ++i) acc += edge_first[e * sg_w + i] * ring[i & (kAdjRing - 1)];
-                out[e] = acc;
-            }
-        }
-        if (c == n_out - 1) {  // last sg_w samples complete: right edge outputs
-            const long long lo = ja > n_out - half ? ja : n_out - half;
-            for (long long e = lo; e < jb; ++e) {
-                double acc = 0.0;
-                for (int i = 0; i < sg_w; ++i)
-                    acc += edge_last[(e - (n_out - half)) * sg_w + i] * ring[(n_out - sg_w + i) & (kAdjRing - 1)];
-                out[e] = acc;
-            }
-        }
-    }
-};
-
-// which adj indices [ca, cb) a run must compute to emit outputs [ja, jb)
-__device__ __forceinline__ void run_extent(const AdjParams &P, long long ja, long long jb, long long n_out,
-                                           long long &ca, long long &cb) {
-    if (!P.savgol) { ca = ja; cb = jb; return; }
-    const int half = P.sg_w / 2;
-    ca = ja - half; cb = jb + half;
-    if (ja < half) { ca = 0; if (cb < P.sg_w) cb = P.sg_w; }
-    if (jb > n_out - half) { if (ca > n_out - P.sg_w) ca = n_out - P.sg_w; cb = n_out; }
-    if (ca < 0) ca = 0;
-    if (cb > n_out) cb = n_out;
-}
-
-__device__ __forceinline__ long long find_segment(const long long *__restrict__ seg_run_off, int n_seg, long long run) {
-    int lo = 0, hi = n_seg;  // last s with seg_run_off[s] <= run
+__device__ __forceinline__ long long find_segment(const long long *__restrict__ off, int n_seg, long long v) {
+    int lo = 0, hi = n_seg;  // last s with off[s] <= v
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (seg_run_off[mid] <= run) lo = mid; else hi = mid;
+        if (off[mid] <= v) lo = mid; else hi = mid;
     }
     return lo;
 }
 
 // ---------------------------------------------------------------- fast path
-// hist layout: bin-major, slot(tid) = 2*lane + (warp&1) + 64*(warp>>1) so that the 32 lanes
-// of a warp touch 32 distinct banks (two warps share each 32-bit word, 16 bits each).
-__global__ void __launch_bounds__(kAdjThreads)
+// One thread = one run of P.run outputs; it consumes its sample stream g = 0, 1, ... (sample
+// index ca + g): every step adds sample g to its private histogram, drops sample g - w, and once
+// g >= w - 1 emits adj[c] for c = ca + g - w + 1 (centre sample ca + g - w/2 + 1).
+// The three per-lane sequential streams (in, out, centre) would be 32 scattered 4-byte loads per
+// warp instruction; instead each warp refills three 32 x 32 byte tiles with COALESCED loads (row
+// i = 32 consecutive samples of lane i's stream, 128 B per load, stored as histogram bins
+// relative to lane i's base) and every lane then walks its own row from shared memory.
+// hist layout: bin-major, slot(tid) = 2*lane + (warp&1) + 64*(warp>>1): the 32 lanes of a warp hit
+// 32 distinct banks (two warps share each 32-bit word, 16 bits each).  248 bins x 128 threads x
+// int16 + 12.4 KB of tiles = 74.4 KB per CTA -> three CTAs per SM.
+// The median state lives in registers (bin m, c_lt = #samples below bin m, hm = H(m)); the
+// histogram read-modify-writes are side effects off the critical path and H is only re-read
+// when the median bin moves.  Without a shift the adjusted value is an exact half-integer
+// ((2*centre - lo - hi) / 2), computed in integers.
+template <bool MEAN, bool SHIFT>
+__global__ void __launch_bounds__(kAdjThreads, 3)
 adjust_hist_kernel(const float *__restrict__ x, const long long *__restrict__ seg_off,
                    const long long *__restrict__ seg_out_off, const long long *__restrict__ seg_run_off,
                    const double *__restrict__ seg_shift, int n_seg, long long n_runs, AdjParams P,
-                   const double *__restrict__ coef, const double *__restrict__ edge_first,
-                   const double *__restrict__ edge_last, double *__restrict__ out,
-                   unsigned char *__restrict__ fallback) {
-    extern __shared__ short hist_smem[];  // [kAdjBins][kAdjThreads]
+                   double *__restrict__ adj_out, unsigned char *__restrict__ fallback) {
+    extern __shared__ short adj_smem[];
+    short *hist_smem = adj_smem;                                  // [kAdjBins][kAdjThreads]
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    unsigned char *tiles = reinterpret_cast<unsigned char *>(adj_smem + kAdjBins * kAdjThreads) +
+                           warp * (3 * 32 * kAdjTilePitch);
+    unsigned char *t_in = tiles, *t_out = tiles + 32 * kAdjTilePitch, *t_ctr = tiles + 2 * 32 * kAdjTilePitch;
     short *__restrict__ h = hist_smem + (2 * lane + (warp & 1) + 64 * (warp >> 1));
 #define H(b) h[(b) * kAdjThreads]
     for (int b = 0; b < kAdjBins; ++b) H(b) = 0;
 
-    const long long run = (long long)blockIdx.x * kAdjThreads + tid;
-    if (run >= n_runs) return;
-    const long long s = find_segment(seg_run_off, n_seg, run);
-    const long long n = seg_off[s + 1] - seg_off[s];
-    const long long n_out = n - P.w;
-    const float *__restrict__ xs = x + seg_off[s];
-    const double shift = seg_shift ? seg_shift[s] : 0.0;
-    const long long ja = (run - seg_run_off[s]) * P.run;
-    const long long jb = (ja + P.run < n_out) ? ja + P.run : n_out;
-    long long ca, cb;
-    run_extent(P, ja, jb, n_out, ca, cb);
-
-    SgEmitter sg;
-    sg.coef = coef; sg.edge_first = edge_first; sg.edge_last = edge_last;
-    sg.out = out + seg_out_off[s];
-    sg.sg_w = P.sg_w; sg.half = P.sg_w / 2; sg.ja = ja; sg.jb = jb; sg.n_out = n_out;
-
     const int w = P.w;
-    const int kl = (w - 1) >> 1, ku = w >> 1;  // 0-based ranks of the two middle order statistics
-    // bin = value - base; centre the window on the first sample
-    const float x0 = xs[ca];
-    if (x0 != rintf(x0) || fabsf(x0) > 1.0e9f) { fallback[run] = 1; return; }
-    const int base = (int)x0 - kAdjBins / 2;
-    long long isum = 0;
+    const long long run = (long long)blockIdx.x * kAdjThreads + tid;
+    const bool live = run < n_runs;
+    int G = 0;                       // steps of this lane's stream
+    int limit = 0;                   // samples available from xs_ca on (clamped to int32)
+    const float *xs_ca = x;          // &segment[ca]
+    double *out_c = adj_out;         // &adj_out[segment output base + ca]
+    double shift = 0.0;
+    int base = 0;                    // bin = sample - base
     bool bad = false;
-    auto bin_of = [&](float v) -> int {
-        const int b = (int)v - base;
-        if (v != rintf(v) || (unsigned)b >= (unsigned)kAdjBins) { bad = true; return 0; }
-        return b;
-    };
-    for (int t = 0; t < w; ++t) {
-        const float v = xs[ca + t];
-        const int b = bin_of(v);
-        H(b) = H(b) + 1;
-        isum += (long long)v;
+    if (live) {
+        const long long s = find_segment(seg_run_off, n_seg, run);
+        const long long n = seg_off[s + 1] - seg_off[s];
+        const long long n_out = n - w;
+        const long long ca = (run - seg_run_off[s]) * P.run;
+        const long long cb = (ca + P.run < n_out) ? ca + P.run : n_out;
+        xs_ca = x + seg_off[s] + ca;
+        out_c = adj_out + seg_out_off[s] + ca;
+        limit = (int)((n - ca > 0x7fffffff) ? 0x7fffffff : (n - ca));
+        G = (int)(cb - ca) + w - 1;
+        if (SHIFT) shift = seg_shift[s];
+        const float x0 = __ldg(xs_ca);  // centre the bin window on the first sample
+        if (x0 != rintf(x0) || fabsf(x0) > 1.0e9f) bad = true;
+        base = (int)x0 - kAdjBins / 2;
     }
-    if (bad) { fallback[run] = 1; return; }
-    // locate the lower median bin: c_lt = #samples below bin m
-    int m = 0, c_lt = 0;
-    while (c_lt + H(m) <= kl) { c_lt += H(m); ++m; }
+    const int kl = (w - 1) >> 1, ku = w >> 1;  // 0-based ranks of the two middle order statistics
+    int isum = 0;                    // window sum of bins (mean path); |bin| < 256, w <= 32767
+    int m = 0, c_lt = 0, hm = 0;
+    const int g_max = __reduce_max_sync(0xffffffffu, G);
 
-    for (long long c = ca; c < cb; ++c) {
-        double stat;
-        if (P.use_mean) {
-            stat = (double)isum / (double)w - shift;
-        } else {
-            // upper median: same bin if it still covers rank ku, else the next occupied bin
-            int mu = m;
-            if (c_lt + H(m) <= ku) { do { ++mu; } while (H(mu) == 0); }
-            const double lo = (double)(m + base) - shift, hi = (double)(mu + base) - shift;
-            stat = (lo + hi) / 2.0;
+    // Software-pipelined refill.  A tile holds kAdjTile (16) samples of each of the 32 lanes'
+    // three streams.  One load instruction fetches two rows (lanes 0-15 -> row 2i, lanes 16-31 ->
+    // row 2i+1: two coalesced 64-byte segments); the loads of tile k+1 are issued into registers
+    // BEFORE tile k is processed, so HBM latency hides behind kAdjTile histogram steps.
+    float pre[kAdjTile][3];
+    const int col = lane & (kAdjTile - 1), sub = lane >> 4;
+    auto issue_loads = [&](int g0) {
+        const int gi = g0 + col;
+        const int i_out = gi - w, i_ctr = gi - (w >> 1) + 1;
+#pragma unroll
+        for (int i = 0; i < kAdjTile; ++i) {
+            const int row = 2 * i + sub;
+            const unsigned long long p_i = __shfl_sync(0xffffffffu, (unsigned long long)xs_ca, row);
+            const int lim_i = __shfl_sync(0xffffffffu, limit, row);
+            const int G_i = __shfl_sync(0xffffffffu, G, row);
+            const float fb = (float)__shfl_sync(0xffffffffu, base, row);
+            const float *src = reinterpret_cast<const float *>(p_i);
+            const bool need = gi < G_i;
+            pre[i][0] = (need && gi < lim_i) ? __ldg(src + gi) : fb;
+            pre[i][1] = (need && i_out >= 0 && i_out < lim_i) ? __ldg(src + i_out) : fb;
+            pre[i][2] = (need && i_ctr >= 0 && i_ctr < lim_i) ? __ldg(src + i_ctr) : fb;
         }
-        const double centre = (double)xs[c + (w >> 1)] - shift;
-        const double adj = centre - stat;
-        if (P.savgol) sg.push(c, adj); else sg.out[c] = adj;
-        if (c + 1 < cb) {  // slide: drop xs[c], add xs[c + w]
-            const float vo = xs[c], vi = xs[c + w];
-            const int bo = (int)vo - base;  // validated when it entered
-            const int bi = bin_of(vi);
-            if (bad) { fallback[run] = 1; return; }
-            H(bo) = H(bo) - 1;
+    };
+    if (g_max > 0) issue_loads(0);
+
+    for (int g0 = 0; g0 < g_max; g0 += kAdjTile) {
+        // ---- registers -> byte tiles (bins relative to the owning lane's base) + validation:
+        // a sample must be integer-valued and inside the kAdjBins-wide window around the base
+        __syncwarp();   // every lane has finished walking the previous tile
+        unsigned inv_bits = 0;
+#pragma unroll
+        for (int i = 0; i < kAdjTile; ++i) {
+            const int row = 2 * i + sub;
+            const float fb = (float)__shfl_sync(0xffffffffu, base, row);
+            const float d_in = pre[i][0] - fb, d_out = pre[i][1] - fb, d_ctr = pre[i][2] - fb;
+            const bool invalid = (d_in != rintf(d_in)) || !(d_in >= 0.0f && d_in < (float)kAdjBins) ||
+                                 (d_out != rintf(d_out)) || !(d_out >= 0.0f && d_out < (float)kAdjBins) ||
+                                 (d_ctr != rintf(d_ctr)) || !(d_ctr >= 0.0f && d_ctr < (float)kAdjBins);
+            inv_bits |= (invalid ? 1u : 0u) << row;
+            t_in[row * kAdjTilePitch + col] = (unsigned char)(int)d_in;
+            t_out[row * kAdjTilePitch + col] = (unsigned char)(int)d_out;
+            t_ctr[row * kAdjTilePitch + col] = (unsigned char)(int)d_ctr;
+        }
+        if ((__reduce_or_sync(0xffffffffu, inv_bits) >> lane) & 1u) bad = true;
+        __syncwarp();
+        if (g0 + kAdjTile < g_max) issue_loads(g0 + kAdjTile);   // in flight while this tile is walked
+        if (!live || bad) continue;
+        // ---- every lane walks its own row
+        const int g_end = (G - g0 < kAdjTile) ? (G - g0) : kAdjTile;
+        const unsigned char *__restrict__ r_in = t_in + lane * kAdjTilePitch;
+        const unsigned char *__restrict__ r_out = t_out + lane * kAdjTilePitch;
+        const unsigned char *__restrict__ r_ctr = t_ctr + lane * kAdjTilePitch;
+        int t = 0;
+        // fill phase: g < w - 1 (histogram only)
+        for (; t < g_end && g0 + t < w - 1; ++t) {
+            const int bi = r_in[t];
             H(bi) = H(bi) + 1;
-            isum += (long long)vi - (long long)vo;
-            c_lt += (bi < m) - (bo < m);
-            while (c_lt > kl) { --m; c_lt -= H(m); }
-            while (c_lt + H(m) <= kl) { c_lt += H(m); ++m; }
+            if (MEAN) isum += bi;
+        }
+        if (t < g_end && g0 + t == w - 1) {  // first complete window: locate the median from scratch
+            const int bi = r_in[t];
+            H(bi) = H(bi) + 1;
+            if (MEAN) isum += bi;
+            m = 0; c_lt = 0; hm = H(0);
+            while (c_lt + hm <= kl) { c_lt += hm; ++m; hm = H(m); }
+        } else if (t < g_end) {
+            goto slide;
+        } else {
+            continue;
+        }
+        for (;;) {
+            {   // emit the output of step g0 + t
+                const int bc = r_ctr[t];
+                double adj;
+                if (MEAN) {
+                    const double stat = ((double)isum / (double)w + (double)base) - shift;
+                    adj = ((double)(bc + base) - shift) - stat;
+                } else {
+                    int mu = m;  // upper median: same bin if it still covers rank ku, else next occupied bin
+                    if (c_lt + hm <= ku) { do { ++mu; } while (H(mu) == 0); }
+                    if (SHIFT) {
+                        const double lo = (double)(m + base) - shift, hi = (double)(mu + base) - shift;
+                        adj = ((double)(bc + base) - shift) - (lo + hi) / 2.0;
+                    } else {
+                        adj = (double)(2 * bc - m - mu) * 0.5;
+                    }
+                }
+                out_c[g0 + t - (w - 1)] = adj;
+            }
+            if (++t >= g_end) break;
+        slide:
+            {   // slide phase: g >= w
+                const int bi = r_in[t], bo = r_out[t];
+                H(bi) = H(bi) + 1;
+                H(bo) = H(bo) - 1;
+                if (MEAN) isum += bi - bo;
+                c_lt += (bi < m) - (bo < m);
+                hm += (bi == m) - (bo == m);
+                while (c_lt > kl) { --m; hm = H(m); c_lt -= hm; }
+                while (c_lt + hm <= kl) { c_lt += hm; ++m; hm = H(m); }
+            }
         }
     }
+    if (live && bad) fallback[run] = 1;
 #undef H
 }
 
@@ -194,9 +223,7 @@ adjust_generic_kernel(const float *__restrict__ x, const long long *__restrict__
                       const long long *__restrict__ seg_out_off, const long long *__restrict__ seg_run_off,
                       const double *__restrict__ seg_shift, int n_seg,
                       const long long *__restrict__ run_list, long long n_list, AdjParams P,
-                      const double *__restrict__ coef, const double *__restrict__ edge_first,
-                      const double *__restrict__ edge_last, double *__restrict__ out,
-                      float *__restrict__ scratch /* [n_list][w] */) {
+                      double *__restrict__ adj_out, float *__restrict__ scratch /* [n_list][w] */) {
     const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= n_list) return;
     const long long run = run_list[li];
@@ -205,19 +232,12 @@ adjust_generic_kernel(const float *__restrict__ x, const long long *__restrict__
     const long long n = seg_off[s + 1] - seg_off[s];
     const long long n_out = n - P.w;
     const float *__restrict__ xs = x + seg_off[s];
+    double *__restrict__ out = adj_out + seg_out_off[s];
     const double shift = seg_shift ? seg_shift[s] : 0.0;
-    const long long ja = (run - seg_run_off[s]) * P.run;
-    const long long jb = (ja + P.run < n_out) ? ja + P.run : n_out;
-    long long ca, cb;
-    run_extent(P, ja, jb, n_out, ca, cb);
-    SgEmitter sg;
-    sg.coef = coef; sg.edge_first = edge_first; sg.edge_last = edge_last;
-    sg.out = out + seg_out_off[s];
-    sg.sg_w = P.sg_w; sg.half = P.sg_w / 2; sg.ja = ja; sg.jb = jb; sg.n_out = n_out;
+    const long long ca = (run - seg_run_off[s]) * P.run;
+    const long long cb = (ca + P.run < n_out) ? ca + P.run : n_out;
     const int w = P.w;
-    // insertion sort of the first window
-    double sum = 0.0;
-    for (int t = 0; t < w; ++t) {
+    for (int t = 0; t < w; ++t) {  // insertion sort of the first window
         const float v = xs[ca + t];
         int k = t;
         while (k > 0 && win[k - 1] > v) { win[k] = win[k - 1]; --k; }
@@ -226,25 +246,73 @@ adjust_generic_kernel(const float *__restrict__ x, const long long *__restrict__
     for (long long c = ca; c < cb; ++c) {
         double stat;
         if (P.use_mean) {
-            sum = 0.0;  // fp64 left-to-right sum of the shifted window (numpy: pairwise; <= 1e-13 rel apart)
+            double sum = 0.0;  // fp64 left-to-right sum of the shifted window (numpy: pairwise; <= 1e-13 rel apart)
             for (int t = 0; t < w; ++t) sum += (double)xs[c + t] - shift;
             stat = sum / (double)w;
         } else {
             const double lo = (double)win[(w - 1) >> 1] - shift, hi = (double)win[w >> 1] - shift;
             stat = (lo + hi) / 2.0;
         }
-        const double adj = ((double)xs[c + (w >> 1)] - shift) - stat;
-        if (P.savgol) sg.push(c, adj); else sg.out[c] = adj;
+        out[c] = ((double)xs[c + (w >> 1)] - shift) - stat;
         if (c + 1 < cb && !P.use_mean) {
             const float vo = xs[c], vi = xs[c + w];
             int lo = 0, hi = w;  // position of one copy of vo
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (win[mid] < vo) lo = mid + 1; else hi = mid; }
             int k = lo;
-            // remove win[k], insert vi keeping order
             if (vi >= vo) { while (k + 1 < w && win[k + 1] < vi) { win[k] = win[k + 1]; ++k; } }
             else { while (k > 0 && win[k - 1] > vi) { win[k] = win[k - 1]; --k; } }
             win[k] = vi;
         }
+    }
+}
+
+// ---------------------------------------------------------- Savitzky-Golay
+// scipy.signal.savgol_filter(adj, sg_w, deg) with mode='interp': interior = sg_w-tap stencil,
+// the first / last sg_w/2 outputs of every segment = polynomial fit of its first / last sg_w
+// samples evaluated at those positions (the two edge matrices).  One thread per output.
+constexpr int kSgThreads = 256;
+constexpr int kSgPerThread = 4;
+constexpr int kSgTile = kSgThreads * kSgPerThread;   // outputs per CTA
+
+__global__ void __launch_bounds__(kSgThreads)
+adjust_savgol_kernel(const double *__restrict__ adj, const long long *__restrict__ seg_out_off, int n_seg,
+                     long long n_total, int sg_w, const double *__restrict__ coef,
+                     const double *__restrict__ edge_first, const double *__restrict__ edge_last,
+                     double *__restrict__ out) {
+    __shared__ double s_coef[kAdjMaxSg];
+    __shared__ double s_tile[kSgTile + kAdjMaxSg];     // adj[o0 - half, o0 + kSgTile + half)
+    __shared__ long long s_seg0;
+    const int half = sg_w >> 1;
+    for (int i = threadIdx.x; i < sg_w; i += kSgThreads) s_coef[i] = coef[i];
+    const long long o0 = (long long)blockIdx.x * kSgTile;
+    if (threadIdx.x == 0) s_seg0 = find_segment(seg_out_off, n_seg, o0);
+    for (int i = threadIdx.x; i < kSgTile + 2 * half; i += kSgThreads) {   // coalesced tile load
+        const long long g = o0 - half + i;
+        s_tile[i] = (g >= 0 && g < n_total) ? adj[g] : 0.0;
+    }
+    __syncthreads();
+    long long s = s_seg0;
+#pragma unroll
+    for (int k = 0; k < kSgPerThread; ++k) {
+        const int local = k * kSgThreads + threadIdx.x;                    // consecutive lanes -> consecutive LDS
+        const long long o = o0 + local;
+        if (o >= n_total) break;
+        while (s + 1 < n_seg && seg_out_off[s + 1] <= o) ++s;              // monotone in k: the walk is short
+        const long long b = seg_out_off[s];
+        const long long n_out = seg_out_off[s + 1] - b;
+        const long long j = o - b;
+        double acc = 0.0;
+        if (j >= half && j < n_out - half) {
+            const double *p = s_tile + local;                              // = adj[o - half ...]
+            for (int i = 0; i < sg_w; ++i) acc += s_coef[i] * p[i];
+        } else if (j < half) {
+            const double *__restrict__ p = adj + b;
+            for (int i = 0; i < sg_w; ++i) acc += edge_first[j * sg_w + i] * p[i];
+        } else {
+            const double *__restrict__ p = adj + b + n_out - sg_w;
+            for (int i = 0; i < sg_w; ++i) acc += edge_last[(j - (n_out - half)) * sg_w + i] * p[i];
+        }
+        out[o] = acc;
     }
 }
 
@@ -279,40 +347,42 @@ extern "C" int ftk_adjust_edge_shift_f64(const float *x, const int64_t *seg_off,
 
 static int adjust_check(const float *x, const int64_t *seg_off, const int64_t *seg_out_off,
                         const int64_t *seg_run_off, int32_t n_seg, int64_t n_runs, int32_t w,
-                        int32_t savgol, int32_t sg_w, int32_t run_len, const double *coef,
-                        const double *edge_first, const double *edge_last, double *out) {
+                        int32_t run_len, double *out) {
     if (!x || !seg_off || !seg_out_off || !seg_run_off || !out || n_seg < 0 || n_runs < 0) return FTK_E_INVALID;
     if (w < 2 || (w & 1) || w > 32767 || run_len < 1) return FTK_E_INVALID;
-    if (savgol && (!coef || !edge_first || !edge_last || sg_w < 1 || !(sg_w & 1) || sg_w > kAdjMaxSg))
-        return FTK_E_INVALID;
     return FTK_OK;
 }
 
 extern "C" int ftk_adjust_wps_f64(const float *x, const int64_t *seg_off, const int64_t *seg_out_off,
                                   const int64_t *seg_run_off, const double *seg_shift, int32_t n_seg,
-                                  int64_t n_runs, int32_t w, int32_t use_mean, int32_t savgol,
-                                  int32_t sg_w, int32_t run_len, const double *coef,
-                                  const double *edge_first, const double *edge_last, double *out,
-                                  uint8_t *fallback, ftk_stream_t stream_) {
+                                  int64_t n_runs, int32_t w, int32_t use_mean, int32_t run_len,
+                                  double *adj_out, uint8_t *fallback, ftk_stream_t stream_) {
     if (n_runs == 0 || n_seg == 0) return FTK_OK;
-    int rc = adjust_check(x, seg_off, seg_out_off, seg_run_off, n_seg, n_runs, w, savgol, sg_w, run_len,
-                          coef, edge_first, edge_last, out);
+    int rc = adjust_check(x, seg_off, seg_out_off, seg_run_off, n_seg, n_runs, w, run_len, adj_out);
     if (rc != FTK_OK) return rc;
     if (!fallback) return FTK_E_INVALID;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    AdjParams P{w, use_mean, savgol, savgol ? sg_w : 1, run_len};
-    const int smem = kAdjBins * kAdjThreads * (int)sizeof(short);
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        FTK_CUDA_TRY(cudaFuncSetAttribute(adjust_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    AdjParams P{w, use_mean, run_len};
+    const int smem = kAdjBins * kAdjThreads * (int)sizeof(short) + kAdjWarps * 3 * 32 * kAdjTilePitch;
     FTK_CUDA_TRY(cudaMemsetAsync(fallback, 0, (size_t)n_runs, stream));
     const unsigned grid = (unsigned)((n_runs + kAdjThreads - 1) / kAdjThreads);
-    adjust_hist_kernel<<<grid, kAdjThreads, smem, stream>>>(
-        x, reinterpret_cast<const long long *>(seg_off), reinterpret_cast<const long long *>(seg_out_off),
-        reinterpret_cast<const long long *>(seg_run_off), seg_shift, n_seg, n_runs, P, coef, edge_first,
-        edge_last, out, fallback);
+    const long long *so = reinterpret_cast<const long long *>(seg_off);
+    const long long *oo = reinterpret_cast<const long long *>(seg_out_off);
+    const long long *ro = reinterpret_cast<const long long *>(seg_run_off);
+#define FTK_ADJ_LAUNCH(M, S)                                                                                   \
+    do {                                                                                                       \
+        static thread_local bool attr_set = false;                                                             \
+        if (!attr_set) {                                                                                       \
+            FTK_CUDA_TRY(cudaFuncSetAttribute(adjust_hist_kernel<M, S>,                                         \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem));             \
+            attr_set = true;                                                                                   \
+        }                                                                                                      \
+        adjust_hist_kernel<M, S><<<grid, kAdjThreads, smem, stream>>>(x, so, oo, ro, seg_shift, n_seg, n_runs, \
+                                                                      P, adj_out, fallback);                   \
+    } while (0)
+    if (use_mean) { if (seg_shift) FTK_ADJ_LAUNCH(true, true); else FTK_ADJ_LAUNCH(true, false); }
+    else          { if (seg_shift) FTK_ADJ_LAUNCH(false, true); else FTK_ADJ_LAUNCH(false, false); }
+#undef FTK_ADJ_LAUNCH
     FTK_CHECK_LAUNCH("adjust_hist_kernel");
     return FTK_OK;
 }
@@ -320,20 +390,30 @@ extern "C" int ftk_adjust_wps_f64(const float *x, const int64_t *seg_off, const 
 extern "C" int ftk_adjust_wps_generic_f64(const float *x, const int64_t *seg_off, const int64_t *seg_out_off,
                                           const int64_t *seg_run_off, const double *seg_shift, int32_t n_seg,
                                           const int64_t *run_list, int64_t n_list, int32_t w,
-                                          int32_t use_mean, int32_t savgol, int32_t sg_w, int32_t run_len,
-                                          const double *coef, const double *edge_first,
-                                          const double *edge_last, double *out, float *scratch,
-                                          ftk_stream_t stream_) {
+                                          int32_t use_mean, int32_t run_len, double *adj_out,
+                                          float *scratch, ftk_stream_t stream_) {
     if (n_list == 0 || n_seg == 0) return FTK_OK;
-    int rc = adjust_check(x, seg_off, seg_out_off, seg_run_off, n_seg, n_list, w, savgol, sg_w, run_len,
-                          coef, edge_first, edge_last, out);
+    int rc = adjust_check(x, seg_off, seg_out_off, seg_run_off, n_seg, n_list, w, run_len, adj_out);
     if (rc != FTK_OK) return rc;
     if (!run_list || !scratch) return FTK_E_INVALID;
-    AdjParams P{w, use_mean, savgol, savgol ? sg_w : 1, run_len};
+    AdjParams P{w, use_mean, run_len};
     adjust_generic_kernel<<<(unsigned)((n_list + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream_)>>>(
         x, reinterpret_cast<const long long *>(seg_off), reinterpret_cast<const long long *>(seg_out_off),
         reinterpret_cast<const long long *>(seg_run_off), seg_shift, n_seg,
-        reinterpret_cast<const long long *>(run_list), n_list, P, coef, edge_first, edge_last, out, scratch);
+        reinterpret_cast<const long long *>(run_list), n_list, P, adj_out, scratch);
     FTK_CHECK_LAUNCH("adjust_generic_kernel");
+    return FTK_OK;
+}
+
+extern "C" int ftk_savgol_f64(const double *adj, const int64_t *seg_out_off, int32_t n_seg, int64_t n_total,
+                              int32_t sg_w, const double *coef, const double *edge_first,
+                              const double *edge_last, double *out, ftk_stream_t stream_) {
+    if (n_total == 0 || n_seg == 0) return FTK_OK;
+    if (!adj || !seg_out_off || !coef || !edge_first || !edge_last || !out || n_seg < 0 || n_total < 0)
+        return FTK_E_INVALID;
+    if (sg_w < 1 || !(sg_w & 1) || sg_w > kAdjMaxSg || adj == out) return FTK_E_INVALID;
+    adjust_savgol_kernel<<<(unsigned)((n_total + kSgTile - 1) / kSgTile), kSgThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+        adj, reinterpret_cast<const long long *>(seg_out_off), n_seg, n_total, sg_w, coef, edge_first, edge_last, out);
+    FTK_CHECK_LAUNCH("adjust_savgol_kernel");
     return FTK_OK;
 }

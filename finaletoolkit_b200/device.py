@@ -317,6 +317,9 @@ def end_motif_hist(frags: ContigFragments, ref: PackedContig, ivl_start, ivl_sto
     return counts[:rows]
 
 
+_ADJ_SLOTS = 148 * 3 * 128
+
+
 def savgol_tables(window: int, degree: int):
     """Savitzky-Golay interior coefficients and mode='interp' edge-fit matrices (host, fp64).
 
@@ -342,7 +345,7 @@ def savgol_tables(window: int, degree: int):
 
 def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, savgol=True,
                     savgol_window_size=21, savgol_poly_deg=2, subtract_edges=False, edge_size=500,
-                    run_len=2048):
+                    run_len=None):
     """Median/mean-adjust + Savitzky-Golay smooth contiguous raw-WPS segments on the GPU.
 
     ``x``: float32 samples of all segments back to back (numpy or CUDA tensor);
@@ -367,24 +370,27 @@ def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, sav
     n_seg = len(seg_lengths)
     seg_off = np.zeros(n_seg + 1, np.int64); np.cumsum(seg_lengths, out=seg_off[1:])
     out_off = np.zeros(n_seg + 1, np.int64); np.cumsum(n_out, out=out_off[1:])
+    if run_len is None:
+        # one thread slides one run: aim for a single full wave of the 148 SMs x 3 CTAs x 128 threads,
+        # keep the w-sample window fill amortised (>= 1024 outputs) and split short segments evenly
+        slots = _ADJ_SLOTS
+        run_len = int(min(max(-(-int(n_out.sum()) // slots), 1024), 16384))
+        nmax = int(n_out.max()) if n_seg else 0
+        if 0 < nmax <= 4 * run_len:
+            run_len = -(-nmax // max(1, round(nmax / run_len)))
+    run_len = max(int(run_len), 1)
     runs = -(-n_out // run_len)
     run_off = np.zeros(n_seg + 1, np.int64); np.cumsum(runs, out=run_off[1:])
     n_runs = int(run_off[-1])
     xd = x if t.is_tensor(x) else _to_device(np.asarray(x), dev, np.float32)
     xd = xd.to(dev, t.float32).contiguous()
-    out = t.empty(max(int(out_off[-1]), 1), dtype=t.float64, device=dev)
+    n_total = int(out_off[-1])
+    out = t.empty(max(n_total, 1), dtype=t.float64, device=dev)
     if n_runs == 0:
         return out[:0], out_off
     d_seg = _to_device(seg_off, dev, np.int64)
     d_out = _to_device(out_off, dev, np.int64)
     d_run = _to_device(run_off, dev, np.int64)
-    if savgol:
-        coef, ef, el = savgol_tables(int(savgol_window_size), int(savgol_poly_deg))
-    else:
-        coef, ef, el = np.ones(1), np.zeros((1, 1)), np.zeros((1, 1))
-    d_coef = _to_device(coef, dev, np.float64)
-    d_ef = _to_device(ef.reshape(-1) if ef.size else np.zeros(1), dev, np.float64)
-    d_el = _to_device(el.reshape(-1) if el.size else np.zeros(1), dev, np.float64)
     L = lib()
     sp = _stream_ptr(dev)
     shift_ptr = 0
@@ -393,15 +399,24 @@ def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, sav
         check(L.ftk_adjust_edge_shift_f64(xd.data_ptr(), d_seg.data_ptr(), n_seg, int(edge_size),
                                           shift.data_ptr(), sp), "ftk_adjust_edge_shift_f64")
         shift_ptr = shift.data_ptr()
+    adj = t.empty(max(n_total, 1), dtype=t.float64, device=dev) if savgol else out
     fb = t.empty(n_runs, dtype=t.uint8, device=dev)
-    args = (int(w), int(bool(use_mean)), int(bool(savgol)), int(savgol_window_size) if savgol else 1, int(run_len),
-            d_coef.data_ptr(), d_ef.data_ptr(), d_el.data_ptr(), out.data_ptr())
     check(L.ftk_adjust_wps_f64(xd.data_ptr(), d_seg.data_ptr(), d_out.data_ptr(), d_run.data_ptr(), shift_ptr,
-                               n_seg, n_runs, *args, fb.data_ptr(), sp), "ftk_adjust_wps_f64")
+                               n_seg, n_runs, int(w), int(bool(use_mean)), int(run_len), adj.data_ptr(),
+                               fb.data_ptr(), sp), "ftk_adjust_wps_f64")
     flagged = t.nonzero(fb).flatten().to(t.int64)   # plumbing: compact the flagged run ids
     if flagged.numel():
         scratch = t.empty(flagged.numel() * w, dtype=t.float32, device=dev)
         check(L.ftk_adjust_wps_generic_f64(xd.data_ptr(), d_seg.data_ptr(), d_out.data_ptr(), d_run.data_ptr(),
-                                           shift_ptr, n_seg, flagged.data_ptr(), flagged.numel(), *args,
+                                           shift_ptr, n_seg, flagged.data_ptr(), flagged.numel(), int(w),
+                                           int(bool(use_mean)), int(run_len), adj.data_ptr(),
                                            scratch.data_ptr(), sp), "ftk_adjust_wps_generic_f64")
-    return out[: int(out_off[-1])], out_off
+    if savgol:
+        coef, ef, el = savgol_tables(int(savgol_window_size), int(savgol_poly_deg))
+        d_coef = _to_device(coef, dev, np.float64)
+        d_ef = _to_device(ef.reshape(-1) if ef.size else np.zeros(1), dev, np.float64)
+        d_el = _to_device(el.reshape(-1) if el.size else np.zeros(1), dev, np.float64)
+        check(L.ftk_savgol_f64(adj.data_ptr(), d_out.data_ptr(), n_seg, n_total, int(savgol_window_size),
+                               d_coef.data_ptr(), d_ef.data_ptr(), d_el.data_ptr(), out.data_ptr(), sp),
+              "ftk_savgol_f64")
+    return out[:n_total], out_off

@@ -177,15 +177,15 @@ int ftk_end_motif_hist_u64(const int32_t *frag_start_dev, const int32_t *frag_st
  * segments; segment s = x[seg_off[s] .. seg_off[s+1]) with n_s samples and
  * n_s - w outputs written to out[seg_out_off[s] ..] (float64):
  *   adj[j] = (x[j+w/2]-shift) - stat((x-shift)[j:j+w]),  stat = median | mean
- *   out = adj (savgol == 0) or savgol(adj, sg_w, deg, mode='interp') where the
- *   caller passes the sg_w interior coefficients and the two (sg_w/2 x sg_w)
- *   edge-fit matrices.
  * Work is cut into runs of run_len outputs: seg_run_off[s] = first run of
  * segment s (prefix sum of ceil((n_s-w)/run_len)), n_runs in total.
- * ftk_adjust_wps_f64 is the fast path (integer-valued samples whose local range
- * fits a 256-wide window); runs it cannot handle are flagged in fallback_dev[run]
- * and must be redone with ftk_adjust_wps_generic_f64 (any float input;
- * scratch_dev: float[n_list * w]).  w even, 2 <= w <= 32767; sg_w odd <= 127.
+ * ftk_adjust_wps_f64 writes adj (the median/mean-subtracted series) and is the fast
+ * path (integer-valued samples whose local range fits a 256-wide window); runs it
+ * cannot handle are flagged in fallback_dev[run] and must be redone with
+ * ftk_adjust_wps_generic_f64 (any float input; scratch_dev: float[n_list * w]).
+ * ftk_savgol_f64 then applies savgol_filter(adj, sg_w, deg, mode='interp') per
+ * segment (out != adj) from the sg_w interior coefficients and the two
+ * (sg_w/2 x sg_w) edge-fit matrices.  w even, 2 <= w <= 32767; sg_w odd <= 127.
  * seg_shift_dev: per-segment constant to subtract (NULL = 0), e.g. from
  * ftk_adjust_edge_shift_f64 = mean(mean(x[:edge]), mean(x[-edge:]))
  * (subtract_edges, frag/_adjust_wps.py:119-123). */
@@ -194,18 +194,18 @@ int ftk_adjust_edge_shift_f64(const float *x_dev, const int64_t *seg_off_dev, in
 
 int ftk_adjust_wps_f64(const float *x_dev, const int64_t *seg_off_dev, const int64_t *seg_out_off_dev,
                        const int64_t *seg_run_off_dev, const double *seg_shift_dev, int32_t n_seg,
-                       int64_t n_runs, int32_t w, int32_t use_mean, int32_t savgol,
-                       int32_t sg_w, int32_t run_len, const double *coef_dev,
-                       const double *edge_first_dev, const double *edge_last_dev, double *out_dev,
-                       uint8_t *fallback_dev, ftk_stream_t stream);
+                       int64_t n_runs, int32_t w, int32_t use_mean, int32_t run_len,
+                       double *adj_out_dev, uint8_t *fallback_dev, ftk_stream_t stream);
 
 int ftk_adjust_wps_generic_f64(const float *x_dev, const int64_t *seg_off_dev, const int64_t *seg_out_off_dev,
                                const int64_t *seg_run_off_dev, const double *seg_shift_dev, int32_t n_seg,
                                const int64_t *run_list_dev, int64_t n_list, int32_t w,
-                               int32_t use_mean, int32_t savgol, int32_t sg_w, int32_t run_len,
-                               const double *coef_dev, const double *edge_first_dev,
-                               const double *edge_last_dev, double *out_dev, float *scratch_dev,
-                               ftk_stream_t stream);
+                               int32_t use_mean, int32_t run_len, double *adj_out_dev,
+                               float *scratch_dev, ftk_stream_t stream);
+
+int ftk_savgol_f64(const double *adj_dev, const int64_t *seg_out_off_dev, int32_t n_seg, int64_t n_total,
+                   int32_t sg_w, const double *coef_dev, const double *edge_first_dev,
+                   const double *edge_last_dev, double *out_dev, ftk_stream_t stream);
 
 #ifdef __cplusplus
 }
