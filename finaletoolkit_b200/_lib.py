@@ -49,6 +49,14 @@ SYMBOLS = {
     "ftk_adjust_wps_generic_f64": (c_int, [_P, _P, _P, _P, _P, c_int32, _P, c_int64, c_int32, c_int32, c_int32,
                                            _P, _P, _P]),
     "ftk_savgol_f64": (c_int, [_P, _P, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P]),
+    "ftk_fragfile_open": (c_void_p, [c_char_p, c_int32, _i32p]),
+    "ftk_fragfile_is_bed6": (c_int32, [c_void_p]),
+    "ftk_fragfile_skipped": (c_int64, [c_void_p]),
+    "ftk_fragfile_n_contigs": (c_int32, [c_void_p]),
+    "ftk_fragfile_contig_name": (c_char_p, [c_void_p, c_int32]),
+    "ftk_fragfile_contig_count": (c_int64, [c_void_p, c_int32]),
+    "ftk_fragfile_copy": (c_int, [c_void_p, c_int32, _i32p, _i32p, _u8p, _u8p]),
+    "ftk_fragfile_close": (None, [c_void_p]),
 }
 
 _lib = None

@@ -33,7 +33,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return SO
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(REPO, "include"), "-I", HERE,
-           "-o", SO] + sources()
+           "-o", SO] + sources() + ["-lz", "-lpthread"]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     subprocess.check_call(cmd)

@@ -23,6 +23,7 @@ extern "C" const char *ftk_error_string(int code) {
         case FTK_E_INVALID: return "invalid argument";
         case FTK_E_CUDA: return "CUDA error (see ftk_last_cuda_error)";
         case FTK_E_RANGE: return "size or coordinate out of the supported range";
+        case FTK_E_IO: return "file unreadable or not valid (b)gzip";
         default: return "unknown error";
     }
 }

@@ -133,6 +133,42 @@ def _parse_text_rows(lines: Iterable[str]) -> Dict[str, Columns]:
             for c, a in acc.items()}
 
 
+def _decode_native(path: str, threads: int = 0) -> Dict[str, Columns] | None:
+    """Multi-threaded C++ decoder in libftk_b200.so (BGZF blocks inflated + parsed in parallel).
+
+    Returns None when the library is unavailable so the pure-Python parsers can take over
+    (decode is host-side I/O, not the compute path)."""
+    import ctypes
+    try:
+        from .._lib import lib
+        L = lib()
+    except Exception:  # noqa: BLE001
+        return None
+    err = ctypes.c_int32(0)
+    h = L.ftk_fragfile_open(path.encode(), int(threads), ctypes.byref(err))
+    if not h:
+        return None
+    try:
+        if L.ftk_fragfile_is_bed6(h):
+            warnings.warn(
+                "input_file does not follow Fragmentation file format accepted by FinaleToolkit. "
+                "Attempting to read as a BED6 file.", UserWarning)
+        cols: Dict[str, Columns] = {}
+        for i in range(L.ftk_fragfile_n_contigs(h)):
+            n = L.ftk_fragfile_contig_count(h, i)
+            st = np.empty(n, np.int32); sp = np.empty(n, np.int32)
+            mq = np.empty(n, np.uint8); sd = np.empty(n, np.uint8)
+            p32, p8 = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint8)
+            rc = L.ftk_fragfile_copy(h, i, st.ctypes.data_as(p32), sp.ctypes.data_as(p32),
+                                     mq.ctypes.data_as(p8), sd.ctypes.data_as(p8))
+            if rc != 0:
+                return None
+            cols[L.ftk_fragfile_contig_name(h, i).decode()] = (st, sp, mq, sd)
+        return cols
+    finally:
+        L.ftk_fragfile_close(h)
+
+
 def _parse_text_fast(path: str) -> Dict[str, Columns] | None:
     """pandas C parser for well-formed files; None -> caller falls back to the row parser."""
     try:
@@ -208,7 +244,9 @@ def load_fragments(input_file, reference_file=None) -> FragmentTable:
     if path.lower().endswith((".bam", ".cram", ".sam")):
         tab = _load_sam(path, reference_file)
     else:
-        cols = _parse_text_fast(path)
+        cols = _decode_native(path)
+        if cols is None:
+            cols = _parse_text_fast(path)
         if cols is None:
             with gzip.open(path, "rt") as fh:
                 cols = _parse_text_rows(fh)

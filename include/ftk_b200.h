@@ -35,6 +35,7 @@ extern "C" {
 #define FTK_E_INVALID -1   /* bad argument (null pointer, negative size, ...) */
 #define FTK_E_CUDA -2      /* a CUDA runtime call or launch failed            */
 #define FTK_E_RANGE -3     /* a size exceeds what the kernel supports         */
+#define FTK_E_IO -4        /* file unreadable or not valid (b)gzip            */
 
 /* `pooled` modes of ftk_interval_hist_u64 */
 #define FTK_POOL_NONE 0       /* counts and histogram rows per interval            */
@@ -206,6 +207,24 @@ int ftk_adjust_wps_generic_f64(const float *x_dev, const int64_t *seg_off_dev, c
 int ftk_savgol_f64(const double *adj_dev, const int64_t *seg_out_off_dev, int32_t n_seg, int64_t n_total,
                    int32_t sg_w, const double *coef_dev, const double *edge_first_dev,
                    const double *edge_last_dev, double *out_dev, ftk_stream_t stream);
+
+/* ------------------------------------------------- fragment file decode (host)
+ * Multi-threaded decode of a BGZF / gzip fragment file into per-contig columns; replaces the
+ * per-interval pysam.TabixFile.fetch text stream of io/alignment.py:270-302 (5-column FinaleDB
+ * layout or BED6, malformed rows skipped, '+' in the strand field = forward) with one pass.
+ * Host pointers only; no CUDA involved.  n_threads < 1 = all hardware threads.
+ * ftk_fragfile_open returns NULL and sets *err (FTK_E_IO / FTK_E_INVALID) on failure.
+ * ftk_fragfile_copy fills caller buffers (pinned or pageable) of ftk_fragfile_contig_count
+ * elements, rows in file order. */
+void *ftk_fragfile_open(const char *path, int32_t n_threads, int32_t *err);
+int32_t ftk_fragfile_is_bed6(void *handle);
+int64_t ftk_fragfile_skipped(void *handle);
+int32_t ftk_fragfile_n_contigs(void *handle);
+const char *ftk_fragfile_contig_name(void *handle, int32_t i);
+int64_t ftk_fragfile_contig_count(void *handle, int32_t i);
+int ftk_fragfile_copy(void *handle, int32_t i, int32_t *start_host, int32_t *stop_host,
+                      uint8_t *mapq_host, uint8_t *strand_host);
+void ftk_fragfile_close(void *handle);
 
 #ifdef __cplusplus
 }

@@ -59,3 +59,20 @@ def golden_codes(g, name, n):
 def read_gz(path):
     with gzip.open(path, "rt") as fh:
         return fh.read()
+
+
+def write_bgzf(path, text: str, block=30000):
+    """Real BGZF (the container tabix/bgzip write): independent deflate members with a 'BC' extra
+    field holding the block size, terminated by the 28-byte EOF block; + a placeholder .tbi."""
+    import zlib
+    data = text.encode()
+    with open(path, "wb") as fh:
+        for i in list(range(0, len(data), block)) + [None]:
+            chunk = b"" if i is None else data[i:i + block]
+            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            payload = c.compress(chunk) + c.flush()
+            bsize = 12 + 6 + len(payload) + 8 - 1
+            fh.write(struct.pack("<BBBBIBBH", 31, 139, 8, 4, 0, 0, 255, 6) + b"BC" + struct.pack("<HH", 2, bsize))
+            fh.write(payload + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    open(str(path) + ".tbi", "wb").close()
+    return str(path)

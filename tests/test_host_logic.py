@@ -254,3 +254,40 @@ def test_gloo_world2_genome_histogram(tmp_path):
     assert got["total"] == sum(exp.values()) == got["hist_sum"] and got["n"] == len(exp)
     assert got["keys"] == list(exp)[:40] and got["vals"] == list(exp.values())[:40]
     assert got["motif"] == [7, 7, 7, 7, 7]
+
+
+def test_native_decoder_bgzf_gzip_and_quirks(tmp_path, manifest):
+    """C++ multi-threaded decoder (ftk_fragfile_*) == the tolerant Python row parser."""
+    import gzip
+    from helpers import write_bgzf
+    from finaletoolkit_b200.io import fragments as FR
+    from finaletoolkit_b200.synth import synth_fragments
+    rows = []
+    for ci, (c, n) in enumerate([("chr2", 40_000), ("chr10", 25_000), ("chrUn_gl000220", 3)]):
+        st, sp, mq, sd = synth_fragments(3_000_000, n, ci, seed_base=123)
+        rows += [f"{c}\t{a}\t{b}\t{q}\t{'+' if s else '-'}" for a, b, q, s in zip(st.tolist(), sp.tolist(), mq.tolist(), sd.tolist())]
+    rows.insert(10, "chr2\tx\t5\t60\t+"); rows.insert(500, "chr2\t7"); rows.insert(900, "# a comment"); rows.insert(901, "")
+    rows.insert(20_000, "chr2\t100\t260\t300\t+-")      # mapq > 255 clamps, '+' anywhere in the strand field
+    text = "\n".join(rows) + "\n"
+    exp = FR._parse_text_rows(text.splitlines(keepends=True))
+    p1 = write_bgzf(tmp_path / "a.frag.gz", text)
+    with gzip.open(tmp_path / "b.frag.gz", "wt") as fh:
+        fh.write(text)
+    open(str(tmp_path / "b.frag.gz") + ".tbi", "wb").close()
+    for path, threads in [(p1, 0), (p1, 1), (p1, 5), (str(tmp_path / "b.frag.gz"), 3)]:
+        got = FR._decode_native(path, threads)
+        assert got is not None and list(got) == list(exp)
+        for c in exp:
+            for a, b in zip(got[c], exp[c]):
+                assert np.array_equal(a, b), (path, c)
+    # python's gzip reads the BGZF we wrote (it is plain multi-member gzip)
+    assert gzip.open(p1, "rt").read() == text
+    # BED6 detection + warning, through the public loader
+    m = manifest["fixture17"]
+    p6 = write_bgzf(tmp_path / "c.bed.gz", m["frag_bed_gz_text"])
+    with pytest.warns(UserWarning):
+        t = FR.load_fragments(p6)
+    assert t.n_fragments() == 17 and t.host("12")[2][4] == 54
+    # corrupt file -> the native decoder declines, the loader falls back and raises
+    bad = tmp_path / "bad.frag.gz"; bad.write_bytes(b"\x1f\x8b\x08\x00garbage"); open(str(bad) + ".tbi", "wb").close()
+    assert FR._decode_native(str(bad)) is None
