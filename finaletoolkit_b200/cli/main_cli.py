@@ -4,8 +4,8 @@ Table-driven Click group.  For every in-scope subcommand the flag spellings, par
 (== the Python kwarg names, reference cli/_args.py:17-19) and defaults are those of the reference
 (cli/commands/__init__.py:87-640); dispatch filters the parameters by the target's signature like
 cli/_dispatch.py:96-118 and expands ``--strand`` into both_strands / negative_strand
-(cli/_dispatch.py:25-36).  Out-of-scope subcommands (delfi, cleavage-profile, breakpoint motifs,
-filter-file, agg-bw, gap-bed) are not registered.
+(cli/_dispatch.py:25-36).  Out-of-scope subcommands (delfi, breakpoint motifs, filter-file, agg-bw,
+gap-bed) are not registered.
 """
 from __future__ import annotations
 
@@ -97,6 +97,14 @@ COMMANDS = {
         _opt("-W", "--window-size", "window_size", metavar="BP", default=120, show_default=True, type=int,
              help="WPS sliding-window size."),
         _minlen(120), _maxlen(180), _mapq(30), _THREADS, _VERBOSE]),
+    "cleavage-profile": ("finaletoolkit_b200.frag", "multi_cleavage_profile", "Cleavage proportion over BED intervals.", [
+        _INPUT, _arg("interval_file", metavar="REGIONS"), _arg("chrom_sizes", metavar="CHROM_SIZES"), _REF,
+        _out("bigWig file of cleavage proportion."), _minlen(0), _maxlen(None), _mapq(20),
+        _opt("--pad-left", "left", metavar="BP", default=0, show_default=True, type=int,
+             help="Base pairs to subtract from each start coordinate."),
+        _opt("--pad-right", "right", metavar="BP", default=0, show_default=True, type=int,
+             help="Base pairs to add to each stop coordinate."),
+        _THREADS, _VERBOSE]),
     "adjust-wps": ("finaletoolkit_b200.frag", "adjust_wps", "Median-filter + Savitzky-Golay adjust raw WPS.", [
         _arg("input_file", metavar="INPUT"), _arg("interval_file", metavar="REGIONS"),
         _arg("chrom_sizes", metavar="CHROM_SIZES"), _out("bigWig file of adjusted WPS."),

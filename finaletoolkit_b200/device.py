@@ -420,3 +420,23 @@ def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, sav
                                d_coef.data_ptr(), d_ef.data_ptr(), d_el.data_ptr(), out.data_ptr(), sp),
               "ftk_savgol_f64")
     return out[:n_total], out_off
+
+
+def cleavage_intervals(frags: ContigFragments, ivl_start, ivl_stop, chrom_size, min_length=None,
+                       max_length=None, quality_threshold=30):
+    """Cleavage proportion (float64, percent) of every interval back to back + host offsets.
+
+    ``ivl_start/ivl_stop`` are the already padded/clamped bounds (frag/_cleavage_profile.py:188-189).
+    """
+    t = torch()
+    plan = WpsPlan(ivl_start, ivl_stop, int(chrom_size), 0, frags.device)   # max_len 0: mid_lo/hi = [start, stop)
+    out = t.empty(max(plan.n_positions, 1), dtype=t.float64, device=frags.device)
+    if plan.n_tiles:
+        fs, fe, mq = frags.ptrs()
+        sd = 0 if frags.strand is None else frags.strand.data_ptr()
+        check(lib().ftk_cleavage_tiles_f64(
+            fs, fe, mq, sd, frags.n, frags.max_len, plan.tile_p0.data_ptr(), plan.tile_len.data_ptr(),
+            plan.tile_mid_lo.data_ptr(), plan.tile_mid_hi.data_ptr(), plan.tile_out_off.data_ptr(), plan.n_tiles,
+            none_to_ftk(min_length), none_to_ftk(max_length), int(quality_threshold),
+            plan.scratch.data_ptr(), out.data_ptr(), _stream_ptr(frags.device)), "ftk_cleavage_tiles_f64")
+    return out[: plan.n_positions], plan.offsets

@@ -4,9 +4,11 @@ from ._coverage import coverage, single_coverage, CoverageResult
 from ._wps import wps
 from ._multi_wps import multi_wps
 from ._adjust_wps import adjust_wps
+from ._cleavage_profile import cleavage_profile, multi_cleavage_profile
 from ._end_motifs import (EndMotifFreqs, EndMotifsIntervals, region_end_motifs, end_motifs,
                           interval_end_motifs)
 
 __all__ = ["frag_length", "frag_length_bins", "frag_length_intervals", "FragLengthStats", "coverage",
-           "single_coverage", "CoverageResult", "wps", "multi_wps", "adjust_wps", "EndMotifFreqs",
+           "single_coverage", "CoverageResult", "wps", "multi_wps", "adjust_wps", "cleavage_profile",
+           "multi_cleavage_profile", "EndMotifFreqs",
            "EndMotifsIntervals", "region_end_motifs", "end_motifs", "interval_end_motifs"]

@@ -208,6 +208,24 @@ int ftk_savgol_f64(const double *adj_dev, const int64_t *seg_out_off_dev, int32_
                    int32_t sg_w, const double *coef_dev, const double *edge_first_dev,
                    const double *edge_last_dev, double *out_dev, ftk_stream_t stream);
 
+/* ------------------------------------------------------- cleavage profile
+ * Replaces _coverage_and_ends + the proportion step of cleavage_profile
+ * (frag/_cleavage_profile.py:33-90, 190-217).  Tiles as for WPS (ftk_wps_plan_tiles with
+ * max_len = 0 gives tile_mid_lo/hi = the interval [start, stop), passed here as
+ * tile_ivl_lo/hi): a fragment takes part in a tile iff mapq >= min_mapq, min_len <= L <= max_len
+ * (FTK_NONE = unbounded) and stop > ivl_lo and start < ivl_hi (frag_array(...,"any")).
+ * out[tile_out_off + (p - p0)] = depth(p) ? ends(p) / depth(p) * 100 : 0 (float64), ends = start
+ * of '+' fragments / stop of '-' fragments (frag_strand NULL = all '+').
+ * scratch_dev: int64[2 * n_tiles]. */
+int ftk_cleavage_tiles_f64(const int32_t *frag_start_dev, const int32_t *frag_stop_dev,
+                           const uint8_t *frag_mapq_dev, const uint8_t *frag_strand_dev,
+                           int64_t n_frag, int32_t max_frag_len,
+                           const int32_t *tile_p0_dev, const int32_t *tile_len_dev,
+                           const int32_t *tile_ivl_lo_dev, const int32_t *tile_ivl_hi_dev,
+                           const int64_t *tile_out_off_dev, int64_t n_tiles,
+                           int32_t min_len, int32_t max_len, int32_t min_mapq,
+                           int64_t *scratch_dev, double *out_dev, ftk_stream_t stream);
+
 /* ------------------------------------------------- fragment file decode (host)
  * Multi-threaded decode of a BGZF / gzip fragment file into per-contig columns; replaces the
  * per-interval pysam.TabixFile.fetch text stream of io/alignment.py:270-302 (5-column FinaleDB

@@ -253,6 +253,43 @@ int orc_region_end_motifs(const int32_t *fs, const int32_t *fe, const uint8_t *m
     return m.err;
 }
 
+/* ------------------------------------------------------- cleavage profile */
+/*
+ * frag/_cleavage_profile.py:188-217 (cleavage_profile) with _coverage_and_ends (:33-90) restated
+ * as the definition it implements: for every position p of [adj_start, adj_stop), over the
+ * fragments of frag_array(..., start=adj_start, stop=adj_stop, intersect_policy="any"):
+ *   depth = #{start <= p < stop},  ends = #{'+' and start == p} + #{'-' and stop == p},
+ *   proportion = depth ? ends / depth * 100 : 0.
+ */
+typedef struct { sel_t s; const uint8_t *strand; uint8_t *sd; } clv_t;
+static void clv_push(int64_t i, void *ctx) {
+    clv_t *c = (clv_t *)ctx;
+    int64_t before = c->s.cap;
+    sel_push(i, &c->s);
+    if (c->s.cap != before) c->sd = (uint8_t *)realloc(c->sd, (size_t)c->s.cap);
+    c->sd[c->s.n - 1] = c->strand[i];
+}
+int64_t orc_cleavage_interval(const int32_t *fs, const int32_t *fe, const uint8_t *mapq, const uint8_t *strand,
+                              int64_t n, int64_t max_frag_len, int64_t start, int64_t stop, int64_t left,
+                              int64_t right, int64_t chrom_size, int64_t min_len, int64_t max_len, int64_t q,
+                              double *out) {
+    int64_t adj_start = start - left; if (adj_start < 0) adj_start = 0;
+    int64_t adj_stop = stop + right;  if (adj_stop > chrom_size) adj_stop = chrom_size;
+    if (adj_stop <= adj_start) return 0;
+    clv_t c; memset(&c, 0, sizeof(c)); c.s.fs = fs; c.s.fe = fe; c.strand = strand;
+    frag_stream(fs, fe, mapq, n, max_frag_len, adj_start, adj_stop, min_len, max_len, 1, q, clv_push, &c);
+    for (int64_t p = adj_start; p < adj_stop; ++p) {
+        int64_t depth = 0, ends = 0;
+        for (int64_t j = 0; j < c.s.n; ++j) {
+            depth += (c.s.s[j] <= p && p < c.s.e[j]);
+            ends += c.sd[j] ? (c.s.s[j] == p) : (c.s.e[j] == p);
+        }
+        out[p - adj_start] = depth ? (double)ends / (double)depth * 100.0 : 0.0;
+    }
+    free(c.s.s); free(c.s.e); free(c.sd);
+    return adj_stop - adj_start;
+}
+
 /* ------------------------------------------------------------- adjust_wps */
 static int cmp_double(const void *a, const void *b) {
     double x = *(const double *)a, y = *(const double *)b;

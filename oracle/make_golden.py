@@ -494,11 +494,56 @@ def adjust(tbx, cols, cs_path):
     manifest["adjust"] = m
 
 
+# ----------------------------------------------------------------------------
+# E. cleavage profile
+# ----------------------------------------------------------------------------
+def cleavage(tbx, cols, cs_path):
+    arrays, m = {}, {}
+    frag = os.path.join(DATA, "12.3444.b37.frag.gz")
+    cs = os.path.join(DATA, "b37.chrom.sizes")
+    cases = []
+    for j, (src, contig, size, s, e, kw) in enumerate([
+        ("fixture", "12", 133851895, 34443000, 34446700, dict()),
+        ("fixture", "12", 133851895, 34443118, 34443119, dict(left=40, right=60, quality_threshold=0)),
+        ("fixture", "12", 133851895, 34444900, 34445200, dict(min_length=150, max_length=180)),
+        ("synth", "chrA", 200_000, 0, 7000, dict()),
+        ("synth", "chrA", 200_000, 193_000, 200_000, dict(right=500, quality_threshold=0)),
+        ("synth", "chrA", 200_000, 50_000, 62_000, dict(min_length=120, max_length=180, left=10, right=10)),
+        ("synth", "chrC", 4_000, 100, 3_900, dict(left=500, right=500, quality_threshold=60)),
+        ("synth", "chrB", 80_000, 40_000, 40_000, dict()),
+    ]):
+        r = F.cleavage_profile(frag if src == "fixture" else tbx, size, contig, s, e, **kw)
+        arrays[f"clv_{j}_pos"] = r["pos"].astype(np.int64)
+        arrays[f"clv_{j}_prop"] = r["proportion"].astype(np.float64)
+        cases.append(dict(src=src, contig=contig, chrom_size=size, start=s, stop=e, kwargs=kw, n=int(r.shape[0])))
+    m["cases"] = cases
+    # multi_cleavage_profile: BED with overlaps / unknown contig / padding -> bedgraph.gz + bigWig
+    bed_txt = "chrA\t1000\t1400\nchrA\t1300\t2500\nchrA\t9000\t9001\nchrUn\t5\t9\nchrB\t79000\t80000\nchrB\t100\t700\nchrC\t0\t4000\n"
+    bed = os.path.join(TMP, "clv.bed")
+    open(bed, "w").write(bed_txt)
+    m["bed"] = bed_txt
+    multi = []
+    for j, kw in enumerate([dict(), dict(left=30, right=45, min_length=100, max_length=220, quality_threshold=20)]):
+        out = os.path.join(TMP, f"clv_{j}.bed.gz")
+        F.multi_cleavage_profile(tbx, bed, cs_path, output_file=out, workers=1, **kw)
+        txt = read_gz_text(out)
+        obw = os.path.join(TMP, f"clv_{j}.bw")
+        F.multi_cleavage_profile(tbx, bed, cs_path, output_file=obw, workers=1, **kw)
+        d = pyBigWig._STORE[obw]["data"]
+        arrays[f"multi_{j}_bw_val_f32"] = np.concatenate([np.concatenate([e[2] for e in d[c]]) for c in d]).astype(np.float32)
+        multi.append(dict(kwargs=kw, n_lines=len(txt.splitlines()), sha256_text=hashlib.sha256(txt.encode()).hexdigest(),
+                          head=txt.splitlines()[:3], bw_contigs=list(d)))
+    m["multi"] = multi
+    np.savez_compressed(os.path.join(OUT, "cleavage.npz"), **arrays)
+    manifest["cleavage"] = m
+
+
 if __name__ == "__main__":
     fixture17()
     tbx, cols, cs_path = synth_small()
     motifs()
     adjust(tbx, cols, cs_path)
+    cleavage(tbx, cols, cs_path)
     with open(os.path.join(OUT, "manifest.json"), "w") as fh:
         json.dump(manifest, fh, indent=1, default=lambda o: o.item() if hasattr(o, "item") else str(o))
     for f in sorted(os.listdir(OUT)):

@@ -62,6 +62,9 @@ def lib():
         L.orc_frag_lengths.argtypes = [i32p, i32p, u8p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int64, i32p, c_int64]
         L.orc_region_end_motifs.restype = c_int
         L.orc_region_end_motifs.argtypes = [i32p, i32p, u8p, u8p, c_int64, c_int64, c_int64, c_int64, c_char_p, c_int64, c_int, c_int, c_int64, i64p]
+        L.orc_cleavage_interval.restype = c_int64
+        L.orc_cleavage_interval.argtypes = [i32p, i32p, u8p, u8p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                            c_int64, c_int64, c_int64, c_int64, dp]
         L.orc_local_filter.restype = c_int64
         L.orc_local_filter.argtypes = [dp, c_int64, c_int64, c_int, dp]
     return _lib
@@ -273,6 +276,40 @@ def mds(freq, k: int, miller_madow=False, n=None) -> float:
             return float("nan")
         ent = ent + (int(np.count_nonzero(np.nan_to_num(freq))) - 1) / (2 * n)
     return float(ent / np.log(4 ** k))
+
+
+# --------------------------------------------------------- cleavage profile
+def cleavage_profile(fr: Frags, chrom_size, start, stop, left=0, right=0, min_length=None, max_length=None,
+                     quality_threshold=30):
+    """frag/_cleavage_profile.py:93-224 -> (positions int64, proportion float64)."""
+    a = max(int(start) - int(left), 0)
+    b = min(int(stop) + int(right), int(chrom_size))
+    out = np.zeros(max(b - a, 0), np.float64)
+    lib().orc_cleavage_interval(*fr._args()[:3], _p(fr.strand, c_uint8), fr.n, fr.max_len, int(start), int(stop),
+                                int(left), int(right), int(chrom_size), _n(min_length), _n(max_length),
+                                int(quality_threshold), _p(out, c_double))
+    return np.arange(a, max(b, a), dtype=np.int64), out
+
+
+def cleavage_intervals(lines, left, right, chrom_sizes: dict):
+    """frag/_cleavage_profile.py:411-449 (_read_intervals): expand, clamp, merge overlapping neighbours."""
+    contigs, starts, stops = [], [], []
+    prev_contig, prev_start, prev_stop = None, 0, 0
+    for line in lines:
+        c = line.split()
+        contig = c[0].strip()
+        start, stop = int(c[1]), int(c[2])
+        if contig not in chrom_sizes:
+            continue
+        start = max(0, start - left)
+        stop = min(stop + right, chrom_sizes[contig])
+        if prev_contig == contig and start < prev_stop:
+            prev_stop = max(prev_stop, stop)
+        else:
+            contigs.append(prev_contig); starts.append(prev_start); stops.append(prev_stop)
+            prev_contig, prev_start, prev_stop = contig, start, stop
+    contigs.append(prev_contig); starts.append(prev_start); stops.append(prev_stop)
+    return list(zip(contigs[1:], starts[1:], stops[1:]))
 
 
 # --------------------------------------------------------------- adjust_wps

@@ -15,7 +15,7 @@ def test_help_and_kwarg_bijection():
     from finaletoolkit_b200.cli.main_cli import COMMANDS, main_cli
     r = CliRunner().invoke(main_cli, ["--help"])
     assert r.exit_code == 0
-    expected = {"wps", "adjust-wps", "coverage", "frag-length-bins", "frag-length-intervals", "end-motifs",
+    expected = {"wps", "cleavage-profile", "adjust-wps", "coverage", "frag-length-bins", "frag-length-intervals", "end-motifs",
                 "interval-end-motifs", "mds", "regional-mds"}
     assert set(COMMANDS) == expected
     for name, (module, func, _, spec) in COMMANDS.items():

@@ -244,3 +244,14 @@ def test_adjust_driver(manifest, golden):
         pos = np.concatenate(pos_all); val = np.concatenate(val_all).astype(np.float32)
         assert np.array_equal(pos, g[f"adj_{j}_pos"])
         assert np.array_equal(val, g[f"adj_{j}_val_f32"])
+
+
+def test_cleavage(manifest, golden):
+    g = golden("cleavage"); m = manifest["cleavage"]
+    fx = golden("fixture17"); sy = golden("synth_small")
+    for j, c in enumerate(m["cases"]):
+        fr = frags_of(fx) if c["src"] == "fixture" else frags_of(sy, c["contig"] + "_")
+        pos, prop = O.cleavage_profile(fr, c["chrom_size"], c["start"], c["stop"], **c["kwargs"])
+        assert np.array_equal(pos, g[f"clv_{j}_pos"]) and np.array_equal(prop, g[f"clv_{j}_prop"]), c
+    sizes = dict(manifest["synth_small"]["contigs"])
+    assert O.cleavage_intervals(m["bed"].splitlines(), 0, 0, sizes)[:2] == [("chrA", 1000, 2500), ("chrA", 9000, 9001)]
