@@ -155,6 +155,53 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------- secondary kernels (N=1 only)
+def other_kernels(frags, raw_wps_f32, dev, peak):
+    """CUDA-event timings of the other hot-path kernels on the same chr1-scale shard, each against
+    its own algorithmic bytes: adjust_wps, end motifs, cleavage profile."""
+    import torch
+    from finaletoolkit_b200 import device as D
+    from finaletoolkit_b200.synth import synth_twobit
+
+    def timed(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        for i in range(reps):
+            ev[i].record(); fn()
+        ev[reps].record(); torch.cuda.synchronize()
+        return min(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+
+    def row(ms, nbytes, units, unit_name):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return {"ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "frac_of_measured_hbm_peak": gbs / peak,
+                unit_name + "_per_sec": units / (ms * 1e-3)}
+
+    out = {}
+    ivl_s, ivl_e = make_intervals()
+    # adjust_wps: median window 1000 + Savitzky-Golay(21,2) over the full 5-kb intervals of the raw WPS
+    full = int(np.sum((ivl_e - ivl_s) == IVL))
+    lens = np.full(full, IVL, dtype=np.int64)
+    x = raw_wps_f32[: full * IVL]
+    n_out = int((lens - 1000).sum())
+    ms = timed(lambda: D.adjust_segments(x, lens))
+    out["adjust_wps(median1000+savgol21/2)"] = row(ms, 4 * x.numel() + 8 * n_out, n_out, "positions")
+    del x
+    # cleavage profile over the same 5-kb tiling (10 B/fragment + 8 B/position)
+    ms = timed(lambda: D.cleavage_intervals(frags, ivl_s, ivl_e, CONTIG_LEN, None, None, MAPQ))
+    out["cleavage_profile"] = row(ms, 10 * frags.n + 8 * CONTIG_LEN, CONTIG_LEN, "positions")
+    # end motifs k=4, both strands, genome-wide 1-Mb windows pooled (10 B/fragment + L2-resident reference)
+    codes, nm = synth_twobit(CONTIG_LEN, 0)
+    ref = D.PackedContig.from_codes(codes, nm, device=dev)
+    if frags.strand is None:
+        frags.strand = torch.ones(frags.n, dtype=torch.uint8, device=dev)
+    win = [(s, s + 1_000_000) for s in range(0, CONTIG_LEN - 1_000_000, 1_000_000)]
+    win.append((CONTIG_LEN - CONTIG_LEN % 1_000_000, CONTIG_LEN))
+    ws, we = [a for a, _ in win], [b for _, b in win]
+    ms = timed(lambda: D.end_motif_hist(frags, ref, ws, we, k=4, strand_mode=0, quality_threshold=MAPQ, pooled=True))
+    out["end_motifs(k=4,both strands)"] = row(ms, 10 * frags.n, frags.n, "fragments")
+    return out
+
+
 # ------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -180,7 +227,8 @@ def run_ours(args):
     h_st = torch.from_numpy(st).pin_memory()
     h_sp = torch.from_numpy(sp).pin_memory()
     h_mq = torch.from_numpy(mq).pin_memory()
-    frags = D.ContigFragments(h_st.to(dev), h_sp.to(dev), h_mq.to(dev), None, device=dev, max_len=600)
+    frags = D.ContigFragments(h_st.to(dev), h_sp.to(dev), h_mq.to(dev), torch.from_numpy(sd).to(dev), device=dev,
+                              max_len=600)
 
     ivl_s, ivl_e = make_intervals()
     plan = D.WpsPlan(ivl_s, ivl_e, CONTIG_LEN, MAX_LEN, dev)
@@ -243,6 +291,7 @@ def run_ours(args):
     # ---- end-to-end: pinned host columns -> chunked H2D -> kernels -> D2H of every result
     # (finaletoolkit_b200.pipeline.StreamedContig: 3 streams, double-buffered staging, int16 WPS)
     from finaletoolkit_b200.pipeline import StreamedContig
+    wps_out_for_extras = wps_out.to(torch.float32) if (world == 1 and not args.no_extras) else None
     del wps_out
     torch.cuda.empty_cache()
     pipe = StreamedContig(h_st, h_sp, h_mq, ivl_s, ivl_e, CONTIG_LEN, WINDOW, MIN_LEN, MAX_LEN, MAPQ,
@@ -296,6 +345,11 @@ def run_ours(args):
                     "gpu_launches_per_step": pipe.kernel_launches},
             "gpu_launches": launches_per_step * K, "clocks": clocks, "wps_checksum": checksum,
         }
+        if world == 1 and not args.no_extras:
+            try:
+                line["other_kernels"] = other_kernels(frags, wps_out_for_extras, dev, peak)
+            except Exception as e:  # noqa: BLE001 - secondary numbers must never sink the headline line
+                line["other_kernels"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_sample_rate(st, sp, mq, float(os.environ.get("FTK_BENCH_CPU_S", 10.0)))
         else:
@@ -313,6 +367,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernels' timings")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,4 +1,4 @@
-"""Scratch: adjust_wps timing at chr1 scale (raw WPS from our kernel -> float32 -> adjust)."""
+"""Profiling helper (run from the repo root: PYTHONPATH=. python tools/...): adjust_wps timing at chr1 scale (raw WPS from our kernel -> float32 -> adjust)."""
 import sys, time
 import numpy as np, torch
 from finaletoolkit_b200.device import ContigFragments, WpsPlan, adjust_segments

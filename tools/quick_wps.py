@@ -1,4 +1,4 @@
-"""Scratch: quick WPS timing at config 2 (chr1-scale) - not the bench contract."""
+"""Profiling helper (run from the repo root: PYTHONPATH=. python tools/...): quick WPS timing at config 2 (chr1-scale) - not the bench contract."""
 import sys, time
 import numpy as np, torch, os, ctypes
 from finaletoolkit_b200._lib import lib
