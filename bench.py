@@ -58,7 +58,7 @@ class ClockSampler(threading.Thread):
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index: int, period=0.01):
+    def __init__(self, index: int, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.mask, self.max_mhz = [], 0, None
@@ -86,7 +86,16 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(self.period)
 
+    def sample_now(self):
+        if self.ok:
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:  # noqa: BLE001
+                pass
+
     def finish(self):
+        self.sample_now()   # the GPU has just drained the timed region: never report zero samples
         self._stop_evt.set()
         if self.is_alive():
             self.join()
@@ -280,8 +289,9 @@ def run_ours(args):
     for k in range(K):
         step(kev[k])
     e1.record()
-    barrier()
+    torch.cuda.current_stream().synchronize()
     clocks = sampler.finish()
+    barrier()
     ms_total = e0.elapsed_time(e1)
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
