@@ -43,14 +43,15 @@ struct Stream {
         e_eff = (E == FTK_NONE) ? INT32_MAX : E;
         midpoint = p.policy == FTK_POLICY_MIDPOINT;
     }
+    // Branch-free: every test is evaluated and AND-ed (predicate logic, no short-circuit branches).
     __device__ __forceinline__ bool operator()(int fs, int fe, int q) const {
         const int L = fe - fs;
-        bool ok = (q >= min_mapq) && ((unsigned)(L - len_lo) <= len_span) && (fe > s_over) && (fs < e_eff);
-        if (midpoint) {
-            const int mid = fs + (L >> 1);
-            ok = ok && (mid >= s_mid) && (mid < e_eff);
-        }
-        return ok && len_any;
+        const int mid = fs + (L >> 1);
+        const unsigned ok_len = (unsigned)((unsigned)(L - len_lo) <= len_span);
+        const unsigned ok_q = (unsigned)(q >= min_mapq);
+        const unsigned ok_over = (unsigned)(fe > s_over) & (unsigned)(fs < e_eff);
+        const unsigned ok_mid = midpoint ? ((unsigned)(mid >= s_mid) & (unsigned)(mid < e_eff)) : 1u;
+        return (ok_len & ok_q & ok_over & ok_mid & (unsigned)len_any) != 0u;
     }
 };
 

@@ -176,6 +176,7 @@ class WpsPlan:
 
 _POLICY = {"midpoint": 0, "any": 1}
 _TARGET_CTAS = 148 * 8  # SM count x resident CTAs: enough slices to fill the chip
+_UNIT_FRAGS = 2048
 
 
 def policy_code(intersect_policy: str) -> int:
@@ -187,14 +188,18 @@ def policy_code(intersect_policy: str) -> int:
         raise InvalidInputError(f"{intersect_policy} is not a valid policy") from None
 
 
-def _splits_for(n_ivl: int, n_frag: int, per_unit: int = 16384) -> int:
-    """Slices per interval: enough units to fill the chip several times over, none below
-    ~``per_unit`` candidate fragments (estimated from the contig-wide mean)."""
+def _splits_for(n_ivl: int, n_frag: int) -> int:
+    """Slices per interval.  A unit (one warp, or one CTA for per-interval histograms) should hold
+    about ``_UNIT_FRAGS`` candidate fragments - few enough that its loads are all in flight at
+    once, many enough to amortise its descriptor fetch - and there should be at least a few
+    waves of units; estimated from the contig-wide mean fragments per interval."""
     if n_ivl <= 0:
         return 1
+    import os
+    unit = int(os.environ.get("FTK_UNIT_FRAGS", _UNIT_FRAGS))
+    by_size = -(-(n_frag // max(n_ivl, 1)) // unit)
     by_grid = -(-4 * _TARGET_CTAS // n_ivl)
-    by_size = max(1, (n_frag // max(n_ivl, 1)) // per_unit + 1)
-    return int(max(1, min(by_grid, by_size, 65536)))
+    return int(max(1, min(max(by_size, by_grid), 65536)))
 
 
 def _ivl_to_device(ivl_start, ivl_stop, device):
