@@ -39,8 +39,9 @@ cleavage_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__re
                      const int32_t *__restrict__ tile_ivl_lo, const int32_t *__restrict__ tile_ivl_hi,
                      const int64_t *__restrict__ tile_out_off, const int64_t *__restrict__ ranges,
                      int min_len, int max_len, int min_mapq, double *__restrict__ out) {
-    __shared__ __align__(16) int D[kClvCap];   // depth difference array
-    __shared__ __align__(16) int E[kClvCap];   // fragment-end counts
+    __shared__ __align__(16) int DE[2 * kClvCap];
+    int *D = DE;              // depth difference array
+    int *E = DE + kClvCap;    // fragment-end counts (the pair is recycled as double[kClvCap] for the store)
     __shared__ int warp_tot[kClvThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile = blockIdx.x;
@@ -52,9 +53,21 @@ cleavage_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__re
         reinterpret_cast<int4 *>(E)[i] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();
-    for (int64_t i = lo + tid; i < hi; i += kClvThreads) {
-        const int fs = __ldcs(frag_start + i), fe = __ldcs(frag_stop + i);
-        const int q = frag_mapq ? (int)__ldcs(frag_mapq + i) : 255;
+    constexpr int kU = 4;   // independent loads in flight per thread
+    for (int64_t i0 = lo + tid; i0 < hi; i0 += (int64_t)kU * kClvThreads) {
+      int fs_r[kU], fe_r[kU], q_r[kU], sd_r[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t i = i0 + (int64_t)u * kClvThreads;
+        const bool in = i < hi;
+        fs_r[u] = in ? __ldcs(frag_start + i) : 0;
+        fe_r[u] = in ? __ldcs(frag_stop + i) : -1;
+        q_r[u] = in ? (frag_mapq ? (int)__ldcs(frag_mapq + i) : 255) : -1;
+        sd_r[u] = (in && frag_strand) ? (int)__ldcs(frag_strand + i) : 1;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int fs = fs_r[u], fe = fe_r[u], q = q_r[u];
         const int L = fe - fs;
         // frag_array(..., "any") of the INTERVAL: tabix overlap + mapq + inclusive length window
         if (q < min_mapq || L < 0 || !frag_len_ok(L, min_len, max_len) || !(fe > ivl_lo && fs < ivl_hi)) continue;
@@ -63,8 +76,9 @@ cleavage_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__re
             atomicAdd(&D[max(s_idx, 0)], 1);
             if (e_idx < len) atomicAdd(&D[e_idx], -1);
         }
-        const int end_idx = (frag_strand == nullptr || __ldcs(frag_strand + i)) ? s_idx : e_idx;
+        const int end_idx = sd_r[u] ? s_idx : e_idx;
         if (end_idx >= 0 && end_idx < len) atomicAdd(&E[end_idx], 1);
+      }
     }
     __syncthreads();
     // block prefix scan: each thread owns kClvPer contiguous positions (int4 loads, conflict-free)
@@ -88,17 +102,24 @@ cleavage_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__re
     int offset = t - d[kClvPer - 1];
 #pragma unroll
     for (int w = 0; w < kClvThreads / 32; ++w) offset += (w < warp) ? warp_tot[w] : 0;
-    double *__restrict__ dst = out + tile_out_off[tile];
+    int e[kClvPer];
+#pragma unroll
+    for (int j = 0; j < kClvPer / 4; ++j) {
+        const int4 v = *reinterpret_cast<const int4 *>(&E[base + 4 * j]);
+        e[4 * j] = v.x; e[4 * j + 1] = v.y; e[4 * j + 2] = v.z; e[4 * j + 3] = v.w;
+    }
+    __syncthreads();   // every thread holds its depth/end counts: D and E can be recycled
+    double *stage = reinterpret_cast<double *>(DE);
 #pragma unroll
     for (int j = 0; j < kClvPer; ++j) {
-        const int p = base + j;
-        if (p < len) {
-            const int depth = d[j] + offset;
-            const int ends = E[p];
-            // proportions[mask] = ends[mask] / depth[mask] * 100   (frag/_cleavage_profile.py:206-208)
-            dst[p] = depth != 0 ? (double)ends / (double)depth * 100.0 : 0.0;
-        }
+        const int depth = d[j] + offset;
+        // proportions[mask] = ends[mask] / depth[mask] * 100   (frag/_cleavage_profile.py:206-208);
+        // 0 / depth * 100 is exactly 0.0, so the fp64 division only runs where an end was counted
+        stage[base + j] = (depth != 0 && e[j] != 0) ? (double)e[j] / (double)depth * 100.0 : 0.0;
     }
+    __syncthreads();
+    double *__restrict__ dst = out + tile_out_off[tile];
+    for (int p = tid; p < len; p += kClvThreads) dst[p] = stage[p];   // coalesced
 }
 
 }  // namespace ftk
