@@ -267,3 +267,62 @@ extern "C" int ftk_fragfile_copy(void *h, int32_t i, int32_t *start, int32_t *st
     return FTK_OK;
 }
 extern "C" void ftk_fragfile_close(void *h) { delete static_cast<FragFile *>(h); }
+
+// ---------------------------------------------------------------- bigWig section codec
+// Sections are independent zlib streams, so a batch is an embarrassingly parallel loop; the
+// threads take members round-robin (sections are near-uniform in size).
+namespace {
+template <typename F>
+int run_members(int64_t n, int32_t n_threads, F &&one) {
+    if (n_threads < 1) n_threads = (int32_t)std::max(1u, std::thread::hardware_concurrency());
+    const int T = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, n));
+    std::vector<int> rc((size_t)T, 0);
+    auto work = [&](int t) {
+        for (int64_t i = t; i < n; i += T) {
+            int r = one(i);
+            if (r != 0) { rc[(size_t)t] = r; return; }
+        }
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    for (int r : rc) if (r != 0) return r;
+    return 0;
+}
+}  // namespace
+
+extern "C" int ftk_zlib_compress_batch(const uint8_t *in, const int64_t *in_off, int64_t n, int32_t level,
+                                       int32_t n_threads, uint8_t *out, const int64_t *out_off,
+                                       int64_t *out_size) {
+    if (n < 0 || level < -1 || level > 9) return FTK_E_INVALID;
+    if (n == 0) return 0;
+    if (!in || !in_off || !out || !out_off || !out_size) return FTK_E_INVALID;
+    return run_members(n, n_threads, [&](int64_t i) -> int {
+        const int64_t len = in_off[i + 1] - in_off[i], cap = out_off[i + 1] - out_off[i];
+        if (len < 0 || cap < 0 || (uLong)cap < compressBound((uLong)len)) return FTK_E_INVALID;
+        uLongf got = (uLongf)cap;
+        if (compress2(out + out_off[i], &got, in + in_off[i], (uLong)len, level) != Z_OK) return FTK_E_IO;
+        out_size[i] = (int64_t)got;
+        return 0;
+    });
+}
+
+extern "C" int ftk_zlib_uncompress_batch(const uint8_t *in, const int64_t *in_off, const int64_t *in_size,
+                                         int64_t n, int32_t n_threads, uint8_t *out, const int64_t *out_off,
+                                         int64_t *out_size) {
+    if (n < 0) return FTK_E_INVALID;
+    if (n == 0) return 0;
+    if (!in || !in_off || !in_size || !out || !out_off || !out_size) return FTK_E_INVALID;
+    return run_members(n, n_threads, [&](int64_t i) -> int {
+        const int64_t cap = out_off[i + 1] - out_off[i];
+        if (in_size[i] < 0 || cap < 0) return FTK_E_INVALID;
+        uLongf got = (uLongf)cap;
+        if (uncompress(out + out_off[i], &got, in + in_off[i], (uLong)in_size[i]) != Z_OK) return FTK_E_IO;
+        out_size[i] = (int64_t)got;
+        return 0;
+    });
+}

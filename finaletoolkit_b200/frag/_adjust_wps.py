@@ -58,6 +58,7 @@ def adjust_wps(input_file, interval_file, output_file, chrom_sizes, interval_siz
         raise ValueError("Invalid filetype for input_file.")
     raw_wps = pbw.open(input_file, "r")
     try:
+        raw_wps.prefetch(intervals)   # one multi-threaded inflate of every section the intervals touch
         seg_vals, seg_pos, seg_contig = [], [], []
         for contig, start, stop in intervals:
             try:

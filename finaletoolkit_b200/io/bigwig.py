@@ -10,16 +10,23 @@ and ``adjust_wps`` reads it back with ``intervals(contig, start, stop)``
 index, total summary; zoom levels are optional in the format and omitted) so files
 interoperate with pyBigWig / UCSC tools.  Values are stored as float32 like libBigWig.
 
+Sections are independent zlib streams; the writer queues them and deflates a batch at a
+time on all host threads through the C ABI (``ftk_zlib_compress_batch``), and the reader
+can inflate every section a list of queries touches in one call (``prefetch`` ->
+``ftk_zlib_uncompress_batch``).  Both need ``libftk_b200.so`` (host code, no GPU).
+
     bw = open(path, "w"); bw.addHeader([(chrom, size), ...]); bw.addEntries(...); bw.close()
     bw = open(path);      bw.chroms(); bw.intervals(chrom, start, end); bw.values(chrom, s, e)
 """
 from __future__ import annotations
 
 import builtins
+import ctypes
 import struct
-import zlib
 
 import numpy as np
+
+from .._lib import check, lib
 
 __all__ = ["open", "BigWigReader", "BigWigWriter"]
 
@@ -28,6 +35,43 @@ _CHROM_TREE_MAGIC = 0x78CA8C91
 _RTREE_MAGIC = 0x2468ACE0
 _ITEMS_PER_SECTION = 16384   # <= 65535 (itemCount is u16)
 _RTREE_BLOCK = 256
+_FLUSH_BYTES = 64 << 20      # queued raw section bytes before a batch is deflated
+_SECTION_HDR = 24
+
+
+def _ptr(a: np.ndarray, ctype):
+    return a.ctypes.data_as(ctypes.POINTER(ctype))
+
+
+def _deflate_sections(raws: list[bytes], level: int = 6) -> list[bytes]:
+    """zlib-compress independent sections on all host threads (ftk_zlib_compress_batch)."""
+    n = len(raws)
+    lens = np.fromiter((len(r) for r in raws), dtype=np.int64, count=n)
+    in_off = np.zeros(n + 1, dtype=np.int64); np.cumsum(lens, out=in_off[1:])
+    out_off = np.zeros(n + 1, dtype=np.int64); np.cumsum(lens + lens // 1000 + 64, out=out_off[1:])
+    src = np.frombuffer(b"".join(raws), dtype=np.uint8)
+    dst = np.empty(int(out_off[-1]), dtype=np.uint8)
+    sizes = np.zeros(n, dtype=np.int64)
+    check(lib().ftk_zlib_compress_batch(_ptr(src, ctypes.c_uint8), _ptr(in_off, ctypes.c_int64), n, level, 0,
+                                        _ptr(dst, ctypes.c_uint8), _ptr(out_off, ctypes.c_int64),
+                                        _ptr(sizes, ctypes.c_int64)), "ftk_zlib_compress_batch")
+    return [dst[int(o): int(o) + int(z)].tobytes() for o, z in zip(out_off[:-1], sizes)]
+
+
+def _inflate_sections(buf: bytes, blocks: list[tuple[int, int]], max_uncomp: int) -> list[bytes]:
+    """Inflate independent sections on all host threads (ftk_zlib_uncompress_batch)."""
+    n = len(blocks)
+    in_off = np.fromiter((b[0] for b in blocks), dtype=np.int64, count=n)
+    in_size = np.fromiter((b[1] for b in blocks), dtype=np.int64, count=n)
+    out_off = np.arange(n + 1, dtype=np.int64) * int(max_uncomp)
+    src = np.frombuffer(buf, dtype=np.uint8)
+    dst = np.empty(int(out_off[-1]), dtype=np.uint8)
+    sizes = np.zeros(n, dtype=np.int64)
+    check(lib().ftk_zlib_uncompress_batch(_ptr(src, ctypes.c_uint8), _ptr(in_off, ctypes.c_int64),
+                                          _ptr(in_size, ctypes.c_int64), n, 0, _ptr(dst, ctypes.c_uint8),
+                                          _ptr(out_off, ctypes.c_int64), _ptr(sizes, ctypes.c_int64)),
+          "ftk_zlib_uncompress_batch")
+    return [dst[int(o): int(o) + int(z)].tobytes() for o, z in zip(out_off[:-1], sizes)]
 
 
 class BigWigWriter:
@@ -37,6 +81,8 @@ class BigWigWriter:
         self._chroms: list[tuple[str, int]] | None = None
         self._ids: dict[str, int] = {}
         self._sections: list[tuple[int, int, int, int, int]] = []  # chromId, start, end, offset, size
+        self._pending: list[tuple[int, int, int, bytes]] = []      # chromId, start, end, raw section
+        self._pending_bytes = 0
         self._last = (-1, -1)   # (chromId, end) of the previous entry: entries must be sorted
         self._max_uncomp = 0
         self._n_cov, self._min, self._max, self._sum, self._sumsq = 0, np.inf, -np.inf, 0.0, 0.0
@@ -97,6 +143,7 @@ class BigWigWriter:
         if self._chroms is None:
             fh.close()
             return
+        self._flush()
         index_off = fh.tell()
         self._write_rtree(index_off)
         end = fh.tell()
@@ -142,10 +189,19 @@ class BigWigWriter:
     def _emit(self, cid, start, end, step, span, typ, payload: bytes, n_items: int) -> None:
         raw = struct.pack("<IIIIIBBH", cid, start, end, step, span, typ, 0, n_items) + payload
         self._max_uncomp = max(self._max_uncomp, len(raw))
-        comp = zlib.compress(raw, 6)
-        off = self._fh.tell()
-        self._fh.write(comp)
-        self._sections.append((cid, start, end, off, len(comp)))
+        self._pending.append((cid, start, end, raw))
+        self._pending_bytes += len(raw)
+        if self._pending_bytes >= _FLUSH_BYTES:
+            self._flush()
+
+    def _flush(self) -> None:
+        if not self._pending:
+            return
+        pend, self._pending, self._pending_bytes = self._pending, [], 0
+        for (cid, start, end, _), comp in zip(pend, _deflate_sections([p[3] for p in pend])):
+            off = self._fh.tell()
+            self._fh.write(comp)
+            self._sections.append((cid, start, end, off, len(comp)))
 
     def _add_fixed(self, cid, start, span, step, vals) -> None:
         n = vals.size
@@ -233,6 +289,7 @@ class BigWigReader:
         _, _, key_size, _, _, _ = struct.unpack_from(e + "IIIIQQ", b, ct_off)
         self._walk_chrom_tree(ct_off + 32, key_size)
         self._by_id = {cid: (name, size) for name, (cid, size) in self._chroms.items()}
+        self._cache: dict[int, bytes] = {}   # data offset -> inflated section
 
     def _walk_chrom_tree(self, off: int, key_size: int) -> None:
         b, e = self._buf, self._e
@@ -284,6 +341,40 @@ class BigWigReader:
         walk(self._index_off + 48)
         return out
 
+    def _section(self, doff: int, dsize: int) -> bytes:
+        raw = self._cache.get(doff)
+        if raw is None:
+            raw = self._buf[doff: doff + dsize]
+            if self._uncomp:
+                (raw,) = _inflate_sections(self._buf, [(doff, dsize)], self._uncomp)
+        return raw
+
+    def prefetch(self, queries) -> None:
+        """Inflate, in one multi-threaded batch, every section the (chrom, start, end) queries touch.
+
+        Later ``intervals`` / ``intervals_arrays`` / ``values`` calls on those ranges are served from
+        the cache.  Invalid queries are ignored here; they raise when actually queried."""
+        if not self._uncomp:
+            return
+        need: dict[int, int] = {}
+        for chrom, start, end in queries:
+            if chrom not in self._chroms:
+                continue
+            cid, size = self._chroms[chrom]
+            start = 0 if start is None else int(start)
+            end = size if end is None or end == 0 else int(end)
+            if start < 0 or end > size or start >= end:
+                continue
+            for doff, dsize in self._blocks(cid, start, end):
+                if doff not in self._cache:
+                    need[doff] = dsize
+        blocks = sorted(need.items())
+        per_batch = max(1, _FLUSH_BYTES // max(int(self._uncomp), 1))
+        for i in range(0, len(blocks), per_batch):
+            part = blocks[i: i + per_batch]
+            for (doff, _), raw in zip(part, _inflate_sections(self._buf, part, self._uncomp)):
+                self._cache[doff] = raw
+
     def _intervals_arrays(self, chrom, start, end):
         if chrom not in self._chroms:
             raise RuntimeError("Invalid interval bounds!")
@@ -295,9 +386,7 @@ class BigWigReader:
         b, e = self._buf, self._e
         S, E, V = [], [], []
         for doff, dsize in self._blocks(cid, start, end):
-            raw = b[doff: doff + dsize]
-            if self._uncomp:
-                raw = zlib.decompress(raw)
+            raw = self._section(doff, dsize)
             bcid, bstart, bend, step, span, typ, _, n = struct.unpack_from(e + "IIIIIBBH", raw, 0)
             if bcid != cid:
                 continue
@@ -311,12 +400,19 @@ class BigWigReader:
             else:
                 rec = np.frombuffer(raw, np.dtype([("s", e + "u4"), ("e", e + "u4"), ("v", e + "f4")]), n, 24)
                 s = rec["s"].astype(np.int64); en = rec["e"].astype(np.int64); v = rec["v"]
-            m = (en > start) & (s < end)
-            if m.any():
-                S.append(s[m]); E.append(en[m]); V.append(v[m])
+            if n == 0:
+                continue
+            if bstart < start or bend > end:      # only boundary sections need clipping
+                m = (en > start) & (s < end)
+                if not m.any():
+                    continue
+                s, en, v = s[m], en[m], v[m]
+            S.append(s); E.append(en); V.append(v)
         if not S:
             return None
         s, en, v = np.concatenate(S), np.concatenate(E), np.concatenate(V)
+        if np.all(s[1:] >= s[:-1]):
+            return s, en, v
         order = np.argsort(s, kind="stable")
         return s[order], en[order], v[order]
 
@@ -343,6 +439,7 @@ class BigWigReader:
 
     def close(self) -> None:
         self._buf = b""
+        self._cache = {}
 
     def __enter__(self):
         return self

@@ -244,6 +244,25 @@ int ftk_fragfile_copy(void *handle, int32_t i, int32_t *start_host, int32_t *sto
                       uint8_t *mapq_host, uint8_t *strand_host);
 void ftk_fragfile_close(void *handle);
 
+/* ------------------------------------------------- bigWig section codec (host)
+ * bigWig data sections are independent zlib streams (one per <= 65535 items), which the
+ * reference compresses / inflates one at a time inside pyBigWig's addEntries / intervals
+ * (frag/_multi_wps.py:300-325, frag/_adjust_wps.py:80-105,275-291).  These two calls run a
+ * whole batch of sections on n_threads host threads (n_threads < 1 = all hardware threads).
+ * Host pointers only; no CUDA involved.
+ *   compress:   member i = in[in_off[i] .. in_off[i+1]) -> written at out + out_off[i]; the slot
+ *               out_off[i+1] - out_off[i] must be >= zlib's compressBound(len) (len + len/1000 +
+ *               64 is enough); out_size[i] receives the compressed size.
+ *   uncompress: member i = in[in_off[i] .. in_off[i] + in_size[i]) -> out + out_off[i], slot
+ *               out_off[i+1] - out_off[i]; out_size[i] receives the inflated size.
+ * Return 0, FTK_E_INVALID (bad arguments / slot too small) or FTK_E_IO (corrupt stream). */
+int ftk_zlib_compress_batch(const uint8_t *in, const int64_t *in_off, int64_t n, int32_t level,
+                            int32_t n_threads, uint8_t *out, const int64_t *out_off,
+                            int64_t *out_size);
+int ftk_zlib_uncompress_batch(const uint8_t *in, const int64_t *in_off, const int64_t *in_size,
+                              int64_t n, int32_t n_threads, uint8_t *out, const int64_t *out_off,
+                              int64_t *out_size);
+
 #ifdef __cplusplus
 }
 #endif

@@ -165,6 +165,42 @@ def test_bigwig_roundtrip_and_real_file_layout(tmp_path):
     assert hd["nBasesCovered"] == 100_000 + 10 + 20_000 and hd["minVal"] <= -39
 
 
+def test_bigwig_sections_are_standard_zlib_and_prefetch(tmp_path):
+    """The batched section codec (ftk_zlib_*_batch) writes plain zlib streams and reads them back."""
+    import struct
+    import zlib
+    from finaletoolkit_b200.io import bigwig
+    p = str(tmp_path / "b.bw")
+    rng = np.random.default_rng(3)
+    v = rng.integers(-60, 30, 70_000).astype(np.float64)
+    with bigwig.open(p, "w") as w:
+        w.addHeader([("1", 1_000_000)])
+        for i in range(0, 70_000, 5000):                    # multi_wps-style: one call per interval
+            w.addEntries("1", 1000 + i, values=v[i: i + 5000], span=1, step=1)
+    r = bigwig.open(p)
+    # every R-tree leaf points at an independent zlib stream python's zlib inflates
+    got = []
+    for doff, dsize in r._blocks(0, 0, 1_000_000):
+        raw = zlib.decompress(r._buf[doff: doff + dsize])
+        cid, s, e, step, span, typ, _, n = struct.unpack_from("<IIIIIBBH", raw, 0)
+        assert (cid, step, span, typ) == (0, 1, 1, 3) and e - s == n and len(raw) == 24 + 4 * n
+        got.append(np.frombuffer(raw, "<f4", n, 24))
+    assert np.array_equal(np.concatenate(got), v.astype(np.float32))
+    # prefetch == lazy reads; invalid queries are ignored by prefetch and raise when queried
+    lazy = r.intervals_arrays("1", 3000, 60_000)
+    r2 = bigwig.open(p)
+    r2.prefetch([("1", 3000, 60_000), ("nope", 0, 5), ("1", 10, 2_000_000)])
+    assert len(r2._cache) > 0
+    pre = r2.intervals_arrays("1", 3000, 60_000)
+    assert all(np.array_equal(a, b) for a, b in zip(lazy, pre))
+    with pytest.raises(RuntimeError):
+        r2.intervals_arrays("1", 10, 2_000_000)
+    # the raw codec: bad slot -> invalid, corrupt stream -> io error
+    from finaletoolkit_b200._lib import FtkLibraryError
+    with pytest.raises(FtkLibraryError):
+        bigwig._inflate_sections(b"not a zlib stream at all", [(0, 24)], 1024)
+
+
 def test_savgol_tables_match_scipy():
     from scipy.signal import savgol_coeffs, savgol_filter
     from finaletoolkit_b200.device import savgol_tables
