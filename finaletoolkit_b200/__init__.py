@@ -21,6 +21,10 @@ _EXPORTS = {
     "end_motifs": ("frag", "end_motifs"), "region_end_motifs": ("frag", "region_end_motifs"),
     "interval_end_motifs": ("frag", "interval_end_motifs"),
     "EndMotifFreqs": ("frag", "EndMotifFreqs"), "EndMotifsIntervals": ("frag", "EndMotifsIntervals"),
+    "breakpoint_motifs": ("frag", "breakpoint_motifs"), "region_breakpoint_motifs": ("frag", "region_breakpoint_motifs"),
+    "interval_breakpoint_motifs": ("frag", "interval_breakpoint_motifs"),
+    "BreakpointMotifFreqs": ("frag", "BreakpointMotifFreqs"),
+    "BreakpointMotifsIntervals": ("frag", "BreakpointMotifsIntervals"),
     "frag_generator": ("utils", "frag_generator"), "frag_array": ("utils", "frag_array"),
     "frags_in_region": ("utils", "frags_in_region"), "get_intervals": ("utils", "get_intervals"),
     "gen_kmers": ("utils", "gen_kmers"), "reverse_complement": ("utils", "reverse_complement"),

@@ -44,6 +44,9 @@ SYMBOLS = {
     "ftk_end_motif_hist_u64": (c_int, [_P, _P, _P, _P, c_int64, c_int32, _P, _P, c_int64,
                                        _P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32,
                                        _P, _P, _P, _P]),
+    "ftk_breakpoint_motif_hist_u64": (c_int, [_P, _P, _P, _P, c_int64, c_int32, _P, _P, c_int64,
+                                              _P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                              _P, _P, _P]),
     "ftk_adjust_edge_shift_f64": (c_int, [_P, _P, c_int32, c_int32, _P, _P]),
     "ftk_adjust_wps_f64": (c_int, [_P, _P, _P, _P, _P, c_int32, c_int64, c_int32, c_int32, c_int32, _P, _P, _P]),
     "ftk_adjust_wps_generic_f64": (c_int, [_P, _P, _P, _P, _P, c_int32, _P, c_int64, c_int32, c_int32, c_int32,

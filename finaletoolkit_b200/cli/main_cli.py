@@ -123,6 +123,13 @@ COMMANDS = {
     "interval-end-motifs": ("finaletoolkit_b200.frag", "interval_end_motifs", "End-motif counts per BED interval.", [
         _INPUT, _arg("refseq_file", metavar="REFERENCE"), _arg("intervals", metavar="REGIONS"), _k(4), _minlen(50),
         _maxlen(None), _STRAND, _out("TSV or CSV of end-motif frequencies."), _mapq(20), _THREADS, _VERBOSE]),
+    "breakpoint-motifs": ("finaletoolkit_b200.frag", "breakpoint_motifs", "Genome-wide breakpoint-motif k-mer frequencies.", [
+        _INPUT, _arg("refseq_file", metavar="REFERENCE"), _k(6), _minlen(50), _maxlen(None), _STRAND,
+        _out("TSV of k-mer frequencies."), _mapq(20), _THREADS, _VERBOSE]),
+    "interval-breakpoint-motifs": ("finaletoolkit_b200.frag", "interval_breakpoint_motifs",
+                                   "Breakpoint-motif counts per BED interval.", [
+        _INPUT, _arg("refseq_file", metavar="REFERENCE"), _arg("intervals", metavar="REGIONS"), _k(6), _minlen(50),
+        _maxlen(None), _STRAND, _out("TSV or CSV of breakpoint-motif frequencies."), _mapq(20), _THREADS, _VERBOSE]),
     "mds": ("finaletoolkit_b200.frag._end_motifs", "_cli_mds", "Motif diversity score from k-mer frequencies.", [
         _arg("file_path", metavar="INPUT", required=False, default="-"), _SEP, _HEADER]),
     "regional-mds": ("finaletoolkit_b200.frag._end_motifs", "_cli_regional_mds", "Regional MDS for each region.", [

@@ -13,6 +13,12 @@
 // Membership is tabix overlap only - no length filter, no midpoint policy
 // (frag/_end_motifs.py:115-120).
 // Index order = itertools.product("ACGT") (utils/utils.py:388-410): A0 C1 G2 T3.
+// Breakpoint motifs (region_breakpoint_motifs, frag/_breakpoint_motifs.py:53-196) are the same
+// kernel with windows centred on the two breakpoints, h = k/2:
+//   fragment skipped when fs-h < 0 or fs+h >= contig_len (:125-133)
+//   forward k-mer : ref[fs-h, fs+h)            reverse : revcomp(ref[fe-h, fe+h))
+//   reverse window out of bounds -> that end is skipped (OutOfBoundsError is a ValueError, :186)
+//   odd k: every window has 2h != k bases -> "length discrepancy" -> nothing is ever counted
 // Roofline: HBM, 10 B per candidate fragment (start, stop, mapq, strand) + 2 x 2 B
 // of packed reference per end served from L2.
 #include "ftk_common.cuh"
@@ -56,7 +62,7 @@ __global__ void motif_ranges_kernel(const int32_t *__restrict__ frag_start, int6
     ranges[t] = lower_bound(frag_start, n_frag, key);
 }
 
-template <bool SMEM>
+template <bool SMEM, bool BREAKPOINT>
 __global__ void __launch_bounds__(kMotifThreads)
 end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
                  const uint8_t *__restrict__ frag_mapq, const uint8_t *__restrict__ frag_strand,
@@ -101,6 +107,23 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
         for (int u = 0; u < kMotifUnroll; ++u) {
             const int fs = fs_r[u], fe = fe_r[u];
             if (q_r[u] < min_mapq || !(fe > S && fs < E)) continue;
+            if (BREAKPOINT) {
+                const int h = k >> 1;
+                if (fs - h < 0 || (int64_t)fs + h >= contig_len) continue;   // too close to a contig end
+                if ((k & 1) != 0) continue;                                  // 2h != k: never counted
+                if (strand_mode == 0 || (strand_mode == 1 && sd_r[u])) {
+                    if (!has_n(nmask, fs - h, k)) bump(digit_reverse(window2(seq, fs - h, k), k));
+                }
+                if (strand_mode != 1) {
+                    const int64_t rs = (int64_t)fe - h;
+                    if (rs < 0 || (int64_t)fe + h > contig_len) continue;    // OutOfBoundsError -> skipped
+                    if (!has_n(nmask, rs, k)) {
+                        const uint32_t mask = (k >= 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
+                        bump((~window2(seq, rs, k)) & mask);
+                    }
+                }
+                continue;
+            }
             if (strand_mode == 1 && !sd_r[u]) continue;  // forward-only: '+' fragments only
             if (strand_mode != 2) {
                 if (fs < 0 || (int64_t)fs + k > contig_len) continue;  // ValueError -> `continue`
@@ -132,21 +155,21 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
 
 using namespace ftk;
 
-extern "C" int ftk_end_motif_hist_u64(const int32_t *frag_start, const int32_t *frag_stop,
-                                      const uint8_t *frag_mapq, const uint8_t *frag_strand,
-                                      int64_t n_frag, int32_t max_frag_len,
-                                      const uint32_t *seq_words, const uint32_t *nmask_words,
-                                      int64_t contig_len,
-                                      const int32_t *ivl_start, const int32_t *ivl_stop, int64_t n_ivl,
-                                      int32_t k, int32_t strand_mode, int32_t min_mapq,
-                                      int32_t pooled, int32_t splits,
-                                      int64_t *scratch, uint64_t *counts, int32_t *error_flag,
-                                      ftk_stream_t stream_) {
+template <bool BREAKPOINT>
+static int motif_hist_launch(const int32_t *frag_start, const int32_t *frag_stop,
+                             const uint8_t *frag_mapq, const uint8_t *frag_strand,
+                             int64_t n_frag, int32_t max_frag_len,
+                             const uint32_t *seq_words, const uint32_t *nmask_words, int64_t contig_len,
+                             const int32_t *ivl_start, const int32_t *ivl_stop, int64_t n_ivl,
+                             int32_t k, int32_t strand_mode, int32_t min_mapq,
+                             int32_t pooled, int32_t splits,
+                             int64_t *scratch, uint64_t *counts, int32_t *error_flag,
+                             ftk_stream_t stream_) {
     if (n_ivl == 0) return FTK_OK;
     if (n_frag < 0 || n_ivl < 0 || splits < 1 || k < 1 || k > 12) return FTK_E_INVALID;
     if (strand_mode < 0 || strand_mode > 2) return FTK_E_INVALID;
-    if (!seq_words || !nmask_words || !ivl_start || !ivl_stop || !scratch || !counts || !error_flag)
-        return FTK_E_INVALID;
+    if (!seq_words || !nmask_words || !ivl_start || !ivl_stop || !scratch || !counts) return FTK_E_INVALID;
+    if (!BREAKPOINT && !error_flag) return FTK_E_INVALID;
     if (n_frag > 0 && (!frag_start || !frag_stop)) return FTK_E_INVALID;
     if (n_ivl * (int64_t)splits > INT32_MAX) return FTK_E_RANGE;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -159,13 +182,42 @@ extern "C" int ftk_end_motif_hist_u64(const int32_t *frag_start, const int32_t *
     const unsigned grid = (unsigned)(n_ivl * splits);
     auto *c = reinterpret_cast<unsigned long long *>(counts);
     if ((1 << (2 * k)) <= kMotifSmemBins)
-        end_motif_kernel<true><<<grid, kMotifThreads, 0, stream>>>(
+        end_motif_kernel<true, BREAKPOINT><<<grid, kMotifThreads, 0, stream>>>(
             frag_start, frag_stop, frag_mapq, frag_strand, seq_words, nmask_words, contig_len,
             ivl_start, ivl_stop, scratch, k, strand_mode, min_mapq, pooled, splits, c, error_flag);
     else
-        end_motif_kernel<false><<<grid, kMotifThreads, 0, stream>>>(
+        end_motif_kernel<false, BREAKPOINT><<<grid, kMotifThreads, 0, stream>>>(
             frag_start, frag_stop, frag_mapq, frag_strand, seq_words, nmask_words, contig_len,
             ivl_start, ivl_stop, scratch, k, strand_mode, min_mapq, pooled, splits, c, error_flag);
     FTK_CHECK_LAUNCH("end_motif_kernel");
     return FTK_OK;
+}
+
+extern "C" int ftk_end_motif_hist_u64(const int32_t *frag_start, const int32_t *frag_stop,
+                                      const uint8_t *frag_mapq, const uint8_t *frag_strand,
+                                      int64_t n_frag, int32_t max_frag_len,
+                                      const uint32_t *seq_words, const uint32_t *nmask_words,
+                                      int64_t contig_len,
+                                      const int32_t *ivl_start, const int32_t *ivl_stop, int64_t n_ivl,
+                                      int32_t k, int32_t strand_mode, int32_t min_mapq,
+                                      int32_t pooled, int32_t splits,
+                                      int64_t *scratch, uint64_t *counts, int32_t *error_flag,
+                                      ftk_stream_t stream_) {
+    return motif_hist_launch<false>(frag_start, frag_stop, frag_mapq, frag_strand, n_frag, max_frag_len,
+                                    seq_words, nmask_words, contig_len, ivl_start, ivl_stop, n_ivl, k,
+                                    strand_mode, min_mapq, pooled, splits, scratch, counts, error_flag, stream_);
+}
+
+extern "C" int ftk_breakpoint_motif_hist_u64(const int32_t *frag_start, const int32_t *frag_stop,
+                                             const uint8_t *frag_mapq, const uint8_t *frag_strand,
+                                             int64_t n_frag, int32_t max_frag_len,
+                                             const uint32_t *seq_words, const uint32_t *nmask_words,
+                                             int64_t contig_len,
+                                             const int32_t *ivl_start, const int32_t *ivl_stop, int64_t n_ivl,
+                                             int32_t k, int32_t strand_mode, int32_t min_mapq,
+                                             int32_t pooled, int32_t splits,
+                                             int64_t *scratch, uint64_t *counts, ftk_stream_t stream_) {
+    return motif_hist_launch<true>(frag_start, frag_stop, frag_mapq, frag_strand, n_frag, max_frag_len,
+                                   seq_words, nmask_words, contig_len, ivl_start, ivl_stop, n_ivl, k,
+                                   strand_mode, min_mapq, pooled, splits, scratch, counts, nullptr, stream_);
 }

@@ -295,8 +295,11 @@ class PackedContig:
 
 
 def end_motif_hist(frags: ContigFragments, ref: PackedContig, ivl_start, ivl_stop, k=4,
-                   strand_mode=0, quality_threshold=20, pooled=False, counts=None):
-    """k-mer counts int64[rows, 4**k] (device); raises RuntimeError like the reference."""
+                   strand_mode=0, quality_threshold=20, pooled=False, counts=None, breakpoint=False):
+    """k-mer counts int64[rows, 4**k] (device); raises RuntimeError like the reference.
+
+    ``breakpoint=True`` counts k-mers centred on the breakpoints (frag/_breakpoint_motifs.py)
+    instead of 5' end motifs; that variant has no error path."""
     t = torch()
     dev = frags.device
     n_ivl = len(ivl_start)
@@ -310,6 +313,13 @@ def end_motif_hist(frags: ContigFragments, ref: PackedContig, ivl_start, ivl_sto
     err = t.zeros(1, dtype=t.int32, device=dev)
     fs, fe, mq = frags.ptrs()
     sd = 0 if frags.strand is None else frags.strand.data_ptr()
+    if breakpoint:
+        check(lib().ftk_breakpoint_motif_hist_u64(
+            fs, fe, mq, sd, frags.n, frags.max_len, ref.seq.data_ptr(), ref.nmask.data_ptr(), ref.length,
+            s_dev.data_ptr(), e_dev.data_ptr(), n_ivl, int(k), int(strand_mode), int(quality_threshold),
+            int(bool(pooled)), _splits_for(n_ivl, frags.n), scratch.data_ptr(), counts.data_ptr(),
+            _stream_ptr(dev)), "ftk_breakpoint_motif_hist_u64")
+        return counts[:rows]
     check(lib().ftk_end_motif_hist_u64(
         fs, fe, mq, sd, frags.n, frags.max_len, ref.seq.data_ptr(), ref.nmask.data_ptr(), ref.length,
         s_dev.data_ptr(), e_dev.data_ptr(), n_ivl, int(k), int(strand_mode), int(quality_threshold),

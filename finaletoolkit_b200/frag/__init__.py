@@ -7,8 +7,12 @@ from ._adjust_wps import adjust_wps
 from ._cleavage_profile import cleavage_profile, multi_cleavage_profile
 from ._end_motifs import (EndMotifFreqs, EndMotifsIntervals, region_end_motifs, end_motifs,
                           interval_end_motifs)
+from ._breakpoint_motifs import (BreakpointMotifFreqs, BreakpointMotifsIntervals, region_breakpoint_motifs,
+                                 breakpoint_motifs, interval_breakpoint_motifs)
 
 __all__ = ["frag_length", "frag_length_bins", "frag_length_intervals", "FragLengthStats", "coverage",
            "single_coverage", "CoverageResult", "wps", "multi_wps", "adjust_wps", "cleavage_profile",
            "multi_cleavage_profile", "EndMotifFreqs",
-           "EndMotifsIntervals", "region_end_motifs", "end_motifs", "interval_end_motifs"]
+           "EndMotifsIntervals", "region_end_motifs", "end_motifs", "interval_end_motifs", "BreakpointMotifFreqs",
+           "BreakpointMotifsIntervals", "region_breakpoint_motifs", "breakpoint_motifs",
+           "interval_breakpoint_motifs"]

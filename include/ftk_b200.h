@@ -169,6 +169,23 @@ int ftk_end_motif_hist_u64(const int32_t *frag_start_dev, const int32_t *frag_st
                            int64_t *scratch_dev, uint64_t *counts_dev, int32_t *error_flag_dev,
                            ftk_stream_t stream);
 
+/* Breakpoint motifs: the per-fragment loop of region_breakpoint_motifs,
+ * frag/_breakpoint_motifs.py:120-186 (k-mers centred on the two breakpoints, h = k/2:
+ * forward ref[fs-h, fs+h), reverse revcomp(ref[fe-h, fe+h))).  Same operands, layout,
+ * strand_mode and scratch as ftk_end_motif_hist_u64.  Fragments with fs-h < 0 or
+ * fs+h >= contig_len are skipped, an out-of-bounds reverse window skips that end only, and
+ * an odd k never counts anything (the reference's "length discrepancy" branch); there is no
+ * error path. */
+int ftk_breakpoint_motif_hist_u64(const int32_t *frag_start_dev, const int32_t *frag_stop_dev,
+                                  const uint8_t *frag_mapq_dev, const uint8_t *frag_strand_dev,
+                                  int64_t n_frag, int32_t max_frag_len,
+                                  const uint32_t *seq_words_dev, const uint32_t *nmask_words_dev,
+                                  int64_t contig_len,
+                                  const int32_t *ivl_start_dev, const int32_t *ivl_stop_dev,
+                                  int64_t n_ivl, int32_t k, int32_t strand_mode, int32_t min_mapq,
+                                  int32_t pooled, int32_t splits,
+                                  int64_t *scratch_dev, uint64_t *counts_dev, ftk_stream_t stream);
+
 /* ------------------------------------------------------------ adjust_wps
  * Replaces _local_filter/_running_stat (frag/_adjust_wps.py:25-45) and the
  * scipy.signal.savgol_filter call (frag/_adjust_wps.py:135-138) inside

@@ -253,6 +253,40 @@ int orc_region_end_motifs(const int32_t *fs, const int32_t *fe, const uint8_t *m
     return m.err;
 }
 
+/* region_breakpoint_motifs, frag/_breakpoint_motifs.py:120-186: k-mers centred on the breakpoints. */
+static void bkpt_cb(int64_t i, void *ctx) {
+    motif_t *m = (motif_t *)ctx;
+    int k = m->k, h = k / 2;
+    int64_t s = m->fs[i], e = m->fe[i];
+    if (s - h < 0 || s + h >= m->seq_len) return;            /* :125-133 too close to a contig end */
+    int do_fwd = (m->strand_mode == 0) || (m->strand_mode == 1 && m->strand[i]);   /* :135-138 */
+    int do_rev = (m->strand_mode == 0) || (m->strand_mode == 2);
+    if (do_fwd) {
+        if (2 * h != k) return;                              /* :145-152 len(kmer) != k -> continue */
+        int64_t idx = 0; int ok = 1;
+        for (int j = 0; j < k; ++j) { int c = base_code(m->seq[s - h + j]); if (c < 0) { ok = 0; break; } idx = idx * 4 + c; }
+        if (ok) m->counts[idx]++;
+    }
+    if (do_rev) {
+        if (e - h < 0 || e + h > m->seq_len || e - h > e + h) return;   /* OutOfBoundsError (ValueError) -> continue */
+        if (2 * h != k) return;
+        int64_t idx = 0; int ok = 1;
+        for (int j = 0; j < k; ++j) {
+            int c = base_code(m->seq[e + h - 1 - j]); if (c < 0) { ok = 0; break; } idx = idx * 4 + (3 - c);
+        }
+        if (ok) m->counts[idx]++;
+    }
+}
+
+int orc_region_breakpoint_motifs(const int32_t *fs, const int32_t *fe, const uint8_t *mapq, const uint8_t *strand,
+                                 int64_t n, int64_t max_frag_len, int64_t start, int64_t stop,
+                                 const char *seq, int64_t seq_len, int k, int strand_mode, int64_t q,
+                                 int64_t *counts) {
+    motif_t m = {fs, fe, strand, seq, seq_len, k, strand_mode, counts, 0};
+    frag_stream(fs, fe, mapq, n, max_frag_len, start, stop, ORC_NONE, ORC_NONE, 1, q, bkpt_cb, &m);
+    return 0;
+}
+
 /* ------------------------------------------------------- cleavage profile */
 /*
  * frag/_cleavage_profile.py:188-217 (cleavage_profile) with _coverage_and_ends (:33-90) restated

@@ -372,6 +372,8 @@ def motifs():
             # forward k-mer out of bounds at the contig end -> fragment skipped entirely
             # (reference frag/_end_motifs.py:135-136), even when stop > contig length
             st[9:12] = np.array([ln - 2, ln - 1, ln - 2]); sp[9:12] = np.array([ln, ln + 5, ln])
+            # breakpoint motifs: forward window in bounds, reverse window [stop-3, stop+3) past the contig end
+            st[12:15] = np.array([ln - 120, ln - 90, 3]); sp[12:15] = np.array([ln - 1, ln - 2, 150])
             order = np.argsort(st, kind="stable")
             st, sp, mq, fw = st[order], sp[order], mq[order], fw[order]
         codes, nm = synth_twobit(ln, idx, seed_base=9100, telomere=2_000, n_blocks=3, block_len=5_000)
@@ -426,6 +428,36 @@ def motifs():
                        mds_bed=open(mdsb).read()))
     m["interval_end_motifs"] = iv
     m["intervals"] = [list(x) for x in ivs]
+    # breakpoint motifs (frag/_breakpoint_motifs.py) on the same fragments / reference
+    reg = []
+    for j, (c, s, e, kw) in enumerate([
+            ("chrM1", 0, 1_000_000, dict()), ("chrM1", 1_000_000, 1_200_345, dict()),
+            ("chrM1", 1_190_000, 1_200_345, dict(k=4, quality_threshold=0)),
+            ("chrM1", 0, 3_000, dict(k=4, quality_threshold=0)),
+            ("chrM2", 0, 90_000, dict(both_strands=False)),
+            ("chrM2", 0, 90_000, dict(both_strands=False, negative_strand=True)),
+            ("chrM2", 10_000, 30_000, dict(k=3)), ("chrM2", 10_000, 30_000, dict(k=2, quality_threshold=30)),
+            ("chrM2", 500, 2500, dict(k=8))]):
+        d = F.region_breakpoint_motifs(tbx, c, s, e, tb_path, **kw)
+        arrays[f"bp_region_{j}"] = np.array(list(d.values()), np.int64)
+        reg.append(dict(contig=c, start=s, stop=e, kwargs=kw, key=f"bp_region_{j}"))
+    m["region_breakpoint_motifs"] = reg
+    gw = []
+    for j, kw in enumerate([dict(), dict(k=4, quality_threshold=0), dict(both_strands=False),
+                            dict(both_strands=False, negative_strand=True, k=2)]):
+        out = os.path.join(TMP, f"bm_{j}.tsv")
+        r = F.breakpoint_motifs(tbx, tb_path, output_file=out, workers=1, **kw)
+        arrays[f"bp_genome_freq_{j}"] = np.array(r.frequencies(), np.float64)
+        gw.append(dict(kwargs=kw, key=f"bp_genome_freq_{j}", mds=r.motif_diversity_score(), tsv=open(out).read()))
+    m["breakpoint_motifs"] = gw
+    iv = []
+    for j, kw in enumerate([dict(k=4), dict(k=2, quality_threshold=0, both_strands=False)]):
+        out = os.path.join(TMP, f"ibm_{j}.tsv")
+        r = F.interval_breakpoint_motifs(tbx, tb_path, [tuple(x) for x in ivs], output_file=out, workers=1, **kw)
+        arrays[f"bp_interval_counts_{j}"] = np.array([list(d.values()) for _, d in r.intervals], np.int64)
+        iv.append(dict(kwargs=kw, key=f"bp_interval_counts_{j}", tsv=open(out).read(),
+                       mds=[v for _, v in r.motif_diversity_score()]))
+    m["interval_breakpoint_motifs"] = iv
     np.savez_compressed(os.path.join(OUT, "motif.npz"), **arrays)
     manifest["motif"] = m
 

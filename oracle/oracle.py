@@ -62,6 +62,8 @@ def lib():
         L.orc_frag_lengths.argtypes = [i32p, i32p, u8p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int64, i32p, c_int64]
         L.orc_region_end_motifs.restype = c_int
         L.orc_region_end_motifs.argtypes = [i32p, i32p, u8p, u8p, c_int64, c_int64, c_int64, c_int64, c_char_p, c_int64, c_int, c_int, c_int64, i64p]
+        L.orc_region_breakpoint_motifs.restype = c_int
+        L.orc_region_breakpoint_motifs.argtypes = L.orc_region_end_motifs.argtypes
         L.orc_cleavage_interval.restype = c_int64
         L.orc_cleavage_interval.argtypes = [i32p, i32p, u8p, u8p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                             c_int64, c_int64, c_int64, c_int64, dp]
@@ -257,6 +259,19 @@ def region_end_motifs(fr: Frags, seq_ascii: bytes, start, stop, k=4, both_strand
                                       seq_ascii, len(seq_ascii), int(k), mode, int(quality_threshold), _p(counts, c_int64))
     if err:
         raise RuntimeError("Error querying sequence (reverse k-mer out of bounds)")
+    return counts
+
+
+def region_breakpoint_motifs(fr: Frags, seq_ascii: bytes, start, stop, k=6, both_strands=True,
+                             negative_strand=False, quality_threshold=30) -> np.ndarray:
+    """frag/_breakpoint_motifs.py:53-196 -> int64[4**k] in gen_kmers order."""
+    if both_strands and negative_strand:
+        raise ValueError("Cannot have both both_strands and negative_strand.")
+    mode = 0 if both_strands else (2 if negative_strand else 1)
+    counts = np.zeros(4 ** k, np.int64)
+    lib().orc_region_breakpoint_motifs(*fr._args()[:3], _p(fr.strand, c_uint8), fr.n, fr.max_len, int(start),
+                                       int(stop), seq_ascii, len(seq_ascii), int(k), mode, int(quality_threshold),
+                                       _p(counts, c_int64))
     return counts
 
 

@@ -197,6 +197,32 @@ def test_end_motifs(tmp_path, manifest, golden):
     emf.to_tsv(str(tmp_path / "rt.tsv")); assert open(tmp_path / "rt.tsv").read() == f["end_motifs_dif_tsv"]
 
 
+def test_breakpoint_motifs(tmp_path, manifest, golden):
+    """frag/_breakpoint_motifs.py public functions vs outputs of the reference itself."""
+    import finaletoolkit_b200 as F
+    g = golden("motif"); m = manifest["motif"]
+    sizes = dict(m["contigs"])
+    cols = {c: tuple(g[f"{c}_{k}"] for k in ("start", "stop", "mapq", "strand")) for c in sizes}
+    frag = write_frag_gz(tmp_path / "m.frag.gz", cols)
+    tb = write_2bit(tmp_path / "m.2bit", [(c, *golden_codes(g, c, n)) for c, n in sizes.items()])
+    for c in m["region_breakpoint_motifs"]:
+        d = F.region_breakpoint_motifs(frag, c["contig"], c["start"], c["stop"], tb, **c["kwargs"])
+        assert np.array_equal(np.array(list(d.values())), g[c["key"]]) and list(d) == F.gen_kmers(c["kwargs"].get("k", 6))
+    for j, c in enumerate(m["breakpoint_motifs"]):
+        out = str(tmp_path / f"bm{j}.tsv")
+        r = F.breakpoint_motifs(frag, tb, output_file=out, **c["kwargs"])
+        assert isinstance(r, F.BreakpointMotifFreqs) and np.array_equal(np.array(r.frequencies()), g[c["key"]])
+        assert r.motif_diversity_score() == c["mds"] and open(out).read() == c["tsv"]
+    for j, c in enumerate(m["interval_breakpoint_motifs"]):
+        out = str(tmp_path / f"ibm{j}.tsv")
+        r = F.interval_breakpoint_motifs(frag, tb, [tuple(x) for x in m["intervals"]], output_file=out, **c["kwargs"])
+        assert open(out).read() == c["tsv"]
+        got = [v for _, v in r.motif_diversity_score()]
+        assert all((a == b) or (np.isnan(a) and np.isnan(b)) for a, b in zip(got, c["mds"]))
+    with pytest.raises(ValueError):
+        F.region_breakpoint_motifs(frag, "chrM2", 0, 10, tb, negative_strand=True)
+
+
 def test_adjust_wps(fx, syn, manifest, golden, tmp_path):
     import finaletoolkit_b200 as F
     from finaletoolkit_b200.io import bigwig

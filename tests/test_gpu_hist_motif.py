@@ -155,6 +155,31 @@ def test_motifs_golden(manifest, golden, dev):
                           np.array([1, 0], np.uint8), device=dev)
     with pytest.raises(RuntimeError):
         D.end_motif_hist(bad, refs["chrM2"], [0], [1000])
+    # breakpoint motifs (frag/_breakpoint_motifs.py): same kernel, windows centred on the breakpoints
+    for c in m["region_breakpoint_motifs"]:
+        kw = c["kwargs"]
+        got = D.end_motif_hist(frs[c["contig"]], refs[c["contig"]], [c["start"]], [c["stop"]], k=kw.get("k", 6),
+                               strand_mode=mode(kw), quality_threshold=kw.get("quality_threshold", 30), breakpoint=True)
+        assert np.array_equal(got[0].cpu().numpy(), g[c["key"]]), c
+    for c in m["breakpoint_motifs"]:
+        kw = c["kwargs"]; k = kw.get("k", 6)
+        tot = None
+        for contig, n in sizes.items():
+            w = O.genome_windows(n)
+            tot = D.end_motif_hist(frs[contig], refs[contig], [a for a, _ in w], [b for _, b in w], k=k, strand_mode=mode(kw),
+                                   quality_threshold=kw.get("quality_threshold", 30), pooled=True, counts=tot, breakpoint=True)
+        cc = tot[0].cpu().numpy().astype(np.float64)
+        assert np.array_equal(cc / np.sum(cc), g[c["key"]])
+    for c in m["interval_breakpoint_motifs"]:
+        kw = c["kwargs"]; k = kw.get("k", 6)
+        ivs = m["intervals"]
+        rows = np.zeros((len(ivs), 4 ** k), np.int64)
+        for contig in sizes:
+            sel = [i for i, iv in enumerate(ivs) if iv[0] == contig]
+            got = D.end_motif_hist(frs[contig], refs[contig], [ivs[i][1] for i in sel], [ivs[i][2] for i in sel], k=k,
+                                   strand_mode=mode(kw), quality_threshold=kw.get("quality_threshold", 30), breakpoint=True)
+            rows[sel] = got.cpu().numpy()
+        assert np.array_equal(rows, g[c["key"]])
 
 
 @pytest.mark.parametrize("seed", range(4))
@@ -197,6 +222,16 @@ def test_random_counts_vs_oracle(seed, dev):
             exp = O.region_end_motifs(ofr2, seq.tobytes(), a, b, k, mode == 0, mode == 2, q)
             assert np.array_equal(got[j], exp), (k, mode, a, b)
             j += 1
+    # breakpoint variant: fragments ending past the contig are legal here (that end is skipped)
+    sp2 = sp.copy(); sp2[-3:] = clen + np.array([0, 1, 40])
+    ofr3 = O.Frags(st, sp2, mq, sd); dfr3 = ContigFragments(st, sp2, mq, sd, device=dev)
+    sel = [(a, b) for a, b in ivs if a is not None and b is not None]
+    for k, mode in [(6, 0), (2, 1), (4, 2), (5, 0), (8, 0)]:
+        got = D.end_motif_hist(dfr3, ref, [a for a, _ in sel], [b for _, b in sel], k=k, strand_mode=mode,
+                               quality_threshold=q, breakpoint=True).cpu().numpy()
+        for j, (a, b) in enumerate(sel):
+            exp = O.region_breakpoint_motifs(ofr3, seq.tobytes(), a, b, k, mode == 0, mode == 2, q)
+            assert np.array_equal(got[j], exp), (k, mode, a, b)
 
 
 def test_fused_coverage_and_pooled_histogram(dev):

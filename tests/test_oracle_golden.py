@@ -203,6 +203,36 @@ def test_motifs(manifest, golden):
     assert f["regional_mds"][0][1] == pytest.approx(0.5844622669209985, rel=1e-6)
 
 
+def test_breakpoint_motifs(manifest, golden):
+    """oracle restatement of frag/_breakpoint_motifs.py vs outputs of the reference itself."""
+    g = golden("motif")
+    m = manifest["motif"]
+    sizes = dict(m["contigs"])
+    frs = {c: frags_of(g, c + "_") for c in sizes}
+    seqs = {c: _seq_ascii(g, c, n) for c, n in sizes.items()}
+    nonzero = 0
+    for c in m["region_breakpoint_motifs"]:
+        got = O.region_breakpoint_motifs(frs[c["contig"]], seqs[c["contig"]], c["start"], c["stop"], **c["kwargs"])
+        assert np.array_equal(got, g[c["key"]]), c
+        nonzero += int(got.sum() > 0)
+        if c["kwargs"].get("k", 6) % 2:          # odd k: the reference's length check rejects every window
+            assert got.sum() == 0
+    assert nonzero >= 6
+    for c in m["breakpoint_motifs"]:
+        kw = dict(c["kwargs"]); k = kw.get("k", 6)
+        tot = np.zeros(4 ** k, np.float64)
+        for contig, n in sizes.items():
+            for s, e in O.genome_windows(n):
+                tot = tot + O.region_breakpoint_motifs(frs[contig], seqs[contig], s, e, **kw)
+        freq = tot / np.sum(tot)
+        assert np.array_equal(freq, g[c["key"]])
+        assert O.mds(freq, k) == c["mds"]
+    for c in m["interval_breakpoint_motifs"]:
+        kw = dict(c["kwargs"])
+        rows = [O.region_breakpoint_motifs(frs[iv[0]], seqs[iv[0]], iv[1], iv[2], **kw) for iv in m["intervals"]]
+        assert np.array_equal(np.array(rows), g[c["key"]])
+
+
 def test_adjust_core(manifest, golden):
     g = golden("adjust")
     m = manifest["adjust"]
