@@ -10,7 +10,7 @@ from __future__ import annotations
 
 __version__ = "0.1.0"
 
-_SUBMODULES = ("cli", "frag", "io", "utils", "device", "synth", "exceptions", "sharding")
+_SUBMODULES = ("cli", "frag", "genome", "io", "utils", "device", "synth", "exceptions", "sharding")
 
 _EXPORTS = {
     "frag_length": ("frag", "frag_length"), "frag_length_bins": ("frag", "frag_length_bins"),
@@ -21,6 +21,8 @@ _EXPORTS = {
     "end_motifs": ("frag", "end_motifs"), "region_end_motifs": ("frag", "region_end_motifs"),
     "interval_end_motifs": ("frag", "interval_end_motifs"),
     "EndMotifFreqs": ("frag", "EndMotifFreqs"), "EndMotifsIntervals": ("frag", "EndMotifsIntervals"),
+    "delfi": ("frag", "delfi"), "delfi_gc_correct": ("frag", "delfi_gc_correct"),
+    "delfi_merge_bins": ("frag", "delfi_merge_bins"), "trim_coverage": ("frag", "trim_coverage"),
     "breakpoint_motifs": ("frag", "breakpoint_motifs"), "region_breakpoint_motifs": ("frag", "region_breakpoint_motifs"),
     "interval_breakpoint_motifs": ("frag", "interval_breakpoint_motifs"),
     "BreakpointMotifFreqs": ("frag", "BreakpointMotifFreqs"),

@@ -123,6 +123,20 @@ COMMANDS = {
     "interval-end-motifs": ("finaletoolkit_b200.frag", "interval_end_motifs", "End-motif counts per BED interval.", [
         _INPUT, _arg("refseq_file", metavar="REFERENCE"), _arg("intervals", metavar="REGIONS"), _k(4), _minlen(50),
         _maxlen(None), _STRAND, _out("TSV or CSV of end-motif frequencies."), _mapq(20), _THREADS, _VERBOSE]),
+    "delfi": ("finaletoolkit_b200.frag", "delfi", "DELFI short/long fragment counts, ratio and GC content per bin.", [
+        _INPUT, _arg("chrom_sizes", metavar="CHROM_SIZES"), _arg("reference_file", metavar="REFERENCE"),
+        _arg("bins_file", metavar="BINS"),
+        _opt("-b", "--blacklist", "blacklist_file", metavar="BED", help="BED file of regions to ignore."),
+        _opt("-g", "--gap-file", "gap_file", metavar="GAPS",
+             help="BED4 of telomere/centromere/short_arm annotations."),
+        _out("Output file (.bed, .bed.gz, .tsv, or .csv)."),
+        _opt("--no-gc-correct", "no_gc_correct", is_flag=True, default=False, help="Skip GC correction."),
+        _opt("--remove-nocov/--no-remove-nocov", "remove_nocov", default=True,
+             help="Remove the two hg19 regions with no coverage."),
+        _opt("--merge-bins/--no-merge-bins", "merge_bins", default=True, help="Merge input bins to 5Mb."),
+        _opt("--merge-size", "window_size", metavar="BP", default=5000000, show_default=True, type=int,
+             help="Target size of merged genomic intervals."),
+        _mapq(30), _THREADS, _VERBOSE]),
     "breakpoint-motifs": ("finaletoolkit_b200.frag", "breakpoint_motifs", "Genome-wide breakpoint-motif k-mer frequencies.", [
         _INPUT, _arg("refseq_file", metavar="REFERENCE"), _k(6), _minlen(50), _maxlen(None), _STRAND,
         _out("TSV of k-mer frequencies."), _mapq(20), _THREADS, _VERBOSE]),

@@ -12,7 +12,7 @@ import numpy as np
 from ._lib import FTK_NONE, FtkLibraryError, check, lib
 
 __all__ = ["ContigFragments", "WpsPlan", "IntervalSet", "PackedContig", "interval_hist", "frag_lengths",
-           "end_motif_hist", "require_cuda", "none_to_ftk", "policy_code"]
+           "end_motif_hist", "delfi_windows", "blacklist_in_windows", "require_cuda", "none_to_ftk", "policy_code"]
 
 _torch = None
 
@@ -330,6 +330,69 @@ def end_motif_hist(frags: ContigFragments, ref: PackedContig, ivl_start, ivl_sto
             "Error querying sequence: reverse k-mer window out of contig bounds. Please verify "
             "that the reference file matches the fragment file.")
     return counts[:rows]
+
+
+def blacklist_in_windows(bl_start, bl_stop, win_start, win_stop):
+    """Blacklist regions contained in each window (frag/_delfi.py:110-127), as CSR (host).
+
+    ``bl_start``/``bl_stop``: the contig's regions sorted by (start, stop).  A region belongs to a
+    window when ``start >= window_start`` and ``stop <= window_stop``.  Returns
+    ``(off int32[n_win+1], starts int32, stops int32)``."""
+    bs = np.asarray(bl_start, dtype=np.int64); be = np.asarray(bl_stop, dtype=np.int64)
+    ws = np.asarray(win_start, dtype=np.int64); we = np.asarray(win_stop, dtype=np.int64)
+    off = np.zeros(len(ws) + 1, dtype=np.int64)
+    rs, re = [], []
+    if bs.size:
+        lo = np.searchsorted(bs, ws, side="left")
+        # a contained region starts before the window stops: bound the scan with a second search
+        hi = np.searchsorted(bs, we, side="right")
+        for w in range(len(ws)):
+            a, b = int(lo[w]), int(hi[w])
+            if b > a:
+                keep = be[a:b] <= we[w]
+                if keep.any():
+                    rs.append(bs[a:b][keep]); re.append(be[a:b][keep])
+                    off[w + 1] = int(keep.sum())
+    np.cumsum(off, out=off)
+    cat = (lambda x: np.concatenate(x) if x else np.zeros(0, np.int64))
+    return off.astype(np.int32), cat(rs).astype(np.int32), cat(re).astype(np.int32)
+
+
+def delfi_windows(frags: ContigFragments, ref: PackedContig | None, win_start, win_stop, blacklist=None,
+                  gaps=None, quality_threshold=30):
+    """DELFI bin counts of one contig: int64[n_win, 4] = short, long, num_frags, G+C bases (device).
+
+    ``blacklist`` = (starts, stops) of the contig sorted by (start, stop); ``gaps`` = (centromere
+    (start, stop), [telomere (start, stop), ...]) or None (frag/_delfi.py:404-511)."""
+    t = torch()
+    dev = frags.device
+    n_win = len(win_start)
+    counts = t.zeros((max(n_win, 1), 4), dtype=t.int64, device=dev)
+    if n_win == 0:
+        return counts[:0]
+    s_dev, e_dev = _ivl_to_device(win_start, win_stop, dev)
+    scratch = t.empty(2 * n_win, dtype=t.int64, device=dev)
+    fs, fe, mq = frags.ptrs()
+    bl = (0, 0, 0)
+    keep = []
+    if blacklist is not None and len(blacklist[0]):
+        off, rs, re = blacklist_in_windows(blacklist[0], blacklist[1], win_start, win_stop)
+        if rs.size:
+            keep = [_to_device(off, dev, np.int32), _to_device(rs, dev, np.int32), _to_device(re, dev, np.int32)]
+            bl = tuple(x.data_ptr() for x in keep)
+    g5 = None
+    if gaps is not None:
+        (c0, c1), telomeres = gaps[0], list(gaps[1])
+        lim = 2 ** 31 - 1
+        g5 = np.array([c0, c1, len(telomeres), max((a for a, _ in telomeres), default=0),
+                       min((b for _, b in telomeres), default=0)], dtype=np.int64).clip(-lim, lim).astype(np.int32)
+    check(lib().ftk_delfi_windows_u64(
+        fs, fe, mq, frags.n, frags.max_len, 0 if ref is None else ref.seq.data_ptr(),
+        0 if ref is None else ref.nmask.data_ptr(), 0 if ref is None else ref.length,
+        s_dev.data_ptr(), e_dev.data_ptr(), n_win, *bl, None if g5 is None else _np_ptr(g5, c_int32),
+        int(quality_threshold), _splits_for(n_win, frags.n), scratch.data_ptr(), counts.data_ptr(),
+        _stream_ptr(dev)), "ftk_delfi_windows_u64")
+    return counts
 
 
 _ADJ_SLOTS = 148 * 3 * 128

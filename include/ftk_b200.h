@@ -186,6 +186,29 @@ int ftk_breakpoint_motif_hist_u64(const int32_t *frag_start_dev, const int32_t *
                                   int32_t pooled, int32_t splits,
                                   int64_t *scratch_dev, uint64_t *counts_dev, ftk_stream_t stream);
 
+/* ----------------------------------------------------------- DELFI windows
+ * Replaces the per-fragment loop + GC count of _delfi_single_window, frag/_delfi.py:404-511 (run
+ * once per 100 kb bin by the Pool at frag/_delfi.py:283-294) for all bins of one contig.
+ * counts_dev: uint64[n_win][4] = {short (100..150), long (151..220), num_frags, G+C bases};
+ * columns 0-2 are accumulated (zero them first), column 3 is written (only when seq_words_dev
+ * is given; bins that are not valid reference intervals get 0, :472-482).
+ * Fragment filter: tabix overlap with the bin, mapq >= min_mapq, 100 <= L <= 220, midpoint in the
+ * bin, not inside a blacklist region, not in_tcmere (genome/gaps.py:226-248).
+ * Blacklist: bl_off_dev int32[n_win+1] indexes bl_start_dev/bl_stop_dev, the regions contained in
+ * each bin (frag/_delfi.py:110-127); NULL = no blacklist.
+ * gaps5_host (HOST pointer, or NULL = no gap track for the contig): {centromere start, centromere
+ * stop, n_telomeres, max telomere start, min telomere stop}.
+ * seq/nmask layout as for ftk_end_motif_hist_u64.  scratch_dev: int64[2*n_win]. */
+int ftk_delfi_windows_u64(const int32_t *frag_start_dev, const int32_t *frag_stop_dev,
+                          const uint8_t *frag_mapq_dev, int64_t n_frag, int32_t max_frag_len,
+                          const uint32_t *seq_words_dev, const uint32_t *nmask_words_dev,
+                          int64_t contig_len,
+                          const int32_t *win_start_dev, const int32_t *win_stop_dev, int64_t n_win,
+                          const int32_t *bl_off_dev, const int32_t *bl_start_dev,
+                          const int32_t *bl_stop_dev, const int32_t *gaps5_host,
+                          int32_t min_mapq, int32_t splits,
+                          int64_t *scratch_dev, uint64_t *counts_dev, ftk_stream_t stream);
+
 /* ------------------------------------------------------------ adjust_wps
  * Replaces _local_filter/_running_stat (frag/_adjust_wps.py:25-45) and the
  * scipy.signal.savgol_filter call (frag/_adjust_wps.py:135-138) inside

@@ -287,6 +287,67 @@ int orc_region_breakpoint_motifs(const int32_t *fs, const int32_t *fe, const uin
     return 0;
 }
 
+/* ------------------------------------------------------- DELFI window */
+/*
+ * frag/_delfi.py:404-511 (_delfi_single_window), the counting part: short / long / num_frags of one
+ * bin and the number of G + C bases of the bin.  The NOARM test and NaN conventions are in oracle.py.
+ *   bl_start/bl_stop : ALL blacklist regions of the contig sorted by (start, stop) (:85-107)
+ *   telo             : n_telo (start, stop) pairs; gaps_use = 0 when the contig has no ContigGaps
+ * out[4] = {short, long, num_frags, num_gc}
+ */
+typedef struct {
+    const int32_t *fs, *fe; int64_t ws, we;
+    const int64_t *r0, *r1; int64_t n_r;            /* blacklist regions contained in the bin */
+    int gaps_use; int64_t c0, c1; const int64_t *telo; int64_t n_telo;
+    int64_t n_short, n_long;
+} delfi_t;
+
+static void delfi_cb(int64_t i, void *ctx) {
+    delfi_t *d = (delfi_t *)ctx;
+    int64_t s = d->fs[i], e = d->fe[i], len = e - s;
+    if (len < 100 || len > 220) return;                                   /* :442-443 */
+    int64_t mid = (s + e) / 2;                                            /* s, e >= 0 */
+    if (mid < d->ws || mid >= d->we) return;                              /* :445-447 */
+    int blacklisted = 0;
+    for (int64_t j = 0; j < d->n_r; ++j)                                  /* :449-457 */
+        if (s >= d->r0[j] && s < d->r1[j] && e >= d->r0[j] && e < d->r1[j]) { blacklisted = 1; break; }
+    if (d->gaps_use) {                                                    /* genome/gaps.py:226-248 */
+        int in_c = e > d->c0 && s < d->c1;
+        int in_t = 0;
+        if (d->n_telo > 0) {
+            in_t = 1;
+            for (int64_t t = 0; t < d->n_telo; ++t)
+                if (!(e > d->telo[2 * t] && s < d->telo[2 * t + 1])) { in_t = 0; break; }   /* all() */
+        }
+        if (in_c || in_t) return;                                         /* :459-460 */
+    }
+    if (blacklisted) return;
+    if (len >= 151) d->n_long++; else d->n_short++;                       /* :462-467 */
+}
+
+void orc_delfi_window(const int32_t *fs, const int32_t *fe, const uint8_t *mapq, int64_t n, int64_t max_frag_len,
+                      int64_t ws, int64_t we, const int64_t *bl_start, const int64_t *bl_stop, int64_t n_bl,
+                      int gaps_use, int64_t c0, int64_t c1, const int64_t *telo, int64_t n_telo, int64_t q,
+                      const char *seq, int64_t seq_len, int64_t *out) {
+    /* _blacklist_in_window (:110-127): start >= ws by binary search, then stop <= we */
+    int64_t lo = 0, hi = n_bl;
+    while (lo < hi) { int64_t m = (lo + hi) / 2; if (bl_start[m] < ws) lo = m + 1; else hi = m; }
+    int64_t cap = n_bl - lo, n_r = 0;
+    int64_t *r0 = (int64_t *)malloc((size_t)(cap > 0 ? cap : 1) * sizeof(int64_t));
+    int64_t *r1 = (int64_t *)malloc((size_t)(cap > 0 ? cap : 1) * sizeof(int64_t));
+    for (int64_t j = lo; j < n_bl; ++j)
+        if (bl_stop[j] <= we) { r0[n_r] = bl_start[j]; r1[n_r] = bl_stop[j]; n_r++; }
+    delfi_t d = {fs, fe, ws, we, r0, r1, n_r, gaps_use, c0, c1, telo, n_telo, 0, 0};
+    /* AlignmentWrapper.fetch(contig, ws, we): tabix overlap + mapq only */
+    frag_stream(fs, fe, mapq, n, max_frag_len, ws, we, ORC_NONE, ORC_NONE, 1, q, delfi_cb, &d);
+    free(r0); free(r1);
+    int64_t gc = 0;
+    /* valid_interval (utils/validation.py:146-166), else ref_bases = "" (:472-482) */
+    if (seq && ws >= 0 && ws < seq_len && we >= 0 && we <= seq_len)
+        for (int64_t p = ws; p < we; ++p) gc += (seq[p] == 'G' || seq[p] == 'C');
+    out[0] = d.n_short; out[1] = d.n_long; out[2] = d.n_short + d.n_long; out[3] = gc;
+}
+
 /* ------------------------------------------------------- cleavage profile */
 /*
  * frag/_cleavage_profile.py:188-217 (cleavage_profile) with _coverage_and_ends (:33-90) restated

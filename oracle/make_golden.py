@@ -13,7 +13,7 @@ produced it are stored next to it so the GPU box (which has no
 /root/reference) can replay them through the CUDA path and the oracle.
 
 Outputs: tests/golden/fixture17.npz, synth_small.npz, motif.npz, adjust.npz,
-manifest.json.
+cleavage.npz, delfi.npz, manifest.json.
 """
 from __future__ import annotations
 
@@ -570,12 +570,107 @@ def cleavage(tbx, cols, cs_path):
     manifest["cleavage"] = m
 
 
+# ----------------------------------------------------------------------------
+# F. DELFI bin counts + GC content (frag/_delfi.py): _delfi_single_window per bin and the delfi()
+#    table without LOESS (the `loess` package is not installable here)
+# ----------------------------------------------------------------------------
+def delfi_golden():
+    import finaletoolkit.frag._delfi as DL
+    from finaletoolkit.genome.gaps import GenomeGaps
+    arrays, m = {}, {}
+    contigs = [("chr7", 1_300_000, 60_000), ("chr21", 120_000, 8_000), ("chrX9", 64_000, 3_000)]
+    cols, seqs = {}, []
+    for idx, (name, ln, n) in enumerate(contigs):
+        st, sp, mq, fw = synth_fragments(ln, n, idx, seed_base=12_000)
+        codes, nm = synth_twobit(ln, idx, seed_base=12_100, telomere=1_500, n_blocks=2, block_len=3_000)
+        if n:
+            cols[name] = (st, sp, mq, fw)
+        seqs.append((name, codes, nm))
+        for k, v in zip(("start", "stop", "mapq", "strand"), (st, sp, mq, fw)):
+            arrays[f"{name}_{k}"] = v
+        arrays[f"{name}_codes_packed"] = np.packbits(np.unpackbits(codes[:, None], axis=1)[:, 6:].reshape(-1))
+        arrays[f"{name}_nmask_packed"] = np.packbits(nm)
+    tb_path = os.path.join(TMP, "delfi.2bit")
+    write_2bit(tb_path, seqs)
+    tbx = pysam.TabixFile.from_columns(cols)
+    cs_path = os.path.join(TMP, "delfi.chrom.sizes")
+    # chrom.sizes order != bins order; chrNoBins has no bins; chrX9 has no gap annotation
+    cs_txt = "chr21\t120000\nchr7\t1300000\nchrX9\t64000\nchrEmpty\t30000\nchrNoBins\t5000\n"
+    open(cs_path, "w").write(cs_txt)
+    gap_txt = ("chr7\t0\t10000\ttelomere\nchr7\t1290000\t1300000\ttelomere\nchr7\t600000\t640000\tcentromere\n"
+               "chr21\t0\t2000\ttelomere\nchr21\t50000\t56000\tcentromere\nchr21\t2000\t40000\tshort_arm\n"
+               "chrEmpty\t10000\t12000\tcentromere\n")   # contig without bins
+    gap_path = os.path.join(TMP, "delfi.gaps.bed")
+    open(gap_path, "w").write(gap_txt)
+    # blacklist: contained / straddling a bin edge / overlapping pair / tiny / on a contig without gaps
+    bl_txt = ("chr7\t101000\t103500\nchr7\t104900\t105300\nchr7\t102000\t102900\nchr7\t700100\t700400\tname\n"
+              "chr7\t20000\t25000\nchr7\t900000\t900150\n\nbadline\nchr21\t60000\t64000\nchrX9\t1000\t3000\n"
+              "chrX9\t2000\t2600\nchr7\t45000\t50000\n")
+    bl_path = os.path.join(TMP, "delfi.blacklist.bed")
+    open(bl_path, "w").write(bl_txt)
+    bins = []
+    for a in range(0, 1_300_000, 5_000):
+        bins.append(("chr7", a, a + 5_000))
+    for a in range(0, 120_000, 2_000):
+        bins.append(("chr21", a, a + 2_000))
+    bins.append(("chr21", 118_500, 121_000))          # past the contig end: GC skipped (invalid interval)
+    for a in range(0, 64_000, 4_000):
+        bins.append(("chrX9", a, a + 4_000))
+    bins.append(("chrX9", 500, 3500))                 # overlapping bin, blacklist region contained
+    bins_txt = "#comment line\n" + "".join(f"{c}\t{a}\t{b}\n" for c, a, b in bins)
+    bins_path = os.path.join(TMP, "delfi.bins.bed")
+    open(bins_path, "w").write(bins_txt)
+    m.update(contigs=[[c, l] for c, l, _ in contigs], chrom_sizes=cs_txt, gaps=gap_txt, blacklist=bl_txt, bins=bins_txt)
+
+    # per-bin tuples straight from _delfi_single_window (all bins, no gap-overlap prefilter)
+    gaps = GenomeGaps(gap_path)
+    singles = []
+    for q in (30, 0):
+        DL._delfi_pool_initializer(tbx, tb_path, q, DL._load_blacklist_indexed(bl_path),
+                                   {c: gaps.get_contig_gaps(c) for c, _, _ in contigs})
+        rows = [DL._delfi_single_window(c, a, b) for c, a, b in bins]
+        key = f"single_q{q}"
+        arrays[key + "_short"] = np.array([r[4] for r in rows], np.float64)
+        arrays[key + "_long"] = np.array([r[5] for r in rows], np.float64)
+        arrays[key + "_gc"] = np.array([r[6] for r in rows], np.float64)
+        arrays[key + "_num"] = np.array([r[7] for r in rows], np.int64)
+        singles.append(dict(quality_threshold=q, key=key, arms=[r[3] for r in rows], use_gaps=True, use_blacklist=True))
+    DL._delfi_pool_initializer(tbx, tb_path, 30, {}, None)
+    rows = [DL._delfi_single_window(c, a, b) for c, a, b in bins]
+    key = "single_plain"
+    arrays[key + "_short"] = np.array([r[4] for r in rows], np.float64)
+    arrays[key + "_long"] = np.array([r[5] for r in rows], np.float64)
+    arrays[key + "_gc"] = np.array([r[6] for r in rows], np.float64)
+    arrays[key + "_num"] = np.array([r[7] for r in rows], np.int64)
+    singles.append(dict(quality_threshold=30, key=key, arms=[r[3] for r in rows], use_gaps=False, use_blacklist=False))
+    m["single_window"] = singles
+    m["bins_list"] = [list(b) for b in bins]
+
+    # the delfi() table (no LOESS)
+    tables = []
+    for j, kw in enumerate([dict(gap_file=gap_path, blacklist_file=bl_path, merge_bins=False, remove_nocov=False),
+                            dict(gap_file=gap_path, blacklist_file=bl_path, merge_bins=True),
+                            dict(merge_bins=False, quality_threshold=0),
+                            dict(gap_file=gap_path, merge_bins=True, remove_nocov=False, quality_threshold=0)]):
+        out = os.path.join(TMP, f"delfi_{j}.tsv")
+        df = DL.delfi(tbx, cs_path, bins_path, tb_path, output_file=out, no_gc_correct=True, workers=1, **kw)
+        outc = os.path.join(TMP, f"delfi_{j}.csv")
+        DL._write_delfi(df, outc)
+        tables.append(dict(kwargs={k: (os.path.basename(v) if isinstance(v, str) else v) for k, v in kw.items()},
+                           tsv=open(out).read(), csv=open(outc).read(), columns=list(df.columns),
+                           dtypes=[str(t) for t in df.dtypes], n_rows=int(df.shape[0])))
+    m["delfi"] = tables
+    np.savez_compressed(os.path.join(OUT, "delfi.npz"), **arrays)
+    manifest["delfi"] = m
+
+
 if __name__ == "__main__":
     fixture17()
     tbx, cols, cs_path = synth_small()
     motifs()
     adjust(tbx, cols, cs_path)
     cleavage(tbx, cols, cs_path)
+    delfi_golden()
     with open(os.path.join(OUT, "manifest.json"), "w") as fh:
         json.dump(manifest, fh, indent=1, default=lambda o: o.item() if hasattr(o, "item") else str(o))
     for f in sorted(os.listdir(OUT)):

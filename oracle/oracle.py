@@ -62,6 +62,9 @@ def lib():
         L.orc_frag_lengths.argtypes = [i32p, i32p, u8p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int64, i32p, c_int64]
         L.orc_region_end_motifs.restype = c_int
         L.orc_region_end_motifs.argtypes = [i32p, i32p, u8p, u8p, c_int64, c_int64, c_int64, c_int64, c_char_p, c_int64, c_int, c_int, c_int64, i64p]
+        L.orc_delfi_window.restype = None
+        L.orc_delfi_window.argtypes = [i32p, i32p, u8p, c_int64, c_int64, c_int64, c_int64, i64p, i64p, c_int64,
+                                       c_int, c_int64, c_int64, i64p, c_int64, c_int64, c_char_p, c_int64, i64p]
         L.orc_region_breakpoint_motifs.restype = c_int
         L.orc_region_breakpoint_motifs.argtypes = L.orc_region_end_motifs.argtypes
         L.orc_cleavage_interval.restype = c_int64
@@ -291,6 +294,60 @@ def mds(freq, k: int, miller_madow=False, n=None) -> float:
             return float("nan")
         ent = ent + (int(np.count_nonzero(np.nan_to_num(freq))) - 1) / (2 * n)
     return float(ent / np.log(4 ** k))
+
+
+# ------------------------------------------------------------ DELFI windows
+def contig_arm(contig: str, gaps, start: int, stop: int) -> str:
+    """ContigGaps.get_arm, genome/gaps.py:250-268.  ``gaps`` = (centromere, telomeres, has_short_arm)."""
+    (c0, c1), _, has_short_arm = gaps
+    if stop < start:
+        raise ValueError("start must be less than stop")
+    if stop < c0:
+        return "NOARM" if has_short_arm else f"{contig.replace('chr', '')}p"
+    if start > c1:
+        return f"{contig.replace('chr', '')}q"
+    return "NOARM"
+
+
+def in_tcmere(gaps, start: int, stop: int) -> bool:
+    """ContigGaps.in_tcmere, genome/gaps.py:226-248 (``all`` over telomeres, like the reference)."""
+    (c0, c1), telomeres, _ = gaps
+    in_c = stop > c0 and start < c1
+    in_t = bool(telomeres) and all(stop > t0 and start < t1 for t0, t1 in telomeres)
+    return in_c or in_t
+
+
+def delfi_window(fr: Frags, seq_ascii, contig: str, start: int, stop: int, blacklist=None, gaps=None,
+                 quality_threshold=30):
+    """frag/_delfi.py:404-511 -> (contig, start, stop, arm, short, long, gc, num_frags).
+
+    ``blacklist`` = (starts, stops) of the contig sorted by (start, stop) (frag/_delfi.py:85-107);
+    ``gaps`` = (centromere (start, stop), [telomere (start, stop)...], has_short_arm) or None."""
+    if gaps is not None:
+        if in_tcmere(gaps, start, stop) or contig_arm(contig, gaps, start, stop) == "NOARM":
+            return (contig, start, stop, "NOARM", np.nan, np.nan, np.nan, 0)
+        arm = contig_arm(contig, gaps, start, stop)
+    else:
+        arm = contig
+    short, long_, num, gc = delfi_counts(fr, seq_ascii, start, stop, blacklist,
+                                         None if gaps is None else gaps[:2], quality_threshold)
+    gc_content = gc / (stop - start) if num > 0 else np.nan
+    return (contig, start, stop, arm, short, long_, gc_content, num)
+
+
+def delfi_counts(fr: Frags, seq_ascii, start: int, stop: int, blacklist=None, gaps=None, quality_threshold=30):
+    """(short, long, num_frags, G+C bases) of one bin - the loop of frag/_delfi.py:437-484.
+
+    ``gaps`` = (centromere (start, stop), [telomere (start, stop)...]) or None."""
+    bs = np.ascontiguousarray([] if blacklist is None else blacklist[0], np.int64)
+    be = np.ascontiguousarray([] if blacklist is None else blacklist[1], np.int64)
+    telo = np.ascontiguousarray([] if gaps is None else [x for t in gaps[1] for x in t], np.int64)
+    out = np.zeros(4, np.int64)
+    lib().orc_delfi_window(*fr._args()[:3], fr.n, fr.max_len, int(start), int(stop), _p(bs, c_int64), _p(be, c_int64),
+                           len(bs), int(gaps is not None), 0 if gaps is None else int(gaps[0][0]),
+                           0 if gaps is None else int(gaps[0][1]), _p(telo, c_int64), len(telo) // 2,
+                           int(quality_threshold), seq_ascii, 0 if seq_ascii is None else len(seq_ascii), _p(out, c_int64))
+    return tuple(int(x) for x in out)
 
 
 # --------------------------------------------------------- cleavage profile

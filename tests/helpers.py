@@ -76,3 +76,24 @@ def write_bgzf(path, text: str, block=30000):
             fh.write(payload + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
     open(str(path) + ".tbi", "wb").close()
     return str(path)
+
+
+def delfi_tracks(m):
+    """Blacklist and gap tracks of the DELFI golden, parsed the way the reference parses the files
+    (frag/_delfi.py:85-107; genome/gaps.py:54-62,170-182).
+
+    Returns ``(blacklist {contig: (starts, stops)}, gaps {contig: (centromere, telomeres, has_short_arm)})``."""
+    bl = {}
+    for line in m["blacklist"].splitlines():
+        p = line.split()
+        if len(p) >= 3:
+            bl.setdefault(p[0], []).append((int(p[1]), int(p[2])))
+    bl = {c: (np.array([a for a, _ in sorted(r)], np.int64), np.array([b for _, b in sorted(r)], np.int64)) for c, r in bl.items()}
+    rows = [ln.split() for ln in m["gaps"].splitlines() if ln.strip()]
+    gaps = {}
+    for c in {r[0] for r in rows}:
+        cen = [(int(r[1]), int(r[2])) for r in rows if r[0] == c and r[3] == "centromere"]
+        if cen:
+            gaps[c] = (cen[0], [(int(r[1]), int(r[2])) for r in rows if r[0] == c and r[3] == "telomere"],
+                       any(r[0] == c and r[3] == "short_arm" for r in rows))
+    return bl, gaps

@@ -233,6 +233,29 @@ def test_breakpoint_motifs(manifest, golden):
         assert np.array_equal(np.array(rows), g[c["key"]])
 
 
+def test_delfi_windows(manifest, golden):
+    """oracle restatement of _delfi_single_window (frag/_delfi.py:404-511) vs the reference's tuples."""
+    from helpers import delfi_tracks
+    g = golden("delfi"); m = manifest["delfi"]
+    sizes = dict(m["contigs"])
+    frs = {c: frags_of(g, c + "_") for c in sizes}
+    seqs = {c: _seq_ascii(g, c, n) for c, n in sizes.items()}
+    bl, gaps = delfi_tracks(m)
+    for case in m["single_window"]:
+        k = case["key"]
+        for j, (c, a, b) in enumerate(m["bins_list"]):
+            got = O.delfi_window(frs[c], seqs[c], c, a, b, blacklist=bl.get(c) if case["use_blacklist"] else None,
+                                 gaps=gaps.get(c) if case["use_gaps"] else None, quality_threshold=case["quality_threshold"])
+            exp = (c, a, b, case["arms"][j], g[k + "_short"][j], g[k + "_long"][j], g[k + "_gc"][j], g[k + "_num"][j])
+            assert got[:4] == exp[:4] and got[7] == exp[7], (k, c, a, b)
+            for x, y in zip(got[4:7], exp[4:7]):
+                assert (np.isnan(x) and np.isnan(y)) or x == y, (k, c, a, b, got, exp)
+    # the blacklist and the gap rule both removed fragments somewhere, and the invalid bin has gc 0
+    assert g["single_plain_num"].sum() > g["single_q30_num"].sum()
+    j = m["bins_list"].index(["chr21", 118500, 121000])
+    assert g["single_plain_gc"][j] == 0.0 and g["single_plain_num"][j] > 0
+
+
 def test_adjust_core(manifest, golden):
     g = golden("adjust")
     m = manifest["adjust"]
