@@ -208,6 +208,16 @@ def other_kernels(frags, raw_wps_f32, dev, peak):
     ws, we = [a for a, _ in win], [b for _, b in win]
     ms = timed(lambda: D.end_motif_hist(frags, ref, ws, we, k=4, strand_mode=0, quality_threshold=MAPQ, pooled=True))
     out["end_motifs(k=4,both strands)"] = row(ms, 10 * frags.n, frags.n, "fragments")
+    ms = timed(lambda: D.end_motif_hist(frags, ref, ws, we, k=6, strand_mode=0, quality_threshold=MAPQ, pooled=True,
+                                        breakpoint=True))
+    out["breakpoint_motifs(k=6,both strands)"] = row(ms, 10 * frags.n, frags.n, "fragments")
+    # DELFI: 100-kb bins, short/long counts + GC content (9 B/fragment + 0.375 B/base of packed reference)
+    bs = np.arange(0, CONTIG_LEN - 100_000, 100_000, dtype=np.int64); be = bs + 100_000
+    rng = np.random.default_rng(5)
+    r0 = np.sort(rng.integers(0, CONTIG_LEN - 20_000, 400)); blk = (r0, r0 + rng.integers(200, 20_000, 400))
+    gaps = ((121_500_000, 124_500_000), [(0, 10_000), (CONTIG_LEN - 10_000, CONTIG_LEN)])
+    ms = timed(lambda: D.delfi_windows(frags, ref, bs, be, blacklist=blk, gaps=gaps, quality_threshold=MAPQ))
+    out["delfi_windows(100kb bins)"] = row(ms, 9 * frags.n + (3 * CONTIG_LEN) // 8, frags.n, "fragments")
     return out
 
 

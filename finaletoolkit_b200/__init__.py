@@ -31,6 +31,7 @@ _EXPORTS = {
     "frags_in_region": ("utils", "frags_in_region"), "get_intervals": ("utils", "get_intervals"),
     "gen_kmers": ("utils", "gen_kmers"), "reverse_complement": ("utils", "reverse_complement"),
     "chrom_sizes_to_dict": ("utils", "chrom_sizes_to_dict"), "chrom_sizes_to_list": ("utils", "chrom_sizes_to_list"),
+    "agg_bw": ("utils", "agg_bw"),
     "ReferenceWrapper": ("io", "ReferenceWrapper"),
 }
 _ALIASES = {"end_motif": "end_motifs"}

@@ -49,6 +49,7 @@ SYMBOLS = {
                                               _P, _P, _P]),
     "ftk_delfi_windows_u64": (c_int, [_P, _P, _P, c_int64, c_int32, _P, _P, c_int64, _P, _P, c_int64,
                                       _P, _P, _P, _i32p, c_int32, c_int32, _P, _P, _P]),
+    "ftk_agg_signal_f64": (c_int, [_P, c_int64, c_int64, c_int32, c_int32, _P, _P, _P]),
     "ftk_adjust_edge_shift_f64": (c_int, [_P, _P, c_int32, c_int32, _P, _P]),
     "ftk_adjust_wps_f64": (c_int, [_P, _P, _P, _P, _P, c_int32, c_int64, c_int32, c_int32, c_int32, _P, _P, _P]),
     "ftk_adjust_wps_generic_f64": (c_int, [_P, _P, _P, _P, _P, c_int32, _P, c_int64, c_int32, c_int32, c_int32,

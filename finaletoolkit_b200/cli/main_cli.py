@@ -137,6 +137,12 @@ COMMANDS = {
         _opt("--merge-size", "window_size", metavar="BP", default=5000000, show_default=True, type=int,
              help="Target size of merged genomic intervals."),
         _mapq(30), _THREADS, _VERBOSE]),
+    "agg-bw": ("finaletoolkit_b200.utils", "agg_bw", "Strand-aware aggregate of a bigWig signal over BED6 intervals.", [
+        _arg("input_file", metavar="INPUT"), _arg("interval_file", metavar="REGIONS"),
+        _out("Wiggle file of the aggregate signal over the input intervals."),
+        _opt("-m", "--median-window-size", "median_window_size", metavar="BP", default=1, show_default=True, type=int,
+             help="Median filter window used upstream (120 replicates Snyder et al.)."),
+        _opt("--mean", "mean", is_flag=True, help="Mean instead of sum."), _VERBOSE]),
     "breakpoint-motifs": ("finaletoolkit_b200.frag", "breakpoint_motifs", "Genome-wide breakpoint-motif k-mer frequencies.", [
         _INPUT, _arg("refseq_file", metavar="REFERENCE"), _k(6), _minlen(50), _maxlen(None), _STRAND,
         _out("TSV of k-mer frequencies."), _mapq(20), _THREADS, _VERBOSE]),

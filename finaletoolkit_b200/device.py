@@ -12,7 +12,7 @@ import numpy as np
 from ._lib import FTK_NONE, FtkLibraryError, check, lib
 
 __all__ = ["ContigFragments", "WpsPlan", "IntervalSet", "PackedContig", "interval_hist", "frag_lengths",
-           "end_motif_hist", "delfi_windows", "blacklist_in_windows", "require_cuda", "none_to_ftk", "policy_code"]
+           "end_motif_hist", "delfi_windows", "blacklist_in_windows", "agg_signal", "require_cuda", "none_to_ftk", "policy_code"]
 
 _torch = None
 
@@ -203,6 +203,11 @@ def _splits_for(n_ivl: int, n_frag: int) -> int:
 
 
 def _ivl_to_device(ivl_start, ivl_stop, device):
+    if isinstance(ivl_start, np.ndarray) and isinstance(ivl_stop, np.ndarray) and ivl_start.dtype.kind in "iu" \
+            and ivl_stop.dtype.kind in "iu":
+        lim = 2 ** 31 - 1
+        return (_to_device(np.clip(ivl_start, -lim, lim), device, np.int32),
+                _to_device(np.clip(ivl_stop, -lim, lim), device, np.int32))
     s = np.array([FTK_NONE if v is None else int(v) for v in ivl_start], dtype=np.int64)
     e = np.array([FTK_NONE if v is None else int(v) for v in ivl_stop], dtype=np.int64)
     lim = 2 ** 31 - 1
@@ -341,21 +346,17 @@ def blacklist_in_windows(bl_start, bl_stop, win_start, win_stop):
     bs = np.asarray(bl_start, dtype=np.int64); be = np.asarray(bl_stop, dtype=np.int64)
     ws = np.asarray(win_start, dtype=np.int64); we = np.asarray(win_stop, dtype=np.int64)
     off = np.zeros(len(ws) + 1, dtype=np.int64)
-    rs, re = [], []
-    if bs.size:
-        lo = np.searchsorted(bs, ws, side="left")
-        # a contained region starts before the window stops: bound the scan with a second search
-        hi = np.searchsorted(bs, we, side="right")
-        for w in range(len(ws)):
-            a, b = int(lo[w]), int(hi[w])
-            if b > a:
-                keep = be[a:b] <= we[w]
-                if keep.any():
-                    rs.append(bs[a:b][keep]); re.append(be[a:b][keep])
-                    off[w + 1] = int(keep.sum())
-    np.cumsum(off, out=off)
-    cat = (lambda x: np.concatenate(x) if x else np.zeros(0, np.int64))
-    return off.astype(np.int32), cat(rs).astype(np.int32), cat(re).astype(np.int32)
+    if not bs.size or not ws.size:
+        return off.astype(np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32)
+    lo = np.searchsorted(bs, ws, side="left")
+    # a contained region starts before the window stops: bound the scan with a second search
+    cnt = np.maximum(np.searchsorted(bs, we, side="right") - lo, 0)
+    win = np.repeat(np.arange(len(ws)), cnt)                          # candidate (window, region) pairs
+    reg = lo[win] + (np.arange(win.size) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+    keep = be[reg] <= we[win]
+    win, reg = win[keep], reg[keep]
+    np.cumsum(np.bincount(win, minlength=len(ws)), out=off[1:])
+    return off.astype(np.int32), bs[reg].astype(np.int32), be[reg].astype(np.int32)
 
 
 def delfi_windows(frags: ContigFragments, ref: PackedContig | None, win_start, win_stop, blacklist=None,
@@ -393,6 +394,22 @@ def delfi_windows(frags: ContigFragments, ref: PackedContig | None, win_start, w
         int(quality_threshold), _splits_for(n_win, frags.n), scratch.data_ptr(), counts.data_ptr(),
         _stream_ptr(dev)), "ftk_delfi_windows_u64")
     return counts
+
+
+def agg_signal(rows, strand, trim_lo: int, out_len: int, device=None):
+    """Strand-aware fp64 sum of equal-length signal rows (utils/_agg_bw.py:84-123) -> float64[out_len] (device).
+
+    ``rows``: float32 [n_seg, row_len] (numpy or CUDA tensor); ``strand``: int8 per row (+1, -1, 0 = skip)."""
+    t = torch()
+    dev = require_cuda(device)
+    x = rows if t.is_tensor(rows) else _to_device(np.ascontiguousarray(rows, np.float32), dev, np.float32)
+    x = x.to(dev, t.float32).contiguous()
+    sd = _to_device(np.ascontiguousarray(strand, np.int8), dev, np.int8)
+    n_seg, row_len = (int(x.shape[0]), int(x.shape[1])) if x.dim() == 2 else (0, 0)
+    out = t.zeros(int(out_len), dtype=t.float64, device=dev)
+    check(lib().ftk_agg_signal_f64(x.data_ptr(), n_seg, row_len, int(trim_lo), int(out_len), sd.data_ptr(),
+                                   out.data_ptr(), _stream_ptr(dev)), "ftk_agg_signal_f64")
+    return out
 
 
 _ADJ_SLOTS = 148 * 3 * 128

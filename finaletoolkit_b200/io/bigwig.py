@@ -428,13 +428,20 @@ class BigWigReader:
         return self._intervals_arrays(chrom, start, end)
 
     def values(self, chrom, start=0, end=0, numpy=True):
-        cid, size = self._chroms[chrom]
+        """pyBigWig.values: one float32 per base of [start, end), NaN where uncovered."""
+        if chrom not in self._chroms:
+            raise RuntimeError("Invalid interval bounds!")
+        size = self._chroms[chrom][1]
         end = size if end == 0 else end
+        r = self._intervals_arrays(chrom, start, end)      # validates the bounds like pyBigWig
         out = np.full(end - start, np.nan, dtype=np.float32)
-        r = self._intervals_arrays(chrom, start, end)
         if r is not None:
-            for s, e_, v in zip(*r):
-                out[max(s, start) - start: min(e_, end) - start] = v
+            s, e_, v = r
+            if np.all(e_ - s == 1):                          # per-base entries (WPS tracks)
+                out[s - start] = v
+            else:
+                for a, b, x in zip(s.tolist(), e_.tolist(), v.tolist()):
+                    out[max(a, start) - start: min(b, end) - start] = x
         return out if numpy else out.tolist()
 
     def close(self) -> None:

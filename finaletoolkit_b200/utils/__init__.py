@@ -2,5 +2,7 @@
 from .utils import (chrom_sizes_to_dict, chrom_sizes_to_list, frag_array, frag_generator, frags_in_region,
                     gen_kmers, get_intervals, reverse_complement, _none_eq, _none_geq, _none_leq)
 
-__all__ = ["chrom_sizes_to_dict", "chrom_sizes_to_list", "frag_array", "frag_generator", "frags_in_region",
+from ._agg_bw import agg_bw
+
+__all__ = ["agg_bw", "chrom_sizes_to_dict", "chrom_sizes_to_list", "frag_array", "frag_generator", "frags_in_region",
            "gen_kmers", "get_intervals", "reverse_complement", "_none_eq", "_none_geq", "_none_leq"]

@@ -209,6 +209,16 @@ int ftk_delfi_windows_u64(const int32_t *frag_start_dev, const int32_t *frag_sto
                           int32_t min_mapq, int32_t splits,
                           int64_t *scratch_dev, uint64_t *counts_dev, ftk_stream_t stream);
 
+/* ------------------------------------------------------------- agg_bw
+ * Replaces the accumulation loop of agg_bw, utils/_agg_bw.py:84-123.  signal_dev: float32
+ * [n_seg][row_len], one row per accepted interval (the bigWig values of [start, stop), NaN where
+ * uncovered); strand_dev: int8 per row, +1 = '+', -1 = '-' (row is flipped), 0 = skipped.
+ * out_dev[p] = sum over rows in order of row[trim_lo + p] ('+') or row[trim_lo + out_len-1-p] ('-'),
+ * NaN as 0, accumulated in fp64 in row order (bit-identical to the reference's running sum).
+ * trim_lo = median_window_size // 2, out_len = stop - start - median_window_size. */
+int ftk_agg_signal_f64(const float *signal_dev, int64_t n_seg, int64_t row_len, int32_t trim_lo,
+                       int32_t out_len, const int8_t *strand_dev, double *out_dev, ftk_stream_t stream);
+
 /* ------------------------------------------------------------ adjust_wps
  * Replaces _local_filter/_running_stat (frag/_adjust_wps.py:25-45) and the
  * scipy.signal.savgol_filter call (frag/_adjust_wps.py:135-138) inside

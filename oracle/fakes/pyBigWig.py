@@ -7,7 +7,8 @@ as libBigWig stores them.  Used only by ``oracle/make_golden.py``.
 Reference call sites: src/finaletoolkit/frag/_multi_wps.py:300-325 (writer,
 ``addEntries(chrom, start, values=, span=1, step=1)``),
 src/finaletoolkit/frag/_adjust_wps.py:80-105 (``intervals``) and :275-291
-(``addEntries(chroms, starts, ends=, values=)``).
+(``addEntries(chroms, starts, ends=, values=)``), src/finaletoolkit/utils/_agg_bw.py:89
+(``values``).
 """
 from __future__ import annotations
 
@@ -84,6 +85,25 @@ class _BW:
         return tuple(
             (int(a), int(b), float(v)) for a, b, v in zip(pos[m], stops[m], vals[m])
         )
+
+    def values(self, chrom, start=0, end=None, numpy=False):
+        # pyBigWig.c pyBwGetValues: same bounds rule; uncovered bases are nan; python floats
+        sizes = dict(self._f["header"] or [])
+        if chrom not in sizes:
+            raise RuntimeError("Invalid interval bounds!")
+        if end is None:
+            end = sizes[chrom]
+        if end <= start or end > sizes[chrom] or start < 0:
+            raise RuntimeError("Invalid interval bounds!")
+        out = np.full(end - start, np.nan, dtype=np.float32)
+        for pos, stops, vals in self._f["data"].get(chrom, []):
+            m = (stops > start) & (pos < end)
+            if np.all(stops[m] - pos[m] == 1):
+                out[pos[m] - start] = vals[m]
+                continue
+            for a, b, v in zip(pos[m].tolist(), stops[m].tolist(), vals[m].tolist()):
+                out[max(a, start) - start: min(b, end) - start] = v
+        return out if numpy else [float(x) for x in out]
 
     def close(self):
         pass

@@ -13,7 +13,7 @@ produced it are stored next to it so the GPU box (which has no
 /root/reference) can replay them through the CUDA path and the oracle.
 
 Outputs: tests/golden/fixture17.npz, synth_small.npz, motif.npz, adjust.npz,
-cleavage.npz, delfi.npz, manifest.json.
+cleavage.npz, delfi.npz, agg.npz, manifest.json.
 """
 from __future__ import annotations
 
@@ -664,6 +664,60 @@ def delfi_golden():
     manifest["delfi"] = m
 
 
+# ----------------------------------------------------------------------------
+# G. agg_bw (utils/_agg_bw.py): strand-aware aggregate of a bigWig over BED6 intervals -> WIG
+# ----------------------------------------------------------------------------
+def agg():
+    from finaletoolkit.utils._agg_bw import agg_bw
+    arrays, m = {}, {}
+    rng = np.random.default_rng(77)
+    sizes = [("chrA", 60_000), ("chrB", 9_000)]
+    # non-integer float32 signal (adjusted-WPS-like): the fp64 running sum is order dependent
+    sig = {"chrA": (rng.normal(0, 7, 50_000)).astype(np.float32), "chrB": rng.integers(-30, 9, 8_000).astype(np.float32)}
+    starts = {"chrA": 2_000, "chrB": 500}
+    path = os.path.join(TMP, "agg.bw")
+    bw = pyBigWig.open(path, "w")
+    bw.addHeader(sizes)
+    # chrA written in two runs with a 300-base hole (values() -> nan there)
+    bw.addEntries("chrA", 2_000, values=sig["chrA"][:20_000].astype(np.float64), span=1, step=1)
+    bw.addEntries("chrA", 22_300, values=sig["chrA"][20_300:].astype(np.float64), span=1, step=1)
+    bw.addEntries("chrB", 500, values=sig["chrB"].astype(np.float64), span=1, step=1)
+    bw.close()
+    arrays["chrA_signal"], arrays["chrB_signal"] = sig["chrA"], sig["chrB"]
+    m["sizes"] = [list(x) for x in sizes]
+    m["layout"] = [["chrA", 2_000, 0, 20_000], ["chrA", 22_300, 20_300, 50_000], ["chrB", 500, 0, 8_000]]  # contig, pos, lo, hi
+    rows = []
+    for i in range(40):
+        c = "chrA" if i % 4 else "chrB"
+        lim = 50_000 if c == "chrA" else 7_000
+        a = int(rng.integers(starts[c], starts[c] + lim - 2_000))
+        rows.append((c, a, a + 2_000, ".", "0", "+-."[int(rng.integers(0, 3)) if i % 7 else 2]))
+    rows[3] = ("chrA", 21_000, 23_000, ".", "0", "-")        # spans the hole
+    rows[5] = ("chrA", 59_000, 61_000, ".", "0", "+")        # past the contig end -> RuntimeError, skipped
+    rows[6] = ("chrA", 30_000, 31_999, ".", "0", "+")        # wrong size -> skipped
+    rows[8] = ("chrZ", 100, 2_100, ".", "0", "+")            # unknown contig -> skipped
+    rows[9] = ("chrA", 100, 2_100, ".", "0", "-")            # mostly uncovered
+    bed_txt = "".join("\t".join(str(x) for x in r) + "\n" for r in rows)
+    bed = os.path.join(TMP, "agg.bed")
+    open(bed, "w").write(bed_txt)
+    m["bed"] = bed_txt
+    cases = []
+    for j, kw in enumerate([dict(), dict(median_window_size=120), dict(median_window_size=121, mean=True),
+                            dict(median_window_size=0), dict(median_window_size=1000, mean=True)]):
+        out = os.path.join(TMP, f"agg_{j}.wig")
+        with redirect_stdout(io.StringIO()):
+            r = agg_bw(path, bed, out, **kw)
+        arrays[f"agg_{j}"] = np.asarray(r)
+        cases.append(dict(kwargs=kw, key=f"agg_{j}", dtype=str(np.asarray(r).dtype), wig=open(out).read()))
+    m["cases"] = cases
+    # the reference's own fixture (tests/data/test.bw, bw_test.bed) and known answers (tests/test_agg_bw.py:15-26)
+    arrays["ref_test_bw"] = np.frombuffer(open(os.path.join(DATA, "test.bw"), "rb").read(), np.uint8)
+    m["ref_bed"] = open(os.path.join(DATA, "bw_test.bed")).read()
+    m["ref_known"] = [dict(median_window_size=0, expect=[0., 0., 0., 0., 0.]), dict(median_window_size=2, expect=[1., 2., 3.])]
+    np.savez_compressed(os.path.join(OUT, "agg.npz"), **arrays)
+    manifest["agg"] = m
+
+
 if __name__ == "__main__":
     fixture17()
     tbx, cols, cs_path = synth_small()
@@ -671,6 +725,7 @@ if __name__ == "__main__":
     adjust(tbx, cols, cs_path)
     cleavage(tbx, cols, cs_path)
     delfi_golden()
+    agg()
     with open(os.path.join(OUT, "manifest.json"), "w") as fh:
         json.dump(manifest, fh, indent=1, default=lambda o: o.item() if hasattr(o, "item") else str(o))
     for f in sorted(os.listdir(OUT)):

@@ -350,6 +350,31 @@ def delfi_counts(fr: Frags, seq_ascii, start: int, stop: int, blacklist=None, ga
     return tuple(int(x) for x in out)
 
 
+# ------------------------------------------------------------------ agg_bw
+def agg_bw_core(signals, strands, median_window_size=1, mean=False):
+    """utils/_agg_bw.py:84-126: ``signals[i]`` = pyBigWig ``values`` of interval i (float32, NaN where
+    uncovered) or None when the query raised; ``strands[i]`` = BED column 6.  The first interval
+    defines the size.  Returns the aggregate exactly as the reference builds it (running sum)."""
+    first = next(len(v) for v in signals if v is not None) if signals[0] is None else len(signals[0])
+    interval_size = first - median_window_size
+    agg = np.zeros(interval_size, dtype=np.int64)
+    added = 0
+    for v, strand in zip(signals, strands):
+        if v is None:
+            continue
+        values = np.nan_to_num(np.array([float(x) for x in v]), nan=0)
+        trimmed = values[median_window_size // 2: -median_window_size // 2]
+        if trimmed.shape[0] != interval_size:
+            continue
+        if strand == "+":
+            agg = agg + trimmed; added += 1
+        elif strand == "-":
+            agg = agg + np.flip(trimmed); added += 1
+    if mean:
+        agg = agg / added
+    return agg
+
+
 # --------------------------------------------------------- cleavage profile
 def cleavage_profile(fr: Frags, chrom_size, start, stop, left=0, right=0, min_length=None, max_length=None,
                      quality_threshold=30):

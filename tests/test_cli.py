@@ -16,7 +16,7 @@ def test_help_and_kwarg_bijection():
     r = CliRunner().invoke(main_cli, ["--help"])
     assert r.exit_code == 0
     expected = {"wps", "cleavage-profile", "adjust-wps", "coverage", "frag-length-bins", "frag-length-intervals", "end-motifs",
-                "interval-end-motifs", "breakpoint-motifs", "interval-breakpoint-motifs", "delfi", "mds", "regional-mds"}
+                "interval-end-motifs", "breakpoint-motifs", "interval-breakpoint-motifs", "delfi", "agg-bw", "mds", "regional-mds"}
     assert set(COMMANDS) == expected
     for name, (module, func, _, spec) in COMMANDS.items():
         assert CliRunner().invoke(main_cli, [name, "--help"]).exit_code == 0

@@ -256,6 +256,20 @@ def test_delfi_windows(manifest, golden):
     assert g["single_plain_gc"][j] == 0.0 and g["single_plain_num"][j] > 0
 
 
+def test_agg_bw(manifest, golden):
+    """oracle restatement of agg_bw's accumulation (utils/_agg_bw.py:84-126) vs the reference's output."""
+    from helpers import agg_fixture
+    g = golden("agg"); m = manifest["agg"]
+    signals, strands, _ = agg_fixture(g, m)
+    assert sum(v is None for v in signals) == 2          # past-the-end and unknown-contig intervals
+    for c in m["cases"]:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            got = O.agg_bw_core(signals, strands, **c["kwargs"])
+        exp = g[c["key"]]
+        assert str(got.dtype) == c["dtype"] and got.shape == exp.shape
+        assert np.array_equal(got, exp, equal_nan=True), c["kwargs"]
+
+
 def test_adjust_core(manifest, golden):
     g = golden("adjust")
     m = manifest["adjust"]
