@@ -85,6 +85,55 @@ def test_random_vs_oracle(seed, dev):
         assert np.array_equal(gv, exp), (seed, W, lo, hi, q, s, e)
 
 
+@pytest.mark.parametrize("W,lo,hi", [(120, 120, 180), (16, 35, 80), (121, 121, 300), (59, 60, 450), (2, 2, 600),
+                                      (1, 1, 200), (250, 250, 600), (253, 253, 400), (120, 119, 180)])
+def test_window_and_length_grid_vs_oracle(W, lo, hi, dev):
+    """Even / odd / tiny / wide windows with lengths straddling both bounds (many L == W),
+    a pile-up on one start and fragments past the contig end."""
+    from finaletoolkit_b200.device import ContigFragments
+    from finaletoolkit_b200.synth import synth_fragments
+    rng = np.random.default_rng(W * 1000 + lo)
+    clen = 61_000
+    st, sp, mq, sd = synth_fragments(clen, 30_000, W, seed_base=31)
+    ln = rng.integers(max(lo - 3, 1), hi + 4, st.size)
+    ln[rng.random(st.size) < 0.2] = max(W, lo)
+    sp = (st + ln).astype(np.int32)
+    st[:3000] = st[0]; sp[:3000] = st[0] + ln[:3000]
+    st[-40:] = clen - 5; sp[-40:] = clen + ln[-40:]
+    order = np.argsort(st, kind="stable"); st, sp, mq, sd = st[order], sp[order], mq[order], sd[order]
+    ofr = O.Frags(st, sp, mq, sd); dfr = ContigFragments(st, sp, mq, sd, device=dev)
+    ivs = [(0, 5000), (5000, 10_000), (clen - 700, clen), (12_345, 12_346), (3, 5122)]
+    got = _run(dfr, ivs, clen, window_size=W, min_length=lo, max_length=hi, quality_threshold=30)
+    for (s, e), a in zip(ivs, got):
+        assert np.array_equal(a, O.wps_interval(ofr, s, e, clen, W, lo, hi, 30)), (W, lo, hi, s, e)
+
+
+def test_deep_pile_up_exact(dev):
+    """70 000 fragments starting on one base (|WPS| > 65535): int32 scores stay exact and the
+    range scratch is reusable with ``ranges_ready``."""
+    import torch
+    from finaletoolkit_b200.device import ContigFragments, WpsPlan
+    rng = np.random.default_rng(4)
+    clen, n = 20_000, 150_000
+    st = rng.integers(4_000, 9_000, n).astype(np.int32)
+    st[:70_000] = 6_000
+    st = np.sort(st)
+    sp = (st + rng.integers(120, 181, n)).astype(np.int32)
+    mq = np.full(n, 60, np.uint8)
+    ofr = O.Frags(st, sp, mq, np.ones(n, np.uint8)); dfr = ContigFragments(st, sp, mq, None, device=dev)
+    ivs = [(0, 5000), (5000, 10_000), (10_000, 15_000)]
+    got = _run(dfr, ivs, clen)
+    for (s, e), a in zip(ivs, got):
+        assert np.array_equal(a, O.wps_interval(ofr, s, e, clen)), (s, e)
+    assert min(int(a.min()) for a in got) < -65535
+    plan = WpsPlan([s for s, _ in ivs], [e for _, e in ivs], clen, 180, dev)
+    plan.ranges(dfr); torch.cuda.synchronize()
+    before = plan.scratch.clone()
+    out = plan.run(dfr, ranges_ready=True); torch.cuda.synchronize()
+    assert torch.equal(plan.scratch, before)
+    assert np.array_equal(out.cpu().numpy().astype(np.int64), np.concatenate(got))
+
+
 def test_no_mapq_column_and_empty(dev):
     from finaletoolkit_b200.device import ContigFragments
     st = np.array([100, 150, 150, 400], np.int32); sp = st + np.array([167, 121, 180, 130], np.int32)
