@@ -29,19 +29,15 @@ constexpr int kMotifThreads = 256;
 constexpr int kMotifSmemBins = 4096;  // k <= 6 privatised in shared memory
 constexpr int kMotifUnroll = 4;
 
-// 2k-bit window starting at base `pos` (base i at bits 2*(i%16) of word i/16).
-__device__ __forceinline__ uint32_t window2(const uint32_t *__restrict__ seq, int64_t pos, int k) {
-    const int64_t w = pos >> 4;
-    const int sh = (int)(pos & 15) * 2;
-    const unsigned long long v = ((unsigned long long)__ldg(seq + w + 1) << 32) | __ldg(seq + w);
-    const unsigned long long mask = (k >= 16) ? 0xffffffffull : ((1ull << (2 * k)) - 1ull);
-    return (uint32_t)((v >> sh) & mask);
+// 2k-bit window starting at base `pos` (base i at bits 2*(i%16) of word i/16): one funnel shift
+// over two consecutive words; k <= 12, so 24 bits at a shift <= 30 always fit.
+__device__ __forceinline__ uint32_t window2(const uint32_t *__restrict__ seq, int pos, uint32_t mask2k) {
+    const int w = pos >> 4;
+    return __funnelshift_r(__ldg(seq + w), __ldg(seq + w + 1), (pos & 15) * 2) & mask2k;
 }
-__device__ __forceinline__ bool has_n(const uint32_t *__restrict__ nmask, int64_t pos, int k) {
-    const int64_t w = pos >> 5;
-    const int sh = (int)(pos & 31);
-    const unsigned long long v = ((unsigned long long)__ldg(nmask + w + 1) << 32) | __ldg(nmask + w);
-    return ((v >> sh) & ((1ull << k) - 1ull)) != 0ull;
+__device__ __forceinline__ bool has_n(const uint32_t *__restrict__ nmask, int pos, uint32_t maskk) {
+    const int w = pos >> 5;
+    return (__funnelshift_r(__ldg(nmask + w), __ldg(nmask + w + 1), pos & 31) & maskk) != 0u;
 }
 // reverse the order of the k 2-bit digits of x (first base becomes the most significant digit)
 __device__ __forceinline__ uint32_t digit_reverse(uint32_t x, int k) {
@@ -92,53 +88,53 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
         if (SMEM) atomicAdd(&s_cnt[idx], 1); else atomicAdd(&row[idx], 1ull);
     };
 
+    // 32-bit everything inside the slice: contig positions are int32 and a slice is < 2^31 fragments
+    const uint32_t mask2k = (1u << (2 * k)) - 1u, maskk = (1u << k) - 1u;
+    const int len32 = (int)min(contig_len, (int64_t)INT32_MAX);
+    const int h = k >> 1;
+    const int n_here = (int)(hi - lo);
+    const int32_t *__restrict__ fsp = frag_start + lo;
+    const int32_t *__restrict__ fep = frag_stop + lo;
+    const uint8_t *__restrict__ fqp = frag_mapq ? frag_mapq + lo : nullptr;
+    const uint8_t *__restrict__ fdp = frag_strand ? frag_strand + lo : nullptr;
     int fs_r[kMotifUnroll], fe_r[kMotifUnroll], q_r[kMotifUnroll], sd_r[kMotifUnroll];
-    for (int64_t i0 = lo + tid; i0 < hi; i0 += (int64_t)kMotifUnroll * kMotifThreads) {
+    for (int i0 = tid; i0 < n_here; i0 += kMotifUnroll * kMotifThreads) {
 #pragma unroll
         for (int u = 0; u < kMotifUnroll; ++u) {
-            const int64_t i = i0 + (int64_t)u * kMotifThreads;
-            const bool in = i < hi;
-            fs_r[u] = in ? __ldcs(frag_start + i) : 0;
-            fe_r[u] = in ? __ldcs(frag_stop + i) : 0;
-            q_r[u] = in ? (frag_mapq ? (int)__ldcs(frag_mapq + i) : 255) : -1;
-            sd_r[u] = (in && frag_strand) ? (int)__ldcs(frag_strand + i) : 1;
+            const int i = i0 + u * kMotifThreads;
+            const bool in = i < n_here;
+            fs_r[u] = in ? __ldcs(fsp + i) : 0;
+            fe_r[u] = in ? __ldcs(fep + i) : 0;
+            q_r[u] = in ? (fqp ? (int)__ldcs(fqp + i) : 255) : -1;
+            sd_r[u] = (in && fdp) ? (int)__ldcs(fdp + i) : 1;
         }
 #pragma unroll
         for (int u = 0; u < kMotifUnroll; ++u) {
             const int fs = fs_r[u], fe = fe_r[u];
             if (q_r[u] < min_mapq || !(fe > S && fs < E)) continue;
             if (BREAKPOINT) {
-                const int h = k >> 1;
-                if (fs - h < 0 || (int64_t)fs + h >= contig_len) continue;   // too close to a contig end
+                if (fs < h || fs >= len32 - h) continue;                     // too close to a contig end
                 if ((k & 1) != 0) continue;                                  // 2h != k: never counted
                 if (strand_mode == 0 || (strand_mode == 1 && sd_r[u])) {
-                    if (!has_n(nmask, fs - h, k)) bump(digit_reverse(window2(seq, fs - h, k), k));
+                    if (!has_n(nmask, fs - h, maskk)) bump(digit_reverse(window2(seq, fs - h, mask2k), k));
                 }
                 if (strand_mode != 1) {
-                    const int64_t rs = (int64_t)fe - h;
-                    if (rs < 0 || (int64_t)fe + h > contig_len) continue;    // OutOfBoundsError -> skipped
-                    if (!has_n(nmask, rs, k)) {
-                        const uint32_t mask = (k >= 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
-                        bump((~window2(seq, rs, k)) & mask);
-                    }
+                    if (fe < h || fe > len32 - h) continue;                  // OutOfBoundsError -> skipped
+                    if (!has_n(nmask, fe - h, maskk)) bump((~window2(seq, fe - h, mask2k)) & mask2k);
                 }
                 continue;
             }
             if (strand_mode == 1 && !sd_r[u]) continue;  // forward-only: '+' fragments only
             if (strand_mode != 2) {
-                if (fs < 0 || (int64_t)fs + k > contig_len) continue;  // ValueError -> `continue`
-                if (!has_n(nmask, fs, k)) bump(digit_reverse(window2(seq, fs, k), k));
+                if (fs < 0 || fs > len32 - k) continue;  // ValueError -> `continue`
+                if (!has_n(nmask, fs, maskk)) bump(digit_reverse(window2(seq, fs, mask2k), k));
             }
             if (strand_mode != 1) {
-                const int64_t rs = (int64_t)fe - k;
-                if (rs < 0 || (int64_t)fe > contig_len) {
+                if (fe < k || fe > len32) {
                     if (strand_mode == 0) atomicOr(error_flag, 1);  // RuntimeError in the reference
                     continue;
                 }
-                if (!has_n(nmask, rs, k)) {
-                    const uint32_t mask = (k >= 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
-                    bump((~window2(seq, rs, k)) & mask);
-                }
+                if (!has_n(nmask, fe - k, maskk)) bump((~window2(seq, fe - k, mask2k)) & mask2k);
             }
         }
     }
