@@ -188,7 +188,7 @@ def policy_code(intersect_policy: str) -> int:
         raise InvalidInputError(f"{intersect_policy} is not a valid policy") from None
 
 
-def _splits_for(n_ivl: int, n_frag: int) -> int:
+def _splits_for(n_ivl: int, n_frag: int, unit_frags: int | None = None) -> int:
     """Slices per interval.  A unit (one warp, or one CTA for per-interval histograms) should hold
     about ``_UNIT_FRAGS`` candidate fragments - few enough that its loads are all in flight at
     once, many enough to amortise its descriptor fetch - and there should be at least a few
@@ -196,7 +196,7 @@ def _splits_for(n_ivl: int, n_frag: int) -> int:
     if n_ivl <= 0:
         return 1
     import os
-    unit = int(os.environ.get("FTK_UNIT_FRAGS", _UNIT_FRAGS))
+    unit = int(os.environ.get("FTK_UNIT_FRAGS", _UNIT_FRAGS)) if unit_frags is None else int(unit_frags)
     by_size = -(-(n_frag // max(n_ivl, 1)) // unit)
     by_grid = -(-4 * _TARGET_CTAS // n_ivl)
     return int(max(1, min(max(by_size, by_grid), 65536)))
@@ -318,17 +318,19 @@ def end_motif_hist(frags: ContigFragments, ref: PackedContig, ivl_start, ivl_sto
     err = t.zeros(1, dtype=t.int32, device=dev)
     fs, fe, mq = frags.ptrs()
     sd = 0 if frags.strand is None else frags.strand.data_ptr()
+    # a CTA zeroes and flushes a 4^k-bin histogram: give it enough fragments to amortise that
+    splits = _splits_for(n_ivl, frags.n, unit_frags=max(4096, 16 * 4 ** min(int(k), 6)))
     if breakpoint:
         check(lib().ftk_breakpoint_motif_hist_u64(
             fs, fe, mq, sd, frags.n, frags.max_len, ref.seq.data_ptr(), ref.nmask.data_ptr(), ref.length,
             s_dev.data_ptr(), e_dev.data_ptr(), n_ivl, int(k), int(strand_mode), int(quality_threshold),
-            int(bool(pooled)), _splits_for(n_ivl, frags.n), scratch.data_ptr(), counts.data_ptr(),
+            int(bool(pooled)), splits, scratch.data_ptr(), counts.data_ptr(),
             _stream_ptr(dev)), "ftk_breakpoint_motif_hist_u64")
         return counts[:rows]
     check(lib().ftk_end_motif_hist_u64(
         fs, fe, mq, sd, frags.n, frags.max_len, ref.seq.data_ptr(), ref.nmask.data_ptr(), ref.length,
         s_dev.data_ptr(), e_dev.data_ptr(), n_ivl, int(k), int(strand_mode), int(quality_threshold),
-        int(bool(pooled)), _splits_for(n_ivl, frags.n), scratch.data_ptr(), counts.data_ptr(),
+        int(bool(pooled)), splits, scratch.data_ptr(), counts.data_ptr(),
         err.data_ptr(), _stream_ptr(dev)), "ftk_end_motif_hist_u64")
     if int(err.item()):
         raise RuntimeError(
