@@ -269,50 +269,78 @@ adjust_generic_kernel(const float *__restrict__ x, const long long *__restrict__
 // ---------------------------------------------------------- Savitzky-Golay
 // scipy.signal.savgol_filter(adj, sg_w, deg) with mode='interp': interior = sg_w-tap stencil,
 // the first / last sg_w/2 outputs of every segment = polynomial fit of its first / last sg_w
-// samples evaluated at those positions (the two edge matrices).  One thread per output.
+// samples evaluated at those positions (the two edge matrices).
+// A CTA stages adj[o0 - half, o0 + kSgTile + half) in shared memory; every thread owns FOUR
+// consecutive outputs and slides a 4-register window over the taps, so a tap costs one tile read
+// and one (broadcast) coefficient read for four fused multiply-adds - the one-output-per-thread
+// version re-read both operands for every FMA and sat on the shared-memory pipe.  Element e lives
+// at slot e + (e >> 4): with that padding the 32 lanes' 8-byte reads (stride 4 elements) hit every
+// bank pair exactly twice, i.e. they are conflict-free.  Results go back through shared memory so
+// the global stores are coalesced.  Taps are accumulated in tap order like the reference stencil.
 constexpr int kSgThreads = 256;
 constexpr int kSgPerThread = 4;
 constexpr int kSgTile = kSgThreads * kSgPerThread;   // outputs per CTA
+__device__ __forceinline__ int sg_slot(int e) { return e + (e >> 4); }
 
 __global__ void __launch_bounds__(kSgThreads)
 adjust_savgol_kernel(const double *__restrict__ adj, const long long *__restrict__ seg_out_off, int n_seg,
                      long long n_total, int sg_w, const double *__restrict__ coef,
                      const double *__restrict__ edge_first, const double *__restrict__ edge_last,
                      double *__restrict__ out) {
-    __shared__ double s_coef[kAdjMaxSg];
-    __shared__ double s_tile[kSgTile + kAdjMaxSg];     // adj[o0 - half, o0 + kSgTile + half)
+    constexpr int kIn = kSgTile + kAdjMaxSg + 3;
+    __shared__ double s_coef[kAdjMaxSg + 1];
+    __shared__ double s_tile[kIn + (kIn >> 4) + 1];
+    __shared__ double s_out[kSgTile + (kSgTile >> 4) + 1];
     __shared__ long long s_seg0;
     const int half = sg_w >> 1;
     for (int i = threadIdx.x; i < sg_w; i += kSgThreads) s_coef[i] = coef[i];
     const long long o0 = (long long)blockIdx.x * kSgTile;
     if (threadIdx.x == 0) s_seg0 = find_segment(seg_out_off, n_seg, o0);
-    for (int i = threadIdx.x; i < kSgTile + 2 * half; i += kSgThreads) {   // coalesced tile load
+    for (int i = threadIdx.x; i < kSgTile + 2 * half + 3; i += kSgThreads) {   // coalesced tile load
         const long long g = o0 - half + i;
-        s_tile[i] = (g >= 0 && g < n_total) ? adj[g] : 0.0;
+        s_tile[sg_slot(i)] = (g >= 0 && g < n_total) ? adj[g] : 0.0;
     }
     __syncthreads();
+
+    const int l0 = threadIdx.x * kSgPerThread;        // first of this thread's 4 consecutive outputs
+    // interior stencil for all four (edge outputs are overwritten below)
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    double r0 = s_tile[sg_slot(l0)], r1 = s_tile[sg_slot(l0 + 1)], r2 = s_tile[sg_slot(l0 + 2)];
+    for (int i = 0; i < sg_w; ++i) {
+        const double r3 = s_tile[sg_slot(l0 + i + 3)];
+        const double c = s_coef[i];
+        a0 += c * r0; a1 += c * r1; a2 += c * r2; a3 += c * r3;
+        r0 = r1; r1 = r2; r2 = r3;
+    }
     long long s = s_seg0;
+    // first / last `half` outputs of a segment: polynomial edge fit instead of the stencil
+    auto finish = [&](int k, double interior) {
+        const long long o = o0 + l0 + k;
+        double v = interior;
+        if (o < n_total) {
+            while (s + 1 < n_seg && seg_out_off[s + 1] <= o) ++s;          // monotone in k: the walk is short
+            const long long b = seg_out_off[s];
+            const long long n_out = seg_out_off[s + 1] - b;
+            const long long j = o - b;
+            if (j < half) {
+                const double *__restrict__ p = adj + b;
+                v = 0.0;
+                for (int i = 0; i < sg_w; ++i) v += edge_first[j * sg_w + i] * p[i];
+            } else if (j >= n_out - half) {
+                const double *__restrict__ p = adj + b + n_out - sg_w;
+                v = 0.0;
+                for (int i = 0; i < sg_w; ++i) v += edge_last[(j - (n_out - half)) * sg_w + i] * p[i];
+            }
+        }
+        s_out[sg_slot(l0 + k)] = v;
+    };
+    finish(0, a0); finish(1, a1); finish(2, a2); finish(3, a3);
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < kSgPerThread; ++k) {
-        const int local = k * kSgThreads + threadIdx.x;                    // consecutive lanes -> consecutive LDS
+        const int local = k * kSgThreads + threadIdx.x;
         const long long o = o0 + local;
-        if (o >= n_total) break;
-        while (s + 1 < n_seg && seg_out_off[s + 1] <= o) ++s;              // monotone in k: the walk is short
-        const long long b = seg_out_off[s];
-        const long long n_out = seg_out_off[s + 1] - b;
-        const long long j = o - b;
-        double acc = 0.0;
-        if (j >= half && j < n_out - half) {
-            const double *p = s_tile + local;                              // = adj[o - half ...]
-            for (int i = 0; i < sg_w; ++i) acc += s_coef[i] * p[i];
-        } else if (j < half) {
-            const double *__restrict__ p = adj + b;
-            for (int i = 0; i < sg_w; ++i) acc += edge_first[j * sg_w + i] * p[i];
-        } else {
-            const double *__restrict__ p = adj + b + n_out - sg_w;
-            for (int i = 0; i < sg_w; ++i) acc += edge_last[(j - (n_out - half)) * sg_w + i] * p[i];
-        }
-        out[o] = acc;
+        if (o < n_total) out[o] = s_out[sg_slot(local)];
     }
 }
 
