@@ -54,7 +54,7 @@ def _to_device(a: np.ndarray, device, dtype):
     t = torch()
     a = np.ascontiguousarray(a, dtype=dtype)
     host = t.from_numpy(a)
-    if a.nbytes >= (1 << 16):
+    if a.nbytes >= (1 << 23):   # pinning costs a cudaHostAlloc: only worth it for the big columns
         host = host.pin_memory()
     return host.to(device, non_blocking=True)
 
