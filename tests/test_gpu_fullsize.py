@@ -142,3 +142,50 @@ def test_adjust_shift_invariance_mean_closed_form_and_oracle(big):
     one, _ = adjust_segments(wps[:3_000_000], [3_000_000], savgol=False, run_len=4096)
     two, _ = adjust_segments(wps[:3_000_000], [3_000_000], savgol=False, run_len=1531)
     assert torch.equal(one, two)
+
+
+def test_delfi_windows_partition_and_numpy(big):
+    """DELFI bins tiling the contig: every bin equals numpy's histogram of the passing midpoints,
+    G+C counts add up to the contig's, and gaps / blacklist only ever remove fragments."""
+    from finaletoolkit_b200 import device as D
+    from finaletoolkit_b200.synth import synth_twobit
+    fr, st, sp, mq = big["fr"], big["st"], big["sp"], big["mq"]
+    codes, nm = synth_twobit(CLEN, 3)
+    ref = D.PackedContig.from_codes(codes, nm, device=big["dev"])
+    L = (sp - st).astype(np.int64); mid = (st.astype(np.int64) + sp) // 2
+    ok = (mq >= 30) & (L >= 100) & (L <= 220) & (mid < CLEN)
+    step = 100_000
+    ws = np.arange(0, CLEN, step, dtype=np.int64); we = np.minimum(ws + step, CLEN)
+    got = D.delfi_windows(fr, ref, ws, we, quality_threshold=30).cpu().numpy()
+    nb = len(ws)
+    assert np.array_equal(got[:, 0], np.bincount(mid[ok & (L < 151)] // step, minlength=nb))
+    assert np.array_equal(got[:, 1], np.bincount(mid[ok & (L >= 151)] // step, minlength=nb))
+    assert np.array_equal(got[:, 2], got[:, 0] + got[:, 1])
+    gc = ((codes == 1) | (codes == 2)) & ~nm
+    assert np.array_equal(got[:, 3], np.add.reduceat(gc.astype(np.int64), ws))
+    # a gap track + blacklist: monotone (never adds), and exact against the oracle on a few bins
+    rng = np.random.default_rng(8)
+    r0 = np.sort(rng.integers(0, CLEN - 5000, 300)); r1 = r0 + rng.integers(150, 5000, 300)
+    order = np.lexsort((r1, r0)); blk = (r0[order], r1[order])
+    gaps = ((29_000_000, 31_500_000), [(0, 10_000), (CLEN - 10_000, CLEN)])
+    cut = D.delfi_windows(fr, ref, ws, we, blacklist=blk, gaps=gaps, quality_threshold=30).cpu().numpy()
+    assert (cut[:, :3] <= got[:, :3]).all() and cut[:, 2].sum() < got[:, 2].sum() and np.array_equal(cut[:, 3], got[:, 3])
+    seq = np.frombuffer(b"ACGT", np.uint8)[codes].copy(); seq[nm] = ord("N")
+    for j in (0, 7, 289, 290, 314, nb - 1):
+        assert tuple(cut[j]) == O.delfi_counts(big["ofr"], seq.tobytes(), int(ws[j]), int(we[j]), blk, gaps, 30)
+
+
+def test_agg_signal_linearity_and_numpy():
+    """Strand-aware aggregation at scale: integer rows make the fp64 sum order-free, so the kernel
+    must equal numpy's column sums exactly; a flipped '-' row equals the '+' row reversed."""
+    from finaletoolkit_b200 import device as D
+    rng = np.random.default_rng(12)
+    n_seg, row_len, mws = 20_000, 5000, 120
+    rows = rng.integers(-90, 40, (n_seg, row_len)).astype(np.float32)
+    strand = rng.choice(np.array([1, -1, 0], np.int8), n_seg)
+    lo, isz = mws // 2, row_len - mws
+    got = D.agg_signal(rows, strand, lo, isz).cpu().numpy()
+    core = rows[:, lo: lo + isz].astype(np.float64)
+    exp = core[strand == 1].sum(0) + core[strand == -1][:, ::-1].sum(0)
+    assert np.array_equal(got, exp)
+    assert np.array_equal(D.agg_signal(rows[:1], [-1], lo, isz).cpu().numpy(), core[0][::-1])
