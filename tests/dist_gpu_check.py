@@ -39,5 +39,45 @@ if ctx.rank == 0:
     assert d == exp and list(d) == list(exp), "genome-wide dict / first-seen order mismatch"
     print(f"dist check ok: world={ctx.world} rank0 owns {mine}; total={total}, {len(d)} distinct lengths, "
           f"first keys {list(d)[:5]}")
+
+# motifs (end + breakpoint) and DELFI bins: sharded by contig, one all-reduce each
+from finaletoolkit_b200 import device as D  # noqa: E402
+from finaletoolkit_b200.synth import synth_twobit  # noqa: E402
+
+
+class _Ref:
+    def __init__(self):
+        self.chroms = dict(contigs, extra=20_000)      # "extra": in the reference, not in the fragments
+        self._packed = {c: synth_twobit(n, i, seed_base=6100, telomere=500, block_len=1000)
+                        for i, (c, n) in enumerate(self.chroms.items())}
+
+    def device_contig(self, c, device=None):
+        return D.PackedContig.from_codes(*self._packed[c], device=device)
+
+    def ascii(self, c):
+        codes, nm = self._packed[c]
+        seq = np.frombuffer(b"ACGT", np.uint8)[codes].copy(); seq[nm] = ord("N")
+        return seq.tobytes()
+
+
+ref = _Ref()
+em = FD.genome_end_motif_counts(table, ref, k=3, quality_threshold=30, ctx=ctx, device=dev)
+bm = FD.genome_end_motif_counts(table, ref, k=4, quality_threshold=30, ctx=ctx, device=dev, breakpoint=True)
+bins = {c: (np.arange(0, n, 25_000), np.minimum(np.arange(0, n, 25_000) + 25_000, n)) for c, n in ref.chroms.items()}
+blk = {"1": (np.array([100_000, 400_000]), np.array([110_000, 400_900]))}
+gaps = {"2": ((300_000, 340_000), [(0, 5_000), (695_000, 700_000)])}
+dw = FD.genome_delfi_windows(table, ref, bins, blk, gaps, quality_threshold=30, ctx=ctx, device=dev)
+if ctx.rank == 0:
+    from finaletoolkit_b200.frag._motif_common import genome_windows
+    exp_em = sum(O.region_end_motifs(frs[c], ref.ascii(c), a, b, 3, True, False, 30) for c in contigs for a, b in genome_windows(contigs[c]))
+    exp_bm = sum(O.region_breakpoint_motifs(frs[c], ref.ascii(c), a, b, 4, True, False, 30) for c in contigs for a, b in genome_windows(contigs[c]))
+    assert np.array_equal(em, exp_em) and np.array_equal(bm, exp_bm), "motif counts mismatch"
+    empty = O.Frags(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(0, np.uint8))
+    for c in ref.chroms:
+        fr = frs.get(c, empty)
+        for j, (a, b) in enumerate(zip(*bins[c])):
+            assert tuple(dw[c][j]) == O.delfi_counts(fr, ref.ascii(c), int(a), int(b), blk.get(c), gaps.get(c), 30), (c, a, b)
+    print(f"dist check ok: motifs {int(em.sum())} / {int(bm.sum())} k-mers, DELFI {sum(int(v[:, 2].sum()) for v in dw.values())} "
+          f"fragments in {sum(len(v) for v in dw.values())} bins")
 dist.barrier()
 dist.destroy_process_group()
