@@ -327,3 +327,47 @@ def test_native_decoder_bgzf_gzip_and_quirks(tmp_path, manifest):
     # corrupt file -> the native decoder declines, the loader falls back and raises
     bad = tmp_path / "bad.frag.gz"; bad.write_bytes(b"\x1f\x8b\x08\x00garbage"); open(str(bad) + ".tbi", "wb").close()
     assert FR._decode_native(str(bad)) is None
+
+
+def test_c_abi_argument_validation_needs_no_gpu():
+    """Every entry point validates its arguments before touching CUDA: zero work is FTK_OK, nonsense is
+    a negative code with a message (include/ftk_b200.h: FTK_E_INVALID -1, FTK_E_RANGE -3)."""
+    import ctypes
+    from finaletoolkit_b200._lib import FtkLibraryError, check, lib
+    L = lib()
+    assert L.ftk_abi_version() >= 1
+    assert b"invalid" in L.ftk_error_string(-1).lower() and L.ftk_error_string(-3) and L.ftk_error_string(-4)
+    i64 = (ctypes.c_int64 * 4)(0, 10, 0, 0)
+    i32 = (ctypes.c_int32 * 4)()
+    # zero work -> FTK_OK without any pointer
+    assert L.ftk_wps_tiles_i32(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 120, 120, 180, 30, 0, 0, 0, 0) == 0
+    assert L.ftk_interval_hist_u64(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0) == 0
+    assert L.ftk_end_motif_hist_u64(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 0, 30, 0, 1, 0, 0, 0, 0) == 0
+    assert L.ftk_breakpoint_motif_hist_u64(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 6, 0, 30, 0, 1, 0, 0, 0) == 0
+    assert L.ftk_delfi_windows_u64(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, None, 30, 1, 0, 0, 0) == 0
+    assert L.ftk_agg_signal_f64(0, 0, 0, 0, 0, 0, 0, 0) == 0
+    assert L.ftk_savgol_f64(0, 0, 0, 0, 21, 0, 0, 0, 0, 0) == 0
+    assert L.ftk_cleavage_tiles_f64(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0) == 0
+    # nonsense -> negative code, never a launch
+    assert L.ftk_wps_tiles_i32(0, 0, 0, 5, 0, 0, 0, 0, 0, 3, 120, 120, 180, 30, 0, 0, 0, 0) == -1     # tiles, no tables
+    assert L.ftk_wps_tiles_i16(0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 120, 120, 180, 30, 0, 0, 0, 0, 0) == -1  # no overflow flag
+    assert L.ftk_end_motif_hist_u64(0, 0, 0, 0, 0, 0, 1, 1, 9, 1, 1, 2, 13, 0, 30, 0, 1, 1, 1, 1, 0) == -1    # k > 12
+    assert L.ftk_end_motif_hist_u64(0, 0, 0, 0, 0, 0, 1, 1, 9, 1, 1, 2, 4, 7, 30, 0, 1, 1, 1, 1, 0) == -1     # strand mode
+    assert L.ftk_breakpoint_motif_hist_u64(0, 0, 0, 0, 0, 0, 0, 0, 9, 1, 1, 2, 6, 0, 30, 0, 1, 1, 1, 0) == -1  # no contig
+    assert L.ftk_delfi_windows_u64(0, 0, 0, 5, 0, 0, 0, 0, 1, 1, 2, 0, 0, 0, None, 30, 1, 1, 1, 0) == -1      # fragments, no columns
+    assert L.ftk_delfi_windows_u64(0, 0, 0, 0, 0, 1, 0, 9, 1, 1, 2, 0, 0, 0, None, 30, 1, 1, 1, 0) == -1      # seq without N mask
+    assert L.ftk_agg_signal_f64(1, 2, 10, 6, 6, 1, 1, 0) == -1                                                  # trim + out > row
+    assert L.ftk_savgol_f64(1, 1, 1, 10, 20, 1, 1, 1, 2, 0) == -1                                               # even window
+    assert L.ftk_adjust_wps_f64(1, 1, 1, 1, 0, 1, 1, 999, 0, 100, 1, 1, 0) == -1                                # odd median window
+    n_tiles = L.ftk_wps_plan_tiles(i64, ctypes.cast(ctypes.byref(i64, 8), ctypes.POINTER(ctypes.c_int64)), i64, 1,
+                                   2 ** 40, 180, None, None, None, None, None)
+    assert n_tiles == -3                                                                                         # chrom_size > int32
+    with pytest.raises(FtkLibraryError, match="ftk_wps_plan_tiles"):
+        check(n_tiles, "ftk_wps_plan_tiles")
+    err = ctypes.c_int32(0)
+    assert L.ftk_fragfile_open(b"/nonexistent/x.frag.gz", 1, ctypes.byref(err)) is None and err.value == -4
+    o = (ctypes.c_int64 * 2)(0, 4); sz = (ctypes.c_int64 * 1)()
+    buf = (ctypes.c_uint8 * 8)(); out = (ctypes.c_uint8 * 8)()
+    assert L.ftk_zlib_compress_batch(buf, o, 1, 6, 1, out, o, sz) == -1                                         # slot < compressBound
+    assert L.ftk_zlib_uncompress_batch(buf, o, sz, -1, 1, out, o, sz) == -1
+    del i32
