@@ -282,6 +282,9 @@ constexpr int kSgPerThread = 4;
 constexpr int kSgTile = kSgThreads * kSgPerThread;   // outputs per CTA
 __device__ __forceinline__ int sg_slot(int e) { return e + (e >> 4); }
 
+// SGW > 0: window known at compile time (the reference default, 21): the thread's SGW + 3 inputs are
+// loaded into registers once and the taps are fully unrolled; SGW == 0: any odd window <= 127.
+template <int SGW>
 __global__ void __launch_bounds__(kSgThreads)
 adjust_savgol_kernel(const double *__restrict__ adj, const long long *__restrict__ seg_out_off, int n_seg,
                      long long n_total, int sg_w, const double *__restrict__ coef,
@@ -305,29 +308,42 @@ adjust_savgol_kernel(const double *__restrict__ adj, const long long *__restrict
     const int l0 = threadIdx.x * kSgPerThread;        // first of this thread's 4 consecutive outputs
     // interior stencil for all four (edge outputs are overwritten below)
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    double r0 = s_tile[sg_slot(l0)], r1 = s_tile[sg_slot(l0 + 1)], r2 = s_tile[sg_slot(l0 + 2)];
-    for (int i = 0; i < sg_w; ++i) {
-        const double r3 = s_tile[sg_slot(l0 + i + 3)];
-        const double c = s_coef[i];
-        a0 += c * r0; a1 += c * r1; a2 += c * r2; a3 += c * r3;
-        r0 = r1; r1 = r2; r2 = r3;
+    if (SGW > 0) {
+        double r[SGW + 3];
+#pragma unroll
+        for (int i = 0; i < SGW + 3; ++i) r[i] = s_tile[sg_slot(l0 + i)];
+#pragma unroll
+        for (int i = 0; i < SGW; ++i) {
+            const double c = s_coef[i];
+            a0 += c * r[i]; a1 += c * r[i + 1]; a2 += c * r[i + 2]; a3 += c * r[i + 3];
+        }
+    } else {
+        double r0 = s_tile[sg_slot(l0)], r1 = s_tile[sg_slot(l0 + 1)], r2 = s_tile[sg_slot(l0 + 2)];
+        for (int i = 0; i < sg_w; ++i) {
+            const double r3 = s_tile[sg_slot(l0 + i + 3)];
+            const double c = s_coef[i];
+            a0 += c * r0; a1 += c * r1; a2 += c * r2; a3 += c * r3;
+            r0 = r1; r1 = r2; r2 = r3;
+        }
     }
+    // first / last `half` outputs of a segment: polynomial edge fit instead of the stencil.  The
+    // segment of the thread's first output is located once; the other three only test its end.
     long long s = s_seg0;
-    // first / last `half` outputs of a segment: polynomial edge fit instead of the stencil
+    const long long o_first = o0 + l0;
+    while (s + 1 < n_seg && seg_out_off[s + 1] <= o_first) ++s;
+    long long seg_b = seg_out_off[s], seg_e = seg_out_off[s + 1];
     auto finish = [&](int k, double interior) {
-        const long long o = o0 + l0 + k;
+        const long long o = o_first + k;
         double v = interior;
         if (o < n_total) {
-            while (s + 1 < n_seg && seg_out_off[s + 1] <= o) ++s;          // monotone in k: the walk is short
-            const long long b = seg_out_off[s];
-            const long long n_out = seg_out_off[s + 1] - b;
-            const long long j = o - b;
+            while (o >= seg_e && s + 1 < n_seg) { ++s; seg_b = seg_e; seg_e = seg_out_off[s + 1]; }
+            const long long j = o - seg_b, n_out = seg_e - seg_b;
             if (j < half) {
-                const double *__restrict__ p = adj + b;
+                const double *__restrict__ p = adj + seg_b;
                 v = 0.0;
                 for (int i = 0; i < sg_w; ++i) v += edge_first[j * sg_w + i] * p[i];
             } else if (j >= n_out - half) {
-                const double *__restrict__ p = adj + b + n_out - sg_w;
+                const double *__restrict__ p = adj + seg_e - sg_w;
                 v = 0.0;
                 for (int i = 0; i < sg_w; ++i) v += edge_last[(j - (n_out - half)) * sg_w + i] * p[i];
             }
@@ -440,8 +456,15 @@ extern "C" int ftk_savgol_f64(const double *adj, const int64_t *seg_out_off, int
     if (!adj || !seg_out_off || !coef || !edge_first || !edge_last || !out || n_seg < 0 || n_total < 0)
         return FTK_E_INVALID;
     if (sg_w < 1 || !(sg_w & 1) || sg_w > kAdjMaxSg || adj == out) return FTK_E_INVALID;
-    adjust_savgol_kernel<<<(unsigned)((n_total + kSgTile - 1) / kSgTile), kSgThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
-        adj, reinterpret_cast<const long long *>(seg_out_off), n_seg, n_total, sg_w, coef, edge_first, edge_last, out);
+    const unsigned grid = (unsigned)((n_total + kSgTile - 1) / kSgTile);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long *oo = reinterpret_cast<const long long *>(seg_out_off);
+    if (sg_w == 21)
+        adjust_savgol_kernel<21><<<grid, kSgThreads, 0, stream>>>(adj, oo, n_seg, n_total, sg_w, coef, edge_first,
+                                                                  edge_last, out);
+    else
+        adjust_savgol_kernel<0><<<grid, kSgThreads, 0, stream>>>(adj, oo, n_seg, n_total, sg_w, coef, edge_first,
+                                                                 edge_last, out);
     FTK_CHECK_LAUNCH("adjust_savgol_kernel");
     return FTK_OK;
 }

@@ -5,6 +5,7 @@ call into ``libftk_b200.so`` through the C ABI of ``include/ftk_b200.h``.
 """
 from __future__ import annotations
 
+import functools
 from ctypes import POINTER, c_int32, c_int64
 
 import numpy as np
@@ -418,7 +419,14 @@ _ADJ_SLOTS = 148 * 3 * 128
 
 
 def savgol_tables(window: int, degree: int):
-    """Savitzky-Golay interior coefficients and mode='interp' edge-fit matrices (host, fp64).
+    """Savitzky-Golay interior coefficients and mode='interp' edge-fit matrices (host, fp64); cached."""
+    coef, first, last = _savgol_tables_cached(int(window), int(degree))
+    return coef.copy(), first.copy(), last.copy()
+
+
+@functools.lru_cache(maxsize=32)
+def _savgol_tables_cached(window: int, degree: int):
+    """The tables of ``savgol_tables``.
 
     Same least-squares construction as scipy.signal.savgol_filter (reference call site
     frag/_adjust_wps.py:135-138; scipy/signal/_savitzky_golay.py): interior = the centre
