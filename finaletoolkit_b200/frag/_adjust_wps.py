@@ -98,7 +98,7 @@ def adjust_wps(input_file, interval_file, output_file, chrom_sizes, interval_siz
             if len(starts) == 0:
                 continue
             try:
-                output_bw.addEntries([contig] * len(starts), starts, ends=starts + 1, values=values)
+                output_bw.addEntries(contig, starts, ends=starts + 1, values=values)
             except RuntimeError as e:  # frag/_adjust_wps.py:285-291
                 stderr.write(f"RuntimeError encountered while writing to {output_file} at interval "
                              f"{contig}:{starts[0]}-{starts[-1] + 1}: {e}\n")

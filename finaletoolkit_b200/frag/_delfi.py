@@ -21,7 +21,7 @@ import pandas
 
 from ..genome.gaps import GenomeGaps
 from ..io.fragments import as_table
-from ..io.reference import ReferenceWrapper
+from ..io.reference import open_reference
 from ..utils import chrom_sizes_to_list
 
 __all__ = ["delfi", "delfi_gc_correct", "delfi_merge_bins", "trim_coverage"]
@@ -202,7 +202,7 @@ def delfi(input_file, chrom_sizes, bins_file, reference_file, blacklist_file=Non
 
     blacklist_by_contig = _load_blacklist_indexed(blacklist_file)
     table = as_table(input_file, reference_file)
-    ref = reference_file if isinstance(reference_file, ReferenceWrapper) else ReferenceWrapper(str(reference_file), use_lock=False)
+    ref = open_reference(reference_file)
     windows = []
     bin_contigs = gapless["contig"].to_numpy()
     for contig, _size in contigs:

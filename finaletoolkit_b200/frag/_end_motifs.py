@@ -16,7 +16,7 @@ from time import time
 import numpy as np
 
 from ..io.fragments import as_table
-from ..io.reference import ReferenceWrapper
+from ..io.reference import ReferenceWrapper, open_reference
 from ..utils import gen_kmers
 from ._common import group_by_contig, resolve_length_aliases
 from ._motif_common import (MIN_QUALITY, _MotifFreqs, _MotifsIntervals, _BASES, genome_windows,
@@ -41,7 +41,7 @@ def _strand_mode(both_strands, negative_strand) -> int:
 
 
 def _ref(refseq_file) -> ReferenceWrapper:
-    return refseq_file if isinstance(refseq_file, ReferenceWrapper) else ReferenceWrapper(str(refseq_file), use_lock=False)
+    return open_reference(refseq_file)
 
 
 def region_end_motifs(input_file, contig, start, stop, refseq_file, k=4, fraction_low=50, fraction_high=None,

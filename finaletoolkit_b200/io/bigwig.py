@@ -58,8 +58,9 @@ def _deflate_sections(raws: list[bytes], level: int = 6) -> list[bytes]:
     return [dst[int(o): int(o) + int(z)].tobytes() for o, z in zip(out_off[:-1], sizes)]
 
 
-def _inflate_sections(buf: bytes, blocks: list[tuple[int, int]], max_uncomp: int) -> list[bytes]:
-    """Inflate independent sections on all host threads (ftk_zlib_uncompress_batch)."""
+def _inflate_sections(buf: bytes, blocks: list[tuple[int, int]], max_uncomp: int) -> list[np.ndarray]:
+    """Inflate independent sections on all host threads (ftk_zlib_uncompress_batch); returns uint8 views
+    into one batch buffer (no per-section copy)."""
     n = len(blocks)
     in_off = np.fromiter((b[0] for b in blocks), dtype=np.int64, count=n)
     in_size = np.fromiter((b[1] for b in blocks), dtype=np.int64, count=n)
@@ -71,7 +72,7 @@ def _inflate_sections(buf: bytes, blocks: list[tuple[int, int]], max_uncomp: int
                                           _ptr(in_size, ctypes.c_int64), n, 0, _ptr(dst, ctypes.c_uint8),
                                           _ptr(out_off, ctypes.c_int64), _ptr(sizes, ctypes.c_int64)),
           "ftk_zlib_uncompress_batch")
-    return [dst[int(o): int(o) + int(z)].tobytes() for o, z in zip(out_off[:-1], sizes)]
+    return [dst[int(o): int(o) + int(z)] for o, z in zip(out_off[:-1], sizes)]
 
 
 class BigWigWriter:
@@ -126,6 +127,9 @@ class BigWigWriter:
         en = np.asarray(ends, dtype=np.int64)
         if not (len(chroms) == st.size == en.size == vals.size):
             raise RuntimeError("chroms, starts, ends and values must have the same length")
+        if chroms.count(chroms[0]) == len(chroms):       # the usual call: one contig repeated
+            self._add_bedgraph(self._chrom_id(chroms[0]), st, en, vals)
+            return
         # runs of identical contigs
         i = 0
         while i < len(chroms):
@@ -220,6 +224,13 @@ class BigWigWriter:
         if np.any(st[1:] < en[:-1]) or np.any(en <= st):
             raise RuntimeError("The entries you tried to add are out of order or overlap")
         self._check_order(cid, int(st[0]), int(en[-1]))
+        if st.size > 1:
+            # per-base tracks (adjust_wps output): constant span and step -> fixedStep sections, 4 bytes
+            # per item instead of 12; readers see the same (start, end, value) intervals
+            span, step = int(en[0] - st[0]), int(st[1] - st[0])
+            if step >= span and np.all(en - st == span) and np.all(st[1:] - st[:-1] == step):
+                self._add_fixed(cid, int(st[0]), span, step, vals)
+                return
         for i in range(0, st.size, _ITEMS_PER_SECTION):
             s, e, v = st[i: i + _ITEMS_PER_SECTION], en[i: i + _ITEMS_PER_SECTION], vals[i: i + _ITEMS_PER_SECTION]
             rec = np.empty(s.size, dtype=[("s", "<u4"), ("e", "<u4"), ("v", "<f4")])
@@ -289,7 +300,9 @@ class BigWigReader:
         _, _, key_size, _, _, _ = struct.unpack_from(e + "IIIIQQ", b, ct_off)
         self._walk_chrom_tree(ct_off + 32, key_size)
         self._by_id = {cid: (name, size) for name, (cid, size) in self._chroms.items()}
-        self._cache: dict[int, bytes] = {}   # data offset -> inflated section
+        self._cache: dict = {}               # data offset -> inflated section (uint8 view)
+        self._sections = None                # flat R-tree leaves, built on the first query
+        self._spanning = ()
 
     def _walk_chrom_tree(self, off: int, key_size: int) -> None:
         b, e = self._buf, self._e
@@ -316,29 +329,47 @@ class BigWigReader:
         return {"version": self.version, "nLevels": self.n_zoom, "nBasesCovered": n, "minVal": mn,
                 "maxVal": mx, "sumData": sm, "sumSquared": sq}
 
-    def _blocks(self, cid: int, start: int, end: int):
+    def _load_index(self) -> None:
+        """Flatten the R-tree once: every leaf (data section) as rows of numpy arrays, per chromosome
+        sorted by start with a running maximum of the ends, so a query is two binary searches."""
         b, e = self._buf, self._e
-        out = []
-
-        def overlaps(sc, sb, ec, eb):
-            return (sc, sb) < (cid, end) and (ec, eb) > (cid, start)
-
-        def walk(off):
+        leaf_t = np.dtype([("sc", e + "u4"), ("sb", e + "u4"), ("ec", e + "u4"), ("eb", e + "u4"),
+                           ("off", e + "u8"), ("size", e + "u8")])
+        node_t = np.dtype([("sc", e + "u4"), ("sb", e + "u4"), ("ec", e + "u4"), ("eb", e + "u4"), ("child", e + "u8")])
+        leaves, stack = [], [self._index_off + 48]
+        while stack:
+            off = stack.pop()
             is_leaf, _, count = struct.unpack_from(e + "BBH", b, off)
-            off += 4
-            for _ in range(count):
-                if is_leaf:
-                    sc, sb, ec, eb, doff, dsize = struct.unpack_from(e + "IIIIQQ", b, off)
-                    if overlaps(sc, sb, ec, eb):
-                        out.append((doff, dsize))
-                    off += 32
-                else:
-                    sc, sb, ec, eb, child = struct.unpack_from(e + "IIIIQ", b, off)
-                    if overlaps(sc, sb, ec, eb):
-                        walk(child)
-                    off += 24
+            if is_leaf:
+                leaves.append(np.frombuffer(b, leaf_t, count, off + 4))
+            else:
+                stack.extend(np.frombuffer(b, node_t, count, off + 4)["child"].tolist()[::-1])
+        rows = np.concatenate(leaves) if leaves else np.zeros(0, leaf_t)
+        self._sections = {}
+        for cid in np.unique(rows["sc"]).tolist() if rows.size else []:
+            r = rows[(rows["sc"] == cid) & (rows["ec"] == cid)]
+            r = r[np.argsort(r["sb"], kind="stable")]
+            ends = r["eb"].astype(np.int64)
+            self._sections[cid] = (r["sb"].astype(np.int64), ends, np.maximum.accumulate(ends) if ends.size else ends,
+                                   r["off"].astype(np.int64), r["size"].astype(np.int64))
+        # sections spanning several chromosomes do not occur in bigWig data; keep them reachable anyway
+        self._spanning = rows[rows["sc"] != rows["ec"]]
 
-        walk(self._index_off + 48)
+    def _blocks(self, cid: int, start: int, end: int):
+        if self._sections is None:
+            self._load_index()
+        out = []
+        sec = self._sections.get(cid)
+        if sec is not None:
+            sb, eb, eb_max, off, size = sec
+            lo = int(np.searchsorted(eb_max, start, side="right"))     # first section whose running end > start
+            hi = int(np.searchsorted(sb, end, side="left"))            # sections starting before the query end
+            if hi > lo:
+                keep = eb[lo:hi] > start
+                out = list(zip(off[lo:hi][keep].tolist(), size[lo:hi][keep].tolist()))
+        for r in self._spanning:
+            if (int(r["sc"]), int(r["sb"])) < (cid, end) and (int(r["ec"]), int(r["eb"])) > (cid, start):
+                out.append((int(r["off"]), int(r["size"])))
         return out
 
     def _section(self, doff: int, dsize: int) -> bytes:
@@ -391,9 +422,17 @@ class BigWigReader:
             if bcid != cid:
                 continue
             if typ == 3:
-                v = np.frombuffer(raw, e + "f4", n, 24)
-                s = bstart + np.arange(n, dtype=np.int64) * step
-                en = s + span
+                if n == 0:
+                    continue
+                # fixedStep: clip by index arithmetic instead of building and masking all items
+                i0 = max(0, -(-(start - span + 1 - bstart) // step)) if start > bstart else 0   # first item with end > start
+                i1 = min(n, -(-(end - bstart) // step))                                          # items with start < end
+                if i1 <= i0:
+                    continue
+                v = np.frombuffer(raw, e + "f4", i1 - i0, 24 + 4 * i0)
+                s = np.arange(bstart + i0 * step, bstart + i1 * step, step, dtype=np.int64)
+                S.append(s); E.append(s + span); V.append(v)
+                continue
             elif typ == 2:
                 rec = np.frombuffer(raw, np.dtype([("s", e + "u4"), ("v", e + "f4")]), n, 24)
                 s = rec["s"].astype(np.int64); en = s + span; v = rec["v"]
@@ -410,6 +449,8 @@ class BigWigReader:
             S.append(s); E.append(en); V.append(v)
         if not S:
             return None
+        if len(S) == 1:
+            return S[0], E[0], V[0]
         s, en, v = np.concatenate(S), np.concatenate(E), np.concatenate(V)
         if np.all(s[1:] >= s[:-1]):
             return s, en, v

@@ -18,12 +18,36 @@ import numpy as np
 
 from ..exceptions import ContigNotFoundError, OutOfBoundsError
 
-__all__ = ["ReferenceWrapper"]
+__all__ = ["ReferenceWrapper", "open_reference"]
 
 _TWOBIT_SUFFIXES = (".2bit", ".tb2")
 # UCSC .2bit codes T0 C1 A2 G3 -> ours A0 C1 G2 T3
 _UCSC_TO_ACGT = np.array([3, 1, 0, 2], dtype=np.uint8)
 _ASCII = np.frombuffer(b"ACGT", dtype=np.uint8)
+# one .2bit byte (4 bases, first base in the top two bits, UCSC codes) -> one byte of the device
+# layout (first base in the low two bits, codes A0 C1 G2 T3)
+_TWOBIT_BYTE_LUT = np.array([sum(int(_UCSC_TO_ACGT[(v >> (6 - 2 * j)) & 3]) << (2 * j) for j in range(4))
+                             for v in range(256)], dtype=np.uint8)
+_OPEN: dict = {}
+
+
+def open_reference(reference_path) -> "ReferenceWrapper":
+    """A shared ``ReferenceWrapper`` per file (path, mtime, size): decoded / packed / uploaded contigs
+    survive across API calls instead of being rebuilt by every call (the reference re-opens the
+    file per worker, frag/_motif_common.py:580-610)."""
+    if isinstance(reference_path, ReferenceWrapper):
+        return reference_path
+    path = os.path.abspath(str(reference_path))
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"Reference file not found: {reference_path}")
+    st = os.stat(path)
+    key = (path, st.st_mtime_ns, st.st_size)
+    ref = _OPEN.get(key)
+    if ref is None:
+        if len(_OPEN) >= 4:
+            _OPEN.pop(next(iter(_OPEN)))
+        ref = _OPEN[key] = ReferenceWrapper(path, use_lock=False)
+    return ref
 
 
 class ReferenceWrapper:
@@ -84,6 +108,34 @@ class ReferenceWrapper:
         for s, z in zip(n_starts.tolist(), n_sizes.tolist()):
             nmask[s: s + z] = True
         self._codes[contig], self._nmask[contig] = codes, nmask
+
+    def packed_words(self, contig: str):
+        """``(seq_words, nmask_words)`` in the device layout of ``synth.pack_twobit``.  For .2bit input
+        this is one byte-LUT pass over the file's own 2-bit payload (no per-base expansion)."""
+        if contig not in self._chroms:
+            raise ContigNotFoundError(f"Contig {contig} not found in reference.")
+        if not self._is_2bit:
+            from ..synth import pack_twobit
+            self._ensure(contig)
+            return pack_twobit(self._codes[contig], self._nmask[contig])
+        buf, end, o = self._buf, self._end, self._index[contig]
+        (n,) = struct.unpack_from(end + "I", buf, o); o += 4
+        (nb,) = struct.unpack_from(end + "I", buf, o); o += 4
+        n_starts = np.frombuffer(buf, end + "u4", nb, o); o += 4 * nb
+        n_sizes = np.frombuffer(buf, end + "u4", nb, o); o += 4 * nb
+        (mb,) = struct.unpack_from(end + "I", buf, o); o += 4 + 8 * mb + 4
+        raw = np.frombuffer(buf, np.uint8, (n + 3) // 4, o)
+        nw = (n + 15) // 16 + 2
+        seq_bytes = np.zeros(nw * 4, dtype=np.uint8)
+        seq_bytes[: raw.size] = _TWOBIT_BYTE_LUT[raw]
+        if n % 4:                                     # bases past the end of the contig read as 0, like pack_twobit
+            seq_bytes[raw.size - 1] &= (1 << (2 * (n % 4))) - 1
+        nm = (n + 31) // 32 + 2
+        flags = np.zeros(nm * 32, dtype=np.uint8)
+        for a, z in zip(n_starts.tolist(), n_sizes.tolist()):
+            flags[a: min(a + z, n)] = 1
+        nmask_words = np.packbits(flags.reshape(nm, 32), axis=1, bitorder="little").view("<u4").reshape(nm)
+        return seq_bytes.view("<u4"), nmask_words.astype(np.uint32)
 
     def _open_fasta(self) -> None:
         opener = gzip.open if self.reference_path.endswith(".gz") else open
@@ -151,8 +203,8 @@ class ReferenceWrapper:
         dev = require_cuda(device)
         key = (contig, str(dev))
         if key not in self._device:
-            codes, nmask = self.contig_arrays(contig)
-            self._device[key] = PackedContig.from_codes(codes, nmask, device=dev)
+            seq_words, nmask_words = self.packed_words(contig)
+            self._device[key] = PackedContig(seq_words, nmask_words, self._chroms[contig], device=dev)
         return self._device[key]
 
     def close(self) -> None:
