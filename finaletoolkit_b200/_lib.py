@@ -36,6 +36,8 @@ SYMBOLS = {
                                   c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
     "ftk_wps_tiles_i16": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int64,
                                   c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
+    "ftk_wps_tiles_i8": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int64,
+                                 c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "ftk_interval_hist_u64": (c_int, [_P, _P, _P, c_int64, c_int32, _P, _P, c_int64,
                                       c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                       _P, _P, _P, _P, _P]),

@@ -135,6 +135,19 @@ __device__ __forceinline__ void store4(int16_t *p, const int4 &r, int *overflow)
     v.y = (r.z & 0xffff) | (r.w << 16);
     asm volatile("st.global.L1::no_allocate.v2.s32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
+// int8 (a quarter of the int32 bytes on the wire; fits whenever the local depth stays below 128):
+// one 32-bit store + the same overflow protocol.
+__device__ __forceinline__ void store4(int8_t *p, const int4 &r, int *overflow) {
+    const unsigned bad = ((unsigned)(r.x + 128) | (unsigned)(r.y + 128) | (unsigned)(r.z + 128) |
+                          (unsigned)(r.w + 128)) >> 8;
+    if (bad) atomicOr(overflow, 1);
+    const int v = (r.x & 0xff) | ((r.y & 0xff) << 8) | ((r.z & 0xff) << 16) | (r.w << 24);
+    asm volatile("st.global.L1::no_allocate.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void store1(int8_t *p, int v, int *overflow) {
+    if ((unsigned)(v + 128) >> 8) atomicOr(overflow, 1);
+    *p = (int8_t)v;
+}
 __device__ __forceinline__ void store1(int32_t *p, int v, int *) { *p = v; }
 __device__ __forceinline__ void store1(int16_t *p, int v, int *overflow) {
     if ((unsigned)(v + 32768) >> 16) atomicOr(overflow, 1);
@@ -630,4 +643,18 @@ extern "C" int ftk_wps_tiles_i16(const int32_t *frag_start, const int32_t *frag_
     return wps_tiles_impl<int16_t>(frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo,
                                    tile_mid_hi, tile_out_off, n_tiles, window_size, min_len, max_len, min_mapq,
                                    ranges_ready, scratch, out, overflow_flag, stream_);
+}
+
+extern "C" int ftk_wps_tiles_i8(const int32_t *frag_start, const int32_t *frag_stop,
+                                const uint8_t *frag_mapq, int64_t n_frag,
+                                const int32_t *tile_p0, const int32_t *tile_len,
+                                const int32_t *tile_mid_lo, const int32_t *tile_mid_hi,
+                                const int64_t *tile_out_off, int64_t n_tiles,
+                                int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
+                                int32_t ranges_ready, int64_t *scratch, int8_t *out,
+                                int32_t *overflow_flag, ftk_stream_t stream_) {
+    if (n_tiles > 0 && !overflow_flag) return FTK_E_INVALID;
+    return wps_tiles_impl<int8_t>(frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo,
+                                  tile_mid_hi, tile_out_off, n_tiles, window_size, min_len, max_len, min_mapq,
+                                  ranges_ready, scratch, out, overflow_flag, stream_);
 }

@@ -8,8 +8,11 @@ module hides as much of that as the link allows:
   copied host->device on one stream while chunk c-1 computes on a second stream and chunk c-2's
   WPS drains device->host on a third (PCIe is full duplex), with double-buffered device
   staging and CUDA events for every hand-off;
-* WPS travels back as int16 (``ftk_wps_tiles_i16``; exact - an overflow flag triggers an
-  int32 rerun), halving the D2H bytes;
+* WPS travels back as int16 (``ftk_wps_tiles_i16``) or, with ``wps_dtype="int8"``, as int8
+  (``ftk_wps_tiles_i8``) - both exact: a score that does not fit raises the overflow flag and the
+  caller reruns one size up - which halves / quarters the D2H bytes.  PCIe is full duplex but not
+  free of interference: measured on this box 720 MB H2D takes 13.0 ms alone, 15.2 ms next to a
+  500 MB D2H and 13.5 ms next to a 250 MB one (``tools/pcie_bw.py``);
 * per-interval coverage counts and the pooled length histogram are computed per chunk on the
   same resident slice and come back once at the end.
 
@@ -30,15 +33,19 @@ class StreamedContig:
     """Streamed L-WPS (+ coverage + length histogram) of one contig from pinned host columns.
 
     ``ivl_start/ivl_stop``: intervals sorted by start (e.g. ``multi_wps`` windows).  Outputs:
-    ``h_wps`` (int16 pinned, all intervals back to back; ``offsets`` as in ``WpsPlan``),
+    ``h_wps`` (int16 or int8 pinned, all intervals back to back; ``offsets`` as in ``WpsPlan``),
     ``h_cov`` (int64 per interval), ``h_hist`` (int64[n_bins]), ``h_total`` (int64[1]).
     """
 
     def __init__(self, h_start, h_stop, h_mapq, ivl_start, ivl_stop, chrom_size, window_size=120,
                  min_length=120, max_length=180, quality_threshold=30, max_frag_len=None, n_chunks=8,
-                 device=None, coverage=True, length_hist=True):
+                 device=None, coverage=True, length_hist=True, wps_dtype="int16"):
         t = torch()
         self.device = require_cuda(device)
+        if wps_dtype not in ("int16", "int8"):
+            raise ValueError("wps_dtype must be 'int16' or 'int8'")
+        self.wps_dtype = wps_dtype
+        wire = t.int16 if wps_dtype == "int16" else t.int8
         self.h_start, self.h_stop, self.h_mapq = h_start, h_stop, h_mapq
         for h in (h_start, h_stop, h_mapq):
             if not h.is_pinned():
@@ -74,13 +81,13 @@ class StreamedContig:
         self.d_start = [t.empty(max_f, dtype=t.int32, device=self.device) for _ in range(2)]
         self.d_stop = [t.empty(max_f, dtype=t.int32, device=self.device) for _ in range(2)]
         self.d_mapq = [t.empty(max_f, dtype=t.uint8, device=self.device) for _ in range(2)]
-        self.d_out = [t.empty(max(max_p, 1), dtype=t.int16, device=self.device) for _ in range(2)]
+        self.d_out = [t.empty(max(max_p, 1), dtype=wire, device=self.device) for _ in range(2)]
         self.d_flag = t.zeros(1, dtype=t.int32, device=self.device)
         self.n_bins = self.max_frag_len + 1
         self.d_cov = t.zeros(max(n_ivl, 1), dtype=t.int64, device=self.device)
         self.d_total = t.zeros(1, dtype=t.int64, device=self.device)
         self.d_hist = t.zeros((1, self.n_bins), dtype=t.int64, device=self.device)
-        self.h_wps = t.empty(max(self.n_positions, 1), dtype=t.int16).pin_memory()
+        self.h_wps = t.empty(max(self.n_positions, 1), dtype=wire).pin_memory()
         self.h_cov = t.empty(max(n_ivl, 1), dtype=t.int64).pin_memory()
         self.h_hist = t.empty((1, self.n_bins), dtype=t.int64).pin_memory()
         self.h_total = t.empty(1, dtype=t.int64).pin_memory()
@@ -90,7 +97,7 @@ class StreamedContig:
         self.ev_comp = [t.cuda.Event() for _ in range(2)]
         self.ev_out = [t.cuda.Event() for _ in range(2)]
         self.h2d_bytes = sum((c["f1"] - c["f0"]) * 9 for c in self.chunks)
-        self.d2h_bytes = self.n_positions * 2 + n_ivl * 8 + self.n_bins * 8 + 8 + 4
+        self.d2h_bytes = self.n_positions * (2 if wps_dtype == "int16" else 1) + n_ivl * 8 + self.n_bins * 8 + 8 + 4
         self.kernel_launches = 0
 
     def run(self):
@@ -98,6 +105,7 @@ class StreamedContig:
         t = torch()
         W, lo, hi, q = self.params
         L = lib()
+        wps_tiles = L.ftk_wps_tiles_i16 if self.wps_dtype == "int16" else L.ftk_wps_tiles_i8
         cur = t.cuda.current_stream(self.device)
         for s_ in (self.s_in, self.s_comp, self.s_out):
             s_.wait_stream(cur)
@@ -122,12 +130,12 @@ class StreamedContig:
                                         device=self.device, max_len=self.max_frag_len)
                 plan = c["plan"]
                 if plan.n_tiles:
-                    check(L.ftk_wps_tiles_i16(
+                    check(wps_tiles(
                         frags.start.data_ptr(), frags.stop.data_ptr(), frags.mapq.data_ptr(), frags.n,
                         plan.tile_p0.data_ptr(), plan.tile_len.data_ptr(), plan.tile_mid_lo.data_ptr(),
                         plan.tile_mid_hi.data_ptr(), plan.tile_out_off.data_ptr(), plan.n_tiles,
                         W, none_to_ftk(lo), hi, q, 0, plan.scratch.data_ptr(), self.d_out[b].data_ptr(),
-                        self.d_flag.data_ptr(), _stream_ptr(self.device)), "ftk_wps_tiles_i16")
+                        self.d_flag.data_ptr(), _stream_ptr(self.device)), "ftk_wps_tiles_" + self.wps_dtype[3:])
                     launches += 2
                 if c["ivl"] is not None:
                     interval_hist(frags, intersect_policy="midpoint", quality_threshold=q, ivl_set=c["ivl"],
@@ -154,5 +162,6 @@ class StreamedContig:
         cur.synchronize()
         self.kernel_launches = launches
         if int(self.h_flag[0]):
-            raise OverflowError("WPS does not fit int16 on this input; use the int32 path (WpsPlan.run)")
+            raise OverflowError(f"WPS does not fit {self.wps_dtype} on this input; rerun with "
+                                + ("wps_dtype='int16'" if self.wps_dtype == "int8" else "the int32 path (WpsPlan.run)"))
         return self.h_wps, self.h_cov, self.h_hist, self.h_total

@@ -109,6 +109,18 @@ int ftk_wps_tiles_i16(const int32_t *frag_start_dev, const int32_t *frag_stop_de
                       int32_t ranges_ready, int64_t *scratch_dev, int16_t *out_dev,
                       int32_t *overflow_flag_dev, ftk_stream_t stream);
 
+/* Same, scores as int8 (a quarter of the int32 bytes device->host).  Exact whenever every |WPS| <= 127
+ * (local depth below 128, the case for ordinary whole-genome coverage); otherwise *overflow_flag_dev
+ * is set and the caller reruns with ftk_wps_tiles_i16 / _i32. */
+int ftk_wps_tiles_i8(const int32_t *frag_start_dev, const int32_t *frag_stop_dev,
+                      const uint8_t *frag_mapq_dev, int64_t n_frag,
+                      const int32_t *tile_p0_dev, const int32_t *tile_len_dev,
+                      const int32_t *tile_mid_lo_dev, const int32_t *tile_mid_hi_dev,
+                      const int64_t *tile_out_off_dev, int64_t n_tiles,
+                      int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
+                      int32_t ranges_ready, int64_t *scratch_dev, int8_t *out_dev,
+                      int32_t *overflow_flag_dev, ftk_stream_t stream);
+
 /* ------------------------------------------- coverage / fragment lengths
  * Fragment stream of a region (S, E) - FTK_NONE = None - exactly as the
  * reference builds it: tabix overlap rows (io/alignment.py:270-302:

@@ -214,6 +214,20 @@ def test_streamed_pipeline_matches_resident(dev):
         assert np.array_equal(w.numpy()[: pipe.n_positions].astype(np.int32), ref)
         assert np.array_equal(c.numpy(), cov.cpu().numpy()) and int(t[0]) == int(tot[0])
         assert np.array_equal(h.numpy(), hist.cpu().numpy())
+    # int8 on the wire: exact while |WPS| <= 127 (this 50x-like shard stays below), flagged otherwise
+    assert np.abs(ref).max() <= 127
+    pipe8 = StreamedContig(torch.from_numpy(st).pin_memory(), torch.from_numpy(sp).pin_memory(),
+                           torch.from_numpy(mq).pin_memory(), edges[:-1], edges[1:], clen, n_chunks=4, device=dev,
+                           wps_dtype="int8")
+    w8, c8, h8, t8 = pipe8.run()
+    assert w8.dtype == torch.int8 and np.array_equal(w8.numpy()[: pipe8.n_positions].astype(np.int32), ref)
+    assert np.array_equal(c8.numpy(), cov.cpu().numpy()) and pipe8.d2h_bytes < pipe.d2h_bytes
+    deep_s = np.sort(np.random.default_rng(2).integers(1000, 1400, 30_000)).astype(np.int32)
+    deep = StreamedContig(torch.from_numpy(deep_s).pin_memory(), torch.from_numpy(deep_s + 150).pin_memory(),
+                          torch.full((30_000,), 60, dtype=torch.uint8).pin_memory(), [0], [5000], 10_000, device=dev,
+                          wps_dtype="int8")
+    with pytest.raises(OverflowError, match="int16"):
+        deep.run()
     # int16 overflow is detected, not silently wrapped: 40000 identical fragments
     big_s = np.full(40_000, 1000, np.int32); big_e = big_s + 150
     pipe = StreamedContig(torch.from_numpy(big_s).pin_memory(), torch.from_numpy(big_e).pin_memory(),
