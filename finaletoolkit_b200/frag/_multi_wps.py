@@ -9,7 +9,6 @@ from __future__ import annotations
 import gzip
 import time
 import warnings
-from os import PathLike
 from sys import stderr, stdin
 
 import numpy as np

@@ -13,7 +13,6 @@ plus a ``MIN`` reduce of first-seen keys when the reference's dict order matters
 """
 from __future__ import annotations
 
-import os
 from typing import Dict, Iterable, List, Sequence
 
 import numpy as np

@@ -1,6 +1,5 @@
 """Test helpers: materialise golden inputs as the files the public API reads."""
 import gzip
-import os
 import struct
 
 import numpy as np

@@ -2,7 +2,6 @@
 and one end-to-end stdout check (reference tests/test_cli.py:155-180) on the GPU."""
 import importlib
 import inspect
-import json
 import os
 
 import pytest

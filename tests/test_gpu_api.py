@@ -1,7 +1,6 @@
 """The public API (finaletoolkit_b200.frag / flat namespace) replayed against outputs of the
 unmodified reference (tests/golden/manifest.json): same calls, same kwargs, same files out."""
 import hashlib
-import os
 import warnings
 
 import numpy as np

@@ -2,8 +2,6 @@
 
 Reference: frag/_delfi.py:404-511 (_delfi_single_window) and :129-370 (delfi table, no LOESS).
 """
-import os
-
 import numpy as np
 import pytest
 

@@ -8,7 +8,7 @@ import warnings
 import numpy as np
 import pytest
 
-from helpers import write_2bit, write_frag_gz, write_text_gz
+from helpers import write_2bit, write_text_gz
 from oracle import oracle as O
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

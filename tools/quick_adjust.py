@@ -1,5 +1,5 @@
 """Profiling helper (run from the repo root: PYTHONPATH=. python tools/...): adjust_wps timing at chr1 scale (raw WPS from our kernel -> float32 -> adjust)."""
-import sys, time
+import sys
 import numpy as np, torch
 from finaletoolkit_b200.device import ContigFragments, WpsPlan, adjust_segments
 from finaletoolkit_b200.synth import synth_fragments

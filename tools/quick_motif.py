@@ -1,5 +1,5 @@
 """Profiling helper (PYTHONPATH=. python tools/quick_motif.py [k] [breakpoint]): end-motif kernel at chr1 scale."""
-import sys, time
+import sys
 import numpy as np, torch
 from finaletoolkit_b200 import device as D
 from finaletoolkit_b200.synth import synth_fragments, synth_twobit
