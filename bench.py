@@ -389,7 +389,7 @@ def run_ours(args):
             except Exception as e:  # noqa: BLE001 - secondary numbers must never sink the headline line
                 line["other_kernels"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_sample_rate(st, sp, mq, float(os.environ.get("FTK_BENCH_CPU_S", 10.0)))
+            line["cpu_baseline"] = cpu_sample_rate(st, sp, mq, float(os.environ.get("FTK_BENCH_CPU_S", 20.0)))
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
