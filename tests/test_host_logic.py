@@ -371,3 +371,54 @@ def test_c_abi_argument_validation_needs_no_gpu():
     assert L.ftk_zlib_compress_batch(buf, o, 1, 6, 1, out, o, sz) == -1                                         # slot < compressBound
     assert L.ftk_zlib_uncompress_batch(buf, o, sz, -1, 1, out, o, sz) == -1
     del i32
+
+
+def test_delfi_host_logic_against_reference_tables(tmp_path, manifest):
+    """Host side of the DELFI path (no GPU): gap track -> arms, blacklist CSR, gap-overlap bin filter
+    and the 50-bin merge, against what the reference produced (tests/golden, frag/_delfi.py,
+    frag/_delfi_merge_bins.py, genome/gaps.py)."""
+    import io
+    import pandas
+    from helpers import delfi_tracks
+    from finaletoolkit_b200.device import blacklist_in_windows
+    from finaletoolkit_b200.frag._delfi import _bins_overlapping_gaps, _load_blacklist_indexed, delfi_merge_bins
+    from finaletoolkit_b200.genome import GenomeGaps
+    m = manifest["delfi"]
+    gap_path = tmp_path / "gaps.bed"; gap_path.write_text(m["gaps"])
+    bl_path = tmp_path / "bl.bed"; bl_path.write_text(m["blacklist"])
+    gaps = GenomeGaps(str(gap_path))
+    bins = [tuple(b) for b in m["bins_list"]]
+    # arms exactly as _delfi_single_window derives them (in_tcmere first, then get_arm)
+    case = next(c for c in m["single_window"] if c["use_gaps"])
+    for (c, a, b), arm in zip(bins, case["arms"]):
+        cg = gaps.get_contig_gaps(c)
+        got = c if cg is None else ("NOARM" if cg.in_tcmere(a, b) else cg.get_arm(a, b))
+        assert got == arm, (c, a, b)
+    assert gaps.get_contig_gaps("chrX9") is None and gaps.in_tcmere("chrX9", 0, 10) is None
+    assert gaps.in_tcmere("chr7", 5_000, 20_000) is True and gaps.overlaps_gap("chr21", 45_000, 49_000) is False
+    assert gaps.get_arm("chr21", 10, 20) == "NOARM" and gaps.get_arm("chr7", 700_000, 800_000) == "7q"
+    out = tmp_path / "gaps_out.bed"; gaps.to_bed(str(out))
+    assert sorted(out.read_text().splitlines()) == sorted("\t".join(ln.split()) for ln in m["gaps"].splitlines())
+    # blacklist: same parse as the reference, CSR == brute force containment
+    bl = _load_blacklist_indexed(str(bl_path)); bl_ref, _ = delfi_tracks(m)
+    assert set(bl) == set(bl_ref) and all(np.array_equal(bl[c][0], bl_ref[c][0]) and np.array_equal(bl[c][1], bl_ref[c][1]) for c in bl)
+    ws = np.array([b[1] for b in bins if b[0] == "chr7"]); we = np.array([b[2] for b in bins if b[0] == "chr7"])
+    off, rs, re = blacklist_in_windows(bl["chr7"][0], bl["chr7"][1], ws, we)
+    for j in range(len(ws)):
+        exp = [(a, b) for a, b in zip(bl["chr7"][0].tolist(), bl["chr7"][1].tolist()) if a >= ws[j] and b <= we[j]]
+        assert list(zip(rs[off[j]: off[j + 1]].tolist(), re[off[j]: off[j + 1]].tolist())) == exp
+    assert off[-1] >= 4
+    # bins overlapping any gap are dropped before counting (utils.overlaps)
+    df = pandas.DataFrame(bins, columns=["contig", "start", "stop"])
+    hit = _bins_overlapping_gaps(df, gaps)
+    g = gaps.gaps
+    brute = [bool(np.any((g["contig"] == c) & (a < g["stop"]) & (b > g["start"]))) for c, a, b in bins]
+    assert hit.tolist() == brute and 0 < hit.sum() < len(bins)
+    # merge: the reference's per-bin table -> its merged table (p arms from the first bin, q arms from the last)
+    per_bin = pandas.read_csv(io.StringIO(m["delfi"][0]["tsv"]), sep="\t", float_precision="round_trip").rename(columns={"#contig": "contig"})
+    merged = delfi_merge_bins(per_bin, gc_corrected=False)
+    buf = io.StringIO(); merged.rename(columns={"contig": "#contig"}).to_csv(buf, sep="\t", index=False)
+    assert buf.getvalue() == m["delfi"][1]["tsv"]
+    with pytest.raises(ImportError):
+        from finaletoolkit_b200.frag._delfi import delfi_gc_correct
+        delfi_gc_correct(per_bin)
