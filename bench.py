@@ -238,6 +238,18 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     D.require_cuda(dev)
+    numa = "unbound"
+    if world > 1 and os.environ.get("FTK_BENCH_BIND", "1") == "1":
+        # one process per GPU: keep this rank (and the host columns it is about to allocate and pin)
+        # on the CPUs / memory node next to its GPU, so N ranks do not pull their H2D traffic
+        # through one socket.  N=1 stays unbound: its cpu_baseline leg uses every host core.
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            numa = f"{len(os.sched_getaffinity(0))} cpus near gpu {local}"
+        except Exception as e:  # noqa: BLE001 - placement is an optimisation, never a failure
+            numa = f"unbound ({type(e).__name__})"
 
     t0 = time.time()
     st, sp, mq, sd = synth_fragments(CONTIG_LEN, N_FRAG, rank)
@@ -379,7 +391,7 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": wps_ms, "ranges_prepass_ms": rng_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "steps": E, "chunks": len(pipe.chunks), "wps_dtype_on_the_wire": wire,
+                    "ms_per_step": e2e_ms, "steps": E, "chunks": len(pipe.chunks), "wps_dtype_on_the_wire": wire, "host_placement": numa,
                     "gpu_launches_per_step": pipe.kernel_launches},
             "gpu_launches": launches_per_step * K, "clocks": clocks, "wps_checksum": checksum,
         }
