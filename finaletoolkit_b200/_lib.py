@@ -68,6 +68,8 @@ SYMBOLS = {
     "ftk_fragfile_copy": (c_int, [c_void_p, c_int32, _i32p, _i32p, _u8p, _u8p]),
     "ftk_fragfile_close": (None, [c_void_p]),
     "ftk_zlib_compress_batch": (c_int, [_u8p, _i64p, c_int64, c_int32, c_int32, _u8p, _i64p, _i64p]),
+    "ftk_format_bedgraph_i64": (c_int64, [c_char_p, c_int64, _i64p, c_int64, c_int32, c_void_p, c_int64]),
+    "ftk_gzip_compress_batch": (c_int, [_u8p, _i64p, c_int64, c_int32, c_int32, _u8p, _i64p, _i64p]),
     "ftk_zlib_uncompress_batch": (c_int, [_u8p, _i64p, _i64p, c_int64, c_int32, _u8p, _i64p, _i64p]),
 }
 

@@ -326,3 +326,94 @@ extern "C" int ftk_zlib_uncompress_batch(const uint8_t *in, const int64_t *in_of
         return 0;
     });
 }
+
+// ---------------------------------------------------------------- bedGraph text + gzip members
+// `contig\tpos\tpos+1\tscore\n` for consecutive positions (frag/_multi_wps.py:328-341 writes these
+// lines one f-string at a time).  Two passes per thread slice: measure, then print.
+namespace {
+inline int dec_len(long long v) {
+    int n = v < 0 ? 1 : 0;
+    unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do { ++n; u /= 10; } while (u);
+    return n;
+}
+inline char *put_dec(char *p, long long v) {
+    char tmp[24];
+    int n = 0;
+    unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) *p++ = '-';
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+}  // namespace
+
+extern "C" int64_t ftk_format_bedgraph_i64(const char *contig, int64_t start, const int64_t *scores, int64_t n,
+                                           int32_t n_threads, char *out, int64_t out_cap) {
+    if (!contig || n < 0 || (n > 0 && !scores)) return FTK_E_INVALID;
+    if (n == 0) return 0;
+    const size_t cl = strlen(contig);
+    if (n_threads < 1) n_threads = (int32_t)std::max(1u, std::thread::hardware_concurrency());
+    const int T = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, n / 65536 + 1));
+    std::vector<int64_t> bytes((size_t)T + 1, 0);
+    auto slice = [&](int t, int64_t &a, int64_t &b) { a = n * t / T; b = n * (t + 1) / T; };
+    auto measure = [&](int t) {
+        int64_t a, b; slice(t, a, b);
+        int64_t tot = 0;
+        for (int64_t i = a; i < b; ++i)
+            tot += (int64_t)cl + 4 + dec_len(start + i) + dec_len(start + i + 1) + dec_len(scores[i]);
+        bytes[(size_t)t + 1] = tot;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(measure, t);
+        measure(0);
+        for (auto &x : th) x.join();
+    }
+    for (int t = 0; t < T; ++t) bytes[(size_t)t + 1] += bytes[(size_t)t];
+    const int64_t total = bytes[(size_t)T];
+    if (!out) return total;                     // size query
+    if (out_cap < total) return FTK_E_INVALID;
+    auto print = [&](int t) {
+        int64_t a, b; slice(t, a, b);
+        char *p = out + bytes[(size_t)t];
+        for (int64_t i = a; i < b; ++i) {
+            memcpy(p, contig, cl); p += cl;
+            *p++ = '\t'; p = put_dec(p, start + i);
+            *p++ = '\t'; p = put_dec(p, start + i + 1);
+            *p++ = '\t'; p = put_dec(p, scores[i]);
+            *p++ = '\n';
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(print, t);
+        print(0);
+        for (auto &x : th) x.join();
+    }
+    return total;
+}
+
+// gzip members (RFC 1952) of independent chunks: the concatenation is one valid .gz file that gzip,
+// zcat and Python's gzip read as a single stream - the multi-threaded stand-in for gzip.open(..., "wt").
+extern "C" int ftk_gzip_compress_batch(const uint8_t *in, const int64_t *in_off, int64_t n, int32_t level,
+                                       int32_t n_threads, uint8_t *out, const int64_t *out_off,
+                                       int64_t *out_size) {
+    if (n < 0 || level < -1 || level > 9) return FTK_E_INVALID;
+    if (n == 0) return 0;
+    if (!in || !in_off || !out || !out_off || !out_size) return FTK_E_INVALID;
+    return run_members(n, n_threads, [&](int64_t i) -> int {
+        const int64_t len = in_off[i + 1] - in_off[i], cap = out_off[i + 1] - out_off[i];
+        if (len < 0 || cap < 0) return FTK_E_INVALID;
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return FTK_E_IO;
+        if ((uLong)cap < deflateBound(&zs, (uLong)len)) { deflateEnd(&zs); return FTK_E_INVALID; }
+        zs.next_in = const_cast<uint8_t *>(in + in_off[i]); zs.avail_in = (uInt)len;
+        zs.next_out = out + out_off[i]; zs.avail_out = (uInt)cap;
+        const int rc = deflate(&zs, Z_FINISH);
+        out_size[i] = (int64_t)zs.total_out;
+        deflateEnd(&zs);
+        return rc == Z_STREAM_END ? 0 : FTK_E_IO;
+    });
+}

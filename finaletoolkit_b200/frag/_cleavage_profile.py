@@ -6,7 +6,6 @@ writers, errors) follow the reference.
 """
 from __future__ import annotations
 
-import gzip
 import time
 import warnings
 from sys import stderr, stdin
@@ -14,6 +13,7 @@ from sys import stderr, stdin
 import numpy as np
 
 from ..io import bigwig as pbw
+from ..io.textout import GzipTextWriter
 from ..io.fragments import as_table
 from ..utils import chrom_sizes_to_dict, chrom_sizes_to_list
 from ._common import group_by_contig, resolve_length_aliases
@@ -132,7 +132,7 @@ def multi_cleavage_profile(input_file, interval_file, chrom_sizes, left=0, right
                         stderr.write(f"captured error:\n{e}\n")
                         continue
         else:
-            with gzip.open(output_file, "wt") as bedgraph:
+            with GzipTextWriter(output_file) as bedgraph:   # float text stays Python's repr; deflate is threaded
                 for contig, start, scores in zip(contigs, starts, results):
                     pos = max(start, 0)
                     bedgraph.write("".join(f"{contig}\t{p}\t{p + 1}\t{v}\n"

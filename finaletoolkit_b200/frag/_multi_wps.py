@@ -6,7 +6,6 @@ GPU in ONE launch and ``workers`` is accepted for compatibility only.
 """
 from __future__ import annotations
 
-import gzip
 import time
 import warnings
 from sys import stderr, stdin
@@ -15,8 +14,9 @@ import numpy as np
 
 from ..io import bigwig as pbw
 from ..io.fragments import FragmentTable, as_table
+from ..io.textout import GzipTextWriter, bedgraph_text
 from ..utils import chrom_sizes_to_list
-from ._common import bedgraph_lines, group_by_contig, resolve_length_aliases
+from ._common import group_by_contig, resolve_length_aliases
 from ._wps import _wps_device
 
 __all__ = ["multi_wps"]
@@ -120,9 +120,9 @@ def multi_wps(input_file, site_bed, chrom_sizes=None, output_file=None, window_s
                         stderr.write("/n invalid or out of order interval encountered. Skipping to next.\n")
                         continue
         else:
-            with gzip.open(output_file, "wt") as bedgraph:
+            with GzipTextWriter(output_file) as bedgraph:   # frag/_multi_wps.py:328-341, same text
                 for contig, start, scores in zip(contigs, starts, results):
-                    bedgraph.write(bedgraph_lines(contig, start, scores))
+                    bedgraph.write(bedgraph_text(contig, start, scores))
     if verbose:
         stderr.write(f"multi_wps took {time.time() - start_time} s to complete\n")
     return output_file

@@ -1,0 +1,93 @@
+"""Text outputs of the hot path: bedGraph lines and .gz files, produced by host threads in the C ABI.
+
+The reference formats one f-string per position and writes through ``gzip.open(path, "wt")``
+(frag/_multi_wps.py:328-341, frag/_cleavage_profile.py:392-405) - single-threaded, level 9.  Here
+the lines of a whole interval come from ``ftk_format_bedgraph_i64`` and the file is a sequence of
+independently deflated gzip members (``ftk_gzip_compress_batch``), which every gzip reader sees as
+one stream with the same text.
+"""
+from __future__ import annotations
+
+import builtins
+import ctypes
+
+import numpy as np
+
+from .._lib import check, lib
+
+__all__ = ["bedgraph_bytes", "bedgraph_text", "GzipTextWriter"]
+
+_MEMBER = 1 << 20     # uncompressed bytes per gzip member
+_FLUSH = 64 << 20     # queued bytes before a batch is deflated
+
+
+def bedgraph_bytes(contig: str, start: int, scores) -> bytes:
+    """``contig\\tpos\\tpos+1\\tscore\\n`` for consecutive positions from ``start`` (integer scores)."""
+    return bedgraph_text(contig, start, scores).tobytes()
+
+
+def bedgraph_text(contig: str, start: int, scores) -> np.ndarray:
+    """Same lines as ``bedgraph_bytes`` in a uint8 array (no extra copy; ``GzipTextWriter.write`` takes it)."""
+    v = np.ascontiguousarray(scores, dtype=np.int64)
+    if v.size == 0:
+        return np.zeros(0, dtype=np.uint8)
+    L = lib()
+    name = contig.encode()
+    ptr = v.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+    n = L.ftk_format_bedgraph_i64(name, int(start), ptr, v.size, 0, None, 0)
+    check(n, "ftk_format_bedgraph_i64")
+    buf = np.empty(int(n), dtype=np.uint8)
+    check(L.ftk_format_bedgraph_i64(name, int(start), ptr, v.size, 0, buf.ctypes.data, int(n)), "ftk_format_bedgraph_i64")
+    return buf
+
+
+class GzipTextWriter:
+    """``gzip.open(path, "wt")`` look-alike (``write`` of str or bytes) that deflates on all host threads."""
+
+    def __init__(self, path: str, level: int = 6):
+        self._fh = builtins.open(str(path), "wb")
+        self._level = int(level)
+        self._parts: list[bytes] = []
+        self._size = 0
+
+    def write(self, text) -> None:
+        data = text.encode() if isinstance(text, str) else memoryview(text).cast("B")
+        if len(data):
+            self._parts.append(data)
+            self._size += len(data)
+            if self._size >= _FLUSH:
+                self._flush()
+
+    def _flush(self) -> None:
+        if not self._parts:
+            return
+        raw = np.frombuffer(b"".join(self._parts), dtype=np.uint8)
+        self._parts, self._size = [], 0
+        n = -(-raw.size // _MEMBER)
+        in_off = np.minimum(np.arange(n + 1, dtype=np.int64) * _MEMBER, raw.size)
+        lens = np.diff(in_off)
+        out_off = np.zeros(n + 1, dtype=np.int64); np.cumsum(lens + lens // 1000 + 64, out=out_off[1:])
+        out = np.empty(int(out_off[-1]), dtype=np.uint8)
+        sizes = np.zeros(n, dtype=np.int64)
+        p = lambda a, t: a.ctypes.data_as(ctypes.POINTER(t))   # noqa: E731
+        check(lib().ftk_gzip_compress_batch(p(raw, ctypes.c_uint8), p(in_off, ctypes.c_int64), n, self._level, 0,
+                                            p(out, ctypes.c_uint8), p(out_off, ctypes.c_int64),
+                                            p(sizes, ctypes.c_int64)), "ftk_gzip_compress_batch")
+        for o, z in zip(out_off[:-1].tolist(), sizes.tolist()):
+            self._fh.write(out[o: o + z].tobytes())
+
+    def close(self) -> None:
+        if self._fh is None:
+            return
+        self._flush()
+        if self._fh.tell() == 0:          # an empty text file is still a valid (empty) gzip stream
+            import gzip
+            self._fh.write(gzip.compress(b""))
+        self._fh.close()
+        self._fh = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()

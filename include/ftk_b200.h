@@ -325,6 +325,21 @@ int ftk_zlib_uncompress_batch(const uint8_t *in, const int64_t *in_off, const in
                               int64_t n, int32_t n_threads, uint8_t *out, const int64_t *out_off,
                               int64_t *out_size);
 
+/* ------------------------------------------------- text outputs (host)
+ * bedGraph lines `contig\tpos\tpos+1\tscore\n` for n consecutive positions from `start`, the text
+ * multi_wps writes one f-string at a time (frag/_multi_wps.py:328-341).  With out_host == NULL the
+ * call returns the byte count; otherwise it fills out_host (out_cap >= that count) on n_threads
+ * threads and returns the bytes written, or FTK_E_INVALID. */
+int64_t ftk_format_bedgraph_i64(const char *contig, int64_t start, const int64_t *scores_host, int64_t n,
+                                int32_t n_threads, char *out_host, int64_t out_cap);
+/* gzip (RFC 1952) members of independent chunks, laid out like ftk_zlib_compress_batch (slot >= the
+ * zlib deflateBound of a gzip stream: len + len/1000 + 64 is enough).  Concatenated members form one
+ * valid .gz file - the multi-threaded stand-in for the reference's gzip.open(path, "wt") writers
+ * (frag/_multi_wps.py:328-341, frag/_cleavage_profile.py:392-405). */
+int ftk_gzip_compress_batch(const uint8_t *in, const int64_t *in_off, int64_t n, int32_t level,
+                            int32_t n_threads, uint8_t *out, const int64_t *out_off,
+                            int64_t *out_size);
+
 #ifdef __cplusplus
 }
 #endif

@@ -422,3 +422,32 @@ def test_delfi_host_logic_against_reference_tables(tmp_path, manifest):
     with pytest.raises(ImportError):
         from finaletoolkit_b200.frag._delfi import delfi_gc_correct
         delfi_gc_correct(per_bin)
+
+
+def test_native_text_outputs(tmp_path):
+    """ftk_format_bedgraph_i64 writes the reference's bedGraph lines (frag/_multi_wps.py:328-341) and
+    ftk_gzip_compress_batch members concatenate into a .gz every gzip reader accepts."""
+    import gzip
+    import subprocess
+    from finaletoolkit_b200.io.textout import GzipTextWriter, bedgraph_bytes, bedgraph_text
+    rng = np.random.default_rng(0)
+    for contig, start, n in [("1", 0, 5000), ("chrUn_KI270742v1", 2_147_480_000, 33), ("12", 9, 1), ("X", 99, 200_000)]:
+        sc = rng.integers(-3000, 3000, n)
+        exp = "".join(f"{contig}\t{p}\t{p + 1}\t{v}\n" for p, v in zip(range(start, start + n), sc.tolist()))
+        assert bedgraph_bytes(contig, start, sc).decode() == exp
+    assert bedgraph_bytes("1", 5, []) == b"" and bedgraph_bytes("1", 7, [np.iinfo(np.int64).min]) == f"1\t7\t8\t{np.iinfo(np.int64).min}\n".encode()
+    path = str(tmp_path / "out.bedgraph.gz")
+    chunks = [bedgraph_text("7", 1_000_000 * k, rng.integers(-50, 20, 300_000)) for k in range(8)]
+    with GzipTextWriter(path) as w:
+        w.write("# header as str\n")
+        for c in chunks:
+            w.write(c)
+        w.write(b"tail as bytes\n")
+    exp = b"# header as str\n" + b"".join(c.tobytes() for c in chunks) + b"tail as bytes\n"
+    assert gzip.open(path, "rb").read() == exp
+    assert len(exp) > (4 << 20)                                       # several 1 MiB members
+    assert subprocess.run(["gzip", "-t", path]).returncode == 0
+    empty = str(tmp_path / "empty.gz")
+    with GzipTextWriter(empty):
+        pass
+    assert gzip.open(empty, "rb").read() == b""
