@@ -58,9 +58,16 @@ def adjust_wps(input_file, interval_file, output_file, chrom_sizes, interval_siz
         raise ValueError("Invalid filetype for input_file.")
     raw_wps = pbw.open(input_file, "r")
     try:
-        raw_wps.prefetch(intervals)   # one multi-threaded inflate of every section the intervals touch
         seg_vals, seg_pos, seg_contig = [], [], []
-        for contig, start, stop in intervals:
+        for k, (contig, start, stop) in enumerate(intervals):
+            if k == 0 or contig != intervals[k - 1][0]:
+                # one multi-threaded inflate of every section this contig's intervals touch; the
+                # inflated sections of the previous contig are dropped
+                raw_wps.drop_cache()
+                j = k
+                while j < len(intervals) and intervals[j][0] == contig:
+                    j += 1
+                raw_wps.prefetch(intervals[k:j])
             try:
                 rng = raw_wps.intervals_arrays(contig, start, stop)
             except RuntimeError:  # frag/_adjust_wps.py:145-153: invalid interval -> skipped

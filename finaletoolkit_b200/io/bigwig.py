@@ -410,6 +410,10 @@ class BigWigReader:
             for (doff, _), raw in zip(part, _inflate_sections(self._buf, part, self._uncomp)):
                 self._cache[doff] = raw
 
+    def drop_cache(self) -> None:
+        """Forget the sections inflated by ``prefetch`` (they are re-read on demand)."""
+        self._cache = {}
+
     def _intervals_arrays(self, chrom, start, end):
         if chrom not in self._chroms:
             raise RuntimeError("Invalid interval bounds!")
