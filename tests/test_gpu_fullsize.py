@@ -110,6 +110,29 @@ def test_end_motif_linearity_and_numpy(big):
     rbad = sum(nm[e64 - 1 - j] for j in range(k)) > 0
     exp = np.bincount(fidx[~fbad], weights=mult[~fbad], minlength=256) + np.bincount(ridx[~rbad], weights=mult[~rbad], minlength=256)
     assert np.array_equal(full, exp.astype(np.int64))
+    # breakpoint motifs (k = 6, windows centred on the breakpoints): same checks, numpy restatement of
+    # frag/_breakpoint_motifs.py:120-186 with the same double counting across window edges
+    k, h = 6, 3
+    bp = dict(k=k, quality_threshold=30, pooled=True, breakpoint=True)
+    full = D.end_motif_hist(fr, ref, ws, we, strand_mode=0, **bp)[0].cpu().numpy()
+    parts = sum(D.end_motif_hist(x, ref, ws, we, strand_mode=0, **bp)[0].cpu().numpy() for x in (a, b))
+    assert np.array_equal(full, parts)
+    fwd = D.end_motif_hist(allplus, ref, ws, we, strand_mode=1, **bp)[0].cpu().numpy()
+    rev = D.end_motif_hist(fr, ref, ws, we, strand_mode=2, **bp)[0].cpu().numpy()
+    assert np.array_equal(full, fwd + rev)
+    pw = 4 ** np.arange(k - 1, -1, -1)
+    near = (s64 >= h) & (s64 + h < CLEN)                      # else the fragment is skipped entirely
+    fs_, fe_, mu = s64[near], e64[near], mult[near]
+    fidx = sum(codes[fs_ - h + j].astype(np.int64) * pw[j] for j in range(k))
+    fbad = sum(nm[fs_ - h + j] for j in range(k)) > 0
+    rin = fe_ + h <= CLEN                                     # reverse window past the contig end: that end is skipped
+    fe_r, mu_r = fe_[rin], mu[rin]
+    ridx = sum((3 - codes[fe_r + h - 1 - j].astype(np.int64)) * pw[j] for j in range(k))
+    rbad = sum(nm[fe_r + h - 1 - j] for j in range(k)) > 0
+    exp = (np.bincount(fidx[~fbad], weights=mu[~fbad], minlength=4 ** k)
+           + np.bincount(ridx[~rbad], weights=mu_r[~rbad], minlength=4 ** k))
+    assert np.array_equal(full, exp.astype(np.int64)) and full.sum() > 1_000_000
+    assert not D.end_motif_hist(fr, ref, ws, we, k=5, strand_mode=0, quality_threshold=30, pooled=True, breakpoint=True).any()
 
 
 def test_adjust_shift_invariance_mean_closed_form_and_oracle(big):
