@@ -387,7 +387,7 @@ def run_ours(args):
                                       "one NCCL all_reduce(SUM) of the 601-bin job-wide length histogram per step"),
                        "l2": "no flush: per-step working set 1.7 GB >> 126 MB L2"},
             "positions_per_sec": pos_per_s,
-            "roofline": {"bound": "hbm", "kernel": "wps_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "wps_dual_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": wps_ms, "ranges_prepass_ms": rng_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -217,7 +217,7 @@ __device__ __forceinline__ void wps_scan_store(int *__restrict__ D, int *__restr
 
 // ---------------------------------------------------------------------------
 // Kernel A ("direct"): one CTA per tile, fragments streamed with 128-bit loads.
-// Kept as the simple variant; the pipelined kernel below is the default.
+// Kept as the simple variant (ftk_debug_set_wps_impl(1)); the pipelined kernels below are faster.
 // ---------------------------------------------------------------------------
 template <bool ODD, typename OutT>
 __global__ void __launch_bounds__(kWpsThreads)
@@ -284,7 +284,7 @@ wps_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restric
 }
 
 // ---------------------------------------------------------------------------
-// Kernel B ("stream", default): persistent, warp-specialised, TMA-fed.
+// Kernel B ("stream", ftk_debug_set_wps_impl(2)): persistent, warp-specialised, TMA-fed.
 //
 // grid = resident CTAs (SMs x kStreamCtasPerSm); each CTA walks tiles
 // blockIdx.x, +gridDim.x, ...  One producer warp runs ahead of eight consumer
@@ -472,6 +472,218 @@ wps_stream_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restr
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Kernel C ("dual", default): two tiles in flight per CTA.
+// The eight consumer warps are split into two groups of four, each with its own difference
+// array, its own staging buffer and its own named barrier; the producer warp feeds the groups
+// alternately.  While one group scans and stores its tile the other one is scattering the next,
+// so the barrier / phase latency of a tile is overlapped inside the CTA instead of across CTAs.
+// ---------------------------------------------------------------------------
+constexpr int kDualWarps = 4;
+constexpr int kDualGroupThreads = kDualWarps * 32;
+constexpr int kDualThreads = 2 * kDualGroupThreads + 32;
+constexpr int kDualCtasPerSm = 3;
+constexpr int kDualHalf = kWpsCap / 2;              // slots scanned per pass (4 warps x 640)
+
+struct __align__(128) DualSmem {
+    int D[2][kWpsCap];
+    int start[2][kStreamFrags];
+    int stop[2][kStreamFrags];
+    unsigned char mapq[2][kStreamFrags];
+    StreamDesc desc[2];
+    unsigned long long full_bar[2];
+    unsigned long long empty_bar[2];
+    int warp_tot[2][kDualWarps];
+};
+
+__device__ __forceinline__ void group_sync(int g) {
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + g), "n"(kDualGroupThreads) : "memory");
+}
+
+// Scan + store by one 4-warp group in two passes of kDualHalf slots (same lane layout as
+// wps_scan_store, so the stores stay coalesced and the register footprint stays at 5 int4).
+template <bool ODD, typename OutT>
+__device__ __forceinline__ void wps_scan_store_group(int *__restrict__ D, int *__restrict__ warp_tot,
+                                                     const WpsParams &P, const TileCtx &T,
+                                                     OutT *__restrict__ dst, int *overflow, int gt, int g) {
+    const int lane = gt & 31, warp = gt >> 5;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dst) & (4 * sizeof(OutT) - 1)) == 0);
+    int base_carry = 0;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        int4 v[kWpsIters];
+        int carry = 0;
+        const int span0 = half * kDualHalf + warp * kWpsSpan;
+#pragma unroll
+        for (int j = 0; j < kWpsIters; ++j) {
+            const int base = span0 + j * 128 + lane * 4;
+            int4 d = *reinterpret_cast<const int4 *>(&D[base]);
+            d.y += d.x; d.z += d.y; d.w += d.z;
+            int t = d.w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                int n = __shfl_up_sync(0xffffffffu, t, off);
+                if (lane >= off) t += n;
+            }
+            const int excl = t - d.w + carry;
+            v[j] = make_int4(d.x + excl, d.y + excl, d.z + excl, d.w + excl);
+            carry += __shfl_sync(0xffffffffu, t, 31);
+        }
+        if (lane == 0) warp_tot[warp] = carry;
+        group_sync(g);
+        int offset = base_carry, total = 0;
+#pragma unroll
+        for (int w = 0; w < kDualWarps; ++w) {
+            const int wt = warp_tot[w];
+            offset += (w < warp) ? wt : 0;
+            total += wt;
+        }
+        base_carry += total;
+#pragma unroll
+        for (int j = 0; j < kWpsIters; ++j) {
+            const int base = span0 + j * 128 + lane * 4;
+            const int4 r = make_int4(v[j].x + offset, v[j].y + offset, v[j].z + offset, v[j].w + offset);
+            if (ODD) {
+                *reinterpret_cast<int4 *>(&D[base]) = r;      // stage G; gathered below
+            } else if (aligned && base + 3 < T.len) {
+                store4(dst + base, r, overflow);
+            } else {
+                if (base + 0 < T.len) store1(dst + base + 0, r.x, overflow);
+                if (base + 1 < T.len) store1(dst + base + 1, r.y, overflow);
+                if (base + 2 < T.len) store1(dst + base + 2, r.z, overflow);
+                if (base + 3 < T.len) store1(dst + base + 3, r.w, overflow);
+            }
+        }
+        group_sync(g);   // warp_tot is rewritten by the next pass / D by the next tile
+    }
+    if (ODD) {
+        for (int k = gt; k < T.len; k += kDualGroupThreads) {
+            const int c = T.p0 + k;
+            store1(dst + k, D[c - ((c - P.a) & 1) - T.g0], overflow);
+        }
+        group_sync(g);
+    }
+}
+
+template <bool ODD, typename OutT>
+__global__ void __launch_bounds__(kDualThreads, kDualCtasPerSm)
+wps_dual_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
+                const uint8_t *__restrict__ frag_mapq, int64_t n_frag,
+                const int32_t *__restrict__ tile_p0, const int32_t *__restrict__ tile_len,
+                const int32_t *__restrict__ tile_mid_lo, const int32_t *__restrict__ tile_mid_hi,
+                const int64_t *__restrict__ tile_out_off, const int64_t *__restrict__ ranges,
+                int n_tiles, WpsParams P, OutT *__restrict__ out, int *__restrict__ overflow) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DualSmem &S = *reinterpret_cast<DualSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&S.full_bar[g], 1);
+            mbar_init(&S.empty_bar[g], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= 2 * kDualGroupThreads) {
+        // ===================== producer warp (one elected lane) =====================
+        if (tid == 2 * kDualGroupThreads) {
+            unsigned ph[2] = {0u, 0u};
+            const int64_t n16 = n_frag & ~(int64_t)15;
+            int j = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+                const int g = j & 1;
+                const int64_t lo = ranges[2 * (int64_t)tile], hi = ranges[2 * (int64_t)tile + 1];
+                const int p0 = tile_p0[tile], len = tile_len[tile];
+                const int mlo = tile_mid_lo[tile], mhi = tile_mid_hi[tile];
+                const long long ooff = tile_out_off[tile];
+                const int64_t lo16 = lo & ~(int64_t)15;
+                int64_t hi16 = (hi + 15) & ~(int64_t)15;
+                if (hi16 > n16) hi16 = n16;
+                if (hi16 < lo16) hi16 = lo16;
+                const int64_t t_lo = (hi16 > lo16) ? hi16 : lo16;
+                const bool has_tail = hi > t_lo;
+                const int64_t span = hi16 - lo16;
+                const int n_chunks = span > 0 ? (int)((span + kStreamFrags - 1) / kStreamFrags) : 1;
+                for (int c = 0; c < n_chunks; ++c) {
+                    mbar_wait(&S.empty_bar[g], ph[g] ^ 1u);
+                    const int64_t c0 = lo16 + (int64_t)c * kStreamFrags;
+                    const int n = (int)min((int64_t)kStreamFrags, hi16 - c0);
+                    StreamDesc &d = S.desc[g];
+                    d.tile = tile; d.p0 = p0; d.len = len; d.mid_lo = mlo; d.mid_hi = mhi;
+                    d.n = n > 0 ? n : 0;
+                    d.first = (c == 0); d.last = (c == n_chunks - 1);
+                    d.out_off = ooff;
+                    d.tail_lo = (d.last && has_tail) ? t_lo : 0;
+                    d.tail_hi = (d.last && has_tail) ? hi : 0;
+                    if (n > 0) {
+                        const unsigned bytes = (unsigned)n * (frag_mapq ? 9u : 8u);
+                        mbar_arrive_expect_tx(&S.full_bar[g], bytes);
+                        bulk_g2s(S.start[g], frag_start + c0, (unsigned)n * 4u, &S.full_bar[g]);
+                        bulk_g2s(S.stop[g], frag_stop + c0, (unsigned)n * 4u, &S.full_bar[g]);
+                        if (frag_mapq) bulk_g2s(S.mapq[g], frag_mapq + c0, (unsigned)n, &S.full_bar[g]);
+                    } else {
+                        mbar_arrive(&S.full_bar[g]);
+                    }
+                    ph[g] ^= 1u;
+                }
+            }
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+                mbar_wait(&S.empty_bar[g], ph[g] ^ 1u);
+                S.desc[g].tile = -1;
+                mbar_arrive(&S.full_bar[g]);
+            }
+        }
+        return;
+    }
+
+    // ========================= consumer groups =========================
+    const int g = tid / kDualGroupThreads;
+    const int gt = tid - g * kDualGroupThreads;
+    int *__restrict__ D = S.D[g];
+    unsigned phase = 0;
+    TileCtx T = make_tile_ctx<ODD>(P, 0, 0, 0, 0);
+    for (;;) {
+        mbar_wait(&S.full_bar[g], phase);
+        const StreamDesc d = S.desc[g];
+        if (d.tile < 0) break;
+        if (d.first) {
+            T = make_tile_ctx<ODD>(P, d.p0, d.len, d.mid_lo, d.mid_hi);
+#pragma unroll
+            for (int j = 0; j < kWpsCap / (4 * kDualGroupThreads); ++j)
+                reinterpret_cast<int4 *>(D)[j * kDualGroupThreads + gt] = make_int4(0, 0, 0, 0);
+            group_sync(g);
+        }
+        const int nvec = d.n >> 2;
+        const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(S.start[g]);
+        const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(S.stop[g]);
+        const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(S.mapq[g]);
+        for (int v = gt; v < nvec; v += kDualGroupThreads) {
+            const int4 s = vs[v], e = ve[v];
+            const uchar4 q = frag_mapq ? vq[v] : make_uchar4(255, 255, 255, 255);
+            wps_scatter(D, P, T, s.x, e.x, q.x);
+            wps_scatter(D, P, T, s.y, e.y, q.y);
+            wps_scatter(D, P, T, s.z, e.z, q.z);
+            wps_scatter(D, P, T, s.w, e.w, q.w);
+        }
+        if (d.tail_hi > d.tail_lo) {
+            const int64_t i = d.tail_lo + gt;
+            if (i < d.tail_hi)
+                wps_scatter(D, P, T, __ldcs(frag_start + i), __ldcs(frag_stop + i),
+                            frag_mapq ? (int)__ldcs(frag_mapq + i) : 255);
+        }
+        group_sync(g);                                   // scatter done; the staging buffer is free
+        if (gt == 0) mbar_arrive(&S.empty_bar[g]);
+        if (d.last)
+            wps_scan_store_group<ODD>(D, S.warp_tot[g], P, T, out + d.out_off, overflow, gt, g);
+        phase ^= 1u;
+    }
+}
+
 }  // namespace ftk
 
 extern "C" int64_t ftk_wps_plan_tiles(const int64_t *ivl_start, const int64_t *ivl_stop,
@@ -541,7 +753,9 @@ extern "C" int ftk_wps_tile_ranges(const int32_t *frag_start, int64_t n_frag,
     return FTK_OK;
 }
 
-static int g_wps_impl = 0;  // 0 = stream (TMA pipeline, default), 1 = direct (one CTA per tile)
+// 0 = dual (TMA pipeline, two tiles in flight per CTA; default), 1 = direct (one CTA per tile),
+// 2 = stream (TMA pipeline, one tile per CTA - the default until r1d)
+static int g_wps_impl = 0;
 extern "C" void ftk_debug_set_wps_impl(int impl) { g_wps_impl = impl; }
 
 template <bool ODD, typename OutT>
@@ -565,6 +779,21 @@ static int launch_wps(const int32_t *frag_start, const int32_t *frag_stop, const
     if (dev < 0 || dev >= 64) return FTK_E_RANGE;
     if (!sm_count[dev])
         FTK_CUDA_TRY(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+    if (g_wps_impl != 2) {
+        static thread_local bool dual_attr_set[64] = {false};
+        const int dsmem = (int)sizeof(DualSmem);
+        if (!dual_attr_set[dev]) {
+            FTK_CUDA_TRY(cudaFuncSetAttribute(wps_dual_kernel<ODD, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsmem));
+            dual_attr_set[dev] = true;
+        }
+        int64_t dgrid = (int64_t)sm_count[dev] * kDualCtasPerSm;
+        if (dgrid > (n_tiles + 1) / 2) dgrid = (n_tiles + 1) / 2;
+        wps_dual_kernel<ODD, OutT><<<(unsigned)dgrid, kDualThreads, dsmem, stream>>>(
+            frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo, tile_mid_hi, tile_out_off,
+            ranges, (int)n_tiles, P, out, overflow);
+        FTK_CHECK_LAUNCH("wps_dual_kernel");
+        return FTK_OK;
+    }
     const int smem = (int)sizeof(StreamSmem);
     if (!attr_set[dev]) {
         FTK_CUDA_TRY(cudaFuncSetAttribute(wps_stream_kernel<ODD, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
