@@ -24,6 +24,7 @@ import builtins
 import ctypes
 import os
 import struct
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -36,7 +37,7 @@ _CHROM_TREE_MAGIC = 0x78CA8C91
 _RTREE_MAGIC = 0x2468ACE0
 _ITEMS_PER_SECTION = 16384   # <= 65535 (itemCount is u16)
 _RTREE_BLOCK = 256
-_FLUSH_BYTES = 64 << 20      # queued raw section bytes before a batch is deflated
+_FLUSH_BYTES = 32 << 20      # queued raw section bytes before a batch is deflated
 _SECTION_HDR = 24
 
 
@@ -92,6 +93,10 @@ class BigWigWriter:
         self._max_uncomp = 0
         self._n_cov, self._min, self._max, self._sum, self._sumsq = 0, np.inf, -np.inf, 0.0, 0.0
         self._closed = False
+        # batches are deflated and written by one background thread (ctypes releases the GIL), in
+        # submission order, while the caller keeps queueing the next intervals
+        self._worker = ThreadPoolExecutor(max_workers=1)
+        self._inflight: list = []
 
     # -- pyBigWig-compatible surface ------------------------------------
     def addHeader(self, header, maxZooms: int = 10) -> None:
@@ -149,9 +154,13 @@ class BigWigWriter:
         self._closed = True
         fh = self._fh
         if self._chroms is None:
+            self._worker.shutdown()
             fh.close()
             return
-        self._flush()
+        try:
+            self._flush(wait=True)
+        finally:
+            self._worker.shutdown()
         index_off = fh.tell()
         self._write_rtree(index_off)
         end = fh.tell()
@@ -202,10 +211,14 @@ class BigWigWriter:
         if self._pending_bytes >= _FLUSH_BYTES:
             self._flush()
 
-    def _flush(self) -> None:
-        if not self._pending:
-            return
-        pend, self._pending, self._pending_bytes = self._pending, [], 0
+    def _flush(self, wait: bool = False) -> None:
+        if self._pending:
+            pend, self._pending, self._pending_bytes = self._pending, [], 0
+            self._inflight.append(self._worker.submit(self._write_batch, pend))
+        while self._inflight and (wait or len(self._inflight) > 2 or self._inflight[0].done()):
+            self._inflight.pop(0).result()        # re-raises a failure of the background batch
+
+    def _write_batch(self, pend) -> None:
         for (cid, start, end, _), comp in zip(pend, _deflate_sections([p[3] for p in pend])):
             off = self._fh.tell()
             self._fh.write(comp)
