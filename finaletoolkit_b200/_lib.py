@@ -60,6 +60,7 @@ SYMBOLS = {
     "ftk_cleavage_tiles_f64": (c_int, [_P, _P, _P, _P, c_int64, c_int32, _P, _P, _P, _P, _P, c_int64,
                                        c_int32, c_int32, c_int32, _P, _P, _P]),
     "ftk_fragfile_open": (c_void_p, [c_char_p, c_int32, _i32p]),
+    "ftk_fragfile_open_slice": (c_void_p, [c_char_p, c_int64, c_int32, c_int64, c_int32, c_int32, c_int32, _i32p]),
     "ftk_fragfile_is_bed6": (c_int32, [c_void_p]),
     "ftk_fragfile_skipped": (c_int64, [c_void_p]),
     "ftk_fragfile_n_contigs": (c_int32, [c_void_p]),

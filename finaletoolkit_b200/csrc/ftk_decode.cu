@@ -244,6 +244,103 @@ extern "C" void *ftk_fragfile_open(const char *path, int32_t n_threads, int32_t 
     return ff;
 }
 
+// Decode only the BGZF blocks [coffset_beg, coffset_end] of a tabix-indexed file: the text from
+// virtual offset (coffset_beg, uoffset_beg) up to (coffset_end, uoffset_end), which is where the
+// .tbi index says one contig's records live.  Neighbouring contigs that share the boundary blocks
+// come along as extra entries; the caller picks the contig it asked for.
+extern "C" void *ftk_fragfile_open_slice(const char *path, int64_t coffset_beg, int32_t uoffset_beg,
+                                         int64_t coffset_end, int32_t uoffset_end, int32_t bed6,
+                                         int32_t n_threads, int32_t *err) {
+    auto fail = [&](int code) -> void * { if (err) *err = code; return nullptr; };
+    if (!path || coffset_beg < 0 || coffset_end < coffset_beg || uoffset_beg < 0 || uoffset_end < 0)
+        return fail(FTK_E_INVALID);
+    FILE *fh = fopen(path, "rb");
+    if (!fh) return fail(FTK_E_IO);
+    // a BGZF block is at most 64 KiB: read through the end of the block that starts at coffset_end
+    const size_t want = (size_t)(coffset_end - coffset_beg) + (uoffset_end > 0 ? 65536 + 64 : 0);
+    std::vector<unsigned char> raw(want);
+    if (fseeko(fh, (off_t)coffset_beg, SEEK_SET) != 0) { fclose(fh); return fail(FTK_E_IO); }
+    raw.resize(want ? fread(raw.data(), 1, want, fh) : 0);
+    fclose(fh);
+    if (n_threads < 1) n_threads = (int32_t)std::max(1u, std::thread::hardware_concurrency());
+    // block list up to and including the block at coffset_end (only needed when uoffset_end > 0)
+    std::vector<Block> blocks;
+    size_t p = 0, uoff = 0, last_uoff = 0;
+    const size_t last_rel = (size_t)(coffset_end - coffset_beg);
+    while (p + 18 <= raw.size() && (p < last_rel || (p == last_rel && uoffset_end > 0))) {
+        if (raw[p] != 31 || raw[p + 1] != 139 || raw[p + 2] != 8 || !(raw[p + 3] & 4)) return fail(FTK_E_IO);
+        const unsigned xlen = raw[p + 10] | (raw[p + 11] << 8);
+        size_t q = p + 12;
+        const size_t xend = q + xlen;
+        long bsize = -1;
+        while (q + 4 <= xend && xend <= raw.size()) {
+            const unsigned slen = raw[q + 2] | (raw[q + 3] << 8);
+            if (raw[q] == 'B' && raw[q + 1] == 'C' && slen == 2) bsize = (raw[q + 4] | (raw[q + 5] << 8)) + 1;
+            q += 4 + slen;
+        }
+        if (bsize < 0 || p + (size_t)bsize > raw.size()) return fail(FTK_E_IO);
+        const size_t end = p + (size_t)bsize;
+        const size_t usize = (size_t)raw[end - 4] | ((size_t)raw[end - 3] << 8) | ((size_t)raw[end - 2] << 16) |
+                             ((size_t)raw[end - 1] << 24);
+        if (p == last_rel) last_uoff = uoff;
+        blocks.push_back({xend, end - 8 - xend, usize, uoff});
+        uoff += usize;
+        p = end;
+    }
+    if (p < last_rel) return fail(FTK_E_IO);          // the index points past what the file holds
+    std::vector<unsigned char> text(uoff);
+    {
+        const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads, blocks.size()));
+        std::vector<std::thread> th;
+        std::vector<int> ok((size_t)T, 1);
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t] {
+                for (size_t i = (size_t)t; i < blocks.size(); i += (size_t)T) {
+                    const Block &b = blocks[i];
+                    if (b.usize && !inflate_raw(raw.data() + b.off, b.csize, text.data() + b.uoff, b.usize)) ok[(size_t)t] = 0;
+                }
+            });
+        for (auto &x : th) x.join();
+        for (int v : ok) if (!v) return fail(FTK_E_IO);
+    }
+    const size_t t_end = (uoffset_end > 0) ? last_uoff + (size_t)uoffset_end : uoff;
+    if ((size_t)uoffset_beg > t_end || t_end > text.size()) return fail(FTK_E_IO);
+    const char *base = reinterpret_cast<const char *>(text.data()) + uoffset_beg;
+    const char *end = reinterpret_cast<const char *>(text.data()) + t_end;
+    const size_t len = (size_t)(end - base);
+    const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads, len / (1 << 20) + 1));
+    std::vector<const char *> cut((size_t)T + 1);
+    cut[0] = base; cut[(size_t)T] = end;
+    for (int t = 1; t < T; ++t) {
+        const char *c = base + len * (size_t)t / (size_t)T;
+        const char *nl = (const char *)memchr(c, '\n', (size_t)(end - c));
+        cut[(size_t)t] = nl ? nl + 1 : end;
+    }
+    std::vector<std::vector<Segment>> parts((size_t)T);
+    std::vector<int64_t> skipped((size_t)T, 0);
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t] { parse_range(cut[(size_t)t], cut[(size_t)t + 1], bed6, parts[(size_t)t], skipped[(size_t)t]); });
+        for (auto &x : th) x.join();
+    }
+    FragFile *ff = new FragFile();
+    ff->bed6 = bed6;
+    for (int64_t sk : skipped) ff->skipped += sk;
+    for (auto &segs : parts)
+        for (auto &sg : segs) {
+            Columns *dst = nullptr;
+            for (auto &c : ff->contigs) if (c.name == sg.name) { dst = &c; break; }
+            if (!dst) { ff->contigs.emplace_back(); dst = &ff->contigs.back(); dst->name = sg.name; }
+            dst->start.insert(dst->start.end(), sg.start.begin(), sg.start.end());
+            dst->stop.insert(dst->stop.end(), sg.stop.begin(), sg.stop.end());
+            dst->mapq.insert(dst->mapq.end(), sg.mapq.begin(), sg.mapq.end());
+            dst->strand.insert(dst->strand.end(), sg.strand.begin(), sg.strand.end());
+        }
+    if (err) *err = FTK_OK;
+    return ff;
+}
+
 extern "C" int32_t ftk_fragfile_is_bed6(void *h) { return h ? static_cast<FragFile *>(h)->bed6 : 0; }
 extern "C" int64_t ftk_fragfile_skipped(void *h) { return h ? static_cast<FragFile *>(h)->skipped : 0; }
 extern "C" int32_t ftk_fragfile_n_contigs(void *h) { return h ? (int32_t)static_cast<FragFile *>(h)->contigs.size() : 0; }

@@ -99,7 +99,7 @@ def _contig_windows(table, ref, contig, starts, stops, blacklist, contig_gaps, q
     if idx.size:
         gaps = None if contig_gaps is None else (contig_gaps.centromere, contig_gaps.telomeres)
         dev_ref = ref.device_contig(contig) if contig in ref.chroms else None
-        if contig not in table.columns:   # pysam.TabixFile.fetch on a contig the index does not know
+        if contig not in table.contigs:   # pysam.TabixFile.fetch on a contig the index does not know
             raise ValueError(f"could not create iterator for region '{contig}:{starts[idx[0]] + 1}-{stops[idx[0]]}'")
         got = delfi_windows(table.device(contig), dev_ref, [starts[i] for i in idx], [stops[i] for i in idx],
                             blacklist=blacklist, gaps=gaps, quality_threshold=quality_threshold)

@@ -15,8 +15,10 @@ Formats (io/alignment.py:143-156, 158-203, 270-302):
   * a ``.gz``/``.bgz`` path needs its ``.tbi`` sibling (``MissingIndexError``),
     other extensions raise ``UnsupportedFormatError``; a missing file
     ``FileNotFoundError``.
-BGZF is multi-member gzip, so Python's ``gzip`` reads it; the tabix index itself
-is not needed because whole contigs are decoded.  BAM/CRAM need htslib: they are
+Whole contigs are decoded, so small files are inflated and parsed in one parallel pass; for a
+large BGZF file with a real ``.tbi`` the index's per-contig virtual-offset ranges are used to
+decode a contig on first use and nothing else (``io/tabix.py``, ``ftk_fragfile_open_slice``).
+BAM/CRAM need htslib: they are
 read through ``pysam`` when it is importable (same read filter as
 io/alignment.py:60-71, 242-268) and rejected with ``UnsupportedFormatError``
 otherwise.  The mapq filter is NOT applied at load time - it is a kernel predicate.
@@ -39,35 +41,51 @@ Columns = Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]
 
 
 class FragmentTable:
-    """Per-contig fragment columns (host) with a device cache."""
+    """Per-contig fragment columns (host) with a device cache.
+
+    ``lazy`` = (contig names in file order, loader): contigs are decoded by ``loader(contig)`` the
+    first time they are asked for (tabix-indexed files); ``columns`` then holds the loaded ones."""
 
     def __init__(self, columns: Dict[str, Columns], source: str | None = None, is_sam: bool = False,
-                 contig_lengths: Dict[str, int] | None = None):
+                 contig_lengths: Dict[str, int] | None = None, lazy=None):
         self.source = source
         self.is_sam = is_sam
         self.contig_lengths = contig_lengths  # BAM/CRAM header only
         self.columns: Dict[str, Columns] = {}
-        for contig, (st, sp, mq, sd) in columns.items():
-            st = np.ascontiguousarray(st, dtype=np.int32)
-            sp = np.ascontiguousarray(sp, dtype=np.int32)
-            mq = np.ascontiguousarray(mq, dtype=np.uint8)
-            sd = np.ascontiguousarray(sd, dtype=np.uint8)
-            if st.size and not np.all(st[1:] >= st[:-1]):
-                order = np.argsort(st, kind="stable")  # keeps file order among equal starts
-                st, sp, mq, sd = st[order], sp[order], mq[order], sd[order]
-            self.columns[contig] = (st, sp, mq, sd)
+        self._lazy_names, self._loader = (list(lazy[0]), lazy[1]) if lazy is not None else (None, None)
+        for contig, cols in columns.items():
+            self._put(contig, cols)
         self._device: dict = {}
+
+    def _put(self, contig: str, cols: Columns) -> None:
+        st, sp, mq, sd = cols
+        st = np.ascontiguousarray(st, dtype=np.int32)
+        sp = np.ascontiguousarray(sp, dtype=np.int32)
+        mq = np.ascontiguousarray(mq, dtype=np.uint8)
+        sd = np.ascontiguousarray(sd, dtype=np.uint8)
+        if st.size and not np.all(st[1:] >= st[:-1]):
+            order = np.argsort(st, kind="stable")  # keeps file order among equal starts
+            st, sp, mq, sd = st[order], sp[order], mq[order], sd[order]
+        self.columns[contig] = (st, sp, mq, sd)
+
+    def _ensure(self, contig) -> None:
+        if self._loader is not None and contig not in self.columns and contig in self._lazy_names:
+            self._put(contig, self._loader(contig))
 
     @property
     def contigs(self):
-        return list(self.columns.keys())
+        return list(self._lazy_names) if self._lazy_names is not None else list(self.columns.keys())
 
     def n_fragments(self, contig=None) -> int:
         if contig is None:
+            for c in self.contigs:
+                self._ensure(c)
             return sum(c[0].size for c in self.columns.values())
+        self._ensure(contig)
         return self.columns[contig][0].size if contig in self.columns else 0
 
     def host(self, contig: str) -> Columns:
+        self._ensure(contig)
         if contig not in self.columns:
             z = np.zeros(0, np.int32)
             return z, z.copy(), np.zeros(0, np.uint8), np.zeros(0, np.uint8)
@@ -153,20 +171,71 @@ def _decode_native(path: str, threads: int = 0) -> Dict[str, Columns] | None:
             warnings.warn(
                 "input_file does not follow Fragmentation file format accepted by FinaleToolkit. "
                 "Attempting to read as a BED6 file.", UserWarning)
-        cols: Dict[str, Columns] = {}
-        for i in range(L.ftk_fragfile_n_contigs(h)):
-            n = L.ftk_fragfile_contig_count(h, i)
-            st = np.empty(n, np.int32); sp = np.empty(n, np.int32)
-            mq = np.empty(n, np.uint8); sd = np.empty(n, np.uint8)
-            p32, p8 = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint8)
-            rc = L.ftk_fragfile_copy(h, i, st.ctypes.data_as(p32), sp.ctypes.data_as(p32),
-                                     mq.ctypes.data_as(p8), sd.ctypes.data_as(p8))
-            if rc != 0:
-                return None
-            cols[L.ftk_fragfile_contig_name(h, i).decode()] = (st, sp, mq, sd)
-        return cols
+        return _handle_columns(L, h)
     finally:
         L.ftk_fragfile_close(h)
+
+
+def _handle_columns(L, h) -> Dict[str, Columns] | None:
+    import ctypes
+    cols: Dict[str, Columns] = {}
+    for i in range(L.ftk_fragfile_n_contigs(h)):
+        n = L.ftk_fragfile_contig_count(h, i)
+        st = np.empty(n, np.int32); sp = np.empty(n, np.int32)
+        mq = np.empty(n, np.uint8); sd = np.empty(n, np.uint8)
+        p32, p8 = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint8)
+        if L.ftk_fragfile_copy(h, i, st.ctypes.data_as(p32), sp.ctypes.data_as(p32), mq.ctypes.data_as(p8),
+                               sd.ctypes.data_as(p8)) != 0:
+            return None
+        cols[L.ftk_fragfile_contig_name(h, i).decode()] = (st, sp, mq, sd)
+    return cols
+
+
+_LAZY_MIN_BYTES = 32 << 20   # below this a whole-file decode is cheaper than thinking about it
+
+
+def _lazy_table(path: str) -> "FragmentTable | None":
+    """A ``FragmentTable`` that decodes contigs on demand through the file's tabix index, or None when
+    that does not apply (small file, placeholder / foreign .tbi, not BGZF, library unavailable)."""
+    import ctypes
+    if os.path.getsize(path) < int(os.environ.get("FTK_LAZY_MIN_BYTES", _LAZY_MIN_BYTES)):
+        return None
+    from .tabix import read_tbi
+    index = read_tbi(path + ".tbi")
+    if index is None or not index.ranges or (index.col_seq, index.col_beg, index.col_end) != (1, 2, 3):
+        return None
+    try:
+        from .._lib import lib
+        L = lib()
+        with open(path, "rb") as fh:
+            head = fh.read(18)
+        if len(head) < 18 or head[:4] != b"\x1f\x8b\x08\x04" or head[12:14] != b"BC":
+            return None
+        with gzip.open(path, "rt") as fh:            # column layout from the first data line
+            first = next((ln for ln in fh if ln.strip() and not ln.startswith(index.meta)), "")
+    except Exception:  # noqa: BLE001
+        return None
+    bed6 = len(first.rstrip("\n").split("\t")) > 5
+    if bed6:
+        warnings.warn(
+            "input_file does not follow Fragmentation file format accepted by FinaleToolkit. "
+            "Attempting to read as a BED6 file.", UserWarning)
+
+    def load(contig: str) -> Columns:
+        cb, ub, ce, ue = index.ranges[contig]
+        err = ctypes.c_int32(0)
+        h = L.ftk_fragfile_open_slice(path.encode(), cb, ub, ce, ue, int(bed6), 0, ctypes.byref(err))
+        if not h:
+            raise OSError(f"{path}: cannot decode the tabix range of contig {contig!r} (error {err.value})")
+        try:
+            cols = _handle_columns(L, h)
+        finally:
+            L.ftk_fragfile_close(h)
+        z = np.zeros(0, np.int32)
+        return (cols or {}).get(contig, (z, z.copy(), np.zeros(0, np.uint8), np.zeros(0, np.uint8)))
+
+    names = [n for n in index.names if n in index.ranges]
+    return FragmentTable({}, source=path, lazy=(names, load))
 
 
 def _parse_text_fast(path: str) -> Dict[str, Columns] | None:
@@ -244,13 +313,15 @@ def load_fragments(input_file, reference_file=None) -> FragmentTable:
     if path.lower().endswith((".bam", ".cram", ".sam")):
         tab = _load_sam(path, reference_file)
     else:
-        cols = _decode_native(path)
-        if cols is None:
-            cols = _parse_text_fast(path)
-        if cols is None:
-            with gzip.open(path, "rt") as fh:
-                cols = _parse_text_rows(fh)
-        tab = FragmentTable(cols, source=path)
+        tab = _lazy_table(path)
+        if tab is None:
+            cols = _decode_native(path)
+            if cols is None:
+                cols = _parse_text_fast(path)
+            if cols is None:
+                with gzip.open(path, "rt") as fh:
+                    cols = _parse_text_rows(fh)
+            tab = FragmentTable(cols, source=path)
     if len(_CACHE) > 8:
         _CACHE.pop(next(iter(_CACHE)))
     _CACHE[key] = tab

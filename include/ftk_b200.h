@@ -297,6 +297,13 @@ int ftk_cleavage_tiles_f64(const int32_t *frag_start_dev, const int32_t *frag_st
  * ftk_fragfile_copy fills caller buffers (pinned or pageable) of ftk_fragfile_contig_count
  * elements, rows in file order. */
 void *ftk_fragfile_open(const char *path, int32_t n_threads, int32_t *err);
+/* Same, for the part of a tabix-indexed file between two virtual offsets (coffset = file offset of a
+ * BGZF block, uoffset = byte inside its inflated text): what pysam.TabixFile.fetch(contig) reads
+ * through the .tbi index (io/alignment.py:270-279), here one contig's whole block range in one
+ * parallel pass.  bed6 = the column layout detected on the file's first data line. */
+void *ftk_fragfile_open_slice(const char *path, int64_t coffset_beg, int32_t uoffset_beg,
+                              int64_t coffset_end, int32_t uoffset_end, int32_t bed6,
+                              int32_t n_threads, int32_t *err);
 int32_t ftk_fragfile_is_bed6(void *handle);
 int64_t ftk_fragfile_skipped(void *handle);
 int32_t ftk_fragfile_n_contigs(void *handle);

@@ -83,6 +83,10 @@ def fixture17():
     cs = os.path.join(DATA, "b37.chrom.sizes")
     ct, st, sp, mq, fw = columns_of(frag)
     arrays = dict(start=st, stop=sp, mapq=mq, strand=fw)
+    # the fixture files themselves (bgzip + tabix output of htslib): exercises the BGZF / .tbi readers
+    for key, path in (("frag_gz_file", frag), ("frag_gz_tbi_file", frag + ".tbi"),
+                      ("bed_gz_file", bed6), ("bed_gz_tbi_file", bed6 + ".tbi")):
+        arrays[key] = np.frombuffer(open(path, "rb").read(), np.uint8)
     m = {"contig": "12", "chrom_size": 133851895,
          "frag_gz_text": read_gz_text(frag), "frag_bed_gz_text": read_gz_text(bed6),
          "intervals_bed": open(ivl).read(), "intervals_overlapped_bed": open(ivl_ov).read(),

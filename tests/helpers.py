@@ -128,3 +128,77 @@ def agg_fixture(g, m):
         return str(path)
 
     return signals, strands, write_bw
+
+
+def _reg2bin(beg, end):
+    """UCSC / tabix binning (SAM spec 5.3), 0-based half-open [beg, end)."""
+    end -= 1
+    for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        if beg >> shift == end >> shift:
+            return base + (beg >> shift)
+    return 0
+
+
+def write_bgzf_indexed(path, text: str, block=30000):
+    """``write_bgzf`` plus a REAL tabix index (BED-style: -s 1 -b 2 -e 3 -0) built the way htslib builds
+    it: binning index with merged chunks, 16-kb linear index, the 37450 pseudo-bin, BGZF-compressed."""
+    import zlib
+    data = text.encode()
+    coffs, sizes = [], []
+    with open(path, "wb") as fh:
+        for i in list(range(0, len(data), block)) + [None]:
+            chunk = b"" if i is None else data[i:i + block]
+            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            payload = c.compress(chunk) + c.flush()
+            bsize = 12 + 6 + len(payload) + 8 - 1
+            coffs.append(fh.tell()); sizes.append(len(chunk))
+            fh.write(struct.pack("<BBBBIBBH", 31, 139, 8, 4, 0, 0, 255, 6) + b"BC" + struct.pack("<HH", 2, bsize))
+            fh.write(payload + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+
+    def voff(t):   # virtual offset of text position t; a position at a block end is the NEXT block's start,
+        k = t // block   # as bgzf_tell reports it (for the end of the data that is the EOF block)
+        return (coffs[-1] << 16) if t >= len(data) else (coffs[k] << 16) | (t - k * block)
+
+    names, per_ref = [], {}
+    t = 0
+    for line in data.split(b"\n")[:-1]:
+        t0, t = t, t + len(line) + 1
+        if not line or line.startswith(b"#"):
+            continue
+        f = line.split(b"\t")
+        name, beg, end = f[0].decode(), int(f[1]), int(f[2])
+        if name not in per_ref:
+            names.append(name); per_ref[name] = dict(bins={}, lin={}, beg=voff(t0), end=None, n=0)
+        r = per_ref[name]
+        b = _reg2bin(beg, max(end, beg + 1))
+        ch = r["bins"].setdefault(b, [])
+        if ch and ch[-1][1] >> 16 == voff(t0) >> 16:      # htslib merges chunks that touch the same block
+            ch[-1][1] = voff(t)
+        else:
+            ch.append([voff(t0), voff(t)])
+        for w in range(beg >> 14, ((max(end, beg + 1) - 1) >> 14) + 1):
+            r["lin"].setdefault(w, voff(t0))
+        r["end"], r["n"] = voff(t), r["n"] + 1
+    out = bytearray(b"TBI\x01" + struct.pack("<8i", len(names), 0x10000, 1, 2, 3, ord("#"), 0, sum(len(n) + 1 for n in names)))
+    for n in names:
+        out += n.encode() + b"\0"
+    for n in names:
+        r = per_ref[n]
+        out += struct.pack("<i", len(r["bins"]) + 1)
+        out += struct.pack("<IiQQQQ", 37450, 2, r["beg"], r["end"], r["n"], 0)
+        for b, ch in r["bins"].items():
+            out += struct.pack("<Ii", b, len(ch)) + b"".join(struct.pack("<QQ", a, e) for a, e in ch)
+        n_intv = max(r["lin"]) + 1
+        lin, last = [], 0
+        for w in range(n_intv):
+            last = r["lin"].get(w, last); lin.append(last)
+        out += struct.pack("<i", n_intv) + struct.pack(f"<{n_intv}Q", *lin)
+    out += struct.pack("<Q", 0)
+    with open(str(path) + ".tbi", "wb") as fh:       # BGZF: one data block + the EOF block
+        for chunk in (bytes(out), b""):
+            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            payload = c.compress(chunk) + c.flush()
+            bsize = 12 + 6 + len(payload) + 8 - 1
+            fh.write(struct.pack("<BBBBIBBH", 31, 139, 8, 4, 0, 0, 255, 6) + b"BC" + struct.pack("<HH", 2, bsize))
+            fh.write(payload + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    return str(path)

@@ -451,3 +451,75 @@ def test_native_text_outputs(tmp_path):
     with GzipTextWriter(empty):
         pass
     assert gzip.open(empty, "rb").read() == b""
+
+
+def test_tabix_index_and_lazy_contig_decode(tmp_path, golden, monkeypatch):
+    """.tbi reader + per-contig decode through the index (io/tabix.py, ftk_fragfile_open_slice):
+    the htslib-made fixture index, and synthetic multi-contig BGZF files indexed by the test helper
+    (which reproduces htslib's index bytes on the fixture) - lazy columns == whole-file decode."""
+    import struct
+    from helpers import write_bgzf_indexed
+    from finaletoolkit_b200.io import fragments
+    from finaletoolkit_b200.io.tabix import read_tbi
+    g = golden("fixture17")
+    # 1. the reference's own files, byte for byte
+    for stem, key in (("fx.frag.gz", "frag_gz"), ("fx.bed.gz", "bed_gz")):
+        p = tmp_path / stem
+        p.write_bytes(g[key + "_file"].tobytes()); (tmp_path / (stem + ".tbi")).write_bytes(g[key + "_tbi_file"].tobytes())
+        idx = read_tbi(str(p) + ".tbi")
+        assert idx.names == ["12"] and (idx.col_seq, idx.col_beg, idx.col_end, idx.meta) == (1, 2, 3, "#")
+        cb, ub, ce, ue = idx.ranges["12"]
+        assert (cb, ub, ue) == (0, 0, 0) and ce == p.stat().st_size - 28          # up to the BGZF EOF block
+        monkeypatch.setenv("FTK_LAZY_MIN_BYTES", "0")
+        fragments._CACHE.clear()
+        import warnings as w
+        with w.catch_warnings():
+            w.simplefilter("ignore")
+            lazy = fragments.load_fragments(str(p))
+        assert lazy._loader is not None and lazy.contigs == ["12"] and lazy.columns == {}
+        st, sp, mq, sd = lazy.host("12")
+        assert np.array_equal(st, g["start"]) and np.array_equal(sp, g["stop"]) and np.array_equal(mq, g["mapq"]) \
+            and np.array_equal(sd, g["strand"])
+        assert lazy.n_fragments("nope") == 0 and lazy.n_fragments() == 17
+        # the test indexer writes the same index htslib wrote (modulo its own compressed block size)
+        import gzip
+        mine = write_bgzf_indexed(tmp_path / ("re_" + stem), gzip.open(p, "rt").read(), block=65280)
+        a = gzip.open(mine + ".tbi", "rb").read(); b = gzip.open(str(p) + ".tbi", "rb").read()
+        own_end = (tmp_path / ("re_" + stem)).stat().st_size - 28
+        assert a.replace(struct.pack("<Q", own_end << 16), struct.pack("<Q", ce << 16)) == b
+    assert read_tbi(str(tmp_path / "fx.frag.gz")) is None                            # not an index
+    # 2. three contigs, lines straddling 4 KiB blocks, a one-row contig in the middle, comment lines
+    rng = np.random.default_rng(5)
+    rows, cols = ["#made by the test"], {}
+    for contig, n in (("chr1", 30_000), ("chrTiny", 1), ("chrX_random", 12_345)):
+        st = np.sort(rng.integers(0, 50_000_000, n)); sp = st + rng.integers(30, 600, n)
+        mq = rng.integers(0, 61, n); sd = rng.integers(0, 2, n)
+        cols[contig] = (st.astype(np.int32), sp.astype(np.int32), mq.astype(np.uint8), sd.astype(np.uint8))
+        rows += [f"{contig}\t{a}\t{b}\t{q}\t{'+' if s else '-'}" for a, b, q, s in zip(st.tolist(), sp.tolist(), mq.tolist(), sd.tolist())]
+    path = write_bgzf_indexed(tmp_path / "multi.frag.gz", "\n".join(rows) + "\n", block=4096)
+    monkeypatch.setenv("FTK_LAZY_MIN_BYTES", str(10 ** 12))
+    fragments._CACHE.clear()
+    whole = fragments.load_fragments(path)
+    assert whole._loader is None and whole.contigs == list(cols)
+    monkeypatch.setenv("FTK_LAZY_MIN_BYTES", "0")
+    fragments._CACHE.clear()
+    lazy = fragments.load_fragments(path)
+    assert lazy._loader is not None and lazy.contigs == list(cols) and lazy.columns == {}
+    assert lazy.n_fragments("chrTiny") == 1 and list(lazy.columns) == ["chrTiny"]    # only what was asked for
+    for contig in ("chrX_random", "chr1", "chrTiny"):
+        for x, y, z in zip(lazy.host(contig), whole.host(contig), cols[contig]):
+            assert np.array_equal(x, y) and np.array_equal(x, z), contig
+    assert lazy.n_fragments() == sum(len(c[0]) for c in cols.values())
+    # 3. BED6 layout through the lazy path (mapq = column 5, strand = column 6) + its UserWarning
+    bed_rows = [f"c\t{a}\t{a + 100}\tname\t{q}\t{'+-'[a & 1]}" for a, q in zip(range(0, 90_000, 3), rng.integers(0, 61, 30_000).tolist())]
+    bed = write_bgzf_indexed(tmp_path / "multi.bed.gz", "\n".join(bed_rows) + "\n", block=8192)
+    fragments._CACHE.clear()
+    with pytest.warns(UserWarning, match="BED6"):
+        t6 = fragments.load_fragments(bed)
+    st, sp, mq, sd = t6.host("c")
+    assert st.size == 30_000 and np.array_equal(st, np.arange(0, 90_000, 3)) and np.array_equal(sd, 1 - (st & 1))
+    # a placeholder .tbi (what the other tests write) falls back to the whole-file decode
+    fragments._CACHE.clear()
+    open(path + ".tbi", "wb").close()
+    assert fragments.load_fragments(path)._loader is None
+    fragments._CACHE.clear()
