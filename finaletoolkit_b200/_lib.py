@@ -61,6 +61,12 @@ SYMBOLS = {
                                        c_int32, c_int32, c_int32, _P, _P, _P]),
     "ftk_fragfile_open": (c_void_p, [c_char_p, c_int32, _i32p]),
     "ftk_fragfile_open_slice": (c_void_p, [c_char_p, c_int64, c_int32, c_int64, c_int32, c_int32, c_int32, _i32p]),
+    "ftk_bamfile_open": (c_void_p, [c_char_p, c_int32, _i32p]),
+    "ftk_bamfile_fragments": (c_void_p, [c_void_p]),
+    "ftk_bamfile_n_refs": (c_int32, [c_void_p]),
+    "ftk_bamfile_ref_name": (c_char_p, [c_void_p, c_int32]),
+    "ftk_bamfile_ref_length": (c_int64, [c_void_p, c_int32]),
+    "ftk_bamfile_close": (None, [c_void_p]),
     "ftk_fragfile_is_bed6": (c_int32, [c_void_p]),
     "ftk_fragfile_skipped": (c_int64, [c_void_p]),
     "ftk_fragfile_n_contigs": (c_int32, [c_void_p]),

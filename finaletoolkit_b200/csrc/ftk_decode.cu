@@ -341,6 +341,186 @@ extern "C" void *ftk_fragfile_open_slice(const char *path, int64_t coffset_beg, 
     return ff;
 }
 
+// ---------------------------------------------------------------- BAM -> fragment columns
+// The reference reconstructs fragments from BAM reads in AlignmentWrapper._fetch_sam
+// (io/alignment.py:242-268) behind the flag filter of _read_is_low_quality (:60-71, the mapq test is
+// left to the kernels): keep reads that are paired, proper pair, mapped with a mapped mate, primary,
+// not duplicate / QC-fail / supplementary and not read2; tlen > 0 -> [pos, pos + tlen), tlen < 0 ->
+// [reference_end + tlen, reference_end), tlen == 0 dropped; mapq and strand are the read's own.
+// The file is streamed: BGZF blocks are read in batches, inflated in parallel, and the BAM records
+// (which ignore block boundaries) are walked in order with the unfinished tail carried over.
+namespace {
+struct BamState {
+    bool header_done = false;
+    std::vector<std::string> ref_names;
+    std::vector<int64_t> ref_lens;
+    std::vector<int> ref_to_col;       // refID -> index in FragFile::contigs, -1 = not seen yet
+};
+
+inline int32_t rd_i32(const unsigned char *p) { int32_t v; memcpy(&v, p, 4); return v; }
+inline uint32_t rd_u32(const unsigned char *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline uint16_t rd_u16(const unsigned char *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+// Consume as much of [p, end) as is complete; returns the first unconsumed byte, or nullptr on a
+// malformed stream.
+const unsigned char *bam_consume(const unsigned char *p, const unsigned char *end, BamState &st, FragFile &ff) {
+    if (!st.header_done) {
+        if (end - p < 12) return p;
+        if (memcmp(p, "BAM\1", 4) != 0) return nullptr;
+        const int64_t l_text = rd_i32(p + 4);
+        if (l_text < 0) return nullptr;
+        const unsigned char *q = p + 8 + l_text;
+        if (end - p < 12 + l_text) return p;
+        const int64_t n_ref = rd_i32(q);
+        if (n_ref < 0) return nullptr;
+        q += 4;
+        std::vector<std::string> names;
+        std::vector<int64_t> lens;
+        for (int64_t r = 0; r < n_ref; ++r) {
+            if (end - q < 4) return p;
+            const int64_t l_name = rd_i32(q);
+            if (l_name < 1) return nullptr;
+            if (end - q < 8 + l_name) return p;
+            names.emplace_back(reinterpret_cast<const char *>(q + 4), (size_t)l_name - 1);
+            lens.push_back(rd_i32(q + 4 + l_name));
+            q += 8 + l_name;
+        }
+        st.ref_names.swap(names); st.ref_lens.swap(lens);
+        st.ref_to_col.assign((size_t)n_ref, -1);
+        st.header_done = true;
+        p = q;
+    }
+    while (end - p >= 4) {
+        const int64_t bs = rd_i32(p);
+        if (bs < 32) return nullptr;
+        if (end - p < 4 + bs) break;
+        const unsigned char *r = p + 4;
+        const int32_t ref_id = rd_i32(r), pos = rd_i32(r + 4);
+        const unsigned l_read_name = r[8], mapq = r[9];
+        const unsigned n_cigar = rd_u16(r + 12), flag = rd_u16(r + 14);
+        const int32_t tlen = rd_i32(r + 28);
+        p += 4 + bs;
+        // paired, proper pair; not unmapped / mate unmapped / read2 / secondary / QC fail / duplicate / supplementary
+        if ((flag & 0x3u) != 0x3u || (flag & (0x4u | 0x8u | 0x80u | 0x100u | 0x200u | 0x400u | 0x800u))) continue;
+        if (tlen == 0 || ref_id < 0 || (size_t)ref_id >= st.ref_names.size()) continue;
+        int64_t fs, fe;
+        if (tlen > 0) {
+            fs = pos; fe = (int64_t)pos + tlen;
+        } else {
+            if (n_cigar == 0 || 32 + (int64_t)l_read_name + 4 * (int64_t)n_cigar > bs) continue;
+            int64_t ref_end = pos;
+            const unsigned char *c = r + 32 + l_read_name;
+            for (unsigned k = 0; k < n_cigar; ++k) {
+                const uint32_t op = rd_u32(c + 4 * k);
+                const unsigned code = op & 15u;   // M, D, N, =, X consume the reference
+                if (code == 0 || code == 2 || code == 3 || code == 7 || code == 8) ref_end += op >> 4;
+            }
+            fs = ref_end + tlen; fe = ref_end;
+        }
+        if (fs < INT32_MIN || fs > INT32_MAX || fe < INT32_MIN || fe > INT32_MAX) continue;
+        int &col = st.ref_to_col[(size_t)ref_id];
+        if (col < 0) {
+            col = (int)ff.contigs.size();
+            ff.contigs.emplace_back();
+            ff.contigs.back().name = st.ref_names[(size_t)ref_id];
+        }
+        Columns &dst = ff.contigs[(size_t)col];
+        dst.start.push_back((int32_t)fs); dst.stop.push_back((int32_t)fe);
+        dst.mapq.push_back((uint8_t)mapq); dst.strand.push_back((flag & 0x10u) ? 0 : 1);
+    }
+    return p;
+}
+}  // namespace
+
+struct BamFile { FragFile frags; std::vector<std::string> ref_names; std::vector<int64_t> ref_lens; };
+
+extern "C" void *ftk_bamfile_open(const char *path, int32_t n_threads, int32_t *err) {
+    auto fail = [&](int code) -> void * { if (err) *err = code; return nullptr; };
+    if (!path) return fail(FTK_E_INVALID);
+    FILE *fh = fopen(path, "rb");
+    if (!fh) return fail(FTK_E_IO);
+    if (n_threads < 1) n_threads = (int32_t)std::max(1u, std::thread::hardware_concurrency());
+    BamFile *bf = new BamFile();
+    BamState st;
+    std::vector<unsigned char> cbuf, ubuf;           // compressed carry + batch, inflated carry + batch
+    size_t ufill = 0;
+    const size_t kRead = (size_t)64 << 20;
+    bool eof = false, ok = true;
+    while (ok && !eof) {
+        const size_t have = cbuf.size();
+        cbuf.resize(have + kRead);
+        const size_t got = fread(cbuf.data() + have, 1, kRead, fh);
+        cbuf.resize(have + got);
+        eof = got < kRead;
+        // complete BGZF blocks in cbuf
+        std::vector<Block> blocks;
+        size_t p = 0, uoff = 0;
+        while (p + 18 <= cbuf.size()) {
+            if (cbuf[p] != 31 || cbuf[p + 1] != 139 || cbuf[p + 2] != 8 || !(cbuf[p + 3] & 4)) { ok = false; break; }
+            const unsigned xlen = cbuf[p + 10] | (cbuf[p + 11] << 8);
+            size_t q = p + 12;
+            const size_t xend = q + xlen;
+            if (xend > cbuf.size()) break;
+            long bsize = -1;
+            while (q + 4 <= xend) {
+                const unsigned slen = cbuf[q + 2] | (cbuf[q + 3] << 8);
+                if (cbuf[q] == 'B' && cbuf[q + 1] == 'C' && slen == 2) bsize = (cbuf[q + 4] | (cbuf[q + 5] << 8)) + 1;
+                q += 4 + slen;
+            }
+            if (bsize < 0) { ok = false; break; }
+            if (p + (size_t)bsize > cbuf.size()) break;
+            const size_t end = p + (size_t)bsize;
+            const size_t usize = (size_t)cbuf[end - 4] | ((size_t)cbuf[end - 3] << 8) | ((size_t)cbuf[end - 2] << 16) |
+                                 ((size_t)cbuf[end - 1] << 24);
+            blocks.push_back({xend, end - 8 - xend, usize, uoff});
+            uoff += usize;
+            p = end;
+        }
+        if (!ok) break;
+        if (eof && p != cbuf.size()) { ok = false; break; }      // trailing garbage / truncated block
+        ubuf.resize(ufill + uoff);
+        {
+            const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads, blocks.size()));
+            std::vector<std::thread> th;
+            std::vector<int> good((size_t)T, 1);
+            for (int t = 0; t < T; ++t)
+                th.emplace_back([&, t] {
+                    for (size_t i = (size_t)t; i < blocks.size(); i += (size_t)T) {
+                        const Block &b = blocks[i];
+                        if (b.usize && !inflate_raw(cbuf.data() + b.off, b.csize, ubuf.data() + ufill + b.uoff, b.usize))
+                            good[(size_t)t] = 0;
+                    }
+                });
+            for (auto &x : th) x.join();
+            for (int v : good) if (!v) ok = false;
+        }
+        if (!ok) break;
+        cbuf.erase(cbuf.begin(), cbuf.begin() + (ptrdiff_t)p);
+        const unsigned char *base = ubuf.data(), *endp = ubuf.data() + ubuf.size();
+        const unsigned char *next = bam_consume(base, endp, st, bf->frags);
+        if (!next) { ok = false; break; }
+        ufill = (size_t)(endp - next);
+        memmove(ubuf.data(), next, ufill);
+        ubuf.resize(ufill);
+    }
+    fclose(fh);
+    if (!ok || !st.header_done || ufill != 0) { delete bf; return fail(FTK_E_IO); }
+    bf->ref_names = st.ref_names; bf->ref_lens = st.ref_lens;
+    if (err) *err = FTK_OK;
+    return bf;
+}
+extern "C" void *ftk_bamfile_fragments(void *h) { return h ? &static_cast<BamFile *>(h)->frags : nullptr; }
+extern "C" int32_t ftk_bamfile_n_refs(void *h) { return h ? (int32_t)static_cast<BamFile *>(h)->ref_names.size() : 0; }
+extern "C" const char *ftk_bamfile_ref_name(void *h, int32_t i) {
+    BamFile *b = static_cast<BamFile *>(h);
+    return (b && i >= 0 && (size_t)i < b->ref_names.size()) ? b->ref_names[(size_t)i].c_str() : "";
+}
+extern "C" int64_t ftk_bamfile_ref_length(void *h, int32_t i) {
+    BamFile *b = static_cast<BamFile *>(h);
+    return (b && i >= 0 && (size_t)i < b->ref_lens.size()) ? b->ref_lens[(size_t)i] : -1;
+}
+extern "C" void ftk_bamfile_close(void *h) { delete static_cast<BamFile *>(h); }
+
 extern "C" int32_t ftk_fragfile_is_bed6(void *h) { return h ? static_cast<FragFile *>(h)->bed6 : 0; }
 extern "C" int64_t ftk_fragfile_skipped(void *h) { return h ? static_cast<FragFile *>(h)->skipped : 0; }
 extern "C" int32_t ftk_fragfile_n_contigs(void *h) { return h ? (int32_t)static_cast<FragFile *>(h)->contigs.size() : 0; }

@@ -18,10 +18,12 @@ Formats (io/alignment.py:143-156, 158-203, 270-302):
 Whole contigs are decoded, so small files are inflated and parsed in one parallel pass; for a
 large BGZF file with a real ``.tbi`` the index's per-contig virtual-offset ranges are used to
 decode a contig on first use and nothing else (``io/tabix.py``, ``ftk_fragfile_open_slice``).
-BAM/CRAM need htslib: they are
-read through ``pysam`` when it is importable (same read filter as
-io/alignment.py:60-71, 242-268) and rejected with ``UnsupportedFormatError``
-otherwise.  The mapq filter is NOT applied at load time - it is a kernel predicate.
+BAM is decoded natively (``ftk_bamfile_open``: streamed BGZF inflate + record walk with the read
+filter and fragment reconstruction of io/alignment.py:60-71, 242-268); CRAM / SAM text need htslib
+and go through ``pysam`` when it is importable, ``UnsupportedFormatError`` otherwise.  For BAM input
+the reference selects READS overlapping the query region and then builds fragments; here, as for
+fragment files, whole contigs are loaded and the kernels select FRAGMENTS overlapping the region, so
+a fragment whose read 1 lies outside the query region is kept where the reference would drop it.  The mapq filter is NOT applied at load time - it is a kernel predicate.
 """
 from __future__ import annotations
 
@@ -271,7 +273,35 @@ def _parse_text_fast(path: str) -> Dict[str, Columns] | None:
         return None
 
 
+def _load_bam_native(path: str) -> "FragmentTable | None":
+    """BAM through the C ABI's streamed decoder (``ftk_bamfile_open``): same read filter and fragment
+    reconstruction as the reference (io/alignment.py:60-71,242-268), no htslib.  None = unavailable."""
+    import ctypes
+    try:
+        from .._lib import lib
+        L = lib()
+    except Exception:  # noqa: BLE001
+        return None
+    err = ctypes.c_int32(0)
+    h = L.ftk_bamfile_open(path.encode(), 0, ctypes.byref(err))
+    if not h:
+        return None
+    try:
+        cols = _handle_columns(L, L.ftk_bamfile_fragments(h))
+        lengths = {L.ftk_bamfile_ref_name(h, i).decode(): int(L.ftk_bamfile_ref_length(h, i))
+                   for i in range(L.ftk_bamfile_n_refs(h))}
+    finally:
+        L.ftk_bamfile_close(h)
+    if cols is None:
+        return None
+    return FragmentTable(cols, source=path, is_sam=True, contig_lengths=lengths)
+
+
 def _load_sam(path: str, reference_file=None) -> FragmentTable:
+    if path.lower().endswith(".bam"):
+        tab = _load_bam_native(path)
+        if tab is not None:
+            return tab
     try:
         import pysam
     except ImportError as e:

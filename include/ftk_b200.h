@@ -304,6 +304,17 @@ void *ftk_fragfile_open(const char *path, int32_t n_threads, int32_t *err);
 void *ftk_fragfile_open_slice(const char *path, int64_t coffset_beg, int32_t uoffset_beg,
                               int64_t coffset_end, int32_t uoffset_end, int32_t bed6,
                               int32_t n_threads, int32_t *err);
+/* BAM -> fragment columns: AlignmentWrapper._fetch_sam + _read_is_low_quality (io/alignment.py:60-71,
+ * 242-268; the mapq test stays a kernel predicate) on a streamed, multi-threaded BGZF inflate - no
+ * htslib.  ftk_bamfile_fragments returns a handle for the ftk_fragfile_* accessors (owned by the
+ * BAM handle: do not close it separately); ftk_bamfile_n_refs / _ref_name / _ref_length expose the
+ * header's @SQ table (AlignmentWrapper._chroms, :126-127). */
+void *ftk_bamfile_open(const char *path, int32_t n_threads, int32_t *err);
+void *ftk_bamfile_fragments(void *bam_handle);
+int32_t ftk_bamfile_n_refs(void *bam_handle);
+const char *ftk_bamfile_ref_name(void *bam_handle, int32_t i);
+int64_t ftk_bamfile_ref_length(void *bam_handle, int32_t i);
+void ftk_bamfile_close(void *bam_handle);
 int32_t ftk_fragfile_is_bed6(void *handle);
 int64_t ftk_fragfile_skipped(void *handle);
 int32_t ftk_fragfile_n_contigs(void *handle);

@@ -12,8 +12,9 @@ Only what the reference's hot path touches is modelled:
   (``rec.stop > start and rec.start < end``), ``.close()``.
   (reference call site: src/finaletoolkit/io/alignment.py:270-302)
 * ``asTuple``    - parser marker.
-* ``AlignmentFile`` / ``AlignedSegment`` / ``FastaFile`` - class names for the
-  reference's ``isinstance`` checks; not functional.
+* ``AlignmentFile`` / ``AlignedSegment`` - a pure-Python BAM record reader exposing the fields
+  the reference's read filter and fragment reconstruction use (io/alignment.py:60-71,242-268).
+* ``FastaFile`` - class name for the reference's ``isinstance`` checks; not functional.
 """
 from __future__ import annotations
 
@@ -21,17 +22,77 @@ import bisect
 import gzip
 
 
-class AlignedSegment:  # pragma: no cover - name only
-    pass
+class AlignedSegment:
+    """The fields of one BAM record that io/alignment.py:60-71,242-268 looks at, with pysam's meanings."""
+
+    def __init__(self, ref_name, pos, mapq, flag, tlen, cigar):
+        self.reference_name, self.reference_start, self.mapping_quality = ref_name, pos, mapq
+        self.flag, self.template_length, self._cigar = flag, tlen, cigar
+        self.is_paired = bool(flag & 0x1); self.is_proper_pair = bool(flag & 0x2)
+        self.is_unmapped = bool(flag & 0x4); self.mate_is_unmapped = bool(flag & 0x8)
+        self.is_reverse = bool(flag & 0x10); self.is_forward = not self.is_reverse
+        self.is_read1 = bool(flag & 0x40); self.is_read2 = bool(flag & 0x80)
+        self.is_secondary = bool(flag & 0x100); self.is_qcfail = bool(flag & 0x200)
+        self.is_duplicate = bool(flag & 0x400); self.is_supplementary = bool(flag & 0x800)
+
+    @property
+    def reference_end(self):   # pysam: aligned end (exclusive); None without an alignment
+        if self.is_unmapped or not self._cigar:
+            return None
+        return self.reference_start + sum(n for op, n in self._cigar if op in (0, 2, 3, 7, 8))
 
 
 class AlignmentHeader:  # pragma: no cover - name only
     pass
 
 
-class AlignmentFile:  # pragma: no cover - name only
-    def __init__(self, *a, **k):
-        raise NotImplementedError("fake pysam has no BAM/CRAM reader")
+class AlignmentFile:
+    """Minimal BAM reader (whole file, pure Python): header names / lengths and ``fetch`` in file order
+    with htslib's region rule (read overlaps [start, stop)).  CRAM / SAM text are not modelled."""
+
+    def __init__(self, path, mode="r", *_, **__):
+        import struct
+        self.filename = str(path)
+        if not self.filename.lower().endswith(".bam"):
+            raise NotImplementedError("fake pysam reads BAM only")
+        raw = gzip.open(self.filename, "rb").read()
+        if raw[:4] != b"BAM\x01":
+            raise ValueError("not a BAM file")
+        (l_text,) = struct.unpack_from("<i", raw, 4); off = 8 + l_text
+        (n_ref,) = struct.unpack_from("<i", raw, off); off += 4
+        self.references, self.lengths = [], []
+        for _ in range(n_ref):
+            (ln,) = struct.unpack_from("<i", raw, off)
+            self.references.append(raw[off + 4: off + 4 + ln - 1].decode())
+            self.lengths.append(struct.unpack_from("<i", raw, off + 4 + ln)[0]); off += 8 + ln
+        self._reads = []
+        while off < len(raw):
+            (bs,) = struct.unpack_from("<i", raw, off)
+            ref_id, pos, l_rn, mapq, _bin, n_cig, flag, _l_seq, _nref, _npos, tlen = struct.unpack_from("<iiBBHHHiiii", raw, off + 4)
+            cig = [(c & 15, c >> 4) for c in struct.unpack_from(f"<{n_cig}I", raw, off + 36 + l_rn)]
+            self._reads.append(AlignedSegment(self.references[ref_id] if ref_id >= 0 else None, pos, mapq, flag, tlen, cig))
+            off += 4 + bs
+
+    def fetch(self, contig=None, start=None, stop=None, **_):
+        for r in self._reads:
+            if r.reference_name is None:
+                continue   # unplaced reads are not part of an indexed fetch
+            if contig is not None:
+                if r.reference_name != contig:
+                    continue
+                end = r.reference_end if r.reference_end is not None else r.reference_start + 1
+                if (stop is not None and r.reference_start >= stop) or (start is not None and end <= start):
+                    continue
+            yield r
+
+    def close(self):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 class FastaFile:  # pragma: no cover - name only

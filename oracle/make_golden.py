@@ -87,7 +87,21 @@ def fixture17():
     for key, path in (("frag_gz_file", frag), ("frag_gz_tbi_file", frag + ".tbi"),
                       ("bed_gz_file", bed6), ("bed_gz_tbi_file", bed6 + ".tbi")):
         arrays[key] = np.frombuffer(open(path, "rb").read(), np.uint8)
+    # the same 17 fragments as a BAM (tests/data/12.3444.b37.bam): what the reference's own
+    # AlignmentWrapper._fetch_sam yields from it (read filter + fragment reconstruction)
+    bam = os.path.join(DATA, "12.3444.b37.bam")
+    arrays["bam_file"] = np.frombuffer(open(bam, "rb").read(), np.uint8)
+    from finaletoolkit.io.alignment import AlignmentWrapper
+    with AlignmentWrapper(bam, quality_threshold=0) as wrapper:
+        frs = list(wrapper.fetch())
+        bam_chroms = dict(wrapper._chroms)
+    arrays["bam_start"] = np.array([f.start for f in frs], np.int64); arrays["bam_stop"] = np.array([f.stop for f in frs], np.int64)
+    arrays["bam_mapq"] = np.array([f.mapq for f in frs], np.int64); arrays["bam_strand"] = np.array([f.is_forward for f in frs], np.uint8)
+    arrays["bam_wps"] = F.wps(bam, "12", 34442500, 34447500, 133851895)["wps"].astype(np.int64)
     m = {"contig": "12", "chrom_size": 133851895,
+         "bam_contigs": sorted({f.contig for f in frs}), "bam_n_refs": len(bam_chroms), "bam_ref_12": bam_chroms["12"],
+         "bam_single_coverage": F.single_coverage(bam, "12", 34442500, 34447500, quality_threshold=30),
+         "bam_frag_length_bins": [np.asarray(x).tolist() for x in F.frag_length_bins(bam, "12", 34442500, 34447500, bin_size=10)],
          "frag_gz_text": read_gz_text(frag), "frag_bed_gz_text": read_gz_text(bed6),
          "intervals_bed": open(ivl).read(), "intervals_overlapped_bed": open(ivl_ov).read(),
          "chrom_sizes": open(cs).read()}

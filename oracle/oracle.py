@@ -350,6 +350,46 @@ def delfi_counts(fr: Frags, seq_ascii, start: int, stop: int, blacklist=None, ga
     return tuple(int(x) for x in out)
 
 
+# ---------------------------------------------------------- BAM -> fragments
+def bam_fragments(bam_bytes: bytes):
+    """io/alignment.py:60-71 (_read_is_low_quality without the mapq test) + :242-268 (_fetch_sam) on the
+    records of an uncompressed-by-gzip BAM: returns (references [(name, length)], rows) with rows =
+    (contig, start, stop, mapq, is_forward) in file order."""
+    import gzip
+    import struct
+    raw = gzip.decompress(bam_bytes)
+    assert raw[:4] == b"BAM\x01"
+    (l_text,) = struct.unpack_from("<i", raw, 4); off = 8 + l_text
+    (n_ref,) = struct.unpack_from("<i", raw, off); off += 4
+    refs = []
+    for _ in range(n_ref):
+        (ln,) = struct.unpack_from("<i", raw, off)
+        refs.append((raw[off + 4: off + 4 + ln - 1].decode(), struct.unpack_from("<i", raw, off + 4 + ln)[0])); off += 8 + ln
+    rows = []
+    while off < len(raw):
+        (bs,) = struct.unpack_from("<i", raw, off)
+        ref_id, pos, l_rn, mapq, _b, n_cig, flag, _ls, _nr, _np, tlen = struct.unpack_from("<iiBBHHHiiii", raw, off + 4)
+        cig = struct.unpack_from(f"<{n_cig}I", raw, off + 36 + l_rn)
+        off += 4 + bs
+        unmapped, secondary, paired, mate_unmapped = flag & 0x4, flag & 0x100, flag & 0x1, flag & 0x8
+        dup, qcfail, supp, proper, read2 = flag & 0x400, flag & 0x200, flag & 0x800, flag & 0x2, flag & 0x80
+        if unmapped or secondary or not paired or mate_unmapped or dup or qcfail or supp or not proper:   # :60-71
+            continue
+        if read2:                                                                                          # :248
+            continue
+        if tlen > 0:                                                                                       # :252-260
+            f_start, f_stop = pos, pos + tlen
+        elif tlen < 0:
+            if not cig:
+                continue   # pysam: reference_end is None
+            ref_end = pos + sum(c >> 4 for c in cig if (c & 15) in (0, 2, 3, 7, 8))
+            f_start, f_stop = ref_end + tlen, ref_end
+        else:
+            continue
+        rows.append((refs[ref_id][0], f_start, f_stop, mapq, not (flag & 0x10)))
+    return refs, rows
+
+
 # ------------------------------------------------------------------ agg_bw
 def agg_bw_core(signals, strands, median_window_size=1, mean=False):
     """utils/_agg_bw.py:84-126: ``signals[i]`` = pyBigWig ``values`` of interval i (float32, NaN where

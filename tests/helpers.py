@@ -202,3 +202,34 @@ def write_bgzf_indexed(path, text: str, block=30000):
             fh.write(struct.pack("<BBBBIBBH", 31, 139, 8, 4, 0, 0, 255, 6) + b"BC" + struct.pack("<HH", 2, bsize))
             fh.write(payload + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
     return str(path)
+
+
+def write_bam(path, refs, records, block=4000):
+    """Minimal BAM writer for tests: ``refs`` = [(name, length)], ``records`` = dicts with ref (index or -1),
+    pos, mapq, flag, tlen and cigar [(op, len)]; BGZF blocks of ``block`` bytes so records straddle them.
+    Also writes a placeholder .bai (the loader only checks that it exists)."""
+    import zlib
+    text = b"@HD\tVN:1.6\tSO:coordinate\n" + b"".join(f"@SQ\tSN:{n}\tLN:{ln}\n".encode() for n, ln in refs)
+    out = bytearray(b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs)))
+    for n, ln in refs:
+        out += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", ln)
+    for k, r in enumerate(records):
+        name = f"r{k}".encode() + b"\0"
+        cig = r.get("cigar", [(0, 50)])
+        l_seq = sum(ln for op, ln in cig if op in (0, 1, 4, 7, 8))
+        body = struct.pack("<iiBBHHHiiii", r["ref"], r["pos"], len(name), r["mapq"], 4680, len(cig), r["flag"], l_seq,
+                           r["ref"], r["pos"] + 100, r["tlen"])
+        body += name + b"".join(struct.pack("<I", (ln << 4) | op) for op, ln in cig)
+        body += bytes((l_seq + 1) // 2) + bytes([30]) * l_seq + b"NMC\x00"
+        out += struct.pack("<i", len(body)) + body
+    data = bytes(out)
+    with open(path, "wb") as fh:
+        for i in list(range(0, len(data), block)) + [None]:
+            chunk = b"" if i is None else data[i:i + block]
+            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            payload = c.compress(chunk) + c.flush()
+            bsize = 12 + 6 + len(payload) + 8 - 1
+            fh.write(struct.pack("<BBBBIBBH", 31, 139, 8, 4, 0, 0, 255, 6) + b"BC" + struct.pack("<HH", 2, bsize))
+            fh.write(payload + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    open(str(path) + ".bai", "wb").close()
+    return str(path)

@@ -254,3 +254,19 @@ def test_adjust_wps(fx, syn, manifest, golden, tmp_path):
         F.adjust_wps(bw, str(tmp_path / "s0.bed"), str(tmp_path / "e.bw"), syn["cs"], median_window_size=100000)
     with pytest.raises(ValueError):
         F.adjust_wps(bw, "intervals.txt", str(tmp_path / "e.bw"), syn["cs"])
+
+
+def test_bam_input(tmp_path, manifest, golden):
+    """The reference's own BAM fixture (tests/data/12.3444.b37.bam) through the native BAM decoder:
+    wps / single_coverage / frag_length_bins equal what the reference computes from the BAM."""
+    import finaletoolkit_b200 as F
+    g = golden("fixture17"); m = manifest["fixture17"]
+    bam = str(tmp_path / "12.3444.b37.bam")
+    open(bam, "wb").write(g["bam_file"].tobytes()); open(bam + ".bai", "wb").close()
+    r = F.wps(bam, "12", 34442500, 34447500, 133851895)
+    assert np.array_equal(r["wps"].astype(np.int64), g["bam_wps"]) and r["wps"].any()
+    assert list(F.single_coverage(bam, "12", 34442500, 34447500, quality_threshold=30)) == m["bam_single_coverage"]
+    bins, counts = F.frag_length_bins(bam, "12", 34442500, 34447500, bin_size=10)
+    assert [np.asarray(bins).tolist(), np.asarray(counts).tolist()] == m["bam_frag_length_bins"]
+    got = [list(x) for x in F.frag_generator(bam, "12", quality_threshold=0)]
+    assert [x[1] for x in got] == np.sort(g["bam_start"]).tolist() and len(got) == 17

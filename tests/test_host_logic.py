@@ -523,3 +523,69 @@ def test_tabix_index_and_lazy_contig_decode(tmp_path, golden, monkeypatch):
     open(path + ".tbi", "wb").close()
     assert fragments.load_fragments(path)._loader is None
     fragments._CACHE.clear()
+
+
+def test_native_bam_decoder(tmp_path, manifest, golden):
+    """ftk_bamfile_open == the reference's _fetch_sam on its own BAM fixture, and == the oracle's record
+    walk on synthetic BAMs covering every filtered flag, tlen sign, CIGAR op and block-straddling records."""
+    from helpers import write_bam
+    from finaletoolkit_b200.io import fragments
+    g = golden("fixture17"); m = manifest["fixture17"]
+    # the oracle restatement is pinned on what the reference yields from tests/data/12.3444.b37.bam
+    refs, rows = O.bam_fragments(g["bam_file"].tobytes())
+    assert len(refs) == m["bam_n_refs"] and dict(refs)["12"] == m["bam_ref_12"]
+    assert [r[1] for r in rows] == g["bam_start"].tolist() and [r[2] for r in rows] == g["bam_stop"].tolist()
+    assert [r[3] for r in rows] == g["bam_mapq"].tolist() and [int(r[4]) for r in rows] == g["bam_strand"].tolist()
+    bam = tmp_path / "fx.bam"; bam.write_bytes(g["bam_file"].tobytes()); (tmp_path / "fx.bam.bai").write_bytes(b"")
+    fragments._CACHE.clear()
+    tab = fragments.load_fragments(str(bam))
+    assert tab.is_sam and tab.contigs == m["bam_contigs"] and len(tab.contig_lengths) == m["bam_n_refs"]
+    assert tab.contig_lengths["12"] == m["bam_ref_12"]
+    st, sp, mq, sd = tab.host("12")
+    order = np.argsort(g["bam_start"], kind="stable")          # the table is start-sorted, file order kept among ties
+    assert np.array_equal(st, g["bam_start"][order]) and np.array_equal(sp, g["bam_stop"][order])
+    assert np.array_equal(mq, g["bam_mapq"][order]) and np.array_equal(sd, g["bam_strand"][order])
+    # same coordinates and strands as the fragment file made from this BAM (its mapq column is the pair's)
+    assert np.array_equal(st, g["start"]) and np.array_equal(sp, g["stop"]) and np.array_equal(sd, g["strand"])
+    # synthetic: 3 references, ~6000 reads, every flag bit of the filter, both tlen signs, all CIGAR ops
+    rng = np.random.default_rng(3)
+    refs = [("chrA", 5_000_000), ("chrB", 900_000), ("chrEmpty", 1000)]
+    good = 0x1 | 0x2 | 0x40
+    recs = []
+    for ref, n in ((0, 4000), (1, 2000)):
+        pos = np.sort(rng.integers(0, refs[ref][1] - 1000, n))
+        for p in pos.tolist():
+            flag = good | (0x10 if rng.random() < 0.5 else 0)
+            u = rng.random()
+            if u < 0.30:
+                flag ^= int(rng.choice([0x1, 0x2, 0x4, 0x8, 0x100, 0x200, 0x400, 0x800]))   # one filter bit flipped
+            elif u < 0.40:
+                flag = (flag & ~0x40) | 0x80                                                 # read 2
+            tlen = int(rng.choice([0, 1, -1])) * int(rng.integers(30, 600))
+            ops = [(4, 5)] if rng.random() < 0.3 else []
+            ops += [(0, int(rng.integers(20, 80)))]
+            if rng.random() < 0.5:
+                ops += [(int(rng.choice([1, 2, 3, 7, 8])), int(rng.integers(1, 30))), (0, int(rng.integers(5, 40)))]
+            if rng.random() < 0.2:
+                ops += [(5, 3)]
+            recs.append(dict(ref=ref, pos=p, mapq=int(rng.integers(0, 61)), flag=flag, tlen=tlen, cigar=ops))
+    recs.append(dict(ref=-1, pos=-1, mapq=0, flag=0x4 | 0x1, tlen=0, cigar=[]))              # unplaced read at the end
+    path = write_bam(tmp_path / "syn.bam", refs, recs, block=3000)
+    _, exp = O.bam_fragments(open(path, "rb").read())
+    assert 1500 < len(exp) < len(recs)
+    fragments._CACHE.clear()
+    tab = fragments.load_fragments(path)
+    assert tab.contigs == ["chrA", "chrB"] and tab.contig_lengths == dict(refs)
+    for contig in tab.contigs:
+        rows = [r for r in exp if r[0] == contig]
+        order = np.argsort(np.array([r[1] for r in rows]), kind="stable")
+        st, sp, mq, sd = tab.host(contig)
+        assert st.tolist() == [rows[i][1] for i in order] and sp.tolist() == [rows[i][2] for i in order]
+        assert mq.tolist() == [rows[i][3] for i in order] and sd.tolist() == [int(rows[i][4]) for i in order]
+    # a truncated file is an I/O error for the native decoder; the loader then needs pysam and says so
+    cut = tmp_path / "cut.bam"; cut.write_bytes(open(path, "rb").read()[:5000]); (tmp_path / "cut.bam.bai").write_bytes(b"")
+    from finaletoolkit_b200.exceptions import UnsupportedFormatError
+    fragments._CACHE.clear()
+    with pytest.raises(UnsupportedFormatError):
+        fragments.load_fragments(str(cut))
+    fragments._CACHE.clear()
