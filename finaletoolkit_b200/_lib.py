@@ -29,6 +29,9 @@ SYMBOLS = {
     "ftk_abi_version": (c_int, []),
     "ftk_error_string": (c_char_p, [c_int]),
     "ftk_last_cuda_error": (c_char_p, []),
+    "ftk_pack_fragments_host": (c_int64, [_i32p, _i32p, _u8p, _u8p, c_int64, c_int32, _u32p, _i32p,
+                                          _i32p, _i32p, _u8p, _u8p, c_int64]),
+    "ftk_unpack_fragments": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "ftk_wps_plan_tiles": (c_int64, [_i64p, _i64p, _i64p, c_int64, c_int64, c_int32,
                                      _i32p, _i32p, _i32p, _i32p, _i64p]),
     "ftk_wps_tile_ranges": (c_int, [_P, c_int64, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
@@ -38,6 +41,9 @@ SYMBOLS = {
                                   c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "ftk_wps_tiles_i8": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int64,
                                  c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
+    "ftk_wps_cov_tiles": (c_int, [_P, _P, _P, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_int64,
+                                  c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                  _P, c_int32, _P, _P, _P, _P, _P]),
     "ftk_interval_hist_u64": (c_int, [_P, _P, _P, c_int64, c_int32, _P, _P, c_int64,
                                       c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                       _P, _P, _P, _P, _P]),

@@ -33,15 +33,16 @@ static_assert(FTK_WPS_TILE < kWpsCap, "one guard slot for odd windows");
 __global__ void wps_tile_ranges_kernel(const int32_t *__restrict__ frag_start, int64_t n_frag,
                                        const int32_t *__restrict__ tile_p0,
                                        const int32_t *__restrict__ tile_len, int64_t n_tiles,
-                                       int a, int b, int max_len, int64_t *__restrict__ ranges) {
+                                       int left_reach, int b, int64_t *__restrict__ ranges) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * n_tiles) return;
     int64_t tile = t >> 1;
     int64_t p0 = tile_p0[tile];
     int64_t key;
     if ((t & 1) == 0) {
-        // last event of a fragment sits at fe+a+1 <= fs+max_len+a+1; it must be > g0 >= p0-1
-        key = p0 - 1 - (int64_t)a - (int64_t)max_len;
+        // a fragment starting more than left_reach before p0 - 1 cannot matter to the tile
+        // (WPS: its last event sits at fe+a+1 <= fs+max_len+a+1 and must be > g0 >= p0-1)
+        key = p0 - 1 - (int64_t)left_reach;
     } else {
         // first event sits at fs-b; it must be < p0+len
         key = p0 + (int64_t)tile_len[tile] + (int64_t)b;
@@ -284,41 +285,25 @@ wps_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restric
 }
 
 // ---------------------------------------------------------------------------
-// Kernel B ("stream", ftk_debug_set_wps_impl(2)): persistent, warp-specialised, TMA-fed.
+// Pieces shared by the persistent, warp-specialised, TMA-fed kernels below.
 //
-// grid = resident CTAs (SMs x kStreamCtasPerSm); each CTA walks tiles
-// blockIdx.x, +gridDim.x, ...  One producer warp runs ahead of eight consumer
-// warps: it reads the next tile's descriptor and fragment range and issues 1-D
-// bulk async copies (cp.async.bulk ... mbarrier::complete_tx::bytes, SASS UBLKCP)
-// of the start / stop / mapq slices into a 2-stage shared-memory ring.  The
-// consumers wait on the stage's "full" mbarrier, turn the staged fragments into
-// shared atomics, release the stage through its "empty" mbarrier, then scan and
-// store the tile - while the next tile's bytes are already in flight.  HBM
-// latency is therefore never exposed to the compute warps.
+// A producer lane runs ahead of the consumer warps: it reads the next tile's descriptor and
+// fragment range and issues 1-D bulk async copies (cp.async.bulk ... mbarrier::complete_tx::bytes,
+// SASS UBLKCP) of the start / stop / mapq slices into a shared-memory staging buffer.  The
+// consumers wait on the buffer's "full" mbarrier, turn the staged fragments into shared atomics,
+// release the buffer through its "empty" mbarrier, then scan and store the tile - while the next
+// tile's bytes are already in flight.  HBM latency is therefore never exposed to the compute warps.
 // ---------------------------------------------------------------------------
-constexpr int kStreamFrags = 1920;        // fragments per stage (multiple of 16)
-constexpr int kStreamStages = 2;
-constexpr int kStreamCtasPerSm = 4;
-constexpr int kStreamThreads = kWpsThreads + 32;  // 8 consumer warps + 1 producer warp
+constexpr int kStreamFrags = 1920;        // fragments per staging buffer (multiple of 16)
 
 struct __align__(16) StreamDesc {
     int tile;        // -1: no more work
     int p0, len, mid_lo, mid_hi;
     int n;           // staged fragments (multiple of 16, may be 0)
     int first, last; // first / last chunk of its tile
+    int ivl;         // interval the tile belongs to (fused coverage counts)
     long long out_off;
     long long tail_lo, tail_hi;  // ragged end of the contig, read straight from global (rare)
-};
-
-struct __align__(128) StreamSmem {
-    int D[kWpsCap];
-    int start[kStreamStages][kStreamFrags];
-    int stop[kStreamStages][kStreamFrags];
-    unsigned char mapq[kStreamStages][kStreamFrags];
-    StreamDesc desc[kStreamStages];
-    unsigned long long full_bar[kStreamStages];
-    unsigned long long empty_bar[kStreamStages];
-    int warp_tot[kWpsWarps];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -351,127 +336,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void consumer_sync() {
-    asm volatile("bar.sync 1, %0;" :: "n"(kWpsThreads) : "memory");
-}
-
-template <bool ODD, typename OutT>
-__global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
-wps_stream_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
-                  const uint8_t *__restrict__ frag_mapq, int64_t n_frag,
-                  const int32_t *__restrict__ tile_p0, const int32_t *__restrict__ tile_len,
-                  const int32_t *__restrict__ tile_mid_lo, const int32_t *__restrict__ tile_mid_hi,
-                  const int64_t *__restrict__ tile_out_off, const int64_t *__restrict__ ranges,
-                  int n_tiles, WpsParams P, OutT *__restrict__ out, int *__restrict__ overflow) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    StreamSmem &S = *reinterpret_cast<StreamSmem *>(smem_raw);
-    const int tid = threadIdx.x;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < kStreamStages; ++s) {
-            mbar_init(&S.full_bar[s], 1);   // the producer's arrive(.expect_tx)
-            mbar_init(&S.empty_bar[s], 1);  // one elected consumer
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (tid >= kWpsThreads) {
-        // ===================== producer warp (one elected lane) =====================
-        if (tid == kWpsThreads) {
-            int stage = 0;
-            unsigned phase = 0;
-            const int64_t n16 = n_frag & ~(int64_t)15;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int64_t lo = ranges[2 * (int64_t)tile], hi = ranges[2 * (int64_t)tile + 1];
-                const int p0 = tile_p0[tile], len = tile_len[tile];
-                const int mlo = tile_mid_lo[tile], mhi = tile_mid_hi[tile];
-                const long long ooff = tile_out_off[tile];
-                // bulk copies need 16-byte aligned sources and sizes for all three columns
-                // (mapq is 1 byte wide): widen to multiples of 16 fragments - a superset is
-                // harmless - but never read past the last full 16-block of the arrays.
-                const int64_t lo16 = lo & ~(int64_t)15;
-                int64_t hi16 = (hi + 15) & ~(int64_t)15;
-                if (hi16 > n16) hi16 = n16;
-                if (hi16 < lo16) hi16 = lo16;
-                const int64_t t_lo = (hi16 > lo16) ? hi16 : lo16;
-                const bool has_tail = hi > t_lo;
-                const int64_t span = hi16 - lo16;
-                const int n_chunks = span > 0 ? (int)((span + kStreamFrags - 1) / kStreamFrags) : 1;
-                for (int c = 0; c < n_chunks; ++c) {
-                    mbar_wait(&S.empty_bar[stage], phase ^ 1u);
-                    const int64_t c0 = lo16 + (int64_t)c * kStreamFrags;
-                    const int n = (int)min((int64_t)kStreamFrags, hi16 - c0);
-                    StreamDesc &d = S.desc[stage];
-                    d.tile = tile; d.p0 = p0; d.len = len; d.mid_lo = mlo; d.mid_hi = mhi;
-                    d.n = n > 0 ? n : 0;
-                    d.first = (c == 0); d.last = (c == n_chunks - 1);
-                    d.out_off = ooff;
-                    d.tail_lo = (d.last && has_tail) ? t_lo : 0;
-                    d.tail_hi = (d.last && has_tail) ? hi : 0;
-                    if (n > 0) {
-                        const unsigned bytes = (unsigned)n * (frag_mapq ? 9u : 8u);
-                        mbar_arrive_expect_tx(&S.full_bar[stage], bytes);
-                        bulk_g2s(S.start[stage], frag_start + c0, (unsigned)n * 4u, &S.full_bar[stage]);
-                        bulk_g2s(S.stop[stage], frag_stop + c0, (unsigned)n * 4u, &S.full_bar[stage]);
-                        if (frag_mapq) bulk_g2s(S.mapq[stage], frag_mapq + c0, (unsigned)n, &S.full_bar[stage]);
-                    } else {
-                        mbar_arrive(&S.full_bar[stage]);
-                    }
-                    stage ^= 1;
-                    if (stage == 0) phase ^= 1u;
-                }
-            }
-            mbar_wait(&S.empty_bar[stage], phase ^ 1u);
-            S.desc[stage].tile = -1;
-            mbar_arrive(&S.full_bar[stage]);
-        }
-        return;
-    }
-
-    // ========================= consumer warps =========================
-    int stage = 0;
-    unsigned phase = 0;
-    TileCtx T = make_tile_ctx<ODD>(P, 0, 0, 0, 0);
-    for (;;) {
-        mbar_wait(&S.full_bar[stage], phase);
-        const StreamDesc d = S.desc[stage];
-        if (d.tile < 0) break;
-        if (d.first) {
-            T = make_tile_ctx<ODD>(P, d.p0, d.len, d.mid_lo, d.mid_hi);
-#pragma unroll
-            for (int j = 0; j < kWpsIters; ++j)
-                reinterpret_cast<int4 *>(S.D)[j * kWpsThreads + tid] = make_int4(0, 0, 0, 0);
-            consumer_sync();
-        }
-        const int nvec = d.n >> 2;
-        const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(S.start[stage]);
-        const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(S.stop[stage]);
-        const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(S.mapq[stage]);
-        for (int v = tid; v < nvec; v += kWpsThreads) {
-            const int4 s = vs[v], e = ve[v];
-            const uchar4 q = frag_mapq ? vq[v] : make_uchar4(255, 255, 255, 255);
-            wps_scatter(S.D, P, T, s.x, e.x, q.x);
-            wps_scatter(S.D, P, T, s.y, e.y, q.y);
-            wps_scatter(S.D, P, T, s.z, e.z, q.z);
-            wps_scatter(S.D, P, T, s.w, e.w, q.w);
-        }
-        if (d.tail_hi > d.tail_lo) {  // < 16 fragments at the very end of the contig
-            const int64_t i = d.tail_lo + tid;
-            if (i < d.tail_hi)
-                wps_scatter(S.D, P, T, __ldcs(frag_start + i), __ldcs(frag_stop + i),
-                            frag_mapq ? (int)__ldcs(frag_mapq + i) : 255);
-        }
-        consumer_sync();                                // scatter done; stage buffers are free
-        if (tid == 0) mbar_arrive(&S.empty_bar[stage]);  // hand the stage back to the producer
-        if (d.last)
-            wps_scan_store<ODD>(S.D, S.warp_tot, P, T, out + d.out_off, overflow, tid, [] { consumer_sync(); });
-        stage ^= 1;
-        if (stage == 0) phase ^= 1u;
-    }
-}
-
 
 // ---------------------------------------------------------------------------
 // Kernel C ("dual", default): two tiles in flight per CTA.
@@ -684,6 +548,241 @@ wps_dual_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restric
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Kernel D ("hex", default; the only one with the fused coverage / length-histogram pass):
+// ONE persistent CTA per SM with SIX consumer groups of four warps and THREE producer warps
+// (producer p feeds groups 2p and 2p+1 exactly like the producer of the dual kernel feeds its
+// two).  Six tiles are in flight per SM as with three dual CTAs, but the SM's shared memory is
+// one allocation: the 2 KB the two extra CTAs lost to the per-CTA reservation plus the slack at
+// the end leave room for a CTA-wide 1024-bin length histogram, which is what lets the step make
+// ONE pass over the fragments (FUSE):
+//   * per-interval coverage (frag/_coverage.py:117-130, midpoint policy): a fragment's midpoint
+//     lies in exactly one tile of an interval, so the count of an interval is the sum of its
+//     tiles' counts - a register count per lane, one shuffle reduction and one 64-bit atomic per
+//     warp and tile;
+//   * pooled length histogram of the counted fragments (frag/_frag_length.py:147-153): shared
+//     atomics on the CTA's histogram, flushed once with 64-bit global atomics when the CTA ends
+//     (a CTA sees < 2^31 fragments: n_frag <= INT32_MAX).
+// The coverage predicate has its own length window and mapq cut; the staged range is widened
+// on the left so that every fragment whose midpoint can fall into the tile is staged.
+// ---------------------------------------------------------------------------
+constexpr int kHexGroups = 6;
+constexpr int kHexProducers = kHexGroups / 2;
+constexpr int kHexConsumerThreads = kHexGroups * kDualGroupThreads;
+constexpr int kHexThreads = kHexConsumerThreads + 32 * kHexProducers;
+constexpr int kFuseBins = 1024;           // lengths below this are privatised in shared memory
+
+struct CovParams {
+    int len_lo;
+    unsigned len_span;
+    int min_mapq;
+    int n_bins;             // 0: no histogram
+};
+
+struct __align__(128) HexSmem {
+    int D[kHexGroups][kWpsCap];
+    int start[kHexGroups][kStreamFrags];
+    int stop[kHexGroups][kStreamFrags];
+    unsigned char mapq[kHexGroups][kStreamFrags];
+    StreamDesc desc[kHexGroups];
+    unsigned long long full_bar[kHexGroups];
+    unsigned long long empty_bar[kHexGroups];
+    int warp_tot[kHexGroups][kDualWarps];
+    int hist[kFuseBins];
+};
+static_assert(sizeof(HexSmem) <= 227 * 1024, "HexSmem must fit the 227 KB a CTA may own on sm_100a");
+
+// Coverage / histogram side of one staged fragment: the stream of region [p0, p0+len) under the
+// midpoint policy (io/alignment.py:270-302 overlap rows: stop > S; utils/_frag_generator.py:117-123).
+__device__ __forceinline__ void cov_visit(int *__restrict__ hist_s, unsigned long long *__restrict__ ghist,
+                                          const CovParams &C, const TileCtx &T, int fs, int fe, int q, int &cnt) {
+    const int L = fe - fs;
+    const bool pass = (q >= C.min_mapq) & ((unsigned)(L - C.len_lo) <= C.len_span) &
+                      ((unsigned)(fs + (L >> 1) - T.p0) < (unsigned)T.len) & (fe > T.p0);
+    if (pass) {
+        ++cnt;
+        if (L < C.n_bins) {
+            if (L < kFuseBins) atomicAdd(&hist_s[L], 1);
+            else atomicAdd(&ghist[L], 1ull);
+        }
+    }
+}
+
+struct TileRec {
+    int64_t lo, hi;
+    long long ooff;
+    int tile, p0, len, mlo, mhi, ivl;
+};
+
+template <bool ODD, typename OutT, bool FUSE>
+__global__ void __launch_bounds__(kHexThreads, 1)
+wps_hex_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
+               const uint8_t *__restrict__ frag_mapq, int64_t n_frag,
+               const int32_t *__restrict__ tile_p0, const int32_t *__restrict__ tile_len,
+               const int32_t *__restrict__ tile_mid_lo, const int32_t *__restrict__ tile_mid_hi,
+               const int64_t *__restrict__ tile_out_off, const int32_t *__restrict__ tile_ivl,
+               const int64_t *__restrict__ ranges, int n_tiles, WpsParams P, CovParams C,
+               OutT *__restrict__ out, int *__restrict__ overflow,
+               unsigned long long *__restrict__ counts, unsigned long long *__restrict__ ghist) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    HexSmem &S = *reinterpret_cast<HexSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int g = 0; g < kHexGroups; ++g) {
+            mbar_init(&S.full_bar[g], 1);
+            mbar_init(&S.empty_bar[g], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (FUSE) {
+        for (int b = tid; b < kFuseBins; b += kHexThreads) S.hist[b] = 0;
+    }
+    __syncthreads();
+
+    if (tid >= kHexConsumerThreads) {
+        // ============ producer warps (one elected lane each, two groups per producer) ============
+        const int pt = tid - kHexConsumerThreads;
+        if ((pt & 31) == 0) {
+            const int p = pt >> 5;
+            unsigned ph[2] = {0u, 0u};
+            const int64_t n16 = n_frag & ~(int64_t)15;
+            // the CTA's k-th tile is blockIdx.x + k * gridDim.x and goes to group k % 6; this
+            // producer's j-th tile is k = 6 * (j / 2) + 2p + (j & 1)
+            auto fetch = [&](int j, TileRec &r) -> bool {
+                const int64_t k = 6 * (int64_t)(j >> 1) + 2 * p + (j & 1);
+                const int64_t tile = blockIdx.x + k * (int64_t)gridDim.x;
+                if (tile >= n_tiles) return false;
+                r.tile = (int)tile;
+                r.lo = ranges[2 * tile]; r.hi = ranges[2 * tile + 1];
+                r.p0 = tile_p0[tile]; r.len = tile_len[tile];
+                r.mlo = tile_mid_lo[tile]; r.mhi = tile_mid_hi[tile];
+                r.ooff = tile_out_off[tile];
+                r.ivl = FUSE ? tile_ivl[tile] : 0;
+                return true;
+            };
+            TileRec r, rn;
+            bool have = fetch(0, r);
+            for (int j = 0; have; ++j) {
+                // the next tile's descriptor loads are in flight while this tile waits for its buffer
+                const bool have_next = fetch(j + 1, rn);
+                const int sub = j & 1;
+                const int g = 2 * p + sub;
+                const int64_t lo16 = r.lo & ~(int64_t)15;
+                int64_t hi16 = (r.hi + 15) & ~(int64_t)15;
+                if (hi16 > n16) hi16 = n16;
+                if (hi16 < lo16) hi16 = lo16;
+                const int64_t t_lo = (hi16 > lo16) ? hi16 : lo16;
+                const bool has_tail = r.hi > t_lo;
+                const int64_t span = hi16 - lo16;
+                const int n_chunks = span > 0 ? (int)((span + kStreamFrags - 1) / kStreamFrags) : 1;
+                for (int c = 0; c < n_chunks; ++c) {
+                    mbar_wait(&S.empty_bar[g], ph[sub] ^ 1u);
+                    const int64_t c0 = lo16 + (int64_t)c * kStreamFrags;
+                    const int n = (int)min((int64_t)kStreamFrags, hi16 - c0);
+                    StreamDesc &d = S.desc[g];
+                    d.tile = r.tile; d.p0 = r.p0; d.len = r.len; d.mid_lo = r.mlo; d.mid_hi = r.mhi;
+                    d.n = n > 0 ? n : 0;
+                    d.first = (c == 0); d.last = (c == n_chunks - 1);
+                    d.ivl = r.ivl;
+                    d.out_off = r.ooff;
+                    d.tail_lo = (d.last && has_tail) ? t_lo : 0;
+                    d.tail_hi = (d.last && has_tail) ? r.hi : 0;
+                    if (n > 0) {
+                        const unsigned bytes = (unsigned)n * (frag_mapq ? 9u : 8u);
+                        mbar_arrive_expect_tx(&S.full_bar[g], bytes);
+                        bulk_g2s(S.start[g], frag_start + c0, (unsigned)n * 4u, &S.full_bar[g]);
+                        bulk_g2s(S.stop[g], frag_stop + c0, (unsigned)n * 4u, &S.full_bar[g]);
+                        if (frag_mapq) bulk_g2s(S.mapq[g], frag_mapq + c0, (unsigned)n, &S.full_bar[g]);
+                    } else {
+                        mbar_arrive(&S.full_bar[g]);
+                    }
+                    ph[sub] ^= 1u;
+                }
+                r = rn;
+                have = have_next;
+            }
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+                const int g = 2 * p + sub;
+                mbar_wait(&S.empty_bar[g], ph[sub] ^ 1u);
+                S.desc[g].tile = -1;
+                mbar_arrive(&S.full_bar[g]);
+            }
+        }
+        return;
+    }
+
+    // ========================= consumer groups =========================
+    const int g = tid / kDualGroupThreads;
+    const int gt = tid - g * kDualGroupThreads;
+    int *__restrict__ D = S.D[g];
+    unsigned phase = 0;
+    int cnt = 0;
+    TileCtx T = make_tile_ctx<ODD>(P, 0, 0, 0, 0);
+    for (;;) {
+        mbar_wait(&S.full_bar[g], phase);
+        const StreamDesc d = S.desc[g];
+        if (d.tile < 0) break;
+        if (d.first) {
+            T = make_tile_ctx<ODD>(P, d.p0, d.len, d.mid_lo, d.mid_hi);
+            cnt = 0;
+#pragma unroll
+            for (int j = 0; j < kWpsCap / (4 * kDualGroupThreads); ++j)
+                reinterpret_cast<int4 *>(D)[j * kDualGroupThreads + gt] = make_int4(0, 0, 0, 0);
+            group_sync(g);
+        }
+        const int nvec = d.n >> 2;
+        const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(S.start[g]);
+        const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(S.stop[g]);
+        const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(S.mapq[g]);
+        for (int v = gt; v < nvec; v += kDualGroupThreads) {
+            const int4 s = vs[v], e = ve[v];
+            const uchar4 q = frag_mapq ? vq[v] : make_uchar4(255, 255, 255, 255);
+            wps_scatter(D, P, T, s.x, e.x, q.x);
+            wps_scatter(D, P, T, s.y, e.y, q.y);
+            wps_scatter(D, P, T, s.z, e.z, q.z);
+            wps_scatter(D, P, T, s.w, e.w, q.w);
+            if (FUSE) {
+                cov_visit(S.hist, ghist, C, T, s.x, e.x, q.x, cnt);
+                cov_visit(S.hist, ghist, C, T, s.y, e.y, q.y, cnt);
+                cov_visit(S.hist, ghist, C, T, s.z, e.z, q.z, cnt);
+                cov_visit(S.hist, ghist, C, T, s.w, e.w, q.w, cnt);
+            }
+        }
+        if (d.tail_hi > d.tail_lo) {
+            const int64_t i = d.tail_lo + gt;
+            if (i < d.tail_hi) {
+                const int fs = __ldcs(frag_start + i), fe = __ldcs(frag_stop + i);
+                const int q = frag_mapq ? (int)__ldcs(frag_mapq + i) : 255;
+                wps_scatter(D, P, T, fs, fe, q);
+                if (FUSE) cov_visit(S.hist, ghist, C, T, fs, fe, q, cnt);
+            }
+        }
+        group_sync(g);                                   // scatter done; the staging buffer is free
+        if (gt == 0) mbar_arrive(&S.empty_bar[g]);
+        if (d.last) {
+            if (FUSE) {
+                const int c = __reduce_add_sync(0xffffffffu, cnt);
+                if ((gt & 31) == 0 && c) atomicAdd(&counts[d.ivl], (unsigned long long)c);
+            }
+            wps_scan_store_group<ODD>(D, S.warp_tot[g], P, T, out + d.out_off, overflow, gt, g);
+        }
+        phase ^= 1u;
+    }
+    if (FUSE && C.n_bins > 0) {
+        // all consumer groups are done: flush the CTA's histogram (the producers have exited)
+        asm volatile("bar.sync %0, %1;" :: "n"(kHexGroups + 1), "n"(kHexConsumerThreads) : "memory");
+        const int nb = min(C.n_bins, kFuseBins);
+        for (int b = tid; b < nb; b += kHexConsumerThreads) {
+            const int v = S.hist[b];
+            if (v) atomicAdd(&ghist[b], (unsigned long long)v);
+        }
+    }
+}
+
 }  // namespace ftk
 
 extern "C" int64_t ftk_wps_plan_tiles(const int64_t *ivl_start, const int64_t *ivl_stop,
@@ -733,79 +832,132 @@ static int wps_check_args(const int32_t *frag_start, const int32_t *frag_stop, i
     return FTK_OK;
 }
 
-extern "C" int ftk_wps_tile_ranges(const int32_t *frag_start, int64_t n_frag,
-                                   const int32_t *tile_p0, const int32_t *tile_len, int64_t n_tiles,
-                                   int32_t window_size, int32_t max_len, int64_t *scratch,
-                                   ftk_stream_t stream_) {
+// left_reach: how far left of p0 - 1 a fragment may start and still matter to the tile
+static int launch_tile_ranges(const int32_t *frag_start, int64_t n_frag, const int32_t *tile_p0,
+                              const int32_t *tile_len, int64_t n_tiles, int32_t window_size,
+                              int64_t left_reach, int64_t *scratch, cudaStream_t stream) {
     using namespace ftk;
-    if (n_tiles == 0) return FTK_OK;
-    int rc = wps_check_args(frag_start, frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size, max_len, scratch);
-    if (rc != FTK_OK) return rc;
     const bool odd = (window_size & 1) != 0;
     const int a = odd ? (window_size - 1) / 2 : window_size / 2;
     const int b = odd ? a : a - 1;
+    if (left_reach > INT32_MAX / 2) left_reach = INT32_MAX / 2;
     const int64_t n = 2 * n_tiles;
     const int threads = 128;
-    wps_tile_ranges_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0,
-                             static_cast<cudaStream_t>(stream_)>>>(
-        frag_start, n_frag, tile_p0, tile_len, n_tiles, a, b, max_len, scratch);
+    wps_tile_ranges_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(
+        frag_start, n_frag, tile_p0, tile_len, n_tiles, (int)left_reach, b, scratch);
     FTK_CHECK_LAUNCH("wps_tile_ranges_kernel");
     return FTK_OK;
 }
 
-// 0 = dual (TMA pipeline, two tiles in flight per CTA; default), 1 = direct (one CTA per tile),
-// 2 = stream (TMA pipeline, one tile per CTA - the default until r1d)
+static int64_t wps_left_reach(int32_t window_size, int32_t max_len) {
+    // last event of a fragment sits at fe+a+1 <= fs+max_len+a+1; it must be > g0 >= p0-1
+    const int a = (window_size & 1) ? (window_size - 1) / 2 : window_size / 2;
+    return (int64_t)a + (int64_t)max_len;
+}
+
+extern "C" int ftk_wps_tile_ranges(const int32_t *frag_start, int64_t n_frag,
+                                   const int32_t *tile_p0, const int32_t *tile_len, int64_t n_tiles,
+                                   int32_t window_size, int32_t max_len, int64_t *scratch,
+                                   ftk_stream_t stream_) {
+    if (n_tiles == 0) return FTK_OK;
+    int rc = wps_check_args(frag_start, frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size, max_len, scratch);
+    if (rc != FTK_OK) return rc;
+    return launch_tile_ranges(frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size,
+                              wps_left_reach(window_size, max_len), scratch, static_cast<cudaStream_t>(stream_));
+}
+
+// 0 = hex (one CTA per SM, six tiles in flight; default), 1 = direct (one CTA per tile),
+// 3 = dual (three CTAs per SM, two tiles in flight each - the default of round 1)
 static int g_wps_impl = 0;
 extern "C" void ftk_debug_set_wps_impl(int impl) { g_wps_impl = impl; }
 
-template <bool ODD, typename OutT>
-static int launch_wps(const int32_t *frag_start, const int32_t *frag_stop, const uint8_t *frag_mapq,
-                      int64_t n_frag, const int32_t *tile_p0, const int32_t *tile_len,
-                      const int32_t *tile_mid_lo, const int32_t *tile_mid_hi,
-                      const int64_t *tile_out_off, int64_t n_tiles, const ftk::WpsParams &P,
-                      const int64_t *ranges, OutT *out, int *overflow, cudaStream_t stream) {
-    using namespace ftk;
-    if (g_wps_impl == 1) {
-        wps_tile_kernel<ODD, OutT><<<(unsigned)n_tiles, kWpsThreads, 0, stream>>>(
-            frag_start, frag_stop, frag_mapq, tile_p0, tile_len, tile_mid_lo, tile_mid_hi, tile_out_off,
-            ranges, P, out, overflow);
-        FTK_CHECK_LAUNCH("wps_tile_kernel");
-        return FTK_OK;
-    }
+static int device_sm_count(int *sm) {
     static thread_local int sm_count[64] = {0};
-    static thread_local bool attr_set[64] = {false};
     int dev = 0;
     FTK_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return FTK_E_RANGE;
     if (!sm_count[dev])
         FTK_CUDA_TRY(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-    if (g_wps_impl != 2) {
-        static thread_local bool dual_attr_set[64] = {false};
+    *sm = sm_count[dev];
+    return FTK_OK;
+}
+
+struct WpsLaunch {
+    const int32_t *frag_start, *frag_stop; const uint8_t *frag_mapq; int64_t n_frag;
+    const int32_t *tile_p0, *tile_len, *tile_mid_lo, *tile_mid_hi; const int64_t *tile_out_off;
+    const int32_t *tile_ivl; int64_t n_tiles; const int64_t *ranges;
+    ftk::WpsParams P; ftk::CovParams C;
+    int *overflow; unsigned long long *counts, *hist;
+    cudaStream_t stream;
+};
+
+template <bool ODD, typename OutT, bool FUSE>
+static int launch_hex(const WpsLaunch &a, OutT *out) {
+    using namespace ftk;
+    int sm = 0;
+    int rc = device_sm_count(&sm);
+    if (rc != FTK_OK) return rc;
+    static thread_local bool attr_set = false;
+    const int smem = (int)sizeof(HexSmem);
+    if (!attr_set) {
+        FTK_CUDA_TRY(cudaFuncSetAttribute(wps_hex_kernel<ODD, OutT, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    int64_t grid = sm;                      // one persistent CTA per SM
+    if (grid > a.n_tiles) grid = a.n_tiles;
+    wps_hex_kernel<ODD, OutT, FUSE><<<(unsigned)grid, kHexThreads, smem, a.stream>>>(
+        a.frag_start, a.frag_stop, a.frag_mapq, a.n_frag, a.tile_p0, a.tile_len, a.tile_mid_lo, a.tile_mid_hi,
+        a.tile_out_off, a.tile_ivl, a.ranges, (int)a.n_tiles, a.P, a.C, out, a.overflow, a.counts, a.hist);
+    FTK_CHECK_LAUNCH("wps_hex_kernel");
+    return FTK_OK;
+}
+
+template <bool ODD, typename OutT>
+static int launch_wps(const WpsLaunch &a, OutT *out) {
+    using namespace ftk;
+    if (g_wps_impl == 1) {
+        wps_tile_kernel<ODD, OutT><<<(unsigned)a.n_tiles, kWpsThreads, 0, a.stream>>>(
+            a.frag_start, a.frag_stop, a.frag_mapq, a.tile_p0, a.tile_len, a.tile_mid_lo, a.tile_mid_hi,
+            a.tile_out_off, a.ranges, a.P, out, a.overflow);
+        FTK_CHECK_LAUNCH("wps_tile_kernel");
+        return FTK_OK;
+    }
+    if (g_wps_impl == 3) {
+        int sm = 0;
+        int rc = device_sm_count(&sm);
+        if (rc != FTK_OK) return rc;
+        static thread_local bool dual_attr_set = false;
         const int dsmem = (int)sizeof(DualSmem);
-        if (!dual_attr_set[dev]) {
+        if (!dual_attr_set) {
             FTK_CUDA_TRY(cudaFuncSetAttribute(wps_dual_kernel<ODD, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsmem));
-            dual_attr_set[dev] = true;
+            dual_attr_set = true;
         }
-        int64_t dgrid = (int64_t)sm_count[dev] * kDualCtasPerSm;
-        if (dgrid > (n_tiles + 1) / 2) dgrid = (n_tiles + 1) / 2;
-        wps_dual_kernel<ODD, OutT><<<(unsigned)dgrid, kDualThreads, dsmem, stream>>>(
-            frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo, tile_mid_hi, tile_out_off,
-            ranges, (int)n_tiles, P, out, overflow);
+        int64_t dgrid = (int64_t)sm * kDualCtasPerSm;
+        if (dgrid > (a.n_tiles + 1) / 2) dgrid = (a.n_tiles + 1) / 2;
+        wps_dual_kernel<ODD, OutT><<<(unsigned)dgrid, kDualThreads, dsmem, a.stream>>>(
+            a.frag_start, a.frag_stop, a.frag_mapq, a.n_frag, a.tile_p0, a.tile_len, a.tile_mid_lo, a.tile_mid_hi,
+            a.tile_out_off, a.ranges, (int)a.n_tiles, a.P, out, a.overflow);
         FTK_CHECK_LAUNCH("wps_dual_kernel");
         return FTK_OK;
     }
-    const int smem = (int)sizeof(StreamSmem);
-    if (!attr_set[dev]) {
-        FTK_CUDA_TRY(cudaFuncSetAttribute(wps_stream_kernel<ODD, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set[dev] = true;
+    return launch_hex<ODD, OutT, false>(a, out);
+}
+
+static void wps_fill_params(ftk::WpsParams &P, int32_t window_size, int32_t min_len, int32_t max_len,
+                            int32_t min_mapq) {
+    const bool odd = (window_size & 1) != 0;
+    P.window = window_size;
+    P.a = odd ? (window_size - 1) / 2 : window_size / 2;
+    P.b = odd ? P.a : P.a - 1;
+    P.len_lo = (min_len == FTK_NONE || min_len < 0) ? 0 : min_len;
+    P.max_len = max_len;
+    if (max_len < P.len_lo) {  // empty length window: every position scores 0
+        // (still run the kernel so `out` is fully written; nothing passes the range test)
+        P.len_lo = 1; P.len_span = 0; P.min_mapq = 256;
+    } else {
+        P.len_span = (unsigned)(max_len - P.len_lo);
+        P.min_mapq = min_mapq;
     }
-    int64_t grid = (int64_t)sm_count[dev] * kStreamCtasPerSm;  // one persistent CTA per resident slot
-    if (grid > n_tiles) grid = n_tiles;
-    wps_stream_kernel<ODD, OutT><<<(unsigned)grid, kStreamThreads, smem, stream>>>(
-        frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo, tile_mid_hi, tile_out_off,
-        ranges, (int)n_tiles, P, out, overflow);
-    FTK_CHECK_LAUNCH("wps_stream_kernel");
-    return FTK_OK;
 }
 
 template <typename OutT>
@@ -826,25 +978,15 @@ static int wps_tiles_impl(const int32_t *frag_start, const int32_t *frag_stop,
         rc = ftk_wps_tile_ranges(frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size, max_len, scratch, stream_);
         if (rc != FTK_OK) return rc;
     }
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const bool odd = (window_size & 1) != 0;
-    WpsParams P;
-    P.window = window_size;
-    P.a = odd ? (window_size - 1) / 2 : window_size / 2;
-    P.b = odd ? P.a : P.a - 1;
-    P.len_lo = (min_len == FTK_NONE || min_len < 0) ? 0 : min_len;
-    P.max_len = max_len;
-    if (max_len < P.len_lo) {  // empty length window: every position scores 0
-        // (still run the kernel so `out` is fully written; nothing passes the range test)
-        P.len_lo = 1; P.len_span = 0; P.min_mapq = 256;
-    } else {
-        P.len_span = (unsigned)(max_len - P.len_lo);
-        P.min_mapq = min_mapq;
-    }
-    return odd ? launch_wps<true, OutT>(frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo,
-                                        tile_mid_hi, tile_out_off, n_tiles, P, scratch, out, overflow, stream)
-               : launch_wps<false, OutT>(frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo,
-                                         tile_mid_hi, tile_out_off, n_tiles, P, scratch, out, overflow, stream);
+    WpsLaunch a{};
+    a.frag_start = frag_start; a.frag_stop = frag_stop; a.frag_mapq = frag_mapq; a.n_frag = n_frag;
+    a.tile_p0 = tile_p0; a.tile_len = tile_len; a.tile_mid_lo = tile_mid_lo; a.tile_mid_hi = tile_mid_hi;
+    a.tile_out_off = tile_out_off; a.tile_ivl = nullptr; a.n_tiles = n_tiles; a.ranges = scratch;
+    a.overflow = overflow; a.counts = nullptr; a.hist = nullptr;
+    a.stream = static_cast<cudaStream_t>(stream_);
+    wps_fill_params(a.P, window_size, min_len, max_len, min_mapq);
+    a.C = CovParams{0, 0u, 0, 0};
+    return (window_size & 1) ? launch_wps<true, OutT>(a, out) : launch_wps<false, OutT>(a, out);
 }
 
 extern "C" int ftk_wps_tiles_i32(const int32_t *frag_start, const int32_t *frag_stop,
@@ -886,4 +1028,54 @@ extern "C" int ftk_wps_tiles_i8(const int32_t *frag_start, const int32_t *frag_s
     return wps_tiles_impl<int8_t>(frag_start, frag_stop, frag_mapq, n_frag, tile_p0, tile_len, tile_mid_lo,
                                   tile_mid_hi, tile_out_off, n_tiles, window_size, min_len, max_len, min_mapq,
                                   ranges_ready, scratch, out, overflow_flag, stream_);
+}
+
+// ---- fused pass: WPS + per-interval coverage + pooled length histogram (wps_hex_kernel<.., FUSE>)
+extern "C" int ftk_wps_cov_tiles(const int32_t *frag_start, const int32_t *frag_stop,
+                                 const uint8_t *frag_mapq, int64_t n_frag, int32_t max_frag_len,
+                                 const int32_t *tile_p0, const int32_t *tile_len,
+                                 const int32_t *tile_mid_lo, const int32_t *tile_mid_hi,
+                                 const int64_t *tile_out_off, const int32_t *tile_ivl, int64_t n_tiles,
+                                 int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
+                                 int32_t cov_min_len, int32_t cov_max_len, int32_t cov_min_mapq, int32_t n_bins,
+                                 int64_t *scratch, int32_t out_kind, void *out, int32_t *overflow_flag,
+                                 uint64_t *counts, uint64_t *hist, ftk_stream_t stream_) {
+    using namespace ftk;
+    if (n_tiles == 0) return FTK_OK;
+    int rc = wps_check_args(frag_start, frag_stop, n_frag, tile_p0, tile_len, n_tiles, window_size, max_len, scratch);
+    if (rc != FTK_OK) return rc;
+    if (!tile_mid_lo || !tile_mid_hi || !tile_out_off || !tile_ivl || !out || !counts) return FTK_E_INVALID;
+    if (out_kind < 0 || out_kind > 2 || n_bins < 0 || max_frag_len < 0) return FTK_E_INVALID;
+    if (out_kind != 0 && !overflow_flag) return FTK_E_INVALID;
+    if (n_bins > 0 && !hist) return FTK_E_INVALID;
+    if (n_frag > INT32_MAX) return FTK_E_RANGE;   // a CTA's shared histogram counts in int32
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WpsLaunch a{};
+    wps_fill_params(a.P, window_size, min_len, max_len, min_mapq);
+    // coverage stream predicate (FTK_NONE = unbounded), as Stream in ftk_hist.cu
+    a.C.len_lo = (cov_min_len == FTK_NONE || cov_min_len < 0) ? 0 : cov_min_len;
+    const int cov_hi = (cov_max_len == FTK_NONE) ? INT32_MAX : cov_max_len;
+    if (cov_hi < a.C.len_lo) { a.C.len_lo = 1; a.C.len_span = 0; a.C.min_mapq = 256; }
+    else { a.C.len_span = (unsigned)(cov_hi - a.C.len_lo); a.C.min_mapq = cov_min_mapq; }
+    a.C.n_bins = n_bins;
+    // a fragment whose midpoint fs + (L >> 1) is >= p0 starts at fs >= p0 - (Lmax >> 1)
+    const int64_t lmax = cov_hi < max_frag_len ? cov_hi : max_frag_len;
+    int64_t reach = wps_left_reach(window_size, max_len);
+    if ((lmax >> 1) + 1 > reach) reach = (lmax >> 1) + 1;
+    rc = launch_tile_ranges(frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size, reach, scratch, stream);
+    if (rc != FTK_OK) return rc;
+    a.frag_start = frag_start; a.frag_stop = frag_stop; a.frag_mapq = frag_mapq; a.n_frag = n_frag;
+    a.tile_p0 = tile_p0; a.tile_len = tile_len; a.tile_mid_lo = tile_mid_lo; a.tile_mid_hi = tile_mid_hi;
+    a.tile_out_off = tile_out_off; a.tile_ivl = tile_ivl; a.n_tiles = n_tiles; a.ranges = scratch;
+    a.overflow = overflow_flag;
+    a.counts = reinterpret_cast<unsigned long long *>(counts);
+    a.hist = reinterpret_cast<unsigned long long *>(hist);
+    a.stream = stream;
+    const bool odd = (window_size & 1) != 0;
+#define FTK_FUSED(T)                                                                        \
+    (odd ? launch_hex<true, T, true>(a, static_cast<T *>(out)) : launch_hex<false, T, true>(a, static_cast<T *>(out)))
+    if (out_kind == 0) return FTK_FUSED(int32_t);
+    if (out_kind == 1) return FTK_FUSED(int16_t);
+    return FTK_FUSED(int8_t);
+#undef FTK_FUSED
 }

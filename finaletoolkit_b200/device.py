@@ -142,6 +142,10 @@ class WpsPlan:
         self.tile_mid_lo = _to_device(mlo, self.device, np.int32)
         self.tile_mid_hi = _to_device(mhi, self.device, np.int32)
         self.tile_out_off = _to_device(off, self.device, np.int64)
+        # interval of each tile (empty intervals own no position, hence no tile)
+        self.n_intervals = len(s)
+        ivl = np.searchsorted(self.offsets[1:], off, side="right").astype(np.int32)
+        self.tile_ivl = _to_device(ivl, self.device, np.int32)
         self.scratch = t.empty(2 * max(self.n_tiles, 1), dtype=t.int64, device=self.device)
 
     def ranges(self, frags: ContigFragments, window_size=120):
@@ -173,6 +177,45 @@ class WpsPlan:
             int(bool(ranges_ready)), self.scratch.data_ptr(), out.data_ptr(), _stream_ptr(self.device)),
             "ftk_wps_tiles_i32")
         return out
+
+
+    _KIND = {"int32": 0, "int16": 1, "int8": 2}
+
+    def run_fused(self, frags: ContigFragments, window_size=120, min_length=120, max_length=180,
+                  quality_threshold=30, cov_min_length=None, cov_max_length=None, cov_quality_threshold=30,
+                  n_bins=0, out=None, counts=None, hist=None, overflow=None):
+        """ONE pass over the fragments: WPS of every interval + per-interval midpoint coverage
+        (``counts`` int64[n_intervals]) + the pooled length histogram of the counted fragments
+        (``hist`` int64[n_bins]).  ``counts``/``hist`` are ACCUMULATED into (pass zeroed tensors to
+        reuse buffers); ``out`` may be int32 / int16 / int8 (the narrow types need ``overflow``,
+        an int32[1] flag the caller zeroes).  Returns ``(wps, counts, hist)`` device tensors."""
+        t = torch()
+        if int(max_length) != self.max_length:
+            raise ValueError("plan was built for a different max_length")
+        if out is None:
+            out = t.empty(self.n_positions, dtype=t.int32, device=self.device)
+        kind = {t.int32: 0, t.int16: 1, t.int8: 2}.get(out.dtype)
+        if kind is None or out.numel() < self.n_positions or not out.is_contiguous():
+            raise ValueError("out must be a contiguous int32/int16/int8 tensor with n_positions elements")
+        if kind and overflow is None:
+            raise ValueError("int16/int8 output needs an overflow flag tensor")
+        if counts is None:
+            counts = t.zeros(max(self.n_intervals, 1), dtype=t.int64, device=self.device)
+        if hist is None and n_bins:
+            hist = t.zeros(int(n_bins), dtype=t.int64, device=self.device)
+        if self.n_tiles == 0:
+            return out, counts[: self.n_intervals], hist
+        fs, fe, mq = frags.ptrs()
+        check(lib().ftk_wps_cov_tiles(
+            fs, fe, mq, frags.n, frags.max_len,
+            self.tile_p0.data_ptr(), self.tile_len.data_ptr(), self.tile_mid_lo.data_ptr(),
+            self.tile_mid_hi.data_ptr(), self.tile_out_off.data_ptr(), self.tile_ivl.data_ptr(), self.n_tiles,
+            int(window_size), none_to_ftk(min_length), int(max_length), int(quality_threshold),
+            none_to_ftk(cov_min_length), none_to_ftk(cov_max_length), int(cov_quality_threshold), int(n_bins),
+            self.scratch.data_ptr(), kind, out.data_ptr(), 0 if overflow is None else overflow.data_ptr(),
+            counts.data_ptr(), 0 if hist is None else hist.data_ptr(), _stream_ptr(self.device)),
+            "ftk_wps_cov_tiles")
+        return out, counts[: self.n_intervals], hist
 
 
 _POLICY = {"midpoint": 0, "any": 1}

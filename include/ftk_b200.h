@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FTK_ABI_VERSION 1
+#define FTK_ABI_VERSION 2
 #define FTK_NONE INT32_MIN
 
 #define FTK_OK 0
@@ -54,6 +54,35 @@ int ftk_abi_version(void);
 const char *ftk_error_string(int code);
 /* last CUDA error text recorded by this library on the calling thread ("" if none) */
 const char *ftk_last_cuda_error(void);
+
+/* ------------------------------------------------- packed fragment columns
+ * Wire format host -> HBM, replacing the per-interval text stream of io/alignment.py:270-302 /
+ * utils/_frag_generator.py:124-130 (PCIe is the end-to-end limit: 4.06 B per fragment instead of 10).
+ *   words[i]  = dstart | length << 11 | strand << 23 | mapq << 24   (uint32; dstart = start[i] - start[i-1],
+ *               0 for the first fragment of a block; dstart < 2048, length < 4096)
+ *   anchors[b] = start of the first fragment of block b (FTK_PACK_BLOCK fragments), or -1 - r when the
+ *               block does not fit the fields: its rows are then stored verbatim as raw block r
+ *               (raw_*[r * FTK_PACK_BLOCK ...]).  Lossless for any int32 columns.
+ * words holds n_blocks * FTK_PACK_BLOCK entries (zero padded), n_blocks = ceil(n / FTK_PACK_BLOCK). */
+#define FTK_PACK_BLOCK 64
+
+/* Host (decoder side), multi-threaded (threads <= 0: all cores).  Returns the number of raw blocks.
+ * With words_host == NULL only counts them (so the caller can size the raw columns);
+ * FTK_E_RANGE if raw_capacity_blocks is too small.  mapq_host / strand_host may be NULL (255 / 0). */
+int64_t ftk_pack_fragments_host(const int32_t *start_host, const int32_t *stop_host, const uint8_t *mapq_host,
+                                const uint8_t *strand_host, int64_t n, int32_t threads,
+                                uint32_t *words_host, int32_t *anchors_host,
+                                int32_t *raw_start_host, int32_t *raw_stop_host, uint8_t *raw_mapq_host,
+                                uint8_t *raw_strand_host, int64_t raw_capacity_blocks);
+
+/* Device: words / anchors (of the first block to unpack; a slice of a contig may start at any block
+ * boundary) + the contig's raw columns -> int32 start / stop, uint8 mapq / strand (either may be NULL)
+ * of n fragments.  start_dev / stop_dev / words_dev must be 8-byte aligned. */
+int ftk_unpack_fragments(const uint32_t *words_dev, const int32_t *anchors_dev,
+                         const int32_t *raw_start_dev, const int32_t *raw_stop_dev,
+                         const uint8_t *raw_mapq_dev, const uint8_t *raw_strand_dev, int64_t n_raw_blocks,
+                         int64_t n, int32_t *start_dev, int32_t *stop_dev, uint8_t *mapq_dev, uint8_t *strand_dev,
+                         ftk_stream_t stream);
 
 /* ------------------------------------------------------------------ WPS
  * Replaces the per-position loop of wps() - frag/_wps.py:176-188 calling the
@@ -120,6 +149,29 @@ int ftk_wps_tiles_i8(const int32_t *frag_start_dev, const int32_t *frag_stop_dev
                       int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
                       int32_t ranges_ready, int64_t *scratch_dev, int8_t *out_dev,
                       int32_t *overflow_flag_dev, ftk_stream_t stream);
+
+/* Fused pass: WPS + per-interval coverage counts + ONE pooled length histogram in a single sweep
+ * over the fragments (the three reference loops frag/_wps.py:176-188, frag/_coverage.py:117-130 with
+ * intersect_policy="midpoint", frag/_frag_length.py:147-153 over the same intervals).
+ * tile_ivl_dev[t] = index of the interval tile t belongs to.  counts_dev[ivl] (uint64, ACCUMULATED,
+ * caller zeroes) += fragments with mapq >= cov_min_mapq, cov_min_len <= L <= cov_max_len (FTK_NONE =
+ * unbounded) whose midpoint lies in the interval; hist_dev[L] (uint64[n_bins], ACCUMULATED) += 1 for
+ * each counted fragment with L < n_bins (n_bins = 0: no histogram, hist_dev may be NULL).
+ * max_frag_len = longest fragment of the contig (bounds the candidate search).
+ * out_kind: 0 = int32 scores, 1 = int16, 2 = int8 (overflow protocol of ftk_wps_tiles_i16/_i8;
+ * overflow_flag_dev may be NULL for int32).  scratch_dev: int64[2 * n_tiles]; the per-tile fragment
+ * ranges are always recomputed (they are wider than ftk_wps_tile_ranges').
+ * Every interval is an independent stream (overlapping intervals each count their own fragments,
+ * and the pooled histogram gains one entry per (interval, fragment) pair like the reference's loop). */
+int ftk_wps_cov_tiles(const int32_t *frag_start_dev, const int32_t *frag_stop_dev,
+                      const uint8_t *frag_mapq_dev, int64_t n_frag, int32_t max_frag_len,
+                      const int32_t *tile_p0_dev, const int32_t *tile_len_dev,
+                      const int32_t *tile_mid_lo_dev, const int32_t *tile_mid_hi_dev,
+                      const int64_t *tile_out_off_dev, const int32_t *tile_ivl_dev, int64_t n_tiles,
+                      int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
+                      int32_t cov_min_len, int32_t cov_max_len, int32_t cov_min_mapq, int32_t n_bins,
+                      int64_t *scratch_dev, int32_t out_kind, void *out_dev, int32_t *overflow_flag_dev,
+                      uint64_t *counts_dev, uint64_t *hist_dev, ftk_stream_t stream);
 
 /* ------------------------------------------- coverage / fragment lengths
  * Fragment stream of a region (S, E) - FTK_NONE = None - exactly as the

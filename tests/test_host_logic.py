@@ -27,7 +27,7 @@ def test_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(h, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
-    assert h.ftk_abi_version() == 1
+    assert h.ftk_abi_version() == 2
     assert h.ftk_error_string(-1) == b"invalid argument"
     # the host-only planner is callable without a GPU
     import ctypes
