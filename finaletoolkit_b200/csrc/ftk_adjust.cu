@@ -20,6 +20,8 @@
 // fp64 arithmetic follows numpy's: median of an even window = (lo + hi) / 2 on the
 // shifted values; mean = exact integer sum / w.
 // Roofline: HBM, 4 B in (float32 sample) + 8 B out (float64) per position.
+#include <type_traits>
+
 #include "ftk_common.cuh"
 
 namespace ftk {
@@ -360,6 +362,329 @@ adjust_savgol_kernel(const double *__restrict__ adj, const long long *__restrict
     }
 }
 
+// ------------------------------------------------- rank-bitmap median + fused Savitzky-Golay
+// The sliding-histogram kernel above is one long serial chain per thread (w-1 fill steps before the
+// first output, then a histogram read-modify-write per step): latency- and occupancy-bound at 8 % of
+// the HBM roofline.  This kernel removes the fill and the private histograms:
+//
+//   * one CTA per tile = up to ~4000 consecutive outputs of ONE segment; its A + w samples are
+//     staged in shared memory once (coalesced, int16);
+//   * for a band of 32 consecutive value levels the CTA builds level bitmaps with warp ballots
+//     (bit i of B[r] = sample i <= level r) plus per-word prefix popcounts, so the rank
+//     F(r, j) = #{samples of window j <= level r} is TWO popcount lookups for ANY window j - O(1)
+//     random access instead of a w-step fill;
+//   * every thread owns a short run of R (~11) consecutive outputs: binary search over the band for
+//     its first median (7 rank queries), then slides (+1 / -1 sample, two compares) and consults the
+//     bitmaps only when the median changes level;
+//   * the band is centred on a sampled median of the tile; outputs whose median falls outside are
+//     picked up by further passes with the band moved down / up (rare), a tile that cannot be
+//     resolved (non-integer samples, |x| > 32000, > kRankMaxPasses bands) is flagged and redone by
+//     the histogram / generic path;
+//   * the adjusted series never leaves the SM: Savitzky-Golay (interior stencil + per-segment edge
+//     fits) runs on the shared-memory copy (+-sg_w/2 halo outputs are recomputed per tile) and only
+//     the final float64 result is written, warp-staged for coalesced stores.
+// HBM traffic = the algorithmic 4 B in + 8 B out per position (the split design moved 28 B).
+#ifndef FTK_RANK_THREADS
+#define FTK_RANK_THREADS 384
+#endif
+constexpr int kRankThreads = FTK_RANK_THREADS;
+constexpr int kRankWarps = kRankThreads / 32;
+constexpr int kRankLevels = 32;        // band rows: one ballot row per lane
+constexpr int kRankMaxPasses = 12;
+constexpr int kRankMaxAbs = 32000;     // samples are staged as int16
+
+struct RankGeom {                       // shared-memory carve-up, identical on host and device
+    int a_slots;                        // adj elements incl. padding
+    int nwp;                            // words per bitmap row (odd, >= ceil(S/32) + 1)
+    int s_pad;                          // staged samples (multiple of 32)
+};
+__host__ __device__ inline RankGeom rank_geom(int a_cap, int s_cap) {
+    RankGeom g;
+    g.a_slots = a_cap + (a_cap >> 4) + 2;
+    const int nword = (s_cap + 31) / 32;
+    g.nwp = (nword + 1) | 1;
+    if (g.nwp < 69) g.nwp = 69;     // the bitmap area doubles as the 12 x 136-double store staging
+    g.s_pad = nword * 32;
+    return g;
+}
+template <typename AdjT>
+__host__ __device__ inline size_t rank_smem_bytes(int a_cap, int s_cap) {
+    const RankGeom g = rank_geom(a_cap, s_cap);
+    size_t b = (size_t)g.a_slots * sizeof(AdjT);
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)kRankLevels * g.nwp * 4;       // bitmaps
+    b += (size_t)kRankLevels * g.nwp * 2;       // per-word prefix popcounts
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)(g.s_pad + 32) * 2;            // samples
+    return b;
+}
+
+__device__ __forceinline__ bool rank_stage(float v, int &iv) {
+    iv = (int)v;
+    return (v == (float)iv) && (fabsf(v) <= (float)kRankMaxAbs);
+}
+__device__ __forceinline__ bool rank_stage(int v, int &iv) {
+    iv = v;
+    return (v >= -kRankMaxAbs) && (v <= kRankMaxAbs);
+}
+
+// SHIFT = subtract_edges (per-segment fp64 shift): the adjusted value is then a general double;
+// without it 2 * adj is an integer and the tile keeps it as int32.
+template <typename InT, bool SHIFT, int SGW>   // SGW: 21 = unrolled default, 0 = runtime window, -1 = no smoothing
+__global__ void __launch_bounds__(kRankThreads, 3)
+adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_off,
+                   const long long *__restrict__ seg_out_off, const double *__restrict__ seg_shift,
+                   const int *__restrict__ tile_seg, const int *__restrict__ tile_t0,
+                   const int *__restrict__ tile_n, int w, int sg_w, const double *__restrict__ coef,
+                   const double *__restrict__ edge_first, const double *__restrict__ edge_last,
+                   int a_cap, int s_cap, double *__restrict__ out, unsigned char *__restrict__ tile_flag) {
+    using AdjT = typename std::conditional<SHIFT, double, int>::type;
+    extern __shared__ __align__(16) unsigned char rank_smem[];
+    __shared__ int s_ctl[4];            // 0: need lower band, 1: need higher band, 2: hard / bad, 3: centre
+    __shared__ double s_coef[kAdjMaxSg + 1];
+    const RankGeom G = rank_geom(a_cap, s_cap);
+    AdjT *__restrict__ adj = reinterpret_cast<AdjT *>(rank_smem);
+    size_t o_b = ((size_t)G.a_slots * sizeof(AdjT) + 15) & ~(size_t)15;
+    unsigned *__restrict__ B = reinterpret_cast<unsigned *>(rank_smem + o_b);
+    unsigned short *__restrict__ Wp = reinterpret_cast<unsigned short *>(B + kRankLevels * G.nwp);
+    size_t o_x = (o_b + (size_t)kRankLevels * G.nwp * 6 + 15) & ~(size_t)15;
+    short *__restrict__ xs = reinterpret_cast<short *>(rank_smem + o_x);
+    const int nwp = G.nwp;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int sg = tile_seg[tile];
+    const int t0 = tile_t0[tile], n_t = tile_n[tile];
+    const long long seg0 = seg_off[sg];
+    const int n = (int)(seg_off[sg + 1] - seg0);
+    const int n_out = n - w;
+    const int half = (SGW < 0) ? 0 : (sg_w >> 1);
+    // adjusted values this tile needs: its outputs +- half, plus the first / last sg_w of the
+    // segment when it holds edge outputs
+    int a0 = max(t0 - half, 0), a1 = min(t0 + n_t + half, n_out);
+    if (SGW >= 0) {
+        if (t0 < half) a1 = max(a1, min(sg_w, n_out));
+        if (t0 + n_t > n_out - half) a0 = min(a0, max(n_out - sg_w, 0));
+    }
+    const int A = a1 - a0, S = A + w;
+    if (tid < 3) s_ctl[tid] = 0;
+    if (SGW >= 0) for (int i = tid; i < sg_w; i += kRankThreads) s_coef[i] = coef[i];
+    bool bad = (A > a_cap) || (S > s_cap) || (A <= 0);
+    // ---- stage the samples (coalesced), validate: integer-valued and small
+    if (!bad) {
+        const InT *__restrict__ src = x + seg0 + a0;
+        for (int i = tid; i < G.s_pad; i += kRankThreads) {
+            int iv = 32767;                       // sentinel beyond every level: never counted
+            if (i < S) {
+                if (!rank_stage(__ldg(src + i), iv)) { bad = true; iv = 0; }
+            }
+            xs[i] = (short)iv;
+        }
+    }
+    if (__syncthreads_or(bad ? 1 : 0)) {
+        if (tid == 0) tile_flag[tile] = 1;
+        return;
+    }
+    // ---- band centre: median of 32 samples spread over the tile (rank by 32 shuffles)
+    if (warp == 0) {
+        const int mine = xs[(int)(((long long)lane * S) >> 5) + (S >> 6)];
+        int rank = 0;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) {
+            const int o = __shfl_sync(0xffffffffu, mine, l);
+            rank += (o < mine) || (o == mine && l < lane);
+        }
+        if (rank == 16) s_ctl[3] = mine;
+    }
+    __syncthreads();
+
+    const int kl = (w - 1) >> 1, ku = w >> 1;   // 0-based ranks of the two middle order statistics
+    const int R = (A + kRankThreads - 1) / kRankThreads;   // outputs per thread (<= 32)
+    const int j0 = tid * R;
+    double shift = 0.0;
+    if (SHIFT) shift = seg_shift[sg];
+    auto cnt = [&](int r, int i) -> int {       // #{samples [0, i) <= level r}
+        const int wd = i >> 5;
+        return (int)Wp[r * nwp + wd] + __popc(B[r * nwp + wd] & ((1u << (i & 31)) - 1u));
+    };
+    auto F = [&](int r, int j) -> int { return cnt(r, j + w) - cnt(r, j); };
+
+    unsigned resolved = 0;
+    int L0 = s_ctl[3] - (kRankLevels / 2 - 1);   // row r <-> level L0 - 1 + r; medians on rows 1..31 resolve
+    int lo_band = L0, hi_band = L0;
+    bool is_lowest = true, is_highest = true, pend_lo = false, pend_hi = false;
+    for (int pass = 0;; ++pass) {
+        // ---- level bitmaps: one ballot per row, lane r keeps row r
+        for (int wd = warp; wd < nwp; wd += kRankWarps) {
+            const int i = wd * 32 + lane;
+            const int v = (i < G.s_pad) ? (int)xs[i] : 32767;
+            unsigned mine = 0;
+#pragma unroll
+            for (int r = 0; r < kRankLevels; ++r) {
+                const unsigned b = __ballot_sync(0xffffffffu, v <= L0 - 1 + r);
+                if (lane == r) mine = b;
+            }
+            B[lane * nwp + wd] = mine;
+        }
+        __syncthreads();
+        // ---- per-word exclusive prefix popcounts of every row
+        for (int r = warp; r < kRankLevels; r += kRankWarps) {
+            int carry = 0;
+            for (int w0 = 0; w0 < nwp; w0 += 32) {
+                const int wd = w0 + lane;
+                const int c = (wd < nwp) ? __popc(B[r * nwp + wd]) : 0;
+                int t = c;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, t, off);
+                    if (lane >= off) t += o;
+                }
+                if (wd < nwp) Wp[r * nwp + wd] = (unsigned short)(carry + t - c);
+                carry += __shfl_sync(0xffffffffu, t, 31);
+            }
+        }
+        __syncthreads();
+        // ---- every thread walks its run
+        {
+            bool valid = false;
+            int m = 0, c_lt = 0, hm = 0;
+            for (int i = 0; i < R; ++i) {
+                const int j = j0 + i;
+                if (j >= A) break;
+                if ((resolved >> i) & 1u) { valid = false; continue; }
+                if (valid) {
+                    const int lv = L0 - 1 + m;
+                    const int xo = xs[j - 1], xi = xs[j - 1 + w];
+                    c_lt += (xi < lv) - (xo < lv);
+                    hm += (xi == lv) - (xo == lv);
+                    while (c_lt > kl) {                 // median moved down
+                        if (--m < 1) { valid = false; s_ctl[0] = 1; break; }
+                        const int q = F(m - 1, j);
+                        hm = c_lt - q; c_lt = q;
+                    }
+                    while (valid && c_lt + hm <= kl) {  // median moved up
+                        c_lt += hm;
+                        if (++m > kRankLevels - 1) { valid = false; s_ctl[1] = 1; break; }
+                        hm = F(m, j) - c_lt;
+                    }
+                } else {
+                    int flo = F(0, j);
+                    if (flo >= kl + 1) { s_ctl[0] = 1; continue; }          // median below the band
+                    int fhi = F(kRankLevels - 1, j);
+                    if (fhi < kl + 1) { s_ctl[1] = 1; continue; }           // median above the band
+                    int lo = 0, hi = kRankLevels - 1;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        const int f = F(mid, j);
+                        if (f >= kl + 1) { hi = mid; fhi = f; } else { lo = mid; flo = f; }
+                    }
+                    m = hi; c_lt = flo; hm = fhi - flo; valid = true;
+                }
+                if (!valid) continue;
+                int mu = m;                              // upper median: next occupied level if rank ku is past bin m
+                if (c_lt + hm <= ku) {
+                    const int below = c_lt + hm;
+                    int r = m;
+                    bool found = false;
+                    while (++r <= kRankLevels - 1) {
+                        if (F(r, j) > below) { found = true; break; }
+                    }
+                    if (!found) { s_ctl[2] = 1; continue; }   // gap wider than the band: let the generic path do it
+                    mu = r;
+                }
+                const int bc = xs[j + (w >> 1)];
+                const int vm = L0 - 1 + m, vu = L0 - 1 + mu;
+                if (SHIFT) {
+                    const double lo_s = (double)vm - shift, hi_s = (double)vu - shift;
+                    adj[sg_slot(j)] = (AdjT)(((double)bc - shift) - (lo_s + hi_s) / 2.0);
+                } else {
+                    adj[sg_slot(j)] = (AdjT)(2 * bc - vm - vu);          // 2 * adj, exact
+                }
+                resolved |= 1u << i;
+            }
+        }
+        const int mine_n = max(min(A - j0, R), 0);
+        const bool done = (__popc(resolved) >= mine_n);
+        const int all_done = __syncthreads_and(done ? 1 : 0);
+        const int need_lo = s_ctl[0], need_hi = s_ctl[1], hard = s_ctl[2];
+        __syncthreads();
+        if (all_done) break;
+        if (tid == 0) { s_ctl[0] = 0; s_ctl[1] = 0; }
+        if (is_lowest) pend_lo = need_lo != 0;
+        if (is_highest) pend_hi = need_hi != 0;
+        if (hard || pass + 1 >= kRankMaxPasses || (!pend_lo && !pend_hi)) {
+            if (tid == 0) tile_flag[tile] = 1;
+            return;
+        }
+        if (pend_lo) { L0 = lo_band - (kRankLevels - 1); lo_band = L0; is_lowest = true; is_highest = false; }
+        else { L0 = hi_band + (kRankLevels - 1); hi_band = L0; is_highest = true; is_lowest = false; }
+        __syncthreads();    // s_ctl reset visible before the next walk; bitmaps free to rebuild
+    }
+
+    // ---- Savitzky-Golay on the shared-memory series + coalesced store
+    double *__restrict__ dst = out + seg_out_off[sg] + t0;
+    auto adj_at = [&](int k) -> double {         // adjusted value at tile-relative index k
+        if (SHIFT) return (double)adj[sg_slot(k)];
+        return (double)adj[sg_slot(k)] * 0.5;
+    };
+    if (SGW < 0) {
+        for (int k = tid; k < n_t; k += kRankThreads) dst[k] = adj_at(t0 - a0 + k);
+        return;
+    }
+    double *__restrict__ stage = reinterpret_cast<double *>(B) + warp * (128 + 8);   // per-warp 128 outputs, padded
+    const int groups = (n_t + 127) / 128;        // a warp-iteration covers 128 consecutive outputs
+    for (int gi = warp; gi < groups; gi += kRankWarps) {
+        const int k0 = gi * 128 + 4 * lane;      // first of this lane's 4 consecutive outputs (tile-relative output index)
+        const int c0 = t0 - a0 + k0 - half;      // adj index of the first tap of output k0
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        auto ld = [&](int k) -> double { return (k >= 0 && k < A) ? adj_at(k) : 0.0; };
+        double r0 = ld(c0), r1 = ld(c0 + 1), r2 = ld(c0 + 2);
+        if (SGW > 0) {
+#pragma unroll
+            for (int i = 0; i < (SGW > 0 ? SGW : 1); ++i) {
+                const double r3 = ld(c0 + i + 3);
+                const double c = s_coef[i];
+                acc0 += c * r0; acc1 += c * r1; acc2 += c * r2; acc3 += c * r3;
+                r0 = r1; r1 = r2; r2 = r3;
+            }
+        } else {
+            for (int i = 0; i < sg_w; ++i) {
+                const double r3 = ld(c0 + i + 3);
+                const double c = s_coef[i];
+                acc0 += c * r0; acc1 += c * r1; acc2 += c * r2; acc3 += c * r3;
+                r0 = r1; r1 = r2; r2 = r3;
+            }
+        }
+        double v[4] = {acc0, acc1, acc2, acc3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = t0 + k0 + k;           // segment-relative output index
+            if (k0 + k < n_t) {
+                if (j < half) {                  // polynomial fit of the first sg_w adjusted values
+                    double e = 0.0;
+                    for (int i = 0; i < sg_w; ++i) e += edge_first[j * sg_w + i] * adj_at(i - a0);
+                    v[k] = e;
+                } else if (j >= n_out - half) {
+                    double e = 0.0;
+                    const int jj = j - (n_out - half);
+                    for (int i = 0; i < sg_w; ++i) e += edge_last[jj * sg_w + i] * adj_at(n_out - sg_w + i - a0);
+                    v[k] = e;
+                }
+            }
+            const int e_ = 4 * lane + k;
+            stage[e_ + (e_ >> 4)] = v[k];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e_ = k * 32 + lane;
+            const int o = gi * 128 + e_;
+            if (o < n_t) dst[o] = stage[e_ + (e_ >> 4)];
+        }
+        __syncwarp();
+    }
+}
+
 // subtract_edges (frag/_adjust_wps.py:119-123): shift[s] = mean(mean(x[:e]), mean(x[-e:]))
 __global__ void adjust_edge_shift_kernel(const float *__restrict__ x, const long long *__restrict__ seg_off,
                                          int n_seg, int edge, double *__restrict__ shift) {
@@ -467,4 +792,55 @@ extern "C" int ftk_savgol_f64(const double *adj, const int64_t *seg_out_off, int
                                                                  edge_last, out);
     FTK_CHECK_LAUNCH("adjust_savgol_kernel");
     return FTK_OK;
+}
+
+// One CTA per tile (tile_seg / tile_t0 / tile_n: segment, first output and output count, planned
+// by the caller so that every tile needs at most a_cap adjusted values and s_cap samples).
+template <typename InT>
+static int launch_rank(const InT *x, const long long *so, const long long *oo, const double *seg_shift,
+                       const int *tile_seg, const int *tile_t0, const int *tile_n, int64_t n_tiles, int w,
+                       int sg_w, const double *coef, const double *ef, const double *el, int a_cap, int s_cap,
+                       double *out, unsigned char *flag, cudaStream_t stream) {
+    const unsigned grid = (unsigned)n_tiles;
+#define FTK_RANK(SHIFT, SGW)                                                                                      \
+    do {                                                                                                          \
+        using AdjT = typename std::conditional<SHIFT, double, int>::type;                                         \
+        const int smem = (int)rank_smem_bytes<AdjT>(a_cap, s_cap);                                                \
+        if (smem > 227 * 1024) return FTK_E_RANGE;                                                                \
+        FTK_CUDA_TRY(cudaFuncSetAttribute(adjust_rank_kernel<InT, SHIFT, SGW>,                                     \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
+        adjust_rank_kernel<InT, SHIFT, SGW><<<grid, kRankThreads, smem, stream>>>(                                 \
+            x, so, oo, seg_shift, tile_seg, tile_t0, tile_n, w, sg_w, coef, ef, el, a_cap, s_cap, out, flag);     \
+    } while (0)
+    if (seg_shift) {
+        if (sg_w == 0) FTK_RANK(true, -1); else if (sg_w == 21) FTK_RANK(true, 21); else FTK_RANK(true, 0);
+    } else {
+        if (sg_w == 0) FTK_RANK(false, -1); else if (sg_w == 21) FTK_RANK(false, 21); else FTK_RANK(false, 0);
+    }
+#undef FTK_RANK
+    FTK_CHECK_LAUNCH("adjust_rank_kernel");
+    return FTK_OK;
+}
+
+extern "C" int ftk_adjust_rank_f64(const void *x, int32_t x_kind, const int64_t *seg_off, const int64_t *seg_out_off,
+                                   const double *seg_shift, int32_t n_seg, const int32_t *tile_seg,
+                                   const int32_t *tile_t0, const int32_t *tile_n, int64_t n_tiles, int32_t w,
+                                   int32_t sg_w, const double *coef, const double *edge_first,
+                                   const double *edge_last, int32_t a_cap, int32_t s_cap, double *out,
+                                   uint8_t *tile_flag, ftk_stream_t stream_) {
+    if (n_tiles == 0 || n_seg == 0) return FTK_OK;
+    if (!x || !seg_off || !seg_out_off || !tile_seg || !tile_t0 || !tile_n || !out || !tile_flag) return FTK_E_INVALID;
+    if (n_seg < 0 || n_tiles < 0 || n_tiles > INT32_MAX || (x_kind != 0 && x_kind != 1)) return FTK_E_INVALID;
+    if (w < 2 || (w & 1) || w > 32767) return FTK_E_INVALID;
+    if (sg_w != 0 && (sg_w < 1 || !(sg_w & 1) || sg_w > kAdjMaxSg || !coef || !edge_first || !edge_last)) return FTK_E_INVALID;
+    if (a_cap < 1 || a_cap > 32 * kRankThreads || s_cap < a_cap + w || s_cap > 65535 - 64) return FTK_E_RANGE;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    FTK_CUDA_TRY(cudaMemsetAsync(tile_flag, 0, (size_t)n_tiles, stream));
+    const long long *so = reinterpret_cast<const long long *>(seg_off);
+    const long long *oo = reinterpret_cast<const long long *>(seg_out_off);
+    if (x_kind == 0)
+        return launch_rank<float>(static_cast<const float *>(x), so, oo, seg_shift, tile_seg, tile_t0, tile_n, n_tiles,
+                                  w, sg_w, coef, edge_first, edge_last, a_cap, s_cap, out, tile_flag, stream);
+    return launch_rank<int>(static_cast<const int *>(x), so, oo, seg_shift, tile_seg, tile_t0, tile_n, n_tiles,
+                            w, sg_w, coef, edge_first, edge_last, a_cap, s_cap, out, tile_flag, stream);
 }

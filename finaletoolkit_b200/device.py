@@ -491,16 +491,61 @@ def _savgol_tables_cached(window: int, degree: int):
     return coef, edge_first, edge_last
 
 
+_RANK_T_MAX = 4096          # outputs per tile of the rank-bitmap kernel
+_RANK_SMEM_MAX = 227 * 1024
+
+
+def rank_tiles(seg_lengths, w: int, sg_w: int, t_max: int = _RANK_T_MAX):
+    """Tile plan of ``ftk_adjust_rank_f64``: every segment's ``n - w`` outputs split evenly into
+    pieces of at most ``t_max``.  Returns ``(tile_seg, tile_t0, tile_n, a_cap, s_cap)`` (int32 arrays;
+    caps = most adjusted values / samples a tile stages, same arithmetic as the kernel)."""
+    seg_lengths = np.asarray(seg_lengths, dtype=np.int64)
+    n_out = seg_lengths - int(w)
+    pieces = np.maximum(-(-n_out // int(t_max)), 0)
+    piece = np.where(pieces > 0, -(-n_out // np.maximum(pieces, 1)), 0)
+    tile_seg = np.repeat(np.arange(len(seg_lengths), dtype=np.int64), pieces)
+    first = np.cumsum(pieces) - pieces
+    k = np.arange(int(pieces.sum()), dtype=np.int64) - np.repeat(first, pieces)
+    t0 = k * piece[tile_seg]
+    n_t = np.minimum(piece[tile_seg], n_out[tile_seg] - t0)
+    half = int(sg_w) >> 1
+    no = n_out[tile_seg]
+    a0 = np.maximum(t0 - half, 0)
+    a1 = np.minimum(t0 + n_t + half, no)
+    if sg_w:
+        a1 = np.where(t0 < half, np.maximum(a1, np.minimum(int(sg_w), no)), a1)
+        a0 = np.where(t0 + n_t > no - half, np.minimum(a0, np.maximum(no - int(sg_w), 0)), a0)
+    A = a1 - a0
+    a_cap = int(A.max()) if A.size else 1
+    return (tile_seg.astype(np.int32), t0.astype(np.int32), n_t.astype(np.int32), a_cap, a_cap + int(w))
+
+
+def _rank_smem(a_cap: int, s_cap: int, shifted: bool) -> int:
+    """Shared memory of one ``adjust_rank_kernel`` CTA (rank_smem_bytes in csrc/ftk_adjust.cu)."""
+    a_slots = a_cap + (a_cap >> 4) + 2
+    nword = (s_cap + 31) // 32
+    nwp = max((nword + 1) | 1, 69)
+    b = (a_slots * (8 if shifted else 4) + 15) & ~15
+    b += 32 * nwp * 6
+    b = (b + 15) & ~15
+    return b + (nword * 32 + 32) * 2
+
+
 def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, savgol=True,
                     savgol_window_size=21, savgol_poly_deg=2, subtract_edges=False, edge_size=500,
-                    run_len=None):
+                    run_len=None, impl=None):
     """Median/mean-adjust + Savitzky-Golay smooth contiguous raw-WPS segments on the GPU.
 
-    ``x``: float32 samples of all segments back to back (numpy or CUDA tensor);
-    ``seg_lengths``: samples per segment.  Returns ``(out float64 CUDA tensor, out_off)``
-    with segment s's ``n_s - w`` outputs at ``out[out_off[s]:out_off[s+1]]``.
-    Raises ValueError exactly where the reference does (frag/_adjust_wps.py:125-129 and
-    numpy/scipy shape errors for odd windows / too-short segments).
+    ``x``: samples of all segments back to back - float32 (numpy or CUDA tensor; bigWig values) or an
+    int32 CUDA tensor (device-resident WPS, no conversion pass); ``seg_lengths``: samples per segment.
+    Returns ``(out float64 CUDA tensor, out_off)`` with segment s's ``n_s - w`` outputs at
+    ``out[out_off[s]:out_off[s+1]]``.  Raises ValueError exactly where the reference does
+    (frag/_adjust_wps.py:125-129 and numpy/scipy shape errors for odd windows / too-short segments).
+
+    The median path runs the fused rank-bitmap kernel (``ftk_adjust_rank_f64``: median + Savitzky-Golay in
+    one pass, 12 B of HBM traffic per position); tiles it flags (non-integer samples, huge values) and the
+    mean path go through the sliding-histogram / generic kernels + the separate Savitzky-Golay kernel.
+    ``impl="hist"`` forces that older path (``run_len`` only applies to it).
     """
     t = torch()
     dev = require_cuda(x.device if t.is_tensor(x) and x.is_cuda else None)
@@ -518,6 +563,53 @@ def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, sav
     n_seg = len(seg_lengths)
     seg_off = np.zeros(n_seg + 1, np.int64); np.cumsum(seg_lengths, out=seg_off[1:])
     out_off = np.zeros(n_seg + 1, np.int64); np.cumsum(n_out, out=out_off[1:])
+    n_total = int(out_off[-1])
+    if t.is_tensor(x) and x.is_cuda and x.dtype == t.int32:
+        xd = x.contiguous()
+    else:
+        xd = x if t.is_tensor(x) else _to_device(np.asarray(x), dev, np.float32)
+        xd = xd.to(dev, t.float32).contiguous()
+    out = t.empty(max(n_total, 1), dtype=t.float64, device=dev)
+    if n_total == 0:
+        return out[:0], out_off
+    d_seg = _to_device(seg_off, dev, np.int64)
+    d_out = _to_device(out_off, dev, np.int64)
+    L = lib()
+    sp = _stream_ptr(dev)
+    shift_ptr = 0
+    if subtract_edges:
+        xf = xd if xd.dtype == t.float32 else xd.to(t.float32)
+        shift = t.empty(n_seg, dtype=t.float64, device=dev)
+        check(L.ftk_adjust_edge_shift_f64(xf.data_ptr(), d_seg.data_ptr(), n_seg, int(edge_size),
+                                          shift.data_ptr(), sp), "ftk_adjust_edge_shift_f64")
+        shift_ptr = shift.data_ptr()
+    sg_w = int(savgol_window_size) if savgol else 0
+    tables = None
+    if savgol:
+        coef, ef, el = savgol_tables(sg_w, int(savgol_poly_deg))
+        tables = (_to_device(coef, dev, np.float64),
+                  _to_device(ef.reshape(-1) if ef.size else np.zeros(1), dev, np.float64),
+                  _to_device(el.reshape(-1) if el.size else np.zeros(1), dev, np.float64))
+
+    # ---- fused rank-bitmap kernel (median path)
+    if not use_mean and impl != "hist" and w <= 32766 and sg_w <= 127:
+        tile_seg, tile_t0, tile_n, a_cap, s_cap = rank_tiles(seg_lengths, w, sg_w)
+        if s_cap <= 65535 - 64 and _rank_smem(a_cap, s_cap, bool(subtract_edges)) <= _RANK_SMEM_MAX:
+            d_ts, d_t0, d_tn = (_to_device(a, dev, np.int32) for a in (tile_seg, tile_t0, tile_n))
+            flag = t.empty(len(tile_seg), dtype=t.uint8, device=dev)
+            check(L.ftk_adjust_rank_f64(
+                xd.data_ptr(), 1 if xd.dtype == t.int32 else 0, d_seg.data_ptr(), d_out.data_ptr(), shift_ptr, n_seg,
+                d_ts.data_ptr(), d_t0.data_ptr(), d_tn.data_ptr(), len(tile_seg), w, sg_w,
+                tables[0].data_ptr() if tables else 0, tables[1].data_ptr() if tables else 0,
+                tables[2].data_ptr() if tables else 0, a_cap, s_cap, out.data_ptr(), flag.data_ptr(), sp),
+                "ftk_adjust_rank_f64")
+            if not bool(flag.any().item()):
+                return out[:n_total], out_off
+            # some tile could not be handled: redo the call on the general path (rare: non-integer input)
+
+    # ---- sliding-histogram / generic kernels + separate Savitzky-Golay
+    if xd.dtype != t.float32:
+        xd = xd.to(t.float32)
     if run_len is None:
         # one thread slides one run: aim for a single full wave of the 148 SMs x 3 CTAs x 128 threads,
         # keep the w-sample window fill amortised (>= 1024 outputs) and split short segments evenly
@@ -530,23 +622,9 @@ def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, sav
     runs = -(-n_out // run_len)
     run_off = np.zeros(n_seg + 1, np.int64); np.cumsum(runs, out=run_off[1:])
     n_runs = int(run_off[-1])
-    xd = x if t.is_tensor(x) else _to_device(np.asarray(x), dev, np.float32)
-    xd = xd.to(dev, t.float32).contiguous()
-    n_total = int(out_off[-1])
-    out = t.empty(max(n_total, 1), dtype=t.float64, device=dev)
     if n_runs == 0:
         return out[:0], out_off
-    d_seg = _to_device(seg_off, dev, np.int64)
-    d_out = _to_device(out_off, dev, np.int64)
     d_run = _to_device(run_off, dev, np.int64)
-    L = lib()
-    sp = _stream_ptr(dev)
-    shift_ptr = 0
-    if subtract_edges:
-        shift = t.empty(n_seg, dtype=t.float64, device=dev)
-        check(L.ftk_adjust_edge_shift_f64(xd.data_ptr(), d_seg.data_ptr(), n_seg, int(edge_size),
-                                          shift.data_ptr(), sp), "ftk_adjust_edge_shift_f64")
-        shift_ptr = shift.data_ptr()
     adj = t.empty(max(n_total, 1), dtype=t.float64, device=dev) if savgol else out
     fb = t.empty(n_runs, dtype=t.uint8, device=dev)
     check(L.ftk_adjust_wps_f64(xd.data_ptr(), d_seg.data_ptr(), d_out.data_ptr(), d_run.data_ptr(), shift_ptr,
@@ -560,12 +638,8 @@ def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, sav
                                            int(bool(use_mean)), int(run_len), adj.data_ptr(),
                                            scratch.data_ptr(), sp), "ftk_adjust_wps_generic_f64")
     if savgol:
-        coef, ef, el = savgol_tables(int(savgol_window_size), int(savgol_poly_deg))
-        d_coef = _to_device(coef, dev, np.float64)
-        d_ef = _to_device(ef.reshape(-1) if ef.size else np.zeros(1), dev, np.float64)
-        d_el = _to_device(el.reshape(-1) if el.size else np.zeros(1), dev, np.float64)
-        check(L.ftk_savgol_f64(adj.data_ptr(), d_out.data_ptr(), n_seg, n_total, int(savgol_window_size),
-                               d_coef.data_ptr(), d_ef.data_ptr(), d_el.data_ptr(), out.data_ptr(), sp),
+        check(L.ftk_savgol_f64(adj.data_ptr(), d_out.data_ptr(), n_seg, n_total, sg_w,
+                               tables[0].data_ptr(), tables[1].data_ptr(), tables[2].data_ptr(), out.data_ptr(), sp),
               "ftk_savgol_f64")
     return out[:n_total], out_off
 

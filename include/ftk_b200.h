@@ -322,6 +322,24 @@ int ftk_savgol_f64(const double *adj_dev, const int64_t *seg_out_off_dev, int32_
                    int32_t sg_w, const double *coef_dev, const double *edge_first_dev,
                    const double *edge_last_dev, double *out_dev, ftk_stream_t stream);
 
+/* Fused running-median adjust + Savitzky-Golay for integer-valued input (raw WPS), one CTA per tile:
+ * rank bitmaps in shared memory instead of per-thread sliding histograms, the adjusted series never
+ * leaves the SM (frag/_adjust_wps.py:25-45 _local_filter(median) + :131-138 savgol_filter in ONE kernel).
+ * x_dev: float32 (x_kind 0, bigWig values) or int32 (x_kind 1, device-resident WPS) samples of all
+ * segments back to back.  Tiles are planned by the caller: tile t covers outputs
+ * [tile_t0[t], tile_t0[t] + tile_n[t]) of segment tile_seg[t]; a_cap / s_cap = the largest number of
+ * adjusted values / samples any tile needs (outputs +- sg_w/2 clipped to the segment, + w samples).
+ * sg_w = 0: no smoothing (out = adjusted series).  seg_shift_dev NULL = no subtract_edges.
+ * tile_flag_dev[t] (uint8, zeroed here) is set for tiles that could not be handled (non-integer or
+ * |x| > 32000 samples, value spread beyond the searched bands): the caller redoes those through
+ * ftk_adjust_wps_f64 / ftk_adjust_wps_generic_f64 + ftk_savgol_f64.  Results are identical to that path. */
+int ftk_adjust_rank_f64(const void *x_dev, int32_t x_kind, const int64_t *seg_off_dev,
+                        const int64_t *seg_out_off_dev, const double *seg_shift_dev, int32_t n_seg,
+                        const int32_t *tile_seg_dev, const int32_t *tile_t0_dev, const int32_t *tile_n_dev,
+                        int64_t n_tiles, int32_t median_window, int32_t sg_w, const double *coef_dev,
+                        const double *edge_first_dev, const double *edge_last_dev, int32_t a_cap, int32_t s_cap,
+                        double *out_dev, uint8_t *tile_flag_dev, ftk_stream_t stream);
+
 /* ------------------------------------------------------- cleavage profile
  * Replaces _coverage_and_ends + the proportion step of cleavage_profile
  * (frag/_cleavage_profile.py:33-90, 190-217).  Tiles as for WPS (ftk_wps_plan_tiles with

@@ -104,3 +104,69 @@ def test_errors():
         adjust_segments(x, [500], median_window_size=101)
     with pytest.raises(ValueError):
         adjust_segments(x, [500], median_window_size=490)  # 10 outputs < savgol window
+
+
+def _int_series(rng, l, kind):
+    if kind == 0:        # WPS-like random walk
+        return np.cumsum(rng.integers(-2, 3, l))
+    if kind == 1:        # wide spread: the median wanders over > 32 levels -> several band passes
+        return (np.cumsum(rng.integers(-9, 10, l)) + rng.integers(-40, 41, l))
+    if kind == 2:        # constant + isolated spikes (upper median far above the lower one)
+        v = np.full(l, 7); v[rng.choice(l, l // 50, replace=False)] = 3000
+        return v
+    if kind == 3:        # two plateaus 500 levels apart: the band has to jump
+        v = np.where(np.arange(l) < l // 2, -250, 250) + rng.integers(-3, 4, l)
+        return v
+    return rng.integers(-15, 16, l) * 2   # only even values: gaps between occupied levels
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_rank_kernel_vs_oracle_and_hist_path(seed):
+    """The fused rank-bitmap kernel (median + SG in one pass): vs the oracle (numpy median + scipy
+    savgol) and bit-for-bit vs the sliding-histogram path; float32 and int32 inputs; multi-tile segments."""
+    import torch
+    from finaletoolkit_b200.device import adjust_segments
+    rng = np.random.default_rng(50 + seed)
+    w = int(rng.choice([2, 100, 250, 1000]))
+    lens = [int(v) for v in rng.integers(w + 21, w + 9000, 5)] + [w + 21, w + 22, w + 4096, w + 4097, 13_000 + w]
+    xs = [_int_series(rng, l, (seed + i) % 5) for i, l in enumerate(lens)]
+    x = np.concatenate(xs)
+    for savgol in (True, False):
+        for sub in (False, True):
+            kw = dict(median_window_size=w, savgol=savgol, savgol_window_size=21, savgol_poly_deg=2, subtract_edges=sub,
+                      edge_size=33)
+            got, off = adjust_segments(x.astype(np.float32), lens, **kw)
+            got_i, _ = adjust_segments(torch.from_numpy(x.astype(np.int32)).cuda(), lens, **kw)
+            old, _ = adjust_segments(x.astype(np.float32), lens, impl="hist", **kw)
+            torch.cuda.synchronize()
+            assert torch.equal(got, got_i)
+            assert torch.equal(got, old), (seed, w, savgol, sub, float((got - old).abs().max()))
+            gh = got.cpu().numpy()
+            for i, v in enumerate(xs):
+                xx = v.astype(np.float64)
+                if sub:
+                    xx = xx - np.mean([np.mean(xx[:33]), np.mean(xx[-33:])])
+                exp = O.adjust_core(xx, w, False, savgol, 21, 2)
+                np.testing.assert_allclose(gh[off[i]:off[i + 1]], exp, rtol=RTOL, atol=1e-8, err_msg=f"seg {i} w={w}")
+                if not savgol and not sub:
+                    assert np.array_equal(gh[off[i]:off[i + 1]], exp)     # pre-SG median series is exact
+
+
+def test_rank_kernel_other_sg_windows_and_fallback():
+    """Runtime Savitzky-Golay windows (5, 51) and the flagged-tile fallback (one non-integer sample)."""
+    import torch
+    from finaletoolkit_b200.device import adjust_segments
+    rng = np.random.default_rng(3)
+    lens = [3000, 5000, 1200]
+    x = np.concatenate([_int_series(rng, l, 0) for l in lens]).astype(np.float32)
+    for sgw, deg in ((5, 2), (51, 3)):
+        got, off = adjust_segments(x, lens, median_window_size=500, savgol_window_size=sgw, savgol_poly_deg=deg)
+        old, _ = adjust_segments(x, lens, median_window_size=500, savgol_window_size=sgw, savgol_poly_deg=deg, impl="hist")
+        assert torch.equal(got, old)
+    y = x.copy(); y[4000] += 0.5
+    got, off = adjust_segments(y, lens, median_window_size=500)
+    o = 0
+    for l in lens:
+        exp = O.adjust_core(y[o:o + l].astype(np.float64), 500, False, True, 21, 2)
+        np.testing.assert_allclose(got.cpu().numpy()[off[len([1 for q in lens[:lens.index(l)]])]:][:l - 500], exp, rtol=RTOL, atol=1e-8)
+        o += l
