@@ -63,6 +63,7 @@ struct WpsParams {
 
 struct TileCtx {
     int p0, len, mid_lo, g0, glen;
+    int zl_excl;            // fused coverage: a zero-length fragment sitting exactly here is not in the stream
     int eb;                 // b + g0: first event slot of a fragment = fs - eb
     unsigned mid_span;
     bool need_mid;          // tile-uniform: the midpoint test can exclude a contributing fragment
@@ -72,6 +73,7 @@ template <bool ODD>
 __device__ __forceinline__ TileCtx make_tile_ctx(const WpsParams &P, int p0, int len, int mid_lo, int mid_hi) {
     TileCtx t;
     t.p0 = p0; t.len = len; t.mid_lo = mid_lo;
+    t.zl_excl = INT32_MIN;
     t.mid_span = (mid_hi > mid_lo) ? (unsigned)(mid_hi - mid_lo) : 0u;
     // grid of the symmetric-window score G: one extra slot on the left for odd W
     t.g0 = ODD ? p0 - 1 : p0;
@@ -301,7 +303,7 @@ struct __align__(16) StreamDesc {
     int p0, len, mid_lo, mid_hi;
     int n;           // staged fragments (multiple of 16, may be 0)
     int first, last; // first / last chunk of its tile
-    int ivl;         // interval the tile belongs to (fused coverage counts)
+    int ivl;         // interval the tile belongs to (fused coverage counts); bit 31 = its first tile
     long long out_off;
     long long tail_lo, tail_hi;  // ragged end of the contig, read straight from global (rare)
 };
@@ -338,7 +340,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 }
 
 // ---------------------------------------------------------------------------
-// Kernel C ("dual", default): two tiles in flight per CTA.
+// Kernel C ("dual", default for plain WPS): two tiles in flight per CTA.
 // The eight consumer warps are split into two groups of four, each with its own difference
 // array, its own staging buffer and its own named barrier; the producer warp feeds the groups
 // alternately.  While one group scans and stores its tile the other one is scattering the next,
@@ -550,7 +552,7 @@ wps_dual_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restric
 
 
 // ---------------------------------------------------------------------------
-// Kernel D ("hex", default; the only one with the fused coverage / length-histogram pass):
+// Kernel D ("hex"; the one with the fused coverage / length-histogram pass):
 // ONE persistent CTA per SM with SIX consumer groups of four warps and THREE producer warps
 // (producer p feeds groups 2p and 2p+1 exactly like the producer of the dual kernel feeds its
 // two).  Six tiles are in flight per SM as with three dual CTAs, but the SM's shared memory is
@@ -598,8 +600,10 @@ static_assert(sizeof(HexSmem) <= 227 * 1024, "HexSmem must fit the 227 KB a CTA 
 __device__ __forceinline__ void cov_visit(int *__restrict__ hist_s, unsigned long long *__restrict__ ghist,
                                           const CovParams &C, const TileCtx &T, int fs, int fe, int q, int &cnt) {
     const int L = fe - fs;
+    // tabix overlap "stop > S": only a zero-length row sitting on the interval's own start fails it
+    // once its midpoint is inside (zl_excl = S on the interval's first tile, INT32_MIN elsewhere)
     const bool pass = (q >= C.min_mapq) & ((unsigned)(L - C.len_lo) <= C.len_span) &
-                      ((unsigned)(fs + (L >> 1) - T.p0) < (unsigned)T.len) & (fe > T.p0);
+                      ((unsigned)(fs + (L >> 1) - T.p0) < (unsigned)T.len) & ((L > 0) | (fs != T.zl_excl));
     if (pass) {
         ++cnt;
         if (L < C.n_bins) {
@@ -728,6 +732,7 @@ wps_hex_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict
         if (d.tile < 0) break;
         if (d.first) {
             T = make_tile_ctx<ODD>(P, d.p0, d.len, d.mid_lo, d.mid_hi);
+            if (FUSE && d.ivl < 0) T.zl_excl = d.p0;
             cnt = 0;
 #pragma unroll
             for (int j = 0; j < kWpsCap / (4 * kDualGroupThreads); ++j)
@@ -766,7 +771,7 @@ wps_hex_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict
         if (d.last) {
             if (FUSE) {
                 const int c = __reduce_add_sync(0xffffffffu, cnt);
-                if ((gt & 31) == 0 && c) atomicAdd(&counts[d.ivl], (unsigned long long)c);
+                if ((gt & 31) == 0 && c) atomicAdd(&counts[d.ivl & 0x7fffffff], (unsigned long long)c);
             }
             wps_scan_store_group<ODD>(D, S.warp_tot[g], P, T, out + d.out_off, overflow, gt, g);
         }
@@ -866,8 +871,8 @@ extern "C" int ftk_wps_tile_ranges(const int32_t *frag_start, int64_t n_frag,
                               wps_left_reach(window_size, max_len), scratch, static_cast<cudaStream_t>(stream_));
 }
 
-// 0 = hex (one CTA per SM, six tiles in flight; default), 1 = direct (one CTA per tile),
-// 3 = dual (three CTAs per SM, two tiles in flight each - the default of round 1)
+// plain WPS: 0 = dual (three CTAs per SM, two tiles in flight each; default: 0.350 ms at chr1 scale),
+// 1 = direct (one CTA per tile, 0.458 ms), 2 = hex without the fused pass (0.362 ms)
 static int g_wps_impl = 0;
 extern "C" void ftk_debug_set_wps_impl(int impl) { g_wps_impl = impl; }
 
@@ -922,7 +927,7 @@ static int launch_wps(const WpsLaunch &a, OutT *out) {
         FTK_CHECK_LAUNCH("wps_tile_kernel");
         return FTK_OK;
     }
-    if (g_wps_impl == 3) {
+    if (g_wps_impl != 2) {
         int sm = 0;
         int rc = device_sm_count(&sm);
         if (rc != FTK_OK) return rc;
@@ -1031,6 +1036,28 @@ extern "C" int ftk_wps_tiles_i8(const int32_t *frag_start, const int32_t *frag_s
 }
 
 // ---- fused pass: WPS + per-interval coverage + pooled length histogram (wps_hex_kernel<.., FUSE>)
+// a fragment whose midpoint fs + (L >> 1) is >= p0 starts at fs >= p0 - (Lmax >> 1)
+static int64_t fused_left_reach(int32_t window_size, int32_t max_len, int32_t cov_max_len, int32_t max_frag_len) {
+    const int64_t cov_hi = (cov_max_len == FTK_NONE) ? INT32_MAX : cov_max_len;
+    const int64_t lmax = cov_hi < max_frag_len ? cov_hi : max_frag_len;
+    int64_t reach = wps_left_reach(window_size, max_len);
+    if ((lmax >> 1) + 1 > reach) reach = (lmax >> 1) + 1;
+    return reach;
+}
+
+extern "C" int ftk_wps_cov_tile_ranges(const int32_t *frag_start, int64_t n_frag,
+                                       const int32_t *tile_p0, const int32_t *tile_len, int64_t n_tiles,
+                                       int32_t window_size, int32_t max_len, int32_t cov_max_len,
+                                       int32_t max_frag_len, int64_t *scratch, ftk_stream_t stream_) {
+    if (n_tiles == 0) return FTK_OK;
+    int rc = wps_check_args(frag_start, frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size, max_len, scratch);
+    if (rc != FTK_OK) return rc;
+    if (max_frag_len < 0) return FTK_E_INVALID;
+    return launch_tile_ranges(frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size,
+                              fused_left_reach(window_size, max_len, cov_max_len, max_frag_len), scratch,
+                              static_cast<cudaStream_t>(stream_));
+}
+
 extern "C" int ftk_wps_cov_tiles(const int32_t *frag_start, const int32_t *frag_stop,
                                  const uint8_t *frag_mapq, int64_t n_frag, int32_t max_frag_len,
                                  const int32_t *tile_p0, const int32_t *tile_len,
@@ -1038,8 +1065,8 @@ extern "C" int ftk_wps_cov_tiles(const int32_t *frag_start, const int32_t *frag_
                                  const int64_t *tile_out_off, const int32_t *tile_ivl, int64_t n_tiles,
                                  int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
                                  int32_t cov_min_len, int32_t cov_max_len, int32_t cov_min_mapq, int32_t n_bins,
-                                 int64_t *scratch, int32_t out_kind, void *out, int32_t *overflow_flag,
-                                 uint64_t *counts, uint64_t *hist, ftk_stream_t stream_) {
+                                 int32_t ranges_ready, int64_t *scratch, int32_t out_kind, void *out,
+                                 int32_t *overflow_flag, uint64_t *counts, uint64_t *hist, ftk_stream_t stream_) {
     using namespace ftk;
     if (n_tiles == 0) return FTK_OK;
     int rc = wps_check_args(frag_start, frag_stop, n_frag, tile_p0, tile_len, n_tiles, window_size, max_len, scratch);
@@ -1058,12 +1085,11 @@ extern "C" int ftk_wps_cov_tiles(const int32_t *frag_start, const int32_t *frag_
     if (cov_hi < a.C.len_lo) { a.C.len_lo = 1; a.C.len_span = 0; a.C.min_mapq = 256; }
     else { a.C.len_span = (unsigned)(cov_hi - a.C.len_lo); a.C.min_mapq = cov_min_mapq; }
     a.C.n_bins = n_bins;
-    // a fragment whose midpoint fs + (L >> 1) is >= p0 starts at fs >= p0 - (Lmax >> 1)
-    const int64_t lmax = cov_hi < max_frag_len ? cov_hi : max_frag_len;
-    int64_t reach = wps_left_reach(window_size, max_len);
-    if ((lmax >> 1) + 1 > reach) reach = (lmax >> 1) + 1;
-    rc = launch_tile_ranges(frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size, reach, scratch, stream);
-    if (rc != FTK_OK) return rc;
+    if (!ranges_ready) {
+        rc = ftk_wps_cov_tile_ranges(frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size, max_len,
+                                     cov_max_len, max_frag_len, scratch, stream_);
+        if (rc != FTK_OK) return rc;
+    }
     a.frag_start = frag_start; a.frag_stop = frag_stop; a.frag_mapq = frag_mapq; a.n_frag = n_frag;
     a.tile_p0 = tile_p0; a.tile_len = tile_len; a.tile_mid_lo = tile_mid_lo; a.tile_mid_hi = tile_mid_hi;
     a.tile_out_off = tile_out_off; a.tile_ivl = tile_ivl; a.n_tiles = n_tiles; a.ranges = scratch;

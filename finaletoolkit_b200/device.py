@@ -144,7 +144,9 @@ class WpsPlan:
         self.tile_out_off = _to_device(off, self.device, np.int64)
         # interval of each tile (empty intervals own no position, hence no tile)
         self.n_intervals = len(s)
-        ivl = np.searchsorted(self.offsets[1:], off, side="right").astype(np.int32)
+        ivl = np.searchsorted(self.offsets[1:], off, side="right").astype(np.int64)
+        first = off == self.offsets[np.minimum(ivl, len(s) - 1)] if self.n_tiles else np.zeros(0, bool)
+        ivl = np.where(first, ivl - (1 << 31), ivl).astype(np.int32)   # bit 31: the interval's first tile
         self.tile_ivl = _to_device(ivl, self.device, np.int32)
         self.scratch = t.empty(2 * max(self.n_tiles, 1), dtype=t.int64, device=self.device)
 
@@ -181,9 +183,18 @@ class WpsPlan:
 
     _KIND = {"int32": 0, "int16": 1, "int8": 2}
 
+    def ranges_fused(self, frags: ContigFragments, window_size=120, cov_max_length=None):
+        """Only the fragment-range prepass of ``run_fused`` (lets a caller time the main kernel alone)."""
+        if self.n_tiles:
+            check(lib().ftk_wps_cov_tile_ranges(frags.start.data_ptr(), frags.n, self.tile_p0.data_ptr(),
+                                                self.tile_len.data_ptr(), self.n_tiles, int(window_size),
+                                                self.max_length, none_to_ftk(cov_max_length), frags.max_len,
+                                                self.scratch.data_ptr(), _stream_ptr(self.device)),
+                  "ftk_wps_cov_tile_ranges")
+
     def run_fused(self, frags: ContigFragments, window_size=120, min_length=120, max_length=180,
                   quality_threshold=30, cov_min_length=None, cov_max_length=None, cov_quality_threshold=30,
-                  n_bins=0, out=None, counts=None, hist=None, overflow=None):
+                  n_bins=0, out=None, counts=None, hist=None, overflow=None, ranges_ready=False):
         """ONE pass over the fragments: WPS of every interval + per-interval midpoint coverage
         (``counts`` int64[n_intervals]) + the pooled length histogram of the counted fragments
         (``hist`` int64[n_bins]).  ``counts``/``hist`` are ACCUMULATED into (pass zeroed tensors to
@@ -212,7 +223,7 @@ class WpsPlan:
             self.tile_mid_hi.data_ptr(), self.tile_out_off.data_ptr(), self.tile_ivl.data_ptr(), self.n_tiles,
             int(window_size), none_to_ftk(min_length), int(max_length), int(quality_threshold),
             none_to_ftk(cov_min_length), none_to_ftk(cov_max_length), int(cov_quality_threshold), int(n_bins),
-            self.scratch.data_ptr(), kind, out.data_ptr(), 0 if overflow is None else overflow.data_ptr(),
+            int(bool(ranges_ready)), self.scratch.data_ptr(), kind, out.data_ptr(), 0 if overflow is None else overflow.data_ptr(),
             counts.data_ptr(), 0 if hist is None else hist.data_ptr(), _stream_ptr(self.device)),
             "ftk_wps_cov_tiles")
         return out, counts[: self.n_intervals], hist

@@ -17,13 +17,16 @@ import numpy as np
 from .sharding import DistContext, genome_length_dict, lpt_pack
 
 __all__ = ["owned_contigs", "genome_total_coverage", "genome_length_distribution", "genome_end_motif_counts",
-           "genome_delfi_windows"]
+           "genome_delfi_windows", "ContigWps", "multi_wps_genome", "adjust_wps_genome", "tile_genome",
+           "gather_to_writer"]
 
 
 def owned_contigs(table, ctx: DistContext | None = None):
-    """Contigs of ``table`` this rank owns (LPT by fragment count, deterministic on every rank)."""
+    """Contigs of ``table`` this rank owns (LPT by ``shard_weight``: fragment count, or compressed byte
+    span for a lazy tabix-backed table; deterministic and cheap on every rank)."""
     ctx = ctx or DistContext()
-    weights = {c: table.n_fragments(c) for c in table.contigs}
+    weight = getattr(table, "shard_weight", None) or table.n_fragments
+    weights = {c: weight(c) for c in table.contigs}
     return lpt_pack(weights, ctx.world)[ctx.rank]
 
 
@@ -45,7 +48,8 @@ def genome_total_coverage(table, min_length=None, max_length=None, intersect_pol
 
 
 def genome_length_distribution(table, min_length=0, max_length=None, intersect_policy="midpoint",
-                               quality_threshold=30, ctx: DistContext | None = None, device=None) -> dict:
+                               quality_threshold=30, ctx: DistContext | None = None, device=None,
+                               region=(None, None)) -> dict:
     """The reference's genome-wide ``length -> count`` dict (first-seen order) on every rank."""
     from .device import interval_hist, require_cuda, torch
     ctx = ctx or DistContext()
@@ -53,16 +57,18 @@ def genome_length_distribution(table, min_length=0, max_length=None, intersect_p
     t = torch()
     order = {c: i for i, c in enumerate(table.contigs)}
     mine = owned_contigs(table, ctx)
-    # a common histogram width: the longest admissible fragment over ALL contigs (host-side max)
-    gmax = max([int((table.host(c)[1].astype(np.int64) - table.host(c)[0]).max()) for c in table.contigs
-                if table.n_fragments(c)] + [0])
+    # a common histogram width: the longest fragment over ALL contigs = MAX over the ranks' own contigs
+    gmax_t = t.tensor([max([table.device(c, dev).max_len for c in mine if table.n_fragments(c)] + [0])],
+                      dtype=t.int64, device=dev)
+    ctx.all_reduce_max(gmax_t)
+    gmax = int(gmax_t.item())
     n_bins = (gmax if max_length is None else min(gmax, int(max_length))) + 1
     parts = []
     for c in mine:
         if not table.n_fragments(c):
             continue
-        _, h, f = interval_hist(table.device(c, dev), [None], [None], intersect_policy, min_length, max_length,
-                                quality_threshold, n_bins=n_bins, pooled=True, first_seen=True)
+        _, h, f = interval_hist(table.device(c, dev), [region[0]], [region[1]], intersect_policy, min_length,
+                                max_length, quality_threshold, n_bins=n_bins, pooled=True, first_seen=True)
         parts.append((order[c], h[0], f[0]))
     if not parts:  # rank without fragments still takes part in the collectives
         parts = [(0, t.zeros(n_bins, dtype=t.int64, device=dev), t.full((n_bins,), 2 ** 31 - 1, dtype=t.int32, device=dev))]
@@ -123,3 +129,135 @@ def genome_delfi_windows(table, ref, bins_by_contig, blacklist_by_contig=None, g
     ctx.all_reduce_sum(packed)
     host = packed.cpu().numpy()
     return {c: host[int(offs[i]): int(offs[i + 1])] for i, c in enumerate(names)}
+
+
+# ----------------------------------------------------------------------------------------------
+# Genome-wide WPS (+ coverage + length histogram) and the device-resident WPS -> adjust_wps chain
+# ----------------------------------------------------------------------------------------------
+class ContigWps:
+    """Per-contig result of ``multi_wps_genome`` on the rank that owns the contig (device tensors)."""
+
+    __slots__ = ("contig", "starts", "stops", "offsets", "wps", "cov", "adjusted", "adj_offsets", "adj_segments")
+
+    def __init__(self, contig, starts, stops, offsets, wps, cov=None):
+        self.contig, self.starts, self.stops, self.offsets = contig, starts, stops, offsets
+        self.wps, self.cov = wps, cov
+        self.adjusted = self.adj_offsets = self.adj_segments = None
+
+
+def tile_genome(chrom_sizes, interval_size: int = 5000) -> dict:
+    """{contig: (starts, stops)}: every contig tiled by ``interval_size`` windows (the genome-wide
+    site set of SURVEY.md §8d config 3)."""
+    out = {}
+    for contig, size in chrom_sizes:
+        edges = np.arange(0, int(size) + int(interval_size), int(interval_size), dtype=np.int64).clip(max=int(size))
+        out[contig] = (edges[:-1].copy(), edges[1:].copy())
+    return out
+
+
+def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_size=5000, window_size=120,
+                     min_length=120, max_length=180, quality_threshold=30, coverage=False, length_hist=False,
+                     adjust: dict | None = None, ctx: DistContext | None = None, device=None,
+                     contigs: list | None = None, reduce: bool = True, plans: dict | None = None,
+                     keep_adjusted: bool = True):
+    """Genome-wide L-WPS over the ranks of one box (reference drivers frag/_multi_wps.py:152-198 +,
+    with ``adjust``, frag/_adjust_wps.py:229-291) - contigs LPT-sharded, every rank sweeps the contigs
+    it owns, results stay on the owning rank's GPU, no data-path collective.
+
+    ``sites``: {contig: (starts, stops)} sorted by start (``tile_genome`` when None).  With
+    ``coverage`` / ``length_hist`` the sweep is the fused pass (WPS + per-interval midpoint coverage +
+    pooled length histogram, one read of the fragments); the histogram and the coverage total are the
+    only things combined across ranks (ONE packed all_reduce).  ``adjust`` = kwargs of
+    ``device.adjust_segments`` (median_window_size, savgol, ...): each interval of at least
+    ``median_window_size`` positions is adjusted straight from the int32 WPS in HBM - no bigWig
+    round trip, no float32 copy.
+
+    ``plans``: {contig: WpsPlan} to reuse across calls (built and added when missing);
+    ``contigs``: override the LPT assignment; ``reduce=False`` skips the collectives (single-rank
+    checks inside a multi-rank job); ``keep_adjusted=False`` drops each contig's adjusted series once
+    computed (timing runs).
+
+    Returns ``(results {contig: ContigWps} of this rank, hist int64[n_bins] | None, total | None)``.
+    """
+    from .device import WpsPlan, adjust_segments, require_cuda, torch
+    ctx = ctx or DistContext()
+    dev = require_cuda(device)
+    t = torch()
+    sizes = dict(chrom_sizes)
+    if sites is None:
+        sites = tile_genome(chrom_sizes, interval_size)
+    mine = contigs if contigs is not None else [c for c in owned_contigs(table, ctx) if c in sites]
+    fused = bool(coverage or length_hist)
+    n_bins = 0
+    if length_hist:   # one histogram width for the whole job: MAX over the ranks' own contigs
+        m = t.tensor([max([table.device(c, dev).max_len for c in mine if table.n_fragments(c)] + [0])],
+                     dtype=t.int64, device=dev)
+        if reduce:
+            ctx.all_reduce_max(m)
+        n_bins = int(m.item()) + 1
+    packed = t.zeros(1 + n_bins, dtype=t.int64, device=dev)      # [coverage total, histogram...]
+    results = {}
+    for c in mine:
+        starts, stops = (np.asarray(a, dtype=np.int64) for a in sites[c])
+        plan = plans.get(c) if plans is not None else None
+        if plan is None:
+            plan = WpsPlan(starts, stops, int(sizes[c]), int(max_length), dev)
+            if plans is not None:
+                plans[c] = plan
+        frags = table.device(c, dev)
+        if fused:
+            cov = t.zeros(max(plan.n_intervals, 1), dtype=t.int64, device=dev)
+            wps, cov, _ = plan.run_fused(frags, window_size, min_length, max_length, quality_threshold,
+                                         None, None, quality_threshold, n_bins=n_bins, counts=cov,
+                                         hist=packed[1:] if n_bins else None)
+            packed[0] += cov.sum()
+        else:
+            wps, cov = plan.run(frags, window_size, min_length, max_length, quality_threshold), None
+        res = ContigWps(c, starts, stops, plan.offsets, wps, cov)
+        if adjust is not None:
+            w = int(adjust.get("median_window_size", 1000))
+            lens = np.diff(plan.offsets)
+            keep = np.flatnonzero(lens >= max(w, 1))
+            if keep.size == len(lens):
+                x, seg = wps, lens
+            else:   # intervals shorter than the median window are skipped (frag/_adjust_wps.py:125-129 raises per interval)
+                x = t.cat([wps[plan.offsets[i]: plan.offsets[i + 1]] for i in keep]) if keep.size else wps[:0]
+                seg = lens[keep]
+            if keep.size:
+                res.adjusted, res.adj_offsets = adjust_segments(x, seg, **adjust)
+                if not keep_adjusted:
+                    res.adjusted = None
+            res.adj_segments = keep
+        results[c] = res
+    if fused and reduce:
+        ctx.all_reduce_sum(packed)
+    hist = packed[1:] if n_bins else None
+    return results, hist, (int(packed[0].item()) if fused else None)
+
+
+def adjust_wps_genome(results: dict, **adjust):
+    """Adjust already computed device-resident WPS (``multi_wps_genome`` results) in place of the
+    reference's bigWig -> adjust_wps -> bigWig pass (frag/_adjust_wps.py:59-111)."""
+    from .device import adjust_segments, torch
+    t = torch()
+    w = int(adjust.get("median_window_size", 1000))
+    for res in results.values():
+        lens = np.diff(res.offsets)
+        keep = np.flatnonzero(lens >= max(w, 1))
+        if not keep.size:
+            continue
+        x = res.wps if keep.size == len(lens) else t.cat([res.wps[res.offsets[i]: res.offsets[i + 1]] for i in keep])
+        res.adjusted, res.adj_offsets = adjust_segments(x, lens[keep], **adjust)
+        res.adj_segments = keep
+    return results
+
+
+def gather_to_writer(obj, ctx: DistContext | None = None):
+    """Collect a picklable per-rank object on rank 0 (list in rank order; None elsewhere) - used by the
+    file-writing API mirrors, whose single output file is written by rank 0 only."""
+    ctx = ctx or DistContext()
+    if not (ctx.on and ctx.world > 1):
+        return [obj]
+    out = [None] * ctx.world if ctx.rank == 0 else None
+    ctx.dist.gather_object(obj, out, dst=0)
+    return out

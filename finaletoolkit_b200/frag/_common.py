@@ -28,6 +28,22 @@ def resolve_length_aliases(min_length, max_length, fraction_low, fraction_high, 
     return min_length, max_length
 
 
+def dist_context():
+    """``DistContext`` when ``torch.distributed`` is initialised with more than one rank (one process
+    per GPU; contigs are then LPT-sharded over the ranks and genome-wide totals all-reduced), else None."""
+    import sys
+    if "torch.distributed" not in sys.modules and "torch" not in sys.modules:
+        return None
+    from ..sharding import DistContext
+    ctx = DistContext()
+    return ctx if ctx.on and ctx.world > 1 else None
+
+
+def is_writer(ctx) -> bool:
+    """Under a multi-rank launch only rank 0 writes output files / stdout."""
+    return ctx is None or ctx.rank == 0
+
+
 def group_by_contig(contigs):
     """{contig: [indices]} preserving first-appearance order."""
     groups: dict = {}

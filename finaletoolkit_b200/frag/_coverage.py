@@ -14,7 +14,7 @@ from typing import NamedTuple
 from ..exceptions import InvalidInputError
 from ..io.fragments import as_table
 from ..utils import get_intervals
-from ._common import group_by_contig
+from ._common import dist_context, group_by_contig, is_writer
 
 __all__ = ["coverage", "single_coverage", "CoverageResult"]
 
@@ -27,11 +27,19 @@ class CoverageResult(NamedTuple):
     coverage: float
 
 
-def _count_intervals(table, intervals, min_length, max_length, intersect_policy, quality_threshold):
-    """[(contig, start, stop)] -> list of int counts (input order); contig None = all contigs."""
+def _count_intervals(table, intervals, min_length, max_length, intersect_policy, quality_threshold, ctx=None):
+    """[(contig, start, stop)] -> list of int counts (input order); contig None = all contigs.
+
+    With a multi-rank ``ctx`` every rank counts only on the contigs it owns (LPT sharding) and ONE
+    all_reduce(SUM) of the count vector gives every rank the full answer (the reference's Pool over
+    intervals, frag/_coverage.py:212-248, and its whole-file total, :215-227)."""
     from ..device import interval_hist, policy_code
     policy_code(intersect_policy)
     counts = [0] * len(intervals)
+    mine = None
+    if ctx is not None:
+        from ..distributed import owned_contigs
+        mine = set(owned_contigs(table, ctx))
     for contig, idx in group_by_contig([iv[0] for iv in intervals]).items():
         if contig is None:
             for i in idx:
@@ -40,10 +48,14 @@ def _count_intervals(table, intervals, min_length, max_length, intersect_policy,
                     raise InvalidInputError("contig should be specified if start or stop given.")
                 tot = 0
                 for c in table.contigs:
+                    if mine is not None and c not in mine:
+                        continue
                     cnt, _, _ = interval_hist(table.device(c), [s], [e], intersect_policy, min_length, max_length,
                                               quality_threshold)
                     tot += int(cnt[0])
                 counts[i] = tot
+            continue
+        if mine is not None and contig not in mine:
             continue
         if table.n_fragments(contig) == 0:
             continue
@@ -52,6 +64,12 @@ def _count_intervals(table, intervals, min_length, max_length, intersect_policy,
         host = cnt.cpu().tolist()
         for k, i in enumerate(idx):
             counts[i] = int(host[k])
+    if ctx is not None and counts:
+        import torch
+        from ..device import require_cuda
+        buf = torch.tensor(counts, dtype=torch.int64, device=require_cuda())
+        ctx.all_reduce_sum(buf)
+        counts = [int(v) for v in buf.cpu().tolist()]
     return counts
 
 
@@ -75,12 +93,15 @@ def coverage(input_file, interval_file, output_file, scale_factor=1.0, min_lengt
     if verbose:
         start_time = time.time()
     table = as_table(input_file, reference_file)
+    ctx = dist_context()   # torch.distributed initialised: contigs sharded over the ranks, rank 0 writes
     if normalize:
         total = _count_intervals(table, [(None, 0, None)], min_length, max_length, intersect_policy,
-                                 quality_threshold)[0]
+                                 quality_threshold, ctx)[0]
     intervals = get_intervals(interval_file)
     counts = _count_intervals(table, [iv[:3] for iv in intervals], min_length, max_length, intersect_policy,
-                              quality_threshold)
+                              quality_threshold, ctx)
+    if not is_writer(ctx):
+        output_file = None
     if normalize:
         scale_factor /= total  # frag/_coverage.py:254 (ZeroDivisionError for an empty file, like the reference)
     return_val = []

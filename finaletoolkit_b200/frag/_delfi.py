@@ -23,6 +23,7 @@ from ..genome.gaps import GenomeGaps
 from ..io.fragments import as_table
 from ..io.reference import open_reference
 from ..utils import chrom_sizes_to_list
+from ._common import dist_context, is_writer
 
 __all__ = ["delfi", "delfi_gc_correct", "delfi_merge_bins", "trim_coverage"]
 
@@ -83,8 +84,10 @@ def _bins_overlapping_gaps(bins: pandas.DataFrame, gaps: GenomeGaps) -> np.ndarr
     return hit
 
 
-def _contig_windows(table, ref, contig, starts, stops, blacklist, contig_gaps, quality_threshold):
-    """The tuples ``_delfi_single_window`` returns for all bins of one contig (frag/_delfi.py:404-511)."""
+def _contig_counts(table, ref, contig, starts, stops, blacklist, contig_gaps, quality_threshold, count_here=True):
+    """Arm labels, live mask and int64[n, 4] counts (short, long, num_frags, G+C bases) of one contig's bins
+    (the loop body of ``_delfi_single_window``, frag/_delfi.py:404-511).  ``count_here=False`` (a contig
+    another rank owns) skips the CUDA call and leaves the counts at zero for the all-reduce."""
     from ..device import delfi_windows
     n = len(starts)
     arms = [contig] * n
@@ -97,15 +100,21 @@ def _contig_windows(table, ref, contig, starts, stops, blacklist, contig_gaps, q
     idx = np.flatnonzero(live)
     counts = np.zeros((n, 4), np.int64)
     if idx.size:
-        gaps = None if contig_gaps is None else (contig_gaps.centromere, contig_gaps.telomeres)
-        dev_ref = ref.device_contig(contig) if contig in ref.chroms else None
         if contig not in table.contigs:   # pysam.TabixFile.fetch on a contig the index does not know
             raise ValueError(f"could not create iterator for region '{contig}:{starts[idx[0]] + 1}-{stops[idx[0]]}'")
-        got = delfi_windows(table.device(contig), dev_ref, [starts[i] for i in idx], [stops[i] for i in idx],
-                            blacklist=blacklist, gaps=gaps, quality_threshold=quality_threshold)
-        counts[idx] = got.cpu().numpy()
+        if count_here:
+            gaps = None if contig_gaps is None else (contig_gaps.centromere, contig_gaps.telomeres)
+            dev_ref = ref.device_contig(contig) if contig in ref.chroms else None
+            got = delfi_windows(table.device(contig), dev_ref, [starts[i] for i in idx], [stops[i] for i in idx],
+                                blacklist=blacklist, gaps=gaps, quality_threshold=quality_threshold)
+            counts[idx] = got.cpu().numpy()
+    return arms, live, counts
+
+
+def _rows_from_counts(contig, starts, stops, arms, live, counts):
+    """The tuples ``_delfi_single_window`` returns (frag/_delfi.py:498-511)."""
     rows = []
-    for i in range(n):
+    for i in range(len(starts)):
         s, e = starts[i], stops[i]
         if not live[i]:
             rows.append((contig, s, e, "NOARM", np.nan, np.nan, np.nan, 0))
@@ -113,6 +122,11 @@ def _contig_windows(table, ref, contig, starts, stops, blacklist, contig_gaps, q
         short, long_, num, gc = (int(x) for x in counts[i])
         rows.append((contig, s, e, arms[i], short, long_, gc / (e - s) if num > 0 else np.nan, num))
     return rows
+
+
+def _contig_windows(table, ref, contig, starts, stops, blacklist, contig_gaps, quality_threshold):
+    arms, live, counts = _contig_counts(table, ref, contig, starts, stops, blacklist, contig_gaps, quality_threshold)
+    return _rows_from_counts(contig, starts, stops, arms, live, counts)
 
 
 def delfi_gc_correct(windows: pandas.DataFrame, alpha: float = 0.75, it: int = 8, verbose: bool = False) -> pandas.DataFrame:
@@ -205,13 +219,34 @@ def delfi(input_file, chrom_sizes, bins_file, reference_file, blacklist_file=Non
     ref = open_reference(reference_file)
     windows = []
     bin_contigs = gapless["contig"].to_numpy()
+    ctx = dist_context()
+    mine = None
+    if ctx is not None:   # bins of different contigs are independent (the reference's Pool, frag/_delfi.py:283-294):
+        from ..distributed import owned_contigs   # each rank counts the contigs it owns, one all_reduce merges
+        mine = set(owned_contigs(table, ctx))
+    parts = []
     for contig, _size in contigs:
         sel = gapless.loc[bin_contigs == contig]
         if not sel.shape[0]:
             continue
-        windows.extend(_contig_windows(table, ref, contig, sel["start"].tolist(), sel["stop"].tolist(),
-                                       blacklist_by_contig.get(contig),
-                                       gaps.get_contig_gaps(contig) if gaps is not None else None, quality_threshold))
+        starts, stops = sel["start"].tolist(), sel["stop"].tolist()
+        arms, live, counts = _contig_counts(table, ref, contig, starts, stops, blacklist_by_contig.get(contig),
+                                            gaps.get_contig_gaps(contig) if gaps is not None else None,
+                                            quality_threshold, count_here=(mine is None or contig in mine))
+        parts.append((contig, starts, stops, arms, live, counts))
+    if ctx is not None and parts:
+        import torch
+        from ..device import require_cuda
+        buf = torch.from_numpy(np.concatenate([p[5] for p in parts])).to(require_cuda())
+        ctx.all_reduce_sum(buf)
+        host, o = buf.cpu().numpy(), 0
+        for p in parts:
+            p[5][:] = host[o: o + len(p[5])]
+            o += len(p[5])
+    for p in parts:
+        windows.extend(_rows_from_counts(*p))
+    if not is_writer(ctx):
+        output_file = None
     if verbose:
         stderr.write(f"{len(windows)} windows counted.\n")
 

@@ -18,7 +18,7 @@ import numpy as np
 from ..io.fragments import as_table
 from ..io.reference import ReferenceWrapper, open_reference
 from ..utils import gen_kmers
-from ._common import group_by_contig, resolve_length_aliases
+from ._common import dist_context, group_by_contig, is_writer, resolve_length_aliases
 from ._motif_common import (MIN_QUALITY, _MotifFreqs, _MotifsIntervals, _BASES, genome_windows,
                             parse_intervals_arg, write_motif_freqs)
 
@@ -84,16 +84,27 @@ def end_motifs(input_file, refseq_file, k=4, min_length=50, max_length=None, bot
         raise TypeError("'<' not supported between instances of 'NoneType' and 'int'")  # frag/_end_motifs.py:108
     table = as_table(input_file, refseq_file)
     ref = _ref(refseq_file)
-    total = None
-    for chrom, chrom_length in ref.chroms.items():
-        if table.n_fragments(chrom) == 0:
-            continue
-        w = genome_windows(chrom_length)
-        total = end_motif_hist(table.device(chrom), ref.device_contig(chrom), [a for a, _ in w], [b for _, b in w],
-                               k=k, strand_mode=mode, quality_threshold=quality_threshold, pooled=True, counts=total)
+    ctx = dist_context()
     ccounts = np.zeros((4 ** k,), np.float64)
-    if total is not None:
-        ccounts = ccounts + total[0].cpu().numpy().astype(np.float64)
+    if ctx is not None:
+        # contigs LPT-sharded over the ranks, one all_reduce(SUM) of the 4^k counts
+        # (the reference pools its per-window dicts on the host, frag/_motif_common.py:599-609)
+        from ..distributed import genome_end_motif_counts
+        ccounts = ccounts + genome_end_motif_counts(table, ref, k=k, strand_mode=mode,
+                                                    quality_threshold=quality_threshold, ctx=ctx).astype(np.float64)
+        if not is_writer(ctx):
+            output_file = None
+    else:
+        total = None
+        for chrom, chrom_length in ref.chroms.items():
+            if table.n_fragments(chrom) == 0:
+                continue
+            w = genome_windows(chrom_length)
+            total = end_motif_hist(table.device(chrom), ref.device_contig(chrom), [a for a, _ in w],
+                                   [b for _, b in w], k=k, strand_mode=mode, quality_threshold=quality_threshold,
+                                   pooled=True, counts=total)
+        if total is not None:
+            ccounts = ccounts + total[0].cpu().numpy().astype(np.float64)
     with np.errstate(invalid="ignore", divide="ignore"):
         frequencies = ccounts / np.sum(ccounts)
     results = EndMotifFreqs(zip(gen_kmers(k, _BASES), frequencies), k, quality_threshold)

@@ -20,7 +20,7 @@ import numpy as np
 from ..exceptions import InvalidInputError
 from ..io.fragments import as_table
 from ..utils import get_intervals
-from ._common import group_by_contig
+from ._common import dist_context, group_by_contig, is_writer
 
 __all__ = ["frag_length", "frag_length_bins", "frag_length_intervals", "FragLengthStats"]
 
@@ -125,8 +125,18 @@ def frag_length_bins(input_file, contig=None, start=None, stop=None, min_length=
     policy_code(intersect_policy)
     _check_region(contig, start, stop)
     table = as_table(input_file, reference_file)
-    frag_len_dict = _region_dict(table, contig, start, stop, min_length, max_length, intersect_policy,
-                                 quality_threshold)
+    ctx = dist_context()
+    if ctx is not None and contig is None:
+        # genome-wide dict over the ranks of one box: contigs LPT-sharded, SUM of histograms + MIN of
+        # first-seen keys (frag/_frag_length.py:408-421 streams every contig in file order)
+        from ..distributed import genome_length_distribution
+        frag_len_dict = genome_length_distribution(table, min_length, max_length, intersect_policy,
+                                                   quality_threshold, ctx=ctx, region=(start, stop))
+    else:
+        frag_len_dict = _region_dict(table, contig, start, stop, min_length, max_length, intersect_policy,
+                                     quality_threshold)
+    if not is_writer(ctx):
+        output_file = None
     total_count = sum(frag_len_dict.values())
     if total_count == 0:
         warnings.warn("No fragments found in the specified region. Returning empty result.", RuntimeWarning,

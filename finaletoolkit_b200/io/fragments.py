@@ -55,6 +55,7 @@ class FragmentTable:
         self.contig_lengths = contig_lengths  # BAM/CRAM header only
         self.columns: Dict[str, Columns] = {}
         self._lazy_names, self._loader = (list(lazy[0]), lazy[1]) if lazy is not None else (None, None)
+        self._weights = lazy[2] if (lazy is not None and len(lazy) > 2) else None
         for contig, cols in columns.items():
             self._put(contig, cols)
         self._device: dict = {}
@@ -85,6 +86,14 @@ class FragmentTable:
             return sum(c[0].size for c in self.columns.values())
         self._ensure(contig)
         return self.columns[contig][0].size if contig in self.columns else 0
+
+    def shard_weight(self, contig: str) -> int:
+        """Load estimate of one contig for LPT sharding, identical on every rank: the fragment count for
+        an in-memory table, the compressed byte span of the contig's index range for a lazy tabix-backed
+        one (no rank has to inflate a contig it does not own)."""
+        if self._weights is None:
+            return self.n_fragments(contig)
+        return int(self._weights.get(contig, 0))
 
     def host(self, contig: str) -> Columns:
         self._ensure(contig)
@@ -237,7 +246,8 @@ def _lazy_table(path: str) -> "FragmentTable | None":
         return (cols or {}).get(contig, (z, z.copy(), np.zeros(0, np.uint8), np.zeros(0, np.uint8)))
 
     names = [n for n in index.names if n in index.ranges]
-    return FragmentTable({}, source=path, lazy=(names, load))
+    weights = {n: max(index.ranges[n][2] - index.ranges[n][0], 1) for n in names}
+    return FragmentTable({}, source=path, lazy=(names, load, weights))
 
 
 def _parse_text_fast(path: str) -> Dict[str, Columns] | None:

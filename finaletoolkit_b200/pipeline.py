@@ -182,7 +182,7 @@ class StreamedContig:
                             plan.tile_p0.data_ptr(), plan.tile_len.data_ptr(), plan.tile_mid_lo.data_ptr(),
                             plan.tile_mid_hi.data_ptr(), plan.tile_out_off.data_ptr(), plan.tile_ivl.data_ptr(),
                             plan.n_tiles, W, none_to_ftk(lo), hi, q, none_to_ftk(c_lo), none_to_ftk(c_hi), c_q,
-                            self.n_bins, plan.scratch.data_ptr(), kind, self.d_out[b].data_ptr(),
+                            self.n_bins, 0, plan.scratch.data_ptr(), kind, self.d_out[b].data_ptr(),
                             self.d_flag.data_ptr(), self.d_cov[c["i0"]:].data_ptr(),
                             self.d_hist.data_ptr() if self.n_bins else 0, _stream_ptr(self.device)),
                             "ftk_wps_cov_tiles")

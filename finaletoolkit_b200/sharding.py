@@ -58,6 +58,11 @@ class DistContext:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return t
 
+    def all_reduce_max(self, t):
+        if self.on and self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t
+
     def all_reduce_min(self, t):
         if self.on and self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)

@@ -91,3 +91,33 @@ def synth_twobit(contig_len: int, contig_index: int = 0, seed_base: int = 2000,
         s = int(rng.integers(0, max(contig_len - bl, 1)))
         n_mask[s: s + bl] = True
     return codes, n_mask
+
+
+def synth_fragments_device(contig_len: int, n: int, contig_index: int, device, seed_base: int = 3000):
+    """Same distributions as ``synth_fragments`` drawn ON the GPU (torch Philox generator seeded with
+    ``seed_base + contig_index``): returns start-sorted CUDA tensors ``(start int32, stop int32,
+    mapq uint8)``.  Used for the genome-scale configuration (1e9 fragments), where drawing and sorting
+    on the host would take minutes; checkers copy the columns they need back to the host."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed_base + contig_index)
+    comp = torch.rand(n, generator=g, device=device)
+    length = torch.empty(n, dtype=torch.float32, device=device).normal_(167.0, 15.0, generator=g)
+    di = torch.empty(n, dtype=torch.float32, device=device).normal_(330.0, 25.0, generator=g)
+    length = torch.where(comp >= 0.85, di, length)
+    del di
+    uni = torch.randint(50, 501, (n,), generator=g, device=device, dtype=torch.int32).to(torch.float32)
+    length = torch.where(comp >= 0.97, uni, length)
+    del uni, comp
+    length = length.round_().clamp_(30, 600).to(torch.int32).clamp_(max=max(int(contig_len), 1))
+    u = torch.rand(n, generator=g, device=device, dtype=torch.float64)
+    start = (u * (int(contig_len) - length.to(torch.float64) + 1.0)).floor_().to(torch.int32)
+    del u
+    mapq = torch.where(torch.rand(n, generator=g, device=device) < 0.9,
+                       torch.full((n,), 60, dtype=torch.int32, device=device),
+                       torch.randint(0, 60, (n,), generator=g, device=device, dtype=torch.int32)).to(torch.uint8)
+    start, order = torch.sort(start, stable=True)
+    length = length[order]
+    mapq = mapq[order]
+    del order
+    return start, start + length, mapq

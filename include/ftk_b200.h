@@ -153,16 +153,22 @@ int ftk_wps_tiles_i8(const int32_t *frag_start_dev, const int32_t *frag_stop_dev
 /* Fused pass: WPS + per-interval coverage counts + ONE pooled length histogram in a single sweep
  * over the fragments (the three reference loops frag/_wps.py:176-188, frag/_coverage.py:117-130 with
  * intersect_policy="midpoint", frag/_frag_length.py:147-153 over the same intervals).
- * tile_ivl_dev[t] = index of the interval tile t belongs to.  counts_dev[ivl] (uint64, ACCUMULATED,
+ * tile_ivl_dev[t] = index of the interval tile t belongs to, with bit 31 set on the interval's FIRST tile.  counts_dev[ivl] (uint64, ACCUMULATED,
  * caller zeroes) += fragments with mapq >= cov_min_mapq, cov_min_len <= L <= cov_max_len (FTK_NONE =
  * unbounded) whose midpoint lies in the interval; hist_dev[L] (uint64[n_bins], ACCUMULATED) += 1 for
  * each counted fragment with L < n_bins (n_bins = 0: no histogram, hist_dev may be NULL).
  * max_frag_len = longest fragment of the contig (bounds the candidate search).
  * out_kind: 0 = int32 scores, 1 = int16, 2 = int8 (overflow protocol of ftk_wps_tiles_i16/_i8;
- * overflow_flag_dev may be NULL for int32).  scratch_dev: int64[2 * n_tiles]; the per-tile fragment
- * ranges are always recomputed (they are wider than ftk_wps_tile_ranges').
+ * overflow_flag_dev may be NULL for int32).  scratch_dev: int64[2 * n_tiles] = the per-tile fragment
+ * ranges of ftk_wps_cov_tile_ranges (wider on the left than ftk_wps_tile_ranges': every fragment whose
+ * midpoint can fall into the tile); computed here unless ranges_ready != 0.
  * Every interval is an independent stream (overlapping intervals each count their own fragments,
  * and the pooled histogram gains one entry per (interval, fragment) pair like the reference's loop). */
+int ftk_wps_cov_tile_ranges(const int32_t *frag_start_dev, int64_t n_frag,
+                            const int32_t *tile_p0_dev, const int32_t *tile_len_dev, int64_t n_tiles,
+                            int32_t window_size, int32_t max_len, int32_t cov_max_len, int32_t max_frag_len,
+                            int64_t *scratch_dev, ftk_stream_t stream);
+
 int ftk_wps_cov_tiles(const int32_t *frag_start_dev, const int32_t *frag_stop_dev,
                       const uint8_t *frag_mapq_dev, int64_t n_frag, int32_t max_frag_len,
                       const int32_t *tile_p0_dev, const int32_t *tile_len_dev,
@@ -170,7 +176,7 @@ int ftk_wps_cov_tiles(const int32_t *frag_start_dev, const int32_t *frag_stop_de
                       const int64_t *tile_out_off_dev, const int32_t *tile_ivl_dev, int64_t n_tiles,
                       int32_t window_size, int32_t min_len, int32_t max_len, int32_t min_mapq,
                       int32_t cov_min_len, int32_t cov_max_len, int32_t cov_min_mapq, int32_t n_bins,
-                      int64_t *scratch_dev, int32_t out_kind, void *out_dev, int32_t *overflow_flag_dev,
+                      int32_t ranges_ready, int64_t *scratch_dev, int32_t out_kind, void *out_dev, int32_t *overflow_flag_dev,
                       uint64_t *counts_dev, uint64_t *hist_dev, ftk_stream_t stream);
 
 /* ------------------------------------------- coverage / fragment lengths

@@ -43,7 +43,7 @@ def main():
     res = {"n_frag": N}
     plan.ranges(fr)
     res["ranges"] = timed(lambda: plan.ranges(fr))
-    for name, impl in (("hex", 0), ("dual", 3), ("direct", 1)):
+    for name, impl in (("hex", 2), ("dual", 0), ("direct", 1)):
         lib().ftk_debug_set_wps_impl(impl)
         res["wps_" + name] = timed(lambda: plan.run(fr, out=out, ranges_ready=True))
     lib().ftk_debug_set_wps_impl(0)
