@@ -1,4 +1,5 @@
-"""N-GPU check of the distributed genome-wide reductions (NCCL).  Not collected by pytest:
+"""N-GPU check of the distributed genome-wide reductions and drivers (NCCL).  Spawned by
+tests/test_gpu_dist.py (pytest -m gpu, needs >= 2 GPUs), or by hand:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29533 tests/dist_gpu_check.py
@@ -79,5 +80,50 @@ if ctx.rank == 0:
             assert tuple(dw[c][j]) == O.delfi_counts(fr, ref.ascii(c), int(a), int(b), blk.get(c), gaps.get(c), 30), (c, a, b)
     print(f"dist check ok: motifs {int(em.sum())} / {int(bm.sum())} k-mers, DELFI {sum(int(v[:, 2].sum()) for v in dw.values())} "
           f"fragments in {sum(len(v) for v in dw.values())} bins")
+
+# ---- genome drivers: LPT-sharded WPS + coverage + histogram, device-resident WPS -> adjust
+sizes = list(contigs.items())
+res, hist, tot = FD.multi_wps_genome(table, sizes, None, 5000, 120, 120, 180, 30, coverage=True, length_hist=True,
+                                     adjust=dict(median_window_size=1000), ctx=ctx, device=dev)
+assert sorted(res) == sorted(mine)
+bad = 0
+for c, r in res.items():
+    fr = O.Frags(*cols[c])
+    exp, off = O.wps_intervals(fr, r.starts, r.stops, contigs[c], 120, 120, 180, 30, threads=4)
+    bad += int((r.wps.cpu().numpy().astype(np.int64) != exp).sum())
+    bad += int((r.cov.cpu().numpy() != O.interval_coverage(fr, r.starts, r.stops, None, None, "midpoint", 30)).sum())
+    for k, i in enumerate(r.adj_segments[:3]):
+        ref_adj = O.adjust_core(exp[off[i]: off[i + 1]].astype(np.float64), 1000, False, True, 21, 2)
+        got = r.adjusted[r.adj_offsets[k]: r.adj_offsets[k + 1]].cpu().numpy()
+        bad += int(not np.allclose(got, ref_adj, rtol=1e-5, atol=1e-9))
+badt = torch.tensor([bad], device=dev); dist.all_reduce(badt)
+frs_all = {c: O.Frags(*cols[c]) for c in contigs}
+exp_hist = np.zeros(hist.numel(), np.int64)
+for c, n in contigs.items():
+    for L, v in O.length_dist(frs_all[c], 0, n, None, None, "midpoint", 30).items():
+        exp_hist[L] += v
+assert int(badt.item()) == 0, "multi_wps_genome mismatch vs oracle"
+assert np.array_equal(hist.cpu().numpy(), exp_hist) and tot == int(exp_hist.sum())
+
+# ---- the public API under torch.distributed: every rank gets the full answer, rank 0 writes
+import tempfile  # noqa: E402
+import finaletoolkit_b200 as F  # noqa: E402
+tmp = tempfile.mkdtemp(prefix=f"ftk_dist_{ctx.rank}_")
+bed = os.path.join(tmp, "iv.bed")
+rows = [(c, a, min(a + 40_000, n)) for c, n in contigs.items() for a in range(0, n, 40_000)]
+open(bed, "w").write("".join(f"{c}\t{a}\t{b}\tx\n" for c, a, b in rows))
+out_bed = os.path.join(tmp, "cov.bed")
+got = F.coverage(table, bed, out_bed, normalize=True, scale_factor=1e6, quality_threshold=30)
+exp_total = sum(O.single_coverage(fr, 0, None) for fr in frs_all.values())
+for (c, a, b), g in zip(rows, got):
+    assert g.coverage == O.single_coverage(frs_all[c], a, b) * (1e6 / exp_total), (c, a, b)
+assert os.path.exists(out_bed) == (ctx.rank == 0)
+bins, counts = F.frag_length_bins(table, bin_size=5, quality_threshold=30)
+exp_d = O.merge_dists(O.length_dist(fr, None, None, 0, None, "midpoint", 30) for fr in frs_all.values())
+eb, ec = O.length_bins(exp_d, 5)
+assert list(bins) == list(eb) and list(counts) == list(ec)
+if ctx.rank == 0:
+    print(f"dist check ok: multi_wps_genome {sum(len(r.starts) for r in res.values())} intervals on rank 0, "
+          f"hist total {tot}; API coverage(normalize) + frag_length_bins equal the oracle on every rank")
 dist.barrier()
 dist.destroy_process_group()
