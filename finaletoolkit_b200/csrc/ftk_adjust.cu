@@ -369,17 +369,20 @@ adjust_savgol_kernel(const double *__restrict__ adj, const long long *__restrict
 //
 //   * one CTA per tile = up to ~4000 consecutive outputs of ONE segment; its A + w samples are
 //     staged in shared memory once (coalesced, int16);
-//   * for a band of 32 consecutive value levels the CTA builds level bitmaps with warp ballots
-//     (bit i of B[r] = sample i <= level r) plus per-word prefix popcounts, so the rank
+//   * for a band of 32 consecutive value levels the CTA builds level bitmaps (every lane turns its
+//     sample into a 32-level mask, a 5-step shuffle transpose turns 32 masks into 32 bitmap words:
+//     bit i of B[r] = sample i <= level r) plus per-word prefix popcounts, so the rank
 //     F(r, j) = #{samples of window j <= level r} is TWO popcount lookups for ANY window j - O(1)
 //     random access instead of a w-step fill;
 //   * every thread owns a short run of R (~11) consecutive outputs: binary search over the band for
-//     its first median (7 rank queries), then slides (+1 / -1 sample, two compares) and consults the
-//     bitmaps only when the median changes level;
-//   * the band is centred on a sampled median of the tile; outputs whose median falls outside are
-//     picked up by further passes with the band moved down / up (rare), a tile that cannot be
-//     resolved (non-integer samples, |x| > 32000, > kRankMaxPasses bands) is flagged and redone by
-//     the histogram / generic path;
+//     its first lower median (7 rank queries), then slides (+1 / -1 sample, two compares) and
+//     consults the bitmaps only when the median changes level; the upper median (even window) is
+//     the same level or the next occupied one;
+//   * the band is centred on a sampled median of the tile; an order statistic that falls outside is
+//     picked up by further passes with the band moved down / up (each of the two middle order
+//     statistics of an output resolves independently, in whichever band holds it), a tile that
+//     cannot be resolved (non-integer samples, |x| > 32000, > kRankMaxPasses bands) is flagged and
+//     redone by the histogram / generic path;
 //   * the adjusted series never leaves the SM: Savitzky-Golay (interior stencil + per-segment edge
 //     fits) runs on the shared-memory copy (+-sg_w/2 halo outputs are recomputed per tile) and only
 //     the final float64 result is written, warp-staged for coalesced stores.
@@ -389,7 +392,7 @@ adjust_savgol_kernel(const double *__restrict__ adj, const long long *__restrict
 #endif
 constexpr int kRankThreads = FTK_RANK_THREADS;
 constexpr int kRankWarps = kRankThreads / 32;
-constexpr int kRankLevels = 32;        // band rows: one ballot row per lane
+constexpr int kRankLevels = 32;        // band rows: one bitmap row per lane
 constexpr int kRankMaxPasses = 12;
 constexpr int kRankMaxAbs = 32000;     // samples are staged as int16
 
@@ -407,11 +410,9 @@ __host__ __device__ inline RankGeom rank_geom(int a_cap, int s_cap) {
     g.s_pad = nword * 32;
     return g;
 }
-template <typename AdjT>
 __host__ __device__ inline size_t rank_smem_bytes(int a_cap, int s_cap) {
     const RankGeom g = rank_geom(a_cap, s_cap);
-    size_t b = (size_t)g.a_slots * sizeof(AdjT);
-    b = (b + 15) & ~(size_t)15;
+    size_t b = (size_t)g.a_slots * sizeof(double);
     b += (size_t)kRankLevels * g.nwp * 4;       // bitmaps
     b += (size_t)kRankLevels * g.nwp * 2;       // per-word prefix popcounts
     b = (b + 15) & ~(size_t)15;
@@ -428,8 +429,19 @@ __device__ __forceinline__ bool rank_stage(int v, int &iv) {
     return (v >= -kRankMaxAbs) && (v <= kRankMaxAbs);
 }
 
-// SHIFT = subtract_edges (per-segment fp64 shift): the adjusted value is then a general double;
-// without it 2 * adj is an integer and the tile keeps it as int32.
+// 32 x 32 bit-matrix transpose across a warp: lane i holds row i, afterwards lane r holds column r
+__device__ __forceinline__ unsigned warp_transpose32(unsigned x, int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const unsigned msk = (s == 16) ? 0x0000ffffu : (s == 8) ? 0x00ff00ffu : (s == 4) ? 0x0f0f0f0fu
+                           : (s == 2) ? 0x33333333u : 0x55555555u;
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, s);
+        x = (lane & s) ? ((x & ~msk) | ((y >> s) & msk)) : ((x & msk) | ((y << s) & ~msk));
+    }
+    return x;
+}
+
+// SHIFT = subtract_edges (per-segment fp64 shift).
 template <typename InT, bool SHIFT, int SGW>   // SGW: 21 = unrolled default, 0 = runtime window, -1 = no smoothing
 __global__ void __launch_bounds__(kRankThreads, 3)
 adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_off,
@@ -438,16 +450,17 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
                    const int *__restrict__ tile_n, int w, int sg_w, const double *__restrict__ coef,
                    const double *__restrict__ edge_first, const double *__restrict__ edge_last,
                    int a_cap, int s_cap, double *__restrict__ out, unsigned char *__restrict__ tile_flag) {
-    using AdjT = typename std::conditional<SHIFT, double, int>::type;
     extern __shared__ __align__(16) unsigned char rank_smem[];
-    __shared__ int s_ctl[4];            // 0: need lower band, 1: need higher band, 2: hard / bad, 3: centre
+    __shared__ int s_ctl[4];            // 0: need lower band, 1: need higher band, 2: unused, 3: centre
+    __shared__ int s_tot[kRankWarps][kRankLevels];   // per-warp-chunk row totals of the bitmap build
     __shared__ double s_coef[kAdjMaxSg + 1];
     const RankGeom G = rank_geom(a_cap, s_cap);
-    AdjT *__restrict__ adj = reinterpret_cast<AdjT *>(rank_smem);
-    size_t o_b = ((size_t)G.a_slots * sizeof(AdjT) + 15) & ~(size_t)15;
-    unsigned *__restrict__ B = reinterpret_cast<unsigned *>(rank_smem + o_b);
+    // adj slot j first holds the two middle order statistics of window j as int32 pairs, then the
+    // adjusted value as a double
+    double *__restrict__ adj = reinterpret_cast<double *>(rank_smem);
+    unsigned *__restrict__ B = reinterpret_cast<unsigned *>(adj + G.a_slots);
     unsigned short *__restrict__ Wp = reinterpret_cast<unsigned short *>(B + kRankLevels * G.nwp);
-    size_t o_x = (o_b + (size_t)kRankLevels * G.nwp * 6 + 15) & ~(size_t)15;
+    const size_t o_x = ((size_t)G.a_slots * 8 + (size_t)kRankLevels * G.nwp * 6 + 15) & ~(size_t)15;
     short *__restrict__ xs = reinterpret_cast<short *>(rank_smem + o_x);
     const int nwp = G.nwp;
 
@@ -473,7 +486,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
     // ---- stage the samples (coalesced), validate: integer-valued and small
     if (!bad) {
         const InT *__restrict__ src = x + seg0 + a0;
-        for (int i = tid; i < G.s_pad; i += kRankThreads) {
+        for (int i = tid; i < G.s_pad + 32; i += kRankThreads) {
             int iv = 32767;                       // sentinel beyond every level: never counted
             if (i < S) {
                 if (!rank_stage(__ldg(src + i), iv)) { bad = true; iv = 0; }
@@ -501,58 +514,68 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
     const int kl = (w - 1) >> 1, ku = w >> 1;   // 0-based ranks of the two middle order statistics
     const int R = (A + kRankThreads - 1) / kRankThreads;   // outputs per thread (<= 32)
     const int j0 = tid * R;
-    double shift = 0.0;
-    if (SHIFT) shift = seg_shift[sg];
+    const int mine_n = max(min(A - j0, R), 0);
+    const unsigned full_mask = (mine_n >= 32) ? 0xffffffffu : ((1u << mine_n) - 1u);
     auto cnt = [&](int r, int i) -> int {       // #{samples [0, i) <= level r}
         const int wd = i >> 5;
         return (int)Wp[r * nwp + wd] + __popc(B[r * nwp + wd] & ((1u << (i & 31)) - 1u));
     };
     auto F = [&](int r, int j) -> int { return cnt(r, j + w) - cnt(r, j); };
+    // smallest row whose rank count reaches `need`: -1 below the band (row 0 already does), 32 above
+    auto locate = [&](int j, int need, int &flo, int &fhi) -> int {
+        flo = F(0, j);
+        if (flo >= need) return -1;
+        fhi = F(kRankLevels - 1, j);
+        if (fhi < need) return kRankLevels;
+        int lo = 0, hi = kRankLevels - 1;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            const int f = F(mid, j);
+            if (f >= need) { hi = mid; fhi = f; } else { lo = mid; flo = f; }
+        }
+        return hi;
+    };
+    // words each warp turns into bitmaps: one contiguous chunk per warp (running row counts in registers)
+    const int n_words = min(((S + 31) >> 5) + 1, nwp);
+    const int wpw = (n_words + kRankWarps - 1) / kRankWarps;
+    const int wd_lo = min(warp * wpw, n_words), wd_hi = min(wd_lo + wpw, n_words);
 
-    unsigned resolved = 0;
-    int L0 = s_ctl[3] - (kRankLevels / 2 - 1);   // row r <-> level L0 - 1 + r; medians on rows 1..31 resolve
+    unsigned done_m = 0, done_u = 0;             // per-output bits: lower / upper median known
+    int L0 = s_ctl[3] - (kRankLevels / 2 - 1);   // row r <-> level L0 - 1 + r; rows 1..31 resolve
     int lo_band = L0, hi_band = L0;
     bool is_lowest = true, is_highest = true, pend_lo = false, pend_hi = false;
     for (int pass = 0;; ++pass) {
-        // ---- level bitmaps: one ballot per row, lane r keeps row r
-        for (int wd = warp; wd < nwp; wd += kRankWarps) {
-            const int i = wd * 32 + lane;
-            const int v = (i < G.s_pad) ? (int)xs[i] : 32767;
-            unsigned mine = 0;
-#pragma unroll
-            for (int r = 0; r < kRankLevels; ++r) {
-                const unsigned b = __ballot_sync(0xffffffffu, v <= L0 - 1 + r);
-                if (lane == r) mine = b;
+        // ---- level bitmaps + chunk-local per-word prefix popcounts (lane r owns row r)
+        {
+            int run = 0;
+            for (int wd = wd_lo; wd < wd_hi; ++wd) {
+                const int d = (int)xs[wd * 32 + lane] - (L0 - 1);     // sample <= level r  <=>  r >= d
+                const unsigned mask = (d <= 0) ? 0xffffffffu : (d > 31) ? 0u : (0xffffffffu << d);
+                const unsigned bits = warp_transpose32(mask, lane);
+                B[lane * nwp + wd] = bits;
+                Wp[lane * nwp + wd] = (unsigned short)run;
+                run += __popc(bits);
             }
-            B[lane * nwp + wd] = mine;
+            s_tot[warp][lane] = run;
         }
         __syncthreads();
-        // ---- per-word exclusive prefix popcounts of every row
-        for (int r = warp; r < kRankLevels; r += kRankWarps) {
-            int carry = 0;
-            for (int w0 = 0; w0 < nwp; w0 += 32) {
-                const int wd = w0 + lane;
-                const int c = (wd < nwp) ? __popc(B[r * nwp + wd]) : 0;
-                int t = c;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const int o = __shfl_up_sync(0xffffffffu, t, off);
-                    if (lane >= off) t += o;
-                }
-                if (wd < nwp) Wp[r * nwp + wd] = (unsigned short)(carry + t - c);
-                carry += __shfl_sync(0xffffffffu, t, 31);
-            }
+        {   // add the totals of the chunks to the left (every warp fixes up its own chunk)
+            int off = 0;
+            for (int c = 0; c < warp; ++c) off += s_tot[c][lane];
+            if (off)
+                for (int wd = wd_lo; wd < wd_hi; ++wd) Wp[lane * nwp + wd] = (unsigned short)(Wp[lane * nwp + wd] + off);
         }
         __syncthreads();
         // ---- every thread walks its run
         {
-            bool valid = false;
+            bool valid = false;                  // (m, c_lt, hm) describe window j - 1's lower median
             int m = 0, c_lt = 0, hm = 0;
-            for (int i = 0; i < R; ++i) {
+            for (int i = 0; i < mine_n; ++i) {
                 const int j = j0 + i;
-                if (j >= A) break;
-                if ((resolved >> i) & 1u) { valid = false; continue; }
-                if (valid) {
+                const bool need_m = !((done_m >> i) & 1u), need_u = !((done_u >> i) & 1u);
+                int *__restrict__ slot = reinterpret_cast<int *>(adj + sg_slot(j));
+                if (!need_m) { valid = false; }
+                else if (valid) {
                     const int lv = L0 - 1 + m;
                     const int xo = xs[j - 1], xi = xs[j - 1 + w];
                     c_lt += (xi < lv) - (xo < lv);
@@ -568,51 +591,43 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
                         hm = F(m, j) - c_lt;
                     }
                 } else {
-                    int flo = F(0, j);
-                    if (flo >= kl + 1) { s_ctl[0] = 1; continue; }          // median below the band
-                    int fhi = F(kRankLevels - 1, j);
-                    if (fhi < kl + 1) { s_ctl[1] = 1; continue; }           // median above the band
-                    int lo = 0, hi = kRankLevels - 1;
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        const int f = F(mid, j);
-                        if (f >= kl + 1) { hi = mid; fhi = f; } else { lo = mid; flo = f; }
+                    int flo, fhi;
+                    const int r = locate(j, kl + 1, flo, fhi);
+                    if (r < 0) s_ctl[0] = 1;
+                    else if (r >= kRankLevels) s_ctl[1] = 1;
+                    else { m = r; c_lt = flo; hm = fhi - flo; valid = true; }
+                }
+                if (need_m && valid) { slot[0] = L0 - 1 + m; done_m |= 1u << i; }
+                if (need_u) {
+                    int ru = -2;                         // row of the upper median, -2 = not in this band
+                    if (need_m && valid) {               // next to the lower median just found
+                        if (c_lt + hm > ku) ru = m;
+                        else {
+                            const int below = c_lt + hm;
+                            for (int r = m + 1; r <= kRankLevels - 1; ++r)
+                                if (F(r, j) > below) { ru = r; break; }
+                            if (ru < 0) s_ctl[1] = 1;    // next occupied level lies above the band
+                        }
+                    } else {                             // on its own (its lower partner lives in another band)
+                        int flo, fhi;
+                        const int r = locate(j, ku + 1, flo, fhi);
+                        if (r < 0) s_ctl[0] = 1;
+                        else if (r >= kRankLevels) s_ctl[1] = 1;
+                        else ru = r;
                     }
-                    m = hi; c_lt = flo; hm = fhi - flo; valid = true;
+                    if (ru >= 0) { slot[1] = L0 - 1 + ru; done_u |= 1u << i; }
                 }
-                if (!valid) continue;
-                int mu = m;                              // upper median: next occupied level if rank ku is past bin m
-                if (c_lt + hm <= ku) {
-                    const int below = c_lt + hm;
-                    int r = m;
-                    bool found = false;
-                    while (++r <= kRankLevels - 1) {
-                        if (F(r, j) > below) { found = true; break; }
-                    }
-                    if (!found) { s_ctl[2] = 1; continue; }   // gap wider than the band: let the generic path do it
-                    mu = r;
-                }
-                const int bc = xs[j + (w >> 1)];
-                const int vm = L0 - 1 + m, vu = L0 - 1 + mu;
-                if (SHIFT) {
-                    const double lo_s = (double)vm - shift, hi_s = (double)vu - shift;
-                    adj[sg_slot(j)] = (AdjT)(((double)bc - shift) - (lo_s + hi_s) / 2.0);
-                } else {
-                    adj[sg_slot(j)] = (AdjT)(2 * bc - vm - vu);          // 2 * adj, exact
-                }
-                resolved |= 1u << i;
             }
         }
-        const int mine_n = max(min(A - j0, R), 0);
-        const bool done = (__popc(resolved) >= mine_n);
+        const bool done = (done_m == full_mask) && (done_u == full_mask);
         const int all_done = __syncthreads_and(done ? 1 : 0);
-        const int need_lo = s_ctl[0], need_hi = s_ctl[1], hard = s_ctl[2];
+        const int need_lo = s_ctl[0], need_hi = s_ctl[1];
         __syncthreads();
         if (all_done) break;
         if (tid == 0) { s_ctl[0] = 0; s_ctl[1] = 0; }
         if (is_lowest) pend_lo = need_lo != 0;
         if (is_highest) pend_hi = need_hi != 0;
-        if (hard || pass + 1 >= kRankMaxPasses || (!pend_lo && !pend_hi)) {
+        if (pass + 1 >= kRankMaxPasses || (!pend_lo && !pend_hi)) {
             if (tid == 0) tile_flag[tile] = 1;
             return;
         }
@@ -621,14 +636,30 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
         __syncthreads();    // s_ctl reset visible before the next walk; bitmaps free to rebuild
     }
 
+    // ---- (lower, upper) median -> adjusted value, in place (numpy: median of an even window = mean of the two)
+    {
+        double shift = 0.0;
+        if (SHIFT) shift = seg_shift[sg];
+        for (int j = tid; j < A; j += kRankThreads) {
+            const int *slot = reinterpret_cast<const int *>(adj + sg_slot(j));
+            const int vm = slot[0], vu = slot[1];
+            const int bc = xs[j + (w >> 1)];
+            double v;
+            if (SHIFT) {
+                const double lo_s = (double)vm - shift, hi_s = (double)vu - shift;
+                v = ((double)bc - shift) - (lo_s + hi_s) / 2.0;
+            } else {
+                v = (double)(2 * bc - vm - vu) * 0.5;
+            }
+            adj[sg_slot(j)] = v;
+        }
+    }
+    __syncthreads();
+
     // ---- Savitzky-Golay on the shared-memory series + coalesced store
     double *__restrict__ dst = out + seg_out_off[sg] + t0;
-    auto adj_at = [&](int k) -> double {         // adjusted value at tile-relative index k
-        if (SHIFT) return (double)adj[sg_slot(k)];
-        return (double)adj[sg_slot(k)] * 0.5;
-    };
     if (SGW < 0) {
-        for (int k = tid; k < n_t; k += kRankThreads) dst[k] = adj_at(t0 - a0 + k);
+        for (int k = tid; k < n_t; k += kRankThreads) dst[k] = adj[sg_slot(t0 - a0 + k)];
         return;
     }
     double *__restrict__ stage = reinterpret_cast<double *>(B) + warp * (128 + 8);   // per-warp 128 outputs, padded
@@ -637,7 +668,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
         const int k0 = gi * 128 + 4 * lane;      // first of this lane's 4 consecutive outputs (tile-relative output index)
         const int c0 = t0 - a0 + k0 - half;      // adj index of the first tap of output k0
         double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-        auto ld = [&](int k) -> double { return (k >= 0 && k < A) ? adj_at(k) : 0.0; };
+        auto ld = [&](int k) -> double { return (k >= 0 && k < A) ? adj[sg_slot(k)] : 0.0; };
         double r0 = ld(c0), r1 = ld(c0 + 1), r2 = ld(c0 + 2);
         if (SGW > 0) {
 #pragma unroll
@@ -662,12 +693,12 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
             if (k0 + k < n_t) {
                 if (j < half) {                  // polynomial fit of the first sg_w adjusted values
                     double e = 0.0;
-                    for (int i = 0; i < sg_w; ++i) e += edge_first[j * sg_w + i] * adj_at(i - a0);
+                    for (int i = 0; i < sg_w; ++i) e += edge_first[j * sg_w + i] * adj[sg_slot(i - a0)];
                     v[k] = e;
                 } else if (j >= n_out - half) {
                     double e = 0.0;
                     const int jj = j - (n_out - half);
-                    for (int i = 0; i < sg_w; ++i) e += edge_last[jj * sg_w + i] * adj_at(n_out - sg_w + i - a0);
+                    for (int i = 0; i < sg_w; ++i) e += edge_last[jj * sg_w + i] * adj[sg_slot(n_out - sg_w + i - a0)];
                     v[k] = e;
                 }
             }
@@ -804,8 +835,7 @@ static int launch_rank(const InT *x, const long long *so, const long long *oo, c
     const unsigned grid = (unsigned)n_tiles;
 #define FTK_RANK(SHIFT, SGW)                                                                                      \
     do {                                                                                                          \
-        using AdjT = typename std::conditional<SHIFT, double, int>::type;                                         \
-        const int smem = (int)rank_smem_bytes<AdjT>(a_cap, s_cap);                                                \
+        const int smem = (int)rank_smem_bytes(a_cap, s_cap);                                                      \
         if (smem > 227 * 1024) return FTK_E_RANGE;                                                                \
         FTK_CUDA_TRY(cudaFuncSetAttribute(adjust_rank_kernel<InT, SHIFT, SGW>,                                     \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \

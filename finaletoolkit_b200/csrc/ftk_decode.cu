@@ -52,23 +52,40 @@ bool read_file(const char *path, std::vector<unsigned char> &buf) {
     return got == buf.size();
 }
 
+// One BGZF member header at b[p...] (size bytes in the buffer).  Returns 1 and fills xend (first
+// byte of the deflate stream), end (one past the member) and usize (ISIZE) for a well-formed,
+// complete member; 0 when more bytes are needed; -1 for anything malformed: not a BGZF member, a
+// subfield that overruns the extra area, BSIZE smaller than header + trailer (would underflow the
+// compressed size), ISIZE beyond the 64 KiB a BGZF member may hold.
+int bgzf_member(const unsigned char *b, size_t size, size_t p, size_t &xend, size_t &end, size_t &usize) {
+    if (p + 18 > size) return 0;
+    if (b[p] != 31 || b[p + 1] != 139 || b[p + 2] != 8 || !(b[p + 3] & 4)) return -1;
+    const unsigned xlen = b[p + 10] | (b[p + 11] << 8);
+    size_t q = p + 12;
+    xend = q + xlen;
+    if (xend > size) return 0;
+    long bsize = -1;
+    while (q + 4 <= xend) {
+        const unsigned slen = b[q + 2] | (b[q + 3] << 8);
+        if (q + 4 + slen > xend) return -1;
+        if (b[q] == 'B' && b[q + 1] == 'C' && slen == 2) bsize = (b[q + 4] | (b[q + 5] << 8)) + 1;
+        q += 4 + slen;
+    }
+    if (bsize < 0 || (size_t)bsize < (xend - p) + 8) return -1;
+    end = p + (size_t)bsize;
+    if (end > size) return 0;
+    usize = (size_t)b[end - 4] | ((size_t)b[end - 3] << 8) | ((size_t)b[end - 2] << 16) | ((size_t)b[end - 1] << 24);
+    if (usize > 65536) return -1;
+    return 1;
+}
+
 // BGZF block list, or empty if the file is not BGZF (plain gzip)
 std::vector<Block> scan_bgzf(const std::vector<unsigned char> &b) {
     std::vector<Block> blocks;
     size_t p = 0, uoff = 0;
     while (p + 18 <= b.size()) {
-        if (b[p] != 31 || b[p + 1] != 139 || b[p + 2] != 8 || !(b[p + 3] & 4)) return {};
-        const unsigned xlen = b[p + 10] | (b[p + 11] << 8);
-        size_t q = p + 12, xend = q + xlen;
-        long bsize = -1;
-        while (q + 4 <= xend && xend <= b.size()) {
-            const unsigned slen = b[q + 2] | (b[q + 3] << 8);
-            if (b[q] == 'B' && b[q + 1] == 'C' && slen == 2) bsize = (b[q + 4] | (b[q + 5] << 8)) + 1;
-            q += 4 + slen;
-        }
-        if (bsize < 0 || p + (size_t)bsize > b.size()) return {};
-        const size_t end = p + (size_t)bsize;
-        const size_t usize = (size_t)b[end - 4] | ((size_t)b[end - 3] << 8) | ((size_t)b[end - 2] << 16) | ((size_t)b[end - 1] << 24);
+        size_t xend, end, usize;
+        if (bgzf_member(b.data(), b.size(), p, xend, end, usize) != 1) return {};
         blocks.push_back({xend, end - 8 - xend, usize, uoff});
         uoff += usize;
         p = end;
@@ -268,20 +285,8 @@ extern "C" void *ftk_fragfile_open_slice(const char *path, int64_t coffset_beg, 
     size_t p = 0, uoff = 0, last_uoff = 0;
     const size_t last_rel = (size_t)(coffset_end - coffset_beg);
     while (p + 18 <= raw.size() && (p < last_rel || (p == last_rel && uoffset_end > 0))) {
-        if (raw[p] != 31 || raw[p + 1] != 139 || raw[p + 2] != 8 || !(raw[p + 3] & 4)) return fail(FTK_E_IO);
-        const unsigned xlen = raw[p + 10] | (raw[p + 11] << 8);
-        size_t q = p + 12;
-        const size_t xend = q + xlen;
-        long bsize = -1;
-        while (q + 4 <= xend && xend <= raw.size()) {
-            const unsigned slen = raw[q + 2] | (raw[q + 3] << 8);
-            if (raw[q] == 'B' && raw[q + 1] == 'C' && slen == 2) bsize = (raw[q + 4] | (raw[q + 5] << 8)) + 1;
-            q += 4 + slen;
-        }
-        if (bsize < 0 || p + (size_t)bsize > raw.size()) return fail(FTK_E_IO);
-        const size_t end = p + (size_t)bsize;
-        const size_t usize = (size_t)raw[end - 4] | ((size_t)raw[end - 3] << 8) | ((size_t)raw[end - 2] << 16) |
-                             ((size_t)raw[end - 1] << 24);
+        size_t xend, end, usize;
+        if (bgzf_member(raw.data(), raw.size(), p, xend, end, usize) != 1) return fail(FTK_E_IO);
         if (p == last_rel) last_uoff = uoff;
         blocks.push_back({xend, end - 8 - xend, usize, uoff});
         uoff += usize;
@@ -369,8 +374,8 @@ const unsigned char *bam_consume(const unsigned char *p, const unsigned char *en
         if (memcmp(p, "BAM\1", 4) != 0) return nullptr;
         const int64_t l_text = rd_i32(p + 4);
         if (l_text < 0) return nullptr;
+        if (end - p < 12 + l_text) return p;                      // bound first, then form the pointer
         const unsigned char *q = p + 8 + l_text;
-        if (end - p < 12 + l_text) return p;
         const int64_t n_ref = rd_i32(q);
         if (n_ref < 0) return nullptr;
         q += 4;
@@ -456,22 +461,10 @@ extern "C" void *ftk_bamfile_open(const char *path, int32_t n_threads, int32_t *
         std::vector<Block> blocks;
         size_t p = 0, uoff = 0;
         while (p + 18 <= cbuf.size()) {
-            if (cbuf[p] != 31 || cbuf[p + 1] != 139 || cbuf[p + 2] != 8 || !(cbuf[p + 3] & 4)) { ok = false; break; }
-            const unsigned xlen = cbuf[p + 10] | (cbuf[p + 11] << 8);
-            size_t q = p + 12;
-            const size_t xend = q + xlen;
-            if (xend > cbuf.size()) break;
-            long bsize = -1;
-            while (q + 4 <= xend) {
-                const unsigned slen = cbuf[q + 2] | (cbuf[q + 3] << 8);
-                if (cbuf[q] == 'B' && cbuf[q + 1] == 'C' && slen == 2) bsize = (cbuf[q + 4] | (cbuf[q + 5] << 8)) + 1;
-                q += 4 + slen;
-            }
-            if (bsize < 0) { ok = false; break; }
-            if (p + (size_t)bsize > cbuf.size()) break;
-            const size_t end = p + (size_t)bsize;
-            const size_t usize = (size_t)cbuf[end - 4] | ((size_t)cbuf[end - 3] << 8) | ((size_t)cbuf[end - 2] << 16) |
-                                 ((size_t)cbuf[end - 1] << 24);
+            size_t xend, end, usize;
+            const int st_ = bgzf_member(cbuf.data(), cbuf.size(), p, xend, end, usize);
+            if (st_ < 0) { ok = false; break; }
+            if (st_ == 0) break;                                  // incomplete member: read more
             blocks.push_back({xend, end - 8 - xend, usize, uoff});
             uoff += usize;
             p = end;

@@ -12,7 +12,7 @@ import numpy as np
 
 from ._lib import FTK_NONE, FtkLibraryError, check, lib
 
-__all__ = ["ContigFragments", "WpsPlan", "IntervalSet", "PackedContig", "interval_hist", "frag_lengths",
+__all__ = ["ContigFragments", "WpsPlan", "AdjustPlan", "IntervalSet", "PackedContig", "interval_hist", "frag_lengths",
            "end_motif_hist", "delfi_windows", "blacklist_in_windows", "agg_signal", "require_cuda", "none_to_ftk", "policy_code"]
 
 _torch = None
@@ -531,20 +531,79 @@ def rank_tiles(seg_lengths, w: int, sg_w: int, t_max: int = _RANK_T_MAX):
     return (tile_seg.astype(np.int32), t0.astype(np.int32), n_t.astype(np.int32), a_cap, a_cap + int(w))
 
 
-def _rank_smem(a_cap: int, s_cap: int, shifted: bool) -> int:
+def _rank_smem(a_cap: int, s_cap: int) -> int:
     """Shared memory of one ``adjust_rank_kernel`` CTA (rank_smem_bytes in csrc/ftk_adjust.cu)."""
     a_slots = a_cap + (a_cap >> 4) + 2
     nword = (s_cap + 31) // 32
     nwp = max((nword + 1) | 1, 69)
-    b = (a_slots * (8 if shifted else 4) + 15) & ~15
+    b = a_slots * 8
     b += 32 * nwp * 6
     b = (b + 15) & ~15
     return b + (nword * 32 + 32) * 2
 
 
+class AdjustPlan:
+    """Everything ``adjust_segments`` needs that depends only on the segment layout and the filter
+    parameters - segment / output offsets, the rank kernel's tile table, the Savitzky-Golay tables -
+    built once, resident in HBM, reusable for any number of inputs with the same layout
+    (``distributed.multi_wps_genome`` keeps one per contig)."""
+
+    def __init__(self, seg_lengths, median_window_size=1000, savgol=True, savgol_window_size=21,
+                 savgol_poly_deg=2, device=None):
+        t = torch()
+        self.device = dev = require_cuda(device)
+        self.w = w = int(median_window_size)
+        self.seg_lengths = seg_lengths = np.asarray(seg_lengths, dtype=np.int64)
+        if (seg_lengths < w).any():
+            bad = int(seg_lengths[seg_lengths < w][0])
+            raise ValueError(f"median_window_size ({w}) cannot be greater than the length of interval ({bad}).")
+        if w % 2 or w < 2:
+            raise ValueError("operands could not be broadcast together: median_window_size must be even "
+                             "(frag/_adjust_wps.py:43 slices w//2 from both ends)")
+        self.n_out = n_out = seg_lengths - w
+        if savgol and (n_out < savgol_window_size).any():
+            raise ValueError("If mode is 'interp', window_length must be less than or equal to the size of x.")
+        self.n_seg = len(seg_lengths)
+        self.seg_off = np.zeros(self.n_seg + 1, np.int64); np.cumsum(seg_lengths, out=self.seg_off[1:])
+        self.out_off = np.zeros(self.n_seg + 1, np.int64); np.cumsum(n_out, out=self.out_off[1:])
+        self.n_total = int(self.out_off[-1])
+        self.d_seg = _to_device(self.seg_off, dev, np.int64)
+        self.d_out = _to_device(self.out_off, dev, np.int64)
+        self.sg_w = int(savgol_window_size) if savgol else 0
+        self.tables = None
+        if savgol:
+            coef, ef, el = savgol_tables(self.sg_w, int(savgol_poly_deg))
+            self.tables = (_to_device(coef, dev, np.float64),
+                           _to_device(ef.reshape(-1) if ef.size else np.zeros(1), dev, np.float64),
+                           _to_device(el.reshape(-1) if el.size else np.zeros(1), dev, np.float64))
+        # tile table of the rank kernel (None when the window / tile does not fit its shared memory)
+        self.rank = None
+        if self.n_total and w <= 32766 and self.sg_w <= 127:
+            tile_seg, tile_t0, tile_n, a_cap, s_cap = rank_tiles(seg_lengths, w, self.sg_w)
+            if s_cap <= 65535 - 64 and _rank_smem(a_cap, s_cap) <= _RANK_SMEM_MAX:
+                self.rank = (tuple(_to_device(a, dev, np.int32) for a in (tile_seg, tile_t0, tile_n)),
+                             len(tile_seg), a_cap, s_cap)
+
+    def run_rank(self, xd, shift_ptr=0, out=None):
+        """Launch the fused median + Savitzky-Golay kernel; returns ``(out, tile_flag)`` (no sync:
+        the caller decides when to look at the flags)."""
+        t = torch()
+        (d_ts, d_t0, d_tn), n_tiles, a_cap, s_cap = self.rank
+        if out is None:
+            out = t.empty(max(self.n_total, 1), dtype=t.float64, device=self.device)
+        flag = t.empty(n_tiles, dtype=t.uint8, device=self.device)
+        tb = self.tables
+        check(lib().ftk_adjust_rank_f64(
+            xd.data_ptr(), 1 if xd.dtype == t.int32 else 0, self.d_seg.data_ptr(), self.d_out.data_ptr(), shift_ptr,
+            self.n_seg, d_ts.data_ptr(), d_t0.data_ptr(), d_tn.data_ptr(), n_tiles, self.w, self.sg_w,
+            tb[0].data_ptr() if tb else 0, tb[1].data_ptr() if tb else 0, tb[2].data_ptr() if tb else 0,
+            a_cap, s_cap, out.data_ptr(), flag.data_ptr(), _stream_ptr(self.device)), "ftk_adjust_rank_f64")
+        return out, flag
+
+
 def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, savgol=True,
                     savgol_window_size=21, savgol_poly_deg=2, subtract_edges=False, edge_size=500,
-                    run_len=None, impl=None):
+                    run_len=None, impl=None, plan: AdjustPlan | None = None):
     """Median/mean-adjust + Savitzky-Golay smooth contiguous raw-WPS segments on the GPU.
 
     ``x``: samples of all segments back to back - float32 (numpy or CUDA tensor; bigWig values) or an
@@ -556,25 +615,15 @@ def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, sav
     The median path runs the fused rank-bitmap kernel (``ftk_adjust_rank_f64``: median + Savitzky-Golay in
     one pass, 12 B of HBM traffic per position); tiles it flags (non-integer samples, huge values) and the
     mean path go through the sliding-histogram / generic kernels + the separate Savitzky-Golay kernel.
-    ``impl="hist"`` forces that older path (``run_len`` only applies to it).
+    ``impl="hist"`` forces that older path (``run_len`` only applies to it).  ``plan``: a prebuilt
+    ``AdjustPlan`` for this layout and these parameters (skips all host-side planning and uploads).
     """
     t = torch()
     dev = require_cuda(x.device if t.is_tensor(x) and x.is_cuda else None)
-    w = int(median_window_size)
-    seg_lengths = np.asarray(seg_lengths, dtype=np.int64)
-    if (seg_lengths < w).any():
-        bad = int(seg_lengths[seg_lengths < w][0])
-        raise ValueError(f"median_window_size ({w}) cannot be greater than the length of interval ({bad}).")
-    if w % 2 or w < 2:
-        raise ValueError("operands could not be broadcast together: median_window_size must be even "
-                         "(frag/_adjust_wps.py:43 slices w//2 from both ends)")
-    n_out = seg_lengths - w
-    if savgol and (n_out < savgol_window_size).any():
-        raise ValueError("If mode is 'interp', window_length must be less than or equal to the size of x.")
-    n_seg = len(seg_lengths)
-    seg_off = np.zeros(n_seg + 1, np.int64); np.cumsum(seg_lengths, out=seg_off[1:])
-    out_off = np.zeros(n_seg + 1, np.int64); np.cumsum(n_out, out=out_off[1:])
-    n_total = int(out_off[-1])
+    if plan is None:
+        plan = AdjustPlan(seg_lengths, median_window_size, savgol, savgol_window_size, savgol_poly_deg, dev)
+    w, n_seg, n_out, n_total = plan.w, plan.n_seg, plan.n_out, plan.n_total
+    out_off = plan.out_off
     if t.is_tensor(x) and x.is_cuda and x.dtype == t.int32:
         xd = x.contiguous()
     else:
@@ -583,8 +632,7 @@ def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, sav
     out = t.empty(max(n_total, 1), dtype=t.float64, device=dev)
     if n_total == 0:
         return out[:0], out_off
-    d_seg = _to_device(seg_off, dev, np.int64)
-    d_out = _to_device(out_off, dev, np.int64)
+    d_seg, d_out = plan.d_seg, plan.d_out
     L = lib()
     sp = _stream_ptr(dev)
     shift_ptr = 0
@@ -594,29 +642,14 @@ def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, sav
         check(L.ftk_adjust_edge_shift_f64(xf.data_ptr(), d_seg.data_ptr(), n_seg, int(edge_size),
                                           shift.data_ptr(), sp), "ftk_adjust_edge_shift_f64")
         shift_ptr = shift.data_ptr()
-    sg_w = int(savgol_window_size) if savgol else 0
-    tables = None
-    if savgol:
-        coef, ef, el = savgol_tables(sg_w, int(savgol_poly_deg))
-        tables = (_to_device(coef, dev, np.float64),
-                  _to_device(ef.reshape(-1) if ef.size else np.zeros(1), dev, np.float64),
-                  _to_device(el.reshape(-1) if el.size else np.zeros(1), dev, np.float64))
+    sg_w, tables = plan.sg_w, plan.tables
 
     # ---- fused rank-bitmap kernel (median path)
-    if not use_mean and impl != "hist" and w <= 32766 and sg_w <= 127:
-        tile_seg, tile_t0, tile_n, a_cap, s_cap = rank_tiles(seg_lengths, w, sg_w)
-        if s_cap <= 65535 - 64 and _rank_smem(a_cap, s_cap, bool(subtract_edges)) <= _RANK_SMEM_MAX:
-            d_ts, d_t0, d_tn = (_to_device(a, dev, np.int32) for a in (tile_seg, tile_t0, tile_n))
-            flag = t.empty(len(tile_seg), dtype=t.uint8, device=dev)
-            check(L.ftk_adjust_rank_f64(
-                xd.data_ptr(), 1 if xd.dtype == t.int32 else 0, d_seg.data_ptr(), d_out.data_ptr(), shift_ptr, n_seg,
-                d_ts.data_ptr(), d_t0.data_ptr(), d_tn.data_ptr(), len(tile_seg), w, sg_w,
-                tables[0].data_ptr() if tables else 0, tables[1].data_ptr() if tables else 0,
-                tables[2].data_ptr() if tables else 0, a_cap, s_cap, out.data_ptr(), flag.data_ptr(), sp),
-                "ftk_adjust_rank_f64")
-            if not bool(flag.any().item()):
-                return out[:n_total], out_off
-            # some tile could not be handled: redo the call on the general path (rare: non-integer input)
+    if not use_mean and impl != "hist" and plan.rank is not None:
+        _, flag = plan.run_rank(xd, shift_ptr, out)
+        if not bool(flag.any().item()):
+            return out[:n_total], out_off
+        # some tile could not be handled: redo the call on the general path (rare: non-integer input)
 
     # ---- sliding-histogram / generic kernels + separate Savitzky-Golay
     if xd.dtype != t.float32:

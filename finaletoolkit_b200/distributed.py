@@ -179,7 +179,7 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
 
     Returns ``(results {contig: ContigWps} of this rank, hist int64[n_bins] | None, total | None)``.
     """
-    from .device import WpsPlan, adjust_segments, require_cuda, torch
+    from .device import AdjustPlan, WpsPlan, adjust_segments, require_cuda, torch
     ctx = ctx or DistContext()
     dev = require_cuda(device)
     t = torch()
@@ -224,7 +224,13 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
                 x = t.cat([wps[plan.offsets[i]: plan.offsets[i + 1]] for i in keep]) if keep.size else wps[:0]
                 seg = lens[keep]
             if keep.size:
-                res.adjusted, res.adj_offsets = adjust_segments(x, seg, **adjust)
+                aplan = plans.get((c, "adjust")) if plans is not None else None
+                if aplan is None:
+                    aplan = AdjustPlan(seg, w, adjust.get("savgol", True), adjust.get("savgol_window_size", 21),
+                                       adjust.get("savgol_poly_deg", 2), dev)
+                    if plans is not None:
+                        plans[(c, "adjust")] = aplan
+                res.adjusted, res.adj_offsets = adjust_segments(x, seg, plan=aplan, **adjust)
                 if not keep_adjusted:
                     res.adjusted = None
             res.adj_segments = keep

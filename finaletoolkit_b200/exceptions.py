@@ -35,4 +35,10 @@ class OutOfBoundsError(InvalidInputError, IndexError):
     """Queried interval falls outside chromosome bounds."""
 
 
+class BigWigWriteError(FinaleToolkitError, OSError):
+    """A background compression / write batch of the bigWig writer failed.  Deliberately NOT a
+    RuntimeError: the API mirrors catch RuntimeError to skip out-of-order intervals like the
+    reference does (frag/_multi_wps.py:319-325) and must not swallow real I/O failures."""
+
+
 __all__ = [n for n in dir() if n.endswith("Error")]

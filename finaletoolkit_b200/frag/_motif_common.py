@@ -1,4 +1,8 @@
-"""Motif containers, MDS and drivers - mirror of reference frag/_motif_common.py for end motifs."""
+"""Motif containers, MDS and window helpers behind the end- / breakpoint-motif features.
+
+Same public surface and byte-identical text as reference frag/_motif_common.py (the reference's own
+golden TSVs round-trip through these classes in tests/), but built around the arrays the CUDA kernels
+return - one float64[4^k] vector / one [n_intervals, 4^k] table - instead of dicts of Python scalars."""
 from __future__ import annotations
 
 import gzip
@@ -29,201 +33,240 @@ def _normalized_shannon_mds(counts, k: int, miller_madow: bool = False, n=None) 
     return float(entropy / np.log(num_kmers))
 
 
+def _open_text(path, mode: str):
+    """(handle, close?) for a path, ``"-"`` (stdin / stdout) or a ``.gz`` path (read side only)."""
+    name = str(path)
+    if name == "-":
+        return (stdin if "r" in mode else stdout), False
+    if "r" in mode and name.endswith("gz"):
+        return gzip.open(name, "rt"), True
+    return open(name, mode), True
+
+
+def _require_path(output_file, what: str) -> None:
+    if not isinstance(output_file, (str, Path)):
+        raise TypeError(what)
+
+
 class _MotifFreqs:
-    """Genome-wide k-mer frequencies (frag/_motif_common.py:141-262)."""
+    """Genome-wide k-mer frequencies (API of reference frag/_motif_common.py:141-262).
+
+    Array-backed: the labels and ONE float64 vector (what the kernel's 4^k counts normalise to);
+    ``freq_dict`` and the iteration protocol are views built on demand."""
 
     def __init__(self, kmer_frequencies, k: int, quality_threshold: int = MIN_QUALITY) -> None:
-        self.freq_dict = dict(kmer_frequencies)
+        pairs = list(kmer_frequencies.items()) if isinstance(kmer_frequencies, dict) else list(kmer_frequencies)
+        self._labels = [p[0] for p in pairs]
+        self._values = np.array([p[1] for p in pairs], dtype=np.float64)
         self.k = k
         self.quality_threshold = quality_threshold
-        if not all(len(kmer) == k for kmer in self.freq_dict):
+        if any(len(label) != k for label in self._labels):
             raise ValueError("kmer_frequencies contains a kmer with length not equal to k.")
 
+    @classmethod
+    def from_counts(cls, counts, k: int, quality_threshold: int = MIN_QUALITY):
+        """From the kernel's int64[4^k] counts (lexicographic ACGT order): frequencies = counts / total."""
+        c = np.asarray(counts, dtype=np.float64)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            f = c / np.sum(c)
+        return cls(zip(gen_kmers(k, _BASES), f), k, quality_threshold)
+
+    @property
+    def freq_dict(self) -> dict:
+        return dict(zip(self._labels, self._values.tolist()))
+
     def __iter__(self):
-        return ((kmer, frequency) for kmer, frequency in self.freq_dict.items())
+        return iter(zip(self._labels, self._values.tolist()))
 
     def __len__(self) -> int:
-        return len(self.freq_dict)
+        return len(self._labels)
 
     def __str__(self) -> str:
         return "".join(f"{kmer}: {freq}\n" for kmer, freq in self)
 
     def kmers(self) -> list:
-        return list(self.freq_dict.keys())
+        return list(self._labels)
 
     def frequencies(self) -> list:
-        return list(self.freq_dict.values())
+        return self._values.tolist()
 
     def freq(self, kmer: str) -> float:
-        return self.freq_dict[kmer]
+        try:
+            return float(self._values[self._labels.index(kmer)])
+        except ValueError:
+            raise KeyError(kmer) from None
 
     def to_tsv(self, output_file, sep: str = "\t") -> None:
-        if not isinstance(output_file, (str, Path)):
-            raise TypeError("output_file must be a string or path.")
-        output_is_file = False
+        _require_path(output_file, "output_file must be a string or path.")
+        out, close = _open_text(output_file, "w")
         try:
-            if str(output_file) == "-":
-                output = stdout
-            else:
-                output_is_file, output = True, open(output_file, "w")
-            for kmer, freq in self:
-                output.write(f"{kmer}{sep}{freq}\n")
+            out.write("".join(f"{kmer}{sep}{freq}\n" for kmer, freq in self))
         finally:
-            if output_is_file:
-                output.close()
+            if close:
+                out.close()
 
     def motif_diversity_score(self) -> float:
-        return _normalized_shannon_mds(np.array(self.frequencies()), self.k)
+        return _normalized_shannon_mds(self._values, self.k)
 
     @classmethod
     def from_file(cls, file_path, quality_threshold: int, sep: str = "\t", header: int = 0):
-        file, is_file = None, False
+        """Two-column ``kmer<sep>frequency`` text; reading stops at the first row that is not two
+        columns; the table must hold exactly 4^k rows of equal-length k-mers (RuntimeError otherwise)."""
+        fh, close = _open_text(file_path, "r")
         try:
-            if str(file_path).endswith("gz"):
-                is_file, file = True, gzip.open(file_path, "rt")
-            elif str(file_path) == "-":
-                file = stdin
-            else:
-                is_file, file = True, open(file_path, "rt")
-            for _ in range(header):
-                file.readline()
-            freq_list = []
-            lines = file.readlines()
-            k = len(lines[header].split(sep)[0])
-            for line in lines:
-                line_data = line.split(sep)
-                if len(line_data) != 2:
-                    break
-                freq_list.append((line_data[0], float(line_data[1])))
-                if k != len(line_data[0]):
-                    raise RuntimeError("File contains k-mers of inconsistent length.")
-            if (length := len(freq_list)) != 4 ** k:
-                raise RuntimeError(f"File contains {length} {k}-mers instead of the expected {4**k} {k}-mers.")
+            rows = fh.read().splitlines(keepends=True)[header:]
         finally:
-            if is_file and file is not None:
-                file.close()
-        return cls(freq_list, k, quality_threshold)
+            if close:
+                fh.close()
+        # k comes from the row at index `header` of what is left after skipping (reference :230)
+        k = len(rows[header].split(sep)[0])
+        labels, values = [], []
+        for row in rows:
+            cells = row.split(sep)
+            if len(cells) != 2:
+                break
+            labels.append(cells[0]); values.append(float(cells[1]))
+            if len(cells[0]) != k:
+                raise RuntimeError("File contains k-mers of inconsistent length.")
+        if len(labels) != 4 ** k:
+            raise RuntimeError(f"File contains {len(labels)} {k}-mers instead of the expected {4**k} {k}-mers.")
+        return cls(zip(labels, values), k, quality_threshold)
 
 
 class _MotifsIntervals:
-    """Interval-stratified k-mer counts (frag/_motif_common.py:265-521)."""
+    """Interval-stratified k-mer counts (API of reference frag/_motif_common.py:265-521).
 
-    def __init__(self, intervals, k: int, quality_threshold: int = MIN_QUALITY, total_counts=None) -> None:
-        self.intervals = intervals
+    Array-backed: interval tuples + ONE ``[n_intervals, 4^k]`` table (int64 straight from the kernel,
+    float64 when read back from a file) + the column labels; the reference's
+    ``[(interval, {kmer: value})]`` list is materialised only when ``.intervals`` is asked for.
+    Text is formatted from table rows through ``tolist()``, so ints print as ints and floats as
+    floats exactly like the dict-of-Python-scalars version."""
+
+    def __init__(self, intervals, k: int, quality_threshold: int = MIN_QUALITY, total_counts=None,
+                 table=None, labels=None) -> None:
         self.k = k
         self.quality_threshold = quality_threshold
         self.total_counts = total_counts
-        if not all(len(freqs) == 4 ** k for _, freqs in intervals):
+        if table is not None:
+            self._keys = list(intervals)
+            self._table = np.asarray(table)
+            self._labels = list(labels) if labels is not None else gen_kmers(k, _BASES)
+            widths_ok = self._table.ndim == 2 and (self._table.shape[1] == 4 ** k or not self._keys)
+            self._cache = None
+        else:
+            intervals = list(intervals)
+            self._keys = [iv for iv, _ in intervals]
+            widths_ok = all(len(d) == 4 ** k for _, d in intervals)
+            self._labels = list(intervals[0][1].keys()) if intervals else gen_kmers(k, _BASES)
+            rows = [list(d.values()) for _, d in intervals]
+            self._table = np.array(rows) if (rows and widths_ok) else np.zeros((0, 4 ** k), np.int64)
+            self._cache = intervals
+        if not widths_ok:
             raise ValueError("bins contains results for kmer with length not equal to k.")
-        if total_counts is not None and len(total_counts) != len(intervals):
+        if total_counts is not None and len(total_counts) != len(self._keys):
             raise ValueError("total_counts must have one entry per interval.")
 
+    @property
+    def intervals(self) -> list:
+        if self._cache is None:
+            self._cache = [(key, dict(zip(self._labels, row))) for key, row in zip(self._keys, self._table.tolist())]
+        return self._cache
+
     def __iter__(self):
-        return (interval for interval in self.intervals)
+        return iter(self.intervals)
 
     def __len__(self) -> int:
-        return len(self.intervals)
+        return len(self._keys)
 
     def __str__(self) -> str:
-        return f"{type(self).__name__} over {len(self.intervals)} intervals."
+        return f"{type(self).__name__} over {len(self._keys)} intervals."
 
     @classmethod
     def from_file(cls, file_path: str, quality_threshold: int, sep: str = ",", header: int = 0):
-        file, is_file = None, False
+        """``contig,start,stop,name,count,<4^k values>`` with one header row naming the k-mers."""
+        fh, close = _open_text(file_path, "r")
         try:
-            if file_path.endswith("gz"):
-                is_file, file = True, gzip.open(file_path, "rt")
-            elif file_path == "-":
-                file = stdin
-            else:
-                is_file, file = True, open(file_path)
-            for _ in range(header):
-                file.readline()
-            intervals, total_counts = [], []
-            lines = file.readlines()
-            _, _, _, _, _, *kmers = lines[0].split(sep)
-            k = round(np.log(len(kmers)) / np.log(4))
-            assert 4 ** k == len(kmers), f"k={k} but should be {len(kmers)}."
-            for line in lines[1:]:
-                contig, start, stop, name, count, *freqs = line.split(sep)
-                intervals.append(((contig, int(start), int(stop), name), dict(zip(kmers, [float(f) for f in freqs]))))
-                total_counts.append(float(count))
+            rows = fh.read().splitlines(keepends=True)[header:]
         finally:
-            if is_file and file is not None:
-                file.close()
-        return cls(intervals, k, quality_threshold, total_counts)
+            if close:
+                fh.close()
+        labels = rows[0].split(sep)[5:]
+        k = round(np.log(len(labels)) / np.log(4))
+        assert 4 ** k == len(labels), f"k={k} but should be {len(labels)}."
+        keys, totals, table = [], [], np.empty((len(rows) - 1, len(labels)), np.float64)
+        for i, row in enumerate(rows[1:]):
+            contig, start, stop, name, count, *cells = row.split(sep)
+            keys.append((contig, int(start), int(stop), name))
+            totals.append(float(count))
+            table[i] = [float(c) for c in cells]
+        return cls(keys, k, quality_threshold, totals, table=table, labels=labels)
 
     def freq(self, kmer: str):
-        return dict((*interval, freq[kmer]) for interval, freq in self.intervals)
+        col = self._labels.index(kmer) if kmer in self._labels else None
+        if col is None:
+            raise KeyError(kmer)
+        return dict((*key, v) for key, v in zip(self._keys, self._table[:, col].tolist()))
 
     def motif_diversity_score(self, miller_madow: bool = False):
-        mds = []
-        for index, (interval, kmers) in enumerate(self.intervals):
-            counts = np.array(list(kmers.values()))
+        scores = []
+        for i, key in enumerate(self._keys):
+            counts = self._table[i]
             total = np.sum(counts)
-            n = self.total_counts[index] if self.total_counts is not None else total
+            n = self.total_counts[i] if self.total_counts is not None else total
             with np.errstate(invalid="ignore", divide="ignore"):
-                region_mds = _normalized_shannon_mds(counts / total, self.k, miller_madow, n)
-            mds.append((interval, region_mds))
-        return mds
+                scores.append((key, _normalized_shannon_mds(counts / total, self.k, miller_madow, n)))
+        return scores
 
     def mds_bed(self, output_file, sep: str = "\t", miller_madow: bool = False) -> None:
         with open(output_file, "w") as out:
-            for interval, region_mds in self.motif_diversity_score(miller_madow):
-                contig, start, stop, name = interval
-                out.write(sep.join([contig, str(start), str(stop), name, str(region_mds)]) + "\n")
+            out.write("".join(sep.join([key[0], str(key[1]), str(key[2]), key[3], str(score)]) + "\n"
+                              for key, score in self.motif_diversity_score(miller_madow)))
+
+    @staticmethod
+    def _cell(value, count, calc_freq: bool):
+        if not calc_freq:
+            return value
+        return f"{(value / count):.6f}" if count != 0 else "NaN"
+
+    def _row_values(self, i):
+        """Python scalars of row i and their left-to-right sum (the reference sums dict values in order)."""
+        row = self._table[i].tolist()
+        return row, sum(row)
 
     def to_tsv(self, output_file, calc_freq: bool = True, sep: str = "\t") -> None:
-        if not isinstance(output_file, (str, Path)):
-            raise TypeError("output_file must be a string or path.")
-        output_is_file = False
+        _require_path(output_file, "output_file must be a string or path.")
+        out, close = _open_text(output_file, "w")
         try:
-            if str(output_file) == "-":
-                output = stdout
-            else:
-                output_is_file, output = True, open(output_file, "w")
-            output.write(sep.join(["contig", "start", "stop", "name", "count", *gen_kmers(self.k, _BASES)]) + "\n")
-            for interval, freqs in self.intervals:
-                count = sum(freqs.values())
-                if calc_freq:
-                    values = [f"{(freq / count):.6f}" if count != 0 else "NaN" for freq in freqs.values()]
-                else:
-                    values = [str(freq) for freq in freqs.values()]
-                output.write(sep.join([interval[0], str(interval[1]), str(interval[2]), str(interval[3]),
-                                       str(count), *values]) + "\n")
+            out.write(sep.join(["contig", "start", "stop", "name", "count", *gen_kmers(self.k, _BASES)]) + "\n")
+            for i, key in enumerate(self._keys):
+                row, count = self._row_values(i)
+                cells = [str(self._cell(v, count, calc_freq)) for v in row]
+                out.write(sep.join([key[0], str(key[1]), str(key[2]), str(key[3]), str(count), *cells]) + "\n")
         finally:
-            if output_is_file:
-                output.close()
+            if close:
+                out.close()
 
-    def _to_record(self, kmer, output_file, calc_freq, sep, include_name) -> None:
-        if not isinstance(output_file, (str, Path)):
-            raise TypeError("output_file must be a string.")
-        output_is_file = False
+    def _one_kmer_track(self, kmer, output_file, calc_freq, sep, with_name) -> None:
+        _require_path(output_file, "output_file must be a string.")
+        if kmer not in self._labels:
+            raise KeyError(kmer)
+        col = self._labels.index(kmer)
+        out, close = _open_text(output_file, "w")
         try:
-            if str(output_file) == "-":
-                output = stdout
-            else:
-                output_is_file, output = True, open(output_file, "w")
-            for interval, freqs in self.intervals:
-                count = sum(freqs.values())
-                if calc_freq:
-                    value = f"{(freqs[kmer] / count):.6f}" if count != 0 else "NaN"
-                else:
-                    value = freqs[kmer]
-                fields = [interval[0], str(interval[1]), str(interval[2])]
-                if include_name:
-                    fields.append(interval[3])
-                fields.append(value)
-                output.write(sep.join(fields) + "\n")
+            for i, key in enumerate(self._keys):
+                row, count = self._row_values(i)
+                fields = [key[0], str(key[1]), str(key[2])] + ([key[3]] if with_name else [])
+                fields.append(self._cell(row[col], count, calc_freq))
+                out.write(sep.join(fields) + "\n")      # a raw (non-string) count raises TypeError like the reference
         finally:
-            if output_is_file:
-                output.close()
+            if close:
+                out.close()
 
     def to_bedgraph(self, kmer, output_file, calc_freq: bool = True, sep: str = "\t") -> None:
-        self._to_record(kmer, output_file, calc_freq, sep, include_name=False)
+        self._one_kmer_track(kmer, output_file, calc_freq, sep, with_name=False)
 
     def to_bed(self, kmer, output_file, calc_freq: bool = True, sep: str = "\t") -> None:
-        self._to_record(kmer, output_file, calc_freq, sep, include_name=True)
+        self._one_kmer_track(kmer, output_file, calc_freq, sep, with_name=True)
 
 
 def genome_windows(chrom_length: int):

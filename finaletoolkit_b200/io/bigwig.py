@@ -216,7 +216,12 @@ class BigWigWriter:
             pend, self._pending, self._pending_bytes = self._pending, [], 0
             self._inflight.append(self._worker.submit(self._write_batch, pend))
         while self._inflight and (wait or len(self._inflight) > 2 or self._inflight[0].done()):
-            self._inflight.pop(0).result()        # re-raises a failure of the background batch
+            try:
+                self._inflight.pop(0).result()
+            except Exception as e:   # noqa: BLE001 - a failed background batch (deflate / write) is an I/O
+                # failure of the file, not an "out of order interval": never a RuntimeError
+                from ..exceptions import BigWigWriteError
+                raise BigWigWriteError(f"bigWig section batch failed: {e}") from e
 
     def _write_batch(self, pend) -> None:
         for (cid, start, end, _), comp in zip(pend, _deflate_sections([p[3] for p in pend])):
