@@ -475,7 +475,7 @@ def genome_block(args, dev, rank, world, peak):
     checks["ok"] = checks["ok"] and checks["config4_bins_total"] == checks["config4_lengths_total"]
 
     bytes_a = 9 * tot_frag + 4 * tot_pos
-    n_adj_out = sum(int(np.maximum(np.diff(p.offsets) - 1000, 0).sum()) for p in plans.values())
+    n_adj_out = sum(int(np.maximum(np.diff(p.offsets) - 1000, 0).sum()) for k, p in plans.items() if not isinstance(k, tuple))
     adj_out_t = torch.tensor([n_adj_out], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(adj_out_t)

@@ -195,11 +195,35 @@ def _stats_from_dict(contig, start, stop, name, frag_len_dict, short_reads) -> F
                            max(frag_len_dict.keys()), total_count, n_short / total_count)
 
 
+def _length_stats(hist: np.ndarray, first: np.ndarray, short_reads: int):
+    """(mean, median, stdev, min, max, count, frac_short) columns for the rows of ``hist`` / ``first``."""
+    from ctypes import POINTER, c_double, c_int32, c_int64
+    from .._lib import check, lib
+    hist = np.ascontiguousarray(hist, dtype=np.int32); first = np.ascontiguousarray(first, dtype=np.int32)
+    n, nb = hist.shape
+    f64 = [np.empty(n, np.float64) for _ in range(4)]
+    i64 = [np.empty(n, np.int64) for _ in range(3)]
+    p = lambda a, t: a.ctypes.data_as(POINTER(t))   # noqa: E731
+    check(lib().ftk_length_stats_host(p(hist, c_int32), p(first, c_int32), n, nb, int(short_reads), 0,
+                                      p(f64[0], c_double), p(f64[1], c_double), p(f64[2], c_double),
+                                      p(i64[0], c_int64), p(i64[1], c_int64), p(i64[2], c_int64), p(f64[3], c_double)),
+          "ftk_length_stats_host")
+    return (f64[0].tolist(), f64[1].tolist(), f64[2].tolist(), i64[0].tolist(), i64[1].tolist(), i64[2].tolist(),
+            f64[3].tolist())
+
+
+def _stats_row(contig, start, stop, name, cols, k) -> FragLengthStats:
+    if cols[5][k] < 0:   # empty interval: the reference's all -1 row (ints)
+        return FragLengthStats(contig, start, stop, name, -1, -1, -1, -1, -1, -1, -1)
+    return FragLengthStats(contig, start, stop, name, cols[0][k], cols[1][k], cols[2][k], cols[3][k], cols[4][k],
+                           cols[5][k], cols[6][k])
+
+
 def frag_length_intervals(input_file, interval_file, output_file=None, min_length=0, max_length=None,
                           quality_threshold=30, intersect_policy="midpoint", short_reads=150, workers=1,
                           verbose=False, reference_file=None):
     """Per-interval fragment-length statistics (frag/_frag_length.py:511-640)."""
-    from ..device import interval_hist, policy_code
+    from ..device import interval_hist, policy_code, torch
     if verbose:
         start_time = time.time()
     policy_code(intersect_policy)
@@ -213,15 +237,17 @@ def frag_length_intervals(input_file, interval_file, output_file=None, min_lengt
             continue
         frags = table.device(contig)
         nb = _n_bins(frags, max_length)
-        batch = max(1, (64 << 20) // (12 * nb))  # bound the per-interval histogram block to ~64 MB
+        batch = max(1, (256 << 20) // (12 * nb))  # bound the per-interval histogram block to ~256 MB
         for b0 in range(0, len(idx), batch):
             sub = idx[b0: b0 + batch]
             _, h, f = interval_hist(frags, [intervals[i][1] for i in sub], [intervals[i][2] for i in sub],
                                     intersect_policy, min_length, max_length, quality_threshold, n_bins=nb,
                                     first_seen=True)
-            h, f = h.cpu().numpy(), f.cpu().numpy()
+            # the statistics of all intervals of the batch in one native call (csrc/ftk_hoststats.cu):
+            # the reference's arithmetic and operation order, without a Python loop per interval
+            cols = _length_stats(h.to(torch().int32).cpu().numpy(), f.cpu().numpy(), short_reads)
             for k, i in enumerate(sub):
-                results[i] = _stats_from_dict(*intervals[i], _dict_from(h[k], f[k]), short_reads)
+                results[i] = _stats_row(*intervals[i], cols, k)
     if output_file is not None:
         output_is_file = False
         try:

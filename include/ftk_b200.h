@@ -84,6 +84,17 @@ int ftk_unpack_fragments(const uint32_t *words_dev, const int32_t *anchors_dev,
                          int64_t n, int32_t *start_dev, int32_t *stop_dev, uint8_t *mapq_dev, uint8_t *strand_dev,
                          ftk_stream_t stream);
 
+/* ------------------------------------------------- per-interval length statistics (host)
+ * frag_length_intervals' statistics (frag/_frag_length.py:156-172, :204-238) for n_rows intervals at
+ * once from the rows ftk_interval_hist_u64 produced (hist narrowed to int32, first_seen as is): mean,
+ * the reference's off-by-one median, stdev accumulated in the dict's first-seen order with the same
+ * libm pow() calls CPython makes, min, max, count, fraction of lengths <= short_reads.  Empty rows get
+ * -1 in every field.  Host, multi-threaded (threads <= 0: all cores). */
+int ftk_length_stats_host(const int32_t *hist_host, const int32_t *first_seen_host, int64_t n_rows,
+                          int32_t n_bins, int32_t short_reads, int32_t threads,
+                          double *mean, double *median, double *stdev, int64_t *vmin, int64_t *vmax,
+                          int64_t *count, double *frac_short);
+
 /* ------------------------------------------------------------------ WPS
  * Replaces the per-position loop of wps() - frag/_wps.py:176-188 calling the
  * numba kernel _single_nt_wps (frag/_wps.py:25-53) - and the per-interval
