@@ -424,13 +424,11 @@ def genome_block(args, dev, rank, world, peak):
         # adjust_wps of four of those intervals vs numpy median + scipy savgol on the oracle's WPS
         rb = multi_wps_genome(table, sizes, sites, IVL, WINDOW, MIN_LEN, MAX_LEN, MAPQ, adjust=adjust_kw, ctx=ctx,
                               device=dev, contigs=[small], plans=plans, reduce=False)[0][small]
-        seg_of = {int(i): k for k, i in enumerate(rb.adj_segments)}
         worst = 0.0
         for j, i in enumerate(pick[:4]):
-            if int(i) not in seg_of or e_[j] - s_[j] < 1021:
+            if e_[j] - s_[j] < 1021:
                 continue
-            k = seg_of[int(i)]
-            got = rb.adjusted[rb.adj_offsets[k]: rb.adj_offsets[k + 1]].cpu().numpy()
+            got = rb.adjusted[rb.adj_offsets[i]: rb.adj_offsets[i + 1]].cpu().numpy()
             ref = O.adjust_core(exp[off[j]: off[j + 1]].astype(np.float64), 1000, False, True, 21, 2)
             worst = max(worst, float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-9 / 1e-5))))
         checks["adjust_max_rel_err"] = worst

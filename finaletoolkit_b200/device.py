@@ -506,12 +506,12 @@ _RANK_T_MAX = 4096          # outputs per tile of the rank-bitmap kernel
 _RANK_SMEM_MAX = 227 * 1024
 
 
-def rank_tiles(seg_lengths, w: int, sg_w: int, t_max: int = _RANK_T_MAX):
+def rank_tiles(seg_lengths, w: int, sg_w: int, t_max: int = _RANK_T_MAX, n_out=None):
     """Tile plan of ``ftk_adjust_rank_f64``: every segment's ``n - w`` outputs split evenly into
     pieces of at most ``t_max``.  Returns ``(tile_seg, tile_t0, tile_n, a_cap, s_cap)`` (int32 arrays;
     caps = most adjusted values / samples a tile stages, same arithmetic as the kernel)."""
     seg_lengths = np.asarray(seg_lengths, dtype=np.int64)
-    n_out = seg_lengths - int(w)
+    n_out = (seg_lengths - int(w)) if n_out is None else np.asarray(n_out, dtype=np.int64)
     pieces = np.maximum(-(-n_out // int(t_max)), 0)
     piece = np.where(pieces > 0, -(-n_out // np.maximum(pieces, 1)), 0)
     tile_seg = np.repeat(np.arange(len(seg_lengths), dtype=np.int64), pieces)
@@ -549,20 +549,26 @@ class AdjustPlan:
     (``distributed.multi_wps_genome`` keeps one per contig)."""
 
     def __init__(self, seg_lengths, median_window_size=1000, savgol=True, savgol_window_size=21,
-                 savgol_poly_deg=2, device=None):
+                 savgol_poly_deg=2, device=None, skip_short=False):
         t = torch()
         self.device = dev = require_cuda(device)
         self.w = w = int(median_window_size)
         self.seg_lengths = seg_lengths = np.asarray(seg_lengths, dtype=np.int64)
-        if (seg_lengths < w).any():
-            bad = int(seg_lengths[seg_lengths < w][0])
-            raise ValueError(f"median_window_size ({w}) cannot be greater than the length of interval ({bad}).")
         if w % 2 or w < 2:
             raise ValueError("operands could not be broadcast together: median_window_size must be even "
                              "(frag/_adjust_wps.py:43 slices w//2 from both ends)")
-        self.n_out = n_out = seg_lengths - w
-        if savgol and (n_out < savgol_window_size).any():
-            raise ValueError("If mode is 'interp', window_length must be less than or equal to the size of x.")
+        n_out = seg_lengths - w
+        if skip_short:
+            # segments the reference's driver would skip (frag/_adjust_wps.py:125-129 raises per interval,
+            # :145-153 skips it) stay in the sample layout but produce no output
+            n_out = np.where((n_out >= (savgol_window_size if savgol else 0)) & (n_out > 0), n_out, 0)
+        else:
+            if (seg_lengths < w).any():
+                bad = int(seg_lengths[seg_lengths < w][0])
+                raise ValueError(f"median_window_size ({w}) cannot be greater than the length of interval ({bad}).")
+            if savgol and (n_out < savgol_window_size).any():
+                raise ValueError("If mode is 'interp', window_length must be less than or equal to the size of x.")
+        self.n_out = n_out
         self.n_seg = len(seg_lengths)
         self.seg_off = np.zeros(self.n_seg + 1, np.int64); np.cumsum(seg_lengths, out=self.seg_off[1:])
         self.out_off = np.zeros(self.n_seg + 1, np.int64); np.cumsum(n_out, out=self.out_off[1:])
@@ -579,7 +585,7 @@ class AdjustPlan:
         # tile table of the rank kernel (None when the window / tile does not fit its shared memory)
         self.rank = None
         if self.n_total and w <= 32766 and self.sg_w <= 127:
-            tile_seg, tile_t0, tile_n, a_cap, s_cap = rank_tiles(seg_lengths, w, self.sg_w)
+            tile_seg, tile_t0, tile_n, a_cap, s_cap = rank_tiles(seg_lengths, w, self.sg_w, n_out=n_out)
             if s_cap <= 65535 - 64 and _rank_smem(a_cap, s_cap) <= _RANK_SMEM_MAX:
                 self.rank = (tuple(_to_device(a, dev, np.int32) for a in (tile_seg, tile_t0, tile_n)),
                              len(tile_seg), a_cap, s_cap)

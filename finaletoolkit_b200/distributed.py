@@ -215,25 +215,22 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
             wps, cov = plan.run(frags, window_size, min_length, max_length, quality_threshold), None
         res = ContigWps(c, starts, stops, plan.offsets, wps, cov)
         if adjust is not None:
-            w = int(adjust.get("median_window_size", 1000))
-            lens = np.diff(plan.offsets)
-            keep = np.flatnonzero(lens >= max(w, 1))
-            if keep.size == len(lens):
-                x, seg = wps, lens
-            else:   # intervals shorter than the median window are skipped (frag/_adjust_wps.py:125-129 raises per interval)
-                x = t.cat([wps[plan.offsets[i]: plan.offsets[i + 1]] for i in keep]) if keep.size else wps[:0]
-                seg = lens[keep]
-            if keep.size:
-                aplan = plans.get((c, "adjust")) if plans is not None else None
-                if aplan is None:
-                    aplan = AdjustPlan(seg, w, adjust.get("savgol", True), adjust.get("savgol_window_size", 21),
-                                       adjust.get("savgol_poly_deg", 2), dev)
-                    if plans is not None:
-                        plans[(c, "adjust")] = aplan
-                res.adjusted, res.adj_offsets = adjust_segments(x, seg, plan=aplan, **adjust)
+            # every interval is a segment of the int32 WPS buffer as it lies in HBM (no gather, no float
+            # copy); intervals shorter than the filters need produce no output, like the reference's driver
+            aplan = plans.get((c, "adjust")) if plans is not None else None
+            if aplan is None:
+                aplan = AdjustPlan(np.diff(plan.offsets), int(adjust.get("median_window_size", 1000)),
+                                   adjust.get("savgol", True), adjust.get("savgol_window_size", 21),
+                                   adjust.get("savgol_poly_deg", 2), dev, skip_short=True)
+                if plans is not None:
+                    plans[(c, "adjust")] = aplan
+            if aplan.n_total:
+                res.adjusted, res.adj_offsets = adjust_segments(wps, None, plan=aplan, **adjust)
                 if not keep_adjusted:
                     res.adjusted = None
-            res.adj_segments = keep
+            else:
+                res.adj_offsets = aplan.out_off
+            res.adj_segments = np.flatnonzero(aplan.n_out > 0)
         results[c] = res
     if fused and reduce:
         ctx.all_reduce_sum(packed)
@@ -243,18 +240,17 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
 
 def adjust_wps_genome(results: dict, **adjust):
     """Adjust already computed device-resident WPS (``multi_wps_genome`` results) in place of the
-    reference's bigWig -> adjust_wps -> bigWig pass (frag/_adjust_wps.py:59-111)."""
-    from .device import adjust_segments, torch
-    t = torch()
-    w = int(adjust.get("median_window_size", 1000))
+    reference's bigWig -> adjust_wps -> bigWig pass (frag/_adjust_wps.py:59-111).  Interval i's adjusted
+    series is ``res.adjusted[res.adj_offsets[i]: res.adj_offsets[i + 1]]`` (empty for intervals shorter
+    than the filters need)."""
+    from .device import AdjustPlan, adjust_segments
     for res in results.values():
-        lens = np.diff(res.offsets)
-        keep = np.flatnonzero(lens >= max(w, 1))
-        if not keep.size:
-            continue
-        x = res.wps if keep.size == len(lens) else t.cat([res.wps[res.offsets[i]: res.offsets[i + 1]] for i in keep])
-        res.adjusted, res.adj_offsets = adjust_segments(x, lens[keep], **adjust)
-        res.adj_segments = keep
+        aplan = AdjustPlan(np.diff(res.offsets), int(adjust.get("median_window_size", 1000)),
+                           adjust.get("savgol", True), adjust.get("savgol_window_size", 21),
+                           adjust.get("savgol_poly_deg", 2), res.wps.device, skip_short=True)
+        res.adj_offsets, res.adj_segments = aplan.out_off, np.flatnonzero(aplan.n_out > 0)
+        if aplan.n_total:
+            res.adjusted, _ = adjust_segments(res.wps, None, plan=aplan, **adjust)
     return results
 
 

@@ -92,9 +92,9 @@ for c, r in res.items():
     exp, off = O.wps_intervals(fr, r.starts, r.stops, contigs[c], 120, 120, 180, 30, threads=4)
     bad += int((r.wps.cpu().numpy().astype(np.int64) != exp).sum())
     bad += int((r.cov.cpu().numpy() != O.interval_coverage(fr, r.starts, r.stops, None, None, "midpoint", 30)).sum())
-    for k, i in enumerate(r.adj_segments[:3]):
+    for i in r.adj_segments[:3]:
         ref_adj = O.adjust_core(exp[off[i]: off[i + 1]].astype(np.float64), 1000, False, True, 21, 2)
-        got = r.adjusted[r.adj_offsets[k]: r.adj_offsets[k + 1]].cpu().numpy()
+        got = r.adjusted[r.adj_offsets[i]: r.adj_offsets[i + 1]].cpu().numpy()
         bad += int(not np.allclose(got, ref_adj, rtol=1e-5, atol=1e-9))
 badt = torch.tensor([bad], device=dev); dist.all_reduce(badt)
 frs_all = {c: O.Frags(*cols[c]) for c in contigs}
