@@ -410,9 +410,10 @@ __host__ __device__ inline RankGeom rank_geom(int a_cap, int s_cap) {
     g.s_pad = nword * 32;
     return g;
 }
-__host__ __device__ inline size_t rank_smem_bytes(int a_cap, int s_cap) {
+__host__ __device__ inline size_t rank_smem_bytes(int a_cap, int s_cap, bool shifted) {
     const RankGeom g = rank_geom(a_cap, s_cap);
-    size_t b = (size_t)g.a_slots * sizeof(double);
+    size_t b = (size_t)g.a_slots * (shifted ? sizeof(double) : sizeof(int));
+    b = (b + 15) & ~(size_t)15;
     b += (size_t)kRankLevels * g.nwp * 4;       // bitmaps
     b += (size_t)kRankLevels * g.nwp * 2;       // per-word prefix popcounts
     b = (b + 15) & ~(size_t)15;
@@ -429,19 +430,29 @@ __device__ __forceinline__ bool rank_stage(int v, int &iv) {
     return (v >= -kRankMaxAbs) && (v <= kRankMaxAbs);
 }
 
-// 32 x 32 bit-matrix transpose across a warp: lane i holds row i, afterwards lane r holds column r
+// 32 x 32 bit-matrix transpose across a warp: lane i holds row i, afterwards lane r holds column r.
+// Stage s swaps the off-diagonal s x s blocks between lanes l and l ^ s: the lower lane takes the
+// partner's word shifted up by s into its high sub-blocks, the upper lane takes it shifted down into
+// its low sub-blocks - one rotate (the unwanted half of the rotation is masked away) and one
+// select-by-mask per stage.
 __device__ __forceinline__ unsigned warp_transpose32(unsigned x, int lane) {
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) {
         const unsigned msk = (s == 16) ? 0x0000ffffu : (s == 8) ? 0x00ff00ffu : (s == 4) ? 0x0f0f0f0fu
                            : (s == 2) ? 0x33333333u : 0x55555555u;
+        const bool upper = (lane & s) != 0;
+        const unsigned take = upper ? msk : ~msk;            // bits this lane receives from its partner
         const unsigned y = __shfl_xor_sync(0xffffffffu, x, s);
-        x = (lane & s) ? ((x & ~msk) | ((y >> s) & msk)) : ((x & msk) | ((y << s) & ~msk));
+        const unsigned rot = __funnelshift_l(y, y, upper ? 32 - s : s);
+        x = (x & ~take) | (rot & take);
     }
     return x;
 }
 
-// SHIFT = subtract_edges (per-segment fp64 shift).
+// SHIFT = subtract_edges (per-segment fp64 shift): the adjusted value is then a general double;
+// without it 2 * adj is an integer and the tile keeps THAT as int32 (half the shared memory: three
+// CTAs per SM instead of two), the factor 1/2 folded into the Savitzky-Golay coefficients
+// (fma(c/2, 2a, acc) == fma(c, a, acc) bit for bit).
 template <typename InT, bool SHIFT, int SGW>   // SGW: 21 = unrolled default, 0 = runtime window, -1 = no smoothing
 __global__ void __launch_bounds__(kRankThreads, 3)
 adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_off,
@@ -454,13 +465,15 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
     __shared__ int s_ctl[4];            // 0: need lower band, 1: need higher band, 2: unused, 3: centre
     __shared__ int s_tot[kRankWarps][kRankLevels];   // per-warp-chunk row totals of the bitmap build
     __shared__ double s_coef[kAdjMaxSg + 1];
+    using AdjT = typename std::conditional<SHIFT, double, int>::type;
     const RankGeom G = rank_geom(a_cap, s_cap);
-    // adj slot j first holds the two middle order statistics of window j as int32 pairs, then the
-    // adjusted value as a double
-    double *__restrict__ adj = reinterpret_cast<double *>(rank_smem);
-    unsigned *__restrict__ B = reinterpret_cast<unsigned *>(adj + G.a_slots);
+    // adj slot j first holds the two middle order statistics of window j as an int16 pair, then the
+    // adjusted value (double, or the integer 2 * adj)
+    AdjT *__restrict__ adj = reinterpret_cast<AdjT *>(rank_smem);
+    const size_t o_b = ((size_t)G.a_slots * sizeof(AdjT) + 15) & ~(size_t)15;
+    unsigned *__restrict__ B = reinterpret_cast<unsigned *>(rank_smem + o_b);
     unsigned short *__restrict__ Wp = reinterpret_cast<unsigned short *>(B + kRankLevels * G.nwp);
-    const size_t o_x = ((size_t)G.a_slots * 8 + (size_t)kRankLevels * G.nwp * 6 + 15) & ~(size_t)15;
+    const size_t o_x = (o_b + (size_t)kRankLevels * G.nwp * 6 + 15) & ~(size_t)15;
     short *__restrict__ xs = reinterpret_cast<short *>(rank_smem + o_x);
     const int nwp = G.nwp;
 
@@ -481,7 +494,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
     }
     const int A = a1 - a0, S = A + w;
     if (tid < 3) s_ctl[tid] = 0;
-    if (SGW >= 0) for (int i = tid; i < sg_w; i += kRankThreads) s_coef[i] = coef[i];
+    if (SGW >= 0) for (int i = tid; i < sg_w; i += kRankThreads) s_coef[i] = SHIFT ? coef[i] : coef[i] * 0.5;
     bool bad = (A > a_cap) || (S > s_cap) || (A <= 0);
     // ---- stage the samples (coalesced), validate: integer-valued and small
     if (!bad) {
@@ -573,7 +586,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
             for (int i = 0; i < mine_n; ++i) {
                 const int j = j0 + i;
                 const bool need_m = !((done_m >> i) & 1u), need_u = !((done_u >> i) & 1u);
-                int *__restrict__ slot = reinterpret_cast<int *>(adj + sg_slot(j));
+                short *__restrict__ slot = reinterpret_cast<short *>(adj + sg_slot(j));
                 if (!need_m) { valid = false; }
                 else if (valid) {
                     const int lv = L0 - 1 + m;
@@ -597,7 +610,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
                     else if (r >= kRankLevels) s_ctl[1] = 1;
                     else { m = r; c_lt = flo; hm = fhi - flo; valid = true; }
                 }
-                if (need_m && valid) { slot[0] = L0 - 1 + m; done_m |= 1u << i; }
+                if (need_m && valid) { slot[0] = (short)(L0 - 1 + m); done_m |= 1u << i; }
                 if (need_u) {
                     int ru = -2;                         // row of the upper median, -2 = not in this band
                     if (need_m && valid) {               // next to the lower median just found
@@ -615,7 +628,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
                         else if (r >= kRankLevels) s_ctl[1] = 1;
                         else ru = r;
                     }
-                    if (ru >= 0) { slot[1] = L0 - 1 + ru; done_u |= 1u << i; }
+                    if (ru >= 0) { slot[1] = (short)(L0 - 1 + ru); done_u |= 1u << i; }
                 }
             }
         }
@@ -641,45 +654,59 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
         double shift = 0.0;
         if (SHIFT) shift = seg_shift[sg];
         for (int j = tid; j < A; j += kRankThreads) {
-            const int *slot = reinterpret_cast<const int *>(adj + sg_slot(j));
+            const short *slot = reinterpret_cast<const short *>(adj + sg_slot(j));
             const int vm = slot[0], vu = slot[1];
             const int bc = xs[j + (w >> 1)];
-            double v;
             if (SHIFT) {
                 const double lo_s = (double)vm - shift, hi_s = (double)vu - shift;
-                v = ((double)bc - shift) - (lo_s + hi_s) / 2.0;
+                adj[sg_slot(j)] = (AdjT)(((double)bc - shift) - (lo_s + hi_s) / 2.0);
             } else {
-                v = (double)(2 * bc - vm - vu) * 0.5;
+                adj[sg_slot(j)] = (AdjT)(2 * bc - vm - vu);          // 2 * adj, exact
             }
-            adj[sg_slot(j)] = v;
         }
     }
     __syncthreads();
 
     // ---- Savitzky-Golay on the shared-memory series + coalesced store
     double *__restrict__ dst = out + seg_out_off[sg] + t0;
+    auto val = [&](int k) -> double {            // adjusted value at tile-relative index k (edge fits, no smoothing)
+        return SHIFT ? (double)adj[sg_slot(k)] : (double)adj[sg_slot(k)] * 0.5;
+    };
     if (SGW < 0) {
-        for (int k = tid; k < n_t; k += kRankThreads) dst[k] = adj[sg_slot(t0 - a0 + k)];
+        for (int k = tid; k < n_t; k += kRankThreads) dst[k] = val(t0 - a0 + k);
         return;
     }
     double *__restrict__ stage = reinterpret_cast<double *>(B) + warp * (128 + 8);   // per-warp 128 outputs, padded
     const int groups = (n_t + 127) / 128;        // a warp-iteration covers 128 consecutive outputs
+    const int taps = (SGW > 0) ? SGW : sg_w;
     for (int gi = warp; gi < groups; gi += kRankWarps) {
         const int k0 = gi * 128 + 4 * lane;      // first of this lane's 4 consecutive outputs (tile-relative output index)
         const int c0 = t0 - a0 + k0 - half;      // adj index of the first tap of output k0
         double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-        auto ld = [&](int k) -> double { return (k >= 0 && k < A) ? adj[sg_slot(k)] : 0.0; };
-        double r0 = ld(c0), r1 = ld(c0 + 1), r2 = ld(c0 + 2);
-        if (SGW > 0) {
+        // s_coef holds c (SHIFT) or c / 2 (the tile then stores 2 * adj): the products are the same
+        if (c0 >= 0 && c0 + taps + 3 <= A) {     // every tap in range: unguarded loads
+            const AdjT *__restrict__ p = adj;
+            double r0 = (double)p[sg_slot(c0)], r1 = (double)p[sg_slot(c0 + 1)], r2 = (double)p[sg_slot(c0 + 2)];
+            if (SGW > 0) {
 #pragma unroll
-            for (int i = 0; i < (SGW > 0 ? SGW : 1); ++i) {
-                const double r3 = ld(c0 + i + 3);
-                const double c = s_coef[i];
-                acc0 += c * r0; acc1 += c * r1; acc2 += c * r2; acc3 += c * r3;
-                r0 = r1; r1 = r2; r2 = r3;
+                for (int i = 0; i < (SGW > 0 ? SGW : 1); ++i) {
+                    const double r3 = (double)p[sg_slot(c0 + i + 3)];
+                    const double c = s_coef[i];
+                    acc0 += c * r0; acc1 += c * r1; acc2 += c * r2; acc3 += c * r3;
+                    r0 = r1; r1 = r2; r2 = r3;
+                }
+            } else {
+                for (int i = 0; i < sg_w; ++i) {
+                    const double r3 = (double)p[sg_slot(c0 + i + 3)];
+                    const double c = s_coef[i];
+                    acc0 += c * r0; acc1 += c * r1; acc2 += c * r2; acc3 += c * r3;
+                    r0 = r1; r1 = r2; r2 = r3;
+                }
             }
         } else {
-            for (int i = 0; i < sg_w; ++i) {
+            auto ld = [&](int k) -> double { return (k >= 0 && k < A) ? (double)adj[sg_slot(k)] : 0.0; };
+            double r0 = ld(c0), r1 = ld(c0 + 1), r2 = ld(c0 + 2);
+            for (int i = 0; i < taps; ++i) {
                 const double r3 = ld(c0 + i + 3);
                 const double c = s_coef[i];
                 acc0 += c * r0; acc1 += c * r1; acc2 += c * r2; acc3 += c * r3;
@@ -693,12 +720,12 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
             if (k0 + k < n_t) {
                 if (j < half) {                  // polynomial fit of the first sg_w adjusted values
                     double e = 0.0;
-                    for (int i = 0; i < sg_w; ++i) e += edge_first[j * sg_w + i] * adj[sg_slot(i - a0)];
+                    for (int i = 0; i < sg_w; ++i) e += edge_first[j * sg_w + i] * val(i - a0);
                     v[k] = e;
                 } else if (j >= n_out - half) {
                     double e = 0.0;
                     const int jj = j - (n_out - half);
-                    for (int i = 0; i < sg_w; ++i) e += edge_last[jj * sg_w + i] * adj[sg_slot(n_out - sg_w + i - a0)];
+                    for (int i = 0; i < sg_w; ++i) e += edge_last[jj * sg_w + i] * val(n_out - sg_w + i - a0);
                     v[k] = e;
                 }
             }
@@ -835,7 +862,7 @@ static int launch_rank(const InT *x, const long long *so, const long long *oo, c
     const unsigned grid = (unsigned)n_tiles;
 #define FTK_RANK(SHIFT, SGW)                                                                                      \
     do {                                                                                                          \
-        const int smem = (int)rank_smem_bytes(a_cap, s_cap);                                                      \
+        const int smem = (int)rank_smem_bytes(a_cap, s_cap, SHIFT);                                               \
         if (smem > 227 * 1024) return FTK_E_RANGE;                                                                \
         FTK_CUDA_TRY(cudaFuncSetAttribute(adjust_rank_kernel<InT, SHIFT, SGW>,                                     \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \

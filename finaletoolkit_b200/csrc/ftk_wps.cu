@@ -318,11 +318,13 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
     const uint32_t addr = smem_u32(bar);
     unsigned ok;
     do {
+        // the suspend-time hint lets the hardware park the warp until the phase flips instead of
+        // returning every few hundred cycles: 12 % of the kernel's issued instructions were this loop
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+            : "=r"(ok) : "r"(addr), "r"(parity), "r"(1000000u) : "memory");
     } while (!ok);
 }
 __device__ __forceinline__ void mbar_arrive(void *bar) {

@@ -531,12 +531,12 @@ def rank_tiles(seg_lengths, w: int, sg_w: int, t_max: int = _RANK_T_MAX, n_out=N
     return (tile_seg.astype(np.int32), t0.astype(np.int32), n_t.astype(np.int32), a_cap, a_cap + int(w))
 
 
-def _rank_smem(a_cap: int, s_cap: int) -> int:
+def _rank_smem(a_cap: int, s_cap: int, shifted: bool = True) -> int:
     """Shared memory of one ``adjust_rank_kernel`` CTA (rank_smem_bytes in csrc/ftk_adjust.cu)."""
     a_slots = a_cap + (a_cap >> 4) + 2
     nword = (s_cap + 31) // 32
     nwp = max((nword + 1) | 1, 69)
-    b = a_slots * 8
+    b = (a_slots * (8 if shifted else 4) + 15) & ~15
     b += 32 * nwp * 6
     b = (b + 15) & ~15
     return b + (nword * 32 + 32) * 2
