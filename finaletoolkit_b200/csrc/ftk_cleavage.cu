@@ -53,32 +53,57 @@ cleavage_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__re
         reinterpret_cast<int4 *>(E)[i] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();
-    constexpr int kU = 4;   // independent loads in flight per thread
-    for (int64_t i0 = lo + tid; i0 < hi; i0 += (int64_t)kU * kClvThreads) {
-      int fs_r[kU], fe_r[kU], q_r[kU], sd_r[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int64_t i = i0 + (int64_t)u * kClvThreads;
-        const bool in = i < hi;
-        fs_r[u] = in ? __ldcs(frag_start + i) : 0;
-        fe_r[u] = in ? __ldcs(frag_stop + i) : -1;
-        q_r[u] = in ? (frag_mapq ? (int)__ldcs(frag_mapq + i) : 255) : -1;
-        sd_r[u] = (in && frag_strand) ? (int)__ldcs(frag_strand + i) : 1;
-      }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int fs = fs_r[u], fe = fe_r[u], q = q_r[u];
+    auto visit = [&](int fs, int fe, int q, int sd) {
         const int L = fe - fs;
         // frag_array(..., "any") of the INTERVAL: tabix overlap + mapq + inclusive length window
-        if (q < min_mapq || L < 0 || !frag_len_ok(L, min_len, max_len) || !(fe > ivl_lo && fs < ivl_hi)) continue;
+        if (q < min_mapq || L < 0 || !frag_len_ok(L, min_len, max_len) || !(fe > ivl_lo && fs < ivl_hi)) return;
         const int s_idx = fs - p0, e_idx = fe - p0;
         if (e_idx > 0 && s_idx < len) {                 // covers at least one tile position
             atomicAdd(&D[max(s_idx, 0)], 1);
             if (e_idx < len) atomicAdd(&D[e_idx], -1);
         }
-        const int end_idx = sd_r[u] ? s_idx : e_idx;
+        const int end_idx = sd ? s_idx : e_idx;
         if (end_idx >= 0 && end_idx < len) atomicAdd(&E[end_idx], 1);
-      }
+    };
+    // the candidate slice is widened to a 16-byte boundary on the left (extra fragments are harmless:
+    // the range is only a superset) so every lane streams 4 fragments per 128-bit load
+    constexpr int kU = 2;   // independent vector loads in flight per thread (8 fragments)
+    const int64_t lo_al = lo & ~(int64_t)3;
+    const int cnt = (hi > lo_al) ? (int)(hi - lo_al) : 0;
+    const int nvec = cnt >> 2;
+    const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(frag_start + lo_al);
+    const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(frag_stop + lo_al);
+    const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(frag_mapq ? frag_mapq + lo_al : nullptr);
+    const uchar4 *__restrict__ vd = reinterpret_cast<const uchar4 *>(frag_strand ? frag_strand + lo_al : nullptr);
+    for (int v0 = tid; v0 < nvec; v0 += kU * kClvThreads) {
+        int4 s4[kU], e4[kU];
+        uchar4 q4[kU], d4[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int v = v0 + u * kClvThreads;
+            if (v < nvec) {
+                s4[u] = __ldcs(vs + v); e4[u] = __ldcs(ve + v);
+                q4[u] = vq ? __ldcs(vq + v) : make_uchar4(255, 255, 255, 255);
+                d4[u] = vd ? __ldcs(vd + v) : make_uchar4(1, 1, 1, 1);
+            } else {
+                s4[u] = make_int4(0, 0, 0, 0); e4[u] = make_int4(-1, -1, -1, -1);   // L < 0: skipped
+                q4[u] = make_uchar4(0, 0, 0, 0); d4[u] = make_uchar4(1, 1, 1, 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            visit(s4[u].x, e4[u].x, q4[u].x, d4[u].x);
+            visit(s4[u].y, e4[u].y, q4[u].y, d4[u].y);
+            visit(s4[u].z, e4[u].z, q4[u].z, d4[u].z);
+            visit(s4[u].w, e4[u].w, q4[u].w, d4[u].w);
+        }
+    }
+    {   // tail: at most 3 fragments
+        const int i = nvec * 4 + tid;
+        if (i < cnt)
+            visit(__ldcs(frag_start + lo_al + i), __ldcs(frag_stop + lo_al + i),
+                  frag_mapq ? (int)__ldcs(frag_mapq + lo_al + i) : 255,
+                  frag_strand ? (int)__ldcs(frag_strand + lo_al + i) : 1);
     }
     __syncthreads();
     // block prefix scan: each thread owns kClvPer contiguous positions (int4 loads, conflict-free)
@@ -119,7 +144,16 @@ cleavage_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__re
     }
     __syncthreads();
     double *__restrict__ dst = out + tile_out_off[tile];
-    for (int p = tid; p < len; p += kClvThreads) dst[p] = stage[p];   // coalesced
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {               // coalesced 16-byte streaming stores
+        const int pairs = len >> 1;
+        for (int p = tid; p < pairs; p += kClvThreads) {
+            const double2 v = reinterpret_cast<const double2 *>(stage)[p];
+            asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" :: "l"(dst + 2 * p), "d"(v.x), "d"(v.y) : "memory");
+        }
+        if ((len & 1) && tid == 0) dst[len - 1] = stage[len - 1];
+    } else {
+        for (int p = tid; p < len; p += kClvThreads) dst[p] = stage[p];
+    }
 }
 
 }  // namespace ftk

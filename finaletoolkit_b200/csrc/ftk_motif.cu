@@ -27,7 +27,7 @@ namespace ftk {
 
 constexpr int kMotifThreads = 256;
 constexpr int kMotifSmemBins = 4096;  // k <= 6 privatised in shared memory
-constexpr int kMotifUnroll = 4;
+
 
 // 2k-bit window starting at base `pos` (base i at bits 2*(i%16) of word i/16): one funnel shift
 // over two consecutive words; k <= 12, so 24 bits at a shift <= 30 always fit.
@@ -58,30 +58,21 @@ __global__ void motif_ranges_kernel(const int32_t *__restrict__ frag_start, int6
     ranges[t] = lower_bound(frag_start, n_frag, key);
 }
 
-// A CTA walks its slice of the start-sorted fragments in sub-chunks of kMotifSub fragments.  The
-// k-mer windows of a sub-chunk lie in [first start - h, last start + max_frag_len + k + h): at 30x
-// that is ~13 kb = 0.8 K words of the packed contig + 0.4 K words of N mask, which the CTA copies
-// into shared memory with coalesced loads before touching a fragment.  A window is then one
-// funnel shift over two SHARED words instead of a dependent chain of two L2 loads per end (the
-// round-1 kernel sat on 13.6 long-scoreboard stalls per issue), and when the staged N mask is all
-// zero - nearly every span of a real genome - the N test disappears altogether.  A sub-chunk whose
-// span does not fit (sparse data) reads the contig from global memory as before.  Fragments are
-// fetched four per lane with 128-bit loads.
-constexpr int kMotifSub = 4096;          // fragments per sub-chunk (16 per thread)
-constexpr int kMotifRefWords = 3072;     // staged packed-contig words (49,152 bp); N mask: half as many
-
+// Fragments are fetched four per lane with 128-bit loads (two vectors = eight fragments in flight per
+// thread); the k-mer windows are read from the L2-resident packed contig.  (A variant that staged the
+// contig span of every 4096-fragment sub-chunk in shared memory was measured in round 2 and lost:
+// 0.59 ms against 0.39 ms - the staging serialises bounds -> span -> fragments behind two barriers
+// per sub-chunk and its 75 registers cut the residency to three CTAs per SM.)
 template <bool SMEM, bool BREAKPOINT>
-__global__ void __launch_bounds__(kMotifThreads)
+__global__ void __launch_bounds__(kMotifThreads, 6)
 end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
                  const uint8_t *__restrict__ frag_mapq, const uint8_t *__restrict__ frag_strand,
                  const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask, int64_t contig_len,
                  const int32_t *__restrict__ ivl_start, const int32_t *__restrict__ ivl_stop,
                  const int64_t *__restrict__ ranges, int k, int strand_mode, int min_mapq,
-                 int pooled, int splits, int max_frag_len, unsigned long long *__restrict__ counts,
+                 int pooled, int splits, unsigned long long *__restrict__ counts,
                  int32_t *__restrict__ error_flag) {
     __shared__ int s_cnt[SMEM ? kMotifSmemBins : 1];
-    __shared__ uint32_t s_seq[kMotifRefWords + 2];
-    __shared__ uint32_t s_nm[kMotifRefWords / 2 + 4];
     const int tid = threadIdx.x;
     const int n_bins = 1 << (2 * k);
     const int64_t ivl = blockIdx.x / splits;
@@ -105,122 +96,77 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
     // 32-bit everything inside the slice: contig positions are int32 and a slice is < 2^31 fragments
     const uint32_t mask2k = (1u << (2 * k)) - 1u, maskk = (1u << k) - 1u;
     const int len32 = (int)min(contig_len, (int64_t)INT32_MAX);
-    const int total_words = (len32 + 15) / 16 + 2;      // allocation of the packed contig (synth.pack_twobit)
     const int h = k >> 1;
-    // the slice is widened to a 16-byte boundary on the left so that every lane loads 4 fragments
-    // per 128-bit load; fragments outside [lo, hi) are masked by index
-    const int64_t lo_al = lo & ~(int64_t)3;
-    const int skip = (int)(lo - lo_al);
-    const int n_here = (hi > lo) ? (int)(hi - lo_al) : 0;
-    const int32_t *__restrict__ fsp = frag_start + lo_al;
-    const int32_t *__restrict__ fep = frag_stop + lo_al;
-    const uint8_t *__restrict__ fqp = frag_mapq ? frag_mapq + lo_al : nullptr;
-    const uint8_t *__restrict__ fdp = frag_strand ? frag_strand + lo_al : nullptr;
-
-    for (int c0 = 0; c0 < n_here; c0 += kMotifSub) {
-        const int n_sub = min(kMotifSub, n_here - c0);
-        // ---- stage the span of the packed contig this sub-chunk can touch
-        const int p_first = __ldg(fsp + c0), p_last = __ldg(fsp + c0 + n_sub - 1);
-        const long long pos_lo_ll = max((long long)p_first - h - 1, 0ll);
-        const long long pos_hi_ll = min((long long)p_last + max_frag_len + k + h + 1, (long long)len32);
-        const int w_lo = (int)((pos_lo_ll >> 5) << 1);                      // even: aligned with an N-mask word
-        const long long n_words_ll = ((pos_hi_ll + 15) >> 4) + 2 - w_lo;
-        const bool staged = (pos_hi_ll > pos_lo_ll) && n_words_ll <= kMotifRefWords && p_last >= p_first;
-        const int n_words = staged ? (int)min(n_words_ll, (long long)(total_words - w_lo)) : 0;
-        const int nm_lo = w_lo >> 1;
-        const int st_lo = w_lo << 4, st_hi = (w_lo + n_words - 1) << 4;      // positions [st_lo, st_hi) have both words staged
-        int any_n = 0;
-        if (staged) {
-            unsigned acc = 0;
-            for (int i = tid; i < n_words; i += kMotifThreads) s_seq[i] = __ldg(seq + w_lo + i);
-            const int n_nm = (n_words + 1) / 2 + 1;
-            const int total_nm = (len32 + 31) / 32 + 2;
-            for (int i = tid; i < n_nm; i += kMotifThreads) {
-                const unsigned v = (nm_lo + i < total_nm) ? __ldg(nmask + nm_lo + i) : 0u;
-                s_nm[i] = v; acc |= v;
-            }
-            any_n = __syncthreads_or(acc != 0u);
-        }
-        auto win = [&](int pos) -> uint32_t {
-            if (staged && pos >= st_lo && pos < st_hi) {
-                const int w = (pos >> 4) - w_lo;
-                return __funnelshift_r(s_seq[w], s_seq[w + 1], (pos & 15) * 2) & mask2k;
-            }
-            return window2(seq, pos, mask2k);
-        };
-        auto with_n = [&](int pos) -> bool {
-            if (staged && pos >= st_lo && pos < st_hi) {
-                if (!any_n) return false;
-                const int w = (pos >> 5) - nm_lo;
-                return (__funnelshift_r(s_nm[w], s_nm[w + 1], pos & 31) & maskk) != 0u;
-            }
-            return has_n(nmask, pos, maskk);
-        };
-        auto visit = [&](int fs, int fe, int q, int sd) {
-            if (q < min_mapq || !(fe > S && fs < E)) return;
-            if (BREAKPOINT) {
-                if (fs < h || fs >= len32 - h) return;                       // too close to a contig end
-                if ((k & 1) != 0) return;                                    // 2h != k: never counted
-                if (strand_mode == 0 || (strand_mode == 1 && sd)) {
-                    if (!with_n(fs - h)) bump(digit_reverse(win(fs - h), k));
-                }
-                if (strand_mode != 1) {
-                    if (fe < h || fe > len32 - h) return;                    // OutOfBoundsError -> skipped
-                    if (!with_n(fe - h)) bump((~win(fe - h)) & mask2k);
-                }
-                return;
-            }
-            if (strand_mode == 1 && !sd) return;         // forward-only: '+' fragments only
-            if (strand_mode != 2) {
-                if (fs < 0 || fs > len32 - k) return;    // ValueError -> `continue`
-                if (!with_n(fs)) bump(digit_reverse(win(fs), k));
+    auto visit = [&](int fs, int fe, int q, int sd) {
+        if (q < min_mapq || !(fe > S && fs < E)) return;
+        if (BREAKPOINT) {
+            if (fs < h || fs >= len32 - h) return;                       // too close to a contig end
+            if ((k & 1) != 0) return;                                    // 2h != k: never counted
+            if (strand_mode == 0 || (strand_mode == 1 && sd)) {
+                if (!has_n(nmask, fs - h, maskk)) bump(digit_reverse(window2(seq, fs - h, mask2k), k));
             }
             if (strand_mode != 1) {
-                if (fe < k || fe > len32) {
-                    if (strand_mode == 0) atomicOr(error_flag, 1);  // RuntimeError in the reference
-                    return;
-                }
-                if (!with_n(fe - k)) bump((~win(fe - k)) & mask2k);
+                if (fe < h || fe > len32 - h) return;                    // OutOfBoundsError -> skipped
+                if (!has_n(nmask, fe - h, maskk)) bump((~window2(seq, fe - h, mask2k)) & mask2k);
             }
-        };
-        // ---- the sub-chunk's fragments, four per lane and load
-        const int nvec = n_sub >> 2;
-        const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(fsp + c0);
-        const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(fep + c0);
-        const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(fqp ? fqp + c0 : nullptr);
-        const uchar4 *__restrict__ vd = reinterpret_cast<const uchar4 *>(fdp ? fdp + c0 : nullptr);
-        for (int v0 = tid; v0 < nvec; v0 += kMotifUnroll * kMotifThreads) {
-            int4 s4[kMotifUnroll], e4[kMotifUnroll];
-            uchar4 q4[kMotifUnroll], d4[kMotifUnroll];
-#pragma unroll
-            for (int u = 0; u < kMotifUnroll; ++u) {
-                const int v = v0 + u * kMotifThreads;
-                if (v < nvec) {
-                    s4[u] = __ldcs(vs + v); e4[u] = __ldcs(ve + v);
-                    q4[u] = vq ? __ldcs(vq + v) : make_uchar4(255, 255, 255, 255);
-                    d4[u] = vd ? __ldcs(vd + v) : make_uchar4(1, 1, 1, 1);
-                } else {
-                    s4[u] = make_int4(0, 0, 0, 0); e4[u] = make_int4(0, 0, 0, 0);
-                    q4[u] = make_uchar4(0, 0, 0, 0); d4[u] = make_uchar4(1, 1, 1, 1);
-                }
+            return;
+        }
+        if (strand_mode == 1 && !sd) return;         // forward-only: '+' fragments only
+        if (strand_mode != 2) {
+            if (fs < 0 || fs > len32 - k) return;    // ValueError -> `continue`
+            if (!has_n(nmask, fs, maskk)) bump(digit_reverse(window2(seq, fs, mask2k), k));
+        }
+        if (strand_mode != 1) {
+            if (fe < k || fe > len32) {
+                if (strand_mode == 0) atomicOr(error_flag, 1);  // RuntimeError in the reference
+                return;
             }
+            if (!has_n(nmask, fe - k, maskk)) bump((~window2(seq, fe - k, mask2k)) & mask2k);
+        }
+    };
+    // the slice is widened to a 16-byte boundary on the left so that every lane loads 4 fragments per
+    // 128-bit load; fragments left of lo are masked by index
+    const int64_t lo_al = lo & ~(int64_t)3;
+    const int skip = (int)(lo - lo_al);
+    const int cnt = (hi > lo) ? (int)(hi - lo_al) : 0;
+    const int nvec = cnt >> 2;
+    const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(frag_start + lo_al);
+    const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(frag_stop + lo_al);
+    const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(frag_mapq ? frag_mapq + lo_al : nullptr);
+    const uchar4 *__restrict__ vd = reinterpret_cast<const uchar4 *>(frag_strand ? frag_strand + lo_al : nullptr);
+    constexpr int kU = 2;
+    for (int v0 = tid; v0 < nvec; v0 += kU * kMotifThreads) {
+        int4 s4[kU], e4[kU];
+        uchar4 q4[kU], d4[kU];
 #pragma unroll
-            for (int u = 0; u < kMotifUnroll; ++u) {
-                const int v = v0 + u * kMotifThreads;
-                if (v >= nvec) continue;
-                const int i = c0 + v * 4;                        // index relative to lo_al
-                if (i + 0 >= skip) visit(s4[u].x, e4[u].x, q4[u].x, d4[u].x);
-                if (i + 1 >= skip) visit(s4[u].y, e4[u].y, q4[u].y, d4[u].y);
-                if (i + 2 >= skip) visit(s4[u].z, e4[u].z, q4[u].z, d4[u].z);
-                visit(s4[u].w, e4[u].w, q4[u].w, d4[u].w);
+        for (int u = 0; u < kU; ++u) {
+            const int v = v0 + u * kMotifThreads;
+            if (v < nvec) {
+                s4[u] = __ldcs(vs + v); e4[u] = __ldcs(ve + v);
+                q4[u] = vq ? __ldcs(vq + v) : make_uchar4(255, 255, 255, 255);
+                d4[u] = vd ? __ldcs(vd + v) : make_uchar4(1, 1, 1, 1);
+            } else {
+                s4[u] = make_int4(0, 0, 0, 0); e4[u] = make_int4(0, 0, 0, 0);
+                q4[u] = make_uchar4(0, 0, 0, 0); d4[u] = make_uchar4(1, 1, 1, 1);
             }
         }
-        {   // tail: at most 3 fragments
-            const int i = c0 + nvec * 4 + tid;
-            if (tid < (n_sub & 3) && i >= skip)
-                visit(__ldcs(fsp + i), __ldcs(fep + i), fqp ? (int)__ldcs(fqp + i) : 255, fdp ? (int)__ldcs(fdp + i) : 1);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int v = v0 + u * kMotifThreads;
+            if (v >= nvec) continue;
+            const bool head = (v == 0);
+            if (!(head && skip > 0)) visit(s4[u].x, e4[u].x, q4[u].x, d4[u].x);
+            if (!(head && skip > 1)) visit(s4[u].y, e4[u].y, q4[u].y, d4[u].y);
+            if (!(head && skip > 2)) visit(s4[u].z, e4[u].z, q4[u].z, d4[u].z);
+            visit(s4[u].w, e4[u].w, q4[u].w, d4[u].w);
         }
-        __syncthreads();     // the staged span is rewritten by the next sub-chunk
+    }
+    {   // tail: at most 3 fragments
+        const int i = nvec * 4 + tid;
+        if (i < cnt && i >= skip)
+            visit(__ldcs(frag_start + lo_al + i), __ldcs(frag_stop + lo_al + i),
+                  frag_mapq ? (int)__ldcs(frag_mapq + lo_al + i) : 255,
+                  frag_strand ? (int)__ldcs(frag_strand + lo_al + i) : 1);
     }
     if (SMEM) {
         __syncthreads();
@@ -264,13 +210,11 @@ static int motif_hist_launch(const int32_t *frag_start, const int32_t *frag_stop
     if ((1 << (2 * k)) <= kMotifSmemBins)
         end_motif_kernel<true, BREAKPOINT><<<grid, kMotifThreads, 0, stream>>>(
             frag_start, frag_stop, frag_mapq, frag_strand, seq_words, nmask_words, contig_len,
-            ivl_start, ivl_stop, scratch, k, strand_mode, min_mapq, pooled, splits,
-            max_frag_len < 0 ? 0 : max_frag_len, c, error_flag);
+            ivl_start, ivl_stop, scratch, k, strand_mode, min_mapq, pooled, splits, c, error_flag);
     else
         end_motif_kernel<false, BREAKPOINT><<<grid, kMotifThreads, 0, stream>>>(
             frag_start, frag_stop, frag_mapq, frag_strand, seq_words, nmask_words, contig_len,
-            ivl_start, ivl_stop, scratch, k, strand_mode, min_mapq, pooled, splits,
-            max_frag_len < 0 ? 0 : max_frag_len, c, error_flag);
+            ivl_start, ivl_stop, scratch, k, strand_mode, min_mapq, pooled, splits, c, error_flag);
     FTK_CHECK_LAUNCH("end_motif_kernel");
     return FTK_OK;
 }
