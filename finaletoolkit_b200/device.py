@@ -50,14 +50,52 @@ def _np_ptr(a, ctype):
     return a.ctypes.data_as(POINTER(ctype))
 
 
+class _PinnedStaging:
+    """Two reusable pinned host buffers for the big host -> device uploads.
+
+    ``cudaHostAlloc`` of a fresh buffer per column costs ~0.3 s per GB - more than the copy itself.  The
+    staging buffers are allocated once (grown on demand), a column is memcpy'd into the free one and
+    sent with an asynchronous copy; the buffer is reused only after the event recorded behind that copy
+    has completed, so back-to-back uploads overlap the next memcpy with the previous DMA."""
+
+    def __init__(self):
+        self.bufs = [None, None]
+        self.events = [None, None]
+        self.turn = 0
+
+    def upload(self, a: np.ndarray, device):
+        t = torch()
+        i = self.turn
+        self.turn ^= 1
+        nbytes = a.nbytes
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        if self.bufs[i] is None or self.bufs[i].numel() < nbytes:
+            self.bufs[i] = None
+            self.bufs[i] = t.empty(max(nbytes, 1 << 26), dtype=t.uint8).pin_memory()
+        stage = self.bufs[i][:nbytes]
+        stage.numpy()[:] = a.reshape(-1).view(np.uint8)
+        out = t.empty(a.shape, dtype=t.from_numpy(a[:0]).dtype, device=device)
+        out.view(t.uint8).reshape(-1).copy_(stage, non_blocking=True)
+        ev = t.cuda.Event()
+        ev.record(t.cuda.current_stream(device))
+        self.events[i] = ev
+        return out
+
+
+_STAGING: dict = {}
+
+
 def _to_device(a: np.ndarray, device, dtype):
     """H2D through pinned staging (async on the current stream)."""
     t = torch()
     a = np.ascontiguousarray(a, dtype=dtype)
-    host = t.from_numpy(a)
-    if a.nbytes >= (1 << 23):   # pinning costs a cudaHostAlloc: only worth it for the big columns
-        host = host.pin_memory()
-    return host.to(device, non_blocking=True)
+    if a.nbytes >= (1 << 23):   # big columns go through the reusable pinned staging buffers
+        key = str(device)
+        if key not in _STAGING:
+            _STAGING[key] = _PinnedStaging()
+        return _STAGING[key].upload(a, device)
+    return t.from_numpy(a).to(device, non_blocking=True)
 
 
 class ContigFragments:
@@ -609,7 +647,7 @@ class AdjustPlan:
 
 def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, savgol=True,
                     savgol_window_size=21, savgol_poly_deg=2, subtract_edges=False, edge_size=500,
-                    run_len=None, impl=None, plan: AdjustPlan | None = None):
+                    run_len=None, impl=None, plan: AdjustPlan | None = None, defer_check: bool = False):
     """Median/mean-adjust + Savitzky-Golay smooth contiguous raw-WPS segments on the GPU.
 
     ``x``: samples of all segments back to back - float32 (numpy or CUDA tensor; bigWig values) or an
@@ -623,6 +661,9 @@ def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, sav
     mean path go through the sliding-histogram / generic kernels + the separate Savitzky-Golay kernel.
     ``impl="hist"`` forces that older path (``run_len`` only applies to it).  ``plan``: a prebuilt
     ``AdjustPlan`` for this layout and these parameters (skips all host-side planning and uploads).
+    ``defer_check=True`` (median path with a rank plan only): no host synchronisation - returns
+    ``(out, out_off, tile_flag)`` and the caller looks at ``tile_flag.any()`` later (and calls again
+    with ``impl="hist"`` if it is set).
     """
     t = torch()
     dev = require_cuda(x.device if t.is_tensor(x) and x.is_cuda else None)
@@ -653,6 +694,8 @@ def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, sav
     # ---- fused rank-bitmap kernel (median path)
     if not use_mean and impl != "hist" and plan.rank is not None:
         _, flag = plan.run_rank(xd, shift_ptr, out)
+        if defer_check:
+            return out[:n_total], out_off, flag
         if not bool(flag.any().item()):
             return out[:n_total], out_off
         # some tile could not be handled: redo the call on the general path (rare: non-integer input)
@@ -691,6 +734,8 @@ def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, sav
         check(L.ftk_savgol_f64(adj.data_ptr(), d_out.data_ptr(), n_seg, n_total, sg_w,
                                tables[0].data_ptr(), tables[1].data_ptr(), tables[2].data_ptr(), out.data_ptr(), sp),
               "ftk_savgol_f64")
+    if defer_check:
+        return out[:n_total], out_off, None
     return out[:n_total], out_off
 
 

@@ -13,7 +13,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from finaletoolkit_b200 import device as D
 from finaletoolkit_b200.synth import synth_fragments_device
 
-CLEN, N = 249_250_621, int(os.environ.get("NFRAG", 80_000_000))
+CLEN = int(os.environ.get("CLEN", 249_250_621))
+N = int(os.environ.get("NFRAG", round(CLEN * 80_000_000 / 249_250_621)))
 dev = D.require_cuda("cuda:0")
 st, sp, mq = synth_fragments_device(CLEN, N, 0, dev)
 fr = D.ContigFragments(st, sp, mq, None, device=dev, max_len=600)
