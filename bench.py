@@ -276,6 +276,46 @@ def other_kernels(frags, wps_i32, dev, peak):
     return out
 
 
+# ------------------------------------------------- public API wall clock (N=1 only)
+def api_wall():
+    """Wall clock (second call) of the reference-facing Python API on a 5 M-fragment, 60-Mb contig with
+    12,000 5-kb intervals: where the host-side tail (result download, statistics, text / bigWig writers)
+    stands next to the kernels.  Fragments come from an in-memory FragmentTable (decode excluded)."""
+    import tempfile
+    import finaletoolkit_b200 as F
+    from finaletoolkit_b200.frag import _multi_wps as MW
+    from finaletoolkit_b200.io.fragments import FragmentTable
+    from finaletoolkit_b200.synth import synth_fragments
+    clen, n = 60_000_000, 5_000_000
+    table = FragmentTable({"1": synth_fragments(clen, n, 1)})
+    tmp = tempfile.mkdtemp(prefix="ftk_wall_")
+    tiles = os.path.join(tmp, "tiles.bed")
+    with open(tiles, "w") as fh:
+        fh.write("".join(f"1\t{a}\t{a + 5000}\n" for a in range(0, clen, 5000)))
+    sites = os.path.join(tmp, "sites.bed")
+    with open(sites, "w") as fh:
+        fh.write("".join(f"1\t{a}\t{a + 1}\t.\t0\t+\n" for a in range(2500, clen, 5000)))
+    cs = os.path.join(tmp, "cs")
+    open(cs, "w").write(f"1\t{clen}\n")
+
+    def wall(fn):
+        fn()
+        t0 = time.perf_counter(); fn()
+        return (time.perf_counter() - t0) * 1e3
+
+    out = {"input": f"{n} fragments, {clen} bp, 12000 intervals (in-memory table: decode excluded)"}
+    out["frag_length_intervals_ms"] = wall(lambda: F.frag_length_intervals(table, tiles, os.path.join(tmp, "fli.bed")))
+    out["coverage_ms"] = wall(lambda: F.coverage(table, tiles, os.path.join(tmp, "cov.bed")))
+    out["frag_length_bins_ms"] = wall(lambda: F.frag_length_bins(table, "1", 0, clen, bin_size=5))
+    for ext in (".bed.gz", ".bw"):
+        ms = wall(lambda: F.multi_wps(table, sites, chrom_sizes=cs, output_file=os.path.join(tmp, "wps" + ext)))
+        t = dict(MW.LAST_TIMINGS)
+        out["multi_wps->" + ext] = {"total_ms": ms, "compute_ms": t["compute"] * 1e3, "write_ms": t["write"] * 1e3,
+                                    "total_over_write": ms / max(t["write"] * 1e3, 1e-9)}
+    out["adjust_wps(.bw->.bw)_ms"] = wall(lambda: F.adjust_wps(os.path.join(tmp, "wps.bw"), sites, os.path.join(tmp, "adj.bw"), cs))
+    return out
+
+
 # ------------------------------------------------------------- genome block
 class SynthGenomeTable:
     """FragmentTable stand-in for BASELINE.json configs[2]: 24 b37 contigs, fragments proportional to
@@ -727,6 +767,10 @@ def run_ours(args):
                 line["other_kernels"] = other_kernels(frags, wps_for_extras, dev, peak)
             except Exception as e:  # noqa: BLE001 - secondary numbers must never sink the headline line
                 line["other_kernels"] = {"error": repr(e)}
+            try:
+                line["api_wall"] = api_wall()
+            except Exception as e:  # noqa: BLE001
+                line["api_wall"] = {"error": repr(e)}
         line["cpu_baseline"] = cpu_info
         print(json.dumps(line), flush=True)
     if world > 1:

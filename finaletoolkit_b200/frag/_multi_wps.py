@@ -19,7 +19,11 @@ from ..utils import chrom_sizes_to_list
 from ._common import group_by_contig, resolve_length_aliases
 from ._wps import _wps_device
 
-__all__ = ["multi_wps"]
+__all__ = ["multi_wps", "LAST_TIMINGS"]
+
+# wall-clock split of the most recent multi_wps call (seconds): decode = file -> columns, compute = upload +
+# kernels + download, write = output file; read by bench.py's api_wall block
+LAST_TIMINGS: dict = {}
 
 
 def _read_header(input_file, table: FragmentTable, chrom_sizes):
@@ -79,6 +83,7 @@ def multi_wps(input_file, site_bed, chrom_sizes=None, output_file=None, window_s
     if input_file == "-" and site_bed == "-":
         raise ValueError("input_file and site_bed cannot both read from stdin")
     min_length, max_length = resolve_length_aliases(min_length, max_length, fraction_low, fraction_high)
+    t_begin = time.perf_counter()
     table = as_table(input_file, reference_file)
     header = _read_header(input_file, table, chrom_sizes)
     references = [chrom for chrom, _ in header]
@@ -98,7 +103,9 @@ def multi_wps(input_file, site_bed, chrom_sizes=None, output_file=None, window_s
 
     # one GPU launch per contig, results kept in interval order
     results: list = [None] * len(contigs)
+    t_decoded = time.perf_counter()
     for contig, idx in group_by_contig(contigs).items():
+        table.host(contig)      # lazy tables decode here: keep it out of the compute share
         out, off = _wps_device(table, contig, [starts[i] for i in idx], [stops[i] for i in idx],
                                chrom_sizes_dict[contig], int(window_size), min_length, int(round(max_length)),
                                quality_threshold)
@@ -106,6 +113,7 @@ def multi_wps(input_file, site_bed, chrom_sizes=None, output_file=None, window_s
         for k, i in enumerate(idx):
             results[i] = host[off[k]: off[k + 1]]
 
+    t_computed = time.perf_counter()
     if isinstance(output_file, str):
         if output_file.endswith(".bw"):
             with pbw.open(output_file, "w") as bigwig:
@@ -123,6 +131,10 @@ def multi_wps(input_file, site_bed, chrom_sizes=None, output_file=None, window_s
             with GzipTextWriter(output_file) as bedgraph:   # frag/_multi_wps.py:328-341, same text
                 for contig, start, scores in zip(contigs, starts, results):
                     bedgraph.write(bedgraph_text(contig, start, scores))
+    t_end = time.perf_counter()
+    LAST_TIMINGS.clear()
+    LAST_TIMINGS.update(decode=t_decoded - t_begin, compute=t_computed - t_decoded, write=t_end - t_computed,
+                        total=t_end - t_begin)
     if verbose:
         stderr.write(f"multi_wps took {time.time() - start_time} s to complete\n")
     return output_file
