@@ -596,10 +596,9 @@ def run_ours(args):
     launches_per_step = 2   # fragment-range prepass + the fused kernel
 
     def step(ev=None):
-        cov_out.zero_(); hist_out.zero_()
         if ev is not None:
             ev[0].record()
-        plan.ranges_fused(frags, WINDOW)
+        plan.ranges_fused(frags, WINDOW, zero_counts=cov_out, zero_hist=hist_out)   # also clears the accumulators
         if ev is not None:
             ev[1].record()
         # ONE sweep over the fragments: WPS + per-interval coverage + pooled length histogram

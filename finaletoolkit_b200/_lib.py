@@ -43,7 +43,8 @@ SYMBOLS = {
                                   c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "ftk_wps_tiles_i8": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int64,
                                  c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
-    "ftk_wps_cov_tile_ranges": (c_int, [_P, c_int64, _P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "ftk_wps_cov_tile_ranges": (c_int, [_P, c_int64, _P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, _P,
+                                        _P, c_int64, _P, c_int64, _P]),
     "ftk_wps_cov_tiles": (c_int, [_P, _P, _P, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_int64,
                                   c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                   c_int32, _P, c_int32, _P, _P, _P, _P, _P]),

@@ -580,10 +580,56 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
         }
         __syncthreads();
         // ---- every thread walks its run
+        int i_first = 0;
+        if (pass == 0 && mine_n > 0) {
+            // fast path of the first pass: both middle order statistics of every output are still
+            // unknown and almost always inside the band - locate the first lower median, then slide;
+            // the general loop below takes over at the first output that does not resolve here
+            int flo, fhi;
+            int m = locate(j0, kl + 1, flo, fhi);
+            if (m >= 0 && m < kRankLevels) {
+                int c_lt = flo, hm = fhi - flo;
+                int slot_i = sg_slot(j0);
+                for (;;) {
+                    const int j = j0 + i_first;
+                    int ru = m;                              // upper median: same level unless rank ku is past it
+                    if (c_lt + hm <= ku) {
+                        const int below = c_lt + hm;
+                        ru = -1;
+                        for (int r = m + 1; r <= kRankLevels - 1; ++r)
+                            if (F(r, j) > below) { ru = r; break; }
+                        if (ru < 0) break;                   // next occupied level above the band: general loop
+                    }
+                    const int lvl = L0 - 1;
+                    *reinterpret_cast<unsigned *>(adj + slot_i) = ((unsigned)(lvl + ru) << 16) | ((unsigned)(lvl + m) & 0xffffu);
+                    if (++i_first >= mine_n) break;
+                    // slide to window j + 1
+                    const int lv = lvl + m;
+                    const int xo = xs[j], xi = xs[j + w];
+                    c_lt += (xi < lv) - (xo < lv);
+                    hm += (xi == lv) - (xo == lv);
+                    slot_i += 1 + (((j + 1) & 15) == 0);
+                    bool ok = true;
+                    while (c_lt > kl) {                      // median moved down
+                        if (--m < 1) { ok = false; break; }
+                        const int q = F(m - 1, j + 1);
+                        hm = c_lt - q; c_lt = q;
+                    }
+                    while (ok && c_lt + hm <= kl) {          // median moved up
+                        c_lt += hm;
+                        if (++m > kRankLevels - 1) { ok = false; break; }
+                        hm = F(m, j + 1) - c_lt;
+                    }
+                    if (!ok) break;
+                }
+            }
+            const unsigned got = (i_first >= 32) ? 0xffffffffu : ((1u << i_first) - 1u);
+            done_m = got; done_u = got;
+        }
         {
             bool valid = false;                  // (m, c_lt, hm) describe window j - 1's lower median
             int m = 0, c_lt = 0, hm = 0;
-            for (int i = 0; i < mine_n; ++i) {
+            for (int i = i_first; i < mine_n; ++i) {
                 const int j = j0 + i;
                 const bool need_m = !((done_m >> i) & 1u), need_u = !((done_u >> i) & 1u);
                 short *__restrict__ slot = reinterpret_cast<short *>(adj + sg_slot(j));

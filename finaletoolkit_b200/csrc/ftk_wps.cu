@@ -28,16 +28,22 @@ static_assert(kWpsIters * kWpsThreads * 4 == kWpsCap, "tile must split evenly");
 static_assert(FTK_WPS_TILE < kWpsCap, "one guard slot for odd windows");
 
 // Per-tile fragment index range [lo, hi): a superset of the fragments with any
-// event inside the tile.  One thread per bound; the upper levels of the search
-// tree stay in L2, so this costs a few microseconds per launch.
-__global__ void wps_tile_ranges_kernel(const int32_t *__restrict__ frag_start, int64_t n_frag,
-                                       const int32_t *__restrict__ tile_p0,
-                                       const int32_t *__restrict__ tile_len, int64_t n_tiles,
-                                       int left_reach, int b, int64_t *__restrict__ ranges) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// event inside the tile.  One WARP per bound (32-ary search: six dependent loads for 80 M
+// fragments); the prepass also zeroes the accumulators of the fused pass, so a step is two launches.
+__global__ void __launch_bounds__(256)
+wps_tile_ranges_kernel(const int32_t *__restrict__ frag_start, int64_t n_frag,
+                       const int32_t *__restrict__ tile_p0, const int32_t *__restrict__ tile_len,
+                       int64_t n_tiles, int left_reach, int b, int64_t *__restrict__ ranges,
+                       unsigned long long *__restrict__ zero_a, int64_t n_zero_a,
+                       unsigned long long *__restrict__ zero_b, int64_t n_zero_b) {
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = gtid; i < n_zero_a; i += gthreads) zero_a[i] = 0ull;
+    for (int64_t i = gtid; i < n_zero_b; i += gthreads) zero_b[i] = 0ull;
+    const int64_t t = gtid >> 5;
     if (t >= 2 * n_tiles) return;
-    int64_t tile = t >> 1;
-    int64_t p0 = tile_p0[tile];
+    const int64_t tile = t >> 1;
+    const int64_t p0 = tile_p0[tile];
     int64_t key;
     if ((t & 1) == 0) {
         // a fragment starting more than left_reach before p0 - 1 cannot matter to the tile
@@ -47,7 +53,8 @@ __global__ void wps_tile_ranges_kernel(const int32_t *__restrict__ frag_start, i
         // first event sits at fs-b; it must be < p0+len
         key = p0 + (int64_t)tile_len[tile] + (int64_t)b;
     }
-    ranges[t] = lower_bound(frag_start, n_frag, key);
+    const int64_t r = warp_lower_bound(frag_start, n_frag, key);
+    if ((threadIdx.x & 31) == 0) ranges[t] = r;
 }
 
 // ---------------------------------------------------------------------------
@@ -842,16 +849,19 @@ static int wps_check_args(const int32_t *frag_start, const int32_t *frag_stop, i
 // left_reach: how far left of p0 - 1 a fragment may start and still matter to the tile
 static int launch_tile_ranges(const int32_t *frag_start, int64_t n_frag, const int32_t *tile_p0,
                               const int32_t *tile_len, int64_t n_tiles, int32_t window_size,
-                              int64_t left_reach, int64_t *scratch, cudaStream_t stream) {
+                              int64_t left_reach, int64_t *scratch, cudaStream_t stream,
+                              unsigned long long *zero_a = nullptr, int64_t n_zero_a = 0,
+                              unsigned long long *zero_b = nullptr, int64_t n_zero_b = 0) {
     using namespace ftk;
     const bool odd = (window_size & 1) != 0;
     const int a = odd ? (window_size - 1) / 2 : window_size / 2;
     const int b = odd ? a : a - 1;
     if (left_reach > INT32_MAX / 2) left_reach = INT32_MAX / 2;
-    const int64_t n = 2 * n_tiles;
-    const int threads = 128;
+    const int64_t n = 2 * n_tiles * 32;          // one warp per bound
+    const int threads = 256;
     wps_tile_ranges_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(
-        frag_start, n_frag, tile_p0, tile_len, n_tiles, (int)left_reach, b, scratch);
+        frag_start, n_frag, tile_p0, tile_len, n_tiles, (int)left_reach, b, scratch, zero_a, n_zero_a, zero_b,
+        n_zero_b);
     FTK_CHECK_LAUNCH("wps_tile_ranges_kernel");
     return FTK_OK;
 }
@@ -1050,14 +1060,19 @@ static int64_t fused_left_reach(int32_t window_size, int32_t max_len, int32_t co
 extern "C" int ftk_wps_cov_tile_ranges(const int32_t *frag_start, int64_t n_frag,
                                        const int32_t *tile_p0, const int32_t *tile_len, int64_t n_tiles,
                                        int32_t window_size, int32_t max_len, int32_t cov_max_len,
-                                       int32_t max_frag_len, int64_t *scratch, ftk_stream_t stream_) {
+                                       int32_t max_frag_len, int64_t *scratch,
+                                       uint64_t *zero_counts, int64_t n_counts, uint64_t *zero_hist, int64_t n_hist,
+                                       ftk_stream_t stream_) {
     if (n_tiles == 0) return FTK_OK;
     int rc = wps_check_args(frag_start, frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size, max_len, scratch);
     if (rc != FTK_OK) return rc;
-    if (max_frag_len < 0) return FTK_E_INVALID;
+    if (max_frag_len < 0 || n_counts < 0 || n_hist < 0) return FTK_E_INVALID;
+    if ((n_counts > 0 && !zero_counts) || (n_hist > 0 && !zero_hist)) return FTK_E_INVALID;
     return launch_tile_ranges(frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size,
                               fused_left_reach(window_size, max_len, cov_max_len, max_frag_len), scratch,
-                              static_cast<cudaStream_t>(stream_));
+                              static_cast<cudaStream_t>(stream_),
+                              reinterpret_cast<unsigned long long *>(zero_counts), n_counts,
+                              reinterpret_cast<unsigned long long *>(zero_hist), n_hist);
 }
 
 extern "C" int ftk_wps_cov_tiles(const int32_t *frag_start, const int32_t *frag_stop,
@@ -1089,7 +1104,7 @@ extern "C" int ftk_wps_cov_tiles(const int32_t *frag_start, const int32_t *frag_
     a.C.n_bins = n_bins;
     if (!ranges_ready) {
         rc = ftk_wps_cov_tile_ranges(frag_start, n_frag, tile_p0, tile_len, n_tiles, window_size, max_len,
-                                     cov_max_len, max_frag_len, scratch, stream_);
+                                     cov_max_len, max_frag_len, scratch, nullptr, 0, nullptr, 0, stream_);
         if (rc != FTK_OK) return rc;
     }
     a.frag_start = frag_start; a.frag_stop = frag_stop; a.frag_mapq = frag_mapq; a.n_frag = n_frag;

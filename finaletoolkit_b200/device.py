@@ -221,14 +221,21 @@ class WpsPlan:
 
     _KIND = {"int32": 0, "int16": 1, "int8": 2}
 
-    def ranges_fused(self, frags: ContigFragments, window_size=120, cov_max_length=None):
-        """Only the fragment-range prepass of ``run_fused`` (lets a caller time the main kernel alone)."""
+    def ranges_fused(self, frags: ContigFragments, window_size=120, cov_max_length=None, zero_counts=None,
+                     zero_hist=None):
+        """Only the fragment-range prepass of ``run_fused`` (lets a caller time the main kernel alone).
+        ``zero_counts`` / ``zero_hist``: int64 accumulators the prepass clears on the way (no extra launch)."""
         if self.n_tiles:
-            check(lib().ftk_wps_cov_tile_ranges(frags.start.data_ptr(), frags.n, self.tile_p0.data_ptr(),
-                                                self.tile_len.data_ptr(), self.n_tiles, int(window_size),
-                                                self.max_length, none_to_ftk(cov_max_length), frags.max_len,
-                                                self.scratch.data_ptr(), _stream_ptr(self.device)),
-                  "ftk_wps_cov_tile_ranges")
+            check(lib().ftk_wps_cov_tile_ranges(
+                frags.start.data_ptr(), frags.n, self.tile_p0.data_ptr(), self.tile_len.data_ptr(), self.n_tiles,
+                int(window_size), self.max_length, none_to_ftk(cov_max_length), frags.max_len, self.scratch.data_ptr(),
+                0 if zero_counts is None else zero_counts.data_ptr(), 0 if zero_counts is None else zero_counts.numel(),
+                0 if zero_hist is None else zero_hist.data_ptr(), 0 if zero_hist is None else zero_hist.numel(),
+                _stream_ptr(self.device)), "ftk_wps_cov_tile_ranges")
+        else:
+            for z in (zero_counts, zero_hist):
+                if z is not None:
+                    z.zero_()
 
     def run_fused(self, frags: ContigFragments, window_size=120, min_length=120, max_length=180,
                   quality_threshold=30, cov_min_length=None, cov_max_length=None, cov_quality_threshold=30,

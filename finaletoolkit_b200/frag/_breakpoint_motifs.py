@@ -15,7 +15,7 @@ import numpy as np
 
 from ..io.fragments import as_table
 from ..utils import gen_kmers
-from ._common import group_by_contig, resolve_length_aliases
+from ._common import dist_context, group_by_contig, is_writer, resolve_length_aliases
 from ._end_motifs import _ref, _strand_mode
 from ._motif_common import _BASES, _MotifFreqs, _MotifsIntervals, genome_windows, parse_intervals_arg, write_motif_freqs
 
@@ -62,17 +62,25 @@ def breakpoint_motifs(input_file, refseq_file, k=6, min_length=50, max_length=No
     mode = _strand_mode(both_strands, negative_strand)
     table = as_table(input_file, refseq_file)
     ref = _ref(refseq_file)
-    total = None
-    for chrom, chrom_length in ref.chroms.items():
-        if table.n_fragments(chrom) == 0:
-            continue
-        w = genome_windows(chrom_length)
-        total = end_motif_hist(table.device(chrom), ref.device_contig(chrom), [a for a, _ in w], [b for _, b in w],
-                               k=k, strand_mode=mode, quality_threshold=quality_threshold, pooled=True, counts=total,
-                               breakpoint=True)
     ccounts = np.zeros((4 ** k,), np.float64)
-    if total is not None:
-        ccounts = ccounts + total[0].cpu().numpy().astype(np.float64)
+    ctx = dist_context()
+    if ctx is not None:   # contigs LPT-sharded over the ranks, one all_reduce(SUM) of the 4^k counts
+        from ..distributed import genome_end_motif_counts
+        ccounts = ccounts + genome_end_motif_counts(table, ref, k=k, strand_mode=mode, quality_threshold=quality_threshold,
+                                                    ctx=ctx, breakpoint=True).astype(np.float64)
+        if not is_writer(ctx):
+            output_file = None
+    else:
+        total = None
+        for chrom, chrom_length in ref.chroms.items():
+            if table.n_fragments(chrom) == 0:
+                continue
+            w = genome_windows(chrom_length)
+            total = end_motif_hist(table.device(chrom), ref.device_contig(chrom), [a for a, _ in w],
+                                   [b for _, b in w], k=k, strand_mode=mode, quality_threshold=quality_threshold,
+                                   pooled=True, counts=total, breakpoint=True)
+        if total is not None:
+            ccounts = ccounts + total[0].cpu().numpy().astype(np.float64)
     with np.errstate(invalid="ignore", divide="ignore"):
         frequencies = ccounts / np.sum(ccounts)
     results = BreakpointMotifFreqs(zip(gen_kmers(k, _BASES), frequencies), k, quality_threshold)

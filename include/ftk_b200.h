@@ -175,10 +175,13 @@ int ftk_wps_tiles_i8(const int32_t *frag_start_dev, const int32_t *frag_stop_dev
  * midpoint can fall into the tile); computed here unless ranges_ready != 0.
  * Every interval is an independent stream (overlapping intervals each count their own fragments,
  * and the pooled histogram gains one entry per (interval, fragment) pair like the reference's loop). */
+/* zero_counts_dev / zero_hist_dev (may be NULL with a zero length): accumulators this prepass also
+ * clears (n_counts / n_hist uint64 entries), so that a step is two launches. */
 int ftk_wps_cov_tile_ranges(const int32_t *frag_start_dev, int64_t n_frag,
                             const int32_t *tile_p0_dev, const int32_t *tile_len_dev, int64_t n_tiles,
                             int32_t window_size, int32_t max_len, int32_t cov_max_len, int32_t max_frag_len,
-                            int64_t *scratch_dev, ftk_stream_t stream);
+                            int64_t *scratch_dev, uint64_t *zero_counts_dev, int64_t n_counts,
+                            uint64_t *zero_hist_dev, int64_t n_hist, ftk_stream_t stream);
 
 int ftk_wps_cov_tiles(const int32_t *frag_start_dev, const int32_t *frag_stop_dev,
                       const uint8_t *frag_mapq_dev, int64_t n_frag, int32_t max_frag_len,
