@@ -212,3 +212,30 @@ def test_agg_signal_linearity_and_numpy():
     exp = core[strand == 1].sum(0) + core[strand == -1][:, ::-1].sum(0)
     assert np.array_equal(got, exp)
     assert np.array_equal(D.agg_signal(rows[:1], [-1], lo, isz).cpu().numpy(), core[0][::-1])
+
+
+def test_fused_pass_2000_intervals_vs_oracle(big):
+    """>= 2000 random intervals plus the edge intervals of a chromosome-scale shard, the fused
+    pass (WPS + coverage + length histogram) against the brute-force oracle; totals against numpy."""
+    import os
+    import torch
+    from finaletoolkit_b200 import device as D
+    fr, ofr, st, sp, mq = big["fr"], big["ofr"], big["st"], big["sp"], big["mq"]
+    edges = np.arange(0, CLEN + 5000, 5000).clip(max=CLEN)
+    plan = D.WpsPlan(edges[:-1], edges[1:], CLEN, 180, big["dev"])
+    wps, cov, hist = plan.run_fused(fr, 120, 120, 180, 30, None, None, 30, n_bins=fr.max_len + 1)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(11)
+    pick = np.unique(np.concatenate([[0, 1, plan.n_intervals - 2, plan.n_intervals - 1],
+                                     rng.choice(plan.n_intervals, 2100, replace=False)]))
+    assert len(pick) >= 2000
+    s_, e_ = edges[:-1][pick], edges[1:][pick]
+    exp, off = O.wps_intervals(ofr, s_, e_, CLEN, 120, 120, 180, 30, threads=os.cpu_count() or 1)
+    sel = torch.from_numpy(np.concatenate([np.arange(plan.offsets[i], plan.offsets[i + 1]) for i in pick])).to(big["dev"])
+    assert np.array_equal(wps[sel].cpu().numpy().astype(np.int64), exp)
+    exp_cov = O.interval_coverage(ofr, s_, e_, None, None, "midpoint", 30, threads=os.cpu_count() or 1)
+    assert np.array_equal(cov.cpu().numpy()[pick], exp_cov)
+    L = (sp - st).astype(np.int64); mid = st.astype(np.int64) + L // 2
+    ok = (mq >= 30) & (mid < CLEN)
+    assert np.array_equal(hist.cpu().numpy(), np.bincount(L[ok], minlength=fr.max_len + 1))
+    assert int(cov.sum()) == int(ok.sum())
