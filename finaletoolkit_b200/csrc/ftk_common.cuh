@@ -56,26 +56,6 @@ __device__ __forceinline__ int64_t lower_bound(const int32_t *__restrict__ a, in
     return lo;
 }
 
-// The same lower bound computed by a whole warp: every round the 32 lanes probe 32 evenly spaced
-// elements of the remaining range and a ballot keeps 1/32 of it - log32(n) dependent loads (6 for
-// 80 M fragments) instead of log2(n) (27).  All lanes return the result.
-__device__ __forceinline__ int64_t warp_lower_bound(const int32_t *__restrict__ a, int64_t n, int64_t key) {
-    const int lane = threadIdx.x & 31;
-    int64_t lo = 0, hi = n;                        // the answer lies in [lo, hi]
-    while (hi - lo > 32) {
-        const int64_t step = (hi - lo + 31) >> 5;
-        const int64_t idx = lo + (int64_t)(lane + 1) * step - 1;
-        const bool below = (idx < hi) && ((int64_t)__ldg(a + idx) < key);
-        const int c = __popc(__ballot_sync(0xffffffffu, below));   // sorted: the first c probes are below the key
-        const int64_t new_hi = lo + (int64_t)(c + 1) * step - 1;   // probe c is the first one not below
-        if (c > 0) lo = lo + (int64_t)c * step;
-        if (c < 32 && new_hi < hi) hi = new_hi;
-    }
-    const int64_t idx = lo + lane;
-    const bool below = (idx < hi) && ((int64_t)__ldg(a + idx) < key);
-    return lo + __popc(__ballot_sync(0xffffffffu, below));
-}
-
 // The reference's fragment predicate (utils/_frag_generator.py:117-123,
 // io/alignment.py:291): mapq >= q, min <= L <= max (FTK_NONE = unbounded).
 __device__ __forceinline__ bool frag_len_ok(int len, int min_len, int max_len) {

@@ -28,19 +28,20 @@ static_assert(kWpsIters * kWpsThreads * 4 == kWpsCap, "tile must split evenly");
 static_assert(FTK_WPS_TILE < kWpsCap, "one guard slot for odd windows");
 
 // Per-tile fragment index range [lo, hi): a superset of the fragments with any
-// event inside the tile.  One WARP per bound (32-ary search: six dependent loads for 80 M
-// fragments); the prepass also zeroes the accumulators of the fused pass, so a step is two launches.
-__global__ void __launch_bounds__(256)
+// event inside the tile.  One thread per bound; the upper levels of the search tree stay in L2, so
+// this costs ~30 us per chr1-scale launch.  (A warp-cooperative 32-ary search - 6 dependent rounds
+// instead of 27 - was measured in round 2 and lost, 64 us: every round touches 32 sectors per warp.)
+// The prepass also zeroes the accumulators of the fused pass, so a step is two launches.
+__global__ void __launch_bounds__(128)
 wps_tile_ranges_kernel(const int32_t *__restrict__ frag_start, int64_t n_frag,
                        const int32_t *__restrict__ tile_p0, const int32_t *__restrict__ tile_len,
                        int64_t n_tiles, int left_reach, int b, int64_t *__restrict__ ranges,
                        unsigned long long *__restrict__ zero_a, int64_t n_zero_a,
                        unsigned long long *__restrict__ zero_b, int64_t n_zero_b) {
-    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = gtid; i < n_zero_a; i += gthreads) zero_a[i] = 0ull;
-    for (int64_t i = gtid; i < n_zero_b; i += gthreads) zero_b[i] = 0ull;
-    const int64_t t = gtid >> 5;
+    for (int64_t i = t; i < n_zero_a; i += gthreads) zero_a[i] = 0ull;
+    for (int64_t i = t; i < n_zero_b; i += gthreads) zero_b[i] = 0ull;
     if (t >= 2 * n_tiles) return;
     const int64_t tile = t >> 1;
     const int64_t p0 = tile_p0[tile];
@@ -53,8 +54,7 @@ wps_tile_ranges_kernel(const int32_t *__restrict__ frag_start, int64_t n_frag,
         // first event sits at fs-b; it must be < p0+len
         key = p0 + (int64_t)tile_len[tile] + (int64_t)b;
     }
-    const int64_t r = warp_lower_bound(frag_start, n_frag, key);
-    if ((threadIdx.x & 31) == 0) ranges[t] = r;
+    ranges[t] = lower_bound(frag_start, n_frag, key);
 }
 
 // ---------------------------------------------------------------------------
@@ -857,8 +857,8 @@ static int launch_tile_ranges(const int32_t *frag_start, int64_t n_frag, const i
     const int a = odd ? (window_size - 1) / 2 : window_size / 2;
     const int b = odd ? a : a - 1;
     if (left_reach > INT32_MAX / 2) left_reach = INT32_MAX / 2;
-    const int64_t n = 2 * n_tiles * 32;          // one warp per bound
-    const int threads = 256;
+    const int64_t n = 2 * n_tiles;
+    const int threads = 128;
     wps_tile_ranges_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(
         frag_start, n_frag, tile_p0, tile_len, n_tiles, (int)left_reach, b, scratch, zero_a, n_zero_a, zero_b,
         n_zero_b);

@@ -239,12 +239,13 @@ class WpsPlan:
 
     def run_fused(self, frags: ContigFragments, window_size=120, min_length=120, max_length=180,
                   quality_threshold=30, cov_min_length=None, cov_max_length=None, cov_quality_threshold=30,
-                  n_bins=0, out=None, counts=None, hist=None, overflow=None, ranges_ready=False):
+                  n_bins=0, out=None, counts=None, hist=None, overflow=None, ranges_ready=False, zero_counts=False):
         """ONE pass over the fragments: WPS of every interval + per-interval midpoint coverage
         (``counts`` int64[n_intervals]) + the pooled length histogram of the counted fragments
         (``hist`` int64[n_bins]).  ``counts``/``hist`` are ACCUMULATED into (pass zeroed tensors to
-        reuse buffers); ``out`` may be int32 / int16 / int8 (the narrow types need ``overflow``,
-        an int32[1] flag the caller zeroes).  Returns ``(wps, counts, hist)`` device tensors."""
+        reuse buffers; ``zero_counts=True`` lets the range prepass clear ``counts`` first); ``out`` may be
+        int32 / int16 / int8 (the narrow types need ``overflow``, an int32[1] flag the caller zeroes).
+        Returns ``(wps, counts, hist)`` device tensors."""
         t = torch()
         if int(max_length) != self.max_length:
             raise ValueError("plan was built for a different max_length")
@@ -259,6 +260,9 @@ class WpsPlan:
             counts = t.zeros(max(self.n_intervals, 1), dtype=t.int64, device=self.device)
         if hist is None and n_bins:
             hist = t.zeros(int(n_bins), dtype=t.int64, device=self.device)
+        if zero_counts and not ranges_ready:   # the range prepass clears ``counts`` on the way: no memset launch
+            self.ranges_fused(frags, window_size, cov_max_length, zero_counts=counts)
+            ranges_ready = True
         if self.n_tiles == 0:
             return out, counts[: self.n_intervals], hist
         fs, fe, mq = frags.ptrs()

@@ -197,13 +197,9 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
         n_bins = int(m.item()) + 1
     packed = t.zeros(1 + n_bins, dtype=t.int64, device=dev)      # [coverage total, histogram...]
     results = {}
-    # contigs alternate between two streams: a contig's persistent kernel drains SM by SM, the next
-    # contig's CTAs move in behind it (the per-contig outputs are independent; the shared histogram is
-    # only ever touched by atomics)
-    cur = t.cuda.current_stream(dev)
-    lanes = [t.cuda.Stream(dev), t.cuda.Stream(dev)] if len(mine) > 1 else [cur]
-    for s_ in lanes:
-        s_.wait_stream(cur)
+    # (Alternating the contigs between two streams so that a contig's kernel tail overlaps the next
+    # contig's head was measured and lost - 14.4 ms against 6.5 ms per genome pass: outputs allocated on
+    # side streams defeat the caching allocator's reuse.  One stream it is.)
     deferred = []
     for n_c, c in enumerate(mine):
         starts, stops = (np.asarray(a, dtype=np.int64) for a in sites[c])
@@ -213,41 +209,33 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
             if plans is not None:
                 plans[c] = plan
         frags = table.device(c, dev)
-        with t.cuda.stream(lanes[n_c % len(lanes)]):
-            if fused:
-                cov = t.zeros(max(plan.n_intervals, 1), dtype=t.int64, device=dev)
-                wps, cov, _ = plan.run_fused(frags, window_size, min_length, max_length, quality_threshold,
-                                             None, None, quality_threshold, n_bins=n_bins, counts=cov,
-                                             hist=packed[1:] if n_bins else None)
-            else:
-                wps, cov = plan.run(frags, window_size, min_length, max_length, quality_threshold), None
-            res = ContigWps(c, starts, stops, plan.offsets, wps, cov)
-            if adjust is not None:
-                # every interval is a segment of the int32 WPS buffer as it lies in HBM (no gather, no float
-                # copy); intervals shorter than the filters need produce no output, like the reference's driver
-                aplan = plans.get((c, "adjust")) if plans is not None else None
-                if aplan is None:
-                    aplan = AdjustPlan(np.diff(plan.offsets), int(adjust.get("median_window_size", 1000)),
-                                       adjust.get("savgol", True), adjust.get("savgol_window_size", 21),
-                                       adjust.get("savgol_poly_deg", 2), dev, skip_short=True)
-                    if plans is not None:
-                        plans[(c, "adjust")] = aplan
-                res.adj_offsets = aplan.out_off
-                res.adj_segments = np.flatnonzero(aplan.n_out > 0)
-                if aplan.n_total:
-                    res.adjusted, _, flag = adjust_segments(wps, None, plan=aplan, defer_check=True, **adjust)
-                    if flag is not None:
-                        deferred.append((res, aplan, flag.any()))
-                    if not keep_adjusted:
-                        res.adjusted = None
+        if fused:
+            cov = t.empty(max(plan.n_intervals, 1), dtype=t.int64, device=dev)   # cleared by the range prepass
+            wps, cov, _ = plan.run_fused(frags, window_size, min_length, max_length, quality_threshold,
+                                         None, None, quality_threshold, n_bins=n_bins, counts=cov,
+                                         hist=packed[1:] if n_bins else None, zero_counts=True)
+        else:
+            wps, cov = plan.run(frags, window_size, min_length, max_length, quality_threshold), None
+        res = ContigWps(c, starts, stops, plan.offsets, wps, cov)
+        if adjust is not None:
+            # every interval is a segment of the int32 WPS buffer as it lies in HBM (no gather, no float
+            # copy); intervals shorter than the filters need produce no output, like the reference's driver
+            aplan = plans.get((c, "adjust")) if plans is not None else None
+            if aplan is None:
+                aplan = AdjustPlan(np.diff(plan.offsets), int(adjust.get("median_window_size", 1000)),
+                                   adjust.get("savgol", True), adjust.get("savgol_window_size", 21),
+                                   adjust.get("savgol_poly_deg", 2), dev, skip_short=True)
+                if plans is not None:
+                    plans[(c, "adjust")] = aplan
+            res.adj_offsets = aplan.out_off
+            res.adj_segments = np.flatnonzero(aplan.n_out > 0)
+            if aplan.n_total:
+                res.adjusted, _, flag = adjust_segments(wps, None, plan=aplan, defer_check=True, **adjust)
+                if flag is not None:
+                    deferred.append((res, aplan, flag.any()))
+                if not keep_adjusted:
+                    res.adjusted = None
         results[c] = res
-    for s_ in lanes:
-        cur.wait_stream(s_)
-    if len(lanes) > 1:   # the outputs were allocated on a side stream and are consumed on the caller's
-        for r in results.values():
-            for x in (r.wps, r.cov, r.adjusted):
-                if x is not None:
-                    x.record_stream(cur)
     if deferred and bool(t.stack([f for _, _, f in deferred]).any().item()):
         # a tile the rank kernel could not take (cannot happen for integer WPS of ordinary depth):
         # redo those contigs on the general path
