@@ -410,10 +410,12 @@ def genome_block(args, dev, rank, world, peak):
     state = {}
 
     def pass_a():   # WPS + per-interval coverage + genome-wide length histogram (ONE packed all_reduce)
+        state["a"] = None       # drop the previous pass's outputs first: the allocator reuses their blocks
         state["a"] = multi_wps_genome(table, sizes, sites, IVL, WINDOW, MIN_LEN, MAX_LEN, MAPQ, coverage=True,
-                                      length_hist=True, ctx=ctx, device=dev, contigs=mine, plans=plans)
+                                      length_hist=True, ctx=ctx, device=dev, contigs=mine, plans=plans, n_bins=601)
 
     def pass_b():   # WPS -> adjust_wps, device resident (no bigWig round trip), no collective
+        state["b"] = None
         state["b"] = multi_wps_genome(table, sizes, sites, IVL, WINDOW, MIN_LEN, MAX_LEN, MAPQ, adjust=adjust_kw,
                                       ctx=ctx, device=dev, contigs=mine, plans=plans, keep_adjusted=False)
 
@@ -607,12 +609,20 @@ def run_ours(args):
         if ev is not None:
             ev[2].record()
         if world > 1:
-            # the one real exchange of the path: the job-wide length histogram (4.8 KB) over NCCL
+            # the one real exchange of the path: the job-wide length histogram (4.8 KB) over NCCL, issued
+            # asynchronously so that its ~30 us of latency overlap the next step's kernels; the next
+            # step waits for it before it reuses job_hist, the timed region ends with a wait
+            if pending[0] is not None:
+                pending[0].wait()
             job_hist.copy_(hist_out)
-            dist.all_reduce(job_hist, op=dist.ReduceOp.SUM)
+            pending[0] = dist.all_reduce(job_hist, op=dist.ReduceOp.SUM, async_op=True)
+
+    pending = [None]
 
     def barrier():
         if world > 1:
+            if pending[0] is not None:
+                pending[0].wait(); pending[0] = None
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -631,6 +641,8 @@ def run_ours(args):
     e0.record()
     for k in range(K):
         step(kev[k])
+    if pending[0] is not None:       # the last step's all_reduce belongs to the timed region
+        pending[0].wait(); pending[0] = None
     e1.record()
     torch.cuda.current_stream().synchronize()
     clocks = sampler.finish()

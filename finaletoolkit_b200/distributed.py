@@ -159,7 +159,7 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
                      min_length=120, max_length=180, quality_threshold=30, coverage=False, length_hist=False,
                      adjust: dict | None = None, ctx: DistContext | None = None, device=None,
                      contigs: list | None = None, reduce: bool = True, plans: dict | None = None,
-                     keep_adjusted: bool = True):
+                     keep_adjusted: bool = True, n_bins: int | None = None):
     """Genome-wide L-WPS over the ranks of one box (reference drivers frag/_multi_wps.py:152-198 +,
     with ``adjust``, frag/_adjust_wps.py:229-291) - contigs LPT-sharded, every rank sweeps the contigs
     it owns, results stay on the owning rank's GPU, no data-path collective.
@@ -172,7 +172,9 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
     ``median_window_size`` positions is adjusted straight from the int32 WPS in HBM - no bigWig
     round trip, no float32 copy.
 
-    ``plans``: {contig: WpsPlan} to reuse across calls (built and added when missing);
+    ``n_bins``: histogram width when the caller knows it (longest fragment of the job + 1) - saves the
+    MAX all-reduce and its host synchronisation; ``plans``: {contig: WpsPlan} to reuse across calls
+    (built and added when missing);
     ``contigs``: override the LPT assignment; ``reduce=False`` skips the collectives (single-rank
     checks inside a multi-rank job); ``keep_adjusted=False`` drops each contig's adjusted series once
     computed (timing runs).
@@ -188,13 +190,15 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
         sites = tile_genome(chrom_sizes, interval_size)
     mine = contigs if contigs is not None else [c for c in owned_contigs(table, ctx) if c in sites]
     fused = bool(coverage or length_hist)
-    n_bins = 0
-    if length_hist:   # one histogram width for the whole job: MAX over the ranks' own contigs
+    if not length_hist:
+        n_bins = 0
+    elif n_bins is None:   # one histogram width for the whole job: MAX over the ranks' own contigs
         m = t.tensor([max([table.device(c, dev).max_len for c in mine if table.n_fragments(c)] + [0])],
                      dtype=t.int64, device=dev)
         if reduce:
             ctx.all_reduce_max(m)
         n_bins = int(m.item()) + 1
+    n_bins = int(n_bins)
     packed = t.zeros(1 + n_bins, dtype=t.int64, device=dev)      # [coverage total, histogram...]
     results = {}
     # (Alternating the contigs between two streams so that a contig's kernel tail overlaps the next
