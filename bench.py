@@ -370,7 +370,7 @@ def genome_block(args, dev, rank, world, peak):
     my_pos = sum(dict(sizes)[c] for c in mine)
     tot_pos = sum(n for _, n in sizes)
     tot_frag = sum(table.counts.values())
-    plans = {c: D.WpsPlan(sites[c][0], sites[c][1], dict(sizes)[c], MAX_LEN, dev) for c in mine}
+    plans = {}      # multi_wps_genome caches the rank's GenomeShard (merged tile table, buffers) in here
     adjust_kw = dict(median_window_size=1000, savgol=True, savgol_window_size=21, savgol_poly_deg=2)
 
     def barrier():
@@ -392,16 +392,23 @@ def genome_block(args, dev, rank, world, peak):
         dist.all_gather(out, t)
         return [float(x.item()) for x in out]
 
-    def timed(fn, reps):
+    clock_log = {}
+
+    def timed(fn, reps, name=None):
         for _ in range(2):
             fn()
         barrier()
+        sampler = ClockSampler(dev.index if dev.index is not None else 0, period=0.001) if name else None
+        if sampler:
+            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
             fn()
         e1.record()
         torch.cuda.current_stream().synchronize()
+        if sampler:
+            clock_log[name] = sampler.finish()
         ms = e0.elapsed_time(e1) / reps
         barrier()
         return ms
@@ -419,11 +426,11 @@ def genome_block(args, dev, rank, world, peak):
         state["b"] = multi_wps_genome(table, sizes, sites, IVL, WINDOW, MIN_LEN, MAX_LEN, MAPQ, adjust=adjust_kw,
                                       ctx=ctx, device=dev, contigs=mine, plans=plans, keep_adjusted=False)
 
-    ms_a_local = timed(pass_a, reps)
+    ms_a_local = timed(pass_a, reps, "a")
     ms_a = max_over_ranks(ms_a_local)
     ranks_a = gather_ranks(ms_a_local)
     state.pop("b", None)
-    ms_b_local = timed(pass_b, max(2, reps // 2))
+    ms_b_local = timed(pass_b, max(2, reps // 2), "b")
     ms_b = max_over_ranks(ms_b_local)
     ranks_b = gather_ranks(ms_b_local)
 
@@ -515,7 +522,10 @@ def genome_block(args, dev, rank, world, peak):
     checks["ok"] = checks["ok"] and checks["config4_bins_total"] == checks["config4_lengths_total"]
 
     bytes_a = 9 * tot_frag + 4 * tot_pos
-    n_adj_out = sum(int(np.maximum(np.diff(p.offsets) - 1000, 0).sum()) for k, p in plans.items() if not isinstance(k, tuple))
+    n_adj_out = 0
+    for c in mine:      # outputs of adjust_wps: n - 1000 per interval that is long enough for both filters
+        no = np.maximum(sites[c][1] - sites[c][0], 0) - 1000
+        n_adj_out += int(no[no >= 21].sum())
     adj_out_t = torch.tensor([n_adj_out], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(adj_out_t)
@@ -528,12 +538,16 @@ def genome_block(args, dev, rank, world, peak):
                          "algorithmic_bytes": bytes_a, "achieved_gbs_per_gpu": bytes_a / world / (ms_a * 1e-3) / 1e9,
                          "frac_of_hbm_peak_per_gpu": bytes_a / world / (ms_a * 1e-3) / 1e9 / peak,
                          "ms_per_rank": ranks_a, "imbalance_max_over_mean": max(ranks_a) / (sum(ranks_a) / len(ranks_a)),
-                         "collective": "one all_reduce(SUM) of [coverage total, 601-bin histogram] + one MAX for the bin count"},
+                         "launches_per_pass_this_rank": "per shard group: 1 range prepass + 1 fused persistent kernel; + 1 sum + 1 all_reduce",
+                         "sm_mhz_per_rank": gather_ranks((clock_log.get("a") or {}).get("sm_mhz") or 0.0),
+                         "collective": "one all_reduce(SUM) of [coverage total, 601-bin histogram]"},
         "wps_then_adjust": {"ms": ms_b, "fragments_per_sec": tot_frag / (ms_b * 1e-3), "positions_per_sec": tot_pos / (ms_b * 1e-3),
                             "algorithmic_bytes": bytes_b, "achieved_gbs_per_gpu": bytes_b / world / (ms_b * 1e-3) / 1e9,
                             "frac_of_hbm_peak_per_gpu": bytes_b / world / (ms_b * 1e-3) / 1e9 / peak,
                             "ms_per_rank": ranks_b, "imbalance_max_over_mean": max(ranks_b) / (sum(ranks_b) / len(ranks_b)),
-                            "collective": "none", "note": "int32 WPS stays in HBM; adjust = fused rank-median + Savitzky-Golay kernel"},
+                            "collective": "none", "note": "int32 WPS stays in HBM; adjust = fused rank-median + Savitzky-Golay kernel",
+                            "sm_mhz_per_rank": gather_ranks((clock_log.get("b") or {}).get("sm_mhz") or 0.0),
+                            "clock_reasons_this_rank": (clock_log.get("b") or {}).get("reasons")},
         "coverage5mb_plus_length_bins": {"ms": ms_c4, "bins": int(offs[-1]), "fragments_per_sec": tot_frag / (ms_c4 * 1e-3),
                                          "collective": "all_reduce(SUM) of 5-Mb bin counts + SUM/MIN of the length histogram / first-seen keys"},
         "lpt": {"fragments_this_rank": my_frag, "positions_this_rank": my_pos, "contigs_this_rank": len(mine)},

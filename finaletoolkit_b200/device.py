@@ -149,43 +149,62 @@ class WpsPlan:
     """
 
     def __init__(self, ivl_start, ivl_stop, chrom_size: int, max_length: int, device=None):
-        t = torch()
-        self.device = require_cuda(device)
+        self._install(self.host_tiles(ivl_start, ivl_stop, chrom_size, max_length), max_length, device)
+
+    @staticmethod
+    def host_tiles(ivl_start, ivl_stop, chrom_size: int, max_length: int) -> dict:
+        """Plan the tiles of one contig's intervals on the host (``ftk_wps_plan_tiles``): numpy arrays
+        ``p0, len, mid_lo, mid_hi`` (int32), ``out_off`` (int64), ``ivl`` (int32, bit 31 = the
+        interval's first tile), ``offsets`` (int64[n_intervals + 1]: output offset of every interval)."""
         s = np.ascontiguousarray(ivl_start, dtype=np.int64)
         e = np.ascontiguousarray(ivl_stop, dtype=np.int64)
         ln = np.maximum(e - s, 0)
-        self.offsets = np.zeros(len(s) + 1, dtype=np.int64)
-        np.cumsum(ln, out=self.offsets[1:])
-        self.n_positions = int(self.offsets[-1])
-        self.max_length = int(max_length)
+        offsets = np.zeros(len(s) + 1, dtype=np.int64)
+        np.cumsum(ln, out=offsets[1:])
         L = lib()
         i64p, i32p = POINTER(c_int64), POINTER(c_int32)
         null32, null64 = i32p(), i64p()
-        n_tiles = L.ftk_wps_plan_tiles(_np_ptr(s, c_int64), _np_ptr(e, c_int64), _np_ptr(self.offsets, c_int64),
+        n_tiles = L.ftk_wps_plan_tiles(_np_ptr(s, c_int64), _np_ptr(e, c_int64), _np_ptr(offsets, c_int64),
                                        len(s), int(chrom_size), int(max_length), null32, null32, null32, null32, null64)
         check(n_tiles, "ftk_wps_plan_tiles")
-        self.n_tiles = int(n_tiles)
-        p0 = np.empty(self.n_tiles, np.int32)
-        tl = np.empty(self.n_tiles, np.int32)
-        mlo = np.empty(self.n_tiles, np.int32)
-        mhi = np.empty(self.n_tiles, np.int32)
-        off = np.empty(self.n_tiles, np.int64)
-        if self.n_tiles:
-            check(L.ftk_wps_plan_tiles(_np_ptr(s, c_int64), _np_ptr(e, c_int64), _np_ptr(self.offsets, c_int64),
+        n_tiles = int(n_tiles)
+        p0 = np.empty(n_tiles, np.int32)
+        tl = np.empty(n_tiles, np.int32)
+        mlo = np.empty(n_tiles, np.int32)
+        mhi = np.empty(n_tiles, np.int32)
+        off = np.empty(n_tiles, np.int64)
+        if n_tiles:
+            check(L.ftk_wps_plan_tiles(_np_ptr(s, c_int64), _np_ptr(e, c_int64), _np_ptr(offsets, c_int64),
                                        len(s), int(chrom_size), int(max_length), _np_ptr(p0, c_int32), _np_ptr(tl, c_int32),
                                        _np_ptr(mlo, c_int32), _np_ptr(mhi, c_int32), _np_ptr(off, c_int64)),
                   "ftk_wps_plan_tiles")
-        self.tile_p0 = _to_device(p0, self.device, np.int32)
-        self.tile_len = _to_device(tl, self.device, np.int32)
-        self.tile_mid_lo = _to_device(mlo, self.device, np.int32)
-        self.tile_mid_hi = _to_device(mhi, self.device, np.int32)
-        self.tile_out_off = _to_device(off, self.device, np.int64)
         # interval of each tile (empty intervals own no position, hence no tile)
-        self.n_intervals = len(s)
-        ivl = np.searchsorted(self.offsets[1:], off, side="right").astype(np.int64)
-        first = off == self.offsets[np.minimum(ivl, len(s) - 1)] if self.n_tiles else np.zeros(0, bool)
+        ivl = np.searchsorted(offsets[1:], off, side="right").astype(np.int64)
+        first = off == offsets[np.minimum(ivl, len(s) - 1)] if n_tiles else np.zeros(0, bool)
         ivl = np.where(first, ivl - (1 << 31), ivl).astype(np.int32)   # bit 31: the interval's first tile
-        self.tile_ivl = _to_device(ivl, self.device, np.int32)
+        return {"p0": p0, "len": tl, "mid_lo": mlo, "mid_hi": mhi, "out_off": off, "ivl": ivl, "offsets": offsets}
+
+    @classmethod
+    def from_tiles(cls, tiles: dict, max_length: int, device=None, n_positions: int | None = None):
+        """A plan over an already planned (possibly merged, see ``distributed.GenomeShard``) tile table."""
+        self = cls.__new__(cls)
+        self._install(tiles, max_length, device, n_positions)
+        return self
+
+    def _install(self, tiles: dict, max_length: int, device=None, n_positions: int | None = None):
+        t = torch()
+        self.device = require_cuda(device)
+        self.offsets = tiles["offsets"]
+        self.n_positions = int(self.offsets[-1]) if n_positions is None else int(n_positions)
+        self.max_length = int(max_length)
+        self.n_tiles = int(len(tiles["p0"]))
+        self.tile_p0 = _to_device(tiles["p0"], self.device, np.int32)
+        self.tile_len = _to_device(tiles["len"], self.device, np.int32)
+        self.tile_mid_lo = _to_device(tiles["mid_lo"], self.device, np.int32)
+        self.tile_mid_hi = _to_device(tiles["mid_hi"], self.device, np.int32)
+        self.tile_out_off = _to_device(tiles["out_off"], self.device, np.int64)
+        self.n_intervals = len(self.offsets) - 1
+        self.tile_ivl = _to_device(tiles["ivl"], self.device, np.int32)
         self.scratch = t.empty(2 * max(self.n_tiles, 1), dtype=t.int64, device=self.device)
 
     def ranges(self, frags: ContigFragments, window_size=120):

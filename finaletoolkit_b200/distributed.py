@@ -17,7 +17,7 @@ import numpy as np
 from .sharding import DistContext, genome_length_dict, lpt_pack
 
 __all__ = ["owned_contigs", "genome_total_coverage", "genome_length_distribution", "genome_end_motif_counts",
-           "genome_delfi_windows", "ContigWps", "multi_wps_genome", "adjust_wps_genome", "tile_genome",
+           "genome_delfi_windows", "ContigWps", "GenomeShard", "multi_wps_genome", "adjust_wps_genome", "tile_genome",
            "gather_to_writer"]
 
 
@@ -155,6 +155,152 @@ def tile_genome(chrom_sizes, interval_size: int = 5000) -> dict:
     return out
 
 
+_SHARD_SPAN = (1 << 31) - (1 << 22)     # the virtual coordinates of a group stay well inside int32
+
+
+class _ShardGroup:
+    __slots__ = ("frags", "plan", "wps", "cov", "seg_lengths", "aplans", "adjusted", "n_ivl", "ivl_base")
+
+
+class GenomeShard:
+    """The contigs ONE rank owns, laid end to end in one virtual coordinate space, so that a genome
+    pass is one range prepass + ONE persistent-kernel launch per rank instead of one pair per contig.
+
+    Contig ``c`` is shifted by ``base[c]``: its fragments (``start + base``, ``stop + base``), its tiles
+    (``p0``, the midpoint window ``[mid_lo, mid_hi)`` clamped to the contig as frag/_wps.py:156-157 asks)
+    and nothing else - the kernels are the per-contig ones, unchanged, they simply see one longer
+    start-sorted column and one longer tile table.  Neighbouring contigs are separated by a guard band
+    wider than anything a fragment can reach (window + the longest fragment + max_length, twice), so no
+    fragment of one contig lies in the staged range of, or leaves an event in, a tile of another.  A
+    group ends before the virtual coordinate would leave int32 (the 3.1 Gb genome on one rank: two
+    groups).  Outputs live in buffers the shard owns and reuses from pass to pass: one int32 WPS buffer
+    (every contig's part starts on a 16-byte boundary so the 128-bit stores stay aligned), one int64
+    coverage vector indexed by (contig, interval), one float64 buffer for the adjusted series.
+    """
+
+    def __init__(self, table, sizes: dict, sites: dict, contigs, max_length: int, window_size: int = 120,
+                 device=None):
+        from .device import ContigFragments, WpsPlan, require_cuda, torch
+        t = torch()
+        self.device = dev = require_cuda(device)
+        self.max_length, self.window_size = int(max_length), int(window_size)
+        self.contigs = list(contigs)
+        self.groups: list = []
+        self.layout: dict = {}
+        self._packed = None
+        pend = None                      # the group being filled
+
+        def close():
+            nonlocal pend
+            if pend is None:
+                return
+            g = _ShardGroup()
+            tiles = {k: (np.concatenate(v) if v else np.zeros(0, np.int64 if k in ("out_off", "offsets") else np.int32))
+                     for k, v in pend["tiles"].items()}
+            tiles["offsets"] = np.concatenate([tiles["offsets"], [pend["pos"]]]).astype(np.int64)
+            g.plan = WpsPlan.from_tiles(tiles, self.max_length, dev, n_positions=pend["pos"])
+            cols = pend["cols"]
+            if cols:
+                start = t.cat([c_[0] for c_ in cols]); stop = t.cat([c_[1] for c_ in cols])
+                mapq = None if all(c_[2] is None for c_ in cols) else t.cat(
+                    [c_[2] if c_[2] is not None else t.full((c_[0].numel(),), 255, dtype=t.uint8, device=dev) for c_ in cols])
+            else:
+                start = t.zeros(0, dtype=t.int32, device=dev); stop = start.clone(); mapq = None
+            g.frags = ContigFragments(start, stop, mapq, None, device=dev, max_len=pend["flen"])
+            g.wps = None
+            g.cov = None
+            g.seg_lengths = np.concatenate(pend["segs"]) if pend["segs"] else np.zeros(0, np.int64)
+            g.aplans, g.adjusted = {}, None
+            g.n_ivl, g.ivl_base = pend["ivl"], pend["ivl_base"]
+            self.groups.append(g)
+            pend = None
+
+        ivl_total = 0
+        for c in self.contigs:
+            starts, stops = (np.ascontiguousarray(a, dtype=np.int64) for a in sites[c])
+            clen = int(sizes[c])
+            frags = table.device(c, dev) if table.n_fragments(c) else None
+            n = frags.n if frags is not None else 0
+            flen = frags.max_len if n else 0
+            lo = min([0] + ([int(starts.min())] if len(starts) else []) + ([int(frags.start[0].item())] if n else []))
+            hi = max([clen] + ([int(stops.max())] if len(stops) else []) + ([int(frags.stop.max().item())] if n else []))
+            guard = 2 * (flen + self.max_length + self.window_size) + 4096
+            if hi - lo + 2 * guard > _SHARD_SPAN:
+                raise ValueError(f"contig {c} does not fit the int32 coordinate space of a shard group")
+            if pend is not None and pend["end"] + guard - lo + hi + guard > _SHARD_SPAN:
+                close()
+            if pend is None:
+                pend = {"end": 0, "pos": 0, "ivl": 0, "ivl_base": ivl_total, "flen": 0, "cols": [], "segs": [],
+                        "tiles": {k: [] for k in ("p0", "len", "mid_lo", "mid_hi", "out_off", "ivl", "offsets")}}
+            base = (pend["end"] + guard - lo + 63) & ~63
+            tl = WpsPlan.host_tiles(starts, stops, clen, self.max_length)
+            obase, ibase = pend["pos"], pend["ivl"]
+            first = tl["ivl"] < 0
+            idx = (tl["ivl"].astype(np.int64) & 0x7fffffff) + ibase
+            pend["tiles"]["p0"].append((tl["p0"].astype(np.int64) + base).astype(np.int32))
+            pend["tiles"]["len"].append(tl["len"])
+            pend["tiles"]["mid_lo"].append((tl["mid_lo"].astype(np.int64) + base).astype(np.int32))
+            pend["tiles"]["mid_hi"].append((tl["mid_hi"].astype(np.int64) + base).astype(np.int32))
+            pend["tiles"]["out_off"].append(tl["out_off"] + obase)
+            pend["tiles"]["ivl"].append(np.where(first, idx - (1 << 31), idx).astype(np.int32))
+            pend["tiles"]["offsets"].append(tl["offsets"][:-1] + obase)
+            npos = int(tl["offsets"][-1])
+            pad = (-npos) & 3
+            seg_lo = sum(len(a) for a in pend["segs"])
+            pend["segs"].append(np.diff(tl["offsets"]))
+            pend["segs"].append(np.array([pad], dtype=np.int64))     # alignment gap: a segment without output
+            self.layout[c] = {"group": len(self.groups), "base": int(base), "wps": (obase, obase + npos),
+                              "ivl": (ivl_total, ivl_total + len(starts)), "starts": starts, "stops": stops,
+                              "offsets": tl["offsets"], "seg": (seg_lo, seg_lo + len(starts))}
+            if n:
+                pend["cols"].append((frags.start + int(base), frags.stop + int(base), frags.mapq))
+            pend["flen"] = max(pend["flen"], flen)
+            pend["end"] = base + hi
+            pend["pos"] += npos + pad
+            pend["ivl"] += len(starts)
+            ivl_total += len(starts)
+        close()
+        self.n_intervals = ivl_total
+        self.cov = t.zeros(max(ivl_total, 1), dtype=t.int64, device=dev)
+        for g in self.groups:
+            g.wps = t.empty(max(g.plan.n_positions, 1), dtype=t.int32, device=dev)
+            g.cov = self.cov[g.ivl_base: g.ivl_base + g.n_ivl] if g.n_ivl else self.cov[:1]
+
+    def packed(self, n_bins: int):
+        """[coverage total, length histogram...]: the one buffer that is all-reduced."""
+        from .device import torch
+        t = torch()
+        if self._packed is None or self._packed.numel() != 1 + int(n_bins):
+            self._packed = t.zeros(1 + int(n_bins), dtype=t.int64, device=self.device)
+        return self._packed
+
+    def adjust_plan(self, g: _ShardGroup, adjust: dict):
+        from .device import AdjustPlan
+        key = (int(adjust.get("median_window_size", 1000)), bool(adjust.get("savgol", True)),
+               int(adjust.get("savgol_window_size", 21)), int(adjust.get("savgol_poly_deg", 2)))
+        if key not in g.aplans:
+            g.aplans[key] = AdjustPlan(g.seg_lengths, key[0], key[1], key[2], key[3], self.device, skip_short=True)
+        return g.aplans[key]
+
+    def results(self, fused: bool, adjust: dict | None, keep_adjusted: bool = True) -> dict:
+        """{contig: ContigWps} - views into the shard's buffers (valid until the shard's next pass)."""
+        out = {}
+        for c in self.contigs:
+            lay = self.layout[c]
+            g = self.groups[lay["group"]]
+            res = ContigWps(c, lay["starts"], lay["stops"], lay["offsets"], g.wps[lay["wps"][0]: lay["wps"][1]],
+                            self.cov[lay["ivl"][0]: lay["ivl"][1]] if fused else None)
+            if adjust is not None:
+                ap = self.adjust_plan(g, adjust)
+                s0, s1 = lay["seg"]
+                res.adj_offsets = ap.out_off[s0: s1 + 1] - ap.out_off[s0]
+                res.adj_segments = np.flatnonzero(ap.n_out[s0: s1] > 0)
+                if keep_adjusted and g.adjusted is not None:
+                    res.adjusted = g.adjusted[int(ap.out_off[s0]): int(ap.out_off[s1])]
+            out[c] = res
+        return out
+
+
 def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_size=5000, window_size=120,
                      min_length=120, max_length=180, quality_threshold=30, coverage=False, length_hist=False,
                      adjust: dict | None = None, ctx: DistContext | None = None, device=None,
@@ -163,6 +309,10 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
     """Genome-wide L-WPS over the ranks of one box (reference drivers frag/_multi_wps.py:152-198 +,
     with ``adjust``, frag/_adjust_wps.py:229-291) - contigs LPT-sharded, every rank sweeps the contigs
     it owns, results stay on the owning rank's GPU, no data-path collective.
+
+    The rank's contigs are laid end to end in one virtual coordinate space (``GenomeShard``): a pass is
+    ONE range prepass + ONE launch of the persistent WPS kernel per rank (two of each when a single rank
+    holds more than 2^31 bp), into buffers the shard owns.
 
     ``sites``: {contig: (starts, stops)} sorted by start (``tile_genome`` when None).  With
     ``coverage`` / ``length_hist`` the sweep is the fused pass (WPS + per-interval midpoint coverage +
@@ -173,15 +323,15 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
     round trip, no float32 copy.
 
     ``n_bins``: histogram width when the caller knows it (longest fragment of the job + 1) - saves the
-    MAX all-reduce and its host synchronisation; ``plans``: {contig: WpsPlan} to reuse across calls
-    (built and added when missing);
+    MAX all-reduce and its host synchronisation; ``plans``: a dict the shard is cached in (built on the
+    first call, reused afterwards: same table, sites, contigs and max_length) - the returned tensors
+    are then VIEWS into the shard's buffers, valid until the next call with the same ``plans``;
     ``contigs``: override the LPT assignment; ``reduce=False`` skips the collectives (single-rank
-    checks inside a multi-rank job); ``keep_adjusted=False`` drops each contig's adjusted series once
-    computed (timing runs).
+    checks inside a multi-rank job); ``keep_adjusted=False`` returns no adjusted series (timing runs).
 
     Returns ``(results {contig: ContigWps} of this rank, hist int64[n_bins] | None, total | None)``.
     """
-    from .device import AdjustPlan, WpsPlan, adjust_segments, require_cuda, torch
+    from .device import adjust_segments, require_cuda, torch
     ctx = ctx or DistContext()
     dev = require_cuda(device)
     t = torch()
@@ -190,72 +340,61 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
         sites = tile_genome(chrom_sizes, interval_size)
     mine = contigs if contigs is not None else [c for c in owned_contigs(table, ctx) if c in sites]
     fused = bool(coverage or length_hist)
+    key = ("shard", tuple(mine), int(max_length), int(window_size))
+    shard = plans.get(key) if plans is not None else None
+    if shard is None:
+        shard = GenomeShard(table, sizes, sites, mine, int(max_length), int(window_size), dev)
+        if plans is not None:
+            plans[key] = shard
     if not length_hist:
         n_bins = 0
     elif n_bins is None:   # one histogram width for the whole job: MAX over the ranks' own contigs
-        m = t.tensor([max([table.device(c, dev).max_len for c in mine if table.n_fragments(c)] + [0])],
-                     dtype=t.int64, device=dev)
+        m = t.tensor([max([g.frags.max_len for g in shard.groups if g.frags.n] + [0])], dtype=t.int64, device=dev)
         if reduce:
             ctx.all_reduce_max(m)
         n_bins = int(m.item()) + 1
     n_bins = int(n_bins)
-    packed = t.zeros(1 + n_bins, dtype=t.int64, device=dev)      # [coverage total, histogram...]
-    results = {}
-    # (Alternating the contigs between two streams so that a contig's kernel tail overlaps the next
-    # contig's head was measured and lost - 14.4 ms against 6.5 ms per genome pass: outputs allocated on
-    # side streams defeat the caching allocator's reuse.  One stream it is.)
-    deferred = []
-    for n_c, c in enumerate(mine):
-        starts, stops = (np.asarray(a, dtype=np.int64) for a in sites[c])
-        plan = plans.get(c) if plans is not None else None
-        if plan is None:
-            plan = WpsPlan(starts, stops, int(sizes[c]), int(max_length), dev)
-            if plans is not None:
-                plans[c] = plan
-        frags = table.device(c, dev)
+    packed = shard.packed(n_bins)            # [coverage total, histogram...]
+    cleared = False
+    flags = []
+    general = adjust is not None and (adjust.get("use_mean") or adjust.get("subtract_edges"))
+    for g in shard.groups:
         if fused:
-            cov = t.empty(max(plan.n_intervals, 1), dtype=t.int64, device=dev)   # cleared by the range prepass
-            wps, cov, _ = plan.run_fused(frags, window_size, min_length, max_length, quality_threshold,
-                                         None, None, quality_threshold, n_bins=n_bins, counts=cov,
-                                         hist=packed[1:] if n_bins else None, zero_counts=True)
+            # the range prepass clears the group's coverage counts and (first group) the packed buffer
+            g.plan.ranges_fused(g.frags, window_size, None, zero_counts=g.cov, zero_hist=None if cleared else packed)
+            cleared = True
+            g.plan.run_fused(g.frags, window_size, min_length, max_length, quality_threshold, None, None,
+                             quality_threshold, n_bins=n_bins, out=g.wps, counts=g.cov,
+                             hist=packed[1:] if n_bins else None, ranges_ready=True)
         else:
-            wps, cov = plan.run(frags, window_size, min_length, max_length, quality_threshold), None
-        res = ContigWps(c, starts, stops, plan.offsets, wps, cov)
+            g.plan.run(g.frags, window_size, min_length, max_length, quality_threshold, out=g.wps)
         if adjust is not None:
             # every interval is a segment of the int32 WPS buffer as it lies in HBM (no gather, no float
             # copy); intervals shorter than the filters need produce no output, like the reference's driver
-            aplan = plans.get((c, "adjust")) if plans is not None else None
-            if aplan is None:
-                aplan = AdjustPlan(np.diff(plan.offsets), int(adjust.get("median_window_size", 1000)),
-                                   adjust.get("savgol", True), adjust.get("savgol_window_size", 21),
-                                   adjust.get("savgol_poly_deg", 2), dev, skip_short=True)
-                if plans is not None:
-                    plans[(c, "adjust")] = aplan
-            res.adj_offsets = aplan.out_off
-            res.adj_segments = np.flatnonzero(aplan.n_out > 0)
-            if aplan.n_total:
-                res.adjusted, _, flag = adjust_segments(wps, None, plan=aplan, defer_check=True, **adjust)
-                if flag is not None:
-                    deferred.append((res, aplan, flag.any()))
-                if not keep_adjusted:
-                    res.adjusted = None
-        results[c] = res
-    if deferred and bool(t.stack([f for _, _, f in deferred]).any().item()):
+            ap = shard.adjust_plan(g, adjust)
+            if ap.n_total:
+                if g.adjusted is None or g.adjusted.numel() < ap.n_total:
+                    g.adjusted = t.empty(ap.n_total, dtype=t.float64, device=dev)
+                if ap.rank is not None and not general:
+                    _, flag = ap.run_rank(g.wps, 0, g.adjusted)
+                    flags.append((g, ap, flag.any()))
+                else:
+                    g.adjusted[: ap.n_total] = adjust_segments(g.wps, None, plan=ap, **adjust)[0]
+    if flags and bool(t.stack([f for _, _, f in flags]).any().item()):
         # a tile the rank kernel could not take (cannot happen for integer WPS of ordinary depth):
-        # redo those contigs on the general path
-        for res, aplan, f in deferred:
+        # redo those groups on the general path
+        for g, ap, f in flags:
             if bool(f.item()):
-                res.adjusted, _ = adjust_segments(res.wps, None, plan=aplan, impl="hist", **adjust)
-                if not keep_adjusted:
-                    res.adjusted = None
+                g.adjusted[: ap.n_total] = adjust_segments(g.wps, None, plan=ap, impl="hist", **adjust)[0]
     if fused:
-        covs = [r.cov for r in results.values() if r.cov is not None]
-        if covs:
-            packed[0] = t.stack([c_.sum() for c_ in covs]).sum()
+        if not cleared:
+            packed.zero_()
+        if shard.n_intervals:
+            t.sum(shard.cov[: shard.n_intervals], dim=0, keepdim=True, out=packed[:1])
         if reduce:
             ctx.all_reduce_sum(packed)
     hist = packed[1:] if n_bins else None
-    return results, hist, (int(packed[0].item()) if fused else None)
+    return shard.results(fused, adjust, keep_adjusted), hist, (int(packed[0].item()) if fused else None)
 
 
 def adjust_wps_genome(results: dict, **adjust):
