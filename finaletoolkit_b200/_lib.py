@@ -68,7 +68,7 @@ SYMBOLS = {
                                            _P, _P, _P]),
     "ftk_savgol_f64": (c_int, [_P, _P, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P]),
     "ftk_adjust_rank_f64": (c_int, [_P, c_int32, _P, _P, _P, c_int32, _P, _P, _P, c_int64, c_int32, c_int32,
-                                    _P, _P, _P, c_int32, c_int32, _P, _P, _P]),
+                                    _P, _P, _P, c_int64, c_int64, c_int64, c_int32, c_int32, _P, _P, _P]),
     "ftk_cleavage_tiles_f64": (c_int, [_P, _P, _P, _P, c_int64, c_int32, _P, _P, _P, _P, _P, c_int64,
                                        c_int32, c_int32, c_int32, _P, _P, _P]),
     "ftk_fragfile_open": (c_void_p, [c_char_p, c_int32, _i32p]),

@@ -52,6 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     hdrs = headers()
     extra = ["-Xptxas", "-v"] if verbose else []
+    extra += os.environ.get("FTK_NVCC_EXTRA", "").split()       # e.g. -DFTK_RANK_THREADS=256 for tuning runs
 
     def compile_one(src):
         obj = _obj_of(src)

@@ -460,6 +460,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
                    const int *__restrict__ tile_seg, const int *__restrict__ tile_t0,
                    const int *__restrict__ tile_n, int w, int sg_w, const double *__restrict__ coef,
                    const double *__restrict__ edge_first, const double *__restrict__ edge_last,
+                   long long sg_a, long long sg_b, double sg_scale,
                    int a_cap, int s_cap, double *__restrict__ out, unsigned char *__restrict__ tile_flag) {
     extern __shared__ __align__(16) unsigned char rank_smem[];
     __shared__ int s_ctl[4];            // 0: need lower band, 1: need higher band, 2: unused, 3: centre
@@ -554,6 +555,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
     const int wd_lo = min(warp * wpw, n_words), wd_hi = min(wd_lo + wpw, n_words);
 
     unsigned done_m = 0, done_u = 0;             // per-output bits: lower / upper median known
+    int n_fast = 0;                              // outputs the first pass' fast walk finished (adj already final)
     int L0 = s_ctl[3] - (kRankLevels / 2 - 1);   // row r <-> level L0 - 1 + r; rows 1..31 resolve
     int lo_band = L0, hi_band = L0;
     bool is_lowest = true, is_highest = true, pend_lo = false, pend_hi = false;
@@ -563,7 +565,8 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
             int run = 0;
             for (int wd = wd_lo; wd < wd_hi; ++wd) {
                 const int d = (int)xs[wd * 32 + lane] - (L0 - 1);     // sample <= level r  <=>  r >= d
-                const unsigned mask = (d <= 0) ? 0xffffffffu : (d > 31) ? 0u : (0xffffffffu << d);
+                // ~0 << d with d clamped to [0, 32]: one max + one clamping funnel shift
+                const unsigned mask = __funnelshift_lc(0u, 0xffffffffu, (unsigned)max(d, 0));
                 const unsigned bits = warp_transpose32(mask, lane);
                 B[lane * nwp + wd] = bits;
                 Wp[lane * nwp + wd] = (unsigned short)run;
@@ -601,7 +604,10 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
                         if (ru < 0) break;                   // next occupied level above the band: general loop
                     }
                     const int lvl = L0 - 1;
-                    *reinterpret_cast<unsigned *>(adj + slot_i) = ((unsigned)(lvl + ru) << 16) | ((unsigned)(lvl + m) & 0xffffu);
+                    if (SHIFT)
+                        *reinterpret_cast<unsigned *>(adj + slot_i) = ((unsigned)(lvl + ru) << 16) | ((unsigned)(lvl + m) & 0xffffu);
+                    else        // both medians known: store 2 * adj right away (exact integer)
+                        adj[slot_i] = (AdjT)(2 * (int)xs[j + (w >> 1)] - 2 * lvl - m - ru);
                     if (++i_first >= mine_n) break;
                     // slide to window j + 1
                     const int lv = lvl + m;
@@ -625,6 +631,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
             }
             const unsigned got = (i_first >= 32) ? 0xffffffffu : ((1u << i_first) - 1u);
             done_m = got; done_u = got;
+            n_fast = i_first;
         }
         {
             bool valid = false;                  // (m, c_lt, hm) describe window j - 1's lower median
@@ -697,17 +704,21 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
 
     // ---- (lower, upper) median -> adjusted value, in place (numpy: median of an even window = mean of the two)
     {
-        double shift = 0.0;
-        if (SHIFT) shift = seg_shift[sg];
-        for (int j = tid; j < A; j += kRankThreads) {
-            const short *slot = reinterpret_cast<const short *>(adj + sg_slot(j));
-            const int vm = slot[0], vu = slot[1];
-            const int bc = xs[j + (w >> 1)];
-            if (SHIFT) {
+        if (SHIFT) {
+            const double shift = seg_shift[sg];
+            for (int j = tid; j < A; j += kRankThreads) {
+                const short *slot = reinterpret_cast<const short *>(adj + sg_slot(j));
+                const int vm = slot[0], vu = slot[1];
+                const int bc = xs[j + (w >> 1)];
                 const double lo_s = (double)vm - shift, hi_s = (double)vu - shift;
                 adj[sg_slot(j)] = (AdjT)(((double)bc - shift) - (lo_s + hi_s) / 2.0);
-            } else {
-                adj[sg_slot(j)] = (AdjT)(2 * bc - vm - vu);          // 2 * adj, exact
+            }
+        } else {
+            for (int i = n_fast; i < mine_n; ++i) {                  // usually none
+                const int j = j0 + i;
+                const short *slot = reinterpret_cast<const short *>(adj + sg_slot(j));
+                const int vm = slot[0], vu = slot[1];
+                adj[sg_slot(j)] = (AdjT)(2 * (int)xs[j + (w >> 1)] - vm - vu);   // 2 * adj, exact
             }
         }
     }
@@ -720,6 +731,59 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
     };
     if (SGW < 0) {
         for (int k = tid; k < n_t; k += kRankThreads) dst[k] = val(t0 - a0 + k);
+        return;
+    }
+    if (!SHIFT && sg_scale != 0.0) {
+        // Exact sliding-moment smoothing.  For polynomial degree <= 3 the interior coefficients are
+        // c_i = (sg_a + sg_b * i^2) / den, so with x = 2 * adj (integers)
+        //     y_j = (sg_a * S0_j + sg_b * M2_j) / (2 den),  S0 = sum x, M1 = sum i x, M2 = sum i^2 x over the window,
+        // and the three moments slide in O(1): every thread owns a run of consecutive outputs, pays the
+        // sg_w-tap sum once and then two shared-memory reads + a handful of integer operations per output
+        // (the stencil above costs sg_w fp64 FMAs + sg_w / 4 + 1 loads and conversions per output).  The
+        // result is the correctly rounded exact rational times one rounded constant (<= 1 ulp off the
+        // true value; the fp64 stencil is ~1e-16 x sum |c_i x_i| off it).  Edge outputs keep the
+        // per-segment polynomial fit.  The bitmaps / samples are dead by now: their space stages the
+        // results so the global stores are coalesced.
+        double *__restrict__ ystage = reinterpret_cast<double *>(rank_smem + o_b);
+        const int Ro = ((n_t + kRankThreads - 1) / kRankThreads) | 1;      // odd run length: conflict-free 8-byte staging
+        const int k_lo = min(tid * Ro, n_t), k_hi = min(k_lo + Ro, n_t);
+        const int h = half, h1 = half + 1;
+        const int hh = h * h, h1h1 = h1 * h1;
+        int S0 = 0, M1 = 0, M2 = 0;
+        bool valid = false;
+        for (int k = k_lo; k < k_hi; ++k) {
+            const int j = t0 + k;                // segment-relative output index
+            const int c = j - a0;                // index of its adjusted value in the tile
+            if (j < h || j >= n_out - h) { valid = false; continue; }     // edge outputs: below
+            if (!valid) {
+                S0 = M1 = M2 = 0;
+                for (int i = -h; i <= h; ++i) {
+                    const int xv = adj[sg_slot(c + i)];
+                    S0 += xv; M1 += i * xv; M2 += i * i * xv;
+                }
+                valid = true;
+            } else {                              // window centre c - 1 -> c
+                const int xo = adj[sg_slot(c - h1)], xi = adj[sg_slot(c + h)];
+                M2 += S0 - 2 * M1 - h1h1 * xo + hh * xi;
+                M1 += h1 * xo + h * xi - S0;
+                S0 += xi - xo;
+            }
+            ystage[k] = (double)(sg_a * (long long)S0 + sg_b * (long long)M2) * sg_scale;
+        }
+        // the 2 * half edge outputs of the segment (polynomial fit of its first / last sg_w adjusted
+        // values), one thread each so the table loads of different outputs overlap
+        for (int e = tid; e < 2 * h; e += kRankThreads) {
+            const bool head = e < h;
+            const int j = head ? e : n_out - 2 * h + e;
+            if (j < t0 || j >= t0 + n_t) continue;
+            const double *__restrict__ tab = head ? edge_first + (size_t)e * sg_w : edge_last + (size_t)(e - h) * sg_w;
+            const int first = head ? -a0 : n_out - sg_w - a0;
+            double acc = 0.0;
+            for (int i = 0; i < sg_w; ++i) acc += tab[i] * val(first + i);
+            ystage[j - t0] = acc;
+        }
+        __syncthreads();
+        for (int k = tid; k < n_t; k += kRankThreads) dst[k] = ystage[k];
         return;
     }
     double *__restrict__ stage = reinterpret_cast<double *>(B) + warp * (128 + 8);   // per-warp 128 outputs, padded
@@ -903,7 +967,8 @@ extern "C" int ftk_savgol_f64(const double *adj, const int64_t *seg_out_off, int
 template <typename InT>
 static int launch_rank(const InT *x, const long long *so, const long long *oo, const double *seg_shift,
                        const int *tile_seg, const int *tile_t0, const int *tile_n, int64_t n_tiles, int w,
-                       int sg_w, const double *coef, const double *ef, const double *el, int a_cap, int s_cap,
+                       int sg_w, const double *coef, const double *ef, const double *el, long long sg_a,
+                       long long sg_b, double sg_scale, int a_cap, int s_cap,
                        double *out, unsigned char *flag, cudaStream_t stream) {
     const unsigned grid = (unsigned)n_tiles;
 #define FTK_RANK(SHIFT, SGW)                                                                                      \
@@ -913,7 +978,8 @@ static int launch_rank(const InT *x, const long long *so, const long long *oo, c
         FTK_CUDA_TRY(cudaFuncSetAttribute(adjust_rank_kernel<InT, SHIFT, SGW>,                                     \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
         adjust_rank_kernel<InT, SHIFT, SGW><<<grid, kRankThreads, smem, stream>>>(                                 \
-            x, so, oo, seg_shift, tile_seg, tile_t0, tile_n, w, sg_w, coef, ef, el, a_cap, s_cap, out, flag);     \
+            x, so, oo, seg_shift, tile_seg, tile_t0, tile_n, w, sg_w, coef, ef, el, sg_a, sg_b, sg_scale, a_cap,  \
+            s_cap, out, flag);                                                                                    \
     } while (0)
     if (seg_shift) {
         if (sg_w == 0) FTK_RANK(true, -1); else if (sg_w == 21) FTK_RANK(true, 21); else FTK_RANK(true, 0);
@@ -929,7 +995,8 @@ extern "C" int ftk_adjust_rank_f64(const void *x, int32_t x_kind, const int64_t 
                                    const double *seg_shift, int32_t n_seg, const int32_t *tile_seg,
                                    const int32_t *tile_t0, const int32_t *tile_n, int64_t n_tiles, int32_t w,
                                    int32_t sg_w, const double *coef, const double *edge_first,
-                                   const double *edge_last, int32_t a_cap, int32_t s_cap, double *out,
+                                   const double *edge_last, int64_t sg_num_a, int64_t sg_num_b, int64_t sg_den,
+                                   int32_t a_cap, int32_t s_cap, double *out,
                                    uint8_t *tile_flag, ftk_stream_t stream_) {
     if (n_tiles == 0 || n_seg == 0) return FTK_OK;
     if (!x || !seg_off || !seg_out_off || !tile_seg || !tile_t0 || !tile_n || !out || !tile_flag) return FTK_E_INVALID;
@@ -937,13 +1004,29 @@ extern "C" int ftk_adjust_rank_f64(const void *x, int32_t x_kind, const int64_t 
     if (w < 2 || (w & 1) || w > 32767) return FTK_E_INVALID;
     if (sg_w != 0 && (sg_w < 1 || !(sg_w & 1) || sg_w > kAdjMaxSg || !coef || !edge_first || !edge_last)) return FTK_E_INVALID;
     if (a_cap < 1 || a_cap > 32 * kRankThreads || s_cap < a_cap + w || s_cap > 65535 - 64) return FTK_E_RANGE;
+    // exact sliding-moment smoothing: only when every intermediate provably fits (|2 adj| < 2^17)
+    double sg_scale = 0.0;
+    if (sg_w > 0 && sg_den != 0) {
+        if (sg_den < 0) return FTK_E_INVALID;
+        const long long h = sg_w >> 1;
+        const long long s2 = h * (h + 1) * (2 * h + 1) / 3;                 // sum of i^2 over the window
+        const long long bound = 1ll << 17;
+        const long long aa = sg_num_a < 0 ? -sg_num_a : sg_num_a, bb = sg_num_b < 0 ? -sg_num_b : sg_num_b;
+        // every term of the moment updates summed in absolute value stays inside int32, the final
+        // combination inside 2^53 (exactly representable)
+        if ((s2 + 2 * h * (h + 1) + sg_w + 2 * (h + 1) * (h + 1)) * bound < (1ll << 31) && aa < (1ll << 31) &&
+            bb < (1ll << 31) && (aa * sg_w + bb * s2) < (1ll << 36))
+            sg_scale = 0.5 / (double)sg_den;
+    }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     FTK_CUDA_TRY(cudaMemsetAsync(tile_flag, 0, (size_t)n_tiles, stream));
     const long long *so = reinterpret_cast<const long long *>(seg_off);
     const long long *oo = reinterpret_cast<const long long *>(seg_out_off);
     if (x_kind == 0)
         return launch_rank<float>(static_cast<const float *>(x), so, oo, seg_shift, tile_seg, tile_t0, tile_n, n_tiles,
-                                  w, sg_w, coef, edge_first, edge_last, a_cap, s_cap, out, tile_flag, stream);
+                                  w, sg_w, coef, edge_first, edge_last, sg_num_a, sg_num_b, sg_scale, a_cap, s_cap, out,
+                                  tile_flag, stream);
     return launch_rank<int>(static_cast<const int *>(x), so, oo, seg_shift, tile_seg, tile_t0, tile_n, n_tiles,
-                            w, sg_w, coef, edge_first, edge_last, a_cap, s_cap, out, tile_flag, stream);
+                            w, sg_w, coef, edge_first, edge_last, sg_num_a, sg_num_b, sg_scale, a_cap, s_cap, out,
+                            tile_flag, stream);
 }

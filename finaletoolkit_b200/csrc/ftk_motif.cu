@@ -21,6 +21,8 @@
 //   odd k: every window has 2h != k bases -> "length discrepancy" -> nothing is ever counted
 // Roofline: HBM, 10 B per candidate fragment (start, stop, mapq, strand) + 2 x 2 B
 // of packed reference per end served from L2.
+#include <type_traits>
+
 #include "ftk_common.cuh"
 
 namespace ftk {
@@ -63,116 +65,257 @@ __global__ void motif_ranges_kernel(const int32_t *__restrict__ frag_start, int6
 // contig span of every 4096-fragment sub-chunk in shared memory was measured in round 2 and lost:
 // 0.59 ms against 0.39 ms - the staging serialises bounds -> span -> fragments behind two barriers
 // per sub-chunk and its 75 registers cut the residency to three CTAs per SM.)
-template <bool SMEM, bool BREAKPOINT>
-__global__ void __launch_bounds__(kMotifThreads, 6)
+//
+// What keeps the per-fragment instruction count down (the kernel is issue-bound, not DRAM-bound):
+//   * K and the strand mode are template parameters for the common cases (masks, shifts and the
+//     mode tests fold away instead of being rematerialised under the 40-register budget);
+//   * N runs are rare and long (telomeres, centromere, assembly gaps), so every CTA first ORs the
+//     N-mask words of the span its fragment slice can touch - two loads per thread - and, when that is
+//     zero, runs the loop instantiated without the per-end N test (two loads + four operations less
+//     per end);
+//   * forward k-mers are counted under their raw window bits (first base = least significant digit)
+//     in a second shared histogram and only re-indexed (digit reversal) when the CTA flushes it.
+template <int K>
+struct MotifK {
+    int k_rt;
+    __device__ __forceinline__ int k() const { return K ? K : k_rt; }
+    __device__ __forceinline__ uint32_t mask2k() const { return (1u << (2 * k())) - 1u; }
+    __device__ __forceinline__ uint32_t maskk() const { return (1u << k()) - 1u; }
+};
+
+#ifndef FTK_MOTIF_CTAS
+#define FTK_MOTIF_CTAS 5
+#endif
+constexpr int kMotifCtasPerSm = FTK_MOTIF_CTAS;   // 5 -> 48 registers: the two loop instantiations spill at 40
+constexpr int kMotifNScanWords = 8192;      // longest span (in 32-base mask words) a CTA pre-scans for N
+
+template <int K, int MODE, bool SMEM, bool BREAKPOINT>
+__global__ void __launch_bounds__(kMotifThreads, kMotifCtasPerSm)
 end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restrict__ frag_stop,
                  const uint8_t *__restrict__ frag_mapq, const uint8_t *__restrict__ frag_strand,
                  const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask, int64_t contig_len,
                  const int32_t *__restrict__ ivl_start, const int32_t *__restrict__ ivl_stop,
-                 const int64_t *__restrict__ ranges, int k, int strand_mode, int min_mapq,
+                 const int64_t *__restrict__ ranges, int k, int strand_mode, int min_mapq, int max_frag_len,
                  int pooled, int splits, unsigned long long *__restrict__ counts,
                  int32_t *__restrict__ error_flag) {
-    __shared__ int s_cnt[SMEM ? kMotifSmemBins : 1];
+    // (Bank-interleaved replicas of the histograms - 4 / 8 / 16 copies, lane l bumping copy l % copies -
+    // were measured: no change.  The cost is the shared-memory atomic unit itself, ~3 lane-atomics per
+    // cycle and SM whether the lanes collide or not: 2 atomics x 72 M counted fragments = 0.17 ms.)
+    constexpr int kCopies = 1;
+    __shared__ int s_cnt[SMEM ? (K ? (2 << (2 * K)) * kCopies : 2 * kMotifSmemBins) : 1];
     const int tid = threadIdx.x;
-    const int n_bins = 1 << (2 * k);
+    MotifK<K> KK{k};
+    const int n_bins = 1 << (2 * KK.k());
     const int64_t ivl = blockIdx.x / splits;
     const int split = blockIdx.x % splits;
     unsigned long long *__restrict__ row = counts + (pooled ? 0 : ivl * (int64_t)n_bins);
-    const int S = ivl_start[ivl], E = ivl_stop[ivl];
     const int64_t lo_all = ranges[2 * ivl], hi_all = ranges[2 * ivl + 1];
     int64_t chunk = (hi_all - lo_all + splits - 1) / splits;
     chunk = (chunk + 3) & ~(int64_t)3;
     const int64_t lo = lo_all + (int64_t)split * chunk;
     const int64_t hi = min(hi_all, lo + chunk);
+    if (hi <= lo) return;
 
-    if (SMEM) {
-        for (int b = tid; b < n_bins; b += kMotifThreads) s_cnt[b] = 0;
-        __syncthreads();
-    }
-    auto bump = [&](uint32_t idx) {
-        if (SMEM) atomicAdd(&s_cnt[idx], 1); else atomicAdd(&row[idx], 1ull);
-    };
+    const int S = ivl_start[ivl], E = ivl_stop[ivl];
+    const int len32 = (int)min(contig_len, (int64_t)INT32_MAX);     // 32-bit everything inside the slice
+    const int mode = (MODE < 3) ? MODE : strand_mode;
+    const int kk = KK.k();
+    const uint32_t mask2k = KK.mask2k(), maskk = KK.maskk();
 
-    // 32-bit everything inside the slice: contig positions are int32 and a slice is < 2^31 fragments
-    const uint32_t mask2k = (1u << (2 * k)) - 1u, maskk = (1u << k) - 1u;
-    const int len32 = (int)min(contig_len, (int64_t)INT32_MAX);
-    const int h = k >> 1;
-    auto visit = [&](int fs, int fe, int q, int sd) {
-        if (q < min_mapq || !(fe > S && fs < E)) return;
-        if (BREAKPOINT) {
-            if (fs < h || fs >= len32 - h) return;                       // too close to a contig end
-            if ((k & 1) != 0) return;                                    // 2h != k: never counted
-            if (strand_mode == 0 || (strand_mode == 1 && sd)) {
-                if (!has_n(nmask, fs - h, maskk)) bump(digit_reverse(window2(seq, fs - h, mask2k), k));
-            }
-            if (strand_mode != 1) {
-                if (fe < h || fe > len32 - h) return;                    // OutOfBoundsError -> skipped
-                if (!has_n(nmask, fe - h, maskk)) bump((~window2(seq, fe - h, mask2k)) & mask2k);
-            }
-            return;
-        }
-        if (strand_mode == 1 && !sd) return;         // forward-only: '+' fragments only
-        if (strand_mode != 2) {
-            if (fs < 0 || fs > len32 - k) return;    // ValueError -> `continue`
-            if (!has_n(nmask, fs, maskk)) bump(digit_reverse(window2(seq, fs, mask2k), k));
-        }
-        if (strand_mode != 1) {
-            if (fe < k || fe > len32) {
-                if (strand_mode == 0) atomicOr(error_flag, 1);  // RuntimeError in the reference
-                return;
-            }
-            if (!has_n(nmask, fe - k, maskk)) bump((~window2(seq, fe - k, mask2k)) & mask2k);
-        }
-    };
     // the slice is widened to a 16-byte boundary on the left so that every lane loads 4 fragments per
-    // 128-bit load; fragments left of lo are masked by index
+    // 128-bit load; the (at most three) fragments left of lo get stop = INT32_MIN and fail the overlap test
     const int64_t lo_al = lo & ~(int64_t)3;
     const int skip = (int)(lo - lo_al);
-    const int cnt = (hi > lo) ? (int)(hi - lo_al) : 0;
+    const int cnt = (int)(hi - lo_al);
     const int nvec = cnt >> 2;
     const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(frag_start + lo_al);
     const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(frag_stop + lo_al);
     const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(frag_mapq ? frag_mapq + lo_al : nullptr);
     const uchar4 *__restrict__ vd = reinterpret_cast<const uchar4 *>(frag_strand ? frag_strand + lo_al : nullptr);
-    constexpr int kU = 2;
-    for (int v0 = tid; v0 < nvec; v0 += kU * kMotifThreads) {
-        int4 s4[kU], e4[kU];
-        uchar4 q4[kU], d4[kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const int v = v0 + u * kMotifThreads;
-            if (v < nvec) {
-                s4[u] = __ldcs(vs + v); e4[u] = __ldcs(ve + v);
-                q4[u] = vq ? __ldcs(vq + v) : make_uchar4(255, 255, 255, 255);
-                d4[u] = vd ? __ldcs(vd + v) : make_uchar4(1, 1, 1, 1);
-            } else {
-                s4[u] = make_int4(0, 0, 0, 0); e4[u] = make_int4(0, 0, 0, 0);
-                q4[u] = make_uchar4(0, 0, 0, 0); d4[u] = make_uchar4(1, 1, 1, 1);
+    auto load = [&](int v, int4 &s4, int4 &e4, uchar4 &q4, uchar4 &d4) {
+        if (v < nvec) {
+            s4 = __ldcs(vs + v); e4 = __ldcs(ve + v);
+            q4 = vq ? __ldcs(vq + v) : make_uchar4(255, 255, 255, 255);
+            d4 = vd ? __ldcs(vd + v) : make_uchar4(1, 1, 1, 1);
+        } else {
+            s4 = make_int4(0, 0, 0, 0); e4 = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN);
+            q4 = make_uchar4(0, 0, 0, 0); d4 = make_uchar4(1, 1, 1, 1);
+        }
+    };
+    // the first vector of every thread is requested before the N pre-scan so that the two overlap
+    int4 s_c, e_c;
+    uchar4 q_c, d_c;
+    load(tid, s_c, e_c, q_c, d_c);
+    if (tid == 0 && skip) {
+        e_c.x = INT32_MIN;
+        if (skip > 1) e_c.y = INT32_MIN;
+        if (skip > 2) e_c.z = INT32_MIN;
+    }
+
+    // does the span this slice can touch hold any N?  (start-sorted: first start .. last start + longest fragment)
+    int any_n = 1;
+    {
+        const int64_t p_lo = max((int64_t)__ldg(frag_start + lo) - kk, (int64_t)0);
+        const int64_t p_hi = min((int64_t)__ldg(frag_start + hi - 1) + max_frag_len + 2 * kk, (int64_t)len32);
+        const int64_t w_lo = p_lo >> 5, w_hi = (p_hi >> 5) + 1;     // has_n reads words w and w + 1
+        unsigned acc = 0;
+        if (p_hi >= p_lo && w_hi - w_lo < kMotifNScanWords) {
+            for (int64_t w = w_lo + tid; w <= w_hi; w += kMotifThreads) acc |= __ldg(nmask + w);
+        } else {
+            acc = 1u;
+        }
+        if (SMEM) for (int b = tid; b < 2 * n_bins * kCopies; b += kMotifThreads) s_cnt[b] = 0;
+        any_n = __syncthreads_or(acc != 0u);
+    }
+
+    // The shared histograms are addressed through their 32-bit shared-window address and bumped with
+    // red.shared: left to itself the compiler re-derives that address per atomic (S2R SR_CgaCtaId + LEA
+    // in the hot loop - measured 3x slower than the whole rest of the loop).
+    uint32_t s_base = 0u;
+    if (SMEM) {     // laundered through an opaque move so that it is computed once and kept in a register
+        const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(s_cnt));
+        asm volatile("mov.b32 %0, %1;" : "=r"(s_base) : "r"(a));
+    }
+    const uint32_t s_rev_off = (uint32_t)n_bins * 4u;      // in units of bins x 4 (scaled by kCopies in bump_s)
+    const uint32_t lane_off = (kCopies > 1) ? (uint32_t)(tid & (kCopies - 1)) * 4u : 0u;
+    auto bump_s = [&](uint32_t byte_off) {
+        asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(s_base + byte_off * kCopies + lane_off) : "memory");
+    };
+    auto stream = [&](auto ncheck_tag) {
+        constexpr bool NCHECK = decltype(ncheck_tag)::value;
+        auto fwd = [&](int pos) {      // k-mer read 5'->3' on the forward strand starting at pos
+            if (NCHECK && has_n(nmask, pos, maskk)) return;
+            const uint32_t wbits = window2(seq, pos, mask2k);
+            if (SMEM) bump_s(wbits << 2);
+            else atomicAdd(&row[digit_reverse(wbits, kk)], 1ull);
+        };
+        auto rev = [&](int pos) {      // reverse complement of ref[pos, pos + k)
+            if (NCHECK && has_n(nmask, pos, maskk)) return;
+            const uint32_t idx = (~window2(seq, pos, mask2k)) & mask2k;
+            if (SMEM) bump_s(s_rev_off + (idx << 2));
+            else atomicAdd(&row[idx], 1ull);
+        };
+        auto visit = [&](int fs, int fe, int q, int sd) {
+            if (q < min_mapq || !(fe > S && fs < E)) return;
+            if (BREAKPOINT) {
+                const int h = kk >> 1;
+                if (fs < h || fs >= len32 - h) return;                       // too close to a contig end
+                if ((kk & 1) != 0) return;                                   // 2h != k: never counted
+                if (mode == 0 || (mode == 1 && sd)) fwd(fs - h);
+                if (mode != 1) {
+                    if (fe < h || fe > len32 - h) return;                    // OutOfBoundsError -> skipped
+                    rev(fe - h);
+                }
+                return;
             }
-        }
+            if (mode == 1 && !sd) return;                // forward-only: '+' fragments only
+            if (mode != 2) {
+                if ((unsigned)fs > (unsigned)(len32 - kk)) return;           // fs < 0 or past the end: ValueError -> `continue`
+                fwd(fs);
+            }
+            if (mode != 1) {
+                if (fe < kk || fe > len32) {
+                    if (mode == 0) atomicOr(error_flag, 1);                  // RuntimeError in the reference
+                    return;
+                }
+                rev(fe - kk);
+            }
+        };
+        // N-free span: the four fragments of a vector are handled together and without branches - the
+        // tests of the eight ends turn into predicates, all sixteen window words are requested back to
+        // back (a rejected end reads word 0), and only then are the k-mers formed and counted.  The
+        // per-fragment version above serialises eight dependent L2 round trips per vector; this one has one.
+        auto visit4 = [&](const int4 &s4, const int4 &e4, const uchar4 &q4, const uchar4 &d4, auto between) {
+            const int fs[4] = {s4.x, s4.y, s4.z, s4.w}, fe[4] = {e4.x, e4.y, e4.z, e4.w};
+            const int q[4] = {q4.x, q4.y, q4.z, q4.w}, sd[4] = {d4.x, d4.y, d4.z, d4.w};
+            const int h = BREAKPOINT ? (kk >> 1) : 0;
+            bool f_ok[4], r_ok[4];
+            uint32_t f_lo[4], f_hi[4], r_lo[4], r_hi[4];
+            int pf[4], pr[4];
+            bool err = false;
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const int v = v0 + u * kMotifThreads;
-            if (v >= nvec) continue;
-            const bool head = (v == 0);
-            if (!(head && skip > 0)) visit(s4[u].x, e4[u].x, q4[u].x, d4[u].x);
-            if (!(head && skip > 1)) visit(s4[u].y, e4[u].y, q4[u].y, d4[u].y);
-            if (!(head && skip > 2)) visit(s4[u].z, e4[u].z, q4[u].z, d4[u].z);
-            visit(s4[u].w, e4[u].w, q4[u].w, d4[u].w);
+            for (int i = 0; i < 4; ++i) {
+                bool pass = (q[i] >= min_mapq) && (fe[i] > S) && (fs[i] < E);
+                bool r_try;
+                if (BREAKPOINT) {
+                    pass = pass && (fs[i] >= h) && (fs[i] < len32 - h) && ((kk & 1) == 0);
+                    f_ok[i] = pass && (mode == 0 || (mode == 1 && sd[i]));
+                    r_try = pass && (mode != 1);
+                    r_ok[i] = r_try && !(fe[i] < h || fe[i] > len32 - h);
+                    pf[i] = fs[i] - h; pr[i] = fe[i] - h;
+                } else {
+                    if (mode == 1) pass = pass && sd[i];
+                    const bool f_in = (unsigned)fs[i] <= (unsigned)(len32 - kk);
+                    f_ok[i] = pass && (mode != 2) && f_in;
+                    r_try = pass && (mode != 1) && (mode == 2 || f_in);
+                    const bool r_oob = (fe[i] < kk) || (fe[i] > len32);
+                    r_ok[i] = r_try && !r_oob;
+                    err = err || (mode == 0 && r_try && r_oob);
+                    pf[i] = fs[i]; pr[i] = fe[i] - kk;
+                }
+                pf[i] = f_ok[i] ? pf[i] : 0;
+                pr[i] = r_ok[i] ? pr[i] : 0;
+                const uint32_t *__restrict__ wf = seq + (pf[i] >> 4), *__restrict__ wr = seq + (pr[i] >> 4);
+                f_lo[i] = __ldg(wf); f_hi[i] = __ldg(wf + 1);
+                r_lo[i] = __ldg(wr); r_hi[i] = __ldg(wr + 1);
+            }
+            // the next vector's (DRAM) loads are issued BEHIND the window reads (L1 / L2 hits): the L1
+            // returns a warp's loads through one in-order queue, so a hit queued behind a miss waits for it
+            asm volatile("" ::: "memory");
+            between();
+            asm volatile("" ::: "memory");
+            if (err) atomicOr(error_flag, 1);                                // RuntimeError in the reference
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (f_ok[i]) {
+                    const uint32_t wbits = __funnelshift_r(f_lo[i], f_hi[i], pf[i] << 1) & mask2k;
+                    if (SMEM) bump_s(wbits << 2);
+                    else atomicAdd(&row[digit_reverse(wbits, kk)], 1ull);
+                }
+                if (r_ok[i]) {
+                    const uint32_t idx = (~__funnelshift_r(r_lo[i], r_hi[i], pr[i] << 1)) & mask2k;
+                    if (SMEM) bump_s(s_rev_off + (idx << 2));
+                    else atomicAdd(&row[idx], 1ull);
+                }
+            }
+        };
+        // software pipeline: the next vector of the thread is in flight while the current one is turned
+        // into window reads and atomics
+        for (int v = tid; v < nvec; v += kMotifThreads) {
+            int4 s_n, e_n;
+            uchar4 q_n, d_n;
+            if (NCHECK) {
+                load(v + kMotifThreads, s_n, e_n, q_n, d_n);
+                visit(s_c.x, e_c.x, q_c.x, d_c.x);
+                visit(s_c.y, e_c.y, q_c.y, d_c.y);
+                visit(s_c.z, e_c.z, q_c.z, d_c.z);
+                visit(s_c.w, e_c.w, q_c.w, d_c.w);
+            } else {
+                visit4(s_c, e_c, q_c, d_c, [&] { load(v + kMotifThreads, s_n, e_n, q_n, d_n); });
+            }
+            s_c = s_n; e_c = e_n; q_c = q_n; d_c = d_n;
         }
-    }
-    {   // tail: at most 3 fragments
-        const int i = nvec * 4 + tid;
-        if (i < cnt && i >= skip)
-            visit(__ldcs(frag_start + lo_al + i), __ldcs(frag_stop + lo_al + i),
-                  frag_mapq ? (int)__ldcs(frag_mapq + lo_al + i) : 255,
-                  frag_strand ? (int)__ldcs(frag_strand + lo_al + i) : 1);
-    }
+        {   // tail: at most 3 fragments
+            const int i = nvec * 4 + tid;
+            if (i < cnt && i >= skip)
+                visit(__ldcs(frag_start + lo_al + i), __ldcs(frag_stop + lo_al + i),
+                      frag_mapq ? (int)__ldcs(frag_mapq + lo_al + i) : 255,
+                      frag_strand ? (int)__ldcs(frag_strand + lo_al + i) : 1);
+        }
+    };
+    if (any_n) stream(std::true_type{});
+    else stream(std::false_type{});
     if (SMEM) {
         __syncthreads();
         for (int b = tid; b < n_bins; b += kMotifThreads) {
-            const int c = s_cnt[b];
-            if (c) atomicAdd(&row[b], (unsigned long long)c);
+            int cf = 0, cr = 0;
+#pragma unroll
+            for (int c = 0; c < kCopies; ++c) {
+                cf += s_cnt[b * kCopies + c];
+                cr += s_cnt[(n_bins + b) * kCopies + c];
+            }
+            if (cf) atomicAdd(&row[digit_reverse((uint32_t)b, KK.k())], (unsigned long long)cf);
+            if (cr) atomicAdd(&row[b], (unsigned long long)cr);
         }
     }
 }
@@ -207,14 +350,17 @@ static int motif_hist_launch(const int32_t *frag_start, const int32_t *frag_stop
     }
     const unsigned grid = (unsigned)(n_ivl * splits);
     auto *c = reinterpret_cast<unsigned long long *>(counts);
-    if ((1 << (2 * k)) <= kMotifSmemBins)
-        end_motif_kernel<true, BREAKPOINT><<<grid, kMotifThreads, 0, stream>>>(
-            frag_start, frag_stop, frag_mapq, frag_strand, seq_words, nmask_words, contig_len,
-            ivl_start, ivl_stop, scratch, k, strand_mode, min_mapq, pooled, splits, c, error_flag);
-    else
-        end_motif_kernel<false, BREAKPOINT><<<grid, kMotifThreads, 0, stream>>>(
-            frag_start, frag_stop, frag_mapq, frag_strand, seq_words, nmask_words, contig_len,
-            ivl_start, ivl_stop, scratch, k, strand_mode, min_mapq, pooled, splits, c, error_flag);
+    const int mfl = max_frag_len < 0 ? 0 : max_frag_len;
+#define FTK_MOTIF(K, MODE, SMEM)                                                                             \
+    end_motif_kernel<K, MODE, SMEM, BREAKPOINT><<<grid, kMotifThreads, 0, stream>>>(                         \
+        frag_start, frag_stop, frag_mapq, frag_strand, seq_words, nmask_words, contig_len, ivl_start,        \
+        ivl_stop, scratch, k, strand_mode, min_mapq, mfl, pooled, splits, c, error_flag)
+    // the common cases are compiled with K and the strand mode fixed; everything else takes the runtime variant
+    if (k == 4 && strand_mode == 0) FTK_MOTIF(4, 0, true);
+    else if (k == 6 && strand_mode == 0) FTK_MOTIF(6, 0, true);
+    else if ((1 << (2 * k)) <= kMotifSmemBins) FTK_MOTIF(0, 3, true);
+    else FTK_MOTIF(0, 3, false);
+#undef FTK_MOTIF
     FTK_CHECK_LAUNCH("end_motif_kernel");
     return FTK_OK;
 }

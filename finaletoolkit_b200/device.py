@@ -442,7 +442,11 @@ def end_motif_hist(frags: ContigFragments, ref: PackedContig, ivl_start, ivl_sto
     fs, fe, mq = frags.ptrs()
     sd = 0 if frags.strand is None else frags.strand.data_ptr()
     # a CTA zeroes and flushes a 4^k-bin histogram: give it enough fragments to amortise that
-    splits = _splits_for(n_ivl, frags.n, unit_frags=max(4096, 16 * 4 ** min(int(k), 6)))
+    # a CTA's fixed latency chain (ranges -> slice bounds -> N pre-scan -> first fragments -> windows) is
+    # paid once per slice: 16 K fragments amortise it (and the zero + flush of a 4^k-bin histogram)
+    import os
+    unit = int(os.environ.get("FTK_MOTIF_UNIT", 16384))
+    splits = _splits_for(n_ivl, frags.n, unit_frags=max(unit, 16 * 4 ** min(int(k), 6)))
     if breakpoint:
         check(lib().ftk_breakpoint_motif_hist_u64(
             fs, fe, mq, sd, frags.n, frags.max_len, ref.seq.data_ptr(), ref.nmask.data_ptr(), ref.length,
@@ -570,6 +574,32 @@ def _savgol_tables_cached(window: int, degree: int):
     return coef, edge_first, edge_last
 
 
+def savgol_rational(window: int, degree: int):
+    """Interior Savitzky-Golay coefficients as exact rationals ``c_i = (a + b * i**2) / den`` (degree <= 3;
+    the least-squares fit on symmetric points: degree 0/1 is the moving average, degree 2/3 gives
+    ``a = S4, b = -S2, den = m * S4 - S2**2`` with ``Sk = sum i**k``), reduced by their gcd and checked
+    against the fp64 table ``savgol_tables`` returns.  ``(0, 0, 0)`` when the coefficients have no such form."""
+    import math
+    m, h = int(window), int(window) // 2
+    if degree <= 1:
+        a, b, den = 1, 0, m
+    elif degree <= 3:
+        s2 = sum(i * i for i in range(-h, h + 1))
+        s4 = sum(i ** 4 for i in range(-h, h + 1))
+        a, b, den = s4, -s2, m * s4 - s2 * s2
+    else:
+        return 0, 0, 0
+    if den <= 0:
+        return 0, 0, 0
+    g = math.gcd(math.gcd(abs(a), abs(b)), den)
+    a, b, den = a // g, b // g, den // g
+    coef = _savgol_tables_cached(m, int(degree))[0]
+    exact = np.array([(a + b * i * i) / den for i in range(-h, h + 1)])
+    if coef.shape != exact.shape or float(np.abs(coef - exact).max()) > 1e-12:
+        return 0, 0, 0
+    return a, b, den
+
+
 _RANK_T_MAX = 4096          # outputs per tile of the rank-bitmap kernel
 _RANK_SMEM_MAX = 227 * 1024
 
@@ -645,7 +675,9 @@ class AdjustPlan:
         self.d_out = _to_device(self.out_off, dev, np.int64)
         self.sg_w = int(savgol_window_size) if savgol else 0
         self.tables = None
+        self.sg_rational = (0, 0, 0)
         if savgol:
+            self.sg_rational = savgol_rational(self.sg_w, int(savgol_poly_deg))
             coef, ef, el = savgol_tables(self.sg_w, int(savgol_poly_deg))
             self.tables = (_to_device(coef, dev, np.float64),
                            _to_device(ef.reshape(-1) if ef.size else np.zeros(1), dev, np.float64),
@@ -671,6 +703,7 @@ class AdjustPlan:
             xd.data_ptr(), 1 if xd.dtype == t.int32 else 0, self.d_seg.data_ptr(), self.d_out.data_ptr(), shift_ptr,
             self.n_seg, d_ts.data_ptr(), d_t0.data_ptr(), d_tn.data_ptr(), n_tiles, self.w, self.sg_w,
             tb[0].data_ptr() if tb else 0, tb[1].data_ptr() if tb else 0, tb[2].data_ptr() if tb else 0,
+            *(self.sg_rational if not shift_ptr else (0, 0, 0)),
             a_cap, s_cap, out.data_ptr(), flag.data_ptr(), _stream_ptr(self.device)), "ftk_adjust_rank_f64")
         return out, flag
 

@@ -352,12 +352,19 @@ int ftk_savgol_f64(const double *adj_dev, const int64_t *seg_out_off_dev, int32_
  * sg_w = 0: no smoothing (out = adjusted series).  seg_shift_dev NULL = no subtract_edges.
  * tile_flag_dev[t] (uint8, zeroed here) is set for tiles that could not be handled (non-integer or
  * |x| > 32000 samples, value spread beyond the searched bands): the caller redoes those through
- * ftk_adjust_wps_f64 / ftk_adjust_wps_generic_f64 + ftk_savgol_f64.  Results are identical to that path. */
+ * ftk_adjust_wps_f64 / ftk_adjust_wps_generic_f64 + ftk_savgol_f64.
+ * sg_num_a, sg_num_b, sg_den (sg_den > 0, no subtract_edges): the interior Savitzky-Golay coefficients as the
+ * exact rationals c_i = (sg_num_a + sg_num_b * i^2) / sg_den, i = -sg_w/2 .. sg_w/2 (polynomial degree <= 3:
+ * degree 0/1 = (1, 0, sg_w); degree 2/3 = (S4, -S2, sg_w * S4 - S2^2) with S2 = sum i^2, S4 = sum i^4).  The
+ * smoothing then runs as exact integer sliding moments of 2 * adjusted (O(1) per output) and is rounded once;
+ * it differs from the fp64 stencil of coef_dev (used when sg_den == 0, and by the fallback path) only by that
+ * stencil's own rounding (~1e-16 x sum |c_i x_i|).  Without smoothing the results are identical to the fallback path. */
 int ftk_adjust_rank_f64(const void *x_dev, int32_t x_kind, const int64_t *seg_off_dev,
                         const int64_t *seg_out_off_dev, const double *seg_shift_dev, int32_t n_seg,
                         const int32_t *tile_seg_dev, const int32_t *tile_t0_dev, const int32_t *tile_n_dev,
                         int64_t n_tiles, int32_t median_window, int32_t sg_w, const double *coef_dev,
-                        const double *edge_first_dev, const double *edge_last_dev, int32_t a_cap, int32_t s_cap,
+                        const double *edge_first_dev, const double *edge_last_dev,
+                        int64_t sg_num_a, int64_t sg_num_b, int64_t sg_den, int32_t a_cap, int32_t s_cap,
                         double *out_dev, uint8_t *tile_flag_dev, ftk_stream_t stream);
 
 /* ------------------------------------------------------- cleavage profile

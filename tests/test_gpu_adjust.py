@@ -140,7 +140,12 @@ def test_rank_kernel_vs_oracle_and_hist_path(seed):
             old, _ = adjust_segments(x.astype(np.float32), lens, impl="hist", **kw)
             torch.cuda.synchronize()
             assert torch.equal(got, got_i)
-            assert torch.equal(got, old), (seed, w, savgol, sub, float((got - old).abs().max()))
+            if savgol and not sub:
+                # exact sliding-moment smoothing vs the fp64 stencil of the fallback path: they differ by the
+                # stencil's own rounding only (values are O(100): 1e-11 absolute is ~1e-13 relative)
+                assert float((got - old).abs().max()) < 1e-11, (seed, w, float((got - old).abs().max()))
+            else:
+                assert torch.equal(got, old), (seed, w, savgol, sub, float((got - old).abs().max()))
             gh = got.cpu().numpy()
             for i, v in enumerate(xs):
                 xx = v.astype(np.float64)
@@ -159,10 +164,20 @@ def test_rank_kernel_other_sg_windows_and_fallback():
     rng = np.random.default_rng(3)
     lens = [3000, 5000, 1200]
     x = np.concatenate([_int_series(rng, l, 0) for l in lens]).astype(np.float32)
-    for sgw, deg in ((5, 2), (51, 3)):
+    from finaletoolkit_b200.device import savgol_rational
+    for sgw, deg in ((5, 2), (51, 3), (3, 2), (7, 0), (9, 1), (11, 4), (21, 5), (101, 2)):
         got, off = adjust_segments(x, lens, median_window_size=500, savgol_window_size=sgw, savgol_poly_deg=deg)
         old, _ = adjust_segments(x, lens, median_window_size=500, savgol_window_size=sgw, savgol_poly_deg=deg, impl="hist")
-        assert torch.equal(got, old)
+        if deg >= 4:
+            assert savgol_rational(sgw, deg) == (0, 0, 0) and torch.equal(got, old)      # fp64 stencil in both
+        else:
+            assert savgol_rational(sgw, deg)[2] > 0 and float((got - old).abs().max()) < 1e-11
+        o = 0
+        gh = got.cpu().numpy()
+        for i, l in enumerate(lens):
+            exp = O.adjust_core(x[o:o + l].astype(np.float64), 500, False, True, sgw, deg)
+            np.testing.assert_allclose(gh[off[i]:off[i + 1]], exp, rtol=RTOL, atol=1e-8)
+            o += l
     y = x.copy(); y[4000] += 0.5
     got, off = adjust_segments(y, lens, median_window_size=500)
     o = 0
