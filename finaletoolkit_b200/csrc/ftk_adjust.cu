@@ -500,12 +500,25 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
     // ---- stage the samples (coalesced), validate: integer-valued and small
     if (!bad) {
         const InT *__restrict__ src = x + seg0 + a0;
-        for (int i = tid; i < G.s_pad + 32; i += kRankThreads) {
-            int iv = 32767;                       // sentinel beyond every level: never counted
-            if (i < S) {
-                if (!rank_stage(__ldg(src + i), iv)) { bad = true; iv = 0; }
+        // eight loads per thread are in flight before the first one is looked at: the tile's samples cost
+        // two DRAM round trips instead of one per 384 samples
+        constexpr int kStageU = 8;
+        for (int i0 = tid; i0 < G.s_pad + 32; i0 += kStageU * kRankThreads) {
+            InT v[kStageU];
+#pragma unroll
+            for (int u = 0; u < kStageU; ++u) {
+                const int i = i0 + u * kRankThreads;
+                v[u] = (i < S) ? __ldg(src + i) : InT(0);
             }
-            xs[i] = (short)iv;
+#pragma unroll
+            for (int u = 0; u < kStageU; ++u) {
+                const int i = i0 + u * kRankThreads;
+                int iv = 32767;                   // sentinel beyond every level: never counted
+                if (i < S) {
+                    if (!rank_stage(v[u], iv)) { bad = true; iv = 0; }
+                }
+                if (i < G.s_pad + 32) xs[i] = (short)iv;
+            }
         }
     }
     if (__syncthreads_or(bad ? 1 : 0)) {
@@ -749,6 +762,9 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
         const int k_lo = min(tid * Ro, n_t), k_hi = min(k_lo + Ro, n_t);
         const int h = half, h1 = half + 1;
         const int hh = h * h, h1h1 = h1 * h1;
+        const long long aa = sg_a < 0 ? -sg_a : sg_a, bb = sg_b < 0 ? -sg_b : sg_b;
+        const long long s2sum = (long long)h * h1 * (2 * h + 1) / 3;
+        const bool sg_fit32 = (aa * sg_w + bb * s2sum) * (1ll << 17) < (1ll << 31);
         int S0 = 0, M1 = 0, M2 = 0;
         bool valid = false;
         for (int k = k_lo; k < k_hi; ++k) {
@@ -768,7 +784,9 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
                 M1 += h1 * xo + h * xi - S0;
                 S0 += xi - xo;
             }
-            ystage[k] = (double)(sg_a * (long long)S0 + sg_b * (long long)M2) * sg_scale;
+            // (the launcher passes |sg_a|, |sg_b| < 2^31; sg_fit32: the combination itself fits int32)
+            ystage[k] = sg_fit32 ? (double)((int)sg_a * S0 + (int)sg_b * M2) * sg_scale
+                                 : (double)(sg_a * (long long)S0 + sg_b * (long long)M2) * sg_scale;
         }
         // the 2 * half edge outputs of the segment (polynomial fit of its first / last sg_w adjusted
         // values), one thread each so the table loads of different outputs overlap
@@ -783,7 +801,14 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
             ystage[j - t0] = acc;
         }
         __syncthreads();
-        for (int k = tid; k < n_t; k += kRankThreads) dst[k] = ystage[k];
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {       // 16-byte stores (ystage is 16-byte aligned)
+            const int n2 = n_t >> 1;
+            for (int k = tid; k < n2; k += kRankThreads)
+                reinterpret_cast<double2 *>(dst)[k] = reinterpret_cast<const double2 *>(ystage)[k];
+            if ((n_t & 1) && tid == 0) dst[n_t - 1] = ystage[n_t - 1];
+        } else {
+            for (int k = tid; k < n_t; k += kRankThreads) dst[k] = ystage[k];
+        }
         return;
     }
     double *__restrict__ stage = reinterpret_cast<double *>(B) + warp * (128 + 8);   // per-warp 128 outputs, padded

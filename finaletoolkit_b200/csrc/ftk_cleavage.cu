@@ -53,17 +53,18 @@ cleavage_tile_kernel(const int32_t *__restrict__ frag_start, const int32_t *__re
         reinterpret_cast<int4 *>(E)[i] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();
+    const uint32_t d_addr = smem_addr_once(D), e_addr = smem_addr_once(E);
     auto visit = [&](int fs, int fe, int q, int sd) {
         const int L = fe - fs;
         // frag_array(..., "any") of the INTERVAL: tabix overlap + mapq + inclusive length window
         if (q < min_mapq || L < 0 || !frag_len_ok(L, min_len, max_len) || !(fe > ivl_lo && fs < ivl_hi)) return;
         const int s_idx = fs - p0, e_idx = fe - p0;
         if (e_idx > 0 && s_idx < len) {                 // covers at least one tile position
-            atomicAdd(&D[max(s_idx, 0)], 1);
-            if (e_idx < len) atomicAdd(&D[e_idx], -1);
+            red_shared_inc(d_addr + 4u * (unsigned)max(s_idx, 0));
+            if (e_idx < len) red_shared_add(d_addr + 4u * (unsigned)e_idx, -1);
         }
         const int end_idx = sd ? s_idx : e_idx;
-        if (end_idx >= 0 && end_idx < len) atomicAdd(&E[end_idx], 1);
+        if (end_idx >= 0 && end_idx < len) red_shared_inc(e_addr + 4u * (unsigned)end_idx);
     };
     // the candidate slice is widened to a 16-byte boundary on the left (extra fragments are harmless:
     // the range is only a superset) so every lane streams 4 fragments per 128-bit load

@@ -46,6 +46,26 @@ __device__ __forceinline__ void st_stream4(int4 *p, const int4 &v) {
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// Shared-memory atomics through an explicit 32-bit shared-window address.  For atomicAdd(&smem[i], v) on
+// a static __shared__ array nvcc (12.9, sm_100a) re-derives the array's window address next to every
+// atomic in an unrolled loop (S2R SR_CgaCtaId + LEA per atomic); computing it once, hiding it behind an
+// opaque move and issuing red.shared on it keeps the hot loops free of special-register reads.
+__device__ __forceinline__ uint32_t smem_addr_once(const void *p) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    uint32_t r;
+    asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void red_shared_add(uint32_t addr, int v) {
+    asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_shared_inc(uint32_t addr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory");
+}
+__device__ __forceinline__ void red_shared_min(uint32_t addr, int v) {
+    asm volatile("red.shared.min.s32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+
 // first index i in [0, n) with a[i] >= key (a ascending); n if none
 __device__ __forceinline__ int64_t lower_bound(const int32_t *__restrict__ a, int64_t n, int64_t key) {
     int64_t lo = 0, hi = n;

@@ -108,14 +108,15 @@ interval_hist_kernel(const int32_t *__restrict__ frag_start, const int32_t *__re
 
     const Stream in_stream(S, E, pred);
     unsigned my_count32 = 0;  // a CTA slice never holds 2^32 fragments (n_frag <= INT32_MAX)
+    const uint32_t cnt_addr = HIST ? smem_addr_once(s_cnt) : 0u, first_addr = HIST ? smem_addr_once(s_first) : 0u;
     auto visit = [&](int fs, int fe, int q, int idx) {
         if (!in_stream(fs, fe, q)) return;
         ++my_count32;
         if (HIST) {
             const int L = fe - fs;
             if (L < kHistSmemBins) {
-                atomicAdd(&s_cnt[L], 1);
-                if (want_first) atomicMin(&s_first[L], idx);
+                red_shared_inc(cnt_addr + 4u * (unsigned)L);
+                if (want_first) red_shared_min(first_addr + 4u * (unsigned)L, idx);
             } else if (L < n_bins) {
                 atomicAdd(&hist[row * n_bins + L], 1ull);
                 if (want_first) atomicMin(&first_seen[row * n_bins + L], idx);
@@ -241,14 +242,15 @@ interval_count_warp_kernel(const int32_t *__restrict__ frag_start, const int32_t
         const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(frag_stop + lo_al);
         const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(frag_mapq ? frag_mapq + lo_al : nullptr);
         unsigned c = 0;
+        const uint32_t cnt_addr = PHIST ? smem_addr_once(s_cnt) : 0u, first_addr = PHIST ? smem_addr_once(s_first) : 0u;
         auto visit = [&](int fs, int fe, int q, int idx, bool masked) {
             if (masked || !in_stream(fs, fe, q)) return;
             ++c;
             if (PHIST) {
                 const int L = fe - fs;
                 if (L < kHistSmemBins) {
-                    atomicAdd(&s_cnt[L], 1);
-                    if (want_first) atomicMin(&s_first[L], idx);
+                    red_shared_inc(cnt_addr + 4u * (unsigned)L);
+                    if (want_first) red_shared_min(first_addr + 4u * (unsigned)L, idx);
                 } else if (L < n_bins) {
                     atomicAdd(&hist[L], 1ull);
                     if (want_first) atomicMin(&first_seen[L], idx);

@@ -101,8 +101,10 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
     // (Bank-interleaved replicas of the histograms - 4 / 8 / 16 copies, lane l bumping copy l % copies -
     // were measured: no change.  The cost is the shared-memory atomic unit itself, ~3 lane-atomics per
     // cycle and SM whether the lanes collide or not: 2 atomics x 72 M counted fragments = 0.17 ms.)
-    constexpr int kCopies = 1;
-    __shared__ int s_cnt[SMEM ? (K ? (2 << (2 * K)) * kCopies : 2 * kMotifSmemBins) : 1];
+    // kDual: forward k-mers in their own histogram under the raw window bits, re-indexed at the flush (saves the
+    // digit reversal per fragment; only worth it while zeroing + flushing two histograms per CTA is cheap)
+    constexpr bool kDual = SMEM && K >= 1 && K <= 5;
+    __shared__ int s_cnt[SMEM ? (K ? ((kDual ? 2 : 1) << (2 * K)) : kMotifSmemBins) : 1];
     const int tid = threadIdx.x;
     MotifK<K> KK{k};
     const int n_bins = 1 << (2 * KK.k());
@@ -164,7 +166,7 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
         } else {
             acc = 1u;
         }
-        if (SMEM) for (int b = tid; b < 2 * n_bins * kCopies; b += kMotifThreads) s_cnt[b] = 0;
+        if (SMEM) for (int b = tid; b < (kDual ? 2 : 1) * n_bins; b += kMotifThreads) s_cnt[b] = 0;
         any_n = __syncthreads_or(acc != 0u);
     }
 
@@ -176,17 +178,16 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
         const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(s_cnt));
         asm volatile("mov.b32 %0, %1;" : "=r"(s_base) : "r"(a));
     }
-    const uint32_t s_rev_off = (uint32_t)n_bins * 4u;      // in units of bins x 4 (scaled by kCopies in bump_s)
-    const uint32_t lane_off = (kCopies > 1) ? (uint32_t)(tid & (kCopies - 1)) * 4u : 0u;
+    const uint32_t s_rev_off = kDual ? (uint32_t)n_bins * 4u : 0u;
     auto bump_s = [&](uint32_t byte_off) {
-        asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(s_base + byte_off * kCopies + lane_off) : "memory");
+        asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(s_base + byte_off) : "memory");
     };
     auto stream = [&](auto ncheck_tag) {
         constexpr bool NCHECK = decltype(ncheck_tag)::value;
         auto fwd = [&](int pos) {      // k-mer read 5'->3' on the forward strand starting at pos
             if (NCHECK && has_n(nmask, pos, maskk)) return;
             const uint32_t wbits = window2(seq, pos, mask2k);
-            if (SMEM) bump_s(wbits << 2);
+            if (SMEM) bump_s((kDual ? wbits : digit_reverse(wbits, kk)) << 2);
             else atomicAdd(&row[digit_reverse(wbits, kk)], 1ull);
         };
         auto rev = [&](int pos) {      // reverse complement of ref[pos, pos + k)
@@ -269,7 +270,7 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
             for (int i = 0; i < 4; ++i) {
                 if (f_ok[i]) {
                     const uint32_t wbits = __funnelshift_r(f_lo[i], f_hi[i], pf[i] << 1) & mask2k;
-                    if (SMEM) bump_s(wbits << 2);
+                    if (SMEM) bump_s((kDual ? wbits : digit_reverse(wbits, kk)) << 2);
                     else atomicAdd(&row[digit_reverse(wbits, kk)], 1ull);
                 }
                 if (r_ok[i]) {
@@ -308,13 +309,11 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
     if (SMEM) {
         __syncthreads();
         for (int b = tid; b < n_bins; b += kMotifThreads) {
-            int cf = 0, cr = 0;
-#pragma unroll
-            for (int c = 0; c < kCopies; ++c) {
-                cf += s_cnt[b * kCopies + c];
-                cr += s_cnt[(n_bins + b) * kCopies + c];
+            const int cr = s_cnt[(kDual ? n_bins : 0) + b];
+            if (kDual) {
+                const int cf = s_cnt[b];
+                if (cf) atomicAdd(&row[digit_reverse((uint32_t)b, KK.k())], (unsigned long long)cf);
             }
-            if (cf) atomicAdd(&row[digit_reverse((uint32_t)b, KK.k())], (unsigned long long)cf);
             if (cr) atomicAdd(&row[b], (unsigned long long)cr);
         }
     }

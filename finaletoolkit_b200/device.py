@@ -600,7 +600,8 @@ def savgol_rational(window: int, degree: int):
     return a, b, den
 
 
-_RANK_T_MAX = 4096          # outputs per tile of the rank-bitmap kernel
+import os as _os
+_RANK_T_MAX = int(_os.environ.get("FTK_RANK_T_MAX", 4096))          # outputs per tile of the rank-bitmap kernel
 _RANK_SMEM_MAX = 227 * 1024
 
 

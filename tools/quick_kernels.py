@@ -50,6 +50,11 @@ if "delfi" in what:
 if "cleavage" in what:
     edges = np.arange(0, CLEN + 5000, 5000, dtype=np.int64).clip(max=CLEN)
     timed("cleavage", lambda: D.cleavage_intervals(fr, edges[:-1], edges[1:], CLEN, None, None, 30), 10 * N + 8 * CLEN)
+if "hist" in what:
+    edges = np.arange(0, CLEN + 5000, 5000, dtype=np.int64).clip(max=CLEN)
+    timed("coverage counts (5-kb intervals)", lambda: D.interval_hist(fr, edges[:-1], edges[1:], "midpoint", None, None, 30), 9 * N)
+    timed("coverage counts + pooled length histogram", lambda: D.interval_hist(fr, edges[:-1], edges[1:], "midpoint", None, None, 30, n_bins=601, pooled="hist"), 9 * N)
+    timed("per-interval length histograms (frag_length_intervals)", lambda: D.interval_hist(fr, edges[:-1], edges[1:], "midpoint", None, None, 30, n_bins=601, first_seen=True), 9 * N)
 if "adjust" in what:
     edges = np.arange(0, CLEN + 5000, 5000, dtype=np.int64).clip(max=CLEN)
     plan = D.WpsPlan(edges[:-1], edges[1:], CLEN, 180, dev)
