@@ -30,8 +30,8 @@ SYMBOLS = {
     "ftk_error_string": (c_char_p, [c_int]),
     "ftk_last_cuda_error": (c_char_p, []),
     "ftk_pack_fragments_host": (c_int64, [_i32p, _i32p, _u8p, _u8p, c_int64, c_int32, _u32p, _i32p,
-                                          _i32p, _i32p, _u8p, _u8p, c_int64]),
-    "ftk_unpack_fragments": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
+                                          _i32p, _i32p, _u8p, _u8p, c_int64, c_int32]),
+    "ftk_unpack_fragments": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, c_int32, _P]),
     "ftk_length_stats_host": (c_int, [_i32p, _i32p, c_int64, c_int32, c_int32, c_int32, _f64p, _f64p, _f64p,
                                       _i64p, _i64p, _i64p, _f64p]),
     "ftk_wps_plan_tiles": (c_int64, [_i64p, _i64p, _i64p, c_int64, c_int64, c_int32,

@@ -17,6 +17,12 @@
 // 720-800 MB); escapes cost 10 B per fragment of the affected block only.  Lossless: unpacking
 // reproduces start / stop / mapq / strand bit for bit (tests/test_gpu_pack.py).
 //
+// record_bytes = 3 is the narrow variant of the same scheme for deep, short-fragment data (cfDNA at
+// >= ~5x): 24-bit records  dstart (6 bits) | length << 6 (9 bits) | strand << 15 | mapq << 16,
+// 48 words per block = 3.0625 B per fragment (chr1 at 30x: 245 MB).  A block with a gap >= 64 bp or
+// a fragment >= 512 bp escapes to the raw columns exactly like above; the packer reports how many
+// do, so the caller can pick the width that puts fewer bytes on the wire (packed.py does).
+//
 // ftk_pack_fragments_host : host, multi-threaded (the decoder side)
 // ftk_unpack_fragments    : device; one warp per block, two fragments per lane, shuffle prefix sum
 //                           of the start deltas, coalesced 8-byte stores.  HBM-bound:
@@ -33,7 +39,11 @@ constexpr int kPackBlock = FTK_PACK_BLOCK;
 static_assert(kPackBlock == 64, "one warp unpacks a block as 32 lanes x 2 fragments");
 constexpr uint32_t kDeltaBits = 11, kLenBits = 12;
 constexpr uint32_t kDeltaMax = (1u << kDeltaBits) - 1, kLenMax = (1u << kLenBits) - 1;
+constexpr uint32_t kDeltaBits3 = 6, kLenBits3 = 9;
+constexpr uint32_t kDeltaMax3 = (1u << kDeltaBits3) - 1, kLenMax3 = (1u << kLenBits3) - 1;
+constexpr int kWordsPerBlock3 = kPackBlock * 3 / 4;      // 48
 
+template <int RB>
 __global__ void __launch_bounds__(256)
 unpack_fragments_kernel(const uint2 *__restrict__ words, const int32_t *__restrict__ anchors,
                         const int32_t *__restrict__ raw_start, const int32_t *__restrict__ raw_stop,
@@ -48,7 +58,27 @@ unpack_fragments_kernel(const uint2 *__restrict__ words, const int32_t *__restri
         const int64_t i0 = b * kPackBlock + 2 * lane;      // this lane's two fragments
         int s0, s1, e0, e1;
         unsigned q0, q1, d0, d1;
-        if (anchor >= 0) {
+        if (anchor >= 0 && RB == 3) {
+            // the lane's two 24-bit records are bytes [6 lane, 6 lane + 6) of the block: two words
+            const uint32_t *__restrict__ w32 = reinterpret_cast<const uint32_t *>(words) + b * kWordsPerBlock3;
+            const int wi = (6 * lane) >> 2;
+            const unsigned long long both = ((unsigned long long)__ldcs(w32 + wi + 1) << 32) | __ldcs(w32 + wi);
+            const unsigned long long v = both >> (((6 * lane) & 3) * 8);
+            const uint32_t r0 = (uint32_t)v & 0xffffffu, r1 = (uint32_t)(v >> 24) & 0xffffffu;
+            const int dx = (int)(r0 & kDeltaMax3), dy = (int)(r1 & kDeltaMax3);
+            int t = dx + dy;                                 // inclusive scan of the pair sums
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, t, off);
+                if (lane >= off) t += u;
+            }
+            s1 = anchor + t;
+            s0 = s1 - dy;
+            e0 = s0 + (int)((r0 >> kDeltaBits3) & kLenMax3);
+            e1 = s1 + (int)((r1 >> kDeltaBits3) & kLenMax3);
+            d0 = (r0 >> 15) & 1u; d1 = (r1 >> 15) & 1u;
+            q0 = r0 >> 16; q1 = r1 >> 16;
+        } else if (anchor >= 0) {
             const uint2 w = __ldcs(words + b * (kPackBlock / 2) + lane);
             const int dx = (int)(w.x & kDeltaMax), dy = (int)(w.y & kDeltaMax);
             int t = dx + dy;                                 // inclusive scan of the pair sums
@@ -84,14 +114,15 @@ unpack_fragments_kernel(const uint2 *__restrict__ words, const int32_t *__restri
 }
 
 // true when the 64 rows [i0, i1) fit the packed fields
-static bool block_fits(const int32_t *start, const int32_t *stop, int64_t i0, int64_t i1) {
+static bool block_fits(const int32_t *start, const int32_t *stop, int64_t i0, int64_t i1, int64_t len_max,
+                       int64_t delta_max) {
     if (start[i0] < 0) return false;
     for (int64_t i = i0; i < i1; ++i) {
         const int64_t len = (int64_t)stop[i] - start[i];
-        if (len < 0 || len > kLenMax) return false;
+        if (len < 0 || len > len_max) return false;
         if (i > i0) {
             const int64_t d = (int64_t)start[i] - start[i - 1];
-            if (d < 0 || d > kDeltaMax) return false;
+            if (d < 0 || d > delta_max) return false;
         }
     }
     return true;
@@ -105,8 +136,11 @@ extern "C" int64_t ftk_pack_fragments_host(const int32_t *start, const int32_t *
                                            const uint8_t *strand, int64_t n, int32_t threads,
                                            uint32_t *words, int32_t *anchors,
                                            int32_t *raw_start, int32_t *raw_stop, uint8_t *raw_mapq,
-                                           uint8_t *raw_strand, int64_t raw_capacity_blocks) {
+                                           uint8_t *raw_strand, int64_t raw_capacity_blocks, int32_t record_bytes) {
     if (n < 0 || (n > 0 && (!start || !stop))) return FTK_E_INVALID;
+    if (record_bytes != 3 && record_bytes != 4) return FTK_E_INVALID;
+    const bool narrow = record_bytes == 3;
+    const int64_t len_max = narrow ? kLenMax3 : kLenMax, delta_max = narrow ? kDeltaMax3 : kDeltaMax;
     const int64_t n_blocks = (n + kPackBlock - 1) / kPackBlock;
     if (n_blocks == 0) return 0;
     int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
@@ -125,7 +159,7 @@ extern "C" int64_t ftk_pack_fragments_host(const int32_t *start, const int32_t *
     for_blocks([&](int64_t b0, int64_t b1) {
         for (int64_t b = b0; b < b1; ++b) {
             const int64_t i0 = b * kPackBlock, i1 = std::min<int64_t>(n, i0 + kPackBlock);
-            is_raw[(size_t)b] = block_fits(start, stop, i0, i1) ? 0 : 1;
+            is_raw[(size_t)b] = block_fits(start, stop, i0, i1, len_max, delta_max) ? 0 : 1;
         }
     });
     std::vector<int64_t> raw_index((size_t)n_blocks);
@@ -139,7 +173,24 @@ extern "C" int64_t ftk_pack_fragments_host(const int32_t *start, const int32_t *
     for_blocks([&](int64_t b0, int64_t b1) {
         for (int64_t b = b0; b < b1; ++b) {
             const int64_t i0 = b * kPackBlock, i1 = std::min<int64_t>(n, i0 + kPackBlock);
-            uint32_t *w = words + i0;
+            if (narrow) {
+                uint8_t *w8 = reinterpret_cast<uint8_t *>(words) + i0 * 3;
+                std::fill(w8, w8 + kPackBlock * 3, (uint8_t)0);
+                if (!is_raw[(size_t)b]) {
+                    anchors[b] = start[i0];
+                    for (int64_t i = i0; i < i1; ++i) {
+                        const uint32_t d = (i > i0) ? (uint32_t)(start[i] - start[i - 1]) : 0u;
+                        const uint32_t len = (uint32_t)(stop[i] - start[i]);
+                        const uint32_t q = mapq ? mapq[i] : 255u;
+                        const uint32_t sd = strand ? (strand[i] & 1u) : 0u;
+                        const uint32_t rec = d | (len << kDeltaBits3) | (sd << 15) | (q << 16);
+                        uint8_t *r8 = w8 + (i - i0) * 3;
+                        r8[0] = (uint8_t)rec; r8[1] = (uint8_t)(rec >> 8); r8[2] = (uint8_t)(rec >> 16);
+                    }
+                    continue;
+                }
+            }
+            uint32_t *w = narrow ? nullptr : words + i0;
             if (!is_raw[(size_t)b]) {
                 anchors[b] = start[i0];
                 for (int64_t i = i0; i < i1; ++i) {
@@ -155,7 +206,7 @@ extern "C" int64_t ftk_pack_fragments_host(const int32_t *start, const int32_t *
                 anchors[b] = (int32_t)(-1 - r);
                 for (int64_t i = i0; i < i0 + kPackBlock; ++i) {
                     const int64_t k = r * kPackBlock + (i - i0);
-                    w[i - i0] = 0u;
+                    if (w) w[i - i0] = 0u;
                     const bool live = i < i1;
                     raw_start[k] = live ? start[i] : 0;
                     raw_stop[k] = live ? stop[i] : 0;
@@ -172,8 +223,9 @@ extern "C" int ftk_unpack_fragments(const uint32_t *words, const int32_t *anchor
                                     const int32_t *raw_start, const int32_t *raw_stop,
                                     const uint8_t *raw_mapq, const uint8_t *raw_strand, int64_t n_raw_blocks,
                                     int64_t n, int32_t *start, int32_t *stop, uint8_t *mapq, uint8_t *strand,
-                                    ftk_stream_t stream_) {
+                                    int32_t record_bytes, ftk_stream_t stream_) {
     if (n == 0) return FTK_OK;
+    if (record_bytes != 3 && record_bytes != 4) return FTK_E_INVALID;
     if (n < 0 || n_raw_blocks < 0 || !words || !anchors || !start || !stop) return FTK_E_INVALID;
     if (n_raw_blocks > 0 && (!raw_start || !raw_stop || !raw_mapq)) return FTK_E_INVALID;
     // two-fragment stores need 8-byte aligned int32 outputs and 2-byte aligned byte outputs
@@ -184,9 +236,14 @@ extern "C" int ftk_unpack_fragments(const uint32_t *words, const int32_t *anchor
     const int64_t n_blocks = (n + kPackBlock - 1) / kPackBlock;
     const int64_t ctas = (n_blocks + 7) / 8;                   // 8 warps = 8 blocks per CTA
     const unsigned grid = (unsigned)std::min<int64_t>(ctas, (int64_t)kNumSMs * 32);
-    unpack_fragments_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-        reinterpret_cast<const uint2 *>(words), anchors, raw_start, raw_stop, raw_mapq, raw_strand, n, n_blocks,
-        start, stop, mapq, strand);
+    if (record_bytes == 3)
+        unpack_fragments_kernel<3><<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+            reinterpret_cast<const uint2 *>(words), anchors, raw_start, raw_stop, raw_mapq, raw_strand, n, n_blocks,
+            start, stop, mapq, strand);
+    else
+        unpack_fragments_kernel<4><<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+            reinterpret_cast<const uint2 *>(words), anchors, raw_start, raw_stop, raw_mapq, raw_strand, n, n_blocks,
+            start, stop, mapq, strand);
     FTK_CHECK_LAUNCH("unpack_fragments_kernel");
     return FTK_OK;
 }

@@ -137,12 +137,12 @@ def genome_delfi_windows(table, ref, bins_by_contig, blacklist_by_contig=None, g
 class ContigWps:
     """Per-contig result of ``multi_wps_genome`` on the rank that owns the contig (device tensors)."""
 
-    __slots__ = ("contig", "starts", "stops", "offsets", "wps", "cov", "adjusted", "adj_offsets", "adj_segments")
+    __slots__ = ("contig", "starts", "stops", "offsets", "wps", "cov", "adjusted", "adj_offsets", "adj_segments", "flags")
 
     def __init__(self, contig, starts, stops, offsets, wps, cov=None):
         self.contig, self.starts, self.stops, self.offsets = contig, starts, stops, offsets
         self.wps, self.cov = wps, cov
-        self.adjusted = self.adj_offsets = self.adj_segments = None
+        self.adjusted = self.adj_offsets = self.adj_segments = self.flags = None
 
 
 def tile_genome(chrom_sizes, interval_size: int = 5000) -> dict:
@@ -305,7 +305,7 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
                      min_length=120, max_length=180, quality_threshold=30, coverage=False, length_hist=False,
                      adjust: dict | None = None, ctx: DistContext | None = None, device=None,
                      contigs: list | None = None, reduce: bool = True, plans: dict | None = None,
-                     keep_adjusted: bool = True, n_bins: int | None = None):
+                     keep_adjusted: bool = True, n_bins: int | None = None, sync: bool = True):
     """Genome-wide L-WPS over the ranks of one box (reference drivers frag/_multi_wps.py:152-198 +,
     with ``adjust``, frag/_adjust_wps.py:229-291) - contigs LPT-sharded, every rank sweeps the contigs
     it owns, results stay on the owning rank's GPU, no data-path collective.
@@ -327,7 +327,10 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
     first call, reused afterwards: same table, sites, contigs and max_length) - the returned tensors
     are then VIEWS into the shard's buffers, valid until the next call with the same ``plans``;
     ``contigs``: override the LPT assignment; ``reduce=False`` skips the collectives (single-rank
-    checks inside a multi-rank job); ``keep_adjusted=False`` returns no adjusted series (timing runs).
+    checks inside a multi-rank job); ``keep_adjusted=False`` returns no adjusted series (timing runs);
+    ``sync=False``: the coverage total comes back as a one-element device tensor instead of an ``int`` and the
+    rank kernel's tile flags are not looked at (``results[c].flags`` holds them) - nothing in the call waits
+    for the GPU, so back-to-back passes overlap their host work with the previous pass' kernels.
 
     Returns ``(results {contig: ContigWps} of this rank, hist int64[n_bins] | None, total | None)``.
     """
@@ -380,7 +383,7 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
                     flags.append((g, ap, flag.any()))
                 else:
                     g.adjusted[: ap.n_total] = adjust_segments(g.wps, None, plan=ap, **adjust)[0]
-    if flags and bool(t.stack([f for _, _, f in flags]).any().item()):
+    if flags and sync and bool(t.stack([f for _, _, f in flags]).any().item()):
         # a tile the rank kernel could not take (cannot happen for integer WPS of ordinary depth):
         # redo those groups on the general path
         for g, ap, f in flags:
@@ -394,7 +397,12 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
         if reduce:
             ctx.all_reduce_sum(packed)
     hist = packed[1:] if n_bins else None
-    return shard.results(fused, adjust, keep_adjusted), hist, (int(packed[0].item()) if fused else None)
+    res = shard.results(fused, adjust, keep_adjusted)
+    if not sync:
+        for r in res.values():
+            r.flags = [f for _, _, f in flags]
+        return res, hist, (packed[:1] if fused else None)
+    return res, hist, (int(packed[0].item()) if fused else None)
 
 
 def adjust_wps_genome(results: dict, **adjust):

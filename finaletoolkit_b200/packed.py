@@ -1,4 +1,4 @@
-"""Packed fragment columns: what the host decoder hands to the GPU (4.06 B per fragment).
+"""Packed fragment columns: what the host decoder hands to the GPU (3.06 or 4.06 B per fragment).
 
 Layout and rationale: ``csrc/ftk_pack.cu`` / ``include/ftk_b200.h``.  The host side packs once per
 contig (``ftk_pack_fragments_host``, multi-threaded, at decode time); the device side unpacks a
@@ -27,7 +27,8 @@ def _p(a, ctype):
 class PackedFragments:
     """Start-sorted fragments of one contig in the packed wire format, in (pinned) host memory."""
 
-    def __init__(self, start, stop, mapq=None, strand=None, pinned=True, threads=0, max_len=None):
+    def __init__(self, start, stop, mapq=None, strand=None, pinned=True, threads=0, max_len=None,
+                 record_bytes=None):
         t = torch()
         start = np.ascontiguousarray(start, dtype=np.int32)
         stop = np.ascontiguousarray(stop, dtype=np.int32)
@@ -46,15 +47,24 @@ class PackedFragments:
         self.n_blocks = (self.n + PACK_BLOCK - 1) // PACK_BLOCK
         L = lib()
         args = (_p(start, c_int32), _p(stop, c_int32), _p(mapq, c_uint8), _p(strand, c_uint8), self.n, int(threads))
-        n_raw = L.ftk_pack_fragments_host(*args, None, None, None, None, None, None, 0)
-        check(n_raw, "ftk_pack_fragments_host")
-        self.n_raw = int(n_raw)
+        # record width: the narrow 24-bit records unless their escapes (gaps >= 64 bp, fragments >= 512 bp)
+        # would put more bytes on the wire than the 32-bit records (sparse or long-fragment data)
+        widths = (3, 4) if record_bytes is None else (int(record_bytes),)
+        best = None
+        for rb in widths:
+            n_raw = L.ftk_pack_fragments_host(*args, None, None, None, None, None, None, 0, rb)
+            check(n_raw, "ftk_pack_fragments_host")
+            cost = self.n_blocks * (PACK_BLOCK * rb + 4) + int(n_raw) * PACK_BLOCK * 10
+            if best is None or cost < best[0]:
+                best = (cost, rb, int(n_raw))
+        _, self.record_bytes, self.n_raw = best
+        self.words_per_block = PACK_BLOCK * self.record_bytes // 4
 
         def host(shape, dtype):
             x = t.empty(shape, dtype=dtype)
             return x.pin_memory() if (pinned and t.cuda.is_available() and x.numel()) else x
 
-        self.words = host(max(self.n_blocks * PACK_BLOCK, 2), t.int32)       # uint32 bit patterns
+        self.words = host(max(self.n_blocks * self.words_per_block, 2), t.int32)       # record bit patterns
         self.anchors = host(max(self.n_blocks, 1), t.int32)
         r = max(self.n_raw, 1) * PACK_BLOCK
         self.raw_start, self.raw_stop = host(r, t.int32), host(r, t.int32)
@@ -63,7 +73,7 @@ class PackedFragments:
             got = L.ftk_pack_fragments_host(
                 *args, _p(self.words.numpy().view(np.uint32), c_uint32), _p(self.anchors.numpy(), c_int32),
                 _p(self.raw_start.numpy(), c_int32), _p(self.raw_stop.numpy(), c_int32),
-                _p(self.raw_mapq.numpy(), c_uint8), _p(self.raw_strand.numpy(), c_uint8), self.n_raw)
+                _p(self.raw_mapq.numpy(), c_uint8), _p(self.raw_strand.numpy(), c_uint8), self.n_raw, self.record_bytes)
             check(got, "ftk_pack_fragments_host")
         self.first_start = start[::PACK_BLOCK].copy()    # block -> first start (host-side slicing by position)
 
@@ -71,7 +81,7 @@ class PackedFragments:
     def wire_bytes(self, f0=0, f1=None) -> int:
         f1 = self.n if f1 is None else f1
         nb = (f1 - f0 + PACK_BLOCK - 1) // PACK_BLOCK
-        return nb * PACK_BLOCK * 4 + nb * 4
+        return nb * PACK_BLOCK * self.record_bytes + nb * 4
 
     def raw_bytes(self) -> int:
         return self.n_raw * PACK_BLOCK * 10
@@ -88,7 +98,7 @@ class PackedFragments:
             d_words.data_ptr(), d_anchors.data_ptr(), d_raw[0].data_ptr(), d_raw[1].data_ptr(), d_raw[2].data_ptr(),
             d_raw[3].data_ptr() if self.has_strand else 0, self.n_raw, int(n), d_start.data_ptr(), d_stop.data_ptr(),
             0 if d_mapq is None else d_mapq.data_ptr(), 0 if d_strand is None else d_strand.data_ptr(),
-            _stream_ptr(device)), "ftk_unpack_fragments")
+            self.record_bytes, _stream_ptr(device)), "ftk_unpack_fragments")
 
     def to_device(self, device=None, contig=None) -> ContigFragments:
         """H2D of the packed columns + on-device unpack -> resident ``ContigFragments``."""

@@ -101,7 +101,8 @@ class StreamedContig:
         self.d_stop = [t.empty(max_f, dtype=t.int32, device=self.device) for _ in range(2)]
         self.d_mapq = [t.empty(max_f, dtype=t.uint8, device=self.device) for _ in range(2)]
         if packed is not None:
-            self.d_words = [t.empty(max_f, dtype=t.int32, device=self.device) for _ in range(2)]
+            self.d_words = [t.empty(max_f // PACK_BLOCK * packed.words_per_block, dtype=t.int32, device=self.device)
+                            for _ in range(2)]
             self.d_anchors = [t.empty(max_f // PACK_BLOCK, dtype=t.int32, device=self.device) for _ in range(2)]
             self.d_raw = packed.raw_to_device(self.device)
         self.d_out = [t.empty(max_p, dtype=wire, device=self.device) for _ in range(2)]
@@ -124,6 +125,13 @@ class StreamedContig:
             self.h2d_bytes = sum(packed.wire_bytes(c["f0"], c["f1"]) for c in self.chunks) + packed.raw_bytes()
         self.d2h_bytes = self.n_positions * (2 if wps_dtype == "int16" else 1) + n_ivl * 8 + self.n_bins * 8 + 4
         self.kernel_launches = 0
+        # The pass is a fixed DAG of copies and kernels over fixed buffers: after one eager pass it is
+        # captured as a CUDA graph and replayed (no per-chunk host work, no launch gaps between the ~10 nodes
+        # of a chunk).  FTK_PIPE_GRAPH=0 keeps the eager three-stream form.
+        import os
+        self.use_graph = os.environ.get("FTK_PIPE_GRAPH", "1") != "0"
+        self._graph = None
+        self._warm = False
 
     def _stage_in(self, c, b):
         """H2D of chunk c's fragment slice into staging set b (on s_in)."""
@@ -138,11 +146,34 @@ class StreamedContig:
         else:
             nb = (nf + PACK_BLOCK - 1) // PACK_BLOCK
             b0 = f0 // PACK_BLOCK
-            self.d_words[b][: nb * PACK_BLOCK].copy_(self.packed.words[f0: f0 + nb * PACK_BLOCK], non_blocking=True)
+            wpb = self.packed.words_per_block
+            self.d_words[b][: nb * wpb].copy_(self.packed.words[b0 * wpb: (b0 + nb) * wpb], non_blocking=True)
             self.d_anchors[b][:nb].copy_(self.packed.anchors[b0: b0 + nb], non_blocking=True)
 
     def run(self):
         """One end-to-end pass; returns after every result is in the pinned host buffers."""
+        t = torch()
+        if self.use_graph and self._warm:
+            if self._graph is None:
+                g = t.cuda.CUDAGraph()
+                cap = t.cuda.Stream(self.device)
+                cap.wait_stream(t.cuda.current_stream(self.device))
+                with t.cuda.graph(g, stream=cap):
+                    self._enqueue()
+                self._graph = g
+            self._graph.replay()
+        else:
+            self._enqueue()
+            self._warm = True
+        t.cuda.current_stream(self.device).synchronize()
+        if int(self.h_flag[0]):
+            raise OverflowError(f"WPS does not fit {self.wps_dtype} on this input; rerun with "
+                                + ("wps_dtype='int16'" if self.wps_dtype == "int8" else "the int32 path (WpsPlan.run)"))
+        self.h_total[0] = int(self.h_cov[: self.n_ivl].sum()) if self.n_ivl else 0
+        return self.h_wps, self.h_cov, self.h_hist, self.h_total
+
+    def _enqueue(self):
+        """Put one pass on the streams (no host synchronisation; capturable)."""
         t = torch()
         W, lo, hi, q = self.params
         c_lo, c_hi, c_q = self.cov_params
@@ -207,10 +238,5 @@ class StreamedContig:
             self.h_flag.copy_(self.d_flag, non_blocking=True)
         cur.wait_stream(self.s_out)
         cur.wait_stream(self.s_in)
-        cur.synchronize()
+        cur.wait_stream(self.s_comp)
         self.kernel_launches = launches
-        if int(self.h_flag[0]):
-            raise OverflowError(f"WPS does not fit {self.wps_dtype} on this input; rerun with "
-                                + ("wps_dtype='int16'" if self.wps_dtype == "int8" else "the int32 path (WpsPlan.run)"))
-        self.h_total[0] = int(self.h_cov[: self.n_ivl].sum()) if self.n_ivl else 0
-        return self.h_wps, self.h_cov, self.h_hist, self.h_total

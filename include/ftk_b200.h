@@ -66,14 +66,18 @@ const char *ftk_last_cuda_error(void);
  * words holds n_blocks * FTK_PACK_BLOCK entries (zero padded), n_blocks = ceil(n / FTK_PACK_BLOCK). */
 #define FTK_PACK_BLOCK 64
 
-/* Host (decoder side), multi-threaded (threads <= 0: all cores).  Returns the number of raw blocks.
+/* record_bytes = 4: the 32-bit records above (words: 64 per block).  record_bytes = 3: 24-bit records
+ * dstart (6 bits) | length << 6 (9 bits) | strand << 15 | mapq << 16, stored back to back (48 words per
+ * block, 3.0625 B per fragment); a block with a gap >= 64 bp or a fragment >= 512 bp escapes to the raw
+ * columns.  Same anchors, same raw columns, same losslessness.
+ * Host (decoder side), multi-threaded (threads <= 0: all cores).  Returns the number of raw blocks.
  * With words_host == NULL only counts them (so the caller can size the raw columns);
  * FTK_E_RANGE if raw_capacity_blocks is too small.  mapq_host / strand_host may be NULL (255 / 0). */
 int64_t ftk_pack_fragments_host(const int32_t *start_host, const int32_t *stop_host, const uint8_t *mapq_host,
                                 const uint8_t *strand_host, int64_t n, int32_t threads,
                                 uint32_t *words_host, int32_t *anchors_host,
                                 int32_t *raw_start_host, int32_t *raw_stop_host, uint8_t *raw_mapq_host,
-                                uint8_t *raw_strand_host, int64_t raw_capacity_blocks);
+                                uint8_t *raw_strand_host, int64_t raw_capacity_blocks, int32_t record_bytes);
 
 /* Device: words / anchors (of the first block to unpack; a slice of a contig may start at any block
  * boundary) + the contig's raw columns -> int32 start / stop, uint8 mapq / strand (either may be NULL)
@@ -82,7 +86,7 @@ int ftk_unpack_fragments(const uint32_t *words_dev, const int32_t *anchors_dev,
                          const int32_t *raw_start_dev, const int32_t *raw_stop_dev,
                          const uint8_t *raw_mapq_dev, const uint8_t *raw_strand_dev, int64_t n_raw_blocks,
                          int64_t n, int32_t *start_dev, int32_t *stop_dev, uint8_t *mapq_dev, uint8_t *strand_dev,
-                         ftk_stream_t stream);
+                         int32_t record_bytes, ftk_stream_t stream);
 
 /* ------------------------------------------------- per-interval length statistics (host)
  * frag_length_intervals' statistics (frag/_frag_length.py:156-172, :204-238) for n_rows intervals at

@@ -50,6 +50,32 @@ def test_pack_unpack_roundtrip(n, dev):
     assert fr2.mapq is None and fr2.strand is None and np.array_equal(fr2.stop.cpu().numpy(), sp)
 
 
+@pytest.mark.parametrize("n", [1, 64, 65, 129, 5000, 300_007])
+def test_pack_unpack_narrow_records(n, dev):
+    """24-bit records (record_bytes = 3): lossless incl. blocks that escape by gap / length, ragged tails."""
+    import torch
+    from finaletoolkit_b200.packed import PackedFragments
+    rng = np.random.default_rng(900 + n)
+    st = (np.cumsum(rng.integers(0, 9, n)) + 3).astype(np.int32)
+    ln = rng.integers(0, 512, n).astype(np.int32)
+    if n >= 5000:
+        ln[rng.choice(n, 4, replace=False)] = 512             # one past the 9-bit field
+        ln[rng.choice(n, 4, replace=False)] = 511
+        st[n // 3:] += 64                                      # one past the 6-bit gap
+        st[2 * n // 3:] += 63
+    sp = (st + ln).astype(np.int32)
+    mq = rng.integers(0, 256, n).astype(np.uint8); sd = rng.integers(0, 2, n).astype(np.uint8)
+    for rb in (3, None):
+        pk = PackedFragments(st, sp, mq, sd, record_bytes=rb)
+        assert pk.record_bytes == 3 or rb is None          # None: whichever puts fewer bytes on the wire
+        fr = pk.to_device(dev)
+        torch.cuda.synchronize()
+        assert np.array_equal(fr.start.cpu().numpy(), st) and np.array_equal(fr.stop.cpu().numpy(), sp)
+        assert np.array_equal(fr.mapq.cpu().numpy(), mq) and np.array_equal(fr.strand.cpu().numpy(), sd)
+        if n >= 5000 and pk.record_bytes == 3:
+            assert 0 < pk.n_raw <= 10
+
+
 def test_pack_negative_start_and_all_raw(dev):
     from finaletoolkit_b200.packed import PackedFragments
     st = np.array([-5, -1, 0, 10, 10_000_000, 10_000_001], np.int32)
@@ -66,7 +92,7 @@ def test_wire_bytes_budget():
     from finaletoolkit_b200.packed import PACK_BLOCK
     n = 80_000_000
     nb = (n + PACK_BLOCK - 1) // PACK_BLOCK
-    assert nb * PACK_BLOCK * 4 + nb * 4 <= 330_000_000
+    assert nb * PACK_BLOCK * 4 + nb * 4 <= 330_000_000 and nb * PACK_BLOCK * 3 + nb * 4 <= 246_000_000
 
 
 @pytest.mark.parametrize("chunks", [1, 5])
@@ -87,8 +113,10 @@ def test_packed_pipeline_matches_resident(chunks, dev):
     assert pk.n_raw > 0
     pipe = StreamedContig(None, None, None, edges[:-1], edges[1:], clen, n_chunks=chunks, device=dev, packed=pk,
                           wps_dtype="int8")
-    for _ in range(2):
+    for rep in range(3):                 # eager pass, then the captured CUDA graph twice
+        pipe.h_wps.zero_(); pipe.h_cov.zero_(); pipe.h_hist.zero_()
         w, c, h, t = pipe.run()
+        assert (pipe._graph is not None) == (rep > 0)
     assert np.array_equal(w.numpy()[: pipe.n_positions].astype(np.int32), ref.cpu().numpy())
     assert np.array_equal(c.numpy(), cov.cpu().numpy()) and np.array_equal(h.numpy()[0], hist.cpu().numpy())
     assert int(t[0]) == int(cov.sum())
