@@ -397,11 +397,13 @@ def genome_block(args, dev, rank, world, peak):
     def timed(fn, reps, name=None):
         for _ in range(2):
             fn()
-        barrier()
+        # (the NVML sampler is created BEFORE the barrier: its start-up time differs from rank to rank and
+        # would otherwise shift e0 on some ranks, i.e. charge one rank's set-up to the others' first pass)
         sampler = ClockSampler(dev.index if dev.index is not None else 0, period=0.001) if name else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if sampler:
             sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
         e0.record()
         for _ in range(reps):
             fn()
