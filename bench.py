@@ -500,31 +500,16 @@ def genome_block(args, dev, rank, world, peak):
     # ---- configs[3]: DELFI-style 5-Mb-bin coverage + genome-wide fragment-length distribution
     # (first-seen ordered dict of frag_length_bins) with the NCCL reductions
     bins5 = tile_genome(sizes, 5_000_000)
-    n_b = {c: len(bins5[c][0]) for c, _ in sizes}
-    offs = np.concatenate([[0], np.cumsum([n_b[c] for c, _ in sizes])]).astype(np.int64)
-    order = {c: i for i, (c, _) in enumerate(sizes)}
-    sets = {c: D.IntervalSet(bins5[c][0].tolist(), bins5[c][1].tolist(), dev) for c in mine}
     nb_hist = 601
+    from finaletoolkit_b200.distributed import genome_bin_counts
 
-    def config4():
-        packed = torch.zeros(int(offs[-1]), dtype=torch.int64, device=dev)
-        parts = []
-        for c in mine:
-            i = order[c]
-            h = torch.zeros((1, nb_hist), dtype=torch.int64, device=dev)
-            f = torch.full((1, nb_hist), 2 ** 31 - 1, dtype=torch.int32, device=dev)
-            D.interval_hist(table.device(c), intersect_policy="midpoint", quality_threshold=MAPQ, n_bins=nb_hist,
-                            pooled="hist", ivl_set=sets[c], out=(packed[int(offs[i]): int(offs[i + 1])], h, f))
-            parts.append((i, h[0], f[0]))
-        if not parts:
-            parts = [(0, torch.zeros(nb_hist, dtype=torch.int64, device=dev),
-                      torch.full((nb_hist,), 2 ** 31 - 1, dtype=torch.int32, device=dev))]
-        ctx.all_reduce_sum(packed)
-        state["c4"] = (packed, genome_length_dict(ctx, parts, nb_hist))
+    def config4():      # ONE launch per rank over its contigs laid end to end + the three small collectives
+        state["c4"] = genome_bin_counts(table, bins5, n_bins=nb_hist, quality_threshold=MAPQ, ctx=ctx, device=dev,
+                                        contigs=mine, cache_key="bins5")
 
     ms_c4 = max_over_ranks(timed(config4, reps))
-    packed, ldict = state["c4"]
-    checks["config4_bins_total"] = int(packed.sum().item())
+    bin_counts, ldict = state["c4"]
+    checks["config4_bins_total"] = int(sum(int(v.sum()) for v in bin_counts.values()))
     checks["config4_lengths_total"] = int(sum(ldict.values()))
     checks["ok"] = checks["ok"] and checks["config4_bins_total"] == checks["config4_lengths_total"]
 
@@ -555,7 +540,7 @@ def genome_block(args, dev, rank, world, peak):
                             "collective": "none", "note": "int32 WPS stays in HBM; adjust = fused rank-median + Savitzky-Golay kernel",
                             "sm_mhz_per_rank": gather_ranks((clock_log.get("b") or {}).get("sm_mhz") or 0.0),
                             "clock_reasons_this_rank": (clock_log.get("b") or {}).get("reasons")},
-        "coverage5mb_plus_length_bins": {"ms": ms_c4, "bins": int(offs[-1]), "fragments_per_sec": tot_frag / (ms_c4 * 1e-3),
+        "coverage5mb_plus_length_bins": {"ms": ms_c4, "bins": int(sum(len(v[0]) for v in bins5.values())), "fragments_per_sec": tot_frag / (ms_c4 * 1e-3),
                                          "collective": "all_reduce(SUM) of 5-Mb bin counts + SUM/MIN of the length histogram / first-seen keys"},
         "lpt": {"fragments_this_rank": my_frag, "positions_this_rank": my_pos, "contigs_this_rank": len(mine)},
         "checks": checks,

@@ -14,10 +14,10 @@ from __future__ import annotations
 
 import numpy as np
 
-from .sharding import DistContext, genome_length_dict, lpt_pack
+from .sharding import DistContext, genome_length_dict, lpt_pack, reduce_length_dict
 
 __all__ = ["owned_contigs", "genome_total_coverage", "genome_length_distribution", "genome_end_motif_counts",
-           "genome_delfi_windows", "ContigWps", "GenomeShard", "multi_wps_genome", "adjust_wps_genome", "tile_genome",
+           "genome_delfi_windows", "genome_bin_counts", "table_shard", "ContigWps", "GenomeShard", "multi_wps_genome", "adjust_wps_genome", "tile_genome",
            "gather_to_writer"]
 
 
@@ -63,6 +63,12 @@ def genome_length_distribution(table, min_length=0, max_length=None, intersect_p
     ctx.all_reduce_max(gmax_t)
     gmax = int(gmax_t.item())
     n_bins = (gmax if max_length is None else min(gmax, int(max_length))) + 1
+    if region == (None, None):
+        # every contig whole: one launch per shard group over the rank's contigs laid end to end
+        shard = table_shard(table, ctx, dev, mine)
+        _, hist, keys = shard.interval_counts(None, order, intersect_policy, min_length, max_length, quality_threshold,
+                                              n_bins=n_bins, first_seen=True)
+        return reduce_length_dict(ctx, hist, keys)
     parts = []
     for c in mine:
         if not table.n_fragments(c):
@@ -156,6 +162,7 @@ def tile_genome(chrom_sizes, interval_size: int = 5000) -> dict:
 
 
 _SHARD_SPAN = (1 << 31) - (1 << 22)     # the virtual coordinates of a group stay well inside int32
+empty_i64 = np.zeros(0, np.int64)
 
 
 class _ShardGroup:
@@ -216,8 +223,9 @@ class GenomeShard:
             pend = None
 
         ivl_total = 0
+        empty = np.zeros(0, np.int64)
         for c in self.contigs:
-            starts, stops = (np.ascontiguousarray(a, dtype=np.int64) for a in sites[c])
+            starts, stops = (np.ascontiguousarray(a, dtype=np.int64) for a in (sites[c] if sites is not None else (empty, empty)))
             clen = int(sizes[c])
             frags = table.device(c, dev) if table.n_fragments(c) else None
             n = frags.n if frags is not None else 0
@@ -230,7 +238,7 @@ class GenomeShard:
             if pend is not None and pend["end"] + guard - lo + hi + guard > _SHARD_SPAN:
                 close()
             if pend is None:
-                pend = {"end": 0, "pos": 0, "ivl": 0, "ivl_base": ivl_total, "flen": 0, "cols": [], "segs": [],
+                pend = {"end": 0, "pos": 0, "ivl": 0, "ivl_base": ivl_total, "flen": 0, "nfrag": 0, "cols": [], "segs": [],
                         "tiles": {k: [] for k in ("p0", "len", "mid_lo", "mid_hi", "out_off", "ivl", "offsets")}}
             base = (pend["end"] + guard - lo + 63) & ~63
             tl = WpsPlan.host_tiles(starts, stops, clen, self.max_length)
@@ -251,9 +259,11 @@ class GenomeShard:
             pend["segs"].append(np.array([pad], dtype=np.int64))     # alignment gap: a segment without output
             self.layout[c] = {"group": len(self.groups), "base": int(base), "wps": (obase, obase + npos),
                               "ivl": (ivl_total, ivl_total + len(starts)), "starts": starts, "stops": stops,
-                              "offsets": tl["offsets"], "seg": (seg_lo, seg_lo + len(starts))}
+                              "offsets": tl["offsets"], "seg": (seg_lo, seg_lo + len(starts)),
+                              "span": (int(lo), int(hi)), "frag": (pend["nfrag"], pend["nfrag"] + n)}
             if n:
                 pend["cols"].append((frags.start + int(base), frags.stop + int(base), frags.mapq))
+                pend["nfrag"] += n
             pend["flen"] = max(pend["flen"], flen)
             pend["end"] = base + hi
             pend["pos"] += npos + pad
@@ -261,10 +271,70 @@ class GenomeShard:
             ivl_total += len(starts)
         close()
         self.n_intervals = ivl_total
+        self._bin_sets: dict = {}
         self.cov = t.zeros(max(ivl_total, 1), dtype=t.int64, device=dev)
         for g in self.groups:
             g.wps = t.empty(max(g.plan.n_positions, 1), dtype=t.int32, device=dev)
             g.cov = self.cov[g.ivl_base: g.ivl_base + g.n_ivl] if g.n_ivl else self.cov[:1]
+
+    def interval_counts(self, bins: dict | None, order: dict, intersect_policy="midpoint", min_length=None,
+                        max_length=None, quality_threshold=30, n_bins: int = 0, first_seen: bool = False,
+                        cache_key=None):
+        """Fragment counts of ``bins`` {contig: (starts, stops)} (``None``: one whole-contig interval per
+        contig, the reference's region ``(None, None)``) + the pooled length histogram of the counted
+        fragments (+ first-seen keys), ONE ``ftk_interval_hist_u64`` launch per shard group instead of one
+        per contig.  ``order``: {contig: position in the file header} - the first-seen key of a length is
+        ``(order << 32) | row index within the contig``, comparable across ranks (``sharding.first_seen_keys``).
+        Returns ``({contig: int64 counts view}, hist int64[n_bins] | None, keys int64[n_bins] | None)``."""
+        from .device import IntervalSet, interval_hist, torch
+        from .sharding import FIRST_SEEN_NONE
+        t = torch()
+        dev = self.device
+        key = cache_key if cache_key is not None else ("whole" if bins is None else id(bins))
+        sets = self._bin_sets.get(key)
+        if sets is None:
+            sets = []
+            for gi, g in enumerate(self.groups):
+                ss, ee, where, f_off, f_ord = [], [], {}, [0], []
+                n_b = 0
+                for c in self.contigs:
+                    lay = self.layout[c]
+                    if lay["group"] != gi:
+                        continue
+                    if bins is None:
+                        # one below the lowest coordinate: tabix's `stop > start` test must keep zero-length rows
+                        a, b = np.array([lay["span"][0] - 1], np.int64), np.array([lay["span"][1] + 1], np.int64)
+                    else:
+                        # clipped to the contig's own extent (no fragment lies outside it, so membership is
+                        # unchanged): a bin must not reach into the neighbouring contig's coordinates
+                        a, b = (np.clip(np.asarray(x, dtype=np.int64), lay["span"][0] - 1, lay["span"][1] + 1)
+                                for x in bins.get(c, (empty_i64, empty_i64)))
+                    ss.append(a + lay["base"]); ee.append(b + lay["base"])
+                    where[c] = (n_b, n_b + len(a)); n_b += len(a)
+                    f_off.append(lay["frag"][1]); f_ord.append(int(order[c]))
+                ivl = IntervalSet(np.concatenate(ss) if ss else empty_i64, np.concatenate(ee) if ee else empty_i64, dev)
+                sets.append((ivl, where, t.tensor(f_off, dtype=t.int64, device=dev),
+                             t.tensor(f_ord or [0], dtype=t.int64, device=dev),
+                             t.zeros(max(ivl.n, 1), dtype=t.int64, device=dev)))
+            self._bin_sets[key] = sets
+        hist = t.zeros((1, n_bins), dtype=t.int64, device=dev) if n_bins else None
+        keys = t.full((n_bins,), FIRST_SEEN_NONE, dtype=t.int64, device=dev) if (n_bins and first_seen) else None
+        counts = {}
+        for g, (ivl, where, f_off, f_ord, cnt) in zip(self.groups, sets):
+            cnt.zero_()
+            first = t.full((1, n_bins), 2 ** 31 - 1, dtype=t.int32, device=dev) if keys is not None else None
+            if ivl.n and g.frags.n:
+                interval_hist(g.frags, intersect_policy=intersect_policy, min_length=min_length, max_length=max_length,
+                              quality_threshold=quality_threshold, n_bins=n_bins, pooled="hist" if n_bins else False,
+                              ivl_set=ivl, out=(cnt, hist, first))
+            if keys is not None:
+                f = first[0].to(t.int64)
+                ci = t.bucketize(f, f_off[1:], right=True).clamp_(max=max(f_ord.numel() - 1, 0))
+                k = (f_ord[ci] << 32) + (f - f_off[ci])
+                keys = t.minimum(keys, t.where(first[0] == 2 ** 31 - 1, t.full_like(k, FIRST_SEEN_NONE), k))
+            for c, (a, b) in where.items():
+                counts[c] = cnt[a:b]
+        return counts, (hist[0] if hist is not None else None), keys
 
     def packed(self, n_bins: int):
         """[coverage total, length histogram...]: the one buffer that is all-reduced."""
@@ -403,6 +473,55 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
             r.flags = [f for _, _, f in flags]
         return res, hist, (packed[:1] if fused else None)
     return res, hist, (int(packed[0].item()) if fused else None)
+
+
+def table_shard(table, ctx: DistContext | None = None, device=None, contigs=None) -> "GenomeShard":
+    """The count-only shard (no WPS tiles) of the contigs this rank owns, cached on the table."""
+    from .device import require_cuda
+    ctx = ctx or DistContext()
+    dev = require_cuda(device)
+    mine = list(contigs) if contigs is not None else owned_contigs(table, ctx)
+    cache = table.__dict__.setdefault("_ftk_shards", {})
+    key = (tuple(mine), str(dev))
+    if key not in cache:
+        sizes = {c: 0 for c in mine}
+        sizes.update({c: n for c, n in (getattr(table, "contig_lengths", None) or {}).items() if c in sizes})
+        cache[key] = GenomeShard(table, sizes, None, mine, 0, 1, dev)
+    return cache[key]
+
+
+def genome_bin_counts(table, bins: dict, n_bins: int = 0, intersect_policy="midpoint", min_length=None,
+                      max_length=None, quality_threshold=30, ctx: DistContext | None = None, device=None,
+                      contigs=None, cache_key=None):
+    """Fragment counts of genome-wide bins {contig: (starts, stops)} (DELFI-style coverage,
+    frag/_delfi.py:283-300 / frag/_coverage.py:215-254) and, with ``n_bins``, the genome-wide fragment-length
+    dict of the counted fragments in first-seen order (frag/_frag_length.py:408-421) - contigs LPT-sharded,
+    ONE kernel launch per rank, one ``all_reduce(SUM)`` of the packed counts (+ SUM / MIN for the dict).
+    Returns ``({contig: int64[n] counts (host)}, dict | None)``, identical on every rank."""
+    from .device import require_cuda, torch
+    ctx = ctx or DistContext()
+    dev = require_cuda(device)
+    t = torch()
+    shard = table_shard(table, ctx, dev, contigs)
+    names = [c for c in table.contigs if c in bins]
+    order = {c: i for i, c in enumerate(table.contigs)}
+    offs = np.concatenate([[0], np.cumsum([len(bins[c][0]) for c in names])]).astype(np.int64)
+    packed = t.zeros(max(int(offs[-1]), 1), dtype=t.int64, device=dev)
+    counts, hist, keys = shard.interval_counts(bins, order, intersect_policy, min_length, max_length, quality_threshold,
+                                               n_bins=n_bins, first_seen=bool(n_bins), cache_key=cache_key)
+    for i, c in enumerate(names):
+        if c in counts:
+            packed[int(offs[i]): int(offs[i + 1])] = counts[c]
+    ctx.all_reduce_sum(packed)
+    ldict = None
+    if n_bins:
+        if hist is None:
+            from .sharding import FIRST_SEEN_NONE
+            hist = t.zeros(n_bins, dtype=t.int64, device=dev)
+            keys = t.full((n_bins,), FIRST_SEEN_NONE, dtype=t.int64, device=dev)
+        ldict = reduce_length_dict(ctx, hist, keys)
+    host = packed.cpu().numpy()
+    return {c: host[int(offs[i]): int(offs[i + 1])] for i, c in enumerate(names)}, ldict
 
 
 def adjust_wps_genome(results: dict, **adjust):

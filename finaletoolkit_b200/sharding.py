@@ -18,7 +18,7 @@ from typing import Dict, Iterable, List, Sequence
 import numpy as np
 
 __all__ = ["lpt_pack", "my_contigs", "DistContext", "pack_partials", "unpack_partials",
-           "merge_first_seen"]
+           "merge_first_seen", "reduce_length_dict"]
 
 FIRST_SEEN_NONE = np.iinfo(np.int64).max
 
@@ -122,6 +122,12 @@ def genome_length_dict(ctx: DistContext, per_contig: Sequence[tuple], n_bins: in
         hist[: h.numel()] += h.reshape(-1).to(torch.int64)
         k = first_seen_keys(f.reshape(-1), order)
         keys[: k.numel()] = torch.minimum(keys[: k.numel()], k)
+    return reduce_length_dict(ctx, hist, keys)
+
+
+def reduce_length_dict(ctx: DistContext, hist, keys) -> dict:
+    """SUM of the ranks' histograms + MIN of their first-seen keys -> the genome-wide dict, in the
+    reference's stream (first-seen) order, identical on every rank."""
     ctx.all_reduce_sum(hist)
     ctx.all_reduce_min(keys)
     h, k = hist.cpu().numpy(), keys.cpu().numpy()

@@ -106,3 +106,26 @@ def test_shard_splits_into_groups_before_int32_runs_out(dev, monkeypatch):
     assert torch.equal(one[1], two[1]) and one[2] == two[2]
     for c in contigs:
         assert torch.equal(one[0][c].wps, two[0][c].wps) and torch.equal(one[0][c].cov, two[0][c].cov)
+
+
+def test_genome_bin_counts_and_length_dict_through_the_shard(dev):
+    """Genome-wide bin coverage + the first-seen-ordered length dict (frag/_frag_length.py:408-421) from one
+    launch over the contigs laid end to end == the oracle's per-contig stream, zero-length rows included."""
+    from finaletoolkit_b200 import distributed as FD
+    rng = np.random.default_rng(21)
+    contigs = {"a": 61_003, "empty": 20_001, "b": 33_333, "c": 7_001}
+    table, cols = _table(rng, contigs)
+    bins = {c: (np.arange(0, n, 10_000, dtype=np.int64), np.minimum(np.arange(0, n, 10_000, dtype=np.int64) + 10_000, n))
+            for c, n in contigs.items()}
+    n_bins = 2600
+    got, ldict = FD.genome_bin_counts(table, bins, n_bins=n_bins, quality_threshold=30, device=dev)
+    frs = {c: O.Frags(*cols[c]) for c in contigs}
+    exp_dict = O.merge_dists(O.length_dist(frs[c], int(a), int(b), None, None, "midpoint", 30)
+                             for c in contigs for a, b in zip(*bins[c]))
+    for c in contigs:
+        assert np.array_equal(got[c], O.interval_coverage(frs[c], bins[c][0], bins[c][1], None, None, "midpoint", 30)), c
+    assert {k: v for k, v in exp_dict.items() if k < n_bins} == ldict
+    # whole contigs (region None, None), the frag_length_bins stream: dict AND its first-seen order
+    d = FD.genome_length_distribution(table, min_length=0, max_length=None, quality_threshold=30, device=dev)
+    exp = O.merge_dists(O.length_dist(fr, None, None, 0, None, "midpoint", 30) for fr in frs.values())
+    assert d == exp and list(d) == list(exp)
