@@ -285,6 +285,10 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
         for (int v = tid; v < nvec; v += kMotifThreads) {
             int4 s_n, e_n;
             uchar4 q_n, d_n;
+            if (v + 2 * kMotifThreads < nvec) {     // two iterations ahead: pull the lines into L2 (no registers held)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(vs + v + 2 * kMotifThreads));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(ve + v + 2 * kMotifThreads));
+            }
             if (NCHECK) {
                 load(v + kMotifThreads, s_n, e_n, q_n, d_n);
                 visit(s_c.x, e_c.x, q_c.x, d_c.x);
