@@ -19,7 +19,6 @@
 namespace ftk {
 
 constexpr int kDelfiThreads = 256;
-constexpr int kDelfiUnroll = 4;
 
 __global__ void delfi_ranges_kernel(const int32_t *__restrict__ frag_start, int64_t n_frag,
                                     const int32_t *__restrict__ win_start,
@@ -54,37 +53,72 @@ delfi_count_kernel(const int32_t *__restrict__ frag_start, const int32_t *__rest
     const int64_t hi = min(hi_all, lo + chunk);
 
     int n_short = 0, n_long = 0;
-    int fs_r[kDelfiUnroll], fe_r[kDelfiUnroll], q_r[kDelfiUnroll];
-    for (int64_t i0 = lo + tid; i0 < hi; i0 += (int64_t)kDelfiUnroll * kDelfiThreads) {
-#pragma unroll
-        for (int u = 0; u < kDelfiUnroll; ++u) {
-            const int64_t i = i0 + (int64_t)u * kDelfiThreads;
-            const bool in = i < hi;
-            fs_r[u] = in ? __ldcs(frag_start + i) : 0;
-            fe_r[u] = in ? __ldcs(frag_stop + i) : 0;
-            q_r[u] = in ? (frag_mapq ? (int)__ldcs(frag_mapq + i) : 255) : -1;
+    // One fragment, branch-free: every test of frag/_delfi.py:437-470 is a predicate (the tabix overlap
+    // `stop > S and start < E` is implied by 100 <= length and the midpoint lying in [S, E)).  Only the
+    // blacklist walk (a bin's own CSR list, nearly always empty) branches.
+    const unsigned span = E > S ? (unsigned)(E - S) : 0u;
+    auto visit = [&](int fs, int fe, int q) {
+        const int len = fe - fs;
+        const int mid = (int)(((int64_t)fs + fe) >> 1);   // floor, like Python's //
+        bool pass = (q >= min_mapq) & ((unsigned)(len - 100) <= 120u) & ((unsigned)(mid - S) < span);
+        if (gaps.use) {
+            const bool in_c = (fe > gaps.c0) & (fs < gaps.c1);
+            const bool in_t = gaps.has_telo & (fe > gaps.t0_max) & (fs < gaps.t1_min);
+            pass = pass & !(in_c | in_t);
         }
-#pragma unroll
-        for (int u = 0; u < kDelfiUnroll; ++u) {
-            const int fs = fs_r[u], fe = fe_r[u];
-            if (q_r[u] < min_mapq || !(fe > S && fs < E)) continue;
-            const int len = fe - fs;
-            if (len < 100 || len > 220) continue;
-            const int mid = (int)(((int64_t)fs + fe) >> 1);   // floor, like Python's //
-            if (mid < S || mid >= E) continue;
-            bool blacklisted = false;
+        if (b_hi > b_lo && pass) {
             for (int b = b_lo; b < b_hi; ++b) {
                 const int r0 = __ldg(bl_start + b), r1 = __ldg(bl_stop + b);
-                if (fs >= r0 && fs < r1 && fe >= r0 && fe < r1) { blacklisted = true; break; }
+                if (fs >= r0 && fs < r1 && fe >= r0 && fe < r1) { pass = false; break; }
             }
-            if (gaps.use) {
-                const bool in_c = fe > gaps.c0 && fs < gaps.c1;
-                const bool in_t = gaps.has_telo && fe > gaps.t0_max && fs < gaps.t1_min;
-                if (in_c || in_t) continue;
-            }
-            if (blacklisted) continue;
-            if (len >= 151) ++n_long; else ++n_short;
         }
+        const int is_long = len >= 151;
+        n_long += pass & is_long;
+        n_short += pass & !is_long;
+    };
+    // 128-bit streaming loads, two vectors (eight fragments) in flight per thread; the slice is widened
+    // to a 16-byte boundary on the left, the fragments before `lo` get mapq -1 (never counted)
+    const int64_t lo_al = lo & ~(int64_t)3;
+    const int skip = (int)(lo - lo_al);
+    const int cnt = (hi > lo) ? (int)(hi - lo_al) : 0;
+    const int nvec = cnt >> 2;
+    const int4 *__restrict__ vs = reinterpret_cast<const int4 *>(frag_start + lo_al);
+    const int4 *__restrict__ ve = reinterpret_cast<const int4 *>(frag_stop + lo_al);
+    const uchar4 *__restrict__ vq = reinterpret_cast<const uchar4 *>(frag_mapq ? frag_mapq + lo_al : nullptr);
+    constexpr int kU = 2;
+    for (int v0 = tid; v0 < nvec; v0 += kU * kDelfiThreads) {
+        int4 s4[kU], e4[kU];
+        int q0[kU], q1[kU], q2[kU], q3[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int v = v0 + u * kDelfiThreads;
+            if (v < nvec) {
+                s4[u] = __ldcs(vs + v); e4[u] = __ldcs(ve + v);
+                const uchar4 q = vq ? __ldcs(vq + v) : make_uchar4(255, 255, 255, 255);
+                q0[u] = q.x; q1[u] = q.y; q2[u] = q.z; q3[u] = q.w;
+            } else {
+                s4[u] = make_int4(0, 0, 0, 0); e4[u] = make_int4(0, 0, 0, 0);
+                q0[u] = q1[u] = q2[u] = q3[u] = -1;
+            }
+        }
+        if (v0 == 0 && skip) {       // thread 0, first vector only
+            q0[0] = -1;
+            if (skip > 1) q1[0] = -1;
+            if (skip > 2) q2[0] = -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            visit(s4[u].x, e4[u].x, q0[u]);
+            visit(s4[u].y, e4[u].y, q1[u]);
+            visit(s4[u].z, e4[u].z, q2[u]);
+            visit(s4[u].w, e4[u].w, q3[u]);
+        }
+    }
+    {   // tail: at most 3 fragments
+        const int i = nvec * 4 + tid;
+        if (i < cnt && i >= skip)
+            visit(__ldcs(frag_start + lo_al + i), __ldcs(frag_stop + lo_al + i),
+                  frag_mapq ? (int)__ldcs(frag_mapq + lo_al + i) : 255);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -108,13 +142,18 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {
     return x;
 }
 
-// One warp per bin: G/C bases (codes 1, 2 <=> bit0 ^ bit1) that are not N, in [ws, we) clipped to
-// the contig.  Bins that are not valid reference intervals count 0 (frag/_delfi.py:472-482).
+// kGcWarps warps per bin (a 100-kb bin is 37.5 KB of packed contig: one warp per bin left the chip at
+// ~1 TB/s), each striding over the bin's words and adding its partial with one atomic: G/C bases (codes
+// 1, 2 <=> bit0 ^ bit1) that are not N, in [ws, we) clipped to the contig.  Bins that are not valid
+// reference intervals count 0 (frag/_delfi.py:472-482).  counts[][3] accumulates (caller zeroes).
+constexpr int kGcWarps = 8;
 __global__ void __launch_bounds__(kDelfiThreads)
 delfi_gc_kernel(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask, int64_t contig_len,
                 const int32_t *__restrict__ win_start, const int32_t *__restrict__ win_stop, int64_t n_win,
                 unsigned long long *__restrict__ counts) {
-    const int64_t win = ((int64_t)blockIdx.x * kDelfiThreads + threadIdx.x) >> 5;
+    const int64_t gwarp = ((int64_t)blockIdx.x * kDelfiThreads + threadIdx.x) >> 5;
+    const int64_t win = gwarp / kGcWarps;
+    const int part = (int)(gwarp % kGcWarps);
     const int lane = threadIdx.x & 31;
     if (win >= n_win) return;
     const int64_t S = win_start[win], E = win_stop[win];
@@ -123,7 +162,7 @@ delfi_gc_kernel(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ n
     int n = 0;
     if (valid) {
         const int64_t w0 = S >> 4, w1 = (E + 15) >> 4;   // 16-base words
-        for (int64_t w = w0 + lane; w < w1; w += 32) {
+        for (int64_t w = w0 + part * 32 + lane; w < w1; w += 32 * kGcWarps) {
             const uint32_t x = __ldg(seq + w);
             uint32_t gc = (x ^ (x >> 1)) & 0x55555555u;
             const uint32_t nm = __ldg(nmask + (w >> 1)) >> ((w & 1) * 16);
@@ -139,7 +178,7 @@ delfi_gc_kernel(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ n
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
-    if (lane == 0) counts[win * 4 + 3] = (unsigned long long)n;
+    if (lane == 0 && n) atomicAdd(&counts[win * 4 + 3], (unsigned long long)n);
 }
 
 }  // namespace ftk
@@ -172,12 +211,13 @@ extern "C" int ftk_delfi_windows_u64(const int32_t *frag_start, const int32_t *f
         FTK_CHECK_LAUNCH("delfi_ranges_kernel");
     }
     auto *c = reinterpret_cast<unsigned long long *>(counts);
+    if (min_mapq < 0) min_mapq = 0;      // mapq is a uint8 column; the kernel masks rows with mapq -1
     delfi_count_kernel<<<(unsigned)(n_win * splits), kDelfiThreads, 0, stream>>>(
         frag_start, frag_stop, frag_mapq, win_start, win_stop, scratch, bl_off, bl_start, bl_stop, g,
         min_mapq, splits, c);
     FTK_CHECK_LAUNCH("delfi_count_kernel");
     if (seq_words) {
-        const int64_t threads = n_win * 32;
+        const int64_t threads = n_win * 32 * kGcWarps;
         delfi_gc_kernel<<<(unsigned)((threads + kDelfiThreads - 1) / kDelfiThreads), kDelfiThreads, 0, stream>>>(
             seq_words, nmask_words, contig_len, win_start, win_stop, n_win, c);
         FTK_CHECK_LAUNCH("delfi_gc_kernel");

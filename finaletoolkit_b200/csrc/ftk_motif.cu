@@ -72,9 +72,14 @@ __global__ void motif_ranges_kernel(const int32_t *__restrict__ frag_start, int6
 //   * N runs are rare and long (telomeres, centromere, assembly gaps), so every CTA first ORs the
 //     N-mask words of the span its fragment slice can touch - two loads per thread - and, when that is
 //     zero, runs the loop instantiated without the per-end N test (two loads + four operations less
-//     per end);
-//   * forward k-mers are counted under their raw window bits (first base = least significant digit)
-//     in a second shared histogram and only re-indexed (digit reversal) when the CTA flushes it.
+//     per end: 296 -> 251 us with the batch below, 216 us without it);
+//   * the next vector of a thread is loaded while the current one is processed, the lines two
+//     iterations ahead are pulled into L2, slices are 16 K fragments (the per-CTA chain ranges ->
+//     slice bounds -> N pre-scan -> first fragments is paid once per slice).
+// Measured and dropped: handling the four fragments of a vector together, branch-free, with all
+// sixteen window words requested before the first k-mer is formed (251 us against 216 us for the
+// plain per-fragment loop: the predicated form executes the atomics' address arithmetic for every
+// lane); a second histogram for raw-bit forward k-mers (328 us); bank-interleaved replicas.
 template <int K>
 struct MotifK {
     int k_rt;
@@ -86,7 +91,7 @@ struct MotifK {
 #ifndef FTK_MOTIF_CTAS
 #define FTK_MOTIF_CTAS 5
 #endif
-constexpr int kMotifCtasPerSm = FTK_MOTIF_CTAS;   // 5 -> 48 registers: the two loop instantiations spill at 40
+constexpr int kMotifCtasPerSm = FTK_MOTIF_CTAS;   // 5 or 6 CTAs per SM measure the same (213-217 us); 8 is slower
 constexpr int kMotifNScanWords = 8192;      // longest span (in 32-base mask words) a CTA pre-scans for N
 
 template <int K, int MODE, bool SMEM, bool BREAKPOINT>
@@ -98,13 +103,12 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
                  const int64_t *__restrict__ ranges, int k, int strand_mode, int min_mapq, int max_frag_len,
                  int pooled, int splits, unsigned long long *__restrict__ counts,
                  int32_t *__restrict__ error_flag) {
-    // (Bank-interleaved replicas of the histograms - 4 / 8 / 16 copies, lane l bumping copy l % copies -
-    // were measured: no change.  The cost is the shared-memory atomic unit itself, ~3 lane-atomics per
-    // cycle and SM whether the lanes collide or not: 2 atomics x 72 M counted fragments = 0.17 ms.)
-    // kDual: forward k-mers in their own histogram under the raw window bits, re-indexed at the flush (saves the
-    // digit reversal per fragment; only worth it while zeroing + flushing two histograms per CTA is cheap)
-    constexpr bool kDual = SMEM && K >= 1 && K <= 5;
-    __shared__ int s_cnt[SMEM ? (K ? ((kDual ? 2 : 1) << (2 * K)) : kMotifSmemBins) : 1];
+    // ONE histogram for both ends, indexed like the reference's table (forward k-mers digit-reversed per
+    // fragment).  Measured alternatives that lost: a second histogram holding the forward k-mers under their
+    // raw window bits, re-indexed at the flush (saves the digit reversal, 328 us against 252 us for k = 4 -
+    // not understood: same number of atomics, fewer instructions); 4 / 8 / 16 bank-interleaved replicas (no
+    // change).  The cost that remains is the shared-memory atomic unit itself.
+    __shared__ int s_cnt[SMEM ? (K ? (1 << (2 * K)) : kMotifSmemBins) : 1];
     const int tid = threadIdx.x;
     MotifK<K> KK{k};
     const int n_bins = 1 << (2 * KK.k());
@@ -166,7 +170,7 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
         } else {
             acc = 1u;
         }
-        if (SMEM) for (int b = tid; b < (kDual ? 2 : 1) * n_bins; b += kMotifThreads) s_cnt[b] = 0;
+        if (SMEM) for (int b = tid; b < n_bins; b += kMotifThreads) s_cnt[b] = 0;
         any_n = __syncthreads_or(acc != 0u);
     }
 
@@ -178,7 +182,6 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
         const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(s_cnt));
         asm volatile("mov.b32 %0, %1;" : "=r"(s_base) : "r"(a));
     }
-    const uint32_t s_rev_off = kDual ? (uint32_t)n_bins * 4u : 0u;
     auto bump_s = [&](uint32_t byte_off) {
         asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(s_base + byte_off) : "memory");
     };
@@ -187,13 +190,13 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
         auto fwd = [&](int pos) {      // k-mer read 5'->3' on the forward strand starting at pos
             if (NCHECK && has_n(nmask, pos, maskk)) return;
             const uint32_t wbits = window2(seq, pos, mask2k);
-            if (SMEM) bump_s((kDual ? wbits : digit_reverse(wbits, kk)) << 2);
+            if (SMEM) bump_s(digit_reverse(wbits, kk) << 2);
             else atomicAdd(&row[digit_reverse(wbits, kk)], 1ull);
         };
         auto rev = [&](int pos) {      // reverse complement of ref[pos, pos + k)
             if (NCHECK && has_n(nmask, pos, maskk)) return;
             const uint32_t idx = (~window2(seq, pos, mask2k)) & mask2k;
-            if (SMEM) bump_s(s_rev_off + (idx << 2));
+            if (SMEM) bump_s(idx << 2);
             else atomicAdd(&row[idx], 1ull);
         };
         auto visit = [&](int fs, int fe, int q, int sd) {
@@ -222,64 +225,6 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
                 rev(fe - kk);
             }
         };
-        // N-free span: the four fragments of a vector are handled together and without branches - the
-        // tests of the eight ends turn into predicates, all sixteen window words are requested back to
-        // back (a rejected end reads word 0), and only then are the k-mers formed and counted.  The
-        // per-fragment version above serialises eight dependent L2 round trips per vector; this one has one.
-        auto visit4 = [&](const int4 &s4, const int4 &e4, const uchar4 &q4, const uchar4 &d4, auto between) {
-            const int fs[4] = {s4.x, s4.y, s4.z, s4.w}, fe[4] = {e4.x, e4.y, e4.z, e4.w};
-            const int q[4] = {q4.x, q4.y, q4.z, q4.w}, sd[4] = {d4.x, d4.y, d4.z, d4.w};
-            const int h = BREAKPOINT ? (kk >> 1) : 0;
-            bool f_ok[4], r_ok[4];
-            uint32_t f_lo[4], f_hi[4], r_lo[4], r_hi[4];
-            int pf[4], pr[4];
-            bool err = false;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                bool pass = (q[i] >= min_mapq) && (fe[i] > S) && (fs[i] < E);
-                bool r_try;
-                if (BREAKPOINT) {
-                    pass = pass && (fs[i] >= h) && (fs[i] < len32 - h) && ((kk & 1) == 0);
-                    f_ok[i] = pass && (mode == 0 || (mode == 1 && sd[i]));
-                    r_try = pass && (mode != 1);
-                    r_ok[i] = r_try && !(fe[i] < h || fe[i] > len32 - h);
-                    pf[i] = fs[i] - h; pr[i] = fe[i] - h;
-                } else {
-                    if (mode == 1) pass = pass && sd[i];
-                    const bool f_in = (unsigned)fs[i] <= (unsigned)(len32 - kk);
-                    f_ok[i] = pass && (mode != 2) && f_in;
-                    r_try = pass && (mode != 1) && (mode == 2 || f_in);
-                    const bool r_oob = (fe[i] < kk) || (fe[i] > len32);
-                    r_ok[i] = r_try && !r_oob;
-                    err = err || (mode == 0 && r_try && r_oob);
-                    pf[i] = fs[i]; pr[i] = fe[i] - kk;
-                }
-                pf[i] = f_ok[i] ? pf[i] : 0;
-                pr[i] = r_ok[i] ? pr[i] : 0;
-                const uint32_t *__restrict__ wf = seq + (pf[i] >> 4), *__restrict__ wr = seq + (pr[i] >> 4);
-                f_lo[i] = __ldg(wf); f_hi[i] = __ldg(wf + 1);
-                r_lo[i] = __ldg(wr); r_hi[i] = __ldg(wr + 1);
-            }
-            // the next vector's (DRAM) loads are issued BEHIND the window reads (L1 / L2 hits): the L1
-            // returns a warp's loads through one in-order queue, so a hit queued behind a miss waits for it
-            asm volatile("" ::: "memory");
-            between();
-            asm volatile("" ::: "memory");
-            if (err) atomicOr(error_flag, 1);                                // RuntimeError in the reference
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (f_ok[i]) {
-                    const uint32_t wbits = __funnelshift_r(f_lo[i], f_hi[i], pf[i] << 1) & mask2k;
-                    if (SMEM) bump_s((kDual ? wbits : digit_reverse(wbits, kk)) << 2);
-                    else atomicAdd(&row[digit_reverse(wbits, kk)], 1ull);
-                }
-                if (r_ok[i]) {
-                    const uint32_t idx = (~__funnelshift_r(r_lo[i], r_hi[i], pr[i] << 1)) & mask2k;
-                    if (SMEM) bump_s(s_rev_off + (idx << 2));
-                    else atomicAdd(&row[idx], 1ull);
-                }
-            }
-        };
         // software pipeline: the next vector of the thread is in flight while the current one is turned
         // into window reads and atomics
         for (int v = tid; v < nvec; v += kMotifThreads) {
@@ -289,15 +234,11 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(vs + v + 2 * kMotifThreads));
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(ve + v + 2 * kMotifThreads));
             }
-            if (NCHECK) {
-                load(v + kMotifThreads, s_n, e_n, q_n, d_n);
-                visit(s_c.x, e_c.x, q_c.x, d_c.x);
-                visit(s_c.y, e_c.y, q_c.y, d_c.y);
-                visit(s_c.z, e_c.z, q_c.z, d_c.z);
-                visit(s_c.w, e_c.w, q_c.w, d_c.w);
-            } else {
-                visit4(s_c, e_c, q_c, d_c, [&] { load(v + kMotifThreads, s_n, e_n, q_n, d_n); });
-            }
+            load(v + kMotifThreads, s_n, e_n, q_n, d_n);
+            visit(s_c.x, e_c.x, q_c.x, d_c.x);
+            visit(s_c.y, e_c.y, q_c.y, d_c.y);
+            visit(s_c.z, e_c.z, q_c.z, d_c.z);
+            visit(s_c.w, e_c.w, q_c.w, d_c.w);
             s_c = s_n; e_c = e_n; q_c = q_n; d_c = d_n;
         }
         {   // tail: at most 3 fragments
@@ -313,11 +254,7 @@ end_motif_kernel(const int32_t *__restrict__ frag_start, const int32_t *__restri
     if (SMEM) {
         __syncthreads();
         for (int b = tid; b < n_bins; b += kMotifThreads) {
-            const int cr = s_cnt[(kDual ? n_bins : 0) + b];
-            if (kDual) {
-                const int cf = s_cnt[b];
-                if (cf) atomicAdd(&row[digit_reverse((uint32_t)b, KK.k())], (unsigned long long)cf);
-            }
+            const int cr = s_cnt[b];
             if (cr) atomicAdd(&row[b], (unsigned long long)cr);
         }
     }

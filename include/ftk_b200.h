@@ -278,8 +278,8 @@ int ftk_breakpoint_motif_hist_u64(const int32_t *frag_start_dev, const int32_t *
  * Replaces the per-fragment loop + GC count of _delfi_single_window, frag/_delfi.py:404-511 (run
  * once per 100 kb bin by the Pool at frag/_delfi.py:283-294) for all bins of one contig.
  * counts_dev: uint64[n_win][4] = {short (100..150), long (151..220), num_frags, G+C bases};
- * columns 0-2 are accumulated (zero them first), column 3 is written (only when seq_words_dev
- * is given; bins that are not valid reference intervals get 0, :472-482).
+ * all four columns are accumulated (zero them first); column 3 only when seq_words_dev is given
+ * (bins that are not valid reference intervals add 0, :472-482).
  * Fragment filter: tabix overlap with the bin, mapq >= min_mapq, 100 <= L <= 220, midpoint in the
  * bin, not inside a blacklist region, not in_tcmere (genome/gaps.py:226-248).
  * Blacklist: bl_off_dev int32[n_win+1] indexes bl_start_dev/bl_stop_dev, the regions contained in
