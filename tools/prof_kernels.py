@@ -1,7 +1,8 @@
 """Profiling target (run under ncu on a GPU box): one fused WPS+coverage+histogram step and one fused
 adjust (rank median + Savitzky-Golay) call at chr1 scale.
-    ncu --set full --clock-control none --import-source on -k regex:"adjust_rank_kernel|wps_hex_kernel" -c 2 \
-        -o gpurun_out/r2_top python tools/prof_kernels.py
+    EXTRAS=1 ncu --set full --clock-control none --import-source on \
+        -k regex:"adjust_rank_kernel|wps_hex_kernel|end_motif_kernel|cleavage_tile_kernel|delfi_count_kernel" -c 5 \
+        -o gpurun_out/r2b_top python tools/prof_kernels.py
 """
 import os
 import sys
@@ -34,5 +35,7 @@ if os.environ.get("EXTRAS"):
     ws = list(range(0, CLEN - 1_000_000, 1_000_000)); we = [a + 1_000_000 for a in ws]
     D.end_motif_hist(fr, ref, ws, we, k=4, strand_mode=0, quality_threshold=30, pooled=True)
     D.cleavage_intervals(fr, edges[:-1], edges[1:], CLEN, None, None, 30)
+    bs = np.arange(0, CLEN, 100_000, dtype=np.int64); be = np.minimum(bs + 100_000, CLEN)
+    D.delfi_windows(fr, ref, bs, be, quality_threshold=30)
 torch.cuda.synchronize()
 print("ok", int(cov.sum()), float(out[:3].sum()))
