@@ -239,3 +239,55 @@ def test_fused_pass_2000_intervals_vs_oracle(big):
     ok = (mq >= 30) & (mid < CLEN)
     assert np.array_equal(hist.cpu().numpy(), np.bincount(L[ok], minlength=fr.max_len + 1))
     assert int(cov.sum()) == int(ok.sum())
+
+
+def test_narrow_wire_records_and_streamed_pipeline_at_scale(big):
+    """20 M fragments through the 24-bit wire records: lossless round trip (column checksums + equality), and the
+    streamed pipeline (packed in, unpack + fused sweep, int8 out, captured CUDA graph) == the resident int32 pass."""
+    import torch
+    from finaletoolkit_b200 import device as D
+    from finaletoolkit_b200.packed import PackedFragments
+    from finaletoolkit_b200.pipeline import StreamedContig
+    dev, st, sp, mq = big["dev"], big["st"], big["sp"], big["mq"]
+    pk = PackedFragments(st, sp, mq, None)
+    assert pk.record_bytes == 3 and pk.n_raw < pk.n_blocks // 50 and pk.wire_bytes() < 3.07 * NFRAG
+    fr = pk.to_device(dev)
+    assert torch.equal(fr.start, big["fr"].start) and torch.equal(fr.stop, big["fr"].stop) and torch.equal(fr.mapq, big["fr"].mapq)
+    edges = np.arange(0, CLEN + 5000, 5000).clip(max=CLEN)
+    plan = D.WpsPlan(edges[:-1], edges[1:], CLEN, 180, dev)
+    ref, cov, hist = plan.run_fused(big["fr"], n_bins=pk.max_len + 1)
+    pipe = StreamedContig(None, None, None, edges[:-1], edges[1:], CLEN, n_chunks=8, device=dev, packed=pk, wps_dtype="int8")
+    for rep in range(3):          # eager, then the captured graph twice
+        pipe.h_wps.zero_()
+        w, c, h, t = pipe.run()
+    assert pipe._graph is not None
+    assert torch.equal(w[: pipe.n_positions].to(torch.int32), ref.cpu())
+    assert torch.equal(c, cov.cpu()) and torch.equal(h[0], hist.cpu()) and int(t[0]) == int(cov.sum())
+
+
+def test_shard_at_chromosome_scale(big):
+    """Three contigs (the 60-Mb one twice under different names + a short one) through ONE launch of the shard ==
+    the per-contig fused pass, incl. the adjusted series; checksum of checksums across the two copies."""
+    import torch
+    from finaletoolkit_b200 import device as D
+    from finaletoolkit_b200 import distributed as FD
+    from finaletoolkit_b200.io.fragments import FragmentTable
+    dev, st, sp, mq, sd = big["dev"], big["st"], big["sp"], big["mq"], big["sd"]
+    k = 2_000_000
+    cols = {"A": (st, sp, mq, sd), "S": (st[:k], sp[:k], mq[:k], sd[:k]), "B": (st, sp, mq, sd)}
+    sizes = {"A": CLEN, "S": int(sp[:k].max()) + 1000, "B": CLEN}
+    table = FragmentTable(cols)
+    res, hist, tot = FD.multi_wps_genome(table, list(sizes.items()), None, 5000, 120, 120, 180, 30, coverage=True,
+                                         length_hist=True, adjust=dict(median_window_size=1000), device=dev,
+                                         contigs=list(sizes))
+    assert torch.equal(res["A"].wps, res["B"].wps) and torch.equal(res["A"].cov, res["B"].cov)
+    assert torch.equal(res["A"].adjusted, res["B"].adjusted)
+    edges = np.arange(0, CLEN + 5000, 5000).clip(max=CLEN)
+    plan = D.WpsPlan(edges[:-1], edges[1:], CLEN, 180, dev)
+    wps, cov, h = plan.run_fused(big["fr"], 120, 120, 180, 30, None, None, 30, n_bins=hist.numel())
+    assert torch.equal(res["A"].wps, wps) and torch.equal(res["A"].cov, cov)
+    ap = D.AdjustPlan(np.diff(plan.offsets), 1000, True, 21, 2, dev, skip_short=True)
+    adj, _ = D.adjust_segments(wps, None, plan=ap, median_window_size=1000)
+    assert torch.equal(res["A"].adjusted, adj)
+    assert tot == 2 * int(cov.sum()) + int(res["S"].cov.sum())
+    assert int(hist.sum()) == tot
