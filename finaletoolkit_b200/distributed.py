@@ -506,21 +506,27 @@ def genome_bin_counts(table, bins: dict, n_bins: int = 0, intersect_policy="midp
     names = [c for c in table.contigs if c in bins]
     order = {c: i for i, c in enumerate(table.contigs)}
     offs = np.concatenate([[0], np.cumsum([len(bins[c][0]) for c in names])]).astype(np.int64)
-    packed = t.zeros(max(int(offs[-1]), 1), dtype=t.int64, device=dev)
+    n_cnt = int(offs[-1])
+    packed = t.zeros(max(n_cnt + int(n_bins), 1), dtype=t.int64, device=dev)      # [bin counts..., length histogram...]
     counts, hist, keys = shard.interval_counts(bins, order, intersect_policy, min_length, max_length, quality_threshold,
                                                n_bins=n_bins, first_seen=bool(n_bins), cache_key=cache_key)
     for i, c in enumerate(names):
         if c in counts:
             packed[int(offs[i]): int(offs[i + 1])] = counts[c]
-    ctx.all_reduce_sum(packed)
+    if n_bins and hist is not None:
+        packed[n_cnt: n_cnt + n_bins] = hist
+    ctx.all_reduce_sum(packed)                   # ONE SUM for counts and histogram
+    host = packed.cpu().numpy()
     ldict = None
     if n_bins:
-        if hist is None:
+        if keys is None:
             from .sharding import FIRST_SEEN_NONE
-            hist = t.zeros(n_bins, dtype=t.int64, device=dev)
             keys = t.full((n_bins,), FIRST_SEEN_NONE, dtype=t.int64, device=dev)
-        ldict = reduce_length_dict(ctx, hist, keys)
-    host = packed.cpu().numpy()
+        ctx.all_reduce_min(keys)                 # + ONE MIN for the first-seen order
+        h, k = host[n_cnt: n_cnt + n_bins], keys.cpu().numpy()
+        nz = np.flatnonzero(h)
+        nz = nz[np.argsort(k[nz], kind="stable")]
+        ldict = {int(L): int(h[L]) for L in nz}
     return {c: host[int(offs[i]): int(offs[i + 1])] for i, c in enumerate(names)}, ldict
 
 
