@@ -220,13 +220,29 @@ def test_lpt_packing():
     from finaletoolkit_b200.synth import B37_CONTIGS
     w = dict(B37_CONTIGS)
     tot = sum(w.values())
-    for n, bound in [(1, 0.0), (2, 0.01), (4, 0.02), (8, 0.05)]:
+    # greedy LPT + exchange refinement: b37 lands within 1 % of perfect balance up to 8 ranks
+    for n, bound in [(1, 0.0), (2, 0.001), (3, 0.001), (4, 0.002), (5, 0.002), (6, 0.003), (7, 0.01), (8, 0.01)]:
         bins = lpt_pack(w, n)
         assert sorted(c for b in bins for c in b) == sorted(w)
         loads = [sum(w[c] for c in b) for b in bins]
         assert max(loads) / (tot / n) - 1 <= bound, (n, loads)
         order = {c: i for i, c in enumerate(w)}
         assert all(b == sorted(b, key=order.get) for b in bins)
+        assert bins == lpt_pack(dict(w), n)                      # deterministic: every rank computes the same shards
+    # degenerate inputs: more ranks than contigs, zero weights, nothing at all
+    assert sorted(map(tuple, lpt_pack({"a": 5, "b": 3}, 4))) == [(), (), ("a",), ("b",)]
+    assert lpt_pack({"a": 0, "b": 0}, 2) in ([["a", "b"], []], [["a"], ["b"]])
+    assert lpt_pack({}, 3) == [[], [], []]
+    rng = __import__("numpy").random.default_rng(0)
+    for _ in range(20):                                           # never worse than the greedy step it starts from
+        ww = {f"c{i}": int(v) for i, v in enumerate(rng.integers(1, 10_000, int(rng.integers(1, 40))))}
+        n = int(rng.integers(1, 12))
+        bins = lpt_pack(ww, n)
+        assert sorted(c for b in bins for c in b) == sorted(ww)
+        greedy = [0] * n
+        for c in sorted(ww, key=lambda c: -ww[c]):
+            greedy[greedy.index(min(greedy))] += ww[c]
+        assert max(sum(ww[c] for c in b) for b in bins) <= max(greedy)
 
 
 _GLOO_WORKER = r'''
