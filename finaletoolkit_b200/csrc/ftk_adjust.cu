@@ -453,7 +453,9 @@ __device__ __forceinline__ unsigned warp_transpose32(unsigned x, int lane) {
 // without it 2 * adj is an integer and the tile keeps THAT as int32 (half the shared memory: three
 // CTAs per SM instead of two), the factor 1/2 folded into the Savitzky-Golay coefficients
 // (fma(c/2, 2a, acc) == fma(c, a, acc) bit for bit).
-template <typename InT, bool SHIFT, int SGW>   // SGW: 21 = unrolled default, 0 = runtime window, -1 = no smoothing
+// MOM: exact sliding-moment smoothing (no SHIFT, rational coefficients given): the adjusted values then sit
+// unpadded in shared memory (the 1-in-16 padding only serves the fp64 stencil's 8-byte reads)
+template <typename InT, bool SHIFT, int SGW, bool MOM>   // SGW: 21 = unrolled default, 0 = runtime window, -1 = no smoothing
 __global__ void __launch_bounds__(kRankThreads, 3)
 adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_off,
                    const long long *__restrict__ seg_out_off, const double *__restrict__ seg_shift,
@@ -478,6 +480,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
     short *__restrict__ xs = reinterpret_cast<short *>(rank_smem + o_x);
     const int nwp = G.nwp;
 
+    auto aslot = [](int e) { return MOM ? e : sg_slot(e); };
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int sg = tile_seg[tile];
@@ -605,7 +608,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
             int m = locate(j0, kl + 1, flo, fhi);
             if (m >= 0 && m < kRankLevels) {
                 int c_lt = flo, hm = fhi - flo;
-                int slot_i = sg_slot(j0);
+                int slot_i = aslot(j0);
                 for (;;) {
                     const int j = j0 + i_first;
                     int ru = m;                              // upper median: same level unless rank ku is past it
@@ -627,7 +630,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
                     const int xo = xs[j], xi = xs[j + w];
                     c_lt += (xi < lv) - (xo < lv);
                     hm += (xi == lv) - (xo == lv);
-                    slot_i += 1 + (((j + 1) & 15) == 0);
+                    slot_i += MOM ? 1 : 1 + (((j + 1) & 15) == 0);
                     bool ok = true;
                     while (c_lt > kl) {                      // median moved down
                         if (--m < 1) { ok = false; break; }
@@ -652,7 +655,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
             for (int i = i_first; i < mine_n; ++i) {
                 const int j = j0 + i;
                 const bool need_m = !((done_m >> i) & 1u), need_u = !((done_u >> i) & 1u);
-                short *__restrict__ slot = reinterpret_cast<short *>(adj + sg_slot(j));
+                short *__restrict__ slot = reinterpret_cast<short *>(adj + aslot(j));
                 if (!need_m) { valid = false; }
                 else if (valid) {
                     const int lv = L0 - 1 + m;
@@ -720,18 +723,18 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
         if (SHIFT) {
             const double shift = seg_shift[sg];
             for (int j = tid; j < A; j += kRankThreads) {
-                const short *slot = reinterpret_cast<const short *>(adj + sg_slot(j));
+                const short *slot = reinterpret_cast<const short *>(adj + aslot(j));
                 const int vm = slot[0], vu = slot[1];
                 const int bc = xs[j + (w >> 1)];
                 const double lo_s = (double)vm - shift, hi_s = (double)vu - shift;
-                adj[sg_slot(j)] = (AdjT)(((double)bc - shift) - (lo_s + hi_s) / 2.0);
+                adj[aslot(j)] = (AdjT)(((double)bc - shift) - (lo_s + hi_s) / 2.0);
             }
         } else {
             for (int i = n_fast; i < mine_n; ++i) {                  // usually none
                 const int j = j0 + i;
-                const short *slot = reinterpret_cast<const short *>(adj + sg_slot(j));
+                const short *slot = reinterpret_cast<const short *>(adj + aslot(j));
                 const int vm = slot[0], vu = slot[1];
-                adj[sg_slot(j)] = (AdjT)(2 * (int)xs[j + (w >> 1)] - vm - vu);   // 2 * adj, exact
+                adj[aslot(j)] = (AdjT)(2 * (int)xs[j + (w >> 1)] - vm - vu);   // 2 * adj, exact
             }
         }
     }
@@ -740,13 +743,13 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
     // ---- Savitzky-Golay on the shared-memory series + coalesced store
     double *__restrict__ dst = out + seg_out_off[sg] + t0;
     auto val = [&](int k) -> double {            // adjusted value at tile-relative index k (edge fits, no smoothing)
-        return SHIFT ? (double)adj[sg_slot(k)] : (double)adj[sg_slot(k)] * 0.5;
+        return SHIFT ? (double)adj[aslot(k)] : (double)adj[aslot(k)] * 0.5;
     };
     if (SGW < 0) {
         for (int k = tid; k < n_t; k += kRankThreads) dst[k] = val(t0 - a0 + k);
         return;
     }
-    if (!SHIFT && sg_scale != 0.0) {
+    if (MOM) {
         // Exact sliding-moment smoothing.  For polynomial degree <= 3 the interior coefficients are
         // c_i = (sg_a + sg_b * i^2) / den, so with x = 2 * adj (integers)
         //     y_j = (sg_a * S0_j + sg_b * M2_j) / (2 den),  S0 = sum x, M1 = sum i x, M2 = sum i^2 x over the window,
@@ -766,20 +769,17 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
         const long long s2sum = (long long)h * h1 * (2 * h + 1) / 3;
         const bool sg_fit32 = (aa * sg_w + bb * s2sum) * (1ll << 17) < (1ll << 31);
         int S0 = 0, M1 = 0, M2 = 0;
-        bool valid = false;
-        for (int k = k_lo; k < k_hi; ++k) {
-            const int j = t0 + k;                // segment-relative output index
-            const int c = j - a0;                // index of its adjusted value in the tile
-            if (j < h || j >= n_out - h) { valid = false; continue; }     // edge outputs: below
-            if (!valid) {
-                S0 = M1 = M2 = 0;
+        // interior outputs of this thread's run (the segment's first / last `half` outputs are edge fits, below)
+        const int ki_lo = max(k_lo, h - t0), ki_hi = min(k_hi, n_out - h - t0);
+        for (int k = ki_lo; k < ki_hi; ++k) {
+            const int c = t0 + k - a0;           // index of the output's adjusted value in the tile
+            if (k == ki_lo) {
                 for (int i = -h; i <= h; ++i) {
-                    const int xv = adj[sg_slot(c + i)];
+                    const int xv = adj[aslot(c + i)];
                     S0 += xv; M1 += i * xv; M2 += i * i * xv;
                 }
-                valid = true;
             } else {                              // window centre c - 1 -> c
-                const int xo = adj[sg_slot(c - h1)], xi = adj[sg_slot(c + h)];
+                const int xo = adj[aslot(c - h1)], xi = adj[aslot(c + h)];
                 M2 += S0 - 2 * M1 - h1h1 * xo + hh * xi;
                 M1 += h1 * xo + h * xi - S0;
                 S0 += xi - xo;
@@ -821,25 +821,25 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
         // s_coef holds c (SHIFT) or c / 2 (the tile then stores 2 * adj): the products are the same
         if (c0 >= 0 && c0 + taps + 3 <= A) {     // every tap in range: unguarded loads
             const AdjT *__restrict__ p = adj;
-            double r0 = (double)p[sg_slot(c0)], r1 = (double)p[sg_slot(c0 + 1)], r2 = (double)p[sg_slot(c0 + 2)];
+            double r0 = (double)p[aslot(c0)], r1 = (double)p[aslot(c0 + 1)], r2 = (double)p[aslot(c0 + 2)];
             if (SGW > 0) {
 #pragma unroll
                 for (int i = 0; i < (SGW > 0 ? SGW : 1); ++i) {
-                    const double r3 = (double)p[sg_slot(c0 + i + 3)];
+                    const double r3 = (double)p[aslot(c0 + i + 3)];
                     const double c = s_coef[i];
                     acc0 += c * r0; acc1 += c * r1; acc2 += c * r2; acc3 += c * r3;
                     r0 = r1; r1 = r2; r2 = r3;
                 }
             } else {
                 for (int i = 0; i < sg_w; ++i) {
-                    const double r3 = (double)p[sg_slot(c0 + i + 3)];
+                    const double r3 = (double)p[aslot(c0 + i + 3)];
                     const double c = s_coef[i];
                     acc0 += c * r0; acc1 += c * r1; acc2 += c * r2; acc3 += c * r3;
                     r0 = r1; r1 = r2; r2 = r3;
                 }
             }
         } else {
-            auto ld = [&](int k) -> double { return (k >= 0 && k < A) ? (double)adj[sg_slot(k)] : 0.0; };
+            auto ld = [&](int k) -> double { return (k >= 0 && k < A) ? (double)adj[aslot(k)] : 0.0; };
             double r0 = ld(c0), r1 = ld(c0 + 1), r2 = ld(c0 + 2);
             for (int i = 0; i < taps; ++i) {
                 const double r3 = ld(c0 + i + 3);
@@ -996,20 +996,22 @@ static int launch_rank(const InT *x, const long long *so, const long long *oo, c
                        long long sg_b, double sg_scale, int a_cap, int s_cap,
                        double *out, unsigned char *flag, cudaStream_t stream) {
     const unsigned grid = (unsigned)n_tiles;
-#define FTK_RANK(SHIFT, SGW)                                                                                      \
+#define FTK_RANK(SHIFT, SGW, MOM)                                                                                      \
     do {                                                                                                          \
         const int smem = (int)rank_smem_bytes(a_cap, s_cap, SHIFT);                                               \
         if (smem > 227 * 1024) return FTK_E_RANGE;                                                                \
-        FTK_CUDA_TRY(cudaFuncSetAttribute(adjust_rank_kernel<InT, SHIFT, SGW>,                                     \
+        FTK_CUDA_TRY(cudaFuncSetAttribute(adjust_rank_kernel<InT, SHIFT, SGW, MOM>,                                \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
-        adjust_rank_kernel<InT, SHIFT, SGW><<<grid, kRankThreads, smem, stream>>>(                                 \
+        adjust_rank_kernel<InT, SHIFT, SGW, MOM><<<grid, kRankThreads, smem, stream>>>(                            \
             x, so, oo, seg_shift, tile_seg, tile_t0, tile_n, w, sg_w, coef, ef, el, sg_a, sg_b, sg_scale, a_cap,  \
             s_cap, out, flag);                                                                                    \
     } while (0)
     if (seg_shift) {
-        if (sg_w == 0) FTK_RANK(true, -1); else if (sg_w == 21) FTK_RANK(true, 21); else FTK_RANK(true, 0);
+        if (sg_w == 0) FTK_RANK(true, -1, false); else if (sg_w == 21) FTK_RANK(true, 21, false); else FTK_RANK(true, 0, false);
+    } else if (sg_w != 0 && sg_scale != 0.0) {       // exact sliding-moment smoothing
+        if (sg_w == 21) FTK_RANK(false, 21, true); else FTK_RANK(false, 0, true);
     } else {
-        if (sg_w == 0) FTK_RANK(false, -1); else if (sg_w == 21) FTK_RANK(false, 21); else FTK_RANK(false, 0);
+        if (sg_w == 0) FTK_RANK(false, -1, false); else if (sg_w == 21) FTK_RANK(false, 21, false); else FTK_RANK(false, 0, false);
     }
 #undef FTK_RANK
     FTK_CHECK_LAUNCH("adjust_rank_kernel");
