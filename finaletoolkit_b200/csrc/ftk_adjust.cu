@@ -414,8 +414,7 @@ __host__ __device__ inline size_t rank_smem_bytes(int a_cap, int s_cap, bool shi
     const RankGeom g = rank_geom(a_cap, s_cap);
     size_t b = (size_t)g.a_slots * (shifted ? sizeof(double) : sizeof(int));
     b = (b + 15) & ~(size_t)15;
-    b += (size_t)kRankLevels * g.nwp * 4;       // bitmaps
-    b += (size_t)kRankLevels * g.nwp * 2;       // per-word prefix popcounts
+    b += (size_t)kRankLevels * g.nwp * 8;       // (bitmap word, prefix popcount) pairs: one 64-bit read per rank query
     b = (b + 15) & ~(size_t)15;
     b += (size_t)(g.s_pad + 32) * 2;            // samples
     return b;
@@ -474,9 +473,8 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
     // adjusted value (double, or the integer 2 * adj)
     AdjT *__restrict__ adj = reinterpret_cast<AdjT *>(rank_smem);
     const size_t o_b = ((size_t)G.a_slots * sizeof(AdjT) + 15) & ~(size_t)15;
-    unsigned *__restrict__ B = reinterpret_cast<unsigned *>(rank_smem + o_b);
-    unsigned short *__restrict__ Wp = reinterpret_cast<unsigned short *>(B + kRankLevels * G.nwp);
-    const size_t o_x = (o_b + (size_t)kRankLevels * G.nwp * 6 + 15) & ~(size_t)15;
+    uint2 *__restrict__ B = reinterpret_cast<uint2 *>(rank_smem + o_b);      // .x bitmap word, .y samples before it <= level
+    const size_t o_x = (o_b + (size_t)kRankLevels * G.nwp * 8 + 15) & ~(size_t)15;
     short *__restrict__ xs = reinterpret_cast<short *>(rank_smem + o_x);
     const int nwp = G.nwp;
 
@@ -548,7 +546,8 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
     const unsigned full_mask = (mine_n >= 32) ? 0xffffffffu : ((1u << mine_n) - 1u);
     auto cnt = [&](int r, int i) -> int {       // #{samples [0, i) <= level r}
         const int wd = i >> 5;
-        return (int)Wp[r * nwp + wd] + __popc(B[r * nwp + wd] & ((1u << (i & 31)) - 1u));
+        const uint2 e = B[r * nwp + wd];
+        return (int)e.y + __popc(e.x & ((1u << (i & 31)) - 1u));
     };
     auto F = [&](int r, int j) -> int { return cnt(r, j + w) - cnt(r, j); };
     // smallest row whose rank count reaches `need`: -1 below the band (row 0 already does), 32 above
@@ -584,8 +583,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
                 // ~0 << d with d clamped to [0, 32]: one max + one clamping funnel shift
                 const unsigned mask = __funnelshift_lc(0u, 0xffffffffu, (unsigned)max(d, 0));
                 const unsigned bits = warp_transpose32(mask, lane);
-                B[lane * nwp + wd] = bits;
-                Wp[lane * nwp + wd] = (unsigned short)run;
+                B[lane * nwp + wd] = make_uint2(bits, (unsigned)run);
                 run += __popc(bits);
             }
             s_tot[warp][lane] = run;
@@ -595,7 +593,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
             int off = 0;
             for (int c = 0; c < warp; ++c) off += s_tot[c][lane];
             if (off)
-                for (int wd = wd_lo; wd < wd_hi; ++wd) Wp[lane * nwp + wd] = (unsigned short)(Wp[lane * nwp + wd] + off);
+                for (int wd = wd_lo; wd < wd_hi; ++wd) B[lane * nwp + wd].y += (unsigned)off;
         }
         __syncthreads();
         // ---- every thread walks its run

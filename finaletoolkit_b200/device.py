@@ -636,7 +636,7 @@ def _rank_smem(a_cap: int, s_cap: int, shifted: bool = True) -> int:
     nword = (s_cap + 31) // 32
     nwp = max((nword + 1) | 1, 69)
     b = (a_slots * (8 if shifted else 4) + 15) & ~15
-    b += 32 * nwp * 6
+    b += 32 * nwp * 8
     b = (b + 15) & ~15
     return b + (nword * 32 + 32) * 2
 
