@@ -461,7 +461,7 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
                    const int *__restrict__ tile_seg, const int *__restrict__ tile_t0,
                    const int *__restrict__ tile_n, int w, int sg_w, const double *__restrict__ coef,
                    const double *__restrict__ edge_first, const double *__restrict__ edge_last,
-                   long long sg_a, long long sg_b, double sg_scale,
+                   long long sg_a, long long sg_b, double sg_scale, int sg_fit32,
                    int a_cap, int s_cap, double *__restrict__ out, unsigned char *__restrict__ tile_flag) {
     extern __shared__ __align__(16) unsigned char rank_smem[];
     __shared__ int s_ctl[4];            // 0: need lower band, 1: need higher band, 2: unused, 3: centre
@@ -763,9 +763,6 @@ adjust_rank_kernel(const InT *__restrict__ x, const long long *__restrict__ seg_
         const int k_lo = min(tid * Ro, n_t), k_hi = min(k_lo + Ro, n_t);
         const int h = half, h1 = half + 1;
         const int hh = h * h, h1h1 = h1 * h1;
-        const long long aa = sg_a < 0 ? -sg_a : sg_a, bb = sg_b < 0 ? -sg_b : sg_b;
-        const long long s2sum = (long long)h * h1 * (2 * h + 1) / 3;
-        const bool sg_fit32 = (aa * sg_w + bb * s2sum) * (1ll << 17) < (1ll << 31);
         int S0 = 0, M1 = 0, M2 = 0;
         // interior outputs of this thread's run (the segment's first / last `half` outputs are edge fits, below)
         const int ki_lo = max(k_lo, h - t0), ki_hi = min(k_hi, n_out - h - t0);
@@ -991,7 +988,7 @@ template <typename InT>
 static int launch_rank(const InT *x, const long long *so, const long long *oo, const double *seg_shift,
                        const int *tile_seg, const int *tile_t0, const int *tile_n, int64_t n_tiles, int w,
                        int sg_w, const double *coef, const double *ef, const double *el, long long sg_a,
-                       long long sg_b, double sg_scale, int a_cap, int s_cap,
+                       long long sg_b, double sg_scale, int sg_fit32, int a_cap, int s_cap,
                        double *out, unsigned char *flag, cudaStream_t stream) {
     const unsigned grid = (unsigned)n_tiles;
 #define FTK_RANK(SHIFT, SGW, MOM)                                                                                      \
@@ -1001,8 +998,8 @@ static int launch_rank(const InT *x, const long long *so, const long long *oo, c
         FTK_CUDA_TRY(cudaFuncSetAttribute(adjust_rank_kernel<InT, SHIFT, SGW, MOM>,                                \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
         adjust_rank_kernel<InT, SHIFT, SGW, MOM><<<grid, kRankThreads, smem, stream>>>(                            \
-            x, so, oo, seg_shift, tile_seg, tile_t0, tile_n, w, sg_w, coef, ef, el, sg_a, sg_b, sg_scale, a_cap,  \
-            s_cap, out, flag);                                                                                    \
+            x, so, oo, seg_shift, tile_seg, tile_t0, tile_n, w, sg_w, coef, ef, el, sg_a, sg_b, sg_scale, sg_fit32,\
+            a_cap, s_cap, out, flag);                                                                                    \
     } while (0)
     if (seg_shift) {
         if (sg_w == 0) FTK_RANK(true, -1, false); else if (sg_w == 21) FTK_RANK(true, 21, false); else FTK_RANK(true, 0, false);
@@ -1031,6 +1028,7 @@ extern "C" int ftk_adjust_rank_f64(const void *x, int32_t x_kind, const int64_t 
     if (a_cap < 1 || a_cap > 32 * kRankThreads || s_cap < a_cap + w || s_cap > 65535 - 64) return FTK_E_RANGE;
     // exact sliding-moment smoothing: only when every intermediate provably fits (|2 adj| < 2^17)
     double sg_scale = 0.0;
+    int sg_fit32 = 0;                    // the final combination a * S0 + b * M2 itself fits int32
     if (sg_w > 0 && sg_den != 0) {
         if (sg_den < 0) return FTK_E_INVALID;
         const long long h = sg_w >> 1;
@@ -1041,7 +1039,10 @@ extern "C" int ftk_adjust_rank_f64(const void *x, int32_t x_kind, const int64_t 
         // combination inside 2^53 (exactly representable)
         if ((s2 + 2 * h * (h + 1) + sg_w + 2 * (h + 1) * (h + 1)) * bound < (1ll << 31) && aa < (1ll << 31) &&
             bb < (1ll << 31) && (aa * sg_w + bb * s2) < (1ll << 36))
+        {
             sg_scale = 0.5 / (double)sg_den;
+            sg_fit32 = (aa * sg_w + bb * s2) * bound < (1ll << 31);
+        }
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     FTK_CUDA_TRY(cudaMemsetAsync(tile_flag, 0, (size_t)n_tiles, stream));
@@ -1049,9 +1050,9 @@ extern "C" int ftk_adjust_rank_f64(const void *x, int32_t x_kind, const int64_t 
     const long long *oo = reinterpret_cast<const long long *>(seg_out_off);
     if (x_kind == 0)
         return launch_rank<float>(static_cast<const float *>(x), so, oo, seg_shift, tile_seg, tile_t0, tile_n, n_tiles,
-                                  w, sg_w, coef, edge_first, edge_last, sg_num_a, sg_num_b, sg_scale, a_cap, s_cap, out,
+                                  w, sg_w, coef, edge_first, edge_last, sg_num_a, sg_num_b, sg_scale, sg_fit32, a_cap, s_cap, out,
                                   tile_flag, stream);
     return launch_rank<int>(static_cast<const int *>(x), so, oo, seg_shift, tile_seg, tile_t0, tile_n, n_tiles,
-                            w, sg_w, coef, edge_first, edge_last, sg_num_a, sg_num_b, sg_scale, a_cap, s_cap, out,
+                            w, sg_w, coef, edge_first, edge_last, sg_num_a, sg_num_b, sg_scale, sg_fit32, a_cap, s_cap, out,
                             tile_flag, stream);
 }
