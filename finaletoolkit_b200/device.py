@@ -299,7 +299,7 @@ class WpsPlan:
 
 _POLICY = {"midpoint": 0, "any": 1}
 _TARGET_CTAS = 148 * 8  # SM count x resident CTAs: enough slices to fill the chip
-_UNIT_FRAGS = 2048
+_UNIT_FRAGS = 8192      # fragments per (interval, split) unit: 8 K measured best for Mb-scale bins (2 K: +10 %, 32 K: +7 %)
 
 
 def policy_code(intersect_policy: str) -> int:
