@@ -17,7 +17,7 @@ from ..io.fragments import FragmentTable, as_table
 from ..io.textout import GzipTextWriter, bedgraph_text
 from ..utils import chrom_sizes_to_list
 from ._common import group_by_contig, resolve_length_aliases
-from ._wps import _wps_device
+from ._wps import _wps_device, _wps_streamed
 
 __all__ = ["multi_wps", "LAST_TIMINGS"]
 
@@ -103,13 +103,20 @@ def multi_wps(input_file, site_bed, chrom_sizes=None, output_file=None, window_s
 
     # one GPU launch per contig, results kept in interval order
     results: list = [None] * len(contigs)
+    n_streamed = 0
     t_decoded = time.perf_counter()
     for contig, idx in group_by_contig(contigs).items():
         table.host(contig)      # lazy tables decode here: keep it out of the compute share
-        out, off = _wps_device(table, contig, [starts[i] for i in idx], [stops[i] for i in idx],
-                               chrom_sizes_dict[contig], int(window_size), min_length, int(round(max_length)),
-                               quality_threshold)
-        host = out.cpu().numpy()
+        args = (table, contig, [starts[i] for i in idx], [stops[i] for i in idx], chrom_sizes_dict[contig],
+                int(window_size), min_length, int(round(max_length)), quality_threshold)
+        # large contigs stream (pinned columns, chunked H2D || kernels || D2H, int16 scores); small ones upload whole
+        streamed = _wps_streamed(*args)
+        if streamed is not None:
+            host, off = streamed
+            n_streamed += 1
+        else:
+            out, off = _wps_device(*args)
+            host = out.cpu().numpy()
         for k, i in enumerate(idx):
             results[i] = host[off[k]: off[k + 1]]
 
@@ -134,7 +141,7 @@ def multi_wps(input_file, site_bed, chrom_sizes=None, output_file=None, window_s
     t_end = time.perf_counter()
     LAST_TIMINGS.clear()
     LAST_TIMINGS.update(decode=t_decoded - t_begin, compute=t_computed - t_decoded, write=t_end - t_computed,
-                        total=t_end - t_begin)
+                        total=t_end - t_begin, streamed_contigs=n_streamed)
     if verbose:
         stderr.write(f"multi_wps took {time.time() - start_time} s to complete\n")
     return output_file

@@ -30,6 +30,37 @@ def _wps_device(table, chrom, starts, stops, chrom_size, window_size, min_length
     return plan.run(frags, window_size, min_length, max_length, quality_threshold), plan.offsets
 
 
+_STREAM_MIN_FRAGMENTS = 1 << 21     # below this a contig's columns are uploaded whole (nothing to overlap)
+
+
+def _wps_streamed(table, chrom, starts, stops, chrom_size, window_size, min_length, max_length,
+                  quality_threshold, device=None):
+    """WPS of every interval of one large contig through the streamed pipeline: the contig's host columns are
+    page-locked in place, chunks of intervals go H2D (double-buffered) || kernels || D2H on three streams
+    (``pipeline.StreamedContig``) and the scores arrive in pinned host memory as int16 (a quarter of the int64
+    the reference returns, half of int32 on PCIe).  Returns ``(host scores, offsets)`` or ``None`` when the
+    contig is small, its intervals are not start-sorted, its pages cannot be locked or a score does not fit
+    int16 (a > 32767-fold pile-up) - the caller then takes the resident path.  Same numbers either way."""
+    from ..device import require_cuda
+    from ..pipeline import StreamedContig
+    n = table.n_fragments(chrom)
+    s = np.asarray(starts, dtype=np.int64)
+    if n < _STREAM_MIN_FRAGMENTS or len(s) < 16 or np.any(s[1:] < s[:-1]):
+        return None
+    cols = table.pinned(chrom)
+    if cols is None:
+        return None
+    h_start, h_stop, h_mapq = cols
+    try:
+        pipe = StreamedContig(h_start, h_stop, h_mapq, s, np.asarray(stops, dtype=np.int64), int(chrom_size),
+                              int(window_size), min_length, int(max_length), int(quality_threshold), n_chunks=8,
+                              device=require_cuda(device), coverage=False, length_hist=False, wps_dtype="int16")
+        w, _, _, _ = pipe.run()
+    except OverflowError:
+        return None
+    return w.numpy()[: pipe.n_positions], pipe.offsets
+
+
 def wps(input_file, chrom, start, stop, chrom_size, output_file=None, window_size=120, min_length=120,
         max_length=180, quality_threshold=30, verbose=0, fraction_low=None, fraction_high=None,
         reference_file=None) -> np.ndarray:

@@ -102,6 +102,31 @@ class FragmentTable:
             return z, z.copy(), np.zeros(0, np.uint8), np.zeros(0, np.uint8)
         return self.columns[contig]
 
+    def pinned(self, contig: str):
+        """``(start, stop, mapq)`` of one contig as CPU torch tensors that SHARE the host columns' memory,
+        page-locked in place with ``cudaHostRegister`` (once per contig, released with the table) - what
+        the streamed pipeline (``pipeline.StreamedContig``) copies from without an intermediate staging
+        buffer.  ``None`` when the pages cannot be locked (the caller falls back to the resident upload)."""
+        import weakref
+        import torch
+        cache = self.__dict__.setdefault("_pinned", {})
+        if contig in cache:
+            return cache[contig]
+        st, sp, mq, _ = self.host(contig)
+        tensors, ok = [], True
+        rt = torch.cuda.cudart()
+        for a in (st, sp, mq):
+            t = torch.from_numpy(a)
+            if a.nbytes and not t.is_pinned():
+                rc = rt.cudaHostRegister(t.data_ptr(), a.nbytes, 0)
+                if int(rc) != 0:
+                    ok = False
+                    break
+                weakref.finalize(self, _unregister, t.data_ptr())
+            tensors.append(t)
+        cache[contig] = tuple(tensors) if ok and all(t.is_pinned() or t.numel() == 0 for t in tensors) else None
+        return cache[contig]
+
     def device(self, contig: str, device=None):
         """``ContigFragments`` of one contig in HBM (uploaded once, then cached)."""
         from ..device import ContigFragments, require_cuda
@@ -111,6 +136,14 @@ class FragmentTable:
             st, sp, mq, sd = self.host(contig)
             self._device[key] = ContigFragments(st, sp, mq, sd, device=dev, contig=contig)
         return self._device[key]
+
+
+def _unregister(ptr: int) -> None:
+    try:
+        import torch
+        torch.cuda.cudart().cudaHostUnregister(ptr)
+    except Exception:  # noqa: BLE001 - interpreter shutdown / context already gone
+        pass
 
 
 _CACHE: dict = {}

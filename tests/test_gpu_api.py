@@ -270,3 +270,36 @@ def test_bam_input(tmp_path, manifest, golden):
     assert [np.asarray(bins).tolist(), np.asarray(counts).tolist()] == m["bam_frag_length_bins"]
     got = [list(x) for x in F.frag_generator(bam, "12", quality_threshold=0)]
     assert [x[1] for x in got] == np.sort(g["bam_start"]).tolist() and len(got) == 17
+
+
+def test_multi_wps_streams_large_contigs(tmp_path, monkeypatch):
+    """multi_wps sends a large contig through the streamed pipeline (host columns page-locked in place, chunked
+    H2D || kernels || D2H, int16 scores in pinned memory) and a small one through the resident upload; the output
+    text is byte-identical to the all-resident run, and spot intervals equal the oracle."""
+    import finaletoolkit_b200 as F
+    from finaletoolkit_b200.frag import _multi_wps, _wps
+    from finaletoolkit_b200.io.fragments import FragmentTable
+    from finaletoolkit_b200.synth import synth_fragments
+    from oracle import oracle as O
+    big_len, small_len = 8_000_000, 300_000
+    cols = {"1": synth_fragments(big_len, 2_600_000, 3, seed_base=880), "2": synth_fragments(small_len, 90_000, 4, seed_base=880)}
+    table = FragmentTable(cols)
+    cs = tmp_path / "cs.txt"; cs.write_text(f"1\t{big_len}\n2\t{small_len}\n")
+    rng = np.random.default_rng(12)
+    rows = [("1", int(p)) for p in np.sort(rng.integers(3000, big_len - 3000, 400))] + \
+           [("2", int(p)) for p in np.sort(rng.integers(3000, small_len - 3000, 20))]
+    sites = tmp_path / "sites.bed"
+    sites.write_text("".join(f"{c}\t{p}\t{p + 1}\tx\t0\t+\n" for c, p in rows))
+    out_a, out_b = str(tmp_path / "a.bed.gz"), str(tmp_path / "b.bed.gz")
+    F.multi_wps(table, str(sites), chrom_sizes=str(cs), output_file=out_a)
+    assert _multi_wps.LAST_TIMINGS["streamed_contigs"] == 1
+    monkeypatch.setattr(_wps, "_STREAM_MIN_FRAGMENTS", 1 << 40)
+    F.multi_wps(table, str(sites), chrom_sizes=str(cs), output_file=out_b)
+    assert _multi_wps.LAST_TIMINGS["streamed_contigs"] == 0
+    ta, tb = read_gz(out_a), read_gz(out_b)
+    assert ta == tb and len(ta.splitlines()) > 1_000_000
+    # spot check against the oracle: the first window of contig 1
+    p = rows[0][1]
+    exp = O.wps_interval(O.Frags(*cols["1"]), p - 2500, p + 2500, big_len, 120, 120, 180, 30)
+    got = [int(l.split("\t")[3]) for l in ta.splitlines()[:5000]]
+    assert ta.splitlines()[0].startswith(f"1\t{p - 2500}\t") and np.array_equal(np.array(got[: len(exp)]), exp)
