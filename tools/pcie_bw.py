@@ -1,4 +1,6 @@
 """Profiling helper: pinned H2D / D2H bandwidth alone and in duplex (explains the e2e bound)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 dev = "cuda:0"
 n = 720_000_000

@@ -1,4 +1,6 @@
 """Profiling helper (run from the repo root: PYTHONPATH=. python tools/...): adjust_wps timing at chr1 scale (raw WPS from our kernel -> float32 -> adjust)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sys
 import numpy as np, torch
 from finaletoolkit_b200.device import ContigFragments, WpsPlan, adjust_segments

@@ -1,4 +1,6 @@
 """Profiling helper (PYTHONPATH=. python tools/quick_motif.py [k] [breakpoint]): end-motif kernel at chr1 scale."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sys
 import numpy as np, torch
 from finaletoolkit_b200 import device as D

@@ -1,4 +1,6 @@
 """Profiling helper (run from the repo root: PYTHONPATH=. python tools/...): quick WPS timing at config 2 (chr1-scale) - not the bench contract."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sys, time
 import numpy as np, torch, os, ctypes
 from finaletoolkit_b200._lib import lib
