@@ -50,7 +50,7 @@ def _wps_streamed(table, chrom, starts, stops, chrom_size, window_size, min_leng
     cols = table.pinned(chrom)
     if cols is None:
         return None
-    h_start, h_stop, h_mapq = cols
+    h_start, h_stop, h_mapq = cols[:3]
     try:
         pipe = StreamedContig(h_start, h_stop, h_mapq, s, np.asarray(stops, dtype=np.int64), int(chrom_size),
                               int(window_size), min_length, int(max_length), int(quality_threshold), n_chunks=8,
