@@ -135,9 +135,16 @@ def multi_wps(input_file, site_bed, chrom_sizes=None, output_file=None, window_s
                         stderr.write("/n invalid or out of order interval encountered. Skipping to next.\n")
                         continue
         else:
-            with GzipTextWriter(output_file) as bedgraph:   # frag/_multi_wps.py:328-341, same text
-                for contig, start, scores in zip(contigs, starts, results):
-                    bedgraph.write(bedgraph_text(contig, start, scores))
+            # frag/_multi_wps.py:328-341, same text.  The lines of the intervals are formatted by a pool of
+            # host threads (the native formatter releases the GIL; one 5-kb interval is too short to split) and
+            # handed to the writer in interval order
+            import os
+            from concurrent.futures import ThreadPoolExecutor
+            with GzipTextWriter(output_file) as bedgraph, ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as pool:
+                fmt = lambda i: bedgraph_text(contigs[i], starts[i], results[i])          # noqa: E731
+                for b0 in range(0, len(contigs), 512):        # bounded look-ahead: 512 intervals of text in memory
+                    for text in pool.map(fmt, range(b0, min(b0 + 512, len(contigs)))):
+                        bedgraph.write(text)
     t_end = time.perf_counter()
     LAST_TIMINGS.clear()
     LAST_TIMINGS.update(decode=t_decoded - t_begin, compute=t_computed - t_decoded, write=t_end - t_computed,
