@@ -3,7 +3,7 @@
 The device kernels finish a chr1-scale shard in well under a millisecond, so the end-to-end
 time of the reference-facing call is PCIe.  This module keeps the link busy and the bytes few:
 
-* fragments cross the link PACKED (``packed.PackedFragments``: 4.06 B per fragment instead of the
+* fragments cross the link PACKED (``packed.PackedFragments``: 3.06 - 4.06 B per fragment instead of the
   9 B of the int32/int32/uint8 columns) and are unpacked on the device (``ftk_unpack_fragments``);
 * the contig is cut into ``n_chunks`` runs of intervals; chunk c's fragment slice (plus halo) is
   copied host->device on one stream while chunk c-1 computes on a second stream and chunk c-2's

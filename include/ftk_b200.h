@@ -57,7 +57,7 @@ const char *ftk_last_cuda_error(void);
 
 /* ------------------------------------------------- packed fragment columns
  * Wire format host -> HBM, replacing the per-interval text stream of io/alignment.py:270-302 /
- * utils/_frag_generator.py:124-130 (PCIe is the end-to-end limit: 4.06 B per fragment instead of 10).
+ * utils/_frag_generator.py:124-130 (PCIe is the end-to-end limit: 3.06 - 4.06 B per fragment instead of 10).
  *   words[i]  = dstart | length << 11 | strand << 23 | mapq << 24   (uint32; dstart = start[i] - start[i-1],
  *               0 for the first fragment of a block; dstart < 2048, length < 4096)
  *   anchors[b] = start of the first fragment of block b (FTK_PACK_BLOCK fragments), or -1 - r when the
