@@ -605,3 +605,25 @@ def test_native_bam_decoder(tmp_path, manifest, golden):
     with pytest.raises(UnsupportedFormatError):
         fragments.load_fragments(str(cut))
     fragments._CACHE.clear()
+
+
+def test_savgol_rational_coefficients():
+    """The exact rational form of the interior Savitzky-Golay coefficients the sliding-moment smoothing uses
+    (device.savgol_rational: c_i = (a + b i^2) / den) against scipy's own coefficients and exact fractions."""
+    from fractions import Fraction
+    from scipy.signal import savgol_coeffs
+    from finaletoolkit_b200.device import savgol_rational
+    assert savgol_rational(21, 2) == (329, -5, 3059)            # the textbook 21-point quadratic smoother
+    for m in range(3, 61, 2):
+        h = m // 2
+        for deg in range(0, min(m, 6)):
+            a, b, den = savgol_rational(m, deg)
+            if deg >= 4:
+                assert (a, b, den) == (0, 0, 0)
+                continue
+            assert den > 0
+            c = np.array([(a + b * i * i) / den for i in range(-h, h + 1)])
+            assert np.abs(c - savgol_coeffs(m, deg)).max() < 1e-12, (m, deg)
+            assert sum(Fraction(a + b * i * i, den) for i in range(-h, h + 1)) == 1      # a smoother preserves constants
+            if deg >= 2:                                                                   # ... and quadratics
+                assert sum(Fraction(a + b * i * i, den) * i * i for i in range(-h, h + 1)) == 0
