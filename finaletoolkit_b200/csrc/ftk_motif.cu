@@ -298,6 +298,8 @@ static int motif_hist_launch(const int32_t *frag_start, const int32_t *frag_stop
     // the common cases are compiled with K and the strand mode fixed; everything else takes the runtime variant
     if (k == 4 && strand_mode == 0) FTK_MOTIF(4, 0, true);
     else if (k == 6 && strand_mode == 0) FTK_MOTIF(6, 0, true);
+    else if (k == 3 && strand_mode == 0) FTK_MOTIF(3, 0, true);
+    else if (k == 5 && strand_mode == 0) FTK_MOTIF(5, 0, true);
     else if ((1 << (2 * k)) <= kMotifSmemBins) FTK_MOTIF(0, 3, true);
     else FTK_MOTIF(0, 3, false);
 #undef FTK_MOTIF
