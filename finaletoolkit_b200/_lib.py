@@ -85,6 +85,7 @@ SYMBOLS = {
     "ftk_fragfile_contig_name": (c_char_p, [c_void_p, c_int32]),
     "ftk_fragfile_contig_count": (c_int64, [c_void_p, c_int32]),
     "ftk_fragfile_copy": (c_int, [c_void_p, c_int32, _i32p, _i32p, _u8p, _u8p]),
+    "ftk_fragfile_copy_read1": (c_int, [c_void_p, c_int32, _i32p, _i32p]),
     "ftk_fragfile_close": (None, [c_void_p]),
     "ftk_zlib_compress_batch": (c_int, [_u8p, _i64p, c_int64, c_int32, c_int32, _u8p, _i64p, _i64p]),
     "ftk_format_bedgraph_i64": (c_int64, [c_char_p, c_int64, _i64p, c_int64, c_int32, c_void_p, c_int64]),

@@ -30,6 +30,7 @@ struct Columns {
     std::string name;
     std::vector<int32_t> start, stop;
     std::vector<uint8_t> mapq, strand;
+    std::vector<int32_t> r1_start, r1_end;   // BAM only: reference span of read 1 (what an indexed fetch tests)
 };
 
 struct FragFile {
@@ -408,20 +409,26 @@ const unsigned char *bam_consume(const unsigned char *p, const unsigned char *en
         // paired, proper pair; not unmapped / mate unmapped / read2 / secondary / QC fail / duplicate / supplementary
         if ((flag & 0x3u) != 0x3u || (flag & (0x4u | 0x8u | 0x80u | 0x100u | 0x200u | 0x400u | 0x800u))) continue;
         if (tlen == 0 || ref_id < 0 || (size_t)ref_id >= st.ref_names.size()) continue;
-        int64_t fs, fe;
-        if (tlen > 0) {
-            fs = pos; fe = (int64_t)pos + tlen;
-        } else {
-            if (n_cigar == 0 || 32 + (int64_t)l_read_name + 4 * (int64_t)n_cigar > bs) continue;
-            int64_t ref_end = pos;
+        // reference span of the read itself: htslib's region test is `pos < stop && bam_endpos > start`,
+        // bam_endpos = pos + (reference bases the CIGAR consumes, 1 when there are none)
+        const bool cigar_ok = n_cigar != 0 && 32 + (int64_t)l_read_name + 4 * (int64_t)n_cigar <= bs;
+        int64_t ref_end = pos;
+        if (cigar_ok) {
             const unsigned char *c = r + 32 + l_read_name;
             for (unsigned k = 0; k < n_cigar; ++k) {
                 const uint32_t op = rd_u32(c + 4 * k);
                 const unsigned code = op & 15u;   // M, D, N, =, X consume the reference
                 if (code == 0 || code == 2 || code == 3 || code == 7 || code == 8) ref_end += op >> 4;
             }
+        }
+        int64_t fs, fe;
+        if (tlen > 0) {
+            fs = pos; fe = (int64_t)pos + tlen;
+        } else {
+            if (!cigar_ok) continue;   // pysam: reference_end is None without an alignment
             fs = ref_end + tlen; fe = ref_end;
         }
+        const int64_t r1e = std::min<int64_t>(ref_end > pos ? ref_end : (int64_t)pos + 1, INT32_MAX);
         if (fs < INT32_MIN || fs > INT32_MAX || fe < INT32_MIN || fe > INT32_MAX) continue;
         int &col = st.ref_to_col[(size_t)ref_id];
         if (col < 0) {
@@ -432,6 +439,7 @@ const unsigned char *bam_consume(const unsigned char *p, const unsigned char *en
         Columns &dst = ff.contigs[(size_t)col];
         dst.start.push_back((int32_t)fs); dst.stop.push_back((int32_t)fe);
         dst.mapq.push_back((uint8_t)mapq); dst.strand.push_back((flag & 0x10u) ? 0 : 1);
+        dst.r1_start.push_back(pos); dst.r1_end.push_back((int32_t)r1e);
     }
     return p;
 }
@@ -534,6 +542,17 @@ extern "C" int ftk_fragfile_copy(void *h, int32_t i, int32_t *start, int32_t *st
         memcpy(start, c.start.data(), n * 4); memcpy(stop, c.stop.data(), n * 4);
         memcpy(mapq, c.mapq.data(), n); memcpy(strand, c.strand.data(), n);
     }
+    return FTK_OK;
+}
+// read-1 reference spans of a BAM-derived contig (same row order as ftk_fragfile_copy); 1 = the handle has
+// none (fragment files), 0 = copied
+extern "C" int ftk_fragfile_copy_read1(void *h, int32_t i, int32_t *r1_start, int32_t *r1_end) {
+    FragFile *ff = static_cast<FragFile *>(h);
+    if (!ff || i < 0 || (size_t)i >= ff->contigs.size() || !r1_start || !r1_end) return FTK_E_INVALID;
+    const Columns &c = ff->contigs[(size_t)i];
+    const size_t n = c.start.size();
+    if (c.r1_start.size() != n || c.r1_end.size() != n) return 1;
+    if (n) { memcpy(r1_start, c.r1_start.data(), n * 4); memcpy(r1_end, c.r1_end.data(), n * 4); }
     return FTK_OK;
 }
 extern "C" void ftk_fragfile_close(void *h) { delete static_cast<FragFile *>(h); }

@@ -85,8 +85,8 @@ def genome_end_motif_counts(table, ref, k=4, strand_mode=0, quality_threshold=30
                             ctx: DistContext | None = None, device=None, breakpoint=False) -> np.ndarray:
     """int64[4**k] genome-wide end-motif (or, with ``breakpoint``, breakpoint-motif) counts over every
     contig's 1 Mb windows, one all-reduce."""
-    from .device import end_motif_hist, require_cuda, torch
-    from .frag._motif_common import genome_windows
+    from .device import require_cuda, torch
+    from .frag._motif_common import genome_windows, pooled_window_counts
     ctx = ctx or DistContext()
     dev = require_cuda(device)
     t = torch()
@@ -95,10 +95,8 @@ def genome_end_motif_counts(table, ref, k=4, strand_mode=0, quality_threshold=30
     for chrom, chrom_length in ref.chroms.items():
         if chrom not in mine or not table.n_fragments(chrom):
             continue
-        w = genome_windows(chrom_length)
-        end_motif_hist(table.device(chrom, dev), ref.device_contig(chrom, dev), [a for a, _ in w], [b for _, b in w],
-                       k=k, strand_mode=strand_mode, quality_threshold=quality_threshold, pooled=True, counts=total,
-                       breakpoint=breakpoint)
+        pooled_window_counts(table, ref, chrom, genome_windows(chrom_length), k, strand_mode, quality_threshold,
+                             breakpoint=breakpoint, total=total, device=dev)
     ctx.all_reduce_sum(total)
     return total[0].cpu().numpy()
 
@@ -112,7 +110,8 @@ def genome_delfi_windows(table, ref, bins_by_contig, blacklist_by_contig=None, g
     ``bins_by_contig``: {contig: (starts, stops)}; ``blacklist_by_contig``: {contig: (starts, stops)}
     sorted by (start, stop); ``gaps_by_contig``: {contig: (centromere, telomeres)}.
     Returns {contig: int64[n_bins, 4]} = short, long, num_frags, G+C bases, identical on every rank."""
-    from .device import delfi_windows, require_cuda, torch
+    from .device import require_cuda, torch
+    from .frag._delfi import delfi_rows
     ctx = ctx or DistContext()
     dev = require_cuda(device)
     t = torch()
@@ -127,11 +126,9 @@ def genome_delfi_windows(table, ref, bins_by_contig, blacklist_by_contig=None, g
         if not owner_here:
             continue
         ws, we = bins_by_contig[chrom]
-        got = delfi_windows(table.device(chrom, dev), ref.device_contig(chrom, dev) if chrom in ref.chroms else None,
-                            np.asarray(ws, np.int64), np.asarray(we, np.int64),
-                            blacklist=(blacklist_by_contig or {}).get(chrom), gaps=(gaps_by_contig or {}).get(chrom),
-                            quality_threshold=quality_threshold)
-        packed[int(offs[i]): int(offs[i + 1])] = got
+        got = delfi_rows(table, ref, chrom, np.asarray(ws, np.int64).tolist(), np.asarray(we, np.int64).tolist(),
+                         (blacklist_by_contig or {}).get(chrom), (gaps_by_contig or {}).get(chrom), quality_threshold, dev)
+        packed[int(offs[i]): int(offs[i + 1])] = t.from_numpy(got).to(dev)
     ctx.all_reduce_sum(packed)
     host = packed.cpu().numpy()
     return {c: host[int(offs[i]): int(offs[i + 1])] for i, c in enumerate(names)}

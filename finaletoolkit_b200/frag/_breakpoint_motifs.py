@@ -17,7 +17,8 @@ from ..io.fragments import as_table
 from ..utils import gen_kmers
 from ._common import dist_context, group_by_contig, is_writer, resolve_length_aliases
 from ._end_motifs import _ref, _strand_mode
-from ._motif_common import _BASES, _MotifFreqs, _MotifsIntervals, genome_windows, parse_intervals_arg, write_motif_freqs
+from ._motif_common import (_BASES, _MotifFreqs, _MotifsIntervals, genome_windows, interval_motif_rows,
+                            parse_intervals_arg, pooled_window_counts, write_motif_freqs)
 
 __all__ = ["BreakpointMotifFreqs", "BreakpointMotifsIntervals", "region_breakpoint_motifs", "breakpoint_motifs",
            "interval_breakpoint_motifs"]
@@ -42,6 +43,8 @@ def region_breakpoint_motifs(input_file, contig, start, stop, refseq_file, k=6, 
     table = as_table(input_file, refseq_file)
     ref = _ref(refseq_file)
     kmer_list = gen_kmers(k, "ACGT")
+    if table.has_read1(contig):   # BAM: what an indexed fetch of the region yields
+        table = table.fetched(contig, int(start), int(stop))
     if table.n_fragments(contig) == 0:
         return dict(zip(kmer_list, 4 ** k * [0]))
     counts = end_motif_hist(table.device(contig), ref.device_contig(contig), [int(start)], [int(stop)], k=k,
@@ -55,7 +58,6 @@ def breakpoint_motifs(input_file, refseq_file, k=6, min_length=50, max_length=No
                       negative_strand=False, output_file=None, quality_threshold=30, workers=1, verbose=False,
                       fraction_low=None, fraction_high=None) -> BreakpointMotifFreqs:
     """Genome-wide breakpoint-motif frequencies over 1 Mb windows (frag/_breakpoint_motifs.py:204-297)."""
-    from ..device import end_motif_hist
     if verbose:
         start_time = time()
     resolve_length_aliases(min_length, max_length, fraction_low, fraction_high)
@@ -75,10 +77,8 @@ def breakpoint_motifs(input_file, refseq_file, k=6, min_length=50, max_length=No
         for chrom, chrom_length in ref.chroms.items():
             if table.n_fragments(chrom) == 0:
                 continue
-            w = genome_windows(chrom_length)
-            total = end_motif_hist(table.device(chrom), ref.device_contig(chrom), [a for a, _ in w],
-                                   [b for _, b in w], k=k, strand_mode=mode, quality_threshold=quality_threshold,
-                                   pooled=True, counts=total, breakpoint=True)
+            total = pooled_window_counts(table, ref, chrom, genome_windows(chrom_length), k, mode, quality_threshold,
+                                         breakpoint=True, total=total)
         if total is not None:
             ccounts = ccounts + total[0].cpu().numpy().astype(np.float64)
     with np.errstate(invalid="ignore", divide="ignore"):
@@ -94,7 +94,6 @@ def interval_breakpoint_motifs(input_file, refseq_file, intervals, k=6, min_leng
                                both_strands=True, negative_strand=False, output_file=None, quality_threshold=30,
                                workers=1, verbose=False, fraction_low=None, fraction_high=None) -> BreakpointMotifsIntervals:
     """Interval-stratified breakpoint-motif counts (frag/_breakpoint_motifs.py:300-385)."""
-    from ..device import end_motif_hist
     if verbose:
         start_time = time()
     resolve_length_aliases(min_length, max_length, fraction_low, fraction_high)
@@ -107,10 +106,9 @@ def interval_breakpoint_motifs(input_file, refseq_file, intervals, k=6, min_leng
     for chrom, idx in group_by_contig([iv[0] for iv in intervals_tuples]).items():
         if table.n_fragments(chrom) == 0:
             continue
-        got = end_motif_hist(table.device(chrom), ref.device_contig(chrom), [intervals_tuples[i][1] for i in idx],
-                             [intervals_tuples[i][2] for i in idx], k=k, strand_mode=mode,
-                             quality_threshold=quality_threshold, breakpoint=True)
-        rows[idx] = got.cpu().numpy()
+        rows[idx] = interval_motif_rows(table, ref, chrom, [intervals_tuples[i][1] for i in idx],
+                                        [intervals_tuples[i][2] for i in idx], k, mode, quality_threshold,
+                                        breakpoint=True)
     results = BreakpointMotifsIntervals([(iv, dict(zip(kmer_list, r.tolist()))) for iv, r in zip(intervals_tuples, rows)],
                                         k, quality_threshold)
     write_motif_freqs(results, output_file)

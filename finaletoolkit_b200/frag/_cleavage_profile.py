@@ -16,7 +16,7 @@ from ..io import bigwig as pbw
 from ..io.textout import GzipTextWriter
 from ..io.fragments import as_table
 from ..utils import chrom_sizes_to_dict, chrom_sizes_to_list
-from ._common import group_by_contig, resolve_length_aliases
+from ._common import group_by_contig, per_fetch, resolve_length_aliases
 
 __all__ = ["cleavage_profile", "multi_cleavage_profile"]
 
@@ -44,6 +44,8 @@ def cleavage_profile(input_file, chrom_size, contig, start, stop, left=0, right=
     table = as_table(input_file, reference_file)
     if adj_stop <= adj_start:
         return _result(contig, adj_start, np.zeros(0))
+    if table.has_read1(contig):   # BAM: what an indexed fetch of the padded region yields (:193-202)
+        table = table.fetched(contig, adj_start, adj_stop)
     out, _ = cleavage_intervals(table.device(contig), [adj_start], [adj_stop], chrom_size, min_length, max_length,
                                 quality_threshold)
     if verbose:
@@ -108,15 +110,17 @@ def multi_cleavage_profile(input_file, interval_file, chrom_sizes, left=0, right
         # cleavage_profile() re-clamps each interval (left = right = 0 here, frag/_cleavage_profile.py:352-353)
         s = [max(starts[i], 0) for i in idx]
         e = [min(stops[i], size_dict[contig]) for i in idx]
-        if table.n_fragments(contig) == 0:
-            for k, i in enumerate(idx):
-                results[i] = np.zeros(max(e[k] - s[k], 0))
-            continue
-        out, off = cleavage_intervals(table.device(contig), s, e, size_dict[contig], min_length, max_length,
-                                      quality_threshold)
-        host = out.cpu().numpy()
-        for k, i in enumerate(idx):
-            results[i] = host[off[k]: off[k + 1]]
+
+        def run(tab, sel, contig=contig, s=s, e=e):
+            if tab.n_fragments(contig) == 0:
+                return [np.zeros(max(e[k] - s[k], 0)) for k in sel]
+            out, off = cleavage_intervals(tab.device(contig), [s[k] for k in sel], [e[k] for k in sel],
+                                          size_dict[contig], min_length, max_length, quality_threshold)
+            host = out.cpu().numpy()
+            return [host[off[j]: off[j + 1]] for j in range(len(sel))]
+
+        for i, scores in zip(idx, per_fetch(table, contig, s, e, run)):
+            results[i] = scores
     if isinstance(output_file, str):
         if output_file.endswith(".bw"):
             with pbw.open(output_file, "w") as bigwig:

@@ -52,6 +52,42 @@ def group_by_contig(contigs):
     return groups
 
 
+def per_fetch(table, contig, fetch_starts, fetch_stops, run):
+    """The per-interval results ``run`` produces, with the READ-level region selection a BAM query makes.
+
+    ``run(tab, sel) -> list`` computes the intervals at positions ``sel`` of the caller's list from the
+    fragment table ``tab`` (one entry per position, in order); ``fetch_starts[k], fetch_stops[k]`` is the
+    region the reference hands to ``AlignmentWrapper.fetch`` for interval k (None = unbounded).  For a
+    fragment file that region test is the kernels' own fragment predicate and everything is ONE call on the
+    whole table.  For BAM input the fetch returns the fragments whose READ 1 overlaps the region
+    (io/alignment.py:245) - a per-(fragment, interval) condition - so the intervals that hold a fragment
+    the two rules treat differently (``FragmentTable.read1_affected``: those whose edge cuts a fragment
+    between its read 1 and its mate) are computed from the rows the fetch would have yielded
+    (``FragmentTable.fetched_union``).  Such intervals share a launch whenever no fragment can reach two of
+    them (``FragmentTable.fetch_groups``: a tiling of 5-kb windows is two groups, even and odd), so a BAM
+    costs a few batched calls per contig, not one per interval; all unaffected intervals go through one
+    call on the whole table."""
+    n = len(fetch_starts)
+    if n == 0 or not table.has_read1(contig):
+        return run(table, list(range(n)))
+    affected = table.read1_affected(contig, fetch_starts, fetch_stops)
+    out: list = [None] * n
+    clean = np.flatnonzero(~affected).tolist()
+    if clean:
+        for k, r in zip(clean, run(table, clean)):
+            out[k] = r
+    todo = np.flatnonzero(affected)
+    if todo.size:
+        lo = [fetch_starts[k] for k in todo.tolist()]
+        hi = [fetch_stops[k] for k in todo.tolist()]
+        for members in table.fetch_groups(contig, lo, hi):
+            sel = todo[members].tolist()
+            rows = table.fetched_union(contig, [lo[m] for m in members.tolist()], [hi[m] for m in members.tolist()])
+            for k, r in zip(sel, run(rows, sel)):
+                out[k] = r
+    return out
+
+
 def bedgraph_lines(contig: str, start: int, scores: np.ndarray) -> str:
     """``contig\\tpos\\tpos+1\\tscore\\n`` per position (frag/_multi_wps.py:328-341), vectorised."""
     n = scores.shape[0]

@@ -14,7 +14,7 @@ from typing import NamedTuple
 from ..exceptions import InvalidInputError
 from ..io.fragments import as_table
 from ..utils import get_intervals
-from ._common import dist_context, group_by_contig, is_writer
+from ._common import dist_context, group_by_contig, is_writer, per_fetch
 
 __all__ = ["coverage", "single_coverage", "CoverageResult"]
 
@@ -57,13 +57,19 @@ def _count_intervals(table, intervals, min_length, max_length, intersect_policy,
             continue
         if mine is not None and contig not in mine:
             continue
-        if table.n_fragments(contig) == 0:
-            continue
-        cnt, _, _ = interval_hist(table.device(contig), [intervals[i][1] for i in idx], [intervals[i][2] for i in idx],
-                                  intersect_policy, min_length, max_length, quality_threshold)
-        host = cnt.cpu().tolist()
-        for k, i in enumerate(idx):
-            counts[i] = int(host[k])
+
+        def run(tab, sel, contig=contig, idx=idx):
+            if tab.n_fragments(contig) == 0:
+                return [0] * len(sel)
+            cnt, _, _ = interval_hist(tab.device(contig), [intervals[idx[k]][1] for k in sel],
+                                      [intervals[idx[k]][2] for k in sel], intersect_policy, min_length, max_length,
+                                      quality_threshold)
+            return [int(v) for v in cnt.cpu().tolist()]
+
+        # the region handed to the fetch is the interval itself (frag/_coverage.py:118-127)
+        got = per_fetch(table, contig, [intervals[i][1] for i in idx], [intervals[i][2] for i in idx], run)
+        for i, v in zip(idx, got):
+            counts[i] = v
     if ctx is not None and counts:
         import torch
         from ..device import require_cuda

@@ -84,11 +84,26 @@ def _bins_overlapping_gaps(bins: pandas.DataFrame, gaps: GenomeGaps) -> np.ndarr
     return hit
 
 
+def delfi_rows(table, ref, contig, starts, stops, blacklist=None, gaps=None, quality_threshold=30, device=None):
+    """int64[n, 4] (host) = short, long, num_frags, G+C bases of one contig's bins: one ``ftk_delfi_windows_u64``
+    launch; for BAM input every bin is its own read-level fetch (frag/_delfi.py:443, ``_common.per_fetch``)."""
+    from ..device import delfi_windows
+    from ._common import per_fetch
+    dev_ref = ref.device_contig(contig, device) if (ref is not None and contig in ref.chroms) else None
+
+    def run(tab, sel):
+        got = delfi_windows(tab.device(contig, device), dev_ref, [starts[k] for k in sel], [stops[k] for k in sel],
+                            blacklist=blacklist, gaps=gaps, quality_threshold=quality_threshold)
+        return list(got.cpu().numpy())
+
+    rows = per_fetch(table, contig, list(starts), list(stops), run)
+    return np.stack(rows) if rows else np.zeros((0, 4), np.int64)
+
+
 def _contig_counts(table, ref, contig, starts, stops, blacklist, contig_gaps, quality_threshold, count_here=True):
     """Arm labels, live mask and int64[n, 4] counts (short, long, num_frags, G+C bases) of one contig's bins
     (the loop body of ``_delfi_single_window``, frag/_delfi.py:404-511).  ``count_here=False`` (a contig
     another rank owns) skips the CUDA call and leaves the counts at zero for the all-reduce."""
-    from ..device import delfi_windows
     n = len(starts)
     arms = [contig] * n
     live = np.ones(n, dtype=bool)
@@ -104,10 +119,8 @@ def _contig_counts(table, ref, contig, starts, stops, blacklist, contig_gaps, qu
             raise ValueError(f"could not create iterator for region '{contig}:{starts[idx[0]] + 1}-{stops[idx[0]]}'")
         if count_here:
             gaps = None if contig_gaps is None else (contig_gaps.centromere, contig_gaps.telomeres)
-            dev_ref = ref.device_contig(contig) if contig in ref.chroms else None
-            got = delfi_windows(table.device(contig), dev_ref, [starts[i] for i in idx], [stops[i] for i in idx],
-                                blacklist=blacklist, gaps=gaps, quality_threshold=quality_threshold)
-            counts[idx] = got.cpu().numpy()
+            counts[idx] = delfi_rows(table, ref, contig, [starts[i] for i in idx], [stops[i] for i in idx],
+                                     blacklist, gaps, quality_threshold)
     return arms, live, counts
 
 

@@ -20,7 +20,7 @@ from ..io.reference import ReferenceWrapper, open_reference
 from ..utils import gen_kmers
 from ._common import dist_context, group_by_contig, is_writer, resolve_length_aliases
 from ._motif_common import (MIN_QUALITY, _MotifFreqs, _MotifsIntervals, _BASES, genome_windows,
-                            parse_intervals_arg, write_motif_freqs)
+                            interval_motif_rows, parse_intervals_arg, pooled_window_counts, write_motif_freqs)
 
 __all__ = ["EndMotifFreqs", "EndMotifsIntervals", "region_end_motifs", "end_motifs", "interval_end_motifs",
            "MIN_QUALITY"]
@@ -59,6 +59,8 @@ def region_end_motifs(input_file, contig, start, stop, refseq_file, k=4, fractio
     table = as_table(input_file, refseq_file)
     ref = _ref(refseq_file)
     kmer_list = gen_kmers(k, "ACGT")
+    if table.has_read1(contig):   # BAM: what an indexed fetch of the region yields
+        table = table.fetched(contig, int(start), int(stop))
     if table.n_fragments(contig) == 0:
         return dict(zip(kmer_list, 4 ** k * [0]))
     counts = end_motif_hist(table.device(contig), ref.device_contig(contig), [int(start)], [int(stop)], k=k,
@@ -72,7 +74,6 @@ def end_motifs(input_file, refseq_file, k=4, min_length=50, max_length=None, bot
                negative_strand=False, output_file=None, quality_threshold=30, workers=1, verbose=False,
                fraction_low=None, fraction_high=None) -> EndMotifFreqs:
     """Genome-wide 5' end-motif frequencies over 1 Mb windows (frag/_end_motifs.py:198-293)."""
-    from ..device import end_motif_hist
     if verbose:
         start_time = time()
     min_length, max_length = resolve_length_aliases(min_length, max_length, fraction_low, fraction_high)
@@ -99,10 +100,8 @@ def end_motifs(input_file, refseq_file, k=4, min_length=50, max_length=None, bot
         for chrom, chrom_length in ref.chroms.items():
             if table.n_fragments(chrom) == 0:
                 continue
-            w = genome_windows(chrom_length)
-            total = end_motif_hist(table.device(chrom), ref.device_contig(chrom), [a for a, _ in w],
-                                   [b for _, b in w], k=k, strand_mode=mode, quality_threshold=quality_threshold,
-                                   pooled=True, counts=total)
+            total = pooled_window_counts(table, ref, chrom, genome_windows(chrom_length), k, mode, quality_threshold,
+                                         breakpoint=False, total=total)
         if total is not None:
             ccounts = ccounts + total[0].cpu().numpy().astype(np.float64)
     with np.errstate(invalid="ignore", divide="ignore"):
@@ -118,7 +117,6 @@ def interval_end_motifs(input_file, refseq_file, intervals, k=4, min_length=50, 
                         negative_strand=False, output_file=None, quality_threshold=30, workers=1, verbose=False,
                         fraction_low=None, fraction_high=None) -> EndMotifsIntervals:
     """Interval-stratified 5' end-motif counts (frag/_end_motifs.py:296-383)."""
-    from ..device import end_motif_hist
     if verbose:
         start_time = time()
     min_length, max_length = resolve_length_aliases(min_length, max_length, fraction_low, fraction_high)
@@ -136,10 +134,9 @@ def interval_end_motifs(input_file, refseq_file, intervals, k=4, min_length=50, 
     for chrom, idx in group_by_contig([iv[0] for iv in intervals_tuples]).items():
         if table.n_fragments(chrom) == 0:
             continue
-        got = end_motif_hist(table.device(chrom), ref.device_contig(chrom), [intervals_tuples[i][1] for i in idx],
-                             [intervals_tuples[i][2] for i in idx], k=k, strand_mode=mode,
-                             quality_threshold=quality_threshold)
-        rows[idx] = got.cpu().numpy()
+        rows[idx] = interval_motif_rows(table, ref, chrom, [intervals_tuples[i][1] for i in idx],
+                                        [intervals_tuples[i][2] for i in idx], k, mode, quality_threshold,
+                                        breakpoint=False)
     results = EndMotifsIntervals([(iv, dict(zip(kmer_list, r.tolist()))) for iv, r in zip(intervals_tuples, rows)],
                                  k, quality_threshold)
     write_motif_freqs(results, output_file)

@@ -20,7 +20,7 @@ import numpy as np
 from ..exceptions import InvalidInputError
 from ..io.fragments import as_table
 from ..utils import get_intervals
-from ._common import dist_context, group_by_contig, is_writer
+from ._common import dist_context, group_by_contig, is_writer, per_fetch
 
 __all__ = ["frag_length", "frag_length_bins", "frag_length_intervals", "FragLengthStats"]
 
@@ -61,6 +61,8 @@ def _region_dict(table, contig, start, stop, min_length, max_length, intersect_p
     """The reference's ``_distribution_from_gen`` dict (first-seen order) of one region; contig None = all."""
     from ..device import interval_hist
     merged: dict = {}
+    if contig is not None and table.has_read1(contig):
+        table = table.fetched(contig, start, stop)   # BAM: what an indexed fetch of the region yields
     for c in ([contig] if contig is not None else table.contigs):
         if table.n_fragments(c) == 0:
             continue
@@ -95,6 +97,8 @@ def frag_length(input_file, contig=None, start=None, stop=None, intersect_policy
     policy_code(intersect_policy)
     _check_region(contig, start, stop)
     table = as_table(input_file, reference_file)
+    if contig is not None and table.has_read1(contig):
+        table = table.fetched(contig, start, stop)   # BAM: what an indexed fetch of the region yields
     parts = [frag_lengths(table.device(c), start, stop, intersect_policy, 0, 1000000000, quality_threshold).cpu().numpy()
              for c in ([contig] if contig is not None else table.contigs) if table.n_fragments(c)]
     lengths = np.concatenate(parts).astype(np.int32) if parts else np.array([], dtype=np.int32)
@@ -231,23 +235,27 @@ def frag_length_intervals(input_file, interval_file, output_file=None, min_lengt
     intervals = get_intervals(interval_file)
     results: list = [None] * len(intervals)
     for contig, idx in group_by_contig([iv[0] for iv in intervals]).items():
-        if table.n_fragments(contig) == 0:
-            for i in idx:
-                results[i] = _stats_from_dict(*intervals[i], {}, short_reads)
-            continue
-        frags = table.device(contig)
-        nb = _n_bins(frags, max_length)
-        batch = max(1, (256 << 20) // (12 * nb))  # bound the per-interval histogram block to ~256 MB
-        for b0 in range(0, len(idx), batch):
-            sub = idx[b0: b0 + batch]
-            _, h, f = interval_hist(frags, [intervals[i][1] for i in sub], [intervals[i][2] for i in sub],
-                                    intersect_policy, min_length, max_length, quality_threshold, n_bins=nb,
-                                    first_seen=True)
-            # the statistics of all intervals of the batch in one native call (csrc/ftk_hoststats.cu):
-            # the reference's arithmetic and operation order, without a Python loop per interval
-            cols = _length_stats(h.to(torch().int32).cpu().numpy(), f.cpu().numpy(), short_reads)
-            for k, i in enumerate(sub):
-                results[i] = _stats_row(*intervals[i], cols, k)
+        def run(tab, sel, contig=contig, idx=idx):
+            if tab.n_fragments(contig) == 0:
+                return [_stats_from_dict(*intervals[idx[k]], {}, short_reads) for k in sel]
+            frags = tab.device(contig)
+            nb = _n_bins(frags, max_length)
+            batch = max(1, (256 << 20) // (12 * nb))  # bound the per-interval histogram block to ~256 MB
+            rows = []
+            for b0 in range(0, len(sel), batch):
+                sub = [idx[k] for k in sel[b0: b0 + batch]]
+                _, h, f = interval_hist(frags, [intervals[i][1] for i in sub], [intervals[i][2] for i in sub],
+                                        intersect_policy, min_length, max_length, quality_threshold, n_bins=nb,
+                                        first_seen=True)
+                # the statistics of all intervals of the batch in one native call (csrc/ftk_hoststats.cu):
+                # the reference's arithmetic and operation order, without a Python loop per interval
+                cols = _length_stats(h.to(torch().int32).cpu().numpy(), f.cpu().numpy(), short_reads)
+                rows += [_stats_row(*intervals[i], cols, k) for k, i in enumerate(sub)]
+            return rows
+
+        got = per_fetch(table, contig, [intervals[i][1] for i in idx], [intervals[i][2] for i in idx], run)
+        for i, row in zip(idx, got):
+            results[i] = row
     if output_file is not None:
         output_is_file = False
         try:

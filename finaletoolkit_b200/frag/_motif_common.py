@@ -277,6 +277,43 @@ def genome_windows(chrom_length: int):
     return w
 
 
+def interval_motif_rows(table, ref, chrom, starts, stops, k, strand_mode, quality_threshold, breakpoint=False,
+                        device=None):
+    """int64[len(starts), 4^k] (host): end- or breakpoint-motif counts of the fragments each region's fetch
+    yields (frag/_end_motifs.py:115-120, frag/_breakpoint_motifs.py:114-119 - tabix: fragments overlapping the
+    region, one launch for all regions; BAM: read 1 overlapping it, ``_common.per_fetch``)."""
+    from ..device import end_motif_hist
+    from ._common import per_fetch
+
+    def run(tab, sel):
+        if tab.n_fragments(chrom) == 0:
+            return [np.zeros(4 ** k, np.int64) for _ in sel]
+        got = end_motif_hist(tab.device(chrom, device), ref.device_contig(chrom, device), [starts[j] for j in sel],
+                             [stops[j] for j in sel], k=k, strand_mode=strand_mode,
+                             quality_threshold=quality_threshold, breakpoint=breakpoint)
+        return list(got.cpu().numpy())
+
+    rows = per_fetch(table, chrom, starts, stops, run)
+    return np.stack(rows) if rows else np.zeros((0, 4 ** k), np.int64)
+
+
+def pooled_window_counts(table, ref, chrom, windows, k, strand_mode, quality_threshold, breakpoint=False, total=None,
+                         device=None):
+    """Adds the k-mer counts of a contig's 1 Mb windows (frag/_motif_common.py:580-610) to the device tensor
+    ``total`` int64[1, 4^k] (created when None) and returns it.  Fragment files: one pooled launch.  BAM input:
+    every window is its own read-level fetch, so the per-window rows are summed instead."""
+    from ..device import end_motif_hist
+    ws, we = [a for a, _ in windows], [b for _, b in windows]
+    if not table.has_read1(chrom):
+        return end_motif_hist(table.device(chrom, device), ref.device_contig(chrom, device), ws, we, k=k,
+                              strand_mode=strand_mode, quality_threshold=quality_threshold, pooled=True, counts=total,
+                              breakpoint=breakpoint)
+    import torch
+    rows = interval_motif_rows(table, ref, chrom, ws, we, k, strand_mode, quality_threshold, breakpoint, device)
+    add = torch.from_numpy(rows.sum(axis=0, keepdims=True)).to(table.device(chrom, device).device)
+    return add if total is None else total.add_(add)
+
+
 def parse_intervals_arg(intervals):
     """frag/_motif_common.py:613-630: whitespace-split BED or list of tuples."""
     if type(intervals) is str:

@@ -16,8 +16,8 @@ from ..io import bigwig as pbw
 from ..io.fragments import FragmentTable, as_table
 from ..io.textout import GzipTextWriter, bedgraph_text
 from ..utils import chrom_sizes_to_list
-from ._common import group_by_contig, resolve_length_aliases
-from ._wps import _wps_device, _wps_streamed
+from ._common import group_by_contig, per_fetch, resolve_length_aliases
+from ._wps import _wps_device, _wps_streamed, fetch_window
 
 __all__ = ["multi_wps", "LAST_TIMINGS"]
 
@@ -107,18 +107,28 @@ def multi_wps(input_file, site_bed, chrom_sizes=None, output_file=None, window_s
     t_decoded = time.perf_counter()
     for contig, idx in group_by_contig(contigs).items():
         table.host(contig)      # lazy tables decode here: keep it out of the compute share
-        args = (table, contig, [starts[i] for i in idx], [stops[i] for i in idx], chrom_sizes_dict[contig],
-                int(window_size), min_length, int(round(max_length)), quality_threshold)
-        # large contigs stream (pinned columns, chunked H2D || kernels || D2H, int16 scores); small ones upload whole
-        streamed = _wps_streamed(*args)
-        if streamed is not None:
-            host, off = streamed
-            n_streamed += 1
-        else:
-            out, off = _wps_device(*args)
-            host = out.cpu().numpy()
-        for k, i in enumerate(idx):
-            results[i] = host[off[k]: off[k + 1]]
+        size, width = chrom_sizes_dict[contig], int(round(max_length))
+
+        def run(tab, sel, contig=contig, idx=idx, size=size, width=width):
+            nonlocal n_streamed
+            args = (tab, contig, [starts[idx[k]] for k in sel], [stops[idx[k]] for k in sel], size,
+                    int(window_size), min_length, width, quality_threshold)
+            # large contigs stream (pinned columns, chunked H2D || kernels || D2H, int16 scores); small ones upload whole
+            streamed = _wps_streamed(*args)
+            if streamed is not None:
+                host, off = streamed
+                n_streamed += 1
+            else:
+                out, off = _wps_device(*args)
+                host = out.cpu().numpy()
+            return [host[off[k]: off[k + 1]] for k in range(len(sel))]
+
+        # every interval is one wps() call of the reference, which fetches from its own padded window
+        bam = table.has_read1(contig)
+        windows = [fetch_window(starts[i], stops[i], max_length, size) if bam else (None, None) for i in idx]
+        got = per_fetch(table, contig, [w[0] for w in windows], [w[1] for w in windows], run)
+        for i, scores in zip(idx, got):
+            results[i] = scores
 
     t_computed = time.perf_counter()
     if isinstance(output_file, str):

@@ -30,6 +30,11 @@ def _wps_device(table, chrom, starts, stops, chrom_size, window_size, min_length
     return plan.run(frags, window_size, min_length, max_length, quality_threshold), plan.offsets
 
 
+def fetch_window(start, stop, max_length, chrom_size):
+    """frag/_wps.py:156-157: the region ``wps`` fetches fragments from."""
+    return max(round(start - max_length), 0), min(round(stop + max_length), chrom_size)
+
+
 _STREAM_MIN_FRAGMENTS = 1 << 21     # below this a contig's columns are uploaded whole (nothing to overlap)
 
 
@@ -76,6 +81,8 @@ def wps(input_file, chrom, start, stop, chrom_size, output_file=None, window_siz
                       UserWarning, stacklevel=2)
         return np.zeros(0, dtype=_WPS_DTYPE)
     table = as_table(input_file, reference_file)
+    if table.has_read1(chrom):   # BAM: the rows an indexed fetch of the padded window yields (frag/_wps.py:156-168)
+        table = table.fetched(chrom, *fetch_window(start, stop, max_length, chrom_size))
     out, _ = _wps_device(table, chrom, [start], [stop], int(chrom_size), int(window_size), min_length,
                          int(round(max_length)), quality_threshold)
     scores = np.zeros(stop - start, dtype=_WPS_DTYPE)

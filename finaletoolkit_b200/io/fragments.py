@@ -21,9 +21,15 @@ decode a contig on first use and nothing else (``io/tabix.py``, ``ftk_fragfile_o
 BAM is decoded natively (``ftk_bamfile_open``: streamed BGZF inflate + record walk with the read
 filter and fragment reconstruction of io/alignment.py:60-71, 242-268); CRAM / SAM text need htslib
 and go through ``pysam`` when it is importable, ``UnsupportedFormatError`` otherwise.  For BAM input
-the reference selects READS overlapping the query region and then builds fragments; here, as for
-fragment files, whole contigs are loaded and the kernels select FRAGMENTS overlapping the region, so
-a fragment whose read 1 lies outside the query region is kept where the reference would drop it.  The mapq filter is NOT applied at load time - it is a kernel predicate.
+the reference selects READS overlapping the query region and only then builds fragments
+(io/alignment.py:245 ``self._handle.fetch(contig, start, stop)``), so a fragment whose read 1 lies
+outside the region is dropped even when the fragment itself reaches into it.  A BAM-derived table
+therefore keeps the reference span of read 1 next to every fragment (``FragmentTable.read1``) and
+offers the same selection as an index query would make: ``read1_affected`` tells which query regions
+hold a fragment that the fragment-level predicate of the kernels would keep and the read-level fetch
+drops, ``fetched`` returns the rows an indexed fetch of one region yields (``frag/_common.per_fetch``
+routes exactly those regions through it).  The mapq filter is NOT applied at load time - it is a
+kernel predicate.
 """
 from __future__ import annotations
 
@@ -49,11 +55,15 @@ class FragmentTable:
     first time they are asked for (tabix-indexed files); ``columns`` then holds the loaded ones."""
 
     def __init__(self, columns: Dict[str, Columns], source: str | None = None, is_sam: bool = False,
-                 contig_lengths: Dict[str, int] | None = None, lazy=None):
+                 contig_lengths: Dict[str, int] | None = None, lazy=None, read1: Dict[str, tuple] | None = None):
         self.source = source
         self.is_sam = is_sam
         self.contig_lengths = contig_lengths  # BAM/CRAM header only
         self.columns: Dict[str, Columns] = {}
+        # BAM/CRAM only: {contig: (r1_start, r1_end) int32}, the reference span of read 1 of every fragment
+        # (rows as in ``columns``), clipped to the fragment
+        self.read1: Dict[str, tuple] = {}
+        self._read1_in = read1 or {}
         self._lazy_names, self._loader = (list(lazy[0]), lazy[1]) if lazy is not None else (None, None)
         self._weights = lazy[2] if (lazy is not None and len(lazy) > 2) else None
         for contig, cols in columns.items():
@@ -66,10 +76,23 @@ class FragmentTable:
         sp = np.ascontiguousarray(sp, dtype=np.int32)
         mq = np.ascontiguousarray(mq, dtype=np.uint8)
         sd = np.ascontiguousarray(sd, dtype=np.uint8)
+        r1 = self._read1_in.pop(contig, None)
+        if r1 is not None:
+            r1 = (np.asarray(r1[0], dtype=np.int64), np.asarray(r1[1], dtype=np.int64))
+            if r1[0].shape != st.shape or r1[1].shape != st.shape:
+                raise ValueError(f"read-1 columns of contig {contig!r} do not match its fragment columns")
         if st.size and not np.all(st[1:] >= st[:-1]):
             order = np.argsort(st, kind="stable")  # keeps file order among equal starts
             st, sp, mq, sd = st[order], sp[order], mq[order], sd[order]
+            if r1 is not None:
+                r1 = (r1[0][order], r1[1][order])
         self.columns[contig] = (st, sp, mq, sd)
+        if r1 is not None:
+            # only the part of the read inside its own fragment can decide a query: a fragment that does not
+            # overlap the region fails the intersect policy whatever its read does (utils/_frag_generator.py:36-50)
+            lo = np.maximum(r1[0], st).astype(np.int32)
+            hi = np.maximum(np.minimum(r1[1], sp), lo + 1).astype(np.int32)
+            self.read1[contig] = (lo, hi)
 
     def _ensure(self, contig) -> None:
         if self._loader is not None and contig not in self.columns and contig in self._lazy_names:
@@ -102,6 +125,105 @@ class FragmentTable:
             return z, z.copy(), np.zeros(0, np.uint8), np.zeros(0, np.uint8)
         return self.columns[contig]
 
+    # ---- read-level fetch of BAM input (io/alignment.py:242-247)
+    def has_read1(self, contig=None) -> bool:
+        """True when the rows of ``contig`` (any contig for None) carry read-1 spans, i.e. when a region query
+        has to select by READ overlap like ``pysam.AlignmentFile.fetch`` does."""
+        if contig is None:
+            return bool(self.read1) or bool(self._read1_in)
+        self._ensure(contig)
+        return contig in self.read1
+
+    def _read1_sorted(self, contig: str):
+        cache = self.__dict__.setdefault("_r1_sorted", {})
+        if contig not in cache:
+            st, sp = self.columns[contig][:2]
+            lo, hi = self.read1[contig]
+            cache[contig] = (np.sort(sp), np.sort(lo), np.sort(hi),
+                             int((sp.astype(np.int64) - st).max()) if st.size else 0)
+        return cache[contig]
+
+    @staticmethod
+    def _bounds(starts, stops):
+        big = np.int64(1) << 40
+        lo = np.array([-big if v is None else int(v) for v in starts], dtype=np.int64)
+        hi = np.array([big if v is None else int(v) for v in stops], dtype=np.int64)
+        return lo, hi
+
+    def read1_affected(self, contig: str, starts, stops) -> np.ndarray:
+        """bool per query region ``[starts[i], stops[i])`` (None = unbounded): does the region hold a fragment
+        that overlaps it while its read 1 does not?  Only for those regions can the read-level fetch of the
+        reference (io/alignment.py:245) and a fragment-level predicate disagree.  Two binary searches per
+        region over sorted copies of the four coordinate columns."""
+        lo, hi = self._bounds(starts, stops)
+        if not self.has_read1(contig) or not len(lo):
+            return np.zeros(len(lo), dtype=bool)
+        st = self.columns[contig][0]
+        sp_sorted, r1s_sorted, r1e_sorted, _ = self._read1_sorted(contig)
+        # reads and fragments have positive length, so  #overlapping = #(begin < hi) - #(end <= lo)
+        frag = np.searchsorted(st, hi, side="left") - np.searchsorted(sp_sorted, lo, side="right")
+        read = np.searchsorted(r1s_sorted, hi, side="left") - np.searchsorted(r1e_sorted, lo, side="right")
+        return (frag != read) & (hi > lo)
+
+    def fetched(self, contig: str, start=None, stop=None) -> "FragmentTable":
+        """The rows an indexed BAM fetch of ``contig:[start, stop)`` yields (read 1 overlaps the region,
+        io/alignment.py:245; None = unbounded), as a one-contig table without read-1 columns: the fragment-level
+        predicates of the kernels then finish the job exactly like ``frag_generator`` does after the fetch."""
+        if not self.has_read1(contig):
+            return self
+        (lo,), (hi,) = self._bounds([start], [stop])
+        st, sp, mq, sd = self.columns[contig]
+        r1s, r1e = self.read1[contig]
+        max_len = self._read1_sorted(contig)[3]
+        a = int(np.searchsorted(st, lo - max_len, side="left"))      # a row further left ends before the region
+        b = int(np.searchsorted(st, hi, side="left"))                # read 1 begins at or after the fragment start
+        keep = np.flatnonzero((r1s[a:b] < hi) & (r1e[a:b] > lo)) + a
+        sub = FragmentTable({contig: (st[keep], sp[keep], mq[keep], sd[keep])}, source=self.source,
+                            is_sam=self.is_sam, contig_lengths=self.contig_lengths)
+        sub._transient = True     # one query's rows: uploaded through staging, not page-locked in place
+        return sub
+
+    def fetch_groups(self, contig: str, starts, stops) -> list:
+        """Partition query regions into groups that can share ONE fetched table: inside a group any two
+        regions lie at least one maximal fragment length apart, so a row fetched for one of them is entirely
+        outside every other and cannot pass the other's fragment predicate (midpoint or overlap).  A tiling of
+        5-kb windows needs two groups (even / odd) instead of one query per window.  Returns index arrays
+        (ascending) into ``starts``; first-fit over the regions sorted by start."""
+        lo, hi = self._bounds(starts, stops)
+        if not len(lo):
+            return []
+        gap = self._read1_sorted(contig)[3] if self.has_read1(contig) else 0
+        group_end: list = []           # the right-most region end of every group so far
+        members: list = []
+        for j in np.argsort(lo, kind="stable").tolist():
+            for g, end in enumerate(group_end):
+                if lo[j] >= end + gap:
+                    group_end[g] = max(end, int(hi[j])); members[g].append(j)
+                    break
+            else:
+                group_end.append(int(hi[j])); members.append([j])
+        return [np.sort(np.asarray(m, dtype=np.int64)) for m in members]
+
+    def fetched_union(self, contig: str, starts, stops) -> "FragmentTable":
+        """The rows whose read 1 overlaps ANY of the regions of one ``fetch_groups`` group (pairwise disjoint,
+        at least a fragment length apart), as a one-contig table without read-1 columns - the rows of
+        ``fetched`` for every region of the group in one table."""
+        if not self.has_read1(contig):
+            return self
+        lo, hi = self._bounds(starts, stops)
+        order = np.argsort(lo, kind="stable")
+        lo, hi = lo[order], hi[order]
+        st, sp, mq, sd = self.columns[contig]
+        r1s, r1e = self.read1[contig]
+        # the regions are disjoint and sorted: the only candidate of a read is the first region ending after its start
+        k = np.searchsorted(hi, r1s, side="right")
+        ok = k < len(lo)
+        keep = np.flatnonzero(ok & (lo[np.minimum(k, len(lo) - 1)] < r1e))
+        sub = FragmentTable({contig: (st[keep], sp[keep], mq[keep], sd[keep])}, source=self.source,
+                            is_sam=self.is_sam, contig_lengths=self.contig_lengths)
+        sub._transient = True
+        return sub
+
     def pinned(self, contig: str):
         """``(start, stop, mapq, strand)`` of one contig as CPU torch tensors that SHARE the host columns' memory,
         page-locked in place with ``cudaHostRegister`` (once per contig, released with the table) - what
@@ -133,7 +255,7 @@ class FragmentTable:
         dev = require_cuda(device)
         key = (contig, str(dev))
         if key not in self._device:
-            cols = self.pinned(contig) if self.n_fragments(contig) else None
+            cols = self.pinned(contig) if (self.n_fragments(contig) and not getattr(self, "_transient", False)) else None
             if cols is not None:
                 # DMA straight out of the page-locked host columns (80 M fragments: 56 ms to lock the pages +
                 # 21 ms of copies, against 0.8 s through freshly allocated staging buffers); the longest
@@ -228,6 +350,20 @@ def _decode_native(path: str, threads: int = 0) -> Dict[str, Columns] | None:
         return _handle_columns(L, h)
     finally:
         L.ftk_fragfile_close(h)
+
+
+def _handle_read1(L, h) -> Dict[str, tuple] | None:
+    """Read-1 reference spans of a BAM-derived handle, per contig (rows as in ``_handle_columns``)."""
+    import ctypes
+    out: Dict[str, tuple] = {}
+    p32 = ctypes.POINTER(ctypes.c_int32)
+    for i in range(L.ftk_fragfile_n_contigs(h)):
+        n = L.ftk_fragfile_contig_count(h, i)
+        lo = np.empty(n, np.int32); hi = np.empty(n, np.int32)
+        if L.ftk_fragfile_copy_read1(h, i, lo.ctypes.data_as(p32), hi.ctypes.data_as(p32)) != 0:
+            return None
+        out[L.ftk_fragfile_contig_name(h, i).decode()] = (lo, hi)
+    return out
 
 
 def _handle_columns(L, h) -> Dict[str, Columns] | None:
@@ -341,13 +477,14 @@ def _load_bam_native(path: str) -> "FragmentTable | None":
         return None
     try:
         cols = _handle_columns(L, L.ftk_bamfile_fragments(h))
+        read1 = _handle_read1(L, L.ftk_bamfile_fragments(h)) if cols is not None else None
         lengths = {L.ftk_bamfile_ref_name(h, i).decode(): int(L.ftk_bamfile_ref_length(h, i))
                    for i in range(L.ftk_bamfile_n_refs(h))}
     finally:
         L.ftk_bamfile_close(h)
-    if cols is None:
+    if cols is None or read1 is None:
         return None
-    return FragmentTable(cols, source=path, is_sam=True, contig_lengths=lengths)
+    return FragmentTable(cols, source=path, is_sam=True, contig_lengths=lengths, read1=read1)
 
 
 def _load_sam(path: str, reference_file=None) -> FragmentTable:
@@ -377,11 +514,15 @@ def _load_sam(path: str, reference_file=None) -> FragmentTable:
                 st, sp = read.reference_end + tlen, read.reference_end
             else:
                 continue
-            a = acc.setdefault(read.reference_name, ([], [], [], []))
+            a = acc.setdefault(read.reference_name, ([], [], [], [], [], []))
             a[0].append(st); a[1].append(sp); a[2].append(read.mapping_quality); a[3].append(1 if read.is_forward else 0)
+            r_end = read.reference_end
+            a[4].append(read.reference_start)
+            a[5].append(r_end if (r_end is not None and r_end > read.reference_start) else read.reference_start + 1)
     cols = {c: (np.array(a[0], np.int64), np.array(a[1], np.int64), np.array(a[2], np.uint8), np.array(a[3], np.uint8))
             for c, a in acc.items()}
-    return FragmentTable(cols, source=path, is_sam=True, contig_lengths=lengths)
+    read1 = {c: (np.array(a[4], np.int64), np.array(a[5], np.int64)) for c, a in acc.items()}
+    return FragmentTable(cols, source=path, is_sam=True, contig_lengths=lengths, read1=read1)
 
 
 def load_fragments(input_file, reference_file=None) -> FragmentTable:

@@ -108,6 +108,8 @@ def frag_generator(input_file, contig, quality_threshold=30, start=None, stop=No
         if not (start == 0 and stop is None):
             raise InvalidInputError("contig should be specified if start or stop given.")
     table = as_table(input_file, reference_file)
+    if contig is not None and table.has_read1(contig):
+        table = table.fetched(contig, start, stop)   # BAM: the fetch selects by read 1 (io/alignment.py:245)
     for c in ([contig] if contig is not None else table.contigs):
         st, sp, mq, sd = table.host(c)
         m = _stream_mask(st, sp, mq, quality_threshold, start, stop, min_length, max_length, intersect_policy)
@@ -119,6 +121,8 @@ def frag_array(input_file, contig, quality_threshold=30, start=None, stop=None, 
                max_length=None, intersect_policy="midpoint", verbose=False, reference_file=None):
     """utils/utils.py:186-255: structured [('start','i8'),('stop','i8'),('strand','?')]."""
     table = as_table(input_file, reference_file)
+    if contig is not None and table.has_read1(contig):
+        table = table.fetched(contig, start, stop)   # BAM: the fetch selects by read 1 (io/alignment.py:245)
     st, sp, mq, sd = table.host(contig)
     m = _stream_mask(st, sp, mq, quality_threshold, start, stop, min_length, max_length, intersect_policy)
     out = np.zeros(int(m.sum()), dtype=[("start", "i8"), ("stop", "i8"), ("strand", "?")])

@@ -423,6 +423,12 @@ const char *ftk_fragfile_contig_name(void *handle, int32_t i);
 int64_t ftk_fragfile_contig_count(void *handle, int32_t i);
 int ftk_fragfile_copy(void *handle, int32_t i, int32_t *start_host, int32_t *stop_host,
                       uint8_t *mapq_host, uint8_t *strand_host);
+/* BAM-derived handles only: the reference span [pos, bam_endpos) of READ 1 of every fragment, rows as in
+ * ftk_fragfile_copy.  An indexed BAM fetch selects READS overlapping the region before the fragment is
+ * built (io/alignment.py:242-247: `for read in self._handle.fetch(contig, start, stop)`), so the host side
+ * needs these two columns to make the same selection (FragmentTable.fetched).  Returns 0 = copied,
+ * 1 = the handle carries no read-1 columns (fragment files), < 0 = error. */
+int ftk_fragfile_copy_read1(void *handle, int32_t i, int32_t *r1_start_host, int32_t *r1_end_host);
 void ftk_fragfile_close(void *handle);
 
 /* ------------------------------------------------- bigWig section codec (host)

@@ -351,10 +351,12 @@ def delfi_counts(fr: Frags, seq_ascii, start: int, stop: int, blacklist=None, ga
 
 
 # ---------------------------------------------------------- BAM -> fragments
-def bam_fragments(bam_bytes: bytes):
+def bam_fragments(bam_bytes: bytes, with_read1: bool = False):
     """io/alignment.py:60-71 (_read_is_low_quality without the mapq test) + :242-268 (_fetch_sam) on the
     records of an uncompressed-by-gzip BAM: returns (references [(name, length)], rows) with rows =
-    (contig, start, stop, mapq, is_forward) in file order."""
+    (contig, start, stop, mapq, is_forward) in file order.  ``with_read1`` appends the reference span
+    ``(pos, bam_endpos)`` of the read itself - what an indexed fetch tests against the region (htslib:
+    ``pos < stop and bam_endpos > start``, bam_endpos = pos + max(reference bases of the CIGAR, 1))."""
     import gzip
     import struct
     raw = gzip.decompress(bam_bytes)
@@ -377,17 +379,50 @@ def bam_fragments(bam_bytes: bytes):
             continue
         if read2:                                                                                          # :248
             continue
+        ref_end = pos + sum(c >> 4 for c in cig if (c & 15) in (0, 2, 3, 7, 8))
         if tlen > 0:                                                                                       # :252-260
             f_start, f_stop = pos, pos + tlen
         elif tlen < 0:
             if not cig:
                 continue   # pysam: reference_end is None
-            ref_end = pos + sum(c >> 4 for c in cig if (c & 15) in (0, 2, 3, 7, 8))
             f_start, f_stop = ref_end + tlen, ref_end
         else:
             continue
-        rows.append((refs[ref_id][0], f_start, f_stop, mapq, not (flag & 0x10)))
+        row = (refs[ref_id][0], f_start, f_stop, mapq, not (flag & 0x10))
+        rows.append(row + (pos, ref_end if ref_end > pos else pos + 1) if with_read1 else row)
     return refs, rows
+
+
+def bam_fetch(bam_bytes: bytes, contig=None, start=None, stop=None):
+    """``AlignmentWrapper._fetch_sam`` (io/alignment.py:242-268) for one region: the fragments of the READS an
+    indexed ``fetch(contig, start, stop)`` returns, file order, mapq filter not applied."""
+    _, rows = bam_fragments(bam_bytes, with_read1=True)
+    out = []
+    for c, f_start, f_stop, mapq, fwd, r_start, r_end in rows:
+        if contig is not None:
+            if c != contig or (stop is not None and r_start >= stop) or (start is not None and r_end <= start):
+                continue
+        out.append((c, f_start, f_stop, mapq, fwd))
+    return out
+
+
+def frag_stream(rows, quality_threshold=30, start=None, stop=None, min_length=None, max_length=None,
+                intersect_policy="midpoint"):
+    """utils/_frag_generator.py:112-130 over already fetched rows (contig, start, stop, mapq, is_forward):
+    mapq (io/alignment.py:60-71), the inclusive length window and the intersect policy."""
+    out = []
+    for c, s, e, q, fwd in rows:
+        ln = e - s
+        if q < quality_threshold or (min_length is not None and ln < min_length) or (max_length is not None and ln > max_length):
+            continue
+        if intersect_policy == "midpoint":
+            mid = (s + e) // 2
+            ok = (start is None or mid >= start) and (stop is None or mid < stop)
+        else:
+            ok = (start is None or e > start) and (stop is None or s < stop)
+        if ok:
+            out.append((c, s, e, q, fwd))
+    return out
 
 
 # ------------------------------------------------------------------ agg_bw

@@ -1,0 +1,149 @@
+"""Read-level region selection of BAM input (io/alignment.py:242-247), CPU side.
+
+``tests/golden/bam_read1.*`` hold what the UNMODIFIED reference yields on a synthetic short-read BAM
+(oracle/make_golden_bam.py).  Here: (1) the oracle's restatement of the fetch is pinned on those outputs,
+(2) the native decoder's read-1 spans equal the oracle's record walk, (3) the product's host-side selection
+(``FragmentTable.read1_affected / fetch_groups / fetched_union``, ``frag/_common.per_fetch``) reproduces the
+reference's per-interval numbers when the per-table computation is done by the oracle instead of a kernel,
+(4) the host stream helpers (``utils.frag_generator`` / ``frag_array``) equal the reference's output.
+The CUDA path replays the same vectors in ``tests/test_gpu_bam.py``.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def bam(tmp_path_factory, golden):
+    g = golden("bam_read1")
+    with open(os.path.join(GOLDEN, "bam_read1.json")) as fh:
+        m = json.load(fh)
+    d = tmp_path_factory.mktemp("bam_read1")
+    path = str(d / "read1.bam")
+    with open(path, "wb") as fh:
+        fh.write(g["bam_file"].tobytes())
+    open(path + ".bai", "wb").close()
+    return path, g, m
+
+
+def _sorted_rows(a):
+    a = np.asarray(a, np.int64).reshape(-1, 4)
+    return a[np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))]
+
+
+def _frags(rows):
+    a = np.array([[r[1], r[2], r[3], int(r[4])] for r in rows], np.int64).reshape(-1, 4)
+    a = a[np.argsort(a[:, 0], kind="stable")]
+    fr = O.Frags(a[:, 0].astype(np.int32), a[:, 1].astype(np.int32), a[:, 2].astype(np.uint8), a[:, 3].astype(np.uint8))
+    return fr
+
+
+def test_oracle_fetch_pinned_on_reference(bam):
+    path, g, m = bam
+    raw = g["bam_file"].tobytes()
+    for c in m["frag_generator"]:
+        rows = O.frag_stream(O.bam_fetch(raw, c["contig"], c["start"], c["stop"]), start=c["start"], stop=c["stop"],
+                             **{"quality_threshold": 30, **c["kwargs"]})
+        got = np.array([[r[1], r[2], r[3], int(r[4])] for r in rows], np.int64).reshape(-1, 4)
+        assert np.array_equal(got, g[c["key"]]), c       # same rows, same (file) order
+    assert sum(g[c["key"]].shape[0] > 0 for c in m["frag_generator"]) >= 9
+    sizes = dict(m["refs"])
+    for c in m["wps"]:
+        kw = {"window_size": 120, "min_length": 120, "max_length": 180, "quality_threshold": 30, **c["kwargs"]}
+        lo, hi = max(c["start"] - kw["max_length"], 0), min(c["stop"] + kw["max_length"], sizes[c["contig"]])
+        fr = _frags(O.bam_fetch(raw, c["contig"], lo, hi))
+        assert np.array_equal(O.wps_interval(fr, c["start"], c["stop"], sizes[c["contig"]], **kw), g[c["key"]]), c
+        # the fragment-level selection alone is NOT what the reference computes on this file
+    differs = 0
+    for c in m["wps"]:
+        kw = {"window_size": 120, "min_length": 120, "max_length": 180, "quality_threshold": 30, **c["kwargs"]}
+        whole = _frags(O.bam_fetch(raw, c["contig"]))
+        differs += not np.array_equal(O.wps_interval(whole, c["start"], c["stop"], sizes[c["contig"]], **kw), g[c["key"]])
+    assert differs >= 1
+    for c in m["single_coverage"]:
+        if c["contig"] is None:
+            continue
+        fr = _frags(O.bam_fetch(raw, c["contig"], c["start"], c["stop"]))
+        assert O.single_coverage(fr, c["start"], c["stop"], **c["kwargs"]) == c["result"][4], c
+
+
+def test_decoder_read1_spans(bam):
+    from finaletoolkit_b200.io import fragments
+    path, g, m = bam
+    fragments._CACHE.clear()
+    tab = fragments.load_fragments(path)
+    assert tab.is_sam and tab.has_read1() and tab.contigs == ["chrA", "chrB"]
+    _, rows = O.bam_fragments(g["bam_file"].tobytes(), with_read1=True)
+    for contig in tab.contigs:
+        r = [x for x in rows if x[0] == contig]
+        order = np.argsort(np.array([x[1] for x in r]), kind="stable")
+        st, sp, mq, sd = tab.host(contig)
+        assert st.tolist() == [r[i][1] for i in order] and sp.tolist() == [r[i][2] for i in order]
+        lo, hi = tab.read1[contig]
+        # stored clipped to the fragment (a dovetailed read decides nothing outside its own template)
+        assert lo.tolist() == [max(r[i][5], r[i][1]) for i in order]
+        assert hi.tolist() == [max(min(r[i][6], r[i][2]), max(r[i][5], r[i][1]) + 1) for i in order]
+    assert any(x[6] > x[2] or x[5] < x[1] for x in rows if x[0] == "chrB")        # the dovetails are there
+    fragments._CACHE.clear()
+
+
+def test_host_stream_helpers_on_bam(bam):
+    import finaletoolkit_b200 as F
+    path, g, m = bam
+    for c in m["frag_generator"]:
+        rows = list(F.frag_generator(path, c["contig"], start=c["start"], stop=c["stop"], **c["kwargs"]))
+        got = np.array([[r[1], r[2], r[3], int(r[4])] for r in rows], np.int64).reshape(-1, 4)
+        # the table is sorted by fragment start, a BAM by read position: same rows, order within a contig may differ
+        if c["contig"] is None:
+            assert sorted({r[0] for r in rows}) == c["contigs"]
+        assert np.array_equal(_sorted_rows(got), _sorted_rows(g[c["key"]])), c
+    for c in m["frag_array"]:
+        fa = F.frag_array(path, c["contig"], start=c["start"], stop=c["stop"], **c["kwargs"])
+        got = np.stack([fa["start"], fa["stop"], fa["strand"].astype(np.int64)], axis=1)
+        exp = g[c["key"]]
+        assert np.array_equal(got[np.lexsort(got.T[::-1])], exp[np.lexsort(exp.T[::-1])])
+
+
+def test_per_fetch_reproduces_reference_counts(bam):
+    """``per_fetch`` with the per-table work done on the host: the grouping / union logic alone must turn a
+    fragment-level counter into the reference's read-level numbers (coverage text of 110 intervals, 3 configs)."""
+    from finaletoolkit_b200.frag._common import group_by_contig, per_fetch
+    from finaletoolkit_b200.io import fragments
+    path, g, m = bam
+    fragments._CACHE.clear()
+    tab = fragments.load_fragments(path)
+    ivs = [ln.split("\t") for ln in m["tiles"].splitlines()]
+    ivs = [(x[0], int(x[1]), int(x[2]), x[3] if len(x) > 3 else ".") for x in ivs]
+    calls = []
+    for case in m["coverage"]:
+        kw = {"intersect_policy": "midpoint", "min_length": None, "max_length": None, "quality_threshold": 30,
+              **{k: v for k, v in case["kwargs"].items() if k not in ("normalize", "scale_factor")}}
+        counts = [0] * len(ivs)
+        for contig, idx in group_by_contig([iv[0] for iv in ivs]).items():
+            def run(t, sel, contig=contig, idx=idx):
+                calls.append(len(sel))
+                st, sp, mq, sd = t.host(contig)
+                fr = O.Frags(st, sp, mq, sd)
+                return [O.single_coverage(fr, ivs[idx[k]][1], ivs[idx[k]][2], **kw) for k in sel]
+            for i, v in zip(idx, per_fetch(tab, contig, [ivs[i][1] for i in idx], [ivs[i][2] for i in idx], run)):
+                counts[i] = v
+        scale = case["kwargs"].get("scale_factor", 1.0)
+        if case["kwargs"].get("normalize"):
+            total = sum(O.single_coverage(O.Frags(*tab.host(c)), 0, None, **kw) for c in tab.contigs)
+            scale /= total
+        text = "".join(f"{c}\t{s}\t{e}\t{n}\t{v * scale}\n" for (c, s, e, n), v in zip(ivs, counts))
+        assert text == case["text"], case["kwargs"]
+    # a handful of batched calls per contig, not one per interval
+    assert max(calls) > 10 and len(calls) < 40
+    # and the fragment-level predicate alone gives different numbers on this file
+    st, sp, mq, sd = tab.host("chrA")
+    plain = [O.single_coverage(O.Frags(st, sp, mq, sd), s, e) for c, s, e, _ in ivs if c == "chrA"]
+    exp = [float(ln.split("\t")[4]) for ln in m["coverage"][0]["text"].splitlines() if ln.startswith("chrA")]
+    assert plain != exp
+    fragments._CACHE.clear()
