@@ -288,7 +288,9 @@ class GenomeShard:
         t = torch()
         dev = self.device
         key = cache_key if cache_key is not None else ("whole" if bins is None else id(bins))
-        sets = self._bin_sets.get(key)
+        hit = self._bin_sets.get(key)
+        # an id()-keyed entry keeps its dict alive, so the id cannot be handed to another object while cached
+        sets = hit[1] if (hit is not None and (cache_key is not None or bins is None or hit[0] is bins)) else None
         if sets is None:
             sets = []
             for gi, g in enumerate(self.groups):
@@ -313,7 +315,7 @@ class GenomeShard:
                 sets.append((ivl, where, t.tensor(f_off, dtype=t.int64, device=dev),
                              t.tensor(f_ord or [0], dtype=t.int64, device=dev),
                              t.zeros(max(ivl.n, 1), dtype=t.int64, device=dev)))
-            self._bin_sets[key] = sets
+            self._bin_sets[key] = (bins, sets)
         hist = t.zeros((1, n_bins), dtype=t.int64, device=dev) if n_bins else None
         keys = t.full((n_bins,), FIRST_SEEN_NONE, dtype=t.int64, device=dev) if (n_bins and first_seen) else None
         counts = {}

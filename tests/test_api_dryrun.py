@@ -1,0 +1,37 @@
+"""CPU dry run of the public-API tests: the bodies of ``tests/test_gpu_api.py`` (reference fixtures and golden
+texts through wps / multi_wps / coverage / frag_length* / end + breakpoint motifs / cleavage / BAM input) with the
+kernel wrappers swapped for the oracle (``tests/host_shim.py``).  Covers the host side of those calls - argument
+handling, warnings and errors, interval bookkeeping, statistics, text / bigWig writers - where no GPU exists; the
+``-m gpu`` run of the same bodies covers the kernels."""
+import numpy as np
+import pytest
+
+import host_shim
+import test_gpu_api as A
+from test_gpu_api import fx, syn  # noqa: F401  (fixtures)
+
+_NEEDS_DEVICE = {"test_adjust_wps", "test_multi_wps_streams_large_contigs"}   # adjust kernels / streamed pipeline
+
+
+@pytest.fixture(autouse=True)
+def _oracle_device_layer(monkeypatch):
+    from finaletoolkit_b200.io import fragments
+    from finaletoolkit_b200.io.reference import ReferenceWrapper
+
+    def host_sequence(self, contig, device=None):
+        codes, n_mask = self.contig_arrays(contig)
+        s = np.frombuffer(b"ACGT", np.uint8)[np.asarray(codes) & 3].copy()
+        s[np.asarray(n_mask).astype(bool)] = ord("N")
+        return s.tobytes()
+
+    fragments._CACHE.clear()
+    host_shim.install(monkeypatch, {})
+    monkeypatch.setattr(ReferenceWrapper, "device_contig", host_sequence)
+    yield
+    fragments._CACHE.clear()
+
+
+for _name in dir(A):
+    if _name.startswith("test_") and _name not in _NEEDS_DEVICE:
+        globals()[_name] = getattr(A, _name)
+del _name
