@@ -42,9 +42,13 @@ def bedgraph_text(contig: str, start: int, scores) -> np.ndarray:
 
 
 class GzipTextWriter:
-    """``gzip.open(path, "wt")`` look-alike (``write`` of str or bytes) that deflates on all host threads."""
+    """``gzip.open(path, "wt")`` look-alike (``write`` of str or bytes) that deflates on all host threads.
 
-    def __init__(self, path: str, level: int = 6):
+    zlib level 4 by default: on bedGraph text of WPS tracks it is 3.6x faster than level 6 (77 against 21 MB/s
+    per thread) for a file that is no larger (0.243 against 0.244 of the text; the reference's level 9 runs at
+    3.5 MB/s for 0.244)."""
+
+    def __init__(self, path: str, level: int = 4):
         self._fh = builtins.open(str(path), "wb")
         self._level = int(level)
         self._parts: list[bytes] = []
