@@ -354,7 +354,7 @@ def genome_block(args, dev, rank, world, peak):
     import torch.distributed as dist
     from finaletoolkit_b200 import device as D
     from finaletoolkit_b200.distributed import multi_wps_genome, owned_contigs, tile_genome
-    from finaletoolkit_b200.sharding import DistContext, genome_length_dict
+    from finaletoolkit_b200.sharding import DistContext
 
     ctx = DistContext()
     table = SynthGenomeTable(GENOME_NFRAG, dev)

@@ -391,6 +391,10 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
     ``median_window_size`` positions is adjusted straight from the int32 WPS in HBM - no bigWig
     round trip, no float32 copy.
 
+    BAM input: the genome pass selects FRAGMENTS per interval, not reads (a device-resident sweep has no
+    per-interval index query); a table that carries read-1 spans gets a ``UserWarning`` - use
+    ``multi_wps`` where the reference's read-level selection matters.
+
     ``n_bins``: histogram width when the caller knows it (longest fragment of the job + 1) - saves the
     MAX all-reduce and its host synchronisation; ``plans``: a dict the shard is cached in (built on the
     first call, reused afterwards: same table, sites, contigs and max_length) - the returned tensors
@@ -415,6 +419,10 @@ def multi_wps_genome(table, chrom_sizes, sites: dict | None = None, interval_siz
     key = ("shard", tuple(mine), int(max_length), int(window_size))
     shard = plans.get(key) if plans is not None else None
     if shard is None:
+        if getattr(table, "has_read1", None) is not None and any(table.has_read1(c) for c in mine):
+            import warnings
+            warnings.warn("multi_wps_genome selects fragments, not reads, per interval: on BAM input its values can "
+                          "differ from multi_wps at interval edges (DESIGN 7.1)", UserWarning, stacklevel=2)
         shard = GenomeShard(table, sizes, sites, mine, int(max_length), int(window_size), dev)
         if plans is not None:
             plans[key] = shard

@@ -21,7 +21,7 @@ from __future__ import annotations
 import numpy as np
 
 from ._lib import check, lib
-from .device import ContigFragments, WpsPlan, _stream_ptr, none_to_ftk, require_cuda, torch
+from .device import WpsPlan, _stream_ptr, none_to_ftk, require_cuda, torch
 from .packed import PACK_BLOCK, PackedFragments
 
 __all__ = ["StreamedContig"]
