@@ -51,34 +51,43 @@ class GzipTextWriter:
     def __init__(self, path: str, level: int = 4):
         self._fh = builtins.open(str(path), "wb")
         self._level = int(level)
-        self._parts: list[bytes] = []
-        self._size = 0
+        # one staging buffer for the text and one for the deflated members, reused from batch to batch (fresh
+        # 64 MB allocations cost more in page faults than the copy into them)
+        self._raw = np.empty(_FLUSH + _MEMBER, dtype=np.uint8)
+        self._fill = 0
+        self._out = None
 
     def write(self, text) -> None:
-        data = text.encode() if isinstance(text, str) else memoryview(text).cast("B")
-        if len(data):
-            self._parts.append(data)
-            self._size += len(data)
-            if self._size >= _FLUSH:
+        data = np.frombuffer(text.encode() if isinstance(text, str) else memoryview(text).cast("B"), dtype=np.uint8)
+        pos = 0
+        while pos < data.size:
+            n = min(data.size - pos, self._raw.size - self._fill)
+            self._raw[self._fill: self._fill + n] = data[pos: pos + n]
+            self._fill += n
+            pos += n
+            if self._fill >= _FLUSH:
                 self._flush()
 
     def _flush(self) -> None:
-        if not self._parts:
+        if not self._fill:
             return
-        raw = np.frombuffer(b"".join(self._parts), dtype=np.uint8)
-        self._parts, self._size = [], 0
+        raw = self._raw[: self._fill]
+        self._fill = 0
         n = -(-raw.size // _MEMBER)
         in_off = np.minimum(np.arange(n + 1, dtype=np.int64) * _MEMBER, raw.size)
         lens = np.diff(in_off)
         out_off = np.zeros(n + 1, dtype=np.int64); np.cumsum(lens + lens // 1000 + 64, out=out_off[1:])
-        out = np.empty(int(out_off[-1]), dtype=np.uint8)
+        if self._out is None or self._out.size < int(out_off[-1]):
+            cap = self._raw.size
+            self._out = np.empty(max(int(out_off[-1]), cap + cap // 1000 + 64 * (cap // _MEMBER + 1)), dtype=np.uint8)
+        out = self._out
         sizes = np.zeros(n, dtype=np.int64)
         p = lambda a, t: a.ctypes.data_as(ctypes.POINTER(t))   # noqa: E731
         check(lib().ftk_gzip_compress_batch(p(raw, ctypes.c_uint8), p(in_off, ctypes.c_int64), n, self._level, 0,
                                             p(out, ctypes.c_uint8), p(out_off, ctypes.c_int64),
                                             p(sizes, ctypes.c_int64)), "ftk_gzip_compress_batch")
         for o, z in zip(out_off[:-1].tolist(), sizes.tolist()):
-            self._fh.write(out[o: o + z].tobytes())
+            self._fh.write(out[o: o + z].data)
 
     def close(self) -> None:
         if self._fh is None:
