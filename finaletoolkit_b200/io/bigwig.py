@@ -442,8 +442,19 @@ class BigWigReader:
             raise RuntimeError("Invalid interval bounds!")
         b, e = self._buf, self._e
         S, E, V = [], [], []
-        for doff, dsize in self._blocks(cid, start, end):
-            raw = self._section(doff, dsize)
+        blocks = self._blocks(cid, start, end)
+        local = {}
+        if self._uncomp and len(blocks) > 8:
+            # a long query: inflate its sections in multi-threaded batches instead of one zlib call each
+            missing = [b for b in blocks if b[0] not in self._cache]
+            per_batch = max(1, _FLUSH_BYTES // max(int(self._uncomp), 1))
+            for i in range(0, len(missing), per_batch):
+                part = missing[i: i + per_batch]
+                local.update(zip((d for d, _ in part), _inflate_sections(self._buf, part, self._uncomp)))
+        for doff, dsize in blocks:
+            raw = local.pop(doff, None)
+            if raw is None:
+                raw = self._section(doff, dsize)
             bcid, bstart, bend, step, span, typ, _, n = struct.unpack_from(e + "IIIIIBBH", raw, 0)
             if bcid != cid:
                 continue
