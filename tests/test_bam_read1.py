@@ -147,3 +147,51 @@ def test_per_fetch_reproduces_reference_counts(bam):
     exp = [float(ln.split("\t")[4]) for ln in m["coverage"][0]["text"].splitlines() if ln.startswith("chrA")]
     assert plain != exp
     fragments._CACHE.clear()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_fetch_selection_brute_force(seed):
+    """``read1_affected`` / ``fetched`` / ``fetch_groups`` / ``fetched_union`` against a brute-force restatement on
+    random read-1 tables and random region sets (tilings, overlapping padded windows, scattered, unbounded)."""
+    from finaletoolkit_b200.io.fragments import FragmentTable
+    rng = np.random.default_rng(seed)
+    n = 6000
+    st = np.sort(rng.integers(0, 120_000, n))
+    ln = rng.integers(40, 420, n)
+    rl = np.minimum(rng.integers(20, 160, n), ln + rng.integers(-5, 30, n)).clip(1)      # some reads run past the template
+    fwd = rng.random(n) < 0.5
+    sp = st + ln
+    r1s = np.where(fwd, st, sp - rl); r1e = np.where(fwd, st + rl, sp)
+    tab = FragmentTable({"c": (st, sp, rng.integers(0, 61, n).astype(np.uint8), fwd.astype(np.uint8))}, is_sam=True,
+                        read1={"c": (r1s, r1e)})
+    fs, fe, _, _ = tab.host("c")
+    lo1, hi1 = tab.read1["c"]
+    assert np.all(lo1 >= fs) and np.all(hi1 <= fe) and np.all(hi1 > lo1)
+    sets = [(np.arange(0, 120_000, 5_000), np.arange(0, 120_000, 5_000) + 5_000),
+            (np.arange(0, 120_000, 900) - 180, np.arange(0, 120_000, 900) + 1_180),
+            (rng.integers(-500, 120_000, 150), None)]
+    for S, E in sets:
+        if E is None:
+            E = S + rng.integers(1, 6_000, len(S))
+        aff = tab.read1_affected("c", S, E)
+        groups = tab.fetch_groups("c", S, E)
+        assert sorted(np.concatenate(groups).tolist()) == list(range(len(S)))
+        for g in groups:
+            a, b, _, _ = tab.fetched_union("c", S[g], E[g]).host("c")
+            gs = np.sort(S[g]); ge = E[g][np.argsort(S[g], kind="stable")]
+            assert np.all(gs[1:] >= ge[:-1])                                    # disjoint inside a group
+            for k in g.tolist():
+                fetched = (lo1 < E[k]) & (hi1 > S[k])                           # what an indexed fetch yields
+                frag_any = (fs < E[k]) & (fe > S[k])
+                assert aff[k] == bool((frag_any & ~fetched).any())
+                one = tab.fetched("c", int(S[k]), int(E[k])).host("c")
+                assert np.array_equal(one[0], fs[fetched]) and np.array_equal(one[1], fe[fetched])
+                # inside the union table the kernels' own predicates see exactly the fetched rows of region k
+                seen = (a < E[k]) & (b > S[k])
+                assert np.array_equal(np.c_[a[seen], b[seen]], np.c_[fs[fetched & frag_any], fe[fetched & frag_any]])
+                mid, cm = (a + b) // 2, (fs.astype(np.int64) + fe) // 2
+                assert np.array_equal(a[(mid >= S[k]) & (mid < E[k])], fs[fetched & (cm >= S[k]) & (cm < E[k])])
+    assert tab.fetched("c", None, None).n_fragments("c") == n and not tab.read1_affected("c", [None], [None])[0]
+    assert tab.fetched("c", 60_000, None).n_fragments("c") == int((hi1 > 60_000).sum())
+    plain = FragmentTable({"c": (st, sp, np.zeros(n, np.uint8), np.ones(n, np.uint8))})
+    assert not plain.has_read1("c") and plain.fetched("c", 5, 10) is plain and not plain.read1_affected("c", [5], [10]).any()
