@@ -1,5 +1,5 @@
 """CPU dry run of the public-API tests: the bodies of ``tests/test_gpu_api.py`` (reference fixtures and golden
-texts through wps / multi_wps / coverage / frag_length* / end + breakpoint motifs / cleavage / BAM input) with the
+texts through wps / multi_wps / coverage / frag_length* / end + breakpoint motifs / cleavage / delfi / BAM input) with the
 kernel wrappers swapped for the oracle (``tests/host_shim.py``).  Covers the host side of those calls - argument
 handling, warnings and errors, interval bookkeeping, statistics, text / bigWig writers - where no GPU exists; the
 ``-m gpu`` run of the same bodies covers the kernels."""
@@ -35,3 +35,7 @@ for _name in dir(A):
     if _name.startswith("test_") and _name not in _NEEDS_DEVICE:
         globals()[_name] = getattr(A, _name)
 del _name
+
+# the API-level bodies of two more GPU test modules: the delfi() table and the cleavage drivers
+from test_gpu_cleavage import test_golden_cases_through_the_api  # noqa: E402,F401
+from test_gpu_delfi import test_delfi_api  # noqa: E402,F401
