@@ -43,11 +43,15 @@ def region_breakpoint_motifs(input_file, contig, start, stop, refseq_file, k=6, 
     table = as_table(input_file, refseq_file)
     ref = _ref(refseq_file)
     kmer_list = gen_kmers(k, "ACGT")
-    if table.has_read1(contig):   # BAM: what an indexed fetch of the region yields
-        table = table.fetched(contig, int(start), int(stop))
+    widen = 0
+    if table.has_read1(contig):
+        # BAM: every fragment an indexed fetch of the region yields counts, with no fragment-level test
+        # (:115-120) - the sub-table holds exactly those rows and the wider bounds let all of them through
+        widen = table.fetch_reach(contig)
+        table = table.fetched(contig, int(start), int(stop), fetch_only=True)
     if table.n_fragments(contig) == 0:
         return dict(zip(kmer_list, 4 ** k * [0]))
-    counts = end_motif_hist(table.device(contig), ref.device_contig(contig), [int(start)], [int(stop)], k=k,
+    counts = end_motif_hist(table.device(contig), ref.device_contig(contig), [int(start) - widen], [int(stop) + widen], k=k,
                             strand_mode=mode, quality_threshold=quality_threshold, breakpoint=True)
     if verbose:
         stderr.write(f"region_breakpoint_motifs took {time() - start_time} seconds to run\n")

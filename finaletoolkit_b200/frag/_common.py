@@ -52,7 +52,7 @@ def group_by_contig(contigs):
     return groups
 
 
-def per_fetch(table, contig, fetch_starts, fetch_stops, run):
+def per_fetch(table, contig, fetch_starts, fetch_stops, run, fetch_only: bool = False):
     """The per-interval results ``run`` produces, with the READ-level region selection a BAM query makes.
 
     ``run(tab, sel) -> list`` computes the intervals at positions ``sel`` of the caller's list from the
@@ -66,11 +66,18 @@ def per_fetch(table, contig, fetch_starts, fetch_stops, run):
     (``FragmentTable.fetched_union``).  Such intervals share a launch whenever no fragment can reach two of
     them (``FragmentTable.fetch_groups``: a tiling of 5-kb windows is two groups, even and odd), so a BAM
     costs a few batched calls per contig, not one per interval; all unaffected intervals go through one
-    call on the whole table."""
+    call on the whole table.
+
+    ``fetch_only``: the caller applies NO fragment-level test after the fetch (the motif counters,
+    frag/_end_motifs.py:115-120), so a dovetailed pair whose read 1 runs past its own template counts wherever
+    the read reaches.  The fetched tables are then selected by the whole read and ``run(tab, sel, widen)`` is
+    asked to query them with bounds widened by ``widen`` = ``FragmentTable.fetch_reach`` - every row of the
+    sub-table passes the kernel's overlap test for its own region, and the groups are spaced so that it
+    passes for no other."""
     n = len(fetch_starts)
     if n == 0 or not table.has_read1(contig):
         return run(table, list(range(n)))
-    affected = table.read1_affected(contig, fetch_starts, fetch_stops)
+    affected = table.read1_affected(contig, fetch_starts, fetch_stops, fetch_only)
     out: list = [None] * n
     clean = np.flatnonzero(~affected).tolist()
     if clean:
@@ -80,10 +87,12 @@ def per_fetch(table, contig, fetch_starts, fetch_stops, run):
     if todo.size:
         lo = [fetch_starts[k] for k in todo.tolist()]
         hi = [fetch_stops[k] for k in todo.tolist()]
-        for members in table.fetch_groups(contig, lo, hi):
+        extra = (table.fetch_reach(contig),) if fetch_only else ()
+        for members in table.fetch_groups(contig, lo, hi, fetch_only):
             sel = todo[members].tolist()
-            rows = table.fetched_union(contig, [lo[m] for m in members.tolist()], [hi[m] for m in members.tolist()])
-            for k, r in zip(sel, run(rows, sel)):
+            rows = table.fetched_union(contig, [lo[m] for m in members.tolist()], [hi[m] for m in members.tolist()],
+                                       fetch_only)
+            for k, r in zip(sel, run(rows, sel, *extra)):
                 out[k] = r
     return out
 

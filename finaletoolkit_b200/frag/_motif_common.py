@@ -285,15 +285,16 @@ def interval_motif_rows(table, ref, chrom, starts, stops, k, strand_mode, qualit
     from ..device import end_motif_hist
     from ._common import per_fetch
 
-    def run(tab, sel):
+    def run(tab, sel, widen=0):
         if tab.n_fragments(chrom) == 0:
             return [np.zeros(4 ** k, np.int64) for _ in sel]
-        got = end_motif_hist(tab.device(chrom, device), ref.device_contig(chrom, device), [starts[j] for j in sel],
-                             [stops[j] for j in sel], k=k, strand_mode=strand_mode,
-                             quality_threshold=quality_threshold, breakpoint=breakpoint)
+        # widen > 0: ``tab`` holds exactly the fetched rows; the wider bounds let every one of them through
+        got = end_motif_hist(tab.device(chrom, device), ref.device_contig(chrom, device),
+                             [int(starts[j]) - widen for j in sel], [int(stops[j]) + widen for j in sel], k=k,
+                             strand_mode=strand_mode, quality_threshold=quality_threshold, breakpoint=breakpoint)
         return list(got.cpu().numpy())
 
-    rows = per_fetch(table, chrom, starts, stops, run)
+    rows = per_fetch(table, chrom, starts, stops, run, fetch_only=True)
     return np.stack(rows) if rows else np.zeros((0, 4 ** k), np.int64)
 
 

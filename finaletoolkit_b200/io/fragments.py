@@ -63,6 +63,7 @@ class FragmentTable:
         # BAM/CRAM only: {contig: (r1_start, r1_end) int32}, the reference span of read 1 of every fragment
         # (rows as in ``columns``), clipped to the fragment
         self.read1: Dict[str, tuple] = {}
+        self.read1_raw: Dict[str, tuple] = {}      # the spans as aligned (a dovetailed read runs past its template)
         self._read1_in = read1 or {}
         self._lazy_names, self._loader = (list(lazy[0]), lazy[1]) if lazy is not None else (None, None)
         self._weights = lazy[2] if (lazy is not None and len(lazy) > 2) else None
@@ -93,6 +94,9 @@ class FragmentTable:
             lo = np.maximum(r1[0], st).astype(np.int32)
             hi = np.maximum(np.minimum(r1[1], sp), lo + 1).astype(np.int32)
             self.read1[contig] = (lo, hi)
+            # the motif counters take every fetched fragment WITHOUT a fragment-level test
+            # (frag/_end_motifs.py:115-120), so for them the whole read decides: ``fetch_only`` below
+            self.read1_raw[contig] = (r1[0].astype(np.int32), np.maximum(r1[1], r1[0] + 1).astype(np.int32))
 
     def _ensure(self, contig) -> None:
         if self._loader is not None and contig not in self.columns and contig in self._lazy_names:
@@ -139,9 +143,15 @@ class FragmentTable:
         if contig not in cache:
             st, sp = self.columns[contig][:2]
             lo, hi = self.read1[contig]
-            cache[contig] = (np.sort(sp), np.sort(lo), np.sort(hi),
-                             int((sp.astype(np.int64) - st).max()) if st.size else 0)
+            raw_lo, raw_hi = self.read1_raw[contig]
+            max_len = int((sp.astype(np.int64) - st).max()) if st.size else 0
+            reach = max(max_len, int((raw_hi.astype(np.int64) - raw_lo).max()) if st.size else 0)
+            cache[contig] = (np.sort(sp), np.sort(lo), np.sort(hi), max_len, np.sort(raw_lo), np.sort(raw_hi), reach)
         return cache[contig]
+
+    def fetch_reach(self, contig: str) -> int:
+        """How far a fetched row can lie from its query region: the longest fragment or read-1 span of the contig."""
+        return self._read1_sorted(contig)[6] if self.has_read1(contig) else 0
 
     @staticmethod
     def _bounds(starts, stops):
@@ -150,49 +160,64 @@ class FragmentTable:
         hi = np.array([big if v is None else int(v) for v in stops], dtype=np.int64)
         return lo, hi
 
-    def read1_affected(self, contig: str, starts, stops) -> np.ndarray:
-        """bool per query region ``[starts[i], stops[i])`` (None = unbounded): does the region hold a fragment
-        that overlaps it while its read 1 does not?  Only for those regions can the read-level fetch of the
-        reference (io/alignment.py:245) and a fragment-level predicate disagree.  Two binary searches per
-        region over sorted copies of the four coordinate columns."""
+    def read1_affected(self, contig: str, starts, stops, fetch_only: bool = False) -> np.ndarray:
+        """bool per query region ``[starts[i], stops[i])`` (None = unbounded): can the read-level fetch of the
+        reference (io/alignment.py:245) and a fragment-level predicate disagree on it?  Default (the fetch is
+        followed by an intersect policy): the region holds a fragment that overlaps it while its read 1 does not.
+        ``fetch_only`` (the motif counters take every fetched fragment as it comes): additionally a read that
+        overlaps the region while its own - shorter, dovetailed - template does not.  Two binary searches per
+        region and coordinate column over sorted copies."""
         lo, hi = self._bounds(starts, stops)
         if not self.has_read1(contig) or not len(lo):
             return np.zeros(len(lo), dtype=bool)
         st = self.columns[contig][0]
-        sp_sorted, r1s_sorted, r1e_sorted, _ = self._read1_sorted(contig)
+        sp_sorted, r1s_sorted, r1e_sorted, _, raw_s, raw_e, _ = self._read1_sorted(contig)
         # reads and fragments have positive length, so  #overlapping = #(begin < hi) - #(end <= lo)
         frag = np.searchsorted(st, hi, side="left") - np.searchsorted(sp_sorted, lo, side="right")
-        read = np.searchsorted(r1s_sorted, hi, side="left") - np.searchsorted(r1e_sorted, lo, side="right")
-        return (frag != read) & (hi > lo)
+        both = np.searchsorted(r1s_sorted, hi, side="left") - np.searchsorted(r1e_sorted, lo, side="right")
+        differ = frag != both         # ``read1`` = read AND fragment: its overlaps are a subset of either's
+        if fetch_only:
+            read = np.searchsorted(raw_s, hi, side="left") - np.searchsorted(raw_e, lo, side="right")
+            differ |= read != both
+        return differ & (hi > lo)
 
-    def fetched(self, contig: str, start=None, stop=None) -> "FragmentTable":
-        """The rows an indexed BAM fetch of ``contig:[start, stop)`` yields (read 1 overlaps the region,
-        io/alignment.py:245; None = unbounded), as a one-contig table without read-1 columns: the fragment-level
-        predicates of the kernels then finish the job exactly like ``frag_generator`` does after the fetch."""
-        if not self.has_read1(contig):
-            return self
-        (lo,), (hi,) = self._bounds([start], [stop])
+    def _subtable(self, contig: str, keep: np.ndarray) -> "FragmentTable":
         st, sp, mq, sd = self.columns[contig]
-        r1s, r1e = self.read1[contig]
-        max_len = self._read1_sorted(contig)[3]
-        a = int(np.searchsorted(st, lo - max_len, side="left"))      # a row further left ends before the region
-        b = int(np.searchsorted(st, hi, side="left"))                # read 1 begins at or after the fragment start
-        keep = np.flatnonzero((r1s[a:b] < hi) & (r1e[a:b] > lo)) + a
         sub = FragmentTable({contig: (st[keep], sp[keep], mq[keep], sd[keep])}, source=self.source,
                             is_sam=self.is_sam, contig_lengths=self.contig_lengths)
         sub._transient = True     # one query's rows: uploaded through staging, not page-locked in place
         return sub
 
-    def fetch_groups(self, contig: str, starts, stops) -> list:
+    def fetched(self, contig: str, start=None, stop=None, fetch_only: bool = False) -> "FragmentTable":
+        """The rows an indexed BAM fetch of ``contig:[start, stop)`` yields (read 1 overlaps the region,
+        io/alignment.py:245; None = unbounded), as a one-contig table without read-1 columns: the fragment-level
+        predicates of the kernels then finish the job exactly like ``frag_generator`` does after the fetch.
+        ``fetch_only``: select by the whole read (see ``read1_affected``); a caller that applies no intersect
+        policy then queries the sub-table with bounds widened by ``fetch_reach`` so that every row passes."""
+        if not self.has_read1(contig):
+            return self
+        (lo,), (hi,) = self._bounds([start], [stop])
+        st = self.columns[contig][0]
+        r1s, r1e = (self.read1_raw if fetch_only else self.read1)[contig]
+        reach = self._read1_sorted(contig)[6]
+        a = int(np.searchsorted(st, lo - reach, side="left"))     # rows further out cannot reach the region
+        b = int(np.searchsorted(st, hi + reach, side="left"))
+        return self._subtable(contig, np.flatnonzero((r1s[a:b] < hi) & (r1e[a:b] > lo)) + a)
+
+    def fetch_groups(self, contig: str, starts, stops, fetch_only: bool = False) -> list:
         """Partition query regions into groups that can share ONE fetched table: inside a group any two
         regions lie at least one maximal fragment length apart, so a row fetched for one of them is entirely
         outside every other and cannot pass the other's fragment predicate (midpoint or overlap).  A tiling of
-        5-kb windows needs two groups (even / odd) instead of one query per window.  Returns index arrays
-        (ascending) into ``starts``; first-fit over the regions sorted by start."""
+        5-kb windows needs two groups (even / odd) instead of one query per window.  ``fetch_only``: the
+        regions are going to be queried widened by ``fetch_reach`` on either side, so they keep twice that
+        distance plus one.  Returns index arrays (ascending) into ``starts``; first-fit over the regions sorted
+        by start."""
         lo, hi = self._bounds(starts, stops)
         if not len(lo):
             return []
-        gap = self._read1_sorted(contig)[3] if self.has_read1(contig) else 0
+        gap = 0
+        if self.has_read1(contig):
+            gap = 2 * self._read1_sorted(contig)[6] + 1 if fetch_only else self._read1_sorted(contig)[3]
         group_end: list = []           # the right-most region end of every group so far
         members: list = []
         for j in np.argsort(lo, kind="stable").tolist():
@@ -204,7 +229,7 @@ class FragmentTable:
                 group_end.append(int(hi[j])); members.append([j])
         return [np.sort(np.asarray(m, dtype=np.int64)) for m in members]
 
-    def fetched_union(self, contig: str, starts, stops) -> "FragmentTable":
+    def fetched_union(self, contig: str, starts, stops, fetch_only: bool = False) -> "FragmentTable":
         """The rows whose read 1 overlaps ANY of the regions of one ``fetch_groups`` group (pairwise disjoint,
         at least a fragment length apart), as a one-contig table without read-1 columns - the rows of
         ``fetched`` for every region of the group in one table."""
@@ -213,16 +238,11 @@ class FragmentTable:
         lo, hi = self._bounds(starts, stops)
         order = np.argsort(lo, kind="stable")
         lo, hi = lo[order], hi[order]
-        st, sp, mq, sd = self.columns[contig]
-        r1s, r1e = self.read1[contig]
+        r1s, r1e = (self.read1_raw if fetch_only else self.read1)[contig]
         # the regions are disjoint and sorted: the only candidate of a read is the first region ending after its start
         k = np.searchsorted(hi, r1s, side="right")
         ok = k < len(lo)
-        keep = np.flatnonzero(ok & (lo[np.minimum(k, len(lo) - 1)] < r1e))
-        sub = FragmentTable({contig: (st[keep], sp[keep], mq[keep], sd[keep])}, source=self.source,
-                            is_sam=self.is_sam, contig_lengths=self.contig_lengths)
-        sub._transient = True
-        return sub
+        return self._subtable(contig, np.flatnonzero(ok & (lo[np.minimum(k, len(lo) - 1)] < r1e)))
 
     def pinned(self, contig: str):
         """``(start, stop, mapq, strand)`` of one contig as CPU torch tensors that SHARE the host columns' memory,

@@ -109,9 +109,27 @@ def synth_records(seed=20261017):
     return recs
 
 
+def dovetail_regions(records, n=4):
+    """Small regions on chrB that only the OVERHANG of a dovetailed read 1 touches (read past its template)."""
+    out = []
+    for r in records:
+        ref_len = sum(ln for op, ln in r["cigar"] if op in (0, 2, 3, 7, 8))
+        if r["ref"] != 1 or r["flag"] != GOOD and r["flag"] != (GOOD | 0x10) or ref_len <= abs(r["tlen"]):
+            continue
+        if r["tlen"] > 0:
+            out.append(("chrB", r["pos"] + r["tlen"], r["pos"] + r["tlen"] + 3))        # just right of the template
+        else:
+            end = r["pos"] + ref_len
+            out.append(("chrB", max(end + r["tlen"] - 3, 0), end + r["tlen"]))           # just left of it
+        if len(out) == n:
+            break
+    return out
+
+
 def main():
     arrays, m = {}, {"generator": "oracle/make_golden_bam.py", "refs": [list(r) for r in REFS]}
-    bam = write_bam(os.path.join(TMP, "read1.bam"), REFS, synth_records(), block=6000)
+    records = synth_records()
+    bam = write_bam(os.path.join(TMP, "read1.bam"), REFS, records, block=6000)
     arrays["bam_file"] = np.frombuffer(open(bam, "rb").read(), np.uint8)
     seqs = []
     for idx, (name, ln) in enumerate(REFS):
@@ -205,13 +223,14 @@ def main():
         fli.append(dict(kwargs=kw, rows=[[x if isinstance(x, (str, int)) else float(x) for x in r] for r in rows]))
     m["frag_length_intervals"] = fli
 
-    # ---- end / breakpoint motifs on chrA (no dovetailed pairs there; see DESIGN.md for that residual)
+    # ---- end / breakpoint motifs (frag/_end_motifs.py:115-120: every fetched fragment counts, dovetails included)
     ivs = [("chrA", a, a + 1_500, ".") for a in range(500, 58_000, 1_500)] + [("chrA", 30_000, 30_040, "tiny"), ("chrA", 100, 59_900, "wide")]
     mot = []
     for j, (fn, kw) in enumerate([("region_end_motifs", dict(k=4)), ("region_end_motifs", dict(k=3, both_strands=False)),
                                   ("region_end_motifs", dict(k=2, both_strands=False, negative_strand=True, quality_threshold=0)),
                                   ("region_breakpoint_motifs", dict(k=4)), ("region_breakpoint_motifs", dict(k=6, both_strands=False))]):
-        for r, (c, s, e) in enumerate([("chrA", 10_000, 12_000), ("chrA", 45_100, 45_160), ("chrA", 1_000, 59_000)]):
+        for r, (c, s, e) in enumerate([("chrA", 10_000, 12_000), ("chrA", 45_100, 45_160), ("chrA", 1_000, 59_000),
+                                       ("chrB", 5_000, 5_600), ("chrB", 12_000, 12_100)] + dovetail_regions(records)):
             d = getattr(F, fn)(bam, c, s, e, tb, **kw)
             arrays[f"motif_{j}_{r}"] = np.array(list(d.values()), np.int64)
             mot.append(dict(fn=fn, contig=c, start=s, stop=e, kwargs=kw, key=f"motif_{j}_{r}"))
@@ -221,8 +240,15 @@ def main():
         res = getattr(F, fn)(bam, tb, ivs, workers=1, **kw)
         arrays[f"imotif_{j}"] = np.array([list(d.values()) for _, d in res.intervals], np.int64)
         imot.append(dict(fn=fn, kwargs=kw, key=f"imotif_{j}"))
+    # chrB carries dovetailed pairs: the motif counters take a fetched fragment without any fragment-level test
+    ivs_b = [("chrB", a, a + 400, ".") for a in range(300, 24_000, 400)] + [tuple(x) + ("dovetail",) for x in dovetail_regions(records)]
+    for j, (fn, kw) in enumerate([("interval_end_motifs", dict(k=3)), ("interval_breakpoint_motifs", dict(k=4, quality_threshold=0))]):
+        res = getattr(F, fn)(bam, tb, ivs_b, workers=1, **kw)
+        arrays[f"imotif_b_{j}"] = np.array([list(d.values()) for _, d in res.intervals], np.int64)
+        imot.append(dict(fn=fn, kwargs=kw, key=f"imotif_b_{j}", intervals="motif_intervals_b"))
     m["interval_motifs"] = imot
     m["motif_intervals"] = [list(iv) for iv in ivs]
+    m["motif_intervals_b"] = [list(iv) for iv in ivs_b]
 
     # ---- cleavage profile (frag/_cleavage_profile.py:188-217: fetch of the padded region, policy "any")
     clv = []

@@ -94,8 +94,8 @@ def check_motifs(bam):
     for c in m["region_motifs"]:
         d = getattr(F, c["fn"])(bam["path"], c["contig"], c["start"], c["stop"], bam["tb"], **c["kwargs"])
         assert np.array_equal(np.array(list(d.values()), np.int64), g[c["key"]]), c
-    ivs = [tuple(iv) for iv in m["motif_intervals"]]
     for c in m["interval_motifs"]:
+        ivs = [tuple(iv) for iv in m[c.get("intervals", "motif_intervals")]]
         res = getattr(F, c["fn"])(bam["path"], bam["tb"], ivs, **c["kwargs"])
         got = np.array([list(d.values()) for _, d in res.intervals], np.int64)
         assert np.array_equal(got, g[c["key"]]), c

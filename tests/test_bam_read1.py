@@ -191,6 +191,24 @@ def test_fetch_selection_brute_force(seed):
                 assert np.array_equal(np.c_[a[seen], b[seen]], np.c_[fs[fetched & frag_any], fe[fetched & frag_any]])
                 mid, cm = (a + b) // 2, (fs.astype(np.int64) + fe) // 2
                 assert np.array_equal(a[(mid >= S[k]) & (mid < E[k])], fs[fetched & (cm >= S[k]) & (cm < E[k])])
+        # fetch_only (no fragment-level test follows the fetch): selection by the WHOLE read, queried with bounds
+        # widened by fetch_reach - every fetched row of region k passes the overlap test, no other row does
+        raw_lo, raw_hi = tab.read1_raw["c"]
+        reach = tab.fetch_reach("c")
+        assert reach >= int((fe.astype(np.int64) - fs).max()) and reach >= int((raw_hi - raw_lo).max())
+        aff = tab.read1_affected("c", S, E, fetch_only=True)
+        groups = tab.fetch_groups("c", S, E, fetch_only=True)
+        assert sorted(np.concatenate(groups).tolist()) == list(range(len(S)))
+        for g in groups:
+            a, b, _, _ = tab.fetched_union("c", S[g], E[g], fetch_only=True).host("c")
+            for k in g.tolist():
+                fetched = (raw_lo < E[k]) & (raw_hi > S[k])
+                frag_any = (fs < E[k]) & (fe > S[k])
+                assert aff[k] == bool((frag_any != fetched).any())
+                one = tab.fetched("c", int(S[k]), int(E[k]), fetch_only=True).host("c")
+                assert np.array_equal(one[0], fs[fetched]) and np.array_equal(one[1], fe[fetched])
+                seen = (a < E[k] + reach) & (b > S[k] - reach)
+                assert np.array_equal(np.c_[a[seen], b[seen]], np.c_[fs[fetched], fe[fetched]])
     assert tab.fetched("c", None, None).n_fragments("c") == n and not tab.read1_affected("c", [None], [None])[0]
     assert tab.fetched("c", 60_000, None).n_fragments("c") == int((hi1 > 60_000).sum())
     plain = FragmentTable({"c": (st, sp, np.zeros(n, np.uint8), np.ones(n, np.uint8))})
