@@ -69,21 +69,28 @@ def adjust_wps(input_file, interval_file, output_file, chrom_sizes, interval_siz
                     j += 1
                 raw_wps.prefetch(intervals[k:j])
             try:
-                rng = raw_wps.intervals_arrays(contig, start, stop)
+                # per-base WPS tracks (what multi_wps writes) come back as (first position, values); anything
+                # else through the general query with its contiguity check (frag/_adjust_wps.py:85-117)
+                run = raw_wps.per_base_run(contig, start, stop)
+                rng = None if run is not None else raw_wps.intervals_arrays(contig, start, stop)
             except RuntimeError:  # frag/_adjust_wps.py:145-153: invalid interval -> skipped
                 stderr.write(f"Invalid interval detected:\n{contig}:{start}-{stop}. This interval will be skipped.\n")
                 continue
-            if rng is None:
+            if run is not None:
+                first, scores = run
+            elif rng is None:
                 stderr.write(f"No entries in range: {contig}:{start}-{stop}. This interval will be skipped.\n")
                 continue
-            starts, _, scores = rng
-            if not np.all(starts[:-1] + 1 == starts[1:]):
-                raise ValueError("BigWig was found to be nonsequential. There may be multiple entries for one "
-                                 "position or gaps in the regions specified in the interval file.")
+            else:
+                starts, _, scores = rng
+                if not np.all(starts[:-1] + 1 == starts[1:]):
+                    raise ValueError("BigWig was found to be nonsequential. There may be multiple entries for one "
+                                     "position or gaps in the regions specified in the interval file.")
+                first = int(starts[0])
             if median_window_size > scores.shape[0]:
                 raise ValueError(f"median_window_size ({median_window_size}) cannot be greater than the length "
                                  f"of interval ({scores.shape[0]}).")
-            seg_vals.append(scores.astype(np.float32)); seg_pos.append(starts); seg_contig.append(contig)
+            seg_vals.append(scores.astype(np.float32)); seg_pos.append((first, scores.shape[0])); seg_contig.append(contig)
     finally:
         raw_wps.close()
 
@@ -95,19 +102,23 @@ def adjust_wps(input_file, interval_file, output_file, chrom_sizes, interval_siz
                                    subtract_edges=subtract_edges, edge_size=edge_size)
         host = out.cpu().numpy()
         h = median_window_size // 2
-        for k, (contig, pos) in enumerate(zip(seg_contig, seg_pos)):
-            outputs.append((contig, pos[h: len(pos) - h], host[off[k]: off[k + 1]]))
+        for k, (contig, (first, _)) in enumerate(zip(seg_contig, seg_pos)):
+            outputs.append((contig, first + h, host[off[k]: off[k + 1]]))
     if verbose:
         stderr.write("Writing to output\n")
     with pbw.open(output_file, "w") as output_bw:
         output_bw.addHeader(chrom_sizes_to_list(chrom_sizes))
-        for contig, starts, values in outputs:
-            if len(starts) == 0:
+        for contig, first, values in outputs:
+            n = len(values)
+            if n == 0:
                 continue
             try:
-                output_bw.addEntries(contig, starts, ends=starts + 1, values=values)
+                # the positions are one checked-contiguous run (see above): the per-base entries of
+                # frag/_adjust_wps.py:275-283 as one fixedStep block - same intervals for every reader, same
+                # bounds / order errors from the writer
+                output_bw.addEntries(contig, first, values=values, span=1, step=1)
             except RuntimeError as e:  # frag/_adjust_wps.py:285-291
                 stderr.write(f"RuntimeError encountered while writing to {output_file} at interval "
-                             f"{contig}:{starts[0]}-{starts[-1] + 1}: {e}\n")
+                             f"{contig}:{first}-{first + n}: {e}\n")
     if verbose:
         stderr.write(f"Adjust-WPS took {time() - start_time} s to run.\n")

@@ -198,10 +198,14 @@ class BigWigWriter:
 
     def _stats(self, vals: np.ndarray, bases: np.ndarray | int) -> None:
         v = vals.astype(np.float64)
-        b = np.broadcast_to(np.asarray(bases, dtype=np.float64), v.shape)
+        self._min = min(self._min, float(vals.min())); self._max = max(self._max, float(vals.max()))
+        if np.ndim(bases) == 0:      # fixed span: two reductions, no weighted temporaries
+            self._n_cov += int(bases) * v.size
+            self._sum += float(bases) * float(v.sum()); self._sumsq += float(bases) * float(np.dot(v, v))
+            return
+        b = np.asarray(bases, dtype=np.float64)
         self._n_cov += int(b.sum())
-        self._min = min(self._min, float(v.min())); self._max = max(self._max, float(v.max()))
-        self._sum += float((v * b).sum()); self._sumsq += float((v * v * b).sum())
+        self._sum += float(np.dot(v, b)); self._sumsq += float(np.dot(v * v, b))
 
     def _emit(self, cid, start, end, step, span, typ, payload: bytes, n_items: int) -> None:
         raw = struct.pack("<IIIIIBBH", cid, start, end, step, span, typ, 0, n_items) + payload
@@ -493,6 +497,39 @@ class BigWigReader:
             return s, en, v
         order = np.argsort(s, kind="stable")
         return s[order], en[order], v[order]
+
+    def per_base_run(self, chrom, start, end):
+        """``(first position, float32 values)`` when the entries overlapping ``[start, end)`` are per-base
+        fixedStep items (span 1, step 1: what ``multi_wps`` writes) forming ONE run without gap or overlap - the
+        same information as ``intervals_arrays`` without building a position per value.  ``None`` when the
+        range holds anything else (nothing, other section types, gaps): the caller then takes the general
+        query.  Invalid bounds raise like ``intervals``."""
+        if chrom not in self._chroms:
+            raise RuntimeError("Invalid interval bounds!")
+        cid, size = self._chroms[chrom]
+        start = 0 if start is None else int(start)
+        end = size if end is None or end == 0 else int(end)
+        if start < 0 or end > size or start >= end:
+            raise RuntimeError("Invalid interval bounds!")
+        e = self._e
+        first, nxt, parts = None, None, []
+        for doff, dsize in self._blocks(cid, start, end):
+            raw = self._section(doff, dsize)
+            bcid, bstart, _, step, span, typ, _, n = struct.unpack_from(e + "IIIIIBBH", raw, 0)
+            if bcid != cid or typ != 3 or step != 1 or span != 1:
+                return None
+            i0, i1 = max(start - bstart, 0), min(end - bstart, n)
+            if i1 <= i0:
+                continue
+            if nxt is not None and bstart + i0 != nxt:
+                return None
+            if first is None:
+                first = bstart + i0
+            nxt = bstart + i1
+            parts.append(np.frombuffer(raw, e + "f4", i1 - i0, 24 + 4 * i0))
+        if first is None:
+            return None
+        return first, (parts[0] if len(parts) == 1 else np.concatenate(parts))
 
     def intervals(self, chrom, start=0, end=0):
         """pyBigWig.intervals: tuple of (start, end, value) overlapping the range, or None."""

@@ -86,6 +86,24 @@ def delfi_windows(frags, ref, win_start, win_stop, blacklist=None, gaps=None, qu
     return torch.from_numpy(np.array(rows, np.int64).reshape(-1, 4))
 
 
+def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, savgol=True, savgol_window_size=21,
+                    savgol_poly_deg=2, subtract_edges=False, edge_size=500, **_):
+    """frag/_adjust_wps.py:119-140 per segment with the reference's own numpy / scipy calls (oracle.adjust_core)."""
+    x = np.asarray(x.cpu() if torch.is_tensor(x) else x, dtype=np.float64)
+    seg = np.asarray(seg_lengths, np.int64)
+    off = np.zeros(len(seg) + 1, np.int64); np.cumsum(seg, out=off[1:])
+    if median_window_size > 0 and np.any(seg < median_window_size):
+        raise ValueError("median_window_size cannot be greater than the length of interval")
+    parts = []
+    for a, b in zip(off[:-1], off[1:]):
+        v = x[a:b].copy()
+        if subtract_edges:
+            v -= np.mean([np.mean(v[:edge_size]), np.mean(v[-edge_size:])])
+        parts.append(O.adjust_core(v, median_window_size, use_mean, savgol, savgol_window_size, savgol_poly_deg))
+    out_off = np.zeros(len(seg) + 1, np.int64); np.cumsum([len(p) for p in parts], out=out_off[1:])
+    return torch.from_numpy(np.concatenate(parts) if parts else np.zeros(0)), out_off
+
+
 def install(monkeypatch, seqs: dict):
     """``seqs``: {contig: ASCII reference sequence (bytes)} for the motif / DELFI wrappers."""
     import finaletoolkit_b200.device as D
@@ -94,5 +112,6 @@ def install(monkeypatch, seqs: dict):
     monkeypatch.setattr(FragmentTable, "device", lambda self, contig, device=None: HostFrags(*self.host(contig)))
     monkeypatch.setattr(ReferenceWrapper, "device_contig", lambda self, contig, device=None: seqs[contig])
     for name, fn in (("interval_hist", interval_hist), ("frag_lengths", frag_lengths), ("end_motif_hist", end_motif_hist),
-                     ("cleavage_intervals", cleavage_intervals), ("delfi_windows", delfi_windows), ("WpsPlan", HostWpsPlan)):
+                     ("cleavage_intervals", cleavage_intervals), ("delfi_windows", delfi_windows), ("WpsPlan", HostWpsPlan),
+                     ("adjust_segments", adjust_segments)):
         monkeypatch.setattr(D, name, fn)

@@ -10,7 +10,7 @@ import host_shim
 import test_gpu_api as A
 from test_gpu_api import fx, syn  # noqa: F401  (fixtures)
 
-_NEEDS_DEVICE = {"test_adjust_wps", "test_multi_wps_streams_large_contigs"}   # adjust kernels / streamed pipeline
+_NEEDS_DEVICE = {"test_multi_wps_streams_large_contigs"}   # the streamed pipeline has no host stand-in
 
 
 @pytest.fixture(autouse=True)
