@@ -104,6 +104,17 @@ def adjust_segments(x, seg_lengths, median_window_size=1000, use_mean=False, sav
     return torch.from_numpy(np.concatenate(parts) if parts else np.zeros(0)), out_off
 
 
+def agg_signal(rows, strand, trim_lo, out_len, device=None):
+    """utils/_agg_bw.py:84-123: the accepted rows added in file order, '-' rows flipped, NaN -> 0, fp64."""
+    out = np.zeros(int(out_len), np.float64)
+    for row, sd in zip(np.asarray(rows, np.float32), strand):
+        if sd == 0:
+            continue
+        v = np.nan_to_num(np.asarray(row, np.float64)[trim_lo: trim_lo + out_len])
+        out = out + (v if sd > 0 else v[::-1])
+    return torch.from_numpy(out)
+
+
 def install(monkeypatch, seqs: dict):
     """``seqs``: {contig: ASCII reference sequence (bytes)} for the motif / DELFI wrappers."""
     import finaletoolkit_b200.device as D
@@ -113,5 +124,5 @@ def install(monkeypatch, seqs: dict):
     monkeypatch.setattr(ReferenceWrapper, "device_contig", lambda self, contig, device=None: seqs[contig])
     for name, fn in (("interval_hist", interval_hist), ("frag_lengths", frag_lengths), ("end_motif_hist", end_motif_hist),
                      ("cleavage_intervals", cleavage_intervals), ("delfi_windows", delfi_windows), ("WpsPlan", HostWpsPlan),
-                     ("adjust_segments", adjust_segments)):
+                     ("adjust_segments", adjust_segments), ("agg_signal", agg_signal)):
         monkeypatch.setattr(D, name, fn)

@@ -36,6 +36,7 @@ for _name in dir(A):
         globals()[_name] = getattr(A, _name)
 del _name
 
-# the API-level bodies of two more GPU test modules: the delfi() table and the cleavage drivers
+# the API-level bodies of three more GPU test modules: the delfi() table, the cleavage drivers, agg_bw
 from test_gpu_cleavage import test_golden_cases_through_the_api  # noqa: E402,F401
 from test_gpu_delfi import test_delfi_api  # noqa: E402,F401
+from test_gpu_agg import test_agg_bw_api_golden  # noqa: E402,F401
