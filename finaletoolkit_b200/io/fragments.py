@@ -238,6 +238,8 @@ class FragmentTable:
         lo, hi = self._bounds(starts, stops)
         order = np.argsort(lo, kind="stable")
         lo, hi = lo[order], hi[order]
+        if np.any(lo[1:] < hi[:-1]):
+            raise ValueError("fetched_union needs pairwise disjoint regions (one group of fetch_groups)")
         r1s, r1e = (self.read1_raw if fetch_only else self.read1)[contig]
         # the regions are disjoint and sorted: the only candidate of a read is the first region ending after its start
         k = np.searchsorted(hi, r1s, side="right")
