@@ -69,6 +69,8 @@ def _inflate_sections(buf: bytes, blocks: list[tuple[int, int]], max_uncomp: int
     n = len(blocks)
     in_off = np.fromiter((b[0] for b in blocks), dtype=np.int64, count=n)
     in_size = np.fromiter((b[1] for b in blocks), dtype=np.int64, count=n)
+    if n and (int(in_off.min()) < 0 or int(in_size.min()) < 0 or int((in_off + in_size).max()) > len(buf)):
+        raise RuntimeError("corrupt bigWig index: a data section lies outside the file")   # never hand C a bad pointer
     out_off = np.arange(n + 1, dtype=np.int64) * int(max_uncomp)
     src = np.frombuffer(buf, dtype=np.uint8)
     dst = np.empty(int(out_off[-1]), dtype=np.uint8)

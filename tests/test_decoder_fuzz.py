@@ -1,5 +1,6 @@
 """Corrupted input must be rejected (or decoded to whatever well-formed records remain), never crash the
-process: the native BAM and BGZF fragment-file decoders on a few hundred mutated copies of the golden files -
+process: the native BAM and BGZF fragment-file decoders and the bigWig reader on a few hundred mutated copies of the
+golden files -
 byte flips, truncation, insertions, hostile values in the BAM record headers (block_size, l_read_name, n_cigar)
 and in the BGZF member headers (XLEN, BSIZE, ISIZE).  Runs in a child process so that a crash is a test failure
 rather than the end of the test session."""
@@ -89,6 +90,33 @@ for it in range(160):
         drain(h, False)
         L.ftk_fragfile_close(h)
     else:
+        rejected += 1
+# bigWig reader: the R-tree / section offsets of a damaged file must never reach the native inflate as bad pointers
+from finaletoolkit_b200.io import bigwig
+bw = dict(np.load(os.path.join(repo, "tests", "golden", "agg.npz")))["ref_test_bw"].tobytes()
+for it in range(150):
+    b = bytearray(bw)
+    k = int(rng.integers(0, 3))
+    if k == 0:
+        for _ in range(int(rng.integers(1, 10))):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+    elif k == 1:
+        b = b[: int(rng.integers(0, len(b)))]
+    else:
+        i = int(rng.integers(0, len(b) - 8))
+        b[i:i + 8] = struct.pack("<q", int(rng.choice([0, -1, 2 ** 40, len(b) + 5, 2 ** 62])))
+    path = os.path.join(d, "x.bw")
+    open(path, "wb").write(bytes(b))
+    try:
+        r = bigwig.open(path)
+        for c in list(r.chroms())[:3]:
+            try:
+                r.values(c, 0, min(int(r.chroms(c) or 1), 5000))
+                r.intervals(c, 0, 0)
+            except Exception:       # a Python exception is a rejection, not a crash
+                pass
+        opened += 1
+    except Exception:
         rejected += 1
 print("fuzz ok", opened, rejected)
 '''
