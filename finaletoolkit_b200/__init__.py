@@ -31,10 +31,17 @@ _EXPORTS = {
     "frags_in_region": ("utils", "frags_in_region"), "get_intervals": ("utils", "get_intervals"),
     "gen_kmers": ("utils", "gen_kmers"), "reverse_complement": ("utils", "reverse_complement"),
     "chrom_sizes_to_dict": ("utils", "chrom_sizes_to_dict"), "chrom_sizes_to_list": ("utils", "chrom_sizes_to_list"),
-    "agg_bw": ("utils", "agg_bw"),
+    "agg_bw": ("utils", "agg_bw"), "overlaps": ("utils", "overlaps"),
+    "GenomeGaps": ("genome", "GenomeGaps"), "ContigGaps": ("genome", "ContigGaps"),
     "ReferenceWrapper": ("io", "ReferenceWrapper"),
+    # the exception hierarchy is part of the flat namespace too (finaletoolkit/__init__.py:30-40)
+    "FinaleToolkitError": ("exceptions", "FinaleToolkitError"), "InvalidInputError": ("exceptions", "InvalidInputError"),
+    "UnsupportedFormatError": ("exceptions", "UnsupportedFormatError"),
+    "MissingReferenceError": ("exceptions", "MissingReferenceError"), "MissingIndexError": ("exceptions", "MissingIndexError"),
+    "ContigNotFoundError": ("exceptions", "ContigNotFoundError"), "ContigMismatchError": ("exceptions", "ContigMismatchError"),
+    "OutOfBoundsError": ("exceptions", "OutOfBoundsError"),
 }
-_ALIASES = {"end_motif": "end_motifs"}
+_ALIASES = {"end_motif": "end_motifs", "breakpoint_motif": "breakpoint_motifs"}
 
 
 def __getattr__(name: str):
@@ -48,3 +55,7 @@ def __getattr__(name: str):
         globals()[name] = value
         return value
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+
+def __dir__():
+    return sorted(set(globals()) | set(_SUBMODULES) | set(_EXPORTS) | set(_ALIASES))

@@ -15,7 +15,7 @@ from ..exceptions import InvalidInputError
 from ..io.fragments import as_table
 
 __all__ = ["chrom_sizes_to_list", "chrom_sizes_to_dict", "get_intervals", "gen_kmers",
-           "reverse_complement", "frag_generator", "frag_array", "frags_in_region"]
+           "reverse_complement", "frag_generator", "frag_array", "frags_in_region", "overlaps"]
 
 
 # utils/_comparison.py:13-31
@@ -59,6 +59,30 @@ def get_intervals(interval_file) -> list[tuple[str, int, int, str]]:
                 continue
             intervals.append((parts[0], int(parts[1]), int(parts[2]), parts[3] if len(parts) > 3 else "."))
     return intervals
+
+
+def overlaps(contigs_1, starts_1, stops_1, contigs_2, starts_2, stops_2) -> np.ndarray:
+    """utils/utils.py:346-383: for every interval of set 1, does it overlap (``start_1 < stop_2`` and
+    ``stop_1 > start_2``) any interval of set 2 on the same contig?  The reference compares all pairs
+    (an n1 x n2 boolean matrix); here set 2 is sorted by start per contig and a running maximum of its stops
+    answers a query with one binary search - same booleans, O((n1 + n2) log n2)."""
+    c1, s1, e1 = np.asarray(contigs_1), np.asarray(starts_1), np.asarray(stops_1)
+    c2, s2, e2 = np.asarray(contigs_2), np.asarray(starts_2), np.asarray(stops_2)
+    out = np.zeros(c1.shape[0], dtype=bool)
+    for contig in np.unique(c2):
+        q = np.flatnonzero(c1 == contig)
+        m = c2 == contig
+        if not q.size:
+            continue
+        order = np.argsort(s2[m], kind="stable")
+        starts, stops = s2[m][order], e2[m][order]
+        # intervals of set 2 starting before the query ends; one of them must end after the query starts
+        k = np.searchsorted(starts, e1[q], side="left")
+        best = np.maximum.accumulate(stops)
+        hit = k > 0
+        hit[hit] = best[k[hit] - 1] > s1[q][hit]
+        out[q] = hit
+    return out
 
 
 def gen_kmers(k: int, bases: str = "ACGT") -> list[str]:

@@ -627,3 +627,33 @@ def test_savgol_rational_coefficients():
             assert sum(Fraction(a + b * i * i, den) for i in range(-h, h + 1)) == 1      # a smoother preserves constants
             if deg >= 2:                                                                   # ... and quadratics
                 assert sum(Fraction(a + b * i * i, den) * i * i for i in range(-h, h + 1)) == 0
+
+
+def test_flat_namespace_and_overlaps():
+    """The reference's flat namespace (finaletoolkit/__init__.py:30-128) for everything on the path: features,
+    containers, exceptions, aliases; ``overlaps`` (utils/utils.py:346-383) against the all-pairs definition."""
+    import finaletoolkit_b200 as F
+    for name in ("wps", "multi_wps", "adjust_wps", "coverage", "single_coverage", "frag_length", "frag_length_bins",
+                 "frag_length_intervals", "end_motifs", "region_end_motifs", "interval_end_motifs", "EndMotifFreqs",
+                 "EndMotifsIntervals", "breakpoint_motifs", "region_breakpoint_motifs", "interval_breakpoint_motifs",
+                 "BreakpointMotifFreqs", "BreakpointMotifsIntervals", "cleavage_profile", "multi_cleavage_profile", "delfi",
+                 "delfi_gc_correct", "delfi_merge_bins", "agg_bw", "frag_generator", "frag_array", "frags_in_region",
+                 "get_intervals", "overlaps", "gen_kmers", "reverse_complement", "chrom_sizes_to_dict",
+                 "chrom_sizes_to_list", "GenomeGaps", "ContigGaps", "ReferenceWrapper", "FinaleToolkitError",
+                 "InvalidInputError", "UnsupportedFormatError", "MissingReferenceError", "MissingIndexError",
+                 "ContigNotFoundError", "ContigMismatchError", "OutOfBoundsError"):
+        assert getattr(F, name) is not None and name in dir(F), name
+    assert F.end_motif is F.end_motifs and F.breakpoint_motif is F.breakpoint_motifs
+    assert issubclass(F.InvalidInputError, F.FinaleToolkitError) and issubclass(F.InvalidInputError, ValueError)
+    assert issubclass(F.MissingIndexError, FileNotFoundError) and issubclass(F.OutOfBoundsError, IndexError)
+    with pytest.raises(AttributeError):
+        F.no_such_feature
+    rng = np.random.default_rng(5)
+    for _ in range(100):
+        n1, n2 = int(rng.integers(0, 30)), int(rng.integers(0, 30))
+        c1, c2 = rng.choice(["a", "b", "c"], n1), rng.choice(["a", "b", "d"], n2)
+        s1 = rng.integers(0, 100, n1); e1 = s1 + rng.integers(0, 20, n1)
+        s2 = rng.integers(0, 100, n2); e2 = s2 + rng.integers(0, 20, n2)
+        exp = (np.any((s1[:, None] < e2[None]) & (e1[:, None] > s2[None]) & (c1[:, None] == c2[None]), axis=1)
+               if n1 and n2 else np.zeros(n1, bool))
+        assert np.array_equal(F.overlaps(c1, s1, e1, c2, s2, e2), exp)
