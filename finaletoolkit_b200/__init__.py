@@ -33,7 +33,8 @@ _EXPORTS = {
     "chrom_sizes_to_dict": ("utils", "chrom_sizes_to_dict"), "chrom_sizes_to_list": ("utils", "chrom_sizes_to_list"),
     "agg_bw": ("utils", "agg_bw"), "overlaps": ("utils", "overlaps"),
     "GenomeGaps": ("genome", "GenomeGaps"), "ContigGaps": ("genome", "ContigGaps"),
-    "ReferenceWrapper": ("io", "ReferenceWrapper"),
+    "ReferenceWrapper": ("io", "ReferenceWrapper"), "AlignmentWrapper": ("io", "AlignmentWrapper"),
+    "Fragment": ("io", "Fragment"),
     # the exception hierarchy is part of the flat namespace too (finaletoolkit/__init__.py:30-40)
     "FinaleToolkitError": ("exceptions", "FinaleToolkitError"), "InvalidInputError": ("exceptions", "InvalidInputError"),
     "UnsupportedFormatError": ("exceptions", "UnsupportedFormatError"),

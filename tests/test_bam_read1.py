@@ -213,3 +213,32 @@ def test_fetch_selection_brute_force(seed):
     assert tab.fetched("c", 60_000, None).n_fragments("c") == int((hi1 > 60_000).sum())
     plain = FragmentTable({"c": (st, sp, np.zeros(n, np.uint8), np.ones(n, np.uint8))})
     assert not plain.has_read1("c") and plain.fetched("c", 5, 10) is plain and not plain.read1_affected("c", [5], [10]).any()
+
+
+def test_alignment_wrapper(bam, tmp_path, manifest, golden):
+    """``AlignmentWrapper.fetch`` (io/alignment.py:218-302) over the columnar table: BAM = the reads an indexed
+    fetch returns (oracle restatement, pinned above), fragment file = the rows a tabix query returns."""
+    import finaletoolkit_b200 as F
+    from helpers import write_text_gz
+    path, g, m = bam
+    raw = g["bam_file"].tobytes()
+    with F.AlignmentWrapper(path, quality_threshold=20) as w:
+        assert w.is_sam and w.chroms == dict(m["refs"])
+        for contig, s, e in [("chrA", 10_000, 12_000), ("chrB", 5_000, 9_000), ("chrB", None, 700), ("chrA", 59_000, None),
+                             ("chrB", None, None), (None, None, None)]:
+            got = sorted(tuple(f) for f in w.fetch(contig, s, e))
+            exp = sorted(tuple(r) for r in O.bam_fetch(raw, contig, s, e) if r[3] >= 20)
+            assert got == exp and (got or contig == "chrB"), (contig, s, e)
+        f = next(w.fetch("chrA", 10_000, 12_000))
+        assert isinstance(f, F.Fragment) and f.length == f.stop - f.start and isinstance(f.is_forward, bool)
+    with pytest.raises(NotImplementedError):
+        F.AlignmentWrapper(path, read1_only=False)
+    fx = manifest["fixture17"]
+    frag = write_text_gz(tmp_path / "a.frag.gz", fx["frag_gz_text"])
+    rows = [ln.split("\t") for ln in fx["frag_gz_text"].splitlines()]
+    with F.AlignmentWrapper(frag, quality_threshold=0) as w:
+        assert not w.is_sam and w.chroms == {"12": None}
+        got = [tuple(f) for f in w.fetch("12", 34443118, 34443538)]
+        exp = [("12", int(r[1]), int(r[2]), int(r[3]), "+" in r[4]) for r in rows if int(r[2]) > 34443118 and int(r[1]) < 34443538]
+        assert got == exp and len(got) > 0
+        assert len(list(w.fetch())) == len(rows) == 17
